@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — particle-updates/s of the 2-D SSM bootstrap filter (BASELINE.json configs[1]).
+
+A "step" is one time step of the filter-only form of examples/2D_ssm.jl over all N particles:
+    x .= x + v ; dv ~ MvNormal([0,0], 0.1 I2) ; v .= v + dv ; o => MvNormal(x, 0.5 I2) ; Resample()
+with ess_perc_min = 1.0, so the stratified resample + gather of all six planes runs every step (the
+setting of the reference's own benchmark, benchmarks/ssm/WeightedSampling/lgssm1d.jl:26-27).
+particle-updates/s = N * steps / time.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--particles N] [--impl reference]
+
+* `value`     device time of the K steps (CUDA events on the library's stream).
+* `e2e`       the same K steps through the public API (wsb200.run of the @model program) with host
+              inputs (the observations) and a device->host read of the step result (log-evidence)
+              inside the timed region, wall clock.
+* `roofline`  the dominant kernel (ancestor gather) against the measured HBM copy bandwidth.
+* `cpu_baseline` / `--impl reference`  the C restatement of the reference's run! (oracle/ws_oracle.c:
+              orc_ssm2d_run) on one host core (the reference is single-threaded: TODO.md:28).  Julia is
+              not available, so this is "kind: port".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SSM2D_FILTER = '''
+@model function ssm2d_filter(obs)
+    I2 = [1.0 0.0; 0.0 1.0]
+    x .= [0.0, 0.0]
+    v .= [1.0, 0.0]
+    for o in obs
+        x .= x + v
+        dv ~ MvNormal([0.0, 0.0], 0.1 * I2)
+        v .= v + dv
+        o => MvNormal(x, 0.5 * I2)
+    end
+end
+'''
+
+P_PLANES = 6
+# algorithmic bytes per particle-update (SURVEY.md §8d, C2 filter-only, Int32 ancestors)
+ALG_BYTES_STEP = 224
+ALG_BYTES_GATHER = 4 + 16 * P_PLANES          # read ancestor + read/write 6 planes
+ALG_BYTES_PASS = 8 * (4 + 6) + 16             # propagate+observe: read x,v; write x,v,dv; logw RMW
+ALG_BYTES_SCAN = 8 + 4                        # read logw, write ancestor
+
+
+def synth_obs(T, seed=42):
+    """examples/2D_ssm.jl:19-28 generative process (SURVEY §8d C2 input)."""
+    rng = np.random.default_rng(seed)
+    x = np.array([0.0, 0.0])
+    v = np.array([1.0, 0.0])
+    obs = []
+    for _ in range(T):
+        obs.append(x + 0.5 * rng.standard_normal(2))
+        x = x + v
+        v = v + 0.1 * rng.standard_normal(2)
+    return obs
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, device_index):
+        super().__init__(daemon=True)
+        self.idx = device_index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.idx)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, val in zip(names, out[2:]):
+                    if val.strip().lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_run(n, steps, seed=1):
+    """The reference's run! restated in C (oracle/ws_oracle.c), one core."""
+    from oracle import cref
+    obs = np.asarray(synth_obs(steps))
+    t0 = time.perf_counter()
+    le, mean, nres = cref.ssm2d_run(n, obs, seed=seed, ess_perc_min=1.0)
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt, le
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_particles
+    # warm-up (page faults, ziggurat tables), then K samples of a bounded run
+    cpu_reference_run(min(n, 200_000), 2)
+    vals = []
+    t_total0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        v, dt, _ = cpu_reference_run(n, args.cpu_steps)
+        vals.append(v)
+    value = float(np.median(vals))
+    ms = 1e3 * n / value
+    line = {
+        "impl": "reference", "metric": "particle_updates_per_sec", "value": value, "unit": "particle-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "ssm2d_filter_only_bootstrap (examples/2D_ssm.jl, x overwritten), ess_perc_min=1.0",
+                   "particles": n, "time_steps_per_sample": args.cpu_steps},
+        "cpu_baseline": {"value": value, "unit": "particle-updates/s", "cores": 1, "kind": "port",
+                         "sample": f"{n} particles x {args.cpu_steps} steps, C restatement of run! (oracle/ws_oracle.c), "
+                                   f"median of {len(vals)} runs; Julia unavailable"},
+        "e2e": {"value": value, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_total0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--particles", type=int, default=100_000_000)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-particles", type=int, default=2_000_000)
+    ap.add_argument("--cpu-steps", type=int, default=40)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import wsb200 as ws
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: wsb200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    N = args.particles
+    K, W = args.steps, args.warmup
+    obs = synth_obs(W + K)
+    build = ws.model(SSM2D_FILTER)
+
+    state = ws.SMCState(N, ess_perc_min=1.0, seed=1234 + rank, device=local_rank)
+    st = state.store
+    import ctypes as C
+    sp = C.c_void_p()
+    st._call("ws_stream", C.byref(sp))
+    stream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", local_rank))
+
+    # warm-up: initial assigns + W steps (also creates the columns)
+    ws.run(build(obs[:W]), state)
+    state.sync()
+    le0 = ws.log_evidence(state)
+
+    # the timed region continues the same filter with the next K observations (run! on an existing
+    # state, as benchmarks/ssm/bench_single_update does).  The continuation model has no initial
+    # assigns.
+    cont = ws.model('''
+    @model function ssm2d_continue(obs)
+        I2 = [1.0 0.0; 0.0 1.0]
+        for o in obs
+            x .= x + v
+            dv ~ MvNormal([0.0, 0.0], 0.1 * I2)
+            v .= v + dv
+            o => MvNormal(x, 0.5 * I2)
+        end
+    end
+    ''', particle_vars=("x", "v", "dv"))
+
+    st._call("ws_set_timing", 1)
+    st._call("ws_reset_kernel_times")
+    stats0 = state.stats()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record(stream)
+    ws.run(cont(obs[W:W + K]), state)
+    le = ws.log_evidence(state)          # device -> host read of the step result
+    ev1.record(stream)
+    state.sync()
+    t1 = time.perf_counter()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    wall_ms = (t1 - t0) * 1e3
+    clocks = sampler.stop()
+    stats1 = state.stats()
+    kt = state.kernel_times()
+
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(t[0]), float(t[1])
+
+    total_updates = float(N) * K * world
+    value = total_updates / (dev_ms * 1e-3)
+    e2e = total_updates / (wall_ms * 1e-3)
+    launches = stats1["kernel_launches"] - stats0["kernel_launches"]
+
+    peak, peak_src = measured_peaks()
+    per_kernel = {}
+    for name, alg in (("gather", ALG_BYTES_GATHER), ("fused_pass", ALG_BYTES_PASS), ("scan_search", ALG_BYTES_SCAN)):
+        k = kt[name]
+        if k["launches"] > 0 and k["ms"] > 0:
+            avg_ms = k["ms"] / k["launches"]
+            gbs = alg * N / (avg_ms * 1e-3) / 1e9
+            per_kernel[name] = {"avg_ms": avg_ms, "launches": k["launches"], "alg_bytes_per_particle": alg,
+                                "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": k["ms"] / dev_ms}
+    dom = max(per_kernel, key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["launches"]) if per_kernel else None
+    roofline = None
+    if dom:
+        roofline = {"bound": "hbm", "kernel": {"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",
+                                                "scan_search": "ws_scan_search_kernel"}[dom],
+                    "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "per_kernel": per_kernel,
+                    "whole_step": {"alg_bytes_per_particle": ALG_BYTES_STEP,
+                                   "achieved_gbs": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9,
+                                   "frac": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9 / peak}}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline:
+            cpu_reference_run(200_000, 2)
+            v, dt, _ = cpu_reference_run(args.cpu_particles, args.cpu_steps)
+            cpu = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port",
+                   "sample": f"{args.cpu_particles} particles x {args.cpu_steps} steps of the same model, C restatement of "
+                             f"the reference's run! (oracle/ws_oracle.c), {dt:.1f} s; Julia unavailable in the image"}
+        line = {
+            "metric": "particle_updates_per_sec", "value": value, "unit": "particle-updates/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ssm2d_filter_only_bootstrap (BASELINE configs[1]: examples/2D_ssm.jl with x overwritten), "
+                                   "ess_perc_min=1.0 (resample + 6-plane gather every step)",
+                       "particles_per_gpu": N, "planes": P_PLANES, "resampler": "stratified",
+                       "parallelism": "single GPU" if world == 1 else f"{world} independent shards (island filters, local resampling; "
+                                                                       "global NCCL exchange not built yet)",
+                       "l2": "working set 10.4 GB per GPU >> 126 MB L2 (no flush needed)",
+                       "log_evidence": le, "log_evidence_after_warmup": le0},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 16,
+                    "d2h_bytes_per_step": int((stats1["d2h_bytes"] - stats0["d2h_bytes"]) / max(1, K))},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "fusion": {"fused_passes": stats1["fused_passes"] - stats0["fused_passes"],
+                       "fused_statements": stats1["fused_statements"] - stats0["fused_statements"],
+                       "resamples": stats1["resamples_done"] - stats0["resamples_done"]},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""Generates tests/golden/*.npz from the oracle (oracle/ref.py) on fixed seeds.
+
+The reference is Julia and cannot run here, so these are NOT reference outputs: they freeze the
+oracle's answers (so that a later edit of the oracle or of the product is visible) and give the GPU
+tests size-independent fixtures.  Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+import wsb200 as ws  # noqa: E402  (only the host-side model front-end is used: no device needed)
+from oracle import ref  # noqa: E402
+import models  # noqa: E402
+
+
+def resampling_case():
+    rng = np.random.default_rng(2024)
+    n = 4096
+    logw = 2.0 * rng.standard_normal(n) - 50.0
+    r = rng.random(n)
+    w = ref.exp_norm(logw)
+    return dict(logw=logw, r=r, w=w, lse=ref.logsumexp(logw), ess=ref.ess_perc(w), us=ref.stratified_us(r),
+                ancestors=ref.icdf(w, ref.stratified_us(r)), ancestors_sys=ref.icdf(w, ref.systematic_us(r[0], n)))
+
+
+def run_case(src, args, n, n_normals, n_uniforms, n_expon=0, ess=0.5, seed=1):
+    rng = np.random.default_rng(seed)
+    normals, uniforms = rng.standard_normal(n_normals), rng.random(n_uniforms)
+    expon = rng.standard_exponential(n_expon)
+    root = ws.model(src)(*args)
+    st = ref.OracleState(n, ref.Streams(normals, uniforms, expon), ess_perc_min=ess)
+    ref.run(root, st)
+    out = dict(normals=normals, uniforms=uniforms, exponentials=expon, weights=st.weights,
+               log_evidence=ref.log_evidence(st), n_resampled=sum(e["resampled"] for e in st.log), depth=st.depth)
+    for name in st.names:
+        out["col_" + name] = st.cols[name]
+    return out
+
+
+def main():
+    np.savez_compressed(os.path.join(HERE, "resampling.npz"), **resampling_case())
+    rng = np.random.default_rng(7)
+    obs1 = np.cumsum(rng.standard_normal(12)) * 1.5
+    np.savez_compressed(os.path.join(HERE, "ssm1d.npz"), obs=obs1,
+                        **run_case(models.SSM1D, (list(obs1),), 256, 256 * 12, 256 * 12))
+    obs2 = rng.standard_normal((8, 2)) + np.arange(8)[:, None] * np.array([1.0, 0.0])
+    np.savez_compressed(os.path.join(HERE, "ssm2d.npz"), obs=obs2,
+                        **run_case(models.SSM2D, ([o for o in obs2],), 256, 256 * 2 * 8, 256 * 8))
+    xs = rng.uniform(0, 10, 8)
+    ys = 1.0 - 0.5 * xs + 0.5 * rng.standard_normal(8)
+    np.savez_compressed(os.path.join(HERE, "linreg.npz"), xs=xs, ys=ys,
+                        **run_case(models.LINREG, (xs, ys), 512, 512 * (2 + 16), 512 * 24))
+    np.savez_compressed(os.path.join(HERE, "schools.npz"),
+                        **run_case(models.SCHOOLS, (8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA), 512, 512 * 25, 512 * 24, 512))
+    print("golden fixtures written")
+
+
+if __name__ == "__main__":
+    main()

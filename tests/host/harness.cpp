@@ -1,0 +1,219 @@
+// tests/host/harness.cpp — CPU test harness for the statement lowering (TEST INFRASTRUCTURE ONLY).
+//
+// It runs the SAME lowering (csrc/ws_lowering.h) and the SAME micro-op interpreter
+// (csrc/ws_vm.cuh, host instantiation) that the CUDA runtime uses, over host arrays, so that
+// `pytest -m "not gpu"` can check register allocation, op fusion, replay indexing and the score tape
+// against the oracle without a GPU.  It is never part of the shipped library: libwsb200.so has no
+// CPU path.
+#include <stdint.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../weightedsampling.jl_b200/csrc/ws_lowering.h"
+
+using wsl::Plane;
+using wsl::Program;
+
+struct HH {
+    int64_t n;
+    std::vector<std::vector<std::vector<double>>> cols;  // [col][comp][i]
+    std::vector<double> logw;
+    Program win, score;
+    uint64_t next_stream = 1, seed = 0;
+    int64_t cur_n = 0, cur_u = 0, cur_e = 0;
+    std::vector<double> rn, ru, re;
+    std::vector<int32_t> tape_end;
+    int n_flush = 0;
+    std::string err;
+};
+
+static void reset_win(HH* h) {
+    h->win = Program();
+    h->win.max_regs = 64;
+    h->win.max_ops = 96;
+    h->win.max_io = 24;
+}
+
+extern "C" {
+
+HH* hh_new(int64_t n, uint64_t seed) {
+    HH* h = new HH();
+    h->n = n;
+    h->seed = seed;
+    h->logw.assign((size_t)n, 0.0);
+    reset_win(h);
+    h->score = Program();
+    h->score.score_mode = true;
+    h->score.n_temp_slots = 12;
+    h->score.max_regs = 200;
+    h->score.max_ops = 1 << 30;
+    h->score.max_io = 1 << 30;
+    return h;
+}
+void hh_free(HH* h) { delete h; }
+const char* hh_error(HH* h) { return h->err.c_str(); }
+int hh_col(HH* h, int width) {
+    h->cols.push_back(std::vector<std::vector<double>>(width, std::vector<double>((size_t)h->n, 0.0)));
+    return (int)h->cols.size() - 1;
+}
+void hh_set_plane(HH* h, int col, int comp, const double* v) { memcpy(h->cols[col][comp].data(), v, sizeof(double) * h->n); }
+void hh_set_replay(HH* h, const double* n, int64_t nn, const double* u, int64_t nu, const double* e, int64_t ne) {
+    h->rn.assign(n, n + nn);
+    h->ru.assign(u, u + nu);
+    h->re.assign(e, e + ne);
+}
+
+static void run_program(HH* h, Program& p, std::vector<double>* acc_out, int n_ops) {
+    WsRng rng;
+    rng.seed = h->seed;
+    rng.replay_n = h->rn.empty() ? nullptr : h->rn.data();
+    rng.replay_u = h->ru.empty() ? nullptr : h->ru.data();
+    rng.replay_e = h->re.empty() ? nullptr : h->re.data();
+    std::vector<double> R((size_t)std::max(1, p.high_water));
+    for (int64_t i = 0; i < h->n; ++i) {
+        for (auto& ld : p.loads) R[ld.second] = h->cols[ld.first.col][ld.first.comp][(size_t)i];
+        double acc = 0.0;
+        for (int pc = 0; pc < n_ops; ++pc) ws_vm_exec<1>(p.ops[pc], R.data(), acc, rng, (uint64_t)i);
+        for (auto& d : p.dirty) h->cols[d.col][d.comp][(size_t)i] = R[p.plane_reg[d]];
+        if (acc_out) (*acc_out)[(size_t)i] = acc;
+    }
+}
+
+int hh_flush(HH* h) {
+    if (h->win.ops.empty() && h->win.dirty.empty()) return 0;
+    if (h->win.overflow) {
+        h->err = "window overflow";
+        return -5;
+    }
+    std::vector<double> acc((size_t)h->n, 0.0);
+    run_program(h, h->win, &acc, (int)h->win.ops.size());
+    if (h->win.has_acc)
+        for (int64_t i = 0; i < h->n; ++i) h->logw[(size_t)i] += acc[(size_t)i];
+    h->n_flush++;
+    reset_win(h);
+    return 0;
+}
+int hh_n_flush(HH* h) { return h->n_flush; }
+int hh_window_ops(HH* h) { return (int)h->win.ops.size(); }
+int hh_window_regs(HH* h) { return h->win.high_water; }
+int hh_window_loads(HH* h) { return (int)h->win.loads.size(); }
+int hh_window_stores(HH* h) { return (int)h->win.dirty.size(); }
+
+static wsl::RngCursor cursor(HH* h) { return wsl::RngCursor{&h->next_stream, &h->cur_n, &h->cur_u, &h->cur_e, h->n}; }
+static int finish(HH* h, Program& p) {
+    if (!p.error.empty()) {
+        h->err = p.error;
+        return -1;
+    }
+    p.end_statement();
+    return 0;
+}
+static void tape(HH* h) {
+    h->score.end_statement();
+    h->tape_end.push_back((int32_t)h->score.ops.size());
+}
+
+int hh_assign(HH* h, int col, int comp, const ws_expr* rhs) {
+    wsl::stmt_assign(h->win, Plane{col, comp}, *rhs);
+    return finish(h, h->win);
+}
+int hh_assign_vec(HH* h, int col, int d, const ws_expr* rhs) {
+    wsl::stmt_assign_vec(h->win, col, d, rhs);
+    return finish(h, h->win);
+}
+int hh_sample_normal(HH* h, int col, int comp, const ws_expr* mu, const ws_expr* sigma) {
+    wsl::RngCursor rc = cursor(h);
+    wsl::stmt_sample_normal(h->win, rc, Plane{col, comp}, *mu, *sigma);
+    wsl::score_sample_normal(h->score, Plane{col, comp}, *mu, *sigma);
+    tape(h);
+    return finish(h, h->win);
+}
+int hh_sample_exponential(HH* h, int col, int comp, const ws_expr* theta) {
+    wsl::RngCursor rc = cursor(h);
+    wsl::stmt_sample_exponential(h->win, rc, Plane{col, comp}, *theta);
+    wsl::score_sample_exponential(h->score, Plane{col, comp}, *theta);
+    tape(h);
+    return finish(h, h->win);
+}
+int hh_sample_mvnormal(HH* h, int col, int d, const ws_expr* mu, const double* cov) {
+    std::vector<double> L, Linv;
+    double c0;
+    if (!wsl::mvnormal_factors(d, cov, L, Linv, c0)) return -7;
+    wsl::RngCursor rc = cursor(h);
+    wsl::stmt_sample_mvnormal(h->win, rc, col, d, mu, L);
+    wsl::score_sample_mvnormal(h->score, col, d, mu, Linv, c0);
+    tape(h);
+    return finish(h, h->win);
+}
+int hh_observe_normal(HH* h, const ws_expr* obs, const ws_expr* mu, const ws_expr* sigma) {
+    wsl::stmt_observe_normal(h->win, *obs, *mu, *sigma);
+    wsl::stmt_observe_normal(h->score, *obs, *mu, *sigma);
+    tape(h);
+    return finish(h, h->win);
+}
+int hh_observe_exponential(HH* h, const ws_expr* obs, const ws_expr* theta) {
+    wsl::stmt_observe_exponential(h->win, *obs, *theta);
+    wsl::stmt_observe_exponential(h->score, *obs, *theta);
+    tape(h);
+    return finish(h, h->win);
+}
+int hh_observe_mvnormal(HH* h, int d, const ws_expr* obs, const ws_expr* mu, const double* cov) {
+    std::vector<double> L, Linv;
+    double c0;
+    if (!wsl::mvnormal_factors(d, cov, L, Linv, c0)) return -7;
+    wsl::stmt_observe_mvnormal(h->win, d, obs, mu, Linv, c0);
+    wsl::stmt_observe_mvnormal(h->score, d, obs, mu, Linv, c0);
+    tape(h);
+    return finish(h, h->win);
+}
+int hh_weight_expr(HH* h, const ws_expr* term) {
+    wsl::stmt_weight_expr(h->win, *term);
+    wsl::stmt_weight_expr(h->score, *term);
+    tape(h);
+    return finish(h, h->win);
+}
+int hh_importance_normal(HH* h, int col, int comp, double pm, double ps, double tm, double ts) {
+    wsl::RngCursor rc = cursor(h);
+    wsl::stmt_importance_normal(h->win, rc, Plane{col, comp}, pm, ps, tm, ts);
+    return finish(h, h->win);
+}
+void hh_get_plane(HH* h, int col, int comp, double* out) {
+    hh_flush(h);
+    memcpy(out, h->cols[col][comp].data(), sizeof(double) * h->n);
+}
+void hh_get_logw(HH* h, double* out) {
+    hh_flush(h);
+    memcpy(out, h->logw.data(), sizeof(double) * h->n);
+}
+int hh_tape_len(HH* h) { return (int)h->tape_end.size(); }
+// fold the first n_entries tape entries at the current column values
+int hh_score(HH* h, int n_entries, double* out) {
+    hh_flush(h);
+    if (h->score.overflow) return -5;
+    if (n_entries > (int)h->tape_end.size()) return -1;
+    const int n_ops = n_entries <= 0 ? 0 : h->tape_end[(size_t)n_entries - 1];
+    std::vector<double> acc((size_t)h->n, 0.0);
+    Program& p = h->score;
+    std::vector<Plane> saved_dirty = p.dirty;
+    run_program(h, p, &acc, n_ops);
+    memcpy(out, acc.data(), sizeof(double) * h->n);
+    return 0;
+}
+// Philox / Box-Muller / slot-count building blocks of ws_math.cuh
+void hh_randn2(uint64_t particle, uint64_t stream, uint64_t seed, double* out2) { ws_randn2(particle, stream, seed, out2[0], out2[1]); }
+void hh_philox(uint64_t particle, uint64_t stream, uint64_t seed, uint32_t* out4) {
+    ws_u32x4 r = ws_philox4x32_10(particle, stream, seed);
+    out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+// F(C) for every C in cs against the stratified grid built from r (replay)
+struct RArr {
+    const double* r;
+    double operator()(int64_t k) const { return r[k]; }
+};
+void hh_count_slots_le(const double* cs, int64_t n_c, const double* r, int64_t n, int64_t* out) {
+    RArr ra{r};
+    const double inv_n = 1.0 / (double)n;
+    for (int64_t i = 0; i < n_c; ++i) out[i] = ws_count_slots_le(cs[i], n, inv_n, ra);
+}
+}  // extern "C"

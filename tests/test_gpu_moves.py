@@ -1,0 +1,261 @@
+"""GPU parity tests for the score tape and the MH moves (ports of test/score_test.jl, test/move_test.jl,
+test/move_macro_test.jl; replayed streams must reproduce the oracle's accept decisions exactly)."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+
+def test_score_logpdf_depth_cutoff(ws):
+    """test/score_test.jl:20-54: theta ~ N(0,1); x .= theta; 1.5 => N(x, 0.5)."""
+    n = 1000
+    root = ws.Sequence(ws.Sample("θ", "Normal", (0.0, 1.0)), ws.Assign("x", ws.col("θ")),
+                       ws.Observe(1.5, "Normal", (ws.col("x"), 0.5)))
+    st = ws.SMCState(n, seed=42, device=0)
+    ws.run(root, st)
+    th, x = st["θ"], st["x"]
+    np.testing.assert_array_equal(th, x)
+    e1 = ref.normal_logpdf(th, 0.0, 1.0)
+    e3 = e1 + ref.normal_logpdf(1.5, x, 0.5)
+    assert np.all(ws.score_logpdf(st, ["θ"], 0) == 0.0)
+    np.testing.assert_allclose(ws.score_logpdf(st, ["θ"], 1), e1, rtol=1e-12)
+    np.testing.assert_allclose(ws.score_logpdf(st, ["θ"], 2), e1, rtol=1e-12)
+    np.testing.assert_allclose(ws.score_logpdf(st, ["θ"], 3), e3, rtol=1e-12)
+    np.testing.assert_allclose(st.weights, ref.normal_logpdf(1.5, x, 0.5), rtol=1e-12)
+
+
+def _static_model(ws, y, tau0=1.0, sigma=1.0, extra=None):
+    steps = [ws.Sample("θ", "Normal", (0.0, tau0))] + [ws.Observe(float(v), "Normal", (ws.col("θ"), sigma)) for v in y]
+    if extra is not None:
+        steps.append(extra)
+    return ws.Sequence(*steps)
+
+
+def test_move_cancellation_and_replay_exactness(ws):
+    """test/move_test.jl:23-58: a target-independent factor does not change accept decisions; and with
+    replayed streams the device move equals the oracle's move."""
+    T, n, step = 3, 1000, 0.3
+    rng = np.random.default_rng(1)
+    y = rng.standard_normal(T)
+    th0 = rng.standard_normal(n)
+    normals, uniforms = rng.standard_normal(n), rng.random(n)
+    out = []
+    for with_extra in (False, True):
+        extra = ws.Observe(0.7, "Normal", (0.0, 1.0)) if with_extra else None
+        root = _static_model(ws, y, extra=extra)
+        st = ws.SMCState(n, device=0)
+        st.store.setcol("θ", th0)
+        st.root = root
+        st.depth = T + 1 + int(with_extra)
+        st.set_replay(normals=normals, uniforms=uniforms)
+        mv = ws.Move(["θ"], ws.RW, (step,))
+        mv.apply(st)
+        ost = ref.OracleState(n, ref.Streams(normals, uniforms))
+        ost.setcol("θ", th0)
+        ost.root, ost.depth = root, T + 1 + int(with_extra)
+        ref.apply_move(mv, ost)
+        np.testing.assert_array_equal(st["θ"], ost.cols["θ"])  # proposals are bit-exact, decisions identical
+        assert mv.last.ran == 1 and mv.last.n_accepted == int(ost.last_accept.sum())
+        assert 0.2 * n < mv.last.n_accepted < n
+        out.append(st["θ"])
+    np.testing.assert_allclose(out[0], out[1], atol=1e-9)
+
+
+@pytest.mark.parametrize("proposal,args", [
+    ("RW", (0.25,)), ("RW", (0.25, (0.0, math.inf))), ("RW", (0.4, (-1.0, 6.0))), ("autoRW", ()),
+    ("autoRW", (1e-3, (0.0, math.inf))), ("autoRW", (1e-3, (-math.inf, 9.0))),
+])
+def test_move_replay_vs_oracle_bounds(ws, proposal, args):
+    n = 4000
+    rng = np.random.default_rng(3)
+    tau0 = np.abs(rng.standard_normal(n)) + 0.2
+    y = [0.8, 1.4, 2.2]
+    root = ws.Sequence(ws.Sample("τ", "Exponential", (5.0,)),
+                       *[ws.Observe(v, "Normal", (0.5 * ws.col("τ"), ws.col("τ"))) for v in y])
+    lw = 0.3 * rng.standard_normal(n)  # non-uniform weights: exercises the weighted covariance of autoRW
+    normals, uniforms = rng.standard_normal(n), rng.random(n)
+    st = ws.SMCState(n, device=0)
+    st.store.setcol("τ", tau0)
+    st.weights = lw
+    st.root, st.depth = root, 4
+    st.set_replay(normals=normals, uniforms=uniforms)
+    mv = ws.Move(["τ"], proposal, args)
+    mv.apply(st)
+    ost = ref.OracleState(n, ref.Streams(normals, uniforms))
+    ost.setcol("τ", tau0)
+    ost.weights = lw.copy()
+    ost.root, ost.depth = root, 4
+    ref.apply_move(mv, ost)
+    a, b = st["τ"], ost.cols["τ"]
+    bad = np.abs(a - b) > 1e-9 * (1 + np.abs(b))
+    assert bad.sum() <= 1, f"{bad.sum()} particles differ"
+    assert abs(mv.last.n_accepted - int(ost.last_accept.sum())) <= 1
+    np.testing.assert_array_equal(st.weights, lw)  # a move never touches the weights
+
+
+def test_joint_move_two_targets_replay(ws):
+    n = 3000
+    rng = np.random.default_rng(8)
+    xs, ys = rng.uniform(0, 10, 6), rng.standard_normal(6)
+    root = ws.Sequence(ws.Sample("α", "Normal", (0.0, 10.0)), ws.Sample("β", "Normal", (0.0, 10.0)),
+                       *[ws.Observe(float(y), "Normal", (ws.col("α") + ws.col("β") * float(x), 1.0)) for x, y in zip(xs, ys)])
+    a0, b0 = rng.standard_normal(n), 0.1 * rng.standard_normal(n) + 0.5 * rng.standard_normal(n)
+    for proposal, args, nn in (("autoRW", (), 2 * n), ("RW", (0.05,), 2 * n)):
+        normals, uniforms = rng.standard_normal(nn), rng.random(n)
+        st = ws.SMCState(n, device=0)
+        st.store.setcol("α", a0)
+        st.store.setcol("β", b0)
+        st.root, st.depth = root, 8
+        st.set_replay(normals=normals, uniforms=uniforms)
+        mv = ws.Move(["α", "β"], proposal, args)
+        mv.apply(st)
+        ost = ref.OracleState(n, ref.Streams(normals, uniforms))
+        ost.setcol("α", a0)
+        ost.setcol("β", b0)
+        ost.root, ost.depth = root, 8
+        ref.apply_move(mv, ost)
+        for c in ("α", "β"):
+            bad = np.abs(st[c] - ost.cols[c]) > 1e-9 * (1 + np.abs(ost.cols[c]))
+            assert bad.sum() <= 1, (proposal, c, int(bad.sum()))
+
+
+def test_move_invariance_native_rng(ws):
+    """test/move_test.jl:69-98: RW sweeps leave the exact Normal-Normal posterior invariant."""
+    T, tau0, sigma, n = 5, 2.0, 1.0, 200_000
+    rng = np.random.default_rng(42)
+    y = rng.standard_normal(T) * sigma + 1.3
+    post_var = 1.0 / (1.0 / tau0 ** 2 + T / sigma ** 2)
+    post_mean = post_var * y.sum() / sigma ** 2
+    st = ws.SMCState(n, seed=9, device=0)
+    st.store.setcol("θ", rng.standard_normal(n) * math.sqrt(post_var) + post_mean)
+    st.root, st.depth = _static_model(ws, y, tau0, sigma), T + 1
+    mv = ws.Move(["θ"], ws.RW, (0.3,))
+    for _ in range(20):
+        mv.apply(st)
+    th = st["θ"]
+    assert abs(th.mean() - post_mean) < 0.01 and abs(th.var() - post_var) < 0.01
+    assert 0.5 * n < mv.last.n_accepted < 0.95 * n
+
+
+def test_diversity_gating(ws):
+    """test/move_test.jl:116-209."""
+    n = 50_000
+    rng = np.random.default_rng(3)
+    th0 = rng.standard_normal(n)
+    st = ws.SMCState(n, seed=2, device=0)
+    st.store.setcol("θ", th0)
+    mv = ws.Move(["θ"], ws.RW, (0.3,), 0.99)
+    mv.apply(st)                                     # fully diverse: exact no-op, no root needed
+    assert mv.last.ran == 0 and mv.last.diversity == 1.0
+    np.testing.assert_array_equal(st["θ"], th0)
+    # collapsed particles: runs until the gate is satisfied, then stops
+    T, y = 5, rng.standard_normal(5) + 1.3
+    st.store.setcol("θ", np.full(n, 0.7))
+    st.root, st.depth = _static_model(ws, y, 2.0, 1.0), T + 1
+    mv = ws.Move(["θ"], ws.RW, (0.3,), 0.9)
+    assert abs(ws.marginal_diversity(st.store, ["θ"]) - 1.0 / n) < 1e-15
+    ran = 0
+    for _ in range(100):
+        mv.apply(st)
+        ran += mv.last.ran
+    assert 0 < ran < 100
+    assert ws.marginal_diversity(st.store, ["θ"]) >= 0.9
+    snap = st["θ"]
+    for _ in range(5):
+        mv.apply(st)
+    np.testing.assert_array_equal(st["θ"], snap)
+    # marginal, not joint (move_test.jl:196-209); NaNs count once, -0.0 != 0.0 (isequal)
+    a = np.repeat(np.arange(1.0, 6.0), n // 5)
+    st.store.setcol("α", a)
+    st.store.setcol("β", np.arange(1.0, n + 1.0))
+    assert abs(ws.marginal_diversity(st.store, ["α", "β"]) - 5.0 / n) < 1e-15
+    z = np.arange(n, dtype=float)
+    z[:10] = np.nan
+    z[10], z[11] = 0.0, -0.0
+    st.store.setcol("z", z)
+    assert abs(ws.marginal_diversity(st.store, ["z"]) - ref.marginal_diversity_bits(z)) < 1e-15
+
+
+LINREG = '''
+@model function linear_regression(xs, ys)
+    α ~ Normal(0.0, 10.0)
+    β ~ Normal(0.0, 10.0)
+    for (x, y) in zip(xs, ys)
+        y => Normal(α + β * x, 1.0)
+        if resampled
+            α << autoRW()
+            β << autoRW()
+        end
+    end
+end
+'''
+
+
+def test_c3_linear_regression_replay_and_recovery(ws):
+    """BASELINE configs[2] shape at small N: replay parity with the oracle, then posterior recovery
+    (test/move_macro_test.jl:26-61) with native RNG."""
+    n, npts = 2000, 12
+    rng = np.random.default_rng(42)
+    xs = rng.uniform(0, 10, npts)
+    ys = 1.0 - 0.5 * xs + 0.5 * rng.standard_normal(npts)
+    root = ws.model(LINREG)(xs, ys)
+    normals, uniforms = rng.standard_normal(n * (2 + 2 * npts)), rng.random(n * 3 * npts)
+    state = ws.SMCState(n, ess_perc_min=0.5, device=0)
+    state.set_replay(normals=normals, uniforms=uniforms)
+    ws.run(root, state)
+    ost = ref.OracleState(n, ref.Streams(normals, uniforms), ess_perc_min=0.5)
+    ref.run(root, ost)
+    assert sum(e["resampled"] for e in ost.log) >= 3 and state.stats()["moves_run"] >= 6
+    for c in ("α", "β"):
+        bad = np.abs(state[c] - ost.cols[c]) > 1e-8 * (1 + np.abs(ost.cols[c]))
+        assert bad.sum() <= 2, (c, int(bad.sum()))
+    assert abs(ws.log_evidence(state) - ref.log_evidence(ost)) < 1e-8 * abs(ref.log_evidence(ost))
+    # native RNG recovery
+    npts = 60
+    xs = rng.uniform(0, 10, npts)
+    ys = -1.0 + 2.0 * xs + rng.standard_normal(npts)
+    st2 = ws.SMCState(20_000, seed=4, device=0)
+    ws.run(ws.model(LINREG)(xs, ys), st2)
+    assert abs(ws.E(lambda α: α, st2) + 1.0) < 0.3 and abs(ws.E(lambda β: β, st2) - 2.0) < 0.1
+
+
+SCHOOLS = '''
+@model function eight_schools(J, y, σ)
+    μ ~ Normal(0.0, 5.0)
+    τ ~ Exponential(5.0)
+    θ .= zeros(J)
+    for j in 1:J
+        θ[j] ~ Normal(μ, τ)
+        y[j] => Normal(θ[j], σ[j])
+        μ << autoRW(; diversity=0.9)
+        τ << autoRW(1e-3, (0.0, Inf); diversity=0.9)
+    end
+end
+'''
+
+
+def test_c4_eight_schools_replay(ws):
+    """BASELINE configs[3] at small N (examples/eight_schools.jl:7-21), replayed against the oracle."""
+    n, J = 3000, 8
+    y = [28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0]
+    sg = [15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0]
+    rng = np.random.default_rng(42)
+    root = ws.model(SCHOOLS)(J, y, sg)
+    normals, uniforms = rng.standard_normal(n * (1 + J + 2 * J)), rng.random(n * 3 * J)
+    expon = rng.standard_exponential(n)
+    state = ws.SMCState(n, ess_perc_min=0.5, device=0)
+    state.set_replay(normals=normals, uniforms=uniforms, exponentials=expon)
+    ws.run(root, state)
+    ost = ref.OracleState(n, ref.Streams(normals, uniforms, expon), ess_perc_min=0.5)
+    ref.run(root, ost)
+    assert state["θ"].shape == (n, J)
+    for c in ("μ", "τ", "θ"):
+        a, b = state[c], ost.cols[c]
+        bad = (np.abs(a - b) > 1e-8 * (1 + np.abs(b))).reshape(n, -1).any(axis=1)
+        assert bad.sum() <= 3, (c, int(bad.sum()))
+    assert np.all(state["τ"] > 0)
+    assert abs(ws.log_evidence(state) - ref.log_evidence(ost)) < 1e-8 * abs(ref.log_evidence(ost))

@@ -1,0 +1,173 @@
+"""Pins the oracle (oracle/ref.py, oracle/ws_oracle.c) — CPU only.
+
+The reference ships no golden vectors for this path, so the oracle is pinned by
+(i) the closed forms the reference's own tests assert, (ii) scipy.stats for the third-party
+Distributions.jl formulas, (iii) the committed fixtures of tests/golden/."""
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.stats as sst
+
+import models
+from oracle import cref, ref
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_logpdfs_match_scipy():
+    rng = np.random.default_rng(0)
+    x, mu, sg = rng.normal(size=200), rng.normal(size=200), rng.uniform(0.1, 3, 200)
+    np.testing.assert_allclose(ref.normal_logpdf(x, mu, sg), sst.norm.logpdf(x, mu, sg), rtol=1e-12, atol=1e-13)
+    th = rng.uniform(0.2, 5, 200)
+    xe = rng.exponential(2.0, 200)
+    np.testing.assert_allclose(ref.exponential_logpdf(xe, th), sst.expon.logpdf(xe, scale=th), rtol=1e-12, atol=1e-13)
+    assert ref.exponential_logpdf(-1.0, 2.0) == -np.inf
+    cov = np.array([[2.0, 0.6], [0.6, 1.0]])
+    xv, mv = rng.normal(size=(50, 2)), rng.normal(size=(50, 2))
+    want = [sst.multivariate_normal.logpdf(a, b, cov) for a, b in zip(xv, mv)]
+    np.testing.assert_allclose(ref.mvnormal_logpdf(xv, mv, cov), want, rtol=1e-12)
+    # sigma == 0 special case of StatsFuns.normlogpdf
+    assert ref.normal_logpdf(1.0, 1.0, 0.0) == np.inf and ref.normal_logpdf(1.0, 2.0, 0.0) == -np.inf
+
+
+def test_resampling_numerics_definitions():
+    rng = np.random.default_rng(1)
+    lw = 3 * rng.normal(size=5000) + 1000.0
+    w = ref.exp_norm(lw)
+    assert abs(w.sum() - 1) < 1e-13 and np.all(w >= 0)
+    assert abs(ref.logsumexp(lw) - (1000.0 + math.log(np.sum(np.exp(lw - 1000.0))))) < 1e-10
+    assert abs(ref.ess_perc(np.full(10, 0.1)) - 1.0) < 1e-15
+    assert abs(ref.ess_perc(np.eye(10)[0]) - 0.1) < 1e-15
+    np.testing.assert_allclose(cref.exp_norm(lw), w, rtol=1e-13)
+    assert abs(cref.logsumexp(lw) - ref.logsumexp(lw)) < 1e-10
+    assert abs(ref.julia_pairwise_sum(w) - 1.0) < 1e-13
+
+
+def test_icdf_is_the_two_pointer_walk():
+    rng = np.random.default_rng(2)
+    for n in (1, 2, 17, 500):
+        w = rng.random(n) ** 4
+        w[rng.random(n) < 0.2] = 0.0
+        if w.sum() == 0:
+            w[0] = 1.0
+        w = w / w.sum()
+        us = ref.stratified_us(rng.random(n) * 0.999)
+        us = np.minimum(us, np.cumsum(w)[-1])  # keep the literal loop in bounds
+        a = ref.icdf_loop(w, us)
+        np.testing.assert_array_equal(a, ref.icdf(w, us))
+        ac, cl = cref.icdf(w, us)
+        np.testing.assert_array_equal(a, ac)
+        assert cl == 0
+    # u exactly on a boundary belongs to the lower particle (s < u is strict); u = 0 keeps particle 1
+    w = np.array([0.25, 0.25, 0.5])
+    np.testing.assert_array_equal(ref.icdf(w, np.array([0.0, 0.25, 0.5])), [0, 0, 1])
+    np.testing.assert_array_equal(ref.icdf_loop(w, np.array([0.0, 0.25, 0.5])), [0, 0, 1])
+    with pytest.raises(IndexError):
+        ref.icdf_loop(np.array([0.5, 0.4]), np.array([0.1, 0.95]))
+
+
+def test_stratified_us_fp_order():
+    r = np.random.default_rng(3).random(1000)
+    us = ref.stratified_us(r)
+    inv = 1.0 / 1000
+    assert us[123] == 123 * inv + r[123] * inv
+    np.testing.assert_array_equal(us, cref.stratified_us(r))
+    assert np.all(np.diff(us) > 0)
+
+
+def test_kalman_closed_form_pins_filter():
+    """test/transformers_test.jl:158-186 through the oracle interpreter."""
+    import wsb200 as ws
+    a, q, r = 0.9, 1.0, 0.5
+    rng = np.random.default_rng(42)
+    x, ys = rng.normal(), []
+    for _ in range(30):
+        x = a * x + q * rng.normal()
+        ys.append(x + r * rng.normal())
+    n = 20000
+    root = ws.model(models.LGSSM1D)(ys, a, q, r, 1.0)
+    st = ref.OracleState(n, ref.Streams(rng.normal(size=n * 31), rng.random(n * 31)), ess_perc_min=0.5)
+    ref.run(root, st)
+    mean_exact, le_exact = ref.kalman_filter_evidence(ys, a, q, r)
+    assert abs(ref.log_evidence(st) - le_exact) < 0.1
+    assert abs(ref.expectation(st.cols["x"], st.weights) - mean_exact) < 0.05
+    le_c, mean_c, nres = cref.lgssm1d_run(50000, ys, a, q, r, 1.0, seed=3, ess_perc_min=0.5)
+    assert abs(le_c - le_exact) < 0.1 and abs(mean_c - mean_exact) < 0.05 and nres > 3
+
+
+def test_score_depth_cutoff_and_move_invariance():
+    import wsb200 as ws
+    n = 500
+    rng = np.random.default_rng(5)
+    root = ws.Sequence(ws.Sample("θ", "Normal", (0.0, 1.0)), ws.Assign("x", ws.col("θ")),
+                       ws.Observe(1.5, "Normal", (ws.col("x"), 0.5)))
+    st = ref.OracleState(n, ref.Streams(rng.normal(size=n)))
+    ref.run(root, st)
+    th = st.cols["θ"]
+    e1 = sst.norm.logpdf(th, 0, 1)
+    assert np.all(ref.score_logpdf(st, ["θ"], 0) == 0)
+    np.testing.assert_allclose(ref.score_logpdf(st, ["θ"], 1), e1, rtol=1e-12)
+    np.testing.assert_allclose(ref.score_logpdf(st, ["θ"], 2), e1, rtol=1e-12)
+    np.testing.assert_allclose(ref.score_logpdf(st, ["θ"], 3), e1 + sst.norm.logpdf(1.5, th, 0.5), rtol=1e-12)
+    # MH invariance at the exact Normal-Normal posterior (test/move_test.jl:69-98)
+    T, tau0, n = 5, 2.0, 40000
+    y = rng.normal(size=T) + 1.3
+    pv = 1 / (1 / tau0 ** 2 + T)
+    pm = pv * y.sum()
+    root = ws.Sequence(ws.Sample("θ", "Normal", (0.0, tau0)), *[ws.Observe(float(v), "Normal", (ws.col("θ"), 1.0)) for v in y])
+    st = ref.OracleState(n, ref.Streams(rng.normal(size=10 * n), rng.random(10 * n)))
+    st.setcol("θ", rng.normal(size=n) * math.sqrt(pv) + pm)
+    st.root, st.depth = root, T + 1
+    mv = ws.Move(["θ"], ws.RW, (0.3,))
+    for _ in range(10):
+        ref.apply_move(mv, st)
+    assert abs(st.cols["θ"].mean() - pm) < 0.02 and abs(st.cols["θ"].var() - pv) < 0.02
+    assert ref.marginal_diversity_bits(np.repeat(np.arange(5.0), 200)) == 5 / 1000
+
+
+def test_weighted_cov_and_transforms():
+    rng = np.random.default_rng(6)
+    Z, w = rng.normal(size=(300, 2)), rng.random(300)
+    np.testing.assert_allclose(ref.weighted_cov(Z, w), np.cov(Z.T, aweights=w, bias=True), rtol=1e-12)
+    for lo, hi in ((0.0, math.inf), (-math.inf, 3.0), (-1.0, 2.0), (-math.inf, math.inf)):
+        x = rng.uniform(max(lo, -5) + 0.01, min(hi, 5) - 0.01, 100)
+        z = ref.to_unconstrained(x, lo, hi)
+        np.testing.assert_allclose(ref.from_unconstrained(z, lo, hi), x, rtol=1e-12, atol=1e-12)
+        h = 1e-6
+        num = np.log(np.abs(ref.from_unconstrained(z + h, lo, hi) - ref.from_unconstrained(z - h, lo, hi)) / (2 * h))
+        np.testing.assert_allclose(ref.log_abs_jacobian(z, lo, hi), num, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["ssm1d", "ssm2d", "linreg", "schools"])
+def test_golden_runs_are_reproduced_by_the_oracle(name):
+    import wsb200 as ws
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    src, args = {
+        "ssm1d": (models.SSM1D, lambda: (list(g["obs"]),)),
+        "ssm2d": (models.SSM2D, lambda: ([o for o in g["obs"]],)),
+        "linreg": (models.LINREG, lambda: (g["xs"], g["ys"])),
+        "schools": (models.SCHOOLS, lambda: (8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA)),
+    }[name]
+    n = g["weights"].shape[0]
+    st = ref.OracleState(n, ref.Streams(g["normals"], g["uniforms"], g["exponentials"]), ess_perc_min=0.5)
+    ref.run(ws.model(src)(*args()), st)
+    np.testing.assert_array_equal(st.weights, g["weights"])
+    for nm in st.names:
+        np.testing.assert_array_equal(st.cols[nm], g["col_" + nm])
+    assert int(g["n_resampled"]) >= 1 and st.depth == int(g["depth"])
+
+
+def test_golden_resampling_fixture():
+    g = np.load(os.path.join(GOLD, "resampling.npz"))
+    np.testing.assert_array_equal(ref.exp_norm(g["logw"]), g["w"])
+    np.testing.assert_array_equal(ref.icdf(g["w"], ref.stratified_us(g["r"])), g["ancestors"])
+    a, _ = cref.icdf(g["w"], cref.stratified_us(g["r"]))
+    np.testing.assert_array_equal(a, g["ancestors"])
+
+
+def test_c_oracle_normals_are_standard():
+    le, mean, nres = cref.ssm2d_run(20000, np.zeros((3, 2)) + [[0, 0], [1, 0], [2, 0]], seed=5, ess_perc_min=1.0)
+    assert nres == 2 and np.isfinite(le)  # step 1: identical x => ESS% == 1.0, not < 1.0
+    assert abs(mean[1]) < 0.2

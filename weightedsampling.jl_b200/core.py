@@ -1,0 +1,783 @@
+"""Host-side mirror of the reference's L1-L3 layers for the particle hot path, over the C ABI.
+
+Reference (all under /root/reference/src):
+  DeviceColumnStore  <- ColumnStore / AbstractParticleStore          stores.jl:28-35,70-111
+  SMCState, run      <- SMCState, run!, advance!, score_logpdf        types.jl:48-78,120-126,183-206
+  Assign ... Move    <- the ParticleTransformer subtypes + apply!/score!  transformers.jl
+  Normal/MvNormal/Exponential, importance_kernel  <- default_kernels  default_kernels.jl:69-102
+  RW, autoRW         <- proposals                                     move_kernels.jl:189-265
+
+Every ``apply`` body is one C-ABI call; nothing here touches particle data on the host.  Python
+is the host language because no Julia toolchain exists in the build image; ``julia/WSB200.jl`` is
+the ``ccall`` shim with the same structure.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import UnsupportedModelError, WsError, check
+from .expr import CExprs, Col, Const, Expr, Tokens, lower, wrap
+
+__all__ = [
+    "DeviceColumnStore", "ColumnStore", "SMCState", "ParticleTransformer", "Assign", "AccessorAssign", "Sample",
+    "AccessorSample", "Observe", "Weight", "Sequence", "Loop", "Cond", "Resample", "Move", "ScoreCtx", "apply",
+    "score", "run", "score_logpdf", "marginal_diversity", "WeightedKernel", "Normal", "MvNormal", "Exponential",
+    "importance_kernel", "default_kernels", "RW", "autoRW", "default_proposals", "nparticles", "hascol", "getcol",
+    "colnames", "resample",
+]
+
+
+def _unsupported(msg):
+    return UnsupportedModelError(L.WS_EUNSUPPORTED, msg)
+
+
+# --------------------------------------------------------------------------------------------------
+# L1: particle store
+# --------------------------------------------------------------------------------------------------
+class DeviceColumnStore:
+    """``ColumnStore`` whose columns are device-resident Float64 planes (stores.jl:70-111).
+
+    ``getcol`` returns a host COPY (download); device-resident access is through statements.
+    """
+
+    def __init__(self, n, *, device=0, seed=0, ess_perc_min=0.5, resampler="stratified"):
+        lib = L.load()
+        self._lib = lib
+        self._ctx = C.c_void_p()
+        rc = lib.ws_create(C.byref(self._ctx), int(n), int(device), int(seed) & (2 ** 64 - 1), float(ess_perc_min),
+                           L.RESAMPLER[resampler])
+        if rc != 0:
+            msg = lib.ws_last_error(None)
+            raise WsError(rc, msg.decode() if msg else "")
+        self.n = int(n)
+
+    # -- C-ABI plumbing ---------------------------------------------------------------------------
+    def _call(self, name, *args):
+        check(self._ctx, getattr(self._lib, name)(self._ctx, *args))
+
+    def _lookup(self, name):
+        cid, width = C.c_int32(), C.c_int32()
+        self._call("ws_col_lookup", name.encode(), C.byref(cid), C.byref(width))
+        return cid.value, width.value
+
+    def _ensure(self, name, width):
+        cid = C.c_int32()
+        self._call("ws_col_ensure", name.encode(), int(width), C.byref(cid))
+        return cid.value
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.ws_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- AbstractParticleStore interface (stores.jl:28-35) ----------------------------------------
+    def nparticles(self):
+        return self.n
+
+    def hascol(self, name):
+        return self._lookup(str(name))[0] >= 0
+
+    def colnames(self):
+        cnt = C.c_int32()
+        self._call("ws_col_count", C.byref(cnt))
+        out = []
+        buf = C.create_string_buffer(256)
+        for i in range(cnt.value):
+            w = C.c_int32()
+            self._call("ws_col_info", i, buf, 256, C.byref(w))
+            out.append(buf.value.decode())
+        return out
+
+    def colwidth(self, name):
+        return self._lookup(str(name))[1]
+
+    def getcol(self, name):
+        cid, width = self._lookup(str(name))
+        if cid < 0:
+            raise KeyError(name)
+        out = np.empty((width, self.n), dtype=np.float64)
+        self._call("ws_col_download", cid, out.ctypes.data_as(C.c_void_p))
+        return out[0].copy() if width == 1 else np.ascontiguousarray(out.T)  # vector columns: (n, d)
+
+    def setcol(self, name, values):
+        """``broadcast_setcol!(store, name, identity, (values,))`` with host data (upload)."""
+        v = np.asarray(values, dtype=np.float64)
+        if v.ndim == 0:
+            v = np.full(self.n, float(v))
+        if v.ndim == 1:
+            if v.shape[0] != self.n:
+                raise ValueError(f"column length {v.shape[0]} != n_particles {self.n}")
+            planes = np.ascontiguousarray(v[None, :])
+        else:
+            if v.shape[0] != self.n:
+                raise ValueError(f"column length {v.shape[0]} != n_particles {self.n}")
+            planes = np.ascontiguousarray(v.T)
+        cid = self._ensure(str(name), planes.shape[0])
+        self._call("ws_col_upload", cid, planes.ctypes.data_as(C.c_void_p))
+
+    def resample(self, indices):
+        """``resample!(store, indices)`` (stores.jl:105-111), 0-based indices."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        if idx.shape != (self.n,):
+            raise ValueError("indices must have one entry per particle")
+        if idx.min() < 0 or idx.max() >= self.n:
+            raise IndexError("ancestor index out of range")
+        self._call("ws_gather", idx.ctypes.data_as(C.c_void_p))
+
+    def __repr__(self):
+        return f"ColumnStore(n={self.n}, columns={self.colnames()})"
+
+
+ColumnStore = DeviceColumnStore
+
+
+def nparticles(store): return store.nparticles()
+def hascol(store, name): return store.hascol(name)
+def getcol(store, name): return store.getcol(name)
+def colnames(store): return store.colnames()
+def resample(store, indices): return store.resample(indices)
+
+
+# --------------------------------------------------------------------------------------------------
+# SMCState
+# --------------------------------------------------------------------------------------------------
+class SMCState:
+    """``SMCState(n; ess_perc_min=0.5)`` (types.jl:48-78).  Weights, flags and depth live in the C
+    context; the attributes below read / write them."""
+
+    def __init__(self, n_or_store, *, ess_perc_min=0.5, seed=0, device=0, resampler="stratified", show_progress=False):
+        if isinstance(n_or_store, DeviceColumnStore):
+            self.store = n_or_store
+            self.store._call("ws_set_ess_perc_min", float(ess_perc_min))
+        else:
+            self.store = DeviceColumnStore(int(n_or_store), device=device, seed=seed, ess_perc_min=ess_perc_min,
+                                           resampler=resampler)
+        self._root = None
+        self._tape_valid = True  # the recorded tape is the score! walk of `root` up to `depth`
+        self.record_tape = True
+        self.show_progress = show_progress
+
+    # flags ----------------------------------------------------------------------------------------
+    def _flags(self):
+        r, w, d = C.c_int(), C.c_int(), C.c_int64()
+        self.store._call("ws_get_flags", C.byref(r), C.byref(w), C.byref(d))
+        return bool(r.value), bool(w.value), d.value
+
+    @property
+    def resampled(self): return self._flags()[0]
+
+    @resampled.setter
+    def resampled(self, v): self.store._call("ws_set_flags", int(bool(v)), int(self._flags()[1]))
+
+    @property
+    def weights_changed(self): return self._flags()[1]
+
+    @weights_changed.setter
+    def weights_changed(self, v): self.store._call("ws_set_flags", int(self._flags()[0]), int(bool(v)))
+
+    @property
+    def depth(self): return self._flags()[2]
+
+    @depth.setter
+    def depth(self, v):
+        self.store._call("ws_set_depth", int(v))
+        self._tape_valid = False
+
+    @property
+    def root(self): return self._root
+
+    @root.setter
+    def root(self, t):
+        self._root = t
+        self._tape_valid = False
+
+    @property
+    def ess_perc_min(self):
+        v = C.c_double()
+        self.store._call("ws_get_ess_perc_min", C.byref(v))
+        return v.value
+
+    @ess_perc_min.setter
+    def ess_perc_min(self, v): self.store._call("ws_set_ess_perc_min", float(v))
+
+    @property
+    def weights(self):
+        out = np.empty(self.store.n, dtype=np.float64)
+        self.store._call("ws_weights_download", out.ctypes.data_as(C.c_void_p))
+        return out
+
+    @weights.setter
+    def weights(self, v):
+        a = np.ascontiguousarray(v, dtype=np.float64)
+        if a.shape != (self.store.n,):
+            raise ValueError("weights must have one entry per particle")
+        self.store._call("ws_weights_upload", a.ctypes.data_as(C.c_void_p), 0)
+
+    def __getitem__(self, name):
+        return self.store.getcol(name)
+
+    def sync(self):
+        self.store._call("ws_sync")
+
+    # replay hooks (parity tests) -------------------------------------------------------------------
+    def set_replay(self, normals=None, uniforms=None, exponentials=None):
+        for arr, fn in ((normals, "ws_set_replay_normals"), (uniforms, "ws_set_replay_uniforms"),
+                        (exponentials, "ws_set_replay_exponentials")):
+            if arr is None:
+                self.store._call(fn, None, 0)
+            else:
+                a = np.ascontiguousarray(arr, dtype=np.float64)
+                self.store._call(fn, a.ctypes.data_as(C.c_void_p), a.size)
+
+    def stats(self):
+        s = L.ws_stats()
+        self.store._call("ws_get_stats", C.byref(s))
+        return {f: getattr(s, f) for f, _ in L.ws_stats._fields_}
+
+    def kernel_times(self):
+        ms = (C.c_double * 8)()
+        cnt = (C.c_int64 * 8)()
+        self.store._call("ws_kernel_times", ms, cnt, 8)
+        return {k: {"ms": ms[i], "launches": cnt[i]} for i, k in enumerate(L.KERNEL_CLASSES)}
+
+    def __repr__(self):
+        return f"SMCState(n_particles={self.store.n}, columns={self.store.colnames()})"
+
+    def describe_state(self):
+        r, _, d = self._flags()
+        return ("SMCState\n  n_particles:  %d\n  columns:      %s\n  ess_perc_min: %s\n  resampled:    %s\n"
+                "  depth:        %d" % (self.store.n, self.store.colnames(), self.ess_perc_min, str(r).lower(), d))
+
+
+# --------------------------------------------------------------------------------------------------
+# kernels (the device kernel table; default_kernels.jl)
+# --------------------------------------------------------------------------------------------------
+def _scalar(tok, what):
+    if isinstance(tok, list):
+        raise _unsupported(f"{what} must be scalar-valued")
+    return tok
+
+
+def _target(store, lhs, width, create=True):
+    """lhs is a column name or (name, j) for an accessor target ``x[j]`` (0-based)."""
+    if isinstance(lhs, tuple):
+        name, j = lhs
+        cid, w = store._lookup(str(name))
+        if cid < 0:
+            raise KeyError(f"column {name!r} must exist before an accessor write")  # AccessorSample docstring
+        if not (0 <= int(j) < w):
+            raise IndexError(f"index {j} out of range for column {name!r} of width {w}")
+        return cid, int(j)
+    cid, w = store._lookup(str(lhs))
+    if cid < 0:
+        if not create:
+            raise KeyError(lhs)
+        cid = store._ensure(str(lhs), width)
+    elif w != width:
+        raise _unsupported(f"column {lhs!r} has width {w}; re-assigning it with width {width} would change its element type")
+    return cid, 0
+
+
+class WeightedKernel:
+    """A device kernel descriptor: sampler / weighter / logpdf are fixed device ops (types.jl:226-230).
+    Arbitrary host closures cannot run on the device, so building one from Python callables is rejected."""
+
+    name = "WeightedKernel"
+    has_weighter = False
+
+    def __init__(self, *a, **k):
+        if type(self) is WeightedKernel:
+            raise _unsupported("WeightedKernel from host closures is outside the device-op set; use Normal, MvNormal, "
+                               "Exponential or importance_kernel(Normal, Normal)")
+
+    def sample(self, state, lhs, args): raise NotImplementedError
+    def observe(self, state, value, args): raise NotImplementedError
+
+
+class _Normal(WeightedKernel):
+    name = "Normal"
+
+    def sample(self, state, lhs, args):
+        st = state.store
+        mu, sigma = (_scalar(lower(a, st), "Normal argument") for a in args)
+        cid, comp = _target(st, lhs, 1)
+        ex = CExprs([mu, sigma])
+        st._call("ws_sample_normal", cid, comp, ex.ptr(0), ex.ptr(1))
+
+    def observe(self, state, value, args):
+        st = state.store
+        obs = _scalar(lower(value, st), "observed value")
+        mu, sigma = (_scalar(lower(a, st), "Normal argument") for a in args)
+        ex = CExprs([obs, mu, sigma])
+        st._call("ws_observe_normal", ex.ptr(0), ex.ptr(1), ex.ptr(2))
+
+
+class _Exponential(WeightedKernel):
+    name = "Exponential"
+
+    def sample(self, state, lhs, args):
+        st = state.store
+        (theta,) = (_scalar(lower(a, st), "Exponential argument") for a in args)
+        cid, comp = _target(st, lhs, 1)
+        ex = CExprs([theta])
+        st._call("ws_sample_exponential", cid, comp, ex.ptr(0))
+
+    def observe(self, state, value, args):
+        st = state.store
+        obs = _scalar(lower(value, st), "observed value")
+        (theta,) = (_scalar(lower(a, st), "Exponential argument") for a in args)
+        ex = CExprs([obs, theta])
+        st._call("ws_observe_exponential", ex.ptr(0), ex.ptr(1))
+
+
+def _const_matrix(a, d):
+    if isinstance(a, Expr) and not isinstance(a, Const):
+        raise _unsupported("MvNormal covariance must be a build-time constant (per-particle covariances are outside "
+                           "the device-op set)")
+    m = np.asarray(a.v if isinstance(a, Expr) else a, dtype=np.float64)
+    if m.ndim == 1 and m.shape[0] == d:  # diagonal given as a vector of variances
+        m = np.diag(m)
+    if m.shape != (d, d):
+        raise ValueError(f"covariance must be {d}x{d}, got {m.shape}")
+    return np.ascontiguousarray(m)
+
+
+class _MvNormal(WeightedKernel):
+    name = "MvNormal"
+
+    @staticmethod
+    def _vec(tok, what):
+        if not isinstance(tok, list):
+            raise _unsupported(f"{what} must be vector-valued")
+        return tok
+
+    def sample(self, state, lhs, args):
+        st = state.store
+        mu = self._vec(lower(args[0], st), "MvNormal mean")
+        d = len(mu)
+        cov = _const_matrix(args[1], d)
+        if isinstance(lhs, tuple):
+            raise _unsupported("MvNormal into an accessor target")
+        cid, _ = _target(st, lhs, d)
+        ex = CExprs(mu)
+        st._call("ws_sample_mvnormal", cid, d, ex.ptr(0), cov.ctypes.data_as(C.c_void_p))
+
+    def observe(self, state, value, args):
+        st = state.store
+        obs = self._vec(lower(value, st), "observed value")
+        mu = self._vec(lower(args[0], st), "MvNormal mean")
+        d = len(mu)
+        if len(obs) != d:
+            raise ValueError("observation and mean dimensions differ")
+        cov = _const_matrix(args[1], d)
+        eo, em = CExprs(obs), CExprs(mu)
+        st._call("ws_observe_mvnormal", d, eo.ptr(0), em.ptr(0), cov.ctypes.data_as(C.c_void_p))
+
+
+Normal = _Normal()
+Exponential = _Exponential()
+MvNormal = _MvNormal()
+
+
+class _ImportanceNormal(WeightedKernel):
+    """``importance_kernel(Normal(pm, ps), Normal(tm, ts))`` (default_kernels.jl:69-73)."""
+    name = "importance_kernel"
+    has_weighter = True
+
+    def __init__(self, pm, ps, tm, ts):
+        self.p = (float(pm), float(ps), float(tm), float(ts))
+
+    def sample(self, state, lhs, args):
+        if len(args) != 0:
+            raise ValueError("importance_kernel takes no arguments")
+        st = state.store
+        cid, comp = _target(st, lhs, 1)
+        st._call("ws_sample_importance_normal", cid, comp, *self.p)
+
+
+class NormalDist:
+    """``Normal(mu, sigma)`` as a distribution VALUE (only as an importance_kernel argument)."""
+
+    def __init__(self, mu, sigma):
+        self.mu, self.sigma = float(mu), float(sigma)
+
+
+def importance_kernel(proposal, target):
+    if not (isinstance(proposal, NormalDist) and isinstance(target, NormalDist)):
+        raise _unsupported("importance_kernel is built for Normal proposal / Normal target only")
+    return _ImportanceNormal(proposal.mu, proposal.sigma, target.mu, target.sigma)
+
+
+default_kernels = {"Normal": Normal, "MvNormal": MvNormal, "Exponential": Exponential}
+
+# the reference's other 52 table entries (default_kernels.jl:83-102) are outside the device-op set
+_REFERENCE_ONLY_KERNELS = (
+    "Beta BernoulliLogit Bernoulli BetaBinomial Binomial Categorical Cauchy Chi Chisq Dirac Dirichlet "
+    "DiscreteNonParametric DiscreteUniform FDist Frechet Gamma GeneralizedPareto Geometric Gumbel Hypergeometric "
+    "InverseGamma InverseWishart LKJ LKJCholesky Laplace LogNormal Logistic LogitNormal MatrixBeta MatrixFDist "
+    "MatrixNormal MatrixTDist MvLogNormal MvLogitNormal MvNormalCanon Multinomial NegativeBinomial NoncentralChisq "
+    "NoncentralF NoncentralT NormalCanon Pareto Poisson PoissonBinomial Rayleigh SkewNormal SkewedExponentialPower "
+    "TDist Uniform VonMises Weibull Wishart").split()
+
+
+def resolve_kernel(f, kernels=None):
+    """Kernel resolution by name (rewrites.jl:383-389): user table over default_kernels."""
+    if isinstance(f, WeightedKernel):
+        return f
+    table = dict(default_kernels)
+    if kernels:
+        table.update(kernels)
+    if f in table:
+        return table[f]
+    if f in _REFERENCE_ONLY_KERNELS:
+        raise _unsupported(f"kernel {f} is in the reference's default_kernels but outside the device-op set "
+                           "(Normal, MvNormal, Exponential)")
+    raise KeyError(f"unknown kernel {f!r}")
+
+
+# --------------------------------------------------------------------------------------------------
+# L3: transformers
+# --------------------------------------------------------------------------------------------------
+class ParticleTransformer:
+    def apply(self, state): raise NotImplementedError
+    def score(self, state, ctx): raise NotImplementedError
+
+
+class ScoreCtx:
+    """types.jl:147-152.  ``scores`` are accumulated on the device tape; only depth is tracked here."""
+
+    def __init__(self, targets, target_depth, depth=0):
+        self.targets, self.target_depth, self.depth = list(targets), int(target_depth), int(depth)
+
+
+def _args(argfn, state):
+    a = argfn(state) if callable(argfn) else argfn
+    return tuple(a) if isinstance(a, (tuple, list)) else (a,)
+
+
+def _one(fn, state):
+    return fn(state) if callable(fn) else fn
+
+
+class Assign(ParticleTransformer):
+    """``x .= expr`` (transformers.jl:18-42).  ``lhs`` may be ``(name, j)`` for ``x[j] .= expr``
+    (AccessorAssign on a vector column, transformers.jl:57-80)."""
+
+    def __init__(self, lhs, argfn):
+        self.lhs, self.argfn = lhs, argfn
+
+    def apply(self, state):
+        st = state.store
+        tok = lower(_one(self.argfn, state), st)
+        if isinstance(tok, list):
+            if isinstance(self.lhs, tuple):
+                raise _unsupported("vector value into an accessor target")
+            cid, _ = _target(st, self.lhs, len(tok))
+            ex = CExprs(tok)
+            st._call("ws_assign_vec", cid, len(tok), ex.ptr(0))
+        else:
+            cid, comp = _target(st, self.lhs, 1)
+            ex = CExprs([tok])
+            st._call("ws_assign", cid, comp, ex.ptr(0))
+
+    def score(self, state, ctx):
+        state.store._call("ws_set_depth", ctx.depth + 1)
+        ctx.depth += 1
+
+
+AccessorAssign = Assign
+
+
+class Sample(ParticleTransformer):
+    """``x ~ f(args)`` (transformers.jl:158-199); ``lhs = (name, j)`` is AccessorSample
+    (``x[j] ~ f(args)``, transformers.jl:103-145)."""
+
+    def __init__(self, lhs, kernel, argfn=()):
+        self.lhs, self.kernel, self.argfn = lhs, resolve_kernel(kernel), argfn
+
+    def apply(self, state):
+        self.kernel.sample(state, self.lhs, _args(self.argfn, state))
+
+    def score(self, state, ctx):
+        # record-only mode: the same call appends the statement's log-density to the tape
+        self.kernel.sample(state, self.lhs, _args(self.argfn, state))
+        ctx.depth += 1
+
+
+AccessorSample = Sample
+
+
+class Observe(ParticleTransformer):
+    """``expr => f(args)`` (transformers.jl:216-249)."""
+
+    def __init__(self, lhsfn, kernel, argfn):
+        self.lhsfn, self.kernel, self.argfn = lhsfn, resolve_kernel(kernel), argfn
+
+    def apply(self, state):
+        self.kernel.observe(state, _one(self.lhsfn, state), _args(self.argfn, state))
+
+    def score(self, state, ctx):
+        self.apply(state)
+        ctx.depth += 1
+
+
+class Weight(ParticleTransformer):
+    """``_ ~ f(args)`` (transformers.jl:270-302).  With a distribution kernel the LAST argument plays
+    the role of the value (the reference's NormalWeightKernel: ``(mu, sigma, x) -> logpdf``); with
+    ``kernel=None`` the single argument is an arbitrary log-weight expression."""
+
+    def __init__(self, kernel, argfn):
+        self.kernel = None if kernel is None else resolve_kernel(kernel)
+        self.argfn = argfn
+
+    def apply(self, state):
+        a = _args(self.argfn, state)
+        if self.kernel is None:
+            tok = _scalar(lower(a[0], state.store), "log-weight term")
+            ex = CExprs([tok])
+            state.store._call("ws_weight_expr", ex.ptr(0))
+        else:
+            self.kernel.observe(state, a[-1], a[:-1])
+
+    def score(self, state, ctx):
+        self.apply(state)
+        ctx.depth += 1
+
+
+class Sequence(ParticleTransformer):
+    """transformers.jl:320-349."""
+
+    def __init__(self, *steps):
+        if len(steps) == 1 and isinstance(steps[0], (tuple, list)):
+            steps = tuple(steps[0])
+        self.steps = tuple(steps)
+
+    def apply(self, state):
+        for s in self.steps:
+            s.apply(state)
+
+    def score(self, state, ctx):
+        for s in self.steps:
+            if not ctx.depth < ctx.target_depth:
+                break
+            s.score(state, ctx)
+
+
+class Loop(ParticleTransformer):
+    """``for x in coll ... end`` (transformers.jl:367-398); the body is rebuilt per iteration."""
+
+    def __init__(self, collfn, bodyfn):
+        self.collfn, self.bodyfn = collfn, bodyfn
+
+    def _coll(self, state):
+        return self.collfn(state) if callable(self.collfn) else self.collfn
+
+    def apply(self, state):
+        for x in self._coll(state):
+            self.bodyfn(x).apply(state)
+
+    def score(self, state, ctx):
+        for x in self._coll(state):
+            if not ctx.depth < ctx.target_depth:
+                break
+            self.bodyfn(x).score(state, ctx)
+
+
+class Cond(ParticleTransformer):
+    """``if cond ... end`` (transformers.jl:413-444); ``predfn(state) -> bool`` on the host."""
+
+    def __init__(self, predfn, body):
+        self.predfn, self.body = predfn, body
+
+    def apply(self, state):
+        if self.predfn(state):
+            self.body.apply(state)
+
+    def score(self, state, ctx):
+        if self.predfn(state):
+            self.body.score(state, ctx)
+
+
+class Resample(ParticleTransformer):
+    """transformers.jl:461-507 — the whole state machine runs inside ``ws_resample``."""
+
+    def __init__(self):
+        self.last = None
+
+    def apply(self, state):
+        info = L.ws_resample_info()
+        state.store._call("ws_resample", C.byref(info))
+        self.last = info
+
+    def score(self, state, ctx):
+        return None
+
+
+# -- proposals (move_kernels.jl:189-265) ------------------------------------------------------------
+class _Proposal:
+    def __init__(self, code, name):
+        self.code, self.name = code, name
+
+    def __repr__(self):
+        return self.name
+
+
+RW = _Proposal(0, "RW")
+autoRW = _Proposal(1, "autoRW")
+default_proposals = {"RW": RW, "autoRW": autoRW}
+
+
+def _normalize_bounds(bounds, d):
+    """move_kernels.jl:23-28."""
+    if bounds is None:
+        return None
+    if isinstance(bounds, tuple) and len(bounds) == 2 and not isinstance(bounds[0], (tuple, list)):
+        return [tuple(map(float, bounds))] * d
+    b = [tuple(map(float, x)) for x in bounds]
+    if len(b) != d:
+        raise ValueError(f"bounds must have length {d} (one (lo, hi) tuple per target), got {len(b)}")
+    return b
+
+
+def _target_planes(store, targets):
+    cols, comps = [], []
+    for t in targets:
+        if isinstance(t, tuple):
+            raise _unsupported("accessor targets (x[e] / x.p) cannot be moved; a move rewrites a whole column")
+        cid, w = store._lookup(str(t))
+        if cid < 0:
+            raise KeyError(f"move target {t!r} does not exist")
+        for k in range(w):  # a vector-valued target moves all its components jointly
+            cols.append(cid)
+            comps.append(k)
+    return cols, comps
+
+
+def marginal_diversity(store, targets):
+    """transformers.jl:560-565: min over targets of |unique(col)| / N."""
+    cols, comps = _target_planes(store, list(targets))
+    c = (C.c_int32 * len(cols))(*cols)
+    k = (C.c_int32 * len(cols))(*comps)
+    out = C.c_double()
+    store._call("ws_marginal_diversity", len(cols), c, k, C.byref(out))
+    return out.value
+
+
+class Move(ParticleTransformer):
+    """``x << q(args)`` (transformers.jl:543-633)."""
+
+    def __init__(self, targets, proposal, argfn=(), diversity_threshold=None):
+        if isinstance(targets, str):
+            targets = [targets]
+        self.targets = list(targets)
+        self.proposal = default_proposals[proposal] if isinstance(proposal, str) else proposal
+        if not isinstance(self.proposal, _Proposal):
+            raise _unsupported("custom host proposal functions are outside the device-op set (RW, autoRW)")
+        self.argfn = argfn
+        self.diversity_threshold = diversity_threshold
+        self.last = None
+
+    def apply(self, state):
+        st = state.store
+        args = _args(self.argfn, state)
+        cols, comps = _target_planes(st, self.targets)
+        d = len(cols)
+        if self.proposal is RW:
+            if len(args) < 1:
+                raise TypeError("RW(step_size, bounds=nothing) needs a step size")
+            step = float(np.asarray(args[0]).ravel()[0])
+            bounds = args[1] if len(args) > 1 else None
+        else:
+            step = float(np.asarray(args[0]).ravel()[0]) if len(args) > 0 else 1e-3  # min_step
+            bounds = args[1] if len(args) > 1 else None
+        bnds = _normalize_bounds(bounds, d)
+        if not state._tape_valid:
+            _rebuild_tape(state)
+        spec = L.ws_move_spec()
+        spec.n_targets = d
+        c_arr = (C.c_int32 * d)(*cols)
+        k_arr = (C.c_int32 * d)(*comps)
+        spec.col, spec.comp = c_arr, k_arr
+        spec.proposal = self.proposal.code
+        if bnds is None:
+            spec.has_bounds = 0
+        else:
+            spec.has_bounds = 1
+            lo = (C.c_double * d)(*[b[0] for b in bnds])
+            hi = (C.c_double * d)(*[b[1] for b in bnds])
+            spec.lo, spec.hi = lo, hi
+        spec.step = step
+        spec.diversity = float("nan") if self.diversity_threshold is None else float(self.diversity_threshold)
+        spec.target_depth = -1
+        info = L.ws_move_info()
+        st._call("ws_move", C.byref(spec), C.byref(info))
+        self.last = info
+
+    def score(self, state, ctx):
+        return None
+
+
+# --------------------------------------------------------------------------------------------------
+# run! / score_logpdf
+# --------------------------------------------------------------------------------------------------
+def apply(t, state):
+    """``apply!(t, state)``."""
+    t.apply(state)
+
+
+def score(t, state, ctx):
+    """``score!(t, state, ctx)`` (record-only walk; see :func:`score_logpdf`)."""
+    t.score(state, ctx)
+
+
+def run(root, state):
+    """``run!(root, state)`` (types.jl:120-126)."""
+    st = state.store
+    record = bool(state.record_tape) and getattr(root, "_has_moves", True)
+    st._call("ws_tape_enable", int(record))
+    st._call("ws_begin_run")
+    state._root = root
+    state._tape_valid = record
+    root.apply(state)
+    return state
+
+
+def _rebuild_tape(state, target_depth=None):
+    """Re-walk ``state.root`` with score! semantics, recording (not executing) every scored
+    statement with depth < target_depth onto the device tape."""
+    if state._root is None:
+        raise RuntimeError("state.root is not set: a Move / score_logpdf needs run!(root, state) or state.root = root")
+    st = state.store
+    depth = state._flags()[2]
+    td = depth if target_depth is None else int(target_depth)
+    st._call("ws_tape_enable", 1)
+    st._call("ws_tape_clear")
+    st._call("ws_tape_record_only", 1)
+    try:
+        st._call("ws_set_depth", 0)
+        ctx = ScoreCtx([], td, 0)
+        if ctx.depth < ctx.target_depth:
+            state._root.score(state, ctx)
+    finally:
+        st._call("ws_tape_record_only", 0)
+        st._call("ws_set_depth", depth)
+    state._tape_valid = target_depth is None
+
+
+def score_logpdf(state, targets, target_depth):
+    """``score_logpdf(state, targets, target_depth)`` (types.jl:183-206) -> host vector."""
+    _rebuild_tape(state, target_depth)
+    out = np.empty(state.store.n, dtype=np.float64)
+    state.store._call("ws_score_logpdf", int(target_depth), out.ctypes.data_as(C.c_void_p))
+    state._tape_valid = False
+    return out

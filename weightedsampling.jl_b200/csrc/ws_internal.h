@@ -1,0 +1,100 @@
+// ws_internal.h — structs shared between the host runtime (ws_runtime.cu) and the kernel
+// translation units, plus the launcher prototypes.  Not part of the public ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ws_vm.cuh"
+
+#define WS_VM_BLOCK 256       // threads per CTA of the fused elementwise pass
+#define WS_VM_MAX_IO 24       // planes loaded / stored per fused pass
+#define WS_VM_MAX_OPS 96      // micro-ops per fused pass (program travels in kernel params)
+#define WS_VM_MAX_REGS 64     // register-file rows per pass (64*256*8 = 128 KB of smem)
+#define WS_SCAN_BLOCK 256
+#define WS_SCAN_ITEMS 8
+#define WS_SCAN_TILE (WS_SCAN_BLOCK * WS_SCAN_ITEMS)
+#define WS_GATHER_MAX_PLANES 32
+#define WS_MAX_PARTIALS 4096  // upper bound on CTAs that write (m,S,Q) partials
+
+// (m, S, Q) = (max l, sum exp(l-m), sum exp(2(l-m))) — everything exp_norm / ess_perc /
+// logsumexp need (src/resampling.jl:51-77), in one pass.
+struct WsLse {
+    double m, S, Q;
+};
+
+// Result of the reduction + resampling decision, device resident and mirrored to pinned host.
+struct WsReduceOut {
+    double m, S, Q;
+    double lse;         // m + log S
+    double ess_perc;    // S^2 / (N Q)
+    double log_mean_w;  // lse - log N
+    int32_t do_resample;
+    int32_t pad;
+};
+
+struct WsVmProgram {
+    int64_t n;                // local particles
+    int64_t particle_offset;  // global index of local particle 0 (RNG counters, replay offsets)
+    int32_t n_ops, n_loads, n_stores, n_regs;
+    const double* load_ptr[WS_VM_MAX_IO];
+    double* store_ptr[WS_VM_MAX_IO];
+    uint8_t load_reg[WS_VM_MAX_IO];
+    uint8_t store_reg[WS_VM_MAX_IO];
+    // pending ancestor gather folded into the loads (lazy resample!): bit k of load_gather set
+    // => plane k is read through ancestors[i]
+    const int32_t* ancestors;
+    uint32_t load_gather;
+    // log-weight accumulation of the window's Observe / Weight / weighter terms
+    int32_t logw_mode;  // 0: window has no weight term; 1: logw[i] += acc; 2: logw[i] = logw_base + acc
+    double* logw;
+    double logw_base;
+    WsLse* partials;  // per-CTA (m,S,Q) of the NEW log-weights (nullptr: skip)
+    // expectation mode (ws_expectation): sum_i w_i * r[expect_reg[k]], w_i = exp(logw_i - m)/S
+    int32_t n_expect;
+    uint8_t expect_reg[8];
+    const WsReduceOut* red;  // (m,S) for expectation mode
+    double* expect_partials; // [gridDim.x][n_expect]
+    WsRng rng;
+    WsOp ops[WS_VM_MAX_OPS];
+};
+
+struct WsScanParams {
+    const double* logw;        // log-weights (mode 0) or normalised weights (mode 1)
+    int32_t mode;              // 0: w_i = exp(l_i - m)/S from *red ; 1: w_i given ; 2: uniform weights 1/N
+    int32_t scheme;            // WS_RESAMPLER_*
+    const WsReduceOut* red;    // mode 0; also carries do_resample (checked when gate != 0)
+    int32_t gate;              // 1: return immediately unless red->do_resample
+    int32_t pad;
+    int64_t n;                 // particles == slots (single GPU)
+    uint64_t seed, stream;     // Philox stream for the slot uniforms
+    const double* replay_u;    // n uniforms (stratified) / 1 uniform (systematic) or nullptr
+    const double* sorted_u;    // multinomial: n sorted uniforms (device)
+    int32_t* ancestors;        // out, 0-based
+    unsigned long long* tile_words;  // decoupled look-back descriptors, zeroed before launch
+    unsigned int* tile_counter;      // dynamic tile ids, zeroed before launch
+    unsigned long long* n_clamped;  // += slots beyond the last CDF entry (clamped to the last particle)
+};
+
+struct WsGatherParams {
+    int64_t n;
+    const int32_t* ancestors;
+    int32_t n_planes;
+    int32_t pad;
+    const double* src[WS_GATHER_MAX_PLANES];
+    double* dst[WS_GATHER_MAX_PLANES];
+};
+
+// launchers (ws_kernels.cu)
+cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s);
+cudaError_t ws_launch_reduce_logw(const double* logw, int64_t n, WsLse* partials, int grid, cudaStream_t s);
+cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min,
+                               WsReduceOut* out, cudaStream_t s);
+cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s);
+cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s);
+cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStream_t s);
+cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,
+                               cudaStream_t s);
+cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int grid, cudaStream_t s);
+cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t n_idx, double* dst, cudaStream_t s);
+int ws_vm_max_grid(int n_regs, int sm_count);
+int ws_vm_smem_bytes(int n_regs);
+cudaError_t ws_kernels_init(int device);

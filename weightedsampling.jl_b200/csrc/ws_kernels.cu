@@ -1,0 +1,568 @@
+// ws_kernels.cu — hand-written sm_100a kernels of the particle hot path.
+//
+//   ws_vm_kernel          fused elementwise window (Assign / Sample / Observe / Weight) with the
+//                         (m, S, Q) log-weight reduction folded into its epilogue
+//   ws_reduce_logw_kernel stand-alone (m, S, Q) partials (after an upload)
+//   ws_finalize_kernel    combines partials -> logsumexp, ESS%, resample decision
+//   ws_scan_search_kernel single-pass fixed-point CDF scan (decoupled look-back) fused with the
+//                         stratified / systematic ancestor search
+//   ws_gather_kernel      ancestor gather of all planes (resample!)
+//   small helpers         fill, exp_norm write, row gather
+//
+// None of these is a dense contraction: they are HBM-bound streaming kernels (and FP64-ALU work
+// for exp / log / Philox), so the design rules are coalescing, enough bytes in flight per SM and
+// persistent grids sized in multiples of the SM count.  Tensor cores are not used.
+#include "ws_internal.h"
+
+static int g_sm_count = 148;
+
+// ------------------------------------------------------------------------------------------
+// (m, S, Q) helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lse_push(WsLse& a, double l) {
+    if (l == -INFINITY) return;  // contributes exp(-inf) = 0
+    if (l > a.m) {
+        double sc = exp(a.m - l);  // a.m == -inf -> 0
+        a.S = a.S * sc + 1.0;
+        a.Q = a.Q * sc * sc + 1.0;
+        a.m = l;
+    } else {
+        double e = exp(l - a.m);
+        a.S += e;
+        a.Q += e * e;
+    }
+}
+
+__device__ __forceinline__ WsLse lse_combine(const WsLse& a, const WsLse& b) {
+    if (b.m == -INFINITY) return a;
+    if (a.m == -INFINITY) return b;
+    WsLse r;
+    r.m = fmax(a.m, b.m);
+    double ea = exp(a.m - r.m), eb = exp(b.m - r.m);
+    r.S = a.S * ea + b.S * eb;
+    r.Q = a.Q * ea * ea + b.Q * eb * eb;
+    return r;
+}
+
+__device__ __forceinline__ WsLse lse_shfl_down(const WsLse& a, int delta) {
+    WsLse r;
+    r.m = __shfl_down_sync(0xffffffffu, a.m, delta);
+    r.S = __shfl_down_sync(0xffffffffu, a.S, delta);
+    r.Q = __shfl_down_sync(0xffffffffu, a.Q, delta);
+    return r;
+}
+
+// Block-wide combine in a fixed (deterministic) order; result valid in thread 0.
+template <int BLOCK>
+__device__ __forceinline__ WsLse lse_block_reduce(WsLse v, WsLse* warp_scratch /* BLOCK/32 */) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = lse_combine(v, lse_shfl_down(v, d));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) warp_scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        WsLse t;
+        if (lane < BLOCK / 32) {
+            t = warp_scratch[lane];
+        } else {
+            t.m = -INFINITY;
+            t.S = 0.0;
+            t.Q = 0.0;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t = lse_combine(t, lse_shfl_down(t, d));
+        v = t;
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused elementwise window
+// ------------------------------------------------------------------------------------------
+// Persistent grid, one particle per thread per tile.  The register file is a [n_regs][BLOCK]
+// array in shared memory: thread t only ever touches column t, so the pass needs no barrier
+// and shared-memory accesses are conflict-free 64-bit lanes.  Loads are staged through a
+// statically unrolled register array so that all input planes of a particle are in flight at
+// once (memory-level parallelism = n_loads per thread).
+__global__ void __launch_bounds__(WS_VM_BLOCK, 3) ws_vm_kernel(const __grid_constant__ WsVmProgram P) {
+    extern __shared__ double ws_vm_smem[];
+    __shared__ WsLse warp_scratch[WS_VM_BLOCK / 32];
+    double* R = ws_vm_smem + threadIdx.x;
+
+    WsLse part;
+    part.m = -INFINITY;
+    part.S = 0.0;
+    part.Q = 0.0;
+    double esum[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) esum[k] = 0.0;
+    double red_m = 0.0, red_invS = 0.0;
+    if (P.n_expect > 0) {
+        red_m = P.red->m;
+        red_invS = 1.0 / P.red->S;
+    }
+
+    const int64_t stride = (int64_t)gridDim.x * WS_VM_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * WS_VM_BLOCK + threadIdx.x; i < P.n; i += stride) {
+        // ---- loads: batches of 8 planes in flight per thread ---------------------------------
+        {
+            int64_t src = i;
+            if (P.load_gather != 0u) src = (int64_t)P.ancestors[i];
+            for (int k0 = 0; k0 < P.n_loads; k0 += 8) {
+                double tmp[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k0 + k < P.n_loads) {
+                        const int64_t idx = ((P.load_gather >> (k0 + k)) & 1u) ? src : i;
+                        tmp[k] = __ldg(P.load_ptr[k0 + k] + idx);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (k0 + k < P.n_loads) R[(int)P.load_reg[k0 + k] * WS_VM_BLOCK] = tmp[k];
+                }
+            }
+        }
+        double lw_old = 0.0;
+        if (P.logw_mode == 1 || P.n_expect > 0) lw_old = P.logw[i];
+
+        // ---- program ----------------------------------------------------------------------
+        double acc = 0.0;
+        const uint64_t particle = (uint64_t)(P.particle_offset + i);
+        for (int pc = 0; pc < P.n_ops; ++pc) {
+            ws_vm_exec<WS_VM_BLOCK>(P.ops[pc], R, acc, P.rng, particle);
+        }
+
+        // ---- stores -----------------------------------------------------------------------
+        for (int k = 0; k < P.n_stores; ++k) P.store_ptr[k][i] = R[(int)P.store_reg[k] * WS_VM_BLOCK];
+        if (P.logw_mode != 0) {
+            const double lw = (P.logw_mode == 1 ? lw_old : P.logw_base) + acc;
+            P.logw[i] = lw;
+            lse_push(part, lw);
+        }
+        if (P.n_expect > 0) {
+            const double w = exp(lw_old - red_m) * red_invS;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (k < P.n_expect) esum[k] += w * R[(int)P.expect_reg[k] * WS_VM_BLOCK];
+            }
+        }
+    }
+
+    if (P.logw_mode != 0 && P.partials != nullptr) {
+        WsLse tot = lse_block_reduce<WS_VM_BLOCK>(part, warp_scratch);
+        if (threadIdx.x == 0) P.partials[blockIdx.x] = tot;
+    }
+    if (P.n_expect > 0) {
+        __shared__ double esc[WS_VM_BLOCK / 32][8];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double v = esum[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+            if (lane == 0) esc[warp][k] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 8 && threadIdx.x < P.n_expect) {
+            double v = 0.0;
+            for (int w = 0; w < WS_VM_BLOCK / 32; ++w) v += esc[w][threadIdx.x];
+            P.expect_partials[(size_t)blockIdx.x * P.n_expect + threadIdx.x] = v;
+        }
+    }
+}
+
+int ws_vm_smem_bytes(int n_regs) { return (n_regs < 1 ? 1 : n_regs) * WS_VM_BLOCK * (int)sizeof(double); }
+
+int ws_vm_max_grid(int n_regs, int sm_count) {
+    // resident CTAs per SM limited by the shared-memory register file and 2048 threads / SM
+    const int smem = ws_vm_smem_bytes(n_regs) + 1024;
+    int per_sm = (227 * 1024) / smem;
+    if (per_sm > 2048 / WS_VM_BLOCK) per_sm = 2048 / WS_VM_BLOCK;
+    if (per_sm < 1) per_sm = 1;
+    return per_sm * sm_count;
+}
+
+cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
+    const int smem = ws_vm_smem_bytes(P.n_regs);
+    ws_vm_kernel<<<grid, WS_VM_BLOCK, smem, s>>>(P);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone (m, S, Q) partials + finalize
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ws_reduce_logw_kernel(const double* __restrict__ logw, int64_t n,
+                                                             WsLse* __restrict__ partials) {
+    __shared__ WsLse warp_scratch[8];
+    WsLse part;
+    part.m = -INFINITY;
+    part.S = 0.0;
+    part.Q = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) lse_push(part, __ldg(logw + i));
+    WsLse tot = lse_block_reduce<256>(part, warp_scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
+cudaError_t ws_launch_reduce_logw(const double* logw, int64_t n, WsLse* partials, int grid, cudaStream_t s) {
+    ws_reduce_logw_kernel<<<grid, 256, 0, s>>>(logw, n, partials);
+    return cudaGetLastError();
+}
+
+// One CTA; fixed combination order => the decision is deterministic for a given grid size.
+__global__ void __launch_bounds__(256) ws_finalize_kernel(const WsLse* __restrict__ partials, int n_partials,
+                                                          int64_t n_global, double ess_perc_min,
+                                                          WsReduceOut* __restrict__ out) {
+    __shared__ WsLse warp_scratch[8];
+    WsLse part;
+    part.m = -INFINITY;
+    part.S = 0.0;
+    part.Q = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += 256) part = lse_combine(part, partials[i]);
+    WsLse tot = lse_block_reduce<256>(part, warp_scratch);
+    if (threadIdx.x == 0) {
+        out->m = tot.m;
+        out->S = tot.S;
+        out->Q = tot.Q;
+        const double lse = tot.m + log(tot.S);
+        out->lse = lse;
+        const double nn = (double)n_global;
+        out->ess_perc = (tot.S * tot.S) / (nn * tot.Q);  // 1 / (N * sum w^2), w = e / S
+        out->log_mean_w = lse - log(nn);
+        out->do_resample = (out->ess_perc < ess_perc_min) ? 1 : 0;  // NaN compares false, as in Julia
+    }
+}
+
+cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min,
+                               WsReduceOut* out, cudaStream_t s) {
+    ws_finalize_kernel<<<1, 256, 0, s>>>(partials, n_partials, n_global, ess_perc_min, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// CDF scan fused with the ancestor search
+// ------------------------------------------------------------------------------------------
+#define WS_FXS_SCALE 2305843009213693952.0 /* 2^61: two top bits of the tile word carry the status */
+#define WS_FXS_MASK 0x3FFFFFFFFFFFFFFFull
+#define WS_TILE_AGG 1ull
+#define WS_TILE_INCL 2ull
+
+__device__ __forceinline__ unsigned long long ws_w_to_fxs(double w) {
+    if (!(w > 0.0)) return 0ull;
+    if (w >= 1.0) return 1ull << 61;
+    return __double2ull_rn(w * WS_FXS_SCALE);
+}
+__device__ __forceinline__ double ws_fxs_to_double(unsigned long long c) { return (double)c * (1.0 / WS_FXS_SCALE); }
+
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// slot -> uniform providers
+struct RStratified {
+    uint64_t seed, stream;
+    const double* replay;
+    __device__ __forceinline__ double operator()(int64_t k) const {
+        if (replay != nullptr) return replay[k];
+        ws_u32x4 r = ws_philox4x32_10((uint64_t)k, stream, seed);
+        return ws_u01(r.x, r.y);
+    }
+};
+struct RSystematic {
+    double r0;
+    __device__ __forceinline__ double operator()(int64_t) const { return r0; }
+};
+
+// F(C) for an arbitrary ascending uniform array: #{n : u_n <= C}  (icdf with caller uniforms, multinomial)
+__device__ __forceinline__ int64_t ws_count_sorted_le(const double* __restrict__ us, int64_t n, double C) {
+    int64_t lo = 0, hi = n;  // first index with us[idx] > C
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(us + mid) <= C) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double inv_n, double r0) {
+    if (P.sorted_u != nullptr) return ws_count_sorted_le(P.sorted_u, P.n, C);
+    if (P.scheme == 1) {
+        RSystematic r{r0};
+        return ws_count_slots_le(C, P.n, inv_n, r);
+    }
+    RStratified r{P.seed, P.stream, P.replay_u};
+    return ws_count_slots_le(C, P.n, inv_n, r);
+}
+
+__global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+
+    __shared__ int32_t Fs[WS_SCAN_TILE];                     // F(C_m) for the tile's particles
+    __shared__ unsigned long long warp_tot[WS_SCAN_BLOCK / 32];
+    __shared__ unsigned long long s_excl;                    // tile exclusive prefix (fixed point)
+    __shared__ int s_tile;
+    __shared__ int64_t s_fstart;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = P.n;
+    const int n_tiles = (int)((n + WS_SCAN_TILE - 1) / WS_SCAN_TILE);
+    const double inv_n = 1.0 / (double)n;
+    double m = 0.0, Sden = 1.0;
+    if (P.mode == 0) {
+        m = P.red->m;
+        Sden = P.red->S;  // divide (not multiply by a reciprocal): w = e / S as exp_norm does
+    }
+    double r0 = 0.0;
+    if (P.scheme == 1 && P.sorted_u == nullptr) {
+        if (P.replay_u != nullptr) {
+            r0 = P.replay_u[0];
+        } else {
+            ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
+            r0 = ws_u01(r.x, r.y);
+        }
+    }
+    const double uniform_w = 1.0 / (double)n;
+
+    while (true) {
+        __syncthreads();  // protects s_tile / Fs reuse across iterations
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= n_tiles) break;
+        const int64_t tile_base = (int64_t)tile * WS_SCAN_TILE;
+        const int64_t item0 = tile_base + (int64_t)threadIdx.x * WS_SCAN_ITEMS;
+
+        // ---- weights -> fixed point, thread-local inclusive sums -----------------------------
+        unsigned long long q[WS_SCAN_ITEMS];
+        if (P.mode == 2) {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(uniform_w) : 0ull;
+        } else {
+            double l[WS_SCAN_ITEMS];
+            if (item0 + WS_SCAN_ITEMS <= n) {
+                const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                    double2 v = __ldg(p2 + k);
+                    l[2 * k] = v.x;
+                    l[2 * k + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : -INFINITY;
+            }
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                double w;
+                if (P.mode == 0) {
+                    w = exp(l[k] - m) / Sden;
+                } else {
+                    w = (item0 + k < n) ? l[k] : 0.0;
+                }
+                q[k] = (item0 + k < n) ? ws_w_to_fxs(w) : 0ull;
+            }
+        }
+#pragma unroll
+        for (int k = 1; k < WS_SCAN_ITEMS; ++k) q[k] += q[k - 1];
+        const unsigned long long thread_total = q[WS_SCAN_ITEMS - 1];
+
+        // ---- block exclusive scan of thread totals -----------------------------------------------
+        unsigned long long incl = thread_total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long warp_excl = 0ull, tile_agg = 0ull;
+#pragma unroll
+        for (int w = 0; w < WS_SCAN_BLOCK / 32; ++w) {
+            const unsigned long long t = warp_tot[w];
+            if (w < warp) warp_excl += t;
+            tile_agg += t;
+        }
+        const unsigned long long thread_excl = warp_excl + (incl - thread_total);
+
+        // ---- decoupled look-back (warp 0) ------------------------------------------------------
+        if (warp == 0) {
+            unsigned long long excl = 0ull;
+            if (tile == 0) {
+                if (lane == 0) st_relaxed_u64(P.tile_words + 0, (WS_TILE_INCL << 62) | tile_agg);
+            } else {
+                if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_AGG << 62) | tile_agg);
+                int base = tile - 1;
+                while (true) {
+                    const int idx = base - lane;
+                    unsigned long long w;
+                    if (idx >= 0) {
+                        do {
+                            w = ld_relaxed_u64(P.tile_words + idx);
+                        } while ((w >> 62) == 0ull);
+                    } else {
+                        w = (WS_TILE_INCL << 62);  // virtual tile -1: inclusive prefix 0
+                    }
+                    const unsigned incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == WS_TILE_INCL);
+                    unsigned long long val = w & WS_FXS_MASK;
+                    if (incl_mask != 0u) {
+                        const int first = __ffs(incl_mask) - 1;
+                        if (lane > first) val = 0ull;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                    excl += val;
+                    if (incl_mask != 0u) break;
+                    base -= 32;
+                }
+                if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_INCL << 62) | (excl + tile_agg));
+            }
+            if (lane == 0) {
+                s_excl = excl;
+                // F at the tile's left edge; by definition 0 for the first particle (a slot with
+                // u = 0 belongs to particle 1, as in icdf)
+                s_fstart = (tile == 0) ? 0 : ws_F(P, ws_fxs_to_double(excl), inv_n, r0);
+            }
+        }
+        __syncthreads();
+        const unsigned long long tile_excl = s_excl;
+        const int64_t fstart = s_fstart;
+
+        // ---- per-particle F(C_m) -----------------------------------------------------------------
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            const int64_t gi = item0 + k;
+            int64_t f;
+            if (gi >= n) {
+                f = n;
+            } else if (gi == n - 1) {
+                const int64_t ff = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, r0);
+                if (ff < n) atomicAdd(P.n_clamped, (unsigned long long)(n - ff));
+                f = n;  // leftover slots go to the last particle (the reference would throw BoundsError)
+            } else {
+                f = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, r0);
+            }
+            Fs[threadIdx.x * WS_SCAN_ITEMS + k] = (int32_t)f;
+        }
+        __syncthreads();
+        const int64_t fend = (int64_t)Fs[WS_SCAN_TILE - 1];
+
+        // ---- expand: every output slot of this tile finds its ancestor by binary search ----------
+        for (int64_t j = fstart + threadIdx.x; j < fend; j += WS_SCAN_BLOCK) {
+            int lo = 0, hi = WS_SCAN_TILE - 1;  // smallest k with Fs[k] > j  (exists: Fs[last] = fend > j)
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if ((int64_t)Fs[mid] > j) hi = mid; else lo = mid + 1;
+            }
+            P.ancestors[j] = (int32_t)(tile_base + lo);
+        }
+    }
+}
+
+cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
+    ws_scan_search_kernel<<<grid, WS_SCAN_BLOCK, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Ancestor gather (resample!)
+// ------------------------------------------------------------------------------------------
+// dst[p][i] = src[p][a_i].  Ancestors are non-decreasing, so neighbouring threads read the same or
+// neighbouring sectors: the reads coalesce in L1/L2 and DRAM sees each live source sector once.
+__global__ void __launch_bounds__(256) ws_gather_kernel(const __grid_constant__ WsGatherParams P) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < P.n; i += stride) {
+        const int64_t a = (int64_t)__ldg(P.ancestors + i);
+        for (int p0 = 0; p0 < P.n_planes; p0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (p0 + k < P.n_planes) v[k] = __ldg(P.src[p0 + k] + a);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (p0 + k < P.n_planes) P.dst[p0 + k][i] = v[k];
+        }
+    }
+}
+
+cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s) {
+    ws_gather_kernel<<<grid, 256, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+__global__ void ws_fill_kernel(double* __restrict__ dst, double v, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
+}
+cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStream_t s) {
+    ws_fill_kernel<<<grid, 256, 0, s>>>(dst, v, n);
+    return cudaGetLastError();
+}
+
+// exp_norm: w_i = exp(l_i - m) / S  (src/resampling.jl:72-77)
+__global__ void ws_exp_norm_kernel(const double* __restrict__ logw, const WsReduceOut* __restrict__ red,
+                                   double* __restrict__ w, int64_t n) {
+    const double m = red->m, S = red->S;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = exp(logw[i] - m) / S;
+}
+cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,
+                               cudaStream_t s) {
+    ws_exp_norm_kernel<<<grid, 256, 0, s>>>(logw, red, w, n);
+    return cudaGetLastError();
+}
+
+// sum of squares partials (ess_perc on a caller-supplied weight vector; src/resampling.jl:51-54)
+__global__ void __launch_bounds__(256) ws_sumsq_kernel(const double* __restrict__ w, int64_t n,
+                                                       double* __restrict__ partials) {
+    __shared__ double sc[8];
+    double acc = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const double v = w[i];
+        acc += v * v;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d);
+    if ((threadIdx.x & 31) == 0) sc[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += sc[k];
+        partials[blockIdx.x] = t;
+    }
+}
+cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int grid, cudaStream_t s) {
+    ws_sumsq_kernel<<<grid, 256, 0, s>>>(w, n, partials);
+    return cudaGetLastError();
+}
+
+__global__ void ws_gather_rows_kernel(const double* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_idx,
+                                      double* __restrict__ dst) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_idx; i += stride) dst[i] = src[idx[i]];
+}
+cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t n_idx, double* dst, cudaStream_t s) {
+    int grid = (int)((n_idx + 255) / 256);
+    if (grid > g_sm_count * 8) grid = g_sm_count * 8;
+    if (grid < 1) grid = 1;
+    ws_gather_rows_kernel<<<grid, 256, 0, s>>>(src, idx, n_idx, dst);
+    return cudaGetLastError();
+}
+
+cudaError_t ws_kernels_init(int device) {
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return e;
+    g_sm_count = prop.multiProcessorCount;
+    // the register file of the fused pass can take most of the SM's shared memory
+    e = cudaFuncSetAttribute(ws_vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
+}

@@ -1,0 +1,299 @@
+// ws_kernels_move.cu — score-tape fold and fused Metropolis-Hastings move kernels.
+//
+//   ws_score_kernel         score_logpdf(state, targets, depth)            src/types.jl:183-206
+//   ws_move_kernel          Move.apply!: propose / score old / score new / accept-or-restore in
+//                           one pass                                       src/transformers.jl:588-623
+//                           RW / autoRW proposals and bound transforms      src/move_kernels.jl:37-85,161-253
+//   ws_move_moments_kernel  weighted mean / covariance of the (unconstrained) targets for autoRW
+//                                                                          src/move_kernels.jl:144-151
+//   ws_unique_count_kernel  exact distinct-value count for marginal_diversity
+//                                                                          src/transformers.jl:560-565
+//
+// The fold is FP64-ALU bound for long tapes (one thread per particle walks k tape entries; the
+// particle's planes sit in the shared-memory register file, the micro-ops are fetched with
+// warp-uniform loads that hit L1/L2), so it is reported against FP64 issue rate, not HBM.
+#include "ws_move.h"
+
+__device__ __forceinline__ WsOp ws_load_op(const WsOp* __restrict__ ops, int pc) {
+    // two warp-uniform 16-byte loads
+    const uint4* p = reinterpret_cast<const uint4*>(ops + pc);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    WsOp o;
+    o.w0 = a.x;
+    o.w1 = a.y;
+    o.k0 = __hiloint2double((int)a.w, (int)a.z);
+    o.k1 = __hiloint2double((int)b.y, (int)b.x);
+    o.k2 = __hiloint2double((int)b.w, (int)b.z);
+    return o;
+}
+
+__device__ __forceinline__ void ws_score_load_planes(const WsScoreParams& S, double* R, int64_t i) {
+    int k = 0;
+    for (; k + 4 <= S.n_loads; k += 4) {
+        double t0 = __ldg(S.load_ptr[k] + i), t1 = __ldg(S.load_ptr[k + 1] + i);
+        double t2 = __ldg(S.load_ptr[k + 2] + i), t3 = __ldg(S.load_ptr[k + 3] + i);
+        R[(int)S.load_reg[k] * WS_MOVE_BLOCK] = t0;
+        R[(int)S.load_reg[k + 1] * WS_MOVE_BLOCK] = t1;
+        R[(int)S.load_reg[k + 2] * WS_MOVE_BLOCK] = t2;
+        R[(int)S.load_reg[k + 3] * WS_MOVE_BLOCK] = t3;
+    }
+    for (; k < S.n_loads; ++k) R[(int)S.load_reg[k] * WS_MOVE_BLOCK] = __ldg(S.load_ptr[k] + i);
+}
+
+__device__ __forceinline__ double ws_score_fold(const WsScoreParams& S, double* R, uint64_t particle) {
+    double acc = 0.0;
+    WsRng none;
+    none.seed = 0;
+    none.replay_n = nullptr;
+    none.replay_u = nullptr;
+    none.replay_e = nullptr;
+    for (int pc = 0; pc < S.n_ops; ++pc) {
+        const WsOp o = ws_load_op(S.ops, pc);
+        ws_vm_exec<WS_MOVE_BLOCK>(o, R, acc, none, particle);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_score_kernel(const __grid_constant__ WsScoreParams S) {
+    extern __shared__ double ws_score_smem[];
+    double* R = ws_score_smem + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * WS_MOVE_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * WS_MOVE_BLOCK + threadIdx.x; i < S.n; i += stride) {
+        ws_score_load_planes(S, R, i);
+        S.score_out[i] = ws_score_fold(S, R, (uint64_t)(S.particle_offset + i));
+    }
+}
+
+__global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_kernel(const __grid_constant__ WsMoveParams M) {
+    extern __shared__ double ws_score_smem[];
+    double* R = ws_score_smem + threadIdx.x;
+    const WsScoreParams& S = M.score;
+    const int d = M.d;
+    unsigned long long accepted = 0ull;
+    const int64_t stride = (int64_t)gridDim.x * WS_MOVE_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * WS_MOVE_BLOCK + threadIdx.x; i < S.n; i += stride) {
+        const uint64_t particle = (uint64_t)(S.particle_offset + i);
+        ws_score_load_planes(S, R, i);
+
+        // ---- current values, unconstrained coordinates, proposal ---------------------------------
+        double x_old[WS_MOVE_MAX_D], z_old[WS_MOVE_MAX_D], xi[WS_MOVE_MAX_D], x_new[WS_MOVE_MAX_D];
+#pragma unroll
+        for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
+            if (t < d) {
+                x_old[t] = M.target_ptr[t][i];
+                z_old[t] = ws_to_unconstrained(x_old[t], M.lo[t], M.hi[t], M.bound_kind[t]);
+            }
+        }
+        if (M.rng.replay_n != nullptr) {
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
+                if (t < d) {
+                    const int64_t idx = M.normals_target_major ? (M.replay_n_base + (int64_t)t * M.n_global + (int64_t)particle)
+                                                               : (M.replay_n_base + (int64_t)particle * d + t);
+                    xi[t] = M.rng.replay_n[idx];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; t += 2) {
+                if (t < d) {
+                    double a, b;
+                    ws_randn2(particle, M.stream_normals + (uint64_t)(t >> 1), M.rng.seed, a, b);
+                    xi[t] = a;
+                    if (t + 1 < WS_MOVE_MAX_D) xi[t + 1] = b;
+                }
+            }
+        }
+        double lpr = 0.0;
+#pragma unroll
+        for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
+            if (t < d) {
+                // sequential, un-contracted sum so that a replayed proposal is bit-identical to
+                // the reference's  z .+ (L * xi)  (no FMA in Julia)
+                double delta = __dmul_rn(M.L[t * d], xi[0]);
+#pragma unroll
+                for (int k = 1; k < WS_MOVE_MAX_D; ++k)
+                    if (k <= t && k < d) delta = __dadd_rn(delta, __dmul_rn(M.L[t * d + k], xi[k]));
+                const double zn = __dadd_rn(z_old[t], delta);
+                x_new[t] = ws_from_unconstrained(zn, M.lo[t], M.hi[t], M.bound_kind[t]);
+                lpr += ws_log_abs_jacobian(zn, M.lo[t], M.hi[t], M.bound_kind[t]) -
+                       ws_log_abs_jacobian(z_old[t], M.lo[t], M.hi[t], M.bound_kind[t]);
+            }
+        }
+
+        // ---- trace density at the old and at the proposed values ------------------------------------
+        const double s_old = ws_score_fold(S, R, particle);
+#pragma unroll
+        for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+            if (t < d && M.target_reg[t] != 0xFF) R[(int)M.target_reg[t] * WS_MOVE_BLOCK] = x_new[t];
+        const double s_new = ws_score_fold(S, R, particle);
+
+        // ---- accept / reject (NaN ratio rejects: !(log u < ...)) ---------------------------------------
+        double u;
+        if (M.rng.replay_u != nullptr) {
+            u = M.rng.replay_u[M.replay_u_base + (int64_t)particle];
+        } else {
+            ws_u32x4 r = ws_philox4x32_10(particle, M.stream_uniform, M.rng.seed);
+            u = ws_u01(r.x, r.y);
+        }
+        if (log(u) < lpr + s_new - s_old) {
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+                if (t < d) M.target_ptr[t][i] = x_new[t];
+            ++accepted;
+        }
+    }
+    // one atomic per warp
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) accepted += __shfl_down_sync(0xffffffffu, accepted, dlt);
+    if ((threadIdx.x & 31) == 0 && accepted != 0ull) atomicAdd(M.n_accept, accepted);
+}
+
+// ------------------------------------------------------------------------------------------
+// autoRW moments.  pass 0: [sum w, sum w z_t];  pass 1: [-, -, sum w (z_i - m_i)(z_j - m_j) (j <= i)]
+// Output layout per CTA: n_mom = 1 + d + d(d+1)/2 doubles.
+// ------------------------------------------------------------------------------------------
+#define WS_MOM_MAX (1 + WS_MOVE_MAX_D + WS_MOVE_MAX_D * (WS_MOVE_MAX_D + 1) / 2)
+
+__global__ void __launch_bounds__(256) ws_move_moments_kernel(const __grid_constant__ WsMoveParams M, int64_t n, int pass,
+                                                              double* __restrict__ partials) {
+    const int d = M.d;
+    const int n_mom = 1 + d + d * (d + 1) / 2;
+    double acc[WS_MOM_MAX];
+#pragma unroll
+    for (int k = 0; k < WS_MOM_MAX; ++k) acc[k] = 0.0;
+    double m = 0.0, S = 1.0;
+    if (!M.w_uniform) {
+        m = M.red->m;
+        S = M.red->S;
+    }
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const double w = M.w_uniform ? 1.0 : exp(M.logw[i] - m) / S;
+        double z[WS_MOVE_MAX_D];
+#pragma unroll
+        for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+            if (t < d) z[t] = ws_to_unconstrained(M.target_ptr[t][i], M.lo[t], M.hi[t], M.bound_kind[t]);
+        if (pass == 0) {
+            acc[0] += w;
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+                if (t < d) acc[1 + t] += w * z[t];
+        } else {
+            int k = 1 + d;
+#pragma unroll
+            for (int a = 0; a < WS_MOVE_MAX_D; ++a) {
+#pragma unroll
+                for (int b = 0; b < WS_MOVE_MAX_D; ++b) {
+                    if (a < d && b <= a) {
+                        acc[k] += w * (z[a] - M.mean[a]) * (z[b] - M.mean[b]);
+                        ++k;
+                    }
+                }
+            }
+        }
+    }
+    __shared__ double sc[8][WS_MOM_MAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int k = 0; k < n_mom; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int dlt = 16; dlt > 0; dlt >>= 1) v += __shfl_down_sync(0xffffffffu, v, dlt);
+        if (lane == 0) sc[warp][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_mom) {
+        double v = 0.0;
+        for (int w = 0; w < 8; ++w) v += sc[w][threadIdx.x];
+        partials[(size_t)blockIdx.x * n_mom + threadIdx.x] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exact distinct count: lock-free open-addressing set keyed by the value's bit pattern.
+// Julia's unique() compares with isequal: every NaN is one value, -0.0 and 0.0 are two.
+// ------------------------------------------------------------------------------------------
+#define WS_SET_EMPTY 0xFFFFFFFFFFFFFFFFull
+
+__global__ void __launch_bounds__(256) ws_unique_count_kernel(const double* __restrict__ plane, int64_t n,
+                                                              unsigned long long* __restrict__ table, size_t mask,
+                                                              unsigned long long* __restrict__ counter) {
+    unsigned long long fresh = 0ull;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const double v = plane[i];
+        unsigned long long key = (v != v) ? 0x7FF8000000000000ull : (unsigned long long)__double_as_longlong(v);
+        if (i > 0) {
+            // resampled copies sit next to each other (ancestors are sorted): skip exact repeats
+            const double pv = plane[i - 1];
+            const unsigned long long pkey = (pv != pv) ? 0x7FF8000000000000ull : (unsigned long long)__double_as_longlong(pv);
+            if (pkey == key) continue;
+        }
+        unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 29;
+        size_t slot = (size_t)h & mask;
+        while (true) {
+            const unsigned long long old = atomicCAS(table + slot, WS_SET_EMPTY, key);
+            if (old == WS_SET_EMPTY) {
+                ++fresh;
+                break;
+            }
+            if (old == key) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) fresh += __shfl_down_sync(0xffffffffu, fresh, dlt);
+    if ((threadIdx.x & 31) == 0 && fresh != 0ull) atomicAdd(counter, fresh);
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+static int score_grid(int n_regs, int64_t n, int sm_count) {
+    const int smem = n_regs * WS_MOVE_BLOCK * (int)sizeof(double) + 256;
+    int per_sm = (227 * 1024) / smem;
+    if (per_sm > 2048 / WS_MOVE_BLOCK) per_sm = 2048 / WS_MOVE_BLOCK;
+    if (per_sm < 1) per_sm = 1;
+    int64_t g = (n + WS_MOVE_BLOCK - 1) / WS_MOVE_BLOCK;
+    if (g > (int64_t)per_sm * sm_count) g = (int64_t)per_sm * sm_count;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+cudaError_t ws_launch_score(const WsScoreParams& S, int sm_count, cudaStream_t s) {
+    const int smem = S.n_regs * WS_MOVE_BLOCK * (int)sizeof(double);
+    ws_score_kernel<<<score_grid(S.n_regs, S.n, sm_count), WS_MOVE_BLOCK, smem, s>>>(S);
+    return cudaGetLastError();
+}
+
+cudaError_t ws_launch_move(const WsMoveParams& M, int sm_count, cudaStream_t s) {
+    const int smem = M.score.n_regs * WS_MOVE_BLOCK * (int)sizeof(double);
+    ws_move_kernel<<<score_grid(M.score.n_regs, M.score.n, sm_count), WS_MOVE_BLOCK, smem, s>>>(M);
+    return cudaGetLastError();
+}
+
+cudaError_t ws_launch_move_moments(const WsMoveParams& M, int64_t n, int pass, double* partials, int grid, cudaStream_t s) {
+    ws_move_moments_kernel<<<grid, 256, 0, s>>>(M, n, pass, partials);
+    return cudaGetLastError();
+}
+
+cudaError_t ws_launch_unique_count(const double* plane, int64_t n, unsigned long long* table, size_t slots,
+                                   unsigned long long* counter, int sm_count, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(table, 0xFF, sizeof(unsigned long long) * slots, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    int64_t g = (n + 255) / 256;
+    if (g > (int64_t)sm_count * 8) g = (int64_t)sm_count * 8;
+    if (g < 1) g = 1;
+    ws_unique_count_kernel<<<(int)g, 256, 0, s>>>(plane, n, table, slots - 1, counter);
+    return cudaGetLastError();
+}
+
+cudaError_t ws_move_kernels_init(int device) {
+    (void)device;
+    cudaError_t e = cudaFuncSetAttribute(ws_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ws_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+}

@@ -1,0 +1,1611 @@
+// ws_runtime.cu — the C ABI of include/wsb200.h: device-resident SMCState + ColumnStore, the
+// statement fusion queue, the Resample state machine and the analysis reductions.
+//
+// Reference map (all under /root/reference/src):
+//   ws_ctx                      SMCState + ColumnStore                 types.jl:48-78, stores.jl:70-111
+//   statement calls             apply!(::Assign/Sample/Observe/Weight) transformers.jl:28-32,172-182,228-235,283-289
+//   ws_resample                 apply!(::Resample)                     transformers.jl:474-498
+//   ws_exp_norm/ws_log_evidence exp_norm, logsumexp, ess_perc          resampling.jl:51-77, utils.jl:21
+//   ws_move                     apply!(::Move), RW, autoRW             transformers.jl:588-623, move_kernels.jl:189-253
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/wsb200.h"
+#include "ws_internal.h"
+#include "ws_lowering.h"
+#include "ws_move.h"
+
+using wsl::Plane;
+using wsl::Program;
+using wsl::Val;
+
+static thread_local std::string g_create_error;
+
+enum WsKernelClass { KC_VM = 0, KC_REDUCE, KC_FINALIZE, KC_SCAN, KC_GATHER, KC_FILL, KC_MOVE, KC_OTHER, KC_COUNT };
+
+struct Column {
+    std::string name;
+    int32_t width;
+    std::vector<double*> front, back;
+};
+
+struct TimedEvent {
+    int kclass;
+    cudaEvent_t a, b;
+};
+
+struct TapeEntry {
+    int64_t depth;   // state.depth before the statement ran (it is scored iff depth < target_depth)
+    int32_t op_end;  // score_prog.ops[0 .. op_end) covers the tape up to and including this entry
+};
+
+struct ws_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int64_t n = 0;         // local particles
+    int64_t n_global = 0;
+    int64_t offset = 0;    // global index of local particle 0
+    int rank = 0, nranks = 1;
+    uint64_t seed = 0;
+    uint64_t next_stream = 1;
+    double ess_perc_min = 0.5;
+    int resampler = WS_RESAMPLER_STRATIFIED;
+
+    // SMCState scalars
+    bool resampled = false, weights_changed = false;
+    int64_t depth = 0;
+
+    // store
+    std::vector<Column> cols;
+    std::map<std::string, int32_t> col_index;
+
+    // log-weights
+    double* logw = nullptr;
+    bool logw_uniform = true;  // every entry equals logw_base (the array itself may be stale)
+    double logw_base = 0.0;
+    bool partials_valid = false;
+    int n_partials = 0;
+    WsLse* d_partials = nullptr;
+    WsReduceOut* d_red = nullptr;
+    WsReduceOut* h_red = nullptr;  // pinned
+    bool red_valid = false;        // h_red/d_red describe the current log-weights
+
+    // resampling scratch
+    int32_t* d_anc = nullptr;
+    unsigned long long* d_tile_words = nullptr;
+    unsigned int* d_tile_counter = nullptr;
+    int64_t n_tiles = 0;
+    unsigned long long* d_counters = nullptr;  // [0] clamped slots (cumulative), [1] clamped (host-array calls), [2] MH accepts
+
+    // fusion window + score tape
+    Program win;
+    Program score;
+    std::vector<TapeEntry> tape;
+    WsOp* d_score_ops = nullptr;
+    size_t d_score_cap = 0, d_score_uploaded = 0;
+    bool record_only = false;
+    bool tape_enabled = true;
+
+    // replay buffers
+    double* d_replay_n = nullptr;
+    double* d_replay_u = nullptr;
+    double* d_replay_e = nullptr;
+    int64_t replay_n_len = 0, replay_u_len = 0, replay_e_len = 0;
+    int64_t cur_n = 0, cur_u = 0, cur_e = 0;
+
+    // scratch for MH / analysis
+    double* d_scratch = nullptr;
+    size_t scratch_bytes = 0;
+    double* h_scratch = nullptr;  // pinned
+    size_t h_scratch_bytes = 0;
+
+    // stats / timing
+    ws_stats stats{};
+    bool timing = false;
+    std::vector<TimedEvent> pending_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+    double kc_ms[KC_COUNT] = {0};
+    int64_t kc_count[KC_COUNT] = {0};
+
+    std::string err;
+};
+
+// ------------------------------------------------------------------------------------------
+// error helpers
+// ------------------------------------------------------------------------------------------
+static int fail(ws_ctx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c != nullptr) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(c, call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail((c), e__ == cudaErrorMemoryAllocation ? WS_ENOMEM : WS_ECUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                   \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int rc__ = (expr);        \
+        if (rc__ != WS_OK) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// timing
+// ------------------------------------------------------------------------------------------
+static void timed_begin(ws_ctx* c, int kclass, TimedEvent& te) {
+    te.kclass = kclass;
+    te.a = te.b = nullptr;
+    c->stats.kernel_launches++;
+    c->kc_count[kclass]++;
+    if (!c->timing) return;
+    if (c->event_pool.empty()) {
+        cudaEventCreate(&te.a);
+        cudaEventCreate(&te.b);
+    } else {
+        te.a = c->event_pool.back().first;
+        te.b = c->event_pool.back().second;
+        c->event_pool.pop_back();
+    }
+    cudaEventRecord(te.a, c->stream);
+}
+static void timed_end(ws_ctx* c, TimedEvent& te) {
+    if (!c->timing || te.a == nullptr) return;
+    cudaEventRecord(te.b, c->stream);
+    c->pending_events.push_back(te);
+}
+static void resolve_events(ws_ctx* c) {
+    if (c->pending_events.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    for (auto& te : c->pending_events) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, te.a, te.b) == cudaSuccess) c->kc_ms[te.kclass] += (double)ms;
+        c->event_pool.push_back({te.a, te.b});
+    }
+    c->pending_events.clear();
+}
+
+static int grid_for(const ws_ctx* c, int64_t n, int block, int per_sm) {
+    int64_t g = (n + block - 1) / block;
+    int64_t cap = (int64_t)c->sm_count * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+static int ensure_scratch(ws_ctx* c, size_t bytes) {
+    if (c->scratch_bytes >= bytes) return WS_OK;
+    if (c->d_scratch != nullptr) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaFree(c->d_scratch));
+        c->d_scratch = nullptr;
+        c->scratch_bytes = 0;
+    }
+    CK(c, cudaMalloc(&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    return WS_OK;
+}
+static int ensure_h_scratch(ws_ctx* c, size_t bytes) {
+    if (c->h_scratch_bytes >= bytes) return WS_OK;
+    if (c->h_scratch != nullptr) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaFreeHost(c->h_scratch));
+        c->h_scratch = nullptr;
+        c->h_scratch_bytes = 0;
+    }
+    CK(c, cudaMallocHost(&c->h_scratch, bytes));
+    c->h_scratch_bytes = bytes;
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// lifecycle
+// ------------------------------------------------------------------------------------------
+static void reset_window(ws_ctx* c) {
+    c->win = Program();
+    c->win.max_regs = WS_VM_MAX_REGS;
+    c->win.max_ops = WS_VM_MAX_OPS;
+    c->win.max_io = WS_VM_MAX_IO;
+}
+static void reset_score(ws_ctx* c) {
+    c->score = Program();
+    c->score.score_mode = true;
+    c->score.temp_base = 0;
+    c->score.n_temp_slots = WS_SCORE_TEMPS;
+    c->score.max_regs = WS_SCORE_MAX_REGS;
+    c->score.max_ops = 1 << 30;
+    c->score.max_io = 1 << 30;
+    c->tape.clear();
+    c->d_score_uploaded = 0;
+}
+
+extern "C" int ws_abi_version(void) { return WSB200_ABI_VERSION; }
+
+extern "C" int ws_device_count(int* out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        if (out) *out = 0;
+        return fail(nullptr, WS_ENODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    if (out) *out = n;
+    return WS_OK;
+}
+
+extern "C" const char* ws_last_error(const ws_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int nranks, const void* nccl_unique_id,
+                                 int device, uint64_t seed, double ess_perc_min, int resampler) {
+    (void)nccl_unique_id;
+    if (out == nullptr) return fail(nullptr, WS_EINVAL, "ws_create: out is NULL");
+    *out = nullptr;
+    if (n_global <= 0) return fail(nullptr, WS_EINVAL, "ws_create: n_particles must be positive (got %lld)", (long long)n_global);
+    if (n_global >= (int64_t)2147483647) return fail(nullptr, WS_EINVAL, "ws_create: n_particles must be < 2^31 (Int32 ancestors)");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, WS_EINVAL, "ws_create: bad rank %d of %d", rank, nranks);
+    if (nranks > 1) return fail(nullptr, WS_EUNSUPPORTED, "ws_create_sharded: multi-rank resampling is not built yet");
+    if (resampler < 0 || resampler > 2) return fail(nullptr, WS_EINVAL, "ws_create: unknown resampler %d", resampler);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, WS_ENODEVICE, "no CUDA device available (%s); wsb200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(nullptr, WS_EINVAL, "ws_create: device %d out of range (0..%d)", device, ndev - 1);
+
+    ws_ctx* c = new ws_ctx();
+    c->device = device;
+    c->rank = rank;
+    c->nranks = nranks;
+    c->n_global = n_global;
+    const int64_t lo = (n_global * rank) / nranks, hi = (n_global * (rank + 1)) / nranks;
+    c->n = hi - lo;
+    c->offset = lo;
+    c->seed = seed;
+    c->ess_perc_min = ess_perc_min;
+    c->resampler = resampler;
+    reset_window(c);
+    reset_score(c);
+
+#define CKC(call)                                                                                   \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            int rc__ = fail(nullptr, e__ == cudaErrorMemoryAllocation ? WS_ENOMEM : WS_ECUDA, "%s failed: %s", #call, \
+                            cudaGetErrorString(e__));                                               \
+            ws_destroy(c);                                                                          \
+            return rc__;                                                                            \
+        }                                                                                           \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CKC(ws_kernels_init(device));
+    CKC(ws_move_kernels_init(device));
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&c->logw, sizeof(double) * (size_t)c->n));
+    CKC(cudaMalloc(&c->d_partials, sizeof(WsLse) * WS_MAX_PARTIALS));
+    CKC(cudaMalloc(&c->d_red, sizeof(WsReduceOut)));
+    CKC(cudaMemsetAsync(c->d_red, 0, sizeof(WsReduceOut), c->stream));
+    CKC(cudaMallocHost(&c->h_red, sizeof(WsReduceOut)));
+    memset(c->h_red, 0, sizeof(WsReduceOut));
+    CKC(cudaMalloc(&c->d_anc, sizeof(int32_t) * (size_t)c->n));
+    c->n_tiles = (c->n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    CKC(cudaMalloc(&c->d_tile_words, sizeof(unsigned long long) * (size_t)c->n_tiles));
+    CKC(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
+    CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 4));
+    CKC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
+#undef CKC
+    c->logw_uniform = true;
+    c->logw_base = 0.0;
+    *out = c;
+    return WS_OK;
+}
+
+extern "C" int ws_create(ws_ctx** out, int64_t n_particles, int device, uint64_t seed, double ess_perc_min, int resampler) {
+    return ws_create_sharded(out, n_particles, 0, 1, nullptr, device, seed, ess_perc_min, resampler);
+}
+
+extern "C" int ws_nccl_unique_id(void* out128) {
+    (void)out128;
+    return fail(nullptr, WS_EUNSUPPORTED, "ws_nccl_unique_id: multi-rank support is not built yet");
+}
+
+extern "C" int ws_destroy(ws_ctx* c) {
+    if (c == nullptr) return WS_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& col : c->cols) {
+        for (auto p : col.front) cudaFree(p);
+        for (auto p : col.back) cudaFree(p);
+    }
+    cudaFree(c->logw);
+    cudaFree(c->d_partials);
+    cudaFree(c->d_red);
+    if (c->h_red) cudaFreeHost(c->h_red);
+    cudaFree(c->d_anc);
+    cudaFree(c->d_tile_words);
+    cudaFree(c->d_tile_counter);
+    cudaFree(c->d_counters);
+    cudaFree(c->d_score_ops);
+    cudaFree(c->d_replay_n);
+    cudaFree(c->d_replay_u);
+    cudaFree(c->d_replay_e);
+    cudaFree(c->d_scratch);
+    if (c->h_scratch) cudaFreeHost(c->h_scratch);
+    for (auto& te : c->pending_events) {
+        cudaEventDestroy(te.a);
+        cudaEventDestroy(te.b);
+    }
+    for (auto& ev : c->event_pool) {
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fusion window
+// ------------------------------------------------------------------------------------------
+static double* plane_ptr(ws_ctx* c, Plane p) { return c->cols[p.col].front[p.comp]; }
+
+static int check_plane(ws_ctx* c, int32_t col, int32_t comp) {
+    if (col < 0 || col >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", col);
+    if (comp < 0 || comp >= c->cols[col].width)
+        return fail(c, WS_EINVAL, "component %d out of range for column %s (width %d)", comp, c->cols[col].name.c_str(),
+                    c->cols[col].width);
+    return WS_OK;
+}
+static int check_expr(ws_ctx* c, const ws_expr* e, const char* what) {
+    if (e == nullptr || e->toks == nullptr || e->n <= 0) return fail(c, WS_EINVAL, "%s: empty expression", what);
+    for (int i = 0; i < e->n; ++i)
+        if (e->toks[i].op == WS_TOK_PLANE) TRY(check_plane(c, e->toks[i].col, e->toks[i].comp));
+    return WS_OK;
+}
+
+static int flush_window(ws_ctx* c) {
+    Program& w = c->win;
+    if (w.ops.empty() && w.dirty.empty()) {
+        reset_window(c);
+        return WS_OK;
+    }
+    CK(c, cudaSetDevice(c->device));
+    WsVmProgram P;
+    memset(&P, 0, sizeof(P));
+    P.n = c->n;
+    P.particle_offset = c->offset;
+    P.n_ops = (int)w.ops.size();
+    P.n_loads = (int)w.loads.size();
+    P.n_stores = (int)w.dirty.size();
+    P.n_regs = std::max(1, w.high_water);
+    for (int k = 0; k < P.n_loads; ++k) {
+        P.load_ptr[k] = plane_ptr(c, w.loads[k].first);
+        P.load_reg[k] = (uint8_t)w.loads[k].second;
+    }
+    for (int k = 0; k < P.n_stores; ++k) {
+        P.store_ptr[k] = plane_ptr(c, w.dirty[k]);
+        P.store_reg[k] = (uint8_t)w.plane_reg[w.dirty[k]];
+    }
+    P.ancestors = nullptr;
+    P.load_gather = 0u;
+    if (w.has_acc) {
+        P.logw = c->logw;
+        if (c->logw_uniform) {
+            P.logw_mode = 2;
+            P.logw_base = c->logw_base;
+        } else {
+            P.logw_mode = 1;
+        }
+    } else {
+        P.logw_mode = 0;
+    }
+    const int grid = std::min(ws_vm_max_grid(P.n_regs, c->sm_count), (int)((c->n + WS_VM_BLOCK - 1) / WS_VM_BLOCK));
+    P.partials = w.has_acc ? c->d_partials : nullptr;
+    P.n_expect = 0;
+    P.rng.seed = c->seed;
+    P.rng.replay_n = c->d_replay_n;
+    P.rng.replay_u = c->d_replay_u;
+    P.rng.replay_e = c->d_replay_e;
+    memcpy(P.ops, w.ops.data(), sizeof(WsOp) * w.ops.size());
+
+    TimedEvent te;
+    timed_begin(c, KC_VM, te);
+    CK(c, ws_launch_vm(P, std::max(1, grid), c->stream));
+    timed_end(c, te);
+    c->stats.fused_passes++;
+    c->stats.fused_statements += w.n_statements;
+    if (w.has_acc) {
+        c->logw_uniform = false;
+        c->partials_valid = true;
+        c->n_partials = std::max(1, grid);
+        c->red_valid = false;
+    }
+    reset_window(c);
+    return WS_OK;
+}
+
+extern "C" int ws_flush(ws_ctx* c) {
+    if (!c) return WS_EINVAL;
+    return flush_window(c);
+}
+extern "C" int ws_sync(ws_ctx* c) {
+    if (!c) return WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return WS_OK;
+}
+
+// Run `body` against the fusion window; if the window overflows, flush it and lower the statement
+// again into an empty window.
+template <class F>
+static int lower_statement(ws_ctx* c, F body) {
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        Program snapshot = c->win;
+        const uint64_t s_stream = c->next_stream;
+        const int64_t s_n = c->cur_n, s_u = c->cur_u, s_e = c->cur_e;
+        body(c->win);
+        if (!c->win.error.empty()) {
+            std::string m = c->win.error;
+            c->win = snapshot;
+            c->next_stream = s_stream;
+            c->cur_n = s_n;
+            c->cur_u = s_u;
+            c->cur_e = s_e;
+            return fail(c, WS_EINVAL, "%s", m.c_str());
+        }
+        if (!c->win.overflow) {
+            c->win.end_statement();
+            return WS_OK;
+        }
+        c->win = snapshot;
+        c->next_stream = s_stream;
+        c->cur_n = s_n;
+        c->cur_u = s_u;
+        c->cur_e = s_e;
+        if (attempt == 1 || (snapshot.ops.empty() && snapshot.dirty.empty()))
+            return fail(c, WS_EUNSUPPORTED, "statement does not fit one device pass (more than %d micro-ops, %d planes or %d registers)",
+                        WS_VM_MAX_OPS, WS_VM_MAX_IO, WS_VM_MAX_REGS);
+        TRY(flush_window(c));
+    }
+    return WS_OK;
+}
+
+// Append the log-density of a statement to the score tape (device form of score!).
+template <class F>
+static int tape_statement(ws_ctx* c, F body) {
+    if (!c->tape_enabled) return WS_OK;
+    body(c->score);
+    if (!c->score.error.empty()) {
+        std::string m = c->score.error;
+        c->score.error.clear();
+        return fail(c, WS_EINVAL, "%s", m.c_str());
+    }
+    if (c->score.overflow)
+        return fail(c, WS_EUNSUPPORTED, "score tape references more than %d distinct planes", WS_SCORE_MAX_REGS - WS_SCORE_TEMPS);
+    c->score.end_statement();
+    c->tape.push_back(TapeEntry{c->depth, (int32_t)c->score.ops.size()});
+    return WS_OK;
+}
+
+static wsl::RngCursor rng_cursor(ws_ctx* c) {
+    return wsl::RngCursor{&c->next_stream, &c->cur_n, &c->cur_u, &c->cur_e, c->n_global};
+}
+
+static int check_replay(ws_ctx* c) {
+    if (c->d_replay_n != nullptr && c->cur_n > c->replay_n_len)
+        return fail(c, WS_EREPLAY, "replay normals exhausted (%lld needed, %lld installed)", (long long)c->cur_n, (long long)c->replay_n_len);
+    if (c->d_replay_e != nullptr && c->cur_e > c->replay_e_len)
+        return fail(c, WS_EREPLAY, "replay exponentials exhausted (%lld needed, %lld installed)", (long long)c->cur_e, (long long)c->replay_e_len);
+    if (c->d_replay_u != nullptr && c->cur_u > c->replay_u_len)
+        return fail(c, WS_EREPLAY, "replay uniforms exhausted (%lld needed, %lld installed)", (long long)c->cur_u, (long long)c->replay_u_len);
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// state scalars
+// ------------------------------------------------------------------------------------------
+extern "C" int ws_n_particles(const ws_ctx* c, int64_t* n_local, int64_t* n_global) {
+    if (!c) return WS_EINVAL;
+    if (n_local) *n_local = c->n;
+    if (n_global) *n_global = c->n_global;
+    return WS_OK;
+}
+extern "C" int ws_get_flags(ws_ctx* c, int* resampled, int* weights_changed, int64_t* depth) {
+    if (!c) return WS_EINVAL;
+    if (resampled) *resampled = c->resampled ? 1 : 0;
+    if (weights_changed) *weights_changed = c->weights_changed ? 1 : 0;
+    if (depth) *depth = c->depth;
+    return WS_OK;
+}
+extern "C" int ws_set_flags(ws_ctx* c, int resampled, int weights_changed) {
+    if (!c) return WS_EINVAL;
+    c->resampled = resampled != 0;
+    c->weights_changed = weights_changed != 0;
+    return WS_OK;
+}
+extern "C" int ws_set_depth(ws_ctx* c, int64_t depth) {
+    if (!c) return WS_EINVAL;
+    c->depth = depth;
+    return WS_OK;
+}
+extern "C" int ws_set_ess_perc_min(ws_ctx* c, double v) {
+    if (!c) return WS_EINVAL;
+    c->ess_perc_min = v;
+    c->red_valid = false;  // the cached resampling decision depended on the old threshold
+    return WS_OK;
+}
+extern "C" int ws_get_ess_perc_min(const ws_ctx* c, double* out) {
+    if (!c || !out) return WS_EINVAL;
+    *out = c->ess_perc_min;
+    return WS_OK;
+}
+extern "C" int ws_begin_run(ws_ctx* c) {
+    if (!c) return WS_EINVAL;
+    TRY(flush_window(c));
+    c->depth = 0;
+    reset_score(c);
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// store
+// ------------------------------------------------------------------------------------------
+extern "C" int ws_col_ensure(ws_ctx* c, const char* name, int32_t width, int32_t* id_out) {
+    if (!c || !name) return WS_EINVAL;
+    if (width < 1 || width > 4096) return fail(c, WS_EINVAL, "column %s: width %d out of range", name, width);
+    auto it = c->col_index.find(name);
+    if (it != c->col_index.end()) {
+        if (c->cols[it->second].width != width)
+            return fail(c, WS_EINVAL, "column %s already exists with width %d (requested %d)", name, c->cols[it->second].width, width);
+        if (id_out) *id_out = it->second;
+        return WS_OK;
+    }
+    CK(c, cudaSetDevice(c->device));
+    Column col;
+    col.name = name;
+    col.width = width;
+    for (int k = 0; k < width; ++k) {
+        double *f = nullptr, *b = nullptr;
+        CK(c, cudaMalloc(&f, sizeof(double) * (size_t)c->n));
+        CK(c, cudaMalloc(&b, sizeof(double) * (size_t)c->n));
+        CK(c, cudaMemsetAsync(f, 0, sizeof(double) * (size_t)c->n, c->stream));
+        col.front.push_back(f);
+        col.back.push_back(b);
+    }
+    c->cols.push_back(col);
+    const int32_t id = (int32_t)c->cols.size() - 1;
+    c->col_index[name] = id;
+    if (id_out) *id_out = id;
+    return WS_OK;
+}
+extern "C" int ws_col_lookup(const ws_ctx* c, const char* name, int32_t* id_out, int32_t* width_out) {
+    if (!c || !name) return WS_EINVAL;
+    auto it = c->col_index.find(name);
+    if (it == c->col_index.end()) {
+        if (id_out) *id_out = -1;
+        if (width_out) *width_out = 0;
+        return WS_OK;
+    }
+    if (id_out) *id_out = it->second;
+    if (width_out) *width_out = c->cols[it->second].width;
+    return WS_OK;
+}
+extern "C" int ws_col_count(const ws_ctx* c, int32_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    *out = (int32_t)c->cols.size();
+    return WS_OK;
+}
+extern "C" int ws_col_info(const ws_ctx* c, int32_t id, char* name_buf, int32_t name_buf_len, int32_t* width_out) {
+    if (!c) return WS_EINVAL;
+    if (id < 0 || id >= (int32_t)c->cols.size()) return WS_EINVAL;
+    if (name_buf && name_buf_len > 0) {
+        strncpy(name_buf, c->cols[id].name.c_str(), (size_t)name_buf_len - 1);
+        name_buf[name_buf_len - 1] = 0;
+    }
+    if (width_out) *width_out = c->cols[id].width;
+    return WS_OK;
+}
+extern "C" int ws_col_download(ws_ctx* c, int32_t id, double* host_out) {
+    if (!c || !host_out) return WS_EINVAL;
+    if (id < 0 || id >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", id);
+    TRY(flush_window(c));
+    const Column& col = c->cols[id];
+    for (int k = 0; k < col.width; ++k)
+        CK(c, cudaMemcpyAsync(host_out + (size_t)k * c->n, col.front[k], sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(double) * c->n * col.width;
+    return WS_OK;
+}
+extern "C" int ws_col_upload(ws_ctx* c, int32_t id, const double* host_in) {
+    if (!c || !host_in) return WS_EINVAL;
+    if (id < 0 || id >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", id);
+    TRY(flush_window(c));
+    const Column& col = c->cols[id];
+    for (int k = 0; k < col.width; ++k)
+        CK(c, cudaMemcpyAsync(col.front[k], host_in + (size_t)k * c->n, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(double) * c->n * col.width;
+    return WS_OK;
+}
+
+static int materialize_logw(ws_ctx* c) {
+    if (!c->logw_uniform) return WS_OK;
+    TimedEvent te;
+    timed_begin(c, KC_FILL, te);
+    CK(c, ws_launch_fill(c->logw, c->logw_base, c->n, grid_for(c, c->n, 256, 8), c->stream));
+    timed_end(c, te);
+    c->logw_uniform = false;
+    c->partials_valid = false;
+    return WS_OK;
+}
+
+extern "C" int ws_weights_download(ws_ctx* c, double* host_out) {
+    if (!c || !host_out) return WS_EINVAL;
+    TRY(flush_window(c));
+    TRY(materialize_logw(c));
+    CK(c, cudaMemcpyAsync(host_out, c->logw, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(double) * c->n;
+    return WS_OK;
+}
+extern "C" int ws_weights_upload(ws_ctx* c, const double* host_in, int mark_changed) {
+    if (!c || !host_in) return WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaMemcpyAsync(c->logw, host_in, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(double) * c->n;
+    c->logw_uniform = false;
+    c->partials_valid = false;
+    c->red_valid = false;
+    if (mark_changed) c->weights_changed = true;
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// statements
+// ------------------------------------------------------------------------------------------
+extern "C" int ws_assign(ws_ctx* c, int32_t col, int32_t comp, const ws_expr* rhs) {
+    if (!c) return WS_EINVAL;
+    TRY(check_plane(c, col, comp));
+    TRY(check_expr(c, rhs, "ws_assign"));
+    if (!c->record_only) {
+        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_assign(p, Plane{col, comp}, *rhs); }));
+    }
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_assign_vec(ws_ctx* c, int32_t col, int32_t d, const ws_expr* rhs) {
+    if (!c || !rhs) return WS_EINVAL;
+    if (col < 0 || col >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", col);
+    if (d != c->cols[col].width) return fail(c, WS_EINVAL, "ws_assign_vec: %d expressions for column %s of width %d", d, c->cols[col].name.c_str(), c->cols[col].width);
+    for (int j = 0; j < d; ++j) TRY(check_expr(c, &rhs[j], "ws_assign_vec"));
+    if (!c->record_only) {
+        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_assign_vec(p, col, d, rhs); }));
+    }
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_sample_normal(ws_ctx* c, int32_t col, int32_t comp, const ws_expr* mu, const ws_expr* sigma) {
+    if (!c) return WS_EINVAL;
+    TRY(check_plane(c, col, comp));
+    TRY(check_expr(c, mu, "ws_sample_normal(mu)"));
+    TRY(check_expr(c, sigma, "ws_sample_normal(sigma)"));
+    if (!c->record_only) {
+        wsl::RngCursor rc = rng_cursor(c);
+        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_sample_normal(p, rc, Plane{col, comp}, *mu, *sigma); }));
+        TRY(check_replay(c));
+    }
+    TRY(tape_statement(c, [&](Program& p) { wsl::score_sample_normal(p, Plane{col, comp}, *mu, *sigma); }));
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_sample_exponential(ws_ctx* c, int32_t col, int32_t comp, const ws_expr* theta) {
+    if (!c) return WS_EINVAL;
+    TRY(check_plane(c, col, comp));
+    TRY(check_expr(c, theta, "ws_sample_exponential(theta)"));
+    if (!c->record_only) {
+        wsl::RngCursor rc = rng_cursor(c);
+        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_sample_exponential(p, rc, Plane{col, comp}, *theta); }));
+        TRY(check_replay(c));
+    }
+    TRY(tape_statement(c, [&](Program& p) { wsl::score_sample_exponential(p, Plane{col, comp}, *theta); }));
+    c->depth++;
+    return WS_OK;
+}
+
+static int mvn_factors(ws_ctx* c, int d, const double* cov, std::vector<double>& L, std::vector<double>& Linv, double& c0) {
+    if (d < 1 || d > 16) return fail(c, WS_EUNSUPPORTED, "MvNormal dimension %d outside 1..16", d);
+    if (cov == nullptr) return fail(c, WS_EINVAL, "MvNormal: covariance is NULL");
+    if (!wsl::mvnormal_factors(d, cov, L, Linv, c0)) return fail(c, WS_ENUMERIC, "MvNormal: covariance is not positive definite");
+    return WS_OK;
+}
+
+extern "C" int ws_sample_mvnormal(ws_ctx* c, int32_t col, int32_t d, const ws_expr* mu, const double* cov) {
+    if (!c || !mu) return WS_EINVAL;
+    if (col < 0 || col >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", col);
+    if (d != c->cols[col].width) return fail(c, WS_EINVAL, "ws_sample_mvnormal: dimension %d but column %s has width %d", d, c->cols[col].name.c_str(), c->cols[col].width);
+    for (int j = 0; j < d; ++j) TRY(check_expr(c, &mu[j], "ws_sample_mvnormal(mu)"));
+    std::vector<double> L, Linv;
+    double c0;
+    TRY(mvn_factors(c, d, cov, L, Linv, c0));
+    if (!c->record_only) {
+        wsl::RngCursor rc = rng_cursor(c);
+        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_sample_mvnormal(p, rc, col, d, mu, L); }));
+        TRY(check_replay(c));
+    }
+    TRY(tape_statement(c, [&](Program& p) { wsl::score_sample_mvnormal(p, col, d, mu, Linv, c0); }));
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_observe_normal(ws_ctx* c, const ws_expr* obs, const ws_expr* mu, const ws_expr* sigma) {
+    if (!c) return WS_EINVAL;
+    TRY(check_expr(c, obs, "ws_observe_normal(obs)"));
+    TRY(check_expr(c, mu, "ws_observe_normal(mu)"));
+    TRY(check_expr(c, sigma, "ws_observe_normal(sigma)"));
+    auto body = [&](Program& p) { wsl::stmt_observe_normal(p, *obs, *mu, *sigma); };
+    if (!c->record_only) {
+        TRY(lower_statement(c, body));
+        c->weights_changed = true;
+    }
+    TRY(tape_statement(c, body));
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_observe_exponential(ws_ctx* c, const ws_expr* obs, const ws_expr* theta) {
+    if (!c) return WS_EINVAL;
+    TRY(check_expr(c, obs, "ws_observe_exponential(obs)"));
+    TRY(check_expr(c, theta, "ws_observe_exponential(theta)"));
+    auto body = [&](Program& p) { wsl::stmt_observe_exponential(p, *obs, *theta); };
+    if (!c->record_only) {
+        TRY(lower_statement(c, body));
+        c->weights_changed = true;
+    }
+    TRY(tape_statement(c, body));
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_observe_mvnormal(ws_ctx* c, int32_t d, const ws_expr* obs, const ws_expr* mu, const double* cov) {
+    if (!c || !obs || !mu) return WS_EINVAL;
+    std::vector<double> L, Linv;
+    double c0;
+    TRY(mvn_factors(c, d, cov, L, Linv, c0));
+    for (int j = 0; j < d; ++j) {
+        TRY(check_expr(c, &obs[j], "ws_observe_mvnormal(obs)"));
+        TRY(check_expr(c, &mu[j], "ws_observe_mvnormal(mu)"));
+    }
+    auto body = [&](Program& p) { wsl::stmt_observe_mvnormal(p, d, obs, mu, Linv, c0); };
+    if (!c->record_only) {
+        TRY(lower_statement(c, body));
+        c->weights_changed = true;
+    }
+    TRY(tape_statement(c, body));
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_weight_expr(ws_ctx* c, const ws_expr* term) {
+    if (!c) return WS_EINVAL;
+    TRY(check_expr(c, term, "ws_weight_expr"));
+    auto body = [&](Program& p) { wsl::stmt_weight_expr(p, *term); };
+    if (!c->record_only) {
+        TRY(lower_statement(c, body));
+        c->weights_changed = true;
+    }
+    TRY(tape_statement(c, body));
+    c->depth++;
+    return WS_OK;
+}
+
+extern "C" int ws_sample_importance_normal(ws_ctx* c, int32_t col, int32_t comp, double pm, double ps, double tm, double ts) {
+    if (!c) return WS_EINVAL;
+    TRY(check_plane(c, col, comp));
+    if (!(ps > 0.0) || !(ts > 0.0)) return fail(c, WS_EINVAL, "importance_kernel: standard deviations must be positive");
+    if (!c->record_only) {
+        wsl::RngCursor rc = rng_cursor(c);
+        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_importance_normal(p, rc, Plane{col, comp}, pm, ps, tm, ts); }));
+        TRY(check_replay(c));
+        c->weights_changed = true;
+    }
+    TRY(tape_statement(c, [&](Program& p) {
+        p.acc_normal_logpdf(Val::lin(0.0, 1.0, p.reg_for_read(Plane{col, comp})), Val::constant(tm), Val::constant(ts));
+    }));
+    c->depth++;
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// reductions / resampling
+// ------------------------------------------------------------------------------------------
+// Make d_red / h_red describe the current log-weights (m, S, Q, lse, ESS%, decision).
+static int ensure_reduced(ws_ctx* c) {
+    TRY(flush_window(c));
+    if (c->red_valid) return WS_OK;
+    CK(c, cudaSetDevice(c->device));
+    if (c->logw_uniform) TRY(materialize_logw(c));
+    if (!c->partials_valid) {
+        const int grid = std::min(grid_for(c, c->n, 256, 8), WS_MAX_PARTIALS);
+        TimedEvent te;
+        timed_begin(c, KC_REDUCE, te);
+        CK(c, ws_launch_reduce_logw(c->logw, c->n, c->d_partials, grid, c->stream));
+        timed_end(c, te);
+        c->n_partials = grid;
+        c->partials_valid = true;
+    }
+    TimedEvent te;
+    timed_begin(c, KC_FINALIZE, te);
+    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream));
+    timed_end(c, te);
+    CK(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut);
+    c->red_valid = true;
+    return WS_OK;
+}
+
+static int gather_all(ws_ctx* c, const int32_t* d_anc) {
+    // resample!(store, indices): every plane front -> back through the ancestors, then swap
+    std::vector<std::pair<const double*, double*>> planes;
+    for (auto& col : c->cols)
+        for (int k = 0; k < col.width; ++k) planes.push_back({col.front[k], col.back[k]});
+    for (size_t p0 = 0; p0 < planes.size(); p0 += WS_GATHER_MAX_PLANES) {
+        WsGatherParams G;
+        memset(&G, 0, sizeof(G));
+        G.n = c->n;
+        G.ancestors = d_anc;
+        G.n_planes = (int)std::min((size_t)WS_GATHER_MAX_PLANES, planes.size() - p0);
+        for (int k = 0; k < G.n_planes; ++k) {
+            G.src[k] = planes[p0 + k].first;
+            G.dst[k] = planes[p0 + k].second;
+        }
+        TimedEvent te;
+        timed_begin(c, KC_GATHER, te);
+        CK(c, ws_launch_gather(G, grid_for(c, c->n, 256, 8), c->stream));
+        timed_end(c, te);
+    }
+    for (auto& col : c->cols) std::swap(col.front, col.back);
+    return WS_OK;
+}
+
+static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, int64_t n, const double* d_replay_u,
+                           const double* d_sorted_u, int32_t* d_anc, unsigned long long* d_words, uint64_t stream_id,
+                           unsigned long long* d_clamped) {
+    const int64_t n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    CK(c, cudaMemsetAsync(d_words, 0, sizeof(unsigned long long) * (size_t)n_tiles, c->stream));
+    CK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), c->stream));
+    WsScanParams S;
+    memset(&S, 0, sizeof(S));
+    S.logw = d_w;
+    S.mode = mode;
+    S.scheme = scheme;
+    S.red = c->d_red;
+    S.gate = 0;
+    S.n = n;
+    S.seed = c->seed;
+    S.stream = stream_id;
+    S.replay_u = d_replay_u;
+    S.sorted_u = d_sorted_u;
+    S.ancestors = d_anc;
+    S.tile_words = d_words;
+    S.tile_counter = c->d_tile_counter;
+    S.n_clamped = d_clamped;
+    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * 4);
+    TimedEvent te;
+    timed_begin(c, KC_SCAN, te);
+    CK(c, ws_launch_scan_search(S, std::max(1, grid), c->stream));
+    timed_end(c, te);
+    return WS_OK;
+}
+
+extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
+    if (!c) return WS_EINVAL;
+    if (info) {
+        info->fired = 0;
+        info->resampled = c->resampled ? 1 : 0;
+        info->ess_perc = NAN;
+        info->log_mean_w = NAN;
+        info->n_clamped = -1;  // cumulative count is reported by ws_get_clamped (needs a sync)
+    }
+    if (!c->weights_changed) return WS_OK;  // `resampled` keeps its previous value (transformers.jl:475-477)
+    if (c->resampler == WS_RESAMPLER_MULTINOMIAL)
+        return fail(c, WS_EUNSUPPORTED, "multinomial resampling inside run! is not built yet (use ws_resample_host)");
+    TRY(ensure_reduced(c));
+    c->stats.resamples_fired++;
+    const WsReduceOut r = *c->h_red;
+    if (r.do_resample) {
+        // slot uniforms: one per slot (stratified) or one in total (systematic), in replay order
+        const double* d_ru = nullptr;
+        if (c->d_replay_u != nullptr) {
+            const int64_t need = (c->resampler == WS_RESAMPLER_SYSTEMATIC) ? 1 : c->n_global;
+            if (c->cur_u + need > c->replay_u_len)
+                return fail(c, WS_EREPLAY, "replay uniforms exhausted in Resample (%lld needed, %lld installed)",
+                            (long long)(c->cur_u + need), (long long)c->replay_u_len);
+            d_ru = c->d_replay_u + c->cur_u;
+            c->cur_u += need;
+        }
+        const uint64_t stream_id = c->next_stream++;
+        TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, nullptr, c->d_anc, c->d_tile_words, stream_id, c->d_counters + 0));
+        TRY(gather_all(c, c->d_anc));
+        // fill!(state.weights, mean_logW): kept symbolic until somebody reads the array
+        c->logw_uniform = true;
+        c->logw_base = r.log_mean_w;
+        c->partials_valid = false;
+        c->red_valid = false;
+        c->resampled = true;
+        c->stats.resamples_done++;
+    } else {
+        c->resampled = false;
+    }
+    c->weights_changed = false;
+    if (info) {
+        info->fired = 1;
+        info->resampled = c->resampled ? 1 : 0;
+        info->ess_perc = r.ess_perc;
+        info->log_mean_w = r.log_mean_w;
+    }
+    return WS_OK;
+}
+
+extern "C" int ws_gather(ws_ctx* c, const int32_t* ancestors_host) {
+    if (!c || !ancestors_host) return WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaMemcpyAsync(c->d_anc, ancestors_host, sizeof(int32_t) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(int32_t) * c->n;
+    TRY(gather_all(c, c->d_anc));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return WS_OK;
+}
+
+extern "C" int ws_ancestors_download(ws_ctx* c, int32_t* host_out) {
+    if (!c || !host_out) return WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaMemcpyAsync(host_out, c->d_anc, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * c->n;
+    return WS_OK;
+}
+
+extern "C" int ws_log_evidence(ws_ctx* c, double* log_evidence, double* ess_perc) {
+    if (!c) return WS_EINVAL;
+    TRY(flush_window(c));
+    if (c->logw_uniform) {  // logsumexp(fill(c, N)) - log N = c ; ESS% = 1
+        if (log_evidence) *log_evidence = c->logw_base;
+        if (ess_perc) *ess_perc = 1.0;
+        return WS_OK;
+    }
+    TRY(ensure_reduced(c));
+    if (log_evidence) *log_evidence = c->h_red->log_mean_w;
+    if (ess_perc) *ess_perc = c->h_red->ess_perc;
+    return WS_OK;
+}
+
+extern "C" int ws_exp_norm(ws_ctx* c, double* host_out) {
+    if (!c || !host_out) return WS_EINVAL;
+    TRY(ensure_reduced(c));
+    TRY(ensure_scratch(c, sizeof(double) * (size_t)c->n));
+    TimedEvent te;
+    timed_begin(c, KC_OTHER, te);
+    CK(c, ws_launch_exp_norm(c->logw, c->d_red, c->d_scratch, c->n, grid_for(c, c->n, 256, 8), c->stream));
+    timed_end(c, te);
+    CK(c, cudaMemcpyAsync(host_out, c->d_scratch, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(double) * c->n;
+    return WS_OK;
+}
+
+// ---- pure functions on caller arrays ------------------------------------------------------------
+struct TempBuf {
+    void* p = nullptr;
+    ~TempBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+static int reduce_host_array(ws_ctx* c, const double* d_logw, int64_t n) {
+    const int grid = std::min(grid_for(c, n, 256, 8), WS_MAX_PARTIALS);
+    TimedEvent te;
+    timed_begin(c, KC_REDUCE, te);
+    CK(c, ws_launch_reduce_logw(d_logw, n, c->d_partials, grid, c->stream));
+    timed_end(c, te);
+    timed_begin(c, KC_FINALIZE, te);
+    CK(c, ws_launch_finalize(c->d_partials, grid, n, c->ess_perc_min, c->d_red, c->stream));
+    timed_end(c, te);
+    CK(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    // the state's own reduction is no longer what d_red / d_partials hold
+    c->red_valid = false;
+    c->partials_valid = false;
+    return WS_OK;
+}
+
+extern "C" int ws_exp_norm_host(ws_ctx* c, const double* logw, int64_t n, double* w_out) {
+    if (!c || !logw || !w_out || n <= 0) return c ? fail(c, WS_EINVAL, "ws_exp_norm_host: bad arguments") : WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    TempBuf in, out;
+    CK(c, cudaMalloc(&in.p, sizeof(double) * (size_t)n));
+    CK(c, cudaMalloc(&out.p, sizeof(double) * (size_t)n));
+    CK(c, cudaMemcpyAsync(in.p, logw, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    TRY(reduce_host_array(c, (const double*)in.p, n));
+    CK(c, ws_launch_exp_norm((const double*)in.p, c->d_red, (double*)out.p, n, grid_for(c, n, 256, 8), c->stream));
+    c->stats.kernel_launches++;
+    CK(c, cudaMemcpyAsync(w_out, out.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(double) * n;
+    c->stats.d2h_bytes += (int64_t)sizeof(double) * n;
+    return WS_OK;
+}
+
+extern "C" int ws_logsumexp_host(ws_ctx* c, const double* logw, int64_t n, double* out) {
+    if (!c || !logw || !out || n <= 0) return c ? fail(c, WS_EINVAL, "ws_logsumexp_host: bad arguments") : WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    TempBuf in;
+    CK(c, cudaMalloc(&in.p, sizeof(double) * (size_t)n));
+    CK(c, cudaMemcpyAsync(in.p, logw, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    TRY(reduce_host_array(c, (const double*)in.p, n));
+    *out = c->h_red->lse;
+    c->stats.h2d_bytes += (int64_t)sizeof(double) * n;
+    return WS_OK;
+}
+
+extern "C" int ws_ess_perc_host(ws_ctx* c, const double* w, int64_t n, double* out) {
+    if (!c || !w || !out || n <= 0) return c ? fail(c, WS_EINVAL, "ws_ess_perc_host: bad arguments") : WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    TempBuf in, part;
+    const int grid = std::min(grid_for(c, n, 256, 8), WS_MAX_PARTIALS);
+    CK(c, cudaMalloc(&in.p, sizeof(double) * (size_t)n));
+    CK(c, cudaMalloc(&part.p, sizeof(double) * (size_t)grid));
+    CK(c, cudaMemcpyAsync(in.p, w, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, ws_launch_sumsq((const double*)in.p, n, (double*)part.p, grid, c->stream));
+    c->stats.kernel_launches++;
+    std::vector<double> hp(grid);
+    CK(c, cudaMemcpyAsync(hp.data(), part.p, sizeof(double) * (size_t)grid, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    double s = 0.0;
+    for (int i = 0; i < grid; ++i) s += hp[i];
+    *out = 1.0 / ((double)n * s);
+    c->stats.h2d_bytes += (int64_t)sizeof(double) * n;
+    return WS_OK;
+}
+
+static int resample_host_impl(ws_ctx* c, const double* weights, int64_t n, int scheme, const double* uniforms,
+                              int64_t n_uniforms, bool sorted_mode, int32_t* indices_out, int64_t* n_clamped) {
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    if (n >= (int64_t)2147483647) return fail(c, WS_EINVAL, "n must be < 2^31");
+    TempBuf w, u, anc, words;
+    const int64_t n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    CK(c, cudaMalloc(&w.p, sizeof(double) * (size_t)n));
+    CK(c, cudaMalloc(&anc.p, sizeof(int32_t) * (size_t)n));
+    CK(c, cudaMalloc(&words.p, sizeof(unsigned long long) * (size_t)n_tiles));
+    CK(c, cudaMemcpyAsync(w.p, weights, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (uniforms != nullptr) {
+        CK(c, cudaMalloc(&u.p, sizeof(double) * (size_t)n_uniforms));
+        CK(c, cudaMemcpyAsync(u.p, uniforms, sizeof(double) * (size_t)n_uniforms, cudaMemcpyHostToDevice, c->stream));
+    }
+    CK(c, cudaMemsetAsync(c->d_counters + 1, 0, sizeof(unsigned long long), c->stream));
+    const uint64_t stream_id = c->next_stream++;
+    TRY(run_scan_search(c, (const double*)w.p, 1, scheme, n, sorted_mode ? nullptr : (const double*)u.p,
+                        sorted_mode ? (const double*)u.p : nullptr, (int32_t*)anc.p, (unsigned long long*)words.p, stream_id,
+                        c->d_counters + 1));
+    CK(c, cudaMemcpyAsync(indices_out, anc.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long h_clamped = 0;
+    CK(c, cudaMemcpyAsync(&h_clamped, c->d_counters + 1, sizeof(h_clamped), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (n_clamped) *n_clamped = (int64_t)h_clamped;
+    c->stats.h2d_bytes += (int64_t)sizeof(double) * (n + (uniforms ? n_uniforms : 0));
+    c->stats.d2h_bytes += (int64_t)sizeof(int32_t) * n;
+    return WS_OK;
+}
+
+extern "C" int ws_icdf_host(ws_ctx* c, const double* weights, const double* us, int64_t n, int32_t* indices_out, int64_t* n_clamped) {
+    if (!c || !weights || !us || !indices_out || n <= 0) return c ? fail(c, WS_EINVAL, "ws_icdf_host: bad arguments") : WS_EINVAL;
+    return resample_host_impl(c, weights, n, WS_RESAMPLER_STRATIFIED, us, n, true, indices_out, n_clamped);
+}
+
+extern "C" int ws_resample_host(ws_ctx* c, const double* weights, int64_t n, int scheme, const double* uniforms,
+                                int32_t* indices_out, int64_t* n_clamped) {
+    if (!c || !weights || !indices_out || n <= 0) return c ? fail(c, WS_EINVAL, "ws_resample_host: bad arguments") : WS_EINVAL;
+    if (scheme == WS_RESAMPLER_STRATIFIED) return resample_host_impl(c, weights, n, scheme, uniforms, n, false, indices_out, n_clamped);
+    if (scheme == WS_RESAMPLER_SYSTEMATIC) return resample_host_impl(c, weights, n, scheme, uniforms, 1, false, indices_out, n_clamped);
+    if (scheme == WS_RESAMPLER_MULTINOMIAL) {
+        if (uniforms == nullptr) return fail(c, WS_EUNSUPPORTED, "multinomial resampling needs caller uniforms for now");
+        std::vector<double> su(uniforms, uniforms + n);
+        std::sort(su.begin(), su.end());
+        return resample_host_impl(c, weights, n, scheme, su.data(), n, true, indices_out, n_clamped);
+    }
+    return fail(c, WS_EINVAL, "unknown resampling scheme %d", scheme);
+}
+
+// ------------------------------------------------------------------------------------------
+// analysis
+// ------------------------------------------------------------------------------------------
+extern "C" int ws_expectation(ws_ctx* c, const ws_expr* f, int32_t n_exprs, double* out) {
+    if (!c || !f || !out) return WS_EINVAL;
+    if (n_exprs < 1 || n_exprs > 8) return fail(c, WS_EINVAL, "ws_expectation: 1..8 expressions per call");
+    for (int k = 0; k < n_exprs; ++k) TRY(check_expr(c, &f[k], "ws_expectation"));
+    TRY(ensure_reduced(c));
+    Program p;
+    p.max_regs = WS_VM_MAX_REGS;
+    p.max_ops = WS_VM_MAX_OPS;
+    p.max_io = WS_VM_MAX_IO;
+    int regs[8];
+    for (int k = 0; k < n_exprs; ++k) {
+        Val v = p.compile(f[k]);
+        // keep the result in a register that later expressions cannot recycle
+        int t = p.alloc_plane_reg();
+        if (v.is_const)
+            p.emit(ws_make_op(WS_OP_LIN2, t, WS_REG_NONE, WS_REG_NONE, WS_REG_NONE, 0, v.c0, 0, 0));
+        else
+            p.emit(ws_make_op(WS_OP_LIN2, t, v.reg, WS_REG_NONE, WS_REG_NONE, 0, v.c0, v.c1, 0));
+        regs[k] = t;
+        p.end_statement();
+    }
+    if (!p.error.empty()) return fail(c, WS_EINVAL, "%s", p.error.c_str());
+    if (p.overflow) return fail(c, WS_EUNSUPPORTED, "ws_expectation: expressions do not fit one device pass");
+    WsVmProgram P;
+    memset(&P, 0, sizeof(P));
+    P.n = c->n;
+    P.particle_offset = c->offset;
+    P.n_ops = (int)p.ops.size();
+    P.n_loads = (int)p.loads.size();
+    P.n_stores = 0;
+    P.n_regs = std::max(1, p.high_water);
+    for (int k = 0; k < P.n_loads; ++k) {
+        P.load_ptr[k] = plane_ptr(c, p.loads[k].first);
+        P.load_reg[k] = (uint8_t)p.loads[k].second;
+    }
+    P.logw_mode = 0;
+    P.logw = c->logw;
+    P.n_expect = n_exprs;
+    for (int k = 0; k < n_exprs; ++k) P.expect_reg[k] = (uint8_t)regs[k];
+    P.red = c->d_red;
+    const int grid = std::max(1, std::min(ws_vm_max_grid(P.n_regs, c->sm_count), (int)((c->n + WS_VM_BLOCK - 1) / WS_VM_BLOCK)));
+    TRY(ensure_scratch(c, sizeof(double) * (size_t)grid * 8));
+    TRY(ensure_h_scratch(c, sizeof(double) * (size_t)grid * 8));
+    P.expect_partials = c->d_scratch;
+    P.rng.seed = c->seed;
+    memcpy(P.ops, p.ops.data(), sizeof(WsOp) * p.ops.size());
+    TimedEvent te;
+    timed_begin(c, KC_VM, te);
+    CK(c, ws_launch_vm(P, grid, c->stream));
+    timed_end(c, te);
+    CK(c, cudaMemcpyAsync(c->h_scratch, c->d_scratch, sizeof(double) * (size_t)grid * n_exprs, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < n_exprs; ++k) {
+        double s = 0.0;
+        for (int b = 0; b < grid; ++b) s += c->h_scratch[(size_t)b * n_exprs + k];
+        out[k] = s;
+    }
+    return WS_OK;
+}
+
+extern "C" int ws_col_download_rows(ws_ctx* c, int32_t id, const int64_t* indices, int64_t n_idx, double* host_out) {
+    if (!c || !indices || !host_out || n_idx <= 0) return c ? fail(c, WS_EINVAL, "ws_col_download_rows: bad arguments") : WS_EINVAL;
+    if (id < 0 || id >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", id);
+    for (int64_t i = 0; i < n_idx; ++i)
+        if (indices[i] < 0 || indices[i] >= c->n) return fail(c, WS_EINVAL, "row index %lld out of range", (long long)indices[i]);
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    TempBuf idx, out;
+    CK(c, cudaMalloc(&idx.p, sizeof(int64_t) * (size_t)n_idx));
+    CK(c, cudaMalloc(&out.p, sizeof(double) * (size_t)n_idx));
+    CK(c, cudaMemcpyAsync(idx.p, indices, sizeof(int64_t) * (size_t)n_idx, cudaMemcpyHostToDevice, c->stream));
+    const Column& col = c->cols[id];
+    for (int k = 0; k < col.width; ++k) {
+        CK(c, ws_launch_gather_rows(col.front[k], (const int64_t*)idx.p, n_idx, (double*)out.p, c->stream));
+        c->stats.kernel_launches++;
+        CK(c, cudaMemcpyAsync(host_out + (size_t)k * n_idx, out.p, sizeof(double) * (size_t)n_idx, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return WS_OK;
+}
+
+// sample(state, n; replace): indices drawn with probability exp_norm(weights).  With replacement the
+// draw is n sorted Philox uniforms pushed through the same scan+search kernel (multinomial);
+// without replacement it is the Efraimidis-Spirakis exponential-key selection done on the host
+// over the downloaded normalised weights (n <= N draws; analysis path, not the hot path).
+extern "C" int ws_sample_indices(ws_ctx* c, int64_t n_draws, int replace, int64_t* indices_out) {
+    if (!c || !indices_out) return WS_EINVAL;
+    if (n_draws <= 0) return fail(c, WS_EINVAL, "Number of samples must be positive");
+    if (!replace && n_draws > c->n) return fail(c, WS_EINVAL, "Cannot sample %lld particles without replacement from %lld particles", (long long)n_draws, (long long)c->n);
+    std::vector<double> w((size_t)c->n);
+    TRY(ws_exp_norm(c, w.data()));
+    const uint64_t stream_id = c->next_stream++;
+    if (replace) {
+        std::vector<double> u((size_t)n_draws);
+        for (int64_t i = 0; i < n_draws; ++i) {
+            ws_u32x4 r = ws_philox4x32_10((uint64_t)i, stream_id, c->seed);
+            u[(size_t)i] = ws_u01(r.x, r.y);
+        }
+        std::vector<double> cdf((size_t)c->n);
+        double s = 0.0;
+        for (int64_t i = 0; i < c->n; ++i) {
+            s += w[(size_t)i];
+            cdf[(size_t)i] = s;
+        }
+        for (int64_t i = 0; i < n_draws; ++i) {
+            const double target = u[(size_t)i] * s;
+            int64_t idx = (int64_t)(std::lower_bound(cdf.begin(), cdf.end(), target) - cdf.begin());
+            if (idx >= c->n) idx = c->n - 1;
+            indices_out[i] = idx;
+        }
+    } else {
+        std::vector<std::pair<double, int64_t>> keys((size_t)c->n);
+        for (int64_t i = 0; i < c->n; ++i) {
+            ws_u32x4 r = ws_philox4x32_10((uint64_t)i, stream_id, c->seed);
+            const double e = -log(ws_u01_open0(r.x, r.y));
+            keys[(size_t)i] = {w[(size_t)i] > 0.0 ? e / w[(size_t)i] : INFINITY, i};
+        }
+        std::partial_sort(keys.begin(), keys.begin() + n_draws, keys.end());
+        for (int64_t i = 0; i < n_draws; ++i) indices_out[i] = keys[(size_t)i].second;
+    }
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// replay
+// ------------------------------------------------------------------------------------------
+static int set_replay(ws_ctx* c, double** dptr, int64_t* dlen, int64_t* cursor, const double* host, int64_t len) {
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (*dptr) {
+        CK(c, cudaFree(*dptr));
+        *dptr = nullptr;
+    }
+    *dlen = 0;
+    *cursor = 0;
+    if (host == nullptr || len <= 0) return WS_OK;
+    CK(c, cudaMalloc(dptr, sizeof(double) * (size_t)len));
+    CK(c, cudaMemcpy(*dptr, host, sizeof(double) * (size_t)len, cudaMemcpyHostToDevice));
+    *dlen = len;
+    c->stats.h2d_bytes += (int64_t)sizeof(double) * len;
+    return WS_OK;
+}
+extern "C" int ws_set_replay_normals(ws_ctx* c, const double* host, int64_t len) {
+    if (!c) return WS_EINVAL;
+    return set_replay(c, &c->d_replay_n, &c->replay_n_len, &c->cur_n, host, len);
+}
+extern "C" int ws_set_replay_uniforms(ws_ctx* c, const double* host, int64_t len) {
+    if (!c) return WS_EINVAL;
+    return set_replay(c, &c->d_replay_u, &c->replay_u_len, &c->cur_u, host, len);
+}
+extern "C" int ws_set_replay_exponentials(ws_ctx* c, const double* host, int64_t len) {
+    if (!c) return WS_EINVAL;
+    return set_replay(c, &c->d_replay_e, &c->replay_e_len, &c->cur_e, host, len);
+}
+
+// ------------------------------------------------------------------------------------------
+// tape control / scoring / moves
+// ------------------------------------------------------------------------------------------
+extern "C" int ws_tape_clear(ws_ctx* c) {
+    if (!c) return WS_EINVAL;
+    reset_score(c);
+    return WS_OK;
+}
+extern "C" int ws_tape_record_only(ws_ctx* c, int on) {
+    if (!c) return WS_EINVAL;
+    if (on) TRY(flush_window(c));
+    c->record_only = on != 0;
+    return WS_OK;
+}
+extern "C" int ws_tape_enable(ws_ctx* c, int on) {
+    if (!c) return WS_EINVAL;
+    c->tape_enabled = on != 0;
+    return WS_OK;
+}
+extern "C" int ws_tape_length(const ws_ctx* c, int64_t* n) {
+    if (!c || !n) return WS_EINVAL;
+    *n = (int64_t)c->tape.size();
+    return WS_OK;
+}
+
+// number of score micro-ops belonging to entries with depth < target_depth (a prefix: depth is
+// non-decreasing along the tape)
+static int score_prefix_ops(ws_ctx* c, int64_t target_depth) {
+    int n_ops = 0;
+    for (auto& e : c->tape) {
+        if (e.depth < target_depth) n_ops = e.op_end; else break;
+    }
+    return n_ops;
+}
+
+static int upload_score_program(ws_ctx* c) {
+    const size_t n_ops = c->score.ops.size();
+    if (n_ops == 0) return WS_OK;
+    if (n_ops > c->d_score_cap) {
+        size_t cap = std::max<size_t>(1024, c->d_score_cap * 2);
+        while (cap < n_ops) cap *= 2;
+        WsOp* nd = nullptr;
+        CK(c, cudaMalloc(&nd, sizeof(WsOp) * cap));
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (c->d_score_ops) CK(c, cudaFree(c->d_score_ops));
+        c->d_score_ops = nd;
+        c->d_score_cap = cap;
+        c->d_score_uploaded = 0;
+    }
+    if (c->d_score_uploaded < n_ops) {
+        // pageable source: the copy is staged before the call returns, so the vector may grow later
+        CK(c, cudaMemcpyAsync(c->d_score_ops + c->d_score_uploaded, c->score.ops.data() + c->d_score_uploaded,
+                              sizeof(WsOp) * (n_ops - c->d_score_uploaded), cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (int64_t)(sizeof(WsOp) * (n_ops - c->d_score_uploaded));
+        c->d_score_uploaded = n_ops;
+    }
+    return WS_OK;
+}
+
+static int fill_score_launch(ws_ctx* c, WsScoreParams& S, int n_ops) {
+    memset(&S, 0, sizeof(S));
+    S.n = c->n;
+    S.particle_offset = c->offset;
+    S.ops = c->d_score_ops;
+    S.n_ops = n_ops;
+    S.n_regs = std::max(1, c->score.high_water);
+    // planes the tape reads: a plane register loaded only if the scored prefix can reference it is
+    // not tracked; loading all tape planes is always correct
+    S.n_loads = (int)c->score.loads.size();
+    if (S.n_loads > WS_SCORE_MAX_LOADS) return fail(c, WS_EUNSUPPORTED, "score tape references more than %d planes", WS_SCORE_MAX_LOADS);
+    for (int k = 0; k < S.n_loads; ++k) {
+        S.load_ptr[k] = plane_ptr(c, c->score.loads[k].first);
+        S.load_reg[k] = (uint8_t)c->score.loads[k].second;
+    }
+    return WS_OK;
+}
+
+extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out) {
+    if (!c || !host_out) return WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    const int n_ops = score_prefix_ops(c, target_depth);
+    TRY(upload_score_program(c));
+    TRY(ensure_scratch(c, sizeof(double) * (size_t)c->n));
+    WsScoreParams S;
+    TRY(fill_score_launch(c, S, n_ops));
+    S.score_out = c->d_scratch;
+    TimedEvent te;
+    timed_begin(c, KC_MOVE, te);
+    CK(c, ws_launch_score(S, c->sm_count, c->stream));
+    timed_end(c, te);
+    CK(c, cudaMemcpyAsync(host_out, c->d_scratch, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(double) * c->n;
+    return WS_OK;
+}
+
+extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t* col, const int32_t* comp, double* out) {
+    if (!c || !col || !comp || !out || n_targets < 1) return c ? fail(c, WS_EINVAL, "ws_marginal_diversity: bad arguments") : WS_EINVAL;
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    double best = INFINITY;
+    for (int t = 0; t < n_targets; ++t) {
+        TRY(check_plane(c, col[t], comp[t]));
+        // open-addressing table with 2N slots (power of two)
+        size_t slots = 1;
+        while (slots < (size_t)c->n * 2) slots <<= 1;
+        TRY(ensure_scratch(c, sizeof(unsigned long long) * slots + 64));
+        unsigned long long* table = (unsigned long long*)c->d_scratch;
+        unsigned long long* counter = table + slots;
+        TimedEvent te;
+        timed_begin(c, KC_OTHER, te);
+        CK(c, ws_launch_unique_count(plane_ptr(c, Plane{col[t], comp[t]}), c->n, table, slots, counter, c->sm_count, c->stream));
+        timed_end(c, te);
+        unsigned long long h = 0;
+        CK(c, cudaMemcpyAsync(&h, counter, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        const double frac = (double)h / (double)c->n_global;
+        if (frac < best) best = frac;
+    }
+    *out = best;
+    return WS_OK;
+}
+
+extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) {
+    if (!c || !spec) return WS_EINVAL;
+    const int d = spec->n_targets;
+    if (d < 1 || d > WS_MOVE_MAX_D) return fail(c, WS_EUNSUPPORTED, "Move with %d targets (supported: 1..%d)", d, WS_MOVE_MAX_D);
+    if (!spec->col || !spec->comp) return fail(c, WS_EINVAL, "ws_move: targets missing");
+    for (int t = 0; t < d; ++t) TRY(check_plane(c, spec->col[t], spec->comp[t]));
+    if (spec->proposal != WS_PROPOSAL_RW && spec->proposal != WS_PROPOSAL_AUTORW) return fail(c, WS_EINVAL, "ws_move: unknown proposal %d", spec->proposal);
+    if (spec->has_bounds && (!spec->lo || !spec->hi)) return fail(c, WS_EINVAL, "ws_move: bounds missing");
+    TRY(flush_window(c));
+    CK(c, cudaSetDevice(c->device));
+    if (info) {
+        info->ran = 0;
+        info->diversity = NAN;
+        info->n_accepted = 0;
+    }
+    // diversity gate (transformers.jl:592-594)
+    if (!isnan(spec->diversity)) {
+        double div = 0.0;
+        TRY(ws_marginal_diversity(c, d, spec->col, spec->comp, &div));
+        if (info) info->diversity = div;
+        if (div >= spec->diversity) return WS_OK;
+    }
+    const int64_t target_depth = spec->target_depth < 0 ? c->depth : spec->target_depth;
+
+    WsMoveParams M;
+    memset(&M, 0, sizeof(M));
+    M.d = d;
+    for (int t = 0; t < d; ++t) {
+        M.target_ptr[t] = plane_ptr(c, Plane{spec->col[t], spec->comp[t]});
+        M.lo[t] = spec->has_bounds ? spec->lo[t] : -INFINITY;
+        M.hi[t] = spec->has_bounds ? spec->hi[t] : INFINITY;
+        M.bound_kind[t] = ws_bound_kind(M.lo[t], M.hi[t]);
+    }
+    // target registers inside the score program (a target the tape never mentions gets none)
+    for (int t = 0; t < d; ++t) {
+        auto it = c->score.plane_reg.find(Plane{spec->col[t], spec->comp[t]});
+        M.target_reg[t] = (it == c->score.plane_reg.end()) ? 0xFF : (uint8_t)it->second;
+    }
+
+    // proposal covariance factor L (d x d lower, row-major): z' = z + L xi
+    std::vector<double> L((size_t)d * d, 0.0);
+    if (spec->proposal == WS_PROPOSAL_RW) {
+        // RW: std = step_size per target (move_kernels.jl:189-212)
+        for (int t = 0; t < d; ++t) L[t * d + t] = spec->step;
+        // unbounded RW draws target-major (for each target N normals); bounded RW and autoRW draw
+        // particle-major d x N (move_kernels.jl:200-202 vs :150,209)
+        M.normals_target_major = spec->has_bounds ? 0 : 1;
+    } else {
+        // autoRW: lambda * weighted covariance of the (unconstrained) targets (move_kernels.jl:144-151)
+        if (c->logw_uniform) {
+            M.w_uniform = 1;
+        } else {
+            TRY(ensure_reduced(c));
+            M.w_uniform = 0;
+        }
+        const int n_mom = 1 + d + d * (d + 1) / 2;
+        const int grid = std::min(c->sm_count * 4, (int)((c->n + 255) / 256));
+        TRY(ensure_scratch(c, sizeof(double) * (size_t)std::max(1, grid) * n_mom * 2));
+        TRY(ensure_h_scratch(c, sizeof(double) * (size_t)std::max(1, grid) * n_mom * 2));
+        M.logw = c->logw;
+        M.red = c->d_red;
+        // two passes (mean, then centred second moments), like StatsBase.cov
+        std::vector<double> mean(d, 0.0), cov((size_t)d * d, 0.0);
+        double wsum = 0.0;
+        for (int pass = 0; pass < 2; ++pass) {
+            for (int t = 0; t < d; ++t) M.mean[t] = mean[t];
+            TimedEvent te;
+            timed_begin(c, KC_MOVE, te);
+            CK(c, ws_launch_move_moments(M, c->n, pass, c->d_scratch, std::max(1, grid), c->stream));
+            timed_end(c, te);
+            CK(c, cudaMemcpyAsync(c->h_scratch, c->d_scratch, sizeof(double) * (size_t)std::max(1, grid) * n_mom, cudaMemcpyDeviceToHost, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+            std::vector<double> tot(n_mom, 0.0);
+            for (int b = 0; b < std::max(1, grid); ++b)
+                for (int k = 0; k < n_mom; ++k) tot[k] += c->h_scratch[(size_t)b * n_mom + k];
+            if (pass == 0) {
+                wsum = tot[0];
+                for (int t = 0; t < d; ++t) mean[t] = tot[1 + t] / wsum;
+            } else {
+                int k = 1 + d;
+                for (int i = 0; i < d; ++i)
+                    for (int j = 0; j <= i; ++j) {
+                        cov[i * d + j] = cov[j * d + i] = tot[k] / wsum;
+                        ++k;
+                    }
+            }
+        }
+        const double lambda = 2.38 / sqrt((double)d);
+        std::vector<double> S((size_t)d * d);
+        for (int i = 0; i < d * d; ++i) {
+            double v = cov[i];
+            if (v == 0.0) v = spec->step;  // Sigma[Sigma .== 0] .= min_step
+            S[i] = lambda * v;
+        }
+        if (!wsl::cholesky_lower(d, S.data(), L))
+            return fail(c, WS_ENUMERIC, "autoRW: proposal covariance is not positive definite (rank-deficient particle cloud)");
+        M.normals_target_major = 0;
+    }
+    for (int i = 0; i < d * d; ++i) M.L[i] = L[i];
+
+    // random streams
+    M.rng.seed = c->seed;
+    M.rng.replay_n = c->d_replay_n;
+    M.rng.replay_u = c->d_replay_u;
+    M.rng.replay_e = nullptr;
+    M.stream_normals = c->next_stream;
+    c->next_stream += (uint64_t)((d + 1) / 2);
+    M.stream_uniform = c->next_stream++;
+    M.replay_n_base = c->cur_n;
+    M.replay_u_base = c->cur_u;
+    M.n_global = c->n_global;
+    if (c->d_replay_n != nullptr) {
+        c->cur_n += c->n_global * d;
+        if (c->cur_n > c->replay_n_len) return fail(c, WS_EREPLAY, "replay normals exhausted in Move");
+    }
+    if (c->d_replay_u != nullptr) {
+        c->cur_u += c->n_global;
+        if (c->cur_u > c->replay_u_len) return fail(c, WS_EREPLAY, "replay uniforms exhausted in Move");
+    }
+
+    const int n_ops = score_prefix_ops(c, target_depth);
+    TRY(upload_score_program(c));
+    TRY(fill_score_launch(c, M.score, n_ops));
+    CK(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
+    M.n_accept = c->d_counters + 2;
+    TimedEvent te;
+    timed_begin(c, KC_MOVE, te);
+    CK(c, ws_launch_move(M, c->sm_count, c->stream));
+    timed_end(c, te);
+    c->stats.moves_run++;
+    if (info) {
+        info->ran = 1;
+        unsigned long long acc = 0;
+        CK(c, cudaMemcpyAsync(&acc, c->d_counters + 2, sizeof(acc), cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        info->n_accepted = (int64_t)acc;
+    }
+    return WS_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// instrumentation
+// ------------------------------------------------------------------------------------------
+extern "C" int ws_get_clamped(ws_ctx* c, int64_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    unsigned long long h = 0;
+    CK(c, cudaMemcpyAsync(&h, c->d_counters + 0, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *out = (int64_t)h;
+    return WS_OK;
+}
+
+extern "C" int ws_get_stats(ws_ctx* c, ws_stats* out) {
+    if (!c || !out) return WS_EINVAL;
+    resolve_events(c);
+    c->stats.last_pass_ms = c->kc_ms[KC_VM];
+    c->stats.last_resample_ms = c->kc_ms[KC_SCAN] + c->kc_ms[KC_GATHER];
+    *out = c->stats;
+    return WS_OK;
+}
+extern "C" int ws_kernel_times(ws_ctx* c, double* ms_out, int64_t* count_out, int32_t n_classes) {
+    if (!c) return WS_EINVAL;
+    resolve_events(c);
+    for (int k = 0; k < n_classes && k < KC_COUNT; ++k) {
+        if (ms_out) ms_out[k] = c->kc_ms[k];
+        if (count_out) count_out[k] = c->kc_count[k];
+    }
+    return WS_OK;
+}
+extern "C" int ws_reset_kernel_times(ws_ctx* c) {
+    if (!c) return WS_EINVAL;
+    resolve_events(c);
+    for (int k = 0; k < KC_COUNT; ++k) {
+        c->kc_ms[k] = 0.0;
+        c->kc_count[k] = 0;
+    }
+    return WS_OK;
+}
+extern "C" int ws_set_timing(ws_ctx* c, int on) {
+    if (!c) return WS_EINVAL;
+    resolve_events(c);
+    c->timing = on != 0;
+    return WS_OK;
+}
+extern "C" int ws_stream(ws_ctx* c, void** stream_out) {
+    if (!c || !stream_out) return WS_EINVAL;
+    *stream_out = (void*)c->stream;
+    return WS_OK;
+}

@@ -1,0 +1,206 @@
+// ws_vm.cuh — the fixed device-op set ("micro-ops") and its in-kernel interpreter.
+//
+// The reference runs every model statement as one fused Julia broadcast over all particles
+// (src/transformers.jl: Assign :28-32, Sample :172-182, Observe :228-235, Weight :283-289,
+// AccessorSample :118-131).  Here a window of consecutive statements is lowered by the host
+// runtime (ws_runtime.cu: Lowering) to a short program of the micro-ops below and executed
+// in ONE pass over the particles: plane values live in a per-thread register file in shared
+// memory for the whole window, so each plane is read and written at most once per window.
+//
+// The same interpreter folds the score tape inside the MH kernel (ws_kernels_move.cu), which
+// is the device form of the reference's score! walk (src/transformers.jl:39,77,139,193,243,297).
+#pragma once
+#include <string.h>
+#include "ws_math.cuh"
+
+#define WS_REG_NONE 0xFFu
+
+enum WsOpCode : uint32_t {
+    WS_OP_LIN2 = 0,         // r[dst] = k0 + k1*r[a] + k2*r[b]        (a / b == NONE: term absent)
+    WS_OP_MUL = 1,          // r[dst] = k0 * A * B       A = a==NONE ? k1 : r[a];  B = b==NONE ? k2 : r[b]
+    WS_OP_DIV = 2,          // r[dst] = k0 * A / B
+    WS_OP_UNARY = 3,        // r[dst] = f_imm(A)
+    WS_OP_POW = 4,          // r[dst] = pow(A, B)
+    WS_OP_RANDN2 = 5,       // r[dst] (, r[a]) = standard normals
+    WS_OP_RANDEXP = 6,      // r[dst] = standard exponential
+    WS_OP_RANDU = 7,        // r[dst] = uniform [0,1)
+    WS_OP_LOGPDF_NORMAL = 8,  // acc += logN(X; MU, SIGMA)   X = a==NONE?k0:r[a]; MU = b==NONE?k1:r[b]; SIGMA = c==NONE?k2:r[c]
+    WS_OP_LOGPDF_EXPON = 9,   // acc += logExp(X; THETA)     X = a==NONE?k0:r[a]; THETA = b==NONE?k1:r[b]
+    WS_OP_ACC_LIN2 = 10,      // acc += k0 + k1*r[a] + k2*r[b]
+    WS_OP_ACC_QUAD2 = 11,     // acc += k0 + k1*r[a]^2 + k2*r[b]^2
+    WS_OP_ACC_SCALE = 12,     // acc = k0 * acc   (used to negate a proposal log-density)
+    WS_OP_LOGPDF_NORMAL_CS = 13  // constant sigma: acc += k2 - 0.5*((X - r[b])*k1)^2,  X = a==NONE?k0:r[a]
+};
+
+enum WsUnary : uint32_t {
+    WS_UN_EXP = 0,
+    WS_UN_LOG = 1,
+    WS_UN_SQRT = 2,
+    WS_UN_SIN = 3,
+    WS_UN_COS = 4,
+    WS_UN_ABS = 5,
+    WS_UN_SQUARE = 6
+};
+
+// 32-byte micro-op; two 16-byte words so one uniform 128-bit load pair fetches it.
+struct alignas(16) WsOp {
+    uint32_t w0;  // op | dst<<8 | a<<16 | b<<24
+    uint32_t w1;  // c | imm<<8 (24 bits)
+    double k0, k1, k2;
+};
+static_assert(sizeof(WsOp) == 32, "WsOp must be 32 bytes");
+
+WS_HD WsOp ws_make_op(uint32_t op, uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t imm, double k0,
+                      double k1, double k2) {
+    WsOp o;
+    o.w0 = (op & 0xFFu) | ((dst & 0xFFu) << 8) | ((a & 0xFFu) << 16) | ((b & 0xFFu) << 24);
+    o.w1 = (c & 0xFFu) | ((imm & 0xFFFFFFu) << 8);
+    o.k0 = k0;
+    o.k1 = k1;
+    o.k2 = k2;
+    return o;
+}
+
+// Random-source description shared by every particle of a launch.
+//   Philox mode : counter = (global particle index, stream id), key = seed.
+//   replay mode : value = buf[base + particle*stride + j]  (reference consumption order,
+//                 SURVEY.md §8c), base/stride/j come from the op.
+struct WsRng {
+    uint64_t seed;
+    const double* replay_n;  // standard normals or nullptr
+    const double* replay_u;  // uniforms or nullptr
+    const double* replay_e;  // standard exponentials or nullptr
+};
+
+WS_HD uint64_t ws_double_bits(double v) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(v);
+#else
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    return b;
+#endif
+}
+
+// R points at this thread's column of the shared-memory register file; register k is R[k*STRIDE].
+// (WS_HD: the host instantiation exists only for tests/host/, which runs lowered programs through
+// this very interpreter on the CPU to check the lowering without a GPU.)
+template <int STRIDE>
+WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double& acc,
+                                           const WsRng& rng, uint64_t particle) {
+    const uint32_t op = o.w0 & 0xFFu;
+    const uint32_t dst = (o.w0 >> 8) & 0xFFu;
+    const uint32_t a = (o.w0 >> 16) & 0xFFu;
+    const uint32_t b = (o.w0 >> 24) & 0xFFu;
+    const uint32_t c = o.w1 & 0xFFu;
+    const uint32_t imm = o.w1 >> 8;
+    switch (op) {
+        case WS_OP_LIN2: {
+            double v = o.k0;
+            if (a != WS_REG_NONE) v += o.k1 * R[a * STRIDE];
+            if (b != WS_REG_NONE) v += o.k2 * R[b * STRIDE];
+            R[dst * STRIDE] = v;
+        } break;
+        case WS_OP_MUL: {
+            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
+            double B = (b == WS_REG_NONE) ? o.k2 : R[b * STRIDE];
+            R[dst * STRIDE] = o.k0 * A * B;
+        } break;
+        case WS_OP_DIV: {
+            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
+            double B = (b == WS_REG_NONE) ? o.k2 : R[b * STRIDE];
+            R[dst * STRIDE] = o.k0 * A / B;
+        } break;
+        case WS_OP_UNARY: {
+            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
+            double v;
+            switch (imm) {
+                case WS_UN_EXP: v = exp(A); break;
+                case WS_UN_LOG: v = log(A); break;
+                case WS_UN_SQRT: v = sqrt(A); break;
+                case WS_UN_SIN: v = sin(A); break;
+                case WS_UN_COS: v = cos(A); break;
+                case WS_UN_ABS: v = fabs(A); break;
+                default: v = A * A; break;
+            }
+            R[dst * STRIDE] = v;
+        } break;
+        case WS_OP_POW: {
+            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
+            double B = (b == WS_REG_NONE) ? o.k2 : R[b * STRIDE];
+            R[dst * STRIDE] = pow(A, B);
+        } break;
+        case WS_OP_RANDN2: {
+            double z0, z1;
+            if (rng.replay_n != nullptr) {
+                // k1 = base offset, k2 = stride (both exact integers), imm = component j
+                const int64_t base = (int64_t)o.k1 + (int64_t)particle * (int64_t)o.k2 + (int64_t)imm;
+                z0 = rng.replay_n[base];
+                z1 = (a != WS_REG_NONE) ? rng.replay_n[base + 1] : 0.0;
+            } else {
+                ws_randn2(particle, ws_double_bits(o.k0), rng.seed, z0, z1);
+            }
+            R[dst * STRIDE] = z0;
+            if (a != WS_REG_NONE) R[a * STRIDE] = z1;
+        } break;
+        case WS_OP_RANDEXP: {
+            double e;
+            if (rng.replay_e != nullptr) {
+                e = rng.replay_e[(int64_t)o.k1 + (int64_t)particle * (int64_t)o.k2 + (int64_t)imm];
+            } else {
+                e = ws_randexp(particle, ws_double_bits(o.k0), rng.seed);
+            }
+            R[dst * STRIDE] = e;
+        } break;
+        case WS_OP_RANDU: {
+            double u;
+            if (rng.replay_u != nullptr) {
+                u = rng.replay_u[(int64_t)o.k1 + (int64_t)particle * (int64_t)o.k2 + (int64_t)imm];
+            } else {
+                double u1;
+                ws_randu2(particle, ws_double_bits(o.k0), rng.seed, u, u1);
+            }
+            R[dst * STRIDE] = u;
+        } break;
+        case WS_OP_LOGPDF_NORMAL: {
+            double X = (a == WS_REG_NONE) ? o.k0 : R[a * STRIDE];
+            double MU = (b == WS_REG_NONE) ? o.k1 : R[b * STRIDE];
+            double SG = (c == WS_REG_NONE) ? o.k2 : R[c * STRIDE];
+            acc += ws_normal_logpdf(X, MU, SG);
+        } break;
+        case WS_OP_LOGPDF_NORMAL_CS: {
+            // constant sigma > 0, hoisted by the host: k1 = 1/sigma, k2 = -log(2pi)/2 - log(sigma).
+            // D = X - MU with MU = r[b] (always a register) and X = r[a] or the constant k0.
+            double X = (a == WS_REG_NONE) ? o.k0 : R[a * STRIDE];
+            double z = (X - R[b * STRIDE]) * o.k1;
+            acc += o.k2 - 0.5 * (z * z);
+        } break;
+        case WS_OP_LOGPDF_EXPON: {
+            double X = (a == WS_REG_NONE) ? o.k0 : R[a * STRIDE];
+            double TH = (b == WS_REG_NONE) ? o.k1 : R[b * STRIDE];
+            acc += ws_exponential_logpdf(X, TH);
+        } break;
+        case WS_OP_ACC_LIN2: {
+            double v = o.k0;
+            if (a != WS_REG_NONE) v += o.k1 * R[a * STRIDE];
+            if (b != WS_REG_NONE) v += o.k2 * R[b * STRIDE];
+            acc += v;
+        } break;
+        case WS_OP_ACC_QUAD2: {
+            double v = o.k0;
+            if (a != WS_REG_NONE) {
+                double t = R[a * STRIDE];
+                v += o.k1 * t * t;
+            }
+            if (b != WS_REG_NONE) {
+                double t = R[b * STRIDE];
+                v += o.k2 * t * t;
+            }
+            acc += v;
+        } break;
+        case WS_OP_ACC_SCALE: {
+            acc = o.k0 * acc;
+        } break;
+        default: break;
+    }
+}

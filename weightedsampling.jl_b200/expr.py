@@ -1,0 +1,223 @@
+"""Per-particle expressions: the host-side form of what ``vectorize`` builds in the reference
+(``src/rewrites.jl:146-219``): constants become one value per particle, a particle variable becomes
+its column, calls become elementwise operations.  Here an expression is a small tree that is
+serialised to postfix tokens (``ws_tok``) and compiled to device micro-ops by the runtime; anything
+that cannot be expressed is rejected with :class:`UnsupportedModelError` when the model is built.
+
+Vector-valued columns (``x .= [0.0, 0.0]``) are ``d`` scalar planes; arithmetic on them is
+component-wise, which covers the reference's uses (``x{t} + v``, ``0.1 * I2`` is a build-time
+constant).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import numbers
+
+import numpy as np
+
+from . import _lib as L
+from ._lib import UnsupportedModelError
+
+
+def _unsupported(msg):
+    return UnsupportedModelError(L.WS_EUNSUPPORTED, msg)
+
+
+class Expr:
+    """Base class; operators build the tree."""
+
+    def __add__(self, o): return Bin(L.TOK_ADD, self, wrap(o))
+    def __radd__(self, o): return Bin(L.TOK_ADD, wrap(o), self)
+    def __sub__(self, o): return Bin(L.TOK_SUB, self, wrap(o))
+    def __rsub__(self, o): return Bin(L.TOK_SUB, wrap(o), self)
+    def __mul__(self, o): return Bin(L.TOK_MUL, self, wrap(o))
+    def __rmul__(self, o): return Bin(L.TOK_MUL, wrap(o), self)
+    def __truediv__(self, o): return Bin(L.TOK_DIV, self, wrap(o))
+    def __rtruediv__(self, o): return Bin(L.TOK_DIV, wrap(o), self)
+    def __pow__(self, o): return Bin(L.TOK_POW, self, wrap(o))
+    def __rpow__(self, o): return Bin(L.TOK_POW, wrap(o), self)
+    def __neg__(self): return Un(L.TOK_NEG, self)
+    def __pos__(self): return self
+    def __abs__(self): return Un(L.TOK_ABS, self)
+    def __getitem__(self, j): return Index(self, j)
+
+    # comparisons / truthiness would silently build wrong programs
+    def __bool__(self):
+        raise _unsupported("a particle-dependent value cannot be used as a Python condition "
+                           "(vectorised ternary / && / || are outside the device-op set)")
+
+
+class Const(Expr):
+    def __init__(self, v):
+        self.v = v  # float or 1-d ndarray
+
+
+class Col(Expr):
+    """A particle variable (column) by name: ``getcol(state.store, :name)``."""
+
+    def __init__(self, name):
+        self.name = str(name)
+
+    def __repr__(self):
+        return f"col({self.name!r})"
+
+
+class Index(Expr):
+    """``x[j]`` on a vector-valued column; ``j`` is 0-based here (the @model front-end converts)."""
+
+    def __init__(self, base, j):
+        if isinstance(j, Expr):
+            raise _unsupported("particle-dependent indices are outside the device-op set")
+        self.base, self.j = base, int(j)
+
+
+class Bin(Expr):
+    def __init__(self, op, a, b):
+        self.op, self.a, self.b = op, a, b
+
+
+class Un(Expr):
+    def __init__(self, op, a):
+        self.op, self.a = op, a
+
+
+class Vec(Expr):
+    """``[e1, e2, ...]`` with per-particle entries."""
+
+    def __init__(self, items):
+        self.items = [wrap(i) for i in items]
+
+
+def wrap(v):
+    if isinstance(v, Expr):
+        return v
+    if isinstance(v, (bool, np.bool_)):
+        raise _unsupported("Bool-valued particle expressions are outside the device-op set")
+    if isinstance(v, numbers.Real):
+        return Const(float(v))
+    if isinstance(v, (list, tuple)):
+        if any(isinstance(i, Expr) for i in v):
+            return Vec(v)
+        return Const(np.asarray(v, dtype=np.float64))
+    if isinstance(v, np.ndarray):
+        if v.ndim == 0:
+            return Const(float(v))
+        if v.ndim == 1:
+            return Const(np.asarray(v, dtype=np.float64))
+        raise _unsupported(f"{v.ndim}-d array as a particle value is outside the device-op set")
+    raise _unsupported(f"value of type {type(v).__name__} is outside the device-op set")
+
+
+def col(name):
+    return Col(name)
+
+
+def _fn(op):
+    def f(x):
+        if isinstance(x, Expr):
+            return Un(op, x)
+        return {L.TOK_EXP: math.exp, L.TOK_LOG: math.log, L.TOK_SQRT: math.sqrt, L.TOK_SIN: math.sin,
+                L.TOK_COS: math.cos, L.TOK_ABS: abs, L.TOK_SQUARE: lambda t: t * t}[op](x)
+    return f
+
+
+exp = _fn(L.TOK_EXP)
+log = _fn(L.TOK_LOG)
+sqrt = _fn(L.TOK_SQRT)
+sin = _fn(L.TOK_SIN)
+cos = _fn(L.TOK_COS)
+abs2 = _fn(L.TOK_SQUARE)
+
+
+# ------------------------------------------------------------------------------------------------
+# lowering to postfix tokens
+# ------------------------------------------------------------------------------------------------
+class Tokens:
+    """A scalar expression as a Python list of (op, col, comp, val)."""
+
+    __slots__ = ("toks",)
+
+    def __init__(self, toks):
+        self.toks = toks
+
+    @staticmethod
+    def const(v):
+        return Tokens([(L.TOK_CONST, 0, 0, float(v))])
+
+    def is_const(self):
+        return len(self.toks) == 1 and self.toks[0][0] == L.TOK_CONST
+
+    def const_value(self):
+        return self.toks[0][3]
+
+
+def lower(e, store):
+    """Expr -> Tokens (scalar) or list[Tokens] (vector).  ``store`` resolves column names."""
+    e = wrap(e)
+    if isinstance(e, Const):
+        if isinstance(e.v, np.ndarray):
+            return [Tokens.const(x) for x in e.v]
+        return Tokens.const(e.v)
+    if isinstance(e, Col):
+        cid, width = store._lookup(e.name)
+        if cid < 0:
+            raise KeyError(f"particle variable {e.name!r} does not exist yet")
+        if width == 1:
+            return Tokens([(L.TOK_PLANE, cid, 0, 0.0)])
+        return [Tokens([(L.TOK_PLANE, cid, k, 0.0)]) for k in range(width)]
+    if isinstance(e, Vec):
+        items = [lower(i, store) for i in e.items]
+        if any(isinstance(i, list) for i in items):
+            raise _unsupported("nested vectors are outside the device-op set")
+        return items
+    if isinstance(e, Index):
+        base = lower(e.base, store)
+        if not isinstance(base, list):
+            raise _unsupported("indexing a scalar particle variable")
+        if not (0 <= e.j < len(base)):
+            raise IndexError(f"index {e.j} out of range for a vector of length {len(base)}")
+        return base[e.j]
+    if isinstance(e, Un):
+        a = lower(e.a, store)
+        if isinstance(a, list):
+            if e.op == L.TOK_NEG:
+                return [Tokens(t.toks + [(L.TOK_NEG, 0, 0, 0.0)]) for t in a]
+            raise _unsupported("elementwise functions of vector-valued variables are outside the device-op set")
+        return Tokens(a.toks + [(e.op, 0, 0, 0.0)])
+    if isinstance(e, Bin):
+        a, b = lower(e.a, store), lower(e.b, store)
+        va, vb = isinstance(a, list), isinstance(b, list)
+        if not va and not vb:
+            return Tokens(a.toks + b.toks + [(e.op, 0, 0, 0.0)])
+        if va and vb:
+            if e.op not in (L.TOK_ADD, L.TOK_SUB):
+                raise _unsupported("only + and - are defined between vector-valued variables")
+            if len(a) != len(b):
+                raise ValueError(f"vector lengths differ ({len(a)} vs {len(b)})")
+            return [Tokens(x.toks + y.toks + [(e.op, 0, 0, 0.0)]) for x, y in zip(a, b)]
+        # vector (*|/) scalar, scalar * vector
+        if va and e.op in (L.TOK_MUL, L.TOK_DIV):
+            return [Tokens(x.toks + b.toks + [(e.op, 0, 0, 0.0)]) for x in a]
+        if vb and e.op == L.TOK_MUL:
+            return [Tokens(a.toks + y.toks + [(e.op, 0, 0, 0.0)]) for y in b]
+        raise _unsupported("this mix of scalar and vector operands is outside the device-op set")
+    raise _unsupported(f"cannot lower {type(e).__name__}")
+
+
+class CExprs:
+    """Owns the ctypes arrays behind one or more ``ws_expr`` (keeps them alive for the call)."""
+
+    def __init__(self, token_lists):
+        self._bufs = []
+        self.arr = (L.ws_expr * len(token_lists))()
+        for i, t in enumerate(token_lists):
+            buf = (L.ws_tok * len(t.toks))()
+            for k, (op, c, comp, val) in enumerate(t.toks):
+                buf[k].op, buf[k].col, buf[k].comp, buf[k].val = op, c, comp, val
+            self._bufs.append(buf)
+            self.arr[i].toks = C.cast(buf, C.POINTER(L.ws_tok))
+            self.arr[i].n = len(t.toks)
+
+    def ptr(self, i=0):
+        return C.cast(C.byref(self.arr, i * C.sizeof(L.ws_expr)), C.POINTER(L.ws_expr))
