@@ -73,10 +73,11 @@ static void run_program(HH* h, Program& p, std::vector<double>* acc_out, int n_o
     std::vector<double> R((size_t)std::max(1, p.high_water));
     for (int64_t i = 0; i < h->n; ++i) {
         for (auto& ld : p.loads) R[ld.second] = h->cols[ld.first.col][ld.first.comp][(size_t)i];
-        double acc = 0.0;
-        for (int pc = 0; pc < n_ops; ++pc) ws_vm_exec<1>(p.ops[pc], R.data(), acc, rng, (uint64_t)i);
+        double acc[1] = {0.0};
+        const uint64_t pid[1] = {(uint64_t)i};
+        for (int pc = 0; pc < n_ops; ++pc) ws_vm_exec<1, 1>(p.ops[pc], R.data(), acc, rng, pid);
         for (auto& d : p.dirty) h->cols[d.col][d.comp][(size_t)i] = R[p.plane_reg[d]];
-        if (acc_out) (*acc_out)[(size_t)i] = acc;
+        if (acc_out) (*acc_out)[(size_t)i] = acc[0];
     }
 }
 
@@ -209,7 +210,7 @@ void hh_philox(uint64_t particle, uint64_t stream, uint64_t seed, uint32_t* out4
 // F(C) for every C in cs against the stratified grid built from r (replay)
 struct RArr {
     const double* r;
-    double operator()(int64_t k) const { return r[k]; }
+    double operator()(int64_t k) { return r[k]; }
 };
 void hh_count_slots_le(const double* cs, int64_t n_c, const double* r, int64_t n, int64_t* out) {
     RArr ra{r};

@@ -5,14 +5,16 @@
 #include <stdint.h>
 #include "ws_vm.cuh"
 
-#define WS_VM_BLOCK 256       // threads per CTA of the fused elementwise pass
+#define WS_VM_BLOCK 128       // threads per CTA of the fused elementwise pass
+#define WS_VM_P 4             // particles per thread: one decoded micro-op is applied to all of them
 #define WS_VM_MAX_IO 24       // planes loaded / stored per fused pass
 #define WS_VM_MAX_OPS 96      // micro-ops per fused pass (program travels in kernel params)
-#define WS_VM_MAX_REGS 64     // register-file rows per pass (64*256*8 = 128 KB of smem)
+#define WS_VM_MAX_REGS 48     // register-file rows per pass (48 * 128 * 4 * 8 B = 192 KB of smem)
 #define WS_SCAN_BLOCK 256
 #define WS_SCAN_ITEMS 8
 #define WS_SCAN_TILE (WS_SCAN_BLOCK * WS_SCAN_ITEMS)
 #define WS_GATHER_MAX_PLANES 32
+#define WS_HEAVY_TILE_SLOTS (64 * 4096)  // == WS_HEAVY_TILE in ws_kernels.cu
 #define WS_MAX_PARTIALS 4096  // upper bound on CTAs that write (m,S,Q) partials
 
 // (m, S, Q) = (max l, sum exp(l-m), sum exp(2(l-m))) — everything exp_norm / ess_perc /
@@ -72,6 +74,8 @@ struct WsScanParams {
     unsigned long long* tile_words;  // decoupled look-back descriptors, zeroed before launch
     unsigned int* tile_counter;      // dynamic tile ids, zeroed before launch
     unsigned long long* n_clamped;  // += slots beyond the last CDF entry (clamped to the last particle)
+    unsigned int* heavy_count;       // number of heavy tiles, zeroed before launch
+    int32_t* heavy_F;                // [n/WS_HEAVY_TILE + 2][WS_SCAN_TILE + 2]: F table, fstart, tile id
 };
 
 struct WsGatherParams {

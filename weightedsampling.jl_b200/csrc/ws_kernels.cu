@@ -79,15 +79,18 @@ __device__ __forceinline__ WsLse lse_block_reduce(WsLse v, WsLse* warp_scratch /
 // ------------------------------------------------------------------------------------------
 // Fused elementwise window
 // ------------------------------------------------------------------------------------------
-// Persistent grid, one particle per thread per tile.  The register file is a [n_regs][BLOCK]
-// array in shared memory: thread t only ever touches column t, so the pass needs no barrier
-// and shared-memory accesses are conflict-free 64-bit lanes.  Loads are staged through a
-// statically unrolled register array so that all input planes of a particle are in flight at
-// once (memory-level parallelism = n_loads per thread).
-__global__ void __launch_bounds__(WS_VM_BLOCK, 3) ws_vm_kernel(const __grid_constant__ WsVmProgram P) {
+// Persistent grid; a CTA of WS_VM_BLOCK threads works on tiles of WS_VM_BLOCK * WS_VM_P particles,
+// thread t owning particles tile + t + j*WS_VM_BLOCK (j < WS_VM_P: every global access is coalesced).
+// The register file is a [n_regs][WS_VM_P][WS_VM_BLOCK] array in shared memory: a thread only ever
+// touches its own column, so the pass needs no barrier and shared-memory accesses are conflict-free
+// 64-bit lanes.  Each micro-op is decoded once per thread and applied to its WS_VM_P particles, which
+// amortises the interpreter overhead and gives WS_VM_P independent dependency chains.  Loads are staged
+// through registers in batches so that 4 planes x WS_VM_P particles are in flight per thread.
+__global__ void __launch_bounds__(WS_VM_BLOCK, 4) ws_vm_kernel(const __grid_constant__ WsVmProgram P) {
     extern __shared__ double ws_vm_smem[];
     __shared__ WsLse warp_scratch[WS_VM_BLOCK / 32];
     double* R = ws_vm_smem + threadIdx.x;
+    constexpr int RS = WS_VM_P * WS_VM_BLOCK;  // doubles between two registers of the file
 
     WsLse part;
     part.m = -INFINITY;
@@ -102,49 +105,93 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, 3) ws_vm_kernel(const __grid_cons
         red_invS = 1.0 / P.red->S;
     }
 
-    const int64_t stride = (int64_t)gridDim.x * WS_VM_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * WS_VM_BLOCK + threadIdx.x; i < P.n; i += stride) {
-        // ---- loads: batches of 8 planes in flight per thread ---------------------------------
-        {
-            int64_t src = i;
-            if (P.load_gather != 0u) src = (int64_t)P.ancestors[i];
-            for (int k0 = 0; k0 < P.n_loads; k0 += 8) {
-                double tmp[8];
+    constexpr int64_t TILE = (int64_t)WS_VM_BLOCK * WS_VM_P;
+    const int64_t n_tiles = (P.n + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t idx[WS_VM_P];   // clamped (always valid) index of the thread's j-th particle
+        bool live[WS_VM_P];
+        uint64_t particle[WS_VM_P];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+        for (int j = 0; j < WS_VM_P; ++j) {
+            const int64_t i = tile * TILE + (int64_t)j * WS_VM_BLOCK + threadIdx.x;
+            live[j] = i < P.n;
+            idx[j] = live[j] ? i : P.n - 1;
+            particle[j] = (uint64_t)(P.particle_offset + idx[j]);
+        }
+        // ---- loads ------------------------------------------------------------------------------
+        {
+            int64_t src[WS_VM_P];
+#pragma unroll
+            for (int j = 0; j < WS_VM_P; ++j) src[j] = idx[j];
+            if (P.load_gather != 0u) {
+#pragma unroll
+                for (int j = 0; j < WS_VM_P; ++j) src[j] = (int64_t)__ldg(P.ancestors + idx[j]);
+            }
+            for (int k0 = 0; k0 < P.n_loads; k0 += 4) {
+                double tmp[4][WS_VM_P];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
                     if (k0 + k < P.n_loads) {
-                        const int64_t idx = ((P.load_gather >> (k0 + k)) & 1u) ? src : i;
-                        tmp[k] = __ldg(P.load_ptr[k0 + k] + idx);
+                        const bool g = (P.load_gather >> (k0 + k)) & 1u;
+                        const double* __restrict__ ptr = P.load_ptr[k0 + k];
+#pragma unroll
+                        for (int j = 0; j < WS_VM_P; ++j) tmp[k][j] = __ldg(ptr + (g ? src[j] : idx[j]));
                     }
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    if (k0 + k < P.n_loads) R[(int)P.load_reg[k0 + k] * WS_VM_BLOCK] = tmp[k];
+                for (int k = 0; k < 4; ++k) {
+                    if (k0 + k < P.n_loads) {
+                        double* dst = R + (int)P.load_reg[k0 + k] * RS;
+#pragma unroll
+                        for (int j = 0; j < WS_VM_P; ++j) dst[j * WS_VM_BLOCK] = tmp[k][j];
+                    }
                 }
             }
         }
-        double lw_old = 0.0;
-        if (P.logw_mode == 1 || P.n_expect > 0) lw_old = P.logw[i];
-
-        // ---- program ----------------------------------------------------------------------
-        double acc = 0.0;
-        const uint64_t particle = (uint64_t)(P.particle_offset + i);
-        for (int pc = 0; pc < P.n_ops; ++pc) {
-            ws_vm_exec<WS_VM_BLOCK>(P.ops[pc], R, acc, P.rng, particle);
+        double lw_old[WS_VM_P];
+#pragma unroll
+        for (int j = 0; j < WS_VM_P; ++j) lw_old[j] = 0.0;
+        if (P.logw_mode == 1 || P.n_expect > 0) {
+#pragma unroll
+            for (int j = 0; j < WS_VM_P; ++j) lw_old[j] = P.logw[idx[j]];
         }
 
-        // ---- stores -----------------------------------------------------------------------
-        for (int k = 0; k < P.n_stores; ++k) P.store_ptr[k][i] = R[(int)P.store_reg[k] * WS_VM_BLOCK];
+        // ---- program ------------------------------------------------------------------------------
+        double acc[WS_VM_P];
+#pragma unroll
+        for (int j = 0; j < WS_VM_P; ++j) acc[j] = 0.0;
+        for (int pc = 0; pc < P.n_ops; ++pc) {
+            ws_vm_exec<WS_VM_BLOCK, WS_VM_P>(P.ops[pc], R, acc, P.rng, particle);
+        }
+
+        // ---- stores ---------------------------------------------------------------------------------
+        for (int k = 0; k < P.n_stores; ++k) {
+            const double* srcr = R + (int)P.store_reg[k] * RS;
+            double* __restrict__ ptr = P.store_ptr[k];
+#pragma unroll
+            for (int j = 0; j < WS_VM_P; ++j)
+                if (live[j]) ptr[idx[j]] = srcr[j * WS_VM_BLOCK];
+        }
         if (P.logw_mode != 0) {
-            const double lw = (P.logw_mode == 1 ? lw_old : P.logw_base) + acc;
-            P.logw[i] = lw;
-            lse_push(part, lw);
+#pragma unroll
+            for (int j = 0; j < WS_VM_P; ++j) {
+                if (live[j]) {
+                    const double lw = (P.logw_mode == 1 ? lw_old[j] : P.logw_base) + acc[j];
+                    P.logw[idx[j]] = lw;
+                    lse_push(part, lw);
+                }
+            }
         }
         if (P.n_expect > 0) {
-            const double w = exp(lw_old - red_m) * red_invS;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                if (k < P.n_expect) esum[k] += w * R[(int)P.expect_reg[k] * WS_VM_BLOCK];
+            for (int j = 0; j < WS_VM_P; ++j) {
+                if (live[j]) {
+                    const double w = exp(lw_old[j] - red_m) * red_invS;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        if (k < P.n_expect) esum[k] += w * R[(int)P.expect_reg[k] * RS + j * WS_VM_BLOCK];
+                    }
+                }
             }
         }
     }
@@ -172,13 +219,13 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, 3) ws_vm_kernel(const __grid_cons
     }
 }
 
-int ws_vm_smem_bytes(int n_regs) { return (n_regs < 1 ? 1 : n_regs) * WS_VM_BLOCK * (int)sizeof(double); }
+int ws_vm_smem_bytes(int n_regs) { return (n_regs < 1 ? 1 : n_regs) * WS_VM_BLOCK * WS_VM_P * (int)sizeof(double); }
 
 int ws_vm_max_grid(int n_regs, int sm_count) {
     // resident CTAs per SM limited by the shared-memory register file and 2048 threads / SM
     const int smem = ws_vm_smem_bytes(n_regs) + 1024;
     int per_sm = (227 * 1024) / smem;
-    if (per_sm > 2048 / WS_VM_BLOCK) per_sm = 2048 / WS_VM_BLOCK;
+    if (per_sm > 4) per_sm = 4;  // __launch_bounds__(WS_VM_BLOCK, 4)
     if (per_sm < 1) per_sm = 1;
     return per_sm * sm_count;
 }
@@ -264,19 +311,26 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// slot -> uniform providers
-struct RStratified {
+// slot -> uniform provider.  Philox mode: one Philox block serves two neighbouring slots
+// (slot k uses words (2(k&1), 2(k&1)+1) of block k>>1); the last block is cached because
+// consecutive particles ask for the same or neighbouring slots.
+struct SlotUniform {
+    int scheme;  // 0 stratified, 1 systematic
     uint64_t seed, stream;
     const double* replay;
-    __device__ __forceinline__ double operator()(int64_t k) const {
-        if (replay != nullptr) return replay[k];
-        ws_u32x4 r = ws_philox4x32_10((uint64_t)k, stream, seed);
-        return ws_u01(r.x, r.y);
-    }
-};
-struct RSystematic {
     double r0;
-    __device__ __forceinline__ double operator()(int64_t) const { return r0; }
+    int64_t cached_blk;
+    ws_u32x4 cached;
+    __device__ __forceinline__ double operator()(int64_t k) {
+        if (scheme == 1) return r0;
+        if (replay != nullptr) return replay[k];
+        const int64_t blk = k >> 1;
+        if (blk != cached_blk) {
+            cached = ws_philox4x32_10((uint64_t)blk, stream, seed);
+            cached_blk = blk;
+        }
+        return (k & 1) ? ws_u01(cached.z, cached.w) : ws_u01(cached.x, cached.y);
+    }
 };
 
 // F(C) for an arbitrary ascending uniform array: #{n : u_n <= C}  (icdf with caller uniforms, multinomial)
@@ -289,23 +343,25 @@ __device__ __forceinline__ int64_t ws_count_sorted_le(const double* __restrict__
     return lo;
 }
 
-__device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double inv_n, double r0) {
+__device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double inv_n, SlotUniform& su) {
     if (P.sorted_u != nullptr) return ws_count_sorted_le(P.sorted_u, P.n, C);
-    if (P.scheme == 1) {
-        RSystematic r{r0};
-        return ws_count_slots_le(C, P.n, inv_n, r);
-    }
-    RStratified r{P.seed, P.stream, P.replay_u};
-    return ws_count_slots_le(C, P.n, inv_n, r);
+    return ws_count_slots_le(C, P.n, inv_n, su);
 }
+
+#define WS_EXPAND_CHUNK 4096   // output slots staged in shared memory per round
+#define WS_DIRECT_MAX 8        // offspring a thread writes itself; larger families are filled by the CTA
+#define WS_HEAVY_TILE (64 * WS_EXPAND_CHUNK)  // tiles with more offspring than this go to the heavy kernel
 
 __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
 
-    __shared__ int32_t Fs[WS_SCAN_TILE];                     // F(C_m) for the tile's particles
+    __shared__ int32_t Fs[WS_SCAN_TILE];          // F(C_m) for the tile's particles
+    __shared__ int32_t out_s[WS_EXPAND_CHUNK];    // ancestors of one chunk of output slots
+    __shared__ uint16_t big_items[WS_SCAN_TILE];  // items with more than WS_DIRECT_MAX offspring
     __shared__ unsigned long long warp_tot[WS_SCAN_BLOCK / 32];
-    __shared__ unsigned long long s_excl;                    // tile exclusive prefix (fixed point)
+    __shared__ unsigned long long s_excl;         // tile exclusive prefix (fixed point)
     __shared__ int s_tile;
+    __shared__ int s_nbig;
     __shared__ int64_t s_fstart;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -317,20 +373,29 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __g
         m = P.red->m;
         Sden = P.red->S;  // divide (not multiply by a reciprocal): w = e / S as exp_norm does
     }
-    double r0 = 0.0;
+    SlotUniform su;
+    su.scheme = (P.scheme == 1) ? 1 : 0;
+    su.seed = P.seed;
+    su.stream = P.stream;
+    su.replay = P.replay_u;
+    su.r0 = 0.0;
+    su.cached_blk = -1;
     if (P.scheme == 1 && P.sorted_u == nullptr) {
         if (P.replay_u != nullptr) {
-            r0 = P.replay_u[0];
+            su.r0 = P.replay_u[0];
         } else {
             ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
-            r0 = ws_u01(r.x, r.y);
+            su.r0 = ws_u01(r.x, r.y);
         }
     }
     const double uniform_w = 1.0 / (double)n;
 
     while (true) {
-        __syncthreads();  // protects s_tile / Fs reuse across iterations
-        if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();  // protects the shared arrays across iterations
+        if (threadIdx.x == 0) {
+            s_tile = (int)atomicAdd(P.tile_counter, 1u);
+            s_nbig = 0;
+        }
         __syncthreads();
         const int tile = s_tile;
         if (tile >= n_tiles) break;
@@ -425,7 +490,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __g
                 s_excl = excl;
                 // F at the tile's left edge; by definition 0 for the first particle (a slot with
                 // u = 0 belongs to particle 1, as in icdf)
-                s_fstart = (tile == 0) ? 0 : ws_F(P, ws_fxs_to_double(excl), inv_n, r0);
+                s_fstart = (tile == 0) ? 0 : ws_F(P, ws_fxs_to_double(excl), inv_n, su);
             }
         }
         __syncthreads();
@@ -433,27 +498,109 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __g
         const int64_t fstart = s_fstart;
 
         // ---- per-particle F(C_m) -----------------------------------------------------------------
+        int32_t f[WS_SCAN_ITEMS];
 #pragma unroll
         for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
             const int64_t gi = item0 + k;
-            int64_t f;
+            int64_t fk;
             if (gi >= n) {
-                f = n;
+                fk = n;
             } else if (gi == n - 1) {
-                const int64_t ff = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, r0);
+                const int64_t ff = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, su);
                 if (ff < n) atomicAdd(P.n_clamped, (unsigned long long)(n - ff));
-                f = n;  // leftover slots go to the last particle (the reference would throw BoundsError)
+                fk = n;  // leftover slots go to the last particle (the reference would throw BoundsError)
             } else {
-                f = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, r0);
+                fk = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, su);
             }
-            Fs[threadIdx.x * WS_SCAN_ITEMS + k] = (int32_t)f;
+            f[k] = (int32_t)fk;
+            Fs[threadIdx.x * WS_SCAN_ITEMS + k] = f[k];
         }
         __syncthreads();
         const int64_t fend = (int64_t)Fs[WS_SCAN_TILE - 1];
+        const int64_t f_prev0 = (threadIdx.x == 0) ? fstart : (int64_t)Fs[threadIdx.x * WS_SCAN_ITEMS - 1];
 
-        // ---- expand: every output slot of this tile finds its ancestor by binary search ----------
-        for (int64_t j = fstart + threadIdx.x; j < fend; j += WS_SCAN_BLOCK) {
-            int lo = 0, hi = WS_SCAN_TILE - 1;  // smallest k with Fs[k] > j  (exists: Fs[last] = fend > j)
+        if (fend - fstart > (int64_t)WS_HEAVY_TILE) {
+            // a few particles own a huge share of the offspring: publish the tile's F table and let
+            // ws_expand_heavy_kernel fill its slots with the whole grid
+            __shared__ unsigned int s_slot;
+            if (threadIdx.x == 0) s_slot = atomicAdd(P.heavy_count, 1u);
+            __syncthreads();
+            const unsigned int slot = s_slot;
+            int32_t* dst = P.heavy_F + (size_t)slot * (WS_SCAN_TILE + 2);
+            for (int k = threadIdx.x; k < WS_SCAN_TILE; k += WS_SCAN_BLOCK) dst[k] = Fs[k];
+            if (threadIdx.x == 0) {
+                dst[WS_SCAN_TILE] = (int32_t)fstart;
+                dst[WS_SCAN_TILE + 1] = tile;
+            }
+            continue;
+        }
+
+        // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m, staged per chunk ------------
+        // register the families too large for one thread
+        {
+            int64_t lo = f_prev0;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                const int64_t hi = f[k];
+                if (hi - lo > WS_DIRECT_MAX) {
+                    const int pos = atomicAdd(&s_nbig, 1);
+                    big_items[pos] = (uint16_t)(threadIdx.x * WS_SCAN_ITEMS + k);
+                }
+                lo = hi;
+            }
+        }
+        for (int64_t chunk = fstart; chunk < fend; chunk += WS_EXPAND_CHUNK) {
+            const int64_t chunk_end = (chunk + WS_EXPAND_CHUNK < fend) ? chunk + WS_EXPAND_CHUNK : fend;
+            {
+                int64_t lo = f_prev0;
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                    const int64_t hi = f[k];
+                    if (hi - lo <= WS_DIRECT_MAX && hi > chunk && lo < chunk_end) {
+                        const int32_t anc = (int32_t)(item0 + k);
+                        for (int64_t pos = (lo > chunk ? lo : chunk); pos < (hi < chunk_end ? hi : chunk_end); ++pos)
+                            out_s[pos - chunk] = anc;
+                    }
+                    lo = hi;
+                }
+            }
+            __syncthreads();  // also makes s_nbig / big_items visible
+            const int nbig = s_nbig;
+            for (int b = 0; b < nbig; ++b) {
+                const int it = big_items[b];
+                const int64_t lo = (it == 0) ? fstart : (int64_t)Fs[it - 1];
+                const int64_t hi = (int64_t)Fs[it];
+                const int64_t a = lo > chunk ? lo : chunk, e = hi < chunk_end ? hi : chunk_end;
+                const int32_t anc = (int32_t)(tile_base + it);
+                for (int64_t pos = a + threadIdx.x; pos < e; pos += WS_SCAN_BLOCK) out_s[pos - chunk] = anc;
+            }
+            __syncthreads();
+            for (int64_t pos = chunk + threadIdx.x; pos < chunk_end; pos += WS_SCAN_BLOCK) P.ancestors[pos] = out_s[pos - chunk];
+            __syncthreads();
+        }
+    }
+}
+
+// Slots of the heavy tiles (see above): every CTA takes an equal slice of each heavy tile's output
+// window and finds the ancestors by binary search in the tile's F table.
+__global__ void __launch_bounds__(256) ws_expand_heavy_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+    __shared__ int32_t Fs[WS_SCAN_TILE];
+    const unsigned int n_heavy = *P.heavy_count;
+    for (unsigned int h = 0; h < n_heavy; ++h) {
+        const int32_t* src = P.heavy_F + (size_t)h * (WS_SCAN_TILE + 2);
+        __syncthreads();
+        for (int k = threadIdx.x; k < WS_SCAN_TILE; k += 256) Fs[k] = src[k];
+        __syncthreads();
+        const int64_t fstart = (int64_t)src[WS_SCAN_TILE];
+        const int64_t tile_base = (int64_t)src[WS_SCAN_TILE + 1] * WS_SCAN_TILE;
+        const int64_t fend = (int64_t)Fs[WS_SCAN_TILE - 1];
+        const int64_t len = fend - fstart;
+        const int64_t per = (len + gridDim.x - 1) / gridDim.x;
+        const int64_t a = fstart + (int64_t)blockIdx.x * per;
+        const int64_t e = (a + per < fend) ? a + per : fend;
+        for (int64_t j = a + threadIdx.x; j < e; j += 256) {
+            int lo = 0, hi = WS_SCAN_TILE - 1;  // smallest k with Fs[k] > j
             while (lo < hi) {
                 const int mid = (lo + hi) >> 1;
                 if ((int64_t)Fs[mid] > j) hi = mid; else lo = mid + 1;
@@ -465,6 +612,9 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __g
 
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
     ws_scan_search_kernel<<<grid, WS_SCAN_BLOCK, 0, s>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);
     return cudaGetLastError();
 }
 

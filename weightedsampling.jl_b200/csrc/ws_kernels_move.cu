@@ -41,7 +41,8 @@ __device__ __forceinline__ void ws_score_load_planes(const WsScoreParams& S, dou
 }
 
 __device__ __forceinline__ double ws_score_fold(const WsScoreParams& S, double* R, uint64_t particle) {
-    double acc = 0.0;
+    double acc[1] = {0.0};
+    const uint64_t pid[1] = {particle};
     WsRng none;
     none.seed = 0;
     none.replay_n = nullptr;
@@ -49,9 +50,9 @@ __device__ __forceinline__ double ws_score_fold(const WsScoreParams& S, double* 
     none.replay_e = nullptr;
     for (int pc = 0; pc < S.n_ops; ++pc) {
         const WsOp o = ws_load_op(S.ops, pc);
-        ws_vm_exec<WS_MOVE_BLOCK>(o, R, acc, none, particle);
+        ws_vm_exec<WS_MOVE_BLOCK, 1>(o, R, acc, none, pid);
     }
-    return acc;
+    return acc[0];
 }
 
 __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_score_kernel(const __grid_constant__ WsScoreParams S) {

@@ -178,7 +178,8 @@ WS_HD double ws_log_abs_jacobian(double z, double lo, double hi, int kind) {
 // ---------------------------------------------------------------------------
 // The explicit _rn intrinsics stop nvcc from contracting the expression into an
 // FMA (Julia does not contract), so u_n is bit-identical to the reference's.
-WS_HD double ws_slot_u(int64_t n0, double r, double inv_n) {
+template <class I>
+WS_HD double ws_slot_u(I n0, double r, double inv_n) {
 #if defined(__CUDA_ARCH__)
     return __dadd_rn(__dmul_rn((double)n0, inv_n), __dmul_rn(r, inv_n));
 #else
@@ -211,21 +212,28 @@ WS_HD double ws_fx_to_double(uint64_t c) { return (double)c * (1.0 / WS_FX_SCALE
 // restates icdf's  a_n = min{ m : C_m >= u_n }  (src/resampling.jl:13-26) per particle
 // instead of per slot.  `r` is any callable slot -> uniform in [0,1).
 template <class RFn>
-WS_HD int64_t ws_count_slots_le(double C, int64_t N, double inv_n, RFn r) {
-    double t = C * (double)N;
-    int64_t k = (t >= (double)N) ? N : (t > 0.0 ? (int64_t)t : 0);
+WS_HD int64_t ws_count_slots_le(double C, int64_t N, double inv_n, RFn& r) {
+    // Invariant wanted on exit: u(k-1) <= C (or k == 0) and u(k) > C (or k == N).  A uniform is only
+    // drawn when the cheap bounds  fl(k*invN) <= u(k) <= fl(fl(k*invN) + invN)  cannot decide, which
+    // leaves about one draw per call.  N < 2^31 (Int32 ancestors), so k fits an int.
+    const double t = C * (double)N;
+    int k = (t >= (double)N) ? (int)N : (t > 0.0 ? (int)t : 0);
+    const int n = (int)N;
     bool advanced = false;
-    while (k < N && ws_slot_u(k, r(k), inv_n) <= C) {
-        ++k;
-        advanced = true;
-    }
-    if (!advanced) {
-        // u(k-1) <= fl((k-1)*invN + invN) always; only draw r(k-1) when C is below that bound.
-        while (k > 0) {
-            double ub = ws_slot_u(k - 1, 1.0, inv_n);  // fl(fl((k-1)*invN) + invN) >= u(k-1)
-            if (C >= ub) break;
-            if (ws_slot_u(k - 1, r(k - 1), inv_n) > C) --k; else break;
+    while (k < n) {
+        if (C < ws_slot_u(k, 0.0, inv_n)) break;  // u(k) >= fl(k*invN) > C
+        if (ws_slot_u(k, r((int64_t)k), inv_n) <= C) {
+            ++k;
+            advanced = true;
+        } else {
+            break;
         }
     }
-    return k;
+    if (!advanced) {
+        while (k > 0) {
+            if (C >= ws_slot_u(k - 1, 1.0, inv_n)) break;  // u(k-1) <= fl(fl((k-1)*invN) + invN) <= C
+            if (ws_slot_u(k - 1, r((int64_t)(k - 1)), inv_n) > C) --k; else break;
+        }
+    }
+    return (int64_t)k;
 }

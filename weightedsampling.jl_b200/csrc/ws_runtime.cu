@@ -80,7 +80,9 @@ struct ws_ctx {
     // resampling scratch
     int32_t* d_anc = nullptr;
     unsigned long long* d_tile_words = nullptr;
-    unsigned int* d_tile_counter = nullptr;
+    unsigned int* d_tile_counter = nullptr;  // [0] dynamic tile id, [1] heavy-tile count
+    int32_t* d_heavy_F = nullptr;
+    int64_t heavy_cap_n = 0;                  // particle count d_heavy_F is sized for
     int64_t n_tiles = 0;
     unsigned long long* d_counters = nullptr;  // [0] clamped slots (cumulative), [1] clamped (host-array calls), [2] MH accepts
 
@@ -303,7 +305,7 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     CKC(cudaMalloc(&c->d_anc, sizeof(int32_t) * (size_t)c->n));
     c->n_tiles = (c->n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     CKC(cudaMalloc(&c->d_tile_words, sizeof(unsigned long long) * (size_t)c->n_tiles));
-    CKC(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int)));
+    CKC(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int) * 2));
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 4));
     CKC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
 #undef CKC
@@ -337,6 +339,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_anc);
     cudaFree(c->d_tile_words);
     cudaFree(c->d_tile_counter);
+    cudaFree(c->d_heavy_F);
     cudaFree(c->d_counters);
     cudaFree(c->d_score_ops);
     cudaFree(c->d_replay_n);
@@ -412,7 +415,8 @@ static int flush_window(ws_ctx* c) {
     } else {
         P.logw_mode = 0;
     }
-    const int grid = std::min(ws_vm_max_grid(P.n_regs, c->sm_count), (int)((c->n + WS_VM_BLOCK - 1) / WS_VM_BLOCK));
+    const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
+    const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, c->sm_count), (c->n + vm_tile - 1) / vm_tile);
     P.partials = w.has_acc ? c->d_partials : nullptr;
     P.n_expect = 0;
     P.rng.seed = c->seed;
@@ -889,8 +893,19 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
                            const double* d_sorted_u, int32_t* d_anc, unsigned long long* d_words, uint64_t stream_id,
                            unsigned long long* d_clamped) {
     const int64_t n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    if (c->d_heavy_F == nullptr || c->heavy_cap_n < n) {
+        // at most n / WS_HEAVY_TILE_SLOTS tiles can own more than WS_HEAVY_TILE_SLOTS offspring each
+        if (c->d_heavy_F) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            CK(c, cudaFree(c->d_heavy_F));
+            c->d_heavy_F = nullptr;
+        }
+        const size_t slots = (size_t)(n / WS_HEAVY_TILE_SLOTS) + 2;
+        CK(c, cudaMalloc(&c->d_heavy_F, sizeof(int32_t) * slots * (WS_SCAN_TILE + 2)));
+        c->heavy_cap_n = n;
+    }
     CK(c, cudaMemsetAsync(d_words, 0, sizeof(unsigned long long) * (size_t)n_tiles, c->stream));
-    CK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), c->stream));
+    CK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int) * 2, c->stream));
     WsScanParams S;
     memset(&S, 0, sizeof(S));
     S.logw = d_w;
@@ -907,6 +922,8 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     S.tile_words = d_words;
     S.tile_counter = c->d_tile_counter;
     S.n_clamped = d_clamped;
+    S.heavy_count = c->d_tile_counter + 1;
+    S.heavy_F = c->d_heavy_F;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * 4);
     TimedEvent te;
     timed_begin(c, KC_SCAN, te);
@@ -1180,7 +1197,8 @@ extern "C" int ws_expectation(ws_ctx* c, const ws_expr* f, int32_t n_exprs, doub
     P.n_expect = n_exprs;
     for (int k = 0; k < n_exprs; ++k) P.expect_reg[k] = (uint8_t)regs[k];
     P.red = c->d_red;
-    const int grid = std::max(1, std::min(ws_vm_max_grid(P.n_regs, c->sm_count), (int)((c->n + WS_VM_BLOCK - 1) / WS_VM_BLOCK)));
+    const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ws_vm_max_grid(P.n_regs, c->sm_count), (c->n + vm_tile - 1) / vm_tile));
     TRY(ensure_scratch(c, sizeof(double) * (size_t)grid * 8));
     TRY(ensure_h_scratch(c, sizeof(double) * (size_t)grid * 8));
     P.expect_partials = c->d_scratch;

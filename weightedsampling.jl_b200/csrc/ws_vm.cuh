@@ -82,124 +82,185 @@ WS_HD uint64_t ws_double_bits(double v) {
 #endif
 }
 
-// R points at this thread's column of the shared-memory register file; register k is R[k*STRIDE].
+// Register file layout: register r of the thread's j-th particle lives at R[(r*P + j)*STRIDE], where R
+// points at this thread's column of the shared-memory register file.  One decoded micro-op is applied
+// to all P particles of the thread, which amortises the (warp-uniform) decode over P particles and
+// gives P independent dependency chains per thread.  P = 1, STRIDE = 1 is the plain scalar form.
 // (WS_HD: the host instantiation exists only for tests/host/, which runs lowered programs through
 // this very interpreter on the CPU to check the lowering without a GPU.)
-template <int STRIDE>
-WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double& acc,
-                                           const WsRng& rng, uint64_t particle) {
+template <int STRIDE, int P>
+WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], const WsRng& rng,
+                      const uint64_t (&particle)[P]) {
     const uint32_t op = o.w0 & 0xFFu;
     const uint32_t dst = (o.w0 >> 8) & 0xFFu;
     const uint32_t a = (o.w0 >> 16) & 0xFFu;
     const uint32_t b = (o.w0 >> 24) & 0xFFu;
     const uint32_t c = o.w1 & 0xFFu;
     const uint32_t imm = o.w1 >> 8;
+    double* const Rd = R + dst * (P * STRIDE);
+    const double* const Ra = R + a * (P * STRIDE);
+    const double* const Rb = R + b * (P * STRIDE);
+    const double* const Rc = R + c * (P * STRIDE);
+    const double k0 = o.k0, k1 = o.k1, k2 = o.k2;
     switch (op) {
         case WS_OP_LIN2: {
-            double v = o.k0;
-            if (a != WS_REG_NONE) v += o.k1 * R[a * STRIDE];
-            if (b != WS_REG_NONE) v += o.k2 * R[b * STRIDE];
-            R[dst * STRIDE] = v;
+            if (a == WS_REG_NONE && b == WS_REG_NONE) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0;
+            } else if (a == WS_REG_NONE) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k2 * Rb[j * STRIDE];
+            } else if (b == WS_REG_NONE) {
+#pragma unroll
+                for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k1 * Ra[j * STRIDE];
+            } else {
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    double v = k0 + k1 * Ra[j * STRIDE];
+                    Rd[j * STRIDE] = v + k2 * Rb[j * STRIDE];
+                }
+            }
         } break;
         case WS_OP_MUL: {
-            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
-            double B = (b == WS_REG_NONE) ? o.k2 : R[b * STRIDE];
-            R[dst * STRIDE] = o.k0 * A * B;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                Rd[j * STRIDE] = k0 * A * B;
+            }
         } break;
         case WS_OP_DIV: {
-            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
-            double B = (b == WS_REG_NONE) ? o.k2 : R[b * STRIDE];
-            R[dst * STRIDE] = o.k0 * A / B;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                Rd[j * STRIDE] = k0 * A / B;
+            }
         } break;
         case WS_OP_UNARY: {
-            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
-            double v;
-            switch (imm) {
-                case WS_UN_EXP: v = exp(A); break;
-                case WS_UN_LOG: v = log(A); break;
-                case WS_UN_SQRT: v = sqrt(A); break;
-                case WS_UN_SIN: v = sin(A); break;
-                case WS_UN_COS: v = cos(A); break;
-                case WS_UN_ABS: v = fabs(A); break;
-                default: v = A * A; break;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                double v;
+                switch (imm) {
+                    case WS_UN_EXP: v = exp(A); break;
+                    case WS_UN_LOG: v = log(A); break;
+                    case WS_UN_SQRT: v = sqrt(A); break;
+                    case WS_UN_SIN: v = sin(A); break;
+                    case WS_UN_COS: v = cos(A); break;
+                    case WS_UN_ABS: v = fabs(A); break;
+                    default: v = A * A; break;
+                }
+                Rd[j * STRIDE] = v;
             }
-            R[dst * STRIDE] = v;
         } break;
         case WS_OP_POW: {
-            double A = (a == WS_REG_NONE) ? o.k1 : R[a * STRIDE];
-            double B = (b == WS_REG_NONE) ? o.k2 : R[b * STRIDE];
-            R[dst * STRIDE] = pow(A, B);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                Rd[j * STRIDE] = pow(A, B);
+            }
         } break;
         case WS_OP_RANDN2: {
-            double z0, z1;
             if (rng.replay_n != nullptr) {
                 // k1 = base offset, k2 = stride (both exact integers), imm = component j
-                const int64_t base = (int64_t)o.k1 + (int64_t)particle * (int64_t)o.k2 + (int64_t)imm;
-                z0 = rng.replay_n[base];
-                z1 = (a != WS_REG_NONE) ? rng.replay_n[base + 1] : 0.0;
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    const int64_t base = (int64_t)k1 + (int64_t)particle[j] * (int64_t)k2 + (int64_t)imm;
+                    Rd[j * STRIDE] = rng.replay_n[base];
+                    if (a != WS_REG_NONE) const_cast<double*>(Ra)[j * STRIDE] = rng.replay_n[base + 1];
+                }
             } else {
-                ws_randn2(particle, ws_double_bits(o.k0), rng.seed, z0, z1);
+                const uint64_t stream = ws_double_bits(k0);
+#pragma unroll
+                for (int j = 0; j < P; ++j) {
+                    double z0, z1;
+                    ws_randn2(particle[j], stream, rng.seed, z0, z1);
+                    Rd[j * STRIDE] = z0;
+                    if (a != WS_REG_NONE) const_cast<double*>(Ra)[j * STRIDE] = z1;
+                }
             }
-            R[dst * STRIDE] = z0;
-            if (a != WS_REG_NONE) R[a * STRIDE] = z1;
         } break;
         case WS_OP_RANDEXP: {
-            double e;
-            if (rng.replay_e != nullptr) {
-                e = rng.replay_e[(int64_t)o.k1 + (int64_t)particle * (int64_t)o.k2 + (int64_t)imm];
-            } else {
-                e = ws_randexp(particle, ws_double_bits(o.k0), rng.seed);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double e;
+                if (rng.replay_e != nullptr) {
+                    e = rng.replay_e[(int64_t)k1 + (int64_t)particle[j] * (int64_t)k2 + (int64_t)imm];
+                } else {
+                    e = ws_randexp(particle[j], ws_double_bits(k0), rng.seed);
+                }
+                Rd[j * STRIDE] = e;
             }
-            R[dst * STRIDE] = e;
         } break;
         case WS_OP_RANDU: {
-            double u;
-            if (rng.replay_u != nullptr) {
-                u = rng.replay_u[(int64_t)o.k1 + (int64_t)particle * (int64_t)o.k2 + (int64_t)imm];
-            } else {
-                double u1;
-                ws_randu2(particle, ws_double_bits(o.k0), rng.seed, u, u1);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double u;
+                if (rng.replay_u != nullptr) {
+                    u = rng.replay_u[(int64_t)k1 + (int64_t)particle[j] * (int64_t)k2 + (int64_t)imm];
+                } else {
+                    double u1;
+                    ws_randu2(particle[j], ws_double_bits(k0), rng.seed, u, u1);
+                }
+                Rd[j * STRIDE] = u;
             }
-            R[dst * STRIDE] = u;
         } break;
         case WS_OP_LOGPDF_NORMAL: {
-            double X = (a == WS_REG_NONE) ? o.k0 : R[a * STRIDE];
-            double MU = (b == WS_REG_NONE) ? o.k1 : R[b * STRIDE];
-            double SG = (c == WS_REG_NONE) ? o.k2 : R[c * STRIDE];
-            acc += ws_normal_logpdf(X, MU, SG);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double X = (a == WS_REG_NONE) ? k0 : Ra[j * STRIDE];
+                const double MU = (b == WS_REG_NONE) ? k1 : Rb[j * STRIDE];
+                const double SG = (c == WS_REG_NONE) ? k2 : Rc[j * STRIDE];
+                acc[j] += ws_normal_logpdf(X, MU, SG);
+            }
         } break;
         case WS_OP_LOGPDF_NORMAL_CS: {
             // constant sigma > 0, hoisted by the host: k1 = 1/sigma, k2 = -log(2pi)/2 - log(sigma).
             // D = X - MU with MU = r[b] (always a register) and X = r[a] or the constant k0.
-            double X = (a == WS_REG_NONE) ? o.k0 : R[a * STRIDE];
-            double z = (X - R[b * STRIDE]) * o.k1;
-            acc += o.k2 - 0.5 * (z * z);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double X = (a == WS_REG_NONE) ? k0 : Ra[j * STRIDE];
+                const double z = (X - Rb[j * STRIDE]) * k1;
+                acc[j] += k2 - 0.5 * (z * z);
+            }
         } break;
         case WS_OP_LOGPDF_EXPON: {
-            double X = (a == WS_REG_NONE) ? o.k0 : R[a * STRIDE];
-            double TH = (b == WS_REG_NONE) ? o.k1 : R[b * STRIDE];
-            acc += ws_exponential_logpdf(X, TH);
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double X = (a == WS_REG_NONE) ? k0 : Ra[j * STRIDE];
+                const double TH = (b == WS_REG_NONE) ? k1 : Rb[j * STRIDE];
+                acc[j] += ws_exponential_logpdf(X, TH);
+            }
         } break;
         case WS_OP_ACC_LIN2: {
-            double v = o.k0;
-            if (a != WS_REG_NONE) v += o.k1 * R[a * STRIDE];
-            if (b != WS_REG_NONE) v += o.k2 * R[b * STRIDE];
-            acc += v;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double v = k0;
+                if (a != WS_REG_NONE) v += k1 * Ra[j * STRIDE];
+                if (b != WS_REG_NONE) v += k2 * Rb[j * STRIDE];
+                acc[j] += v;
+            }
         } break;
         case WS_OP_ACC_QUAD2: {
-            double v = o.k0;
-            if (a != WS_REG_NONE) {
-                double t = R[a * STRIDE];
-                v += o.k1 * t * t;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double v = k0;
+                if (a != WS_REG_NONE) {
+                    const double t = Ra[j * STRIDE];
+                    v += k1 * t * t;
+                }
+                if (b != WS_REG_NONE) {
+                    const double t = Rb[j * STRIDE];
+                    v += k2 * t * t;
+                }
+                acc[j] += v;
             }
-            if (b != WS_REG_NONE) {
-                double t = R[b * STRIDE];
-                v += o.k2 * t * t;
-            }
-            acc += v;
         } break;
         case WS_OP_ACC_SCALE: {
-            acc = o.k0 * acc;
+#pragma unroll
+            for (int j = 0; j < P; ++j) acc[j] = k0 * acc[j];
         } break;
         default: break;
     }
