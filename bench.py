@@ -50,9 +50,14 @@ end
 P_PLANES = 6
 # algorithmic bytes per particle-update (SURVEY.md §8d, C2 filter-only, Int32 ancestors)
 ALG_BYTES_STEP = 224
-ALG_BYTES_GATHER = 4 + 16 * P_PLANES          # read ancestor + read/write 6 planes
-ALG_BYTES_PASS = 8 * (4 + 6) + 16             # propagate+observe: read x,v; write x,v,dv; logw RMW
+ALG_BYTES_GATHER = 4 + 16 * P_PLANES          # eager mode only: read ancestor + read/write 6 planes
+ALG_BYTES_PASS_EAGER = 8 * (4 + 6) + 16       # propagate+observe: read x,v; write x,v,dv; logw RMW
+# deferred gather (default): the fused pass reads x,v THROUGH the ancestors (4 B index), writes x,v,dv and
+# writes logw = c + logpdf (after a resample the old log-weights are one scalar c: no read); dv is never
+# gathered because it is overwritten before it is read
+ALG_BYTES_PASS_LAZY = 4 + 8 * 4 + 8 * 6 + 8
 ALG_BYTES_SCAN = 8 + 4                        # read logw, write ancestor
+NECESSARY_BYTES_STEP_LAZY = ALG_BYTES_PASS_LAZY + ALG_BYTES_SCAN
 
 
 def synth_obs(T, seed=42):
@@ -158,6 +163,7 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=2_000_000)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager-gather", action="store_true", help="gather every column inside Resample (reference order of work)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -211,6 +217,8 @@ def main():
     end
     ''', particle_vars=("x", "v", "dv"))
 
+    if args.eager_gather:
+        st._call("ws_set_lazy_gather", 0)
     st._call("ws_set_timing", 1)
     st._call("ws_reset_kernel_times")
     stats0 = state.stats()
@@ -250,7 +258,8 @@ def main():
 
     peak, peak_src = measured_peaks()
     per_kernel = {}
-    for name, alg in (("gather", ALG_BYTES_GATHER), ("fused_pass", ALG_BYTES_PASS), ("scan_search", ALG_BYTES_SCAN)):
+    pass_bytes = ALG_BYTES_PASS_EAGER if args.eager_gather else ALG_BYTES_PASS_LAZY
+    for name, alg in (("gather", ALG_BYTES_GATHER), ("fused_pass", pass_bytes), ("scan_search", ALG_BYTES_SCAN)):
         k = kt[name]
         if k["launches"] > 0 and k["ms"] > 0:
             avg_ms = k["ms"] / k["launches"]
@@ -267,7 +276,13 @@ def main():
                     "per_kernel": per_kernel,
                     "whole_step": {"alg_bytes_per_particle": ALG_BYTES_STEP,
                                    "achieved_gbs": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9,
-                                   "frac": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9 / peak}}
+                                   "frac": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9 / peak,
+                                   "note": "224 B is SURVEY §8(d)'s figure for the reference's order of work (eager "
+                                           "6-plane gather); the deferred-gather design only has to move "
+                                           f"{NECESSARY_BYTES_STEP_LAZY} B per particle-update",
+                                   "necessary_bytes_per_particle": None if args.eager_gather else NECESSARY_BYTES_STEP_LAZY,
+                                   "frac_of_necessary": None if args.eager_gather else
+                                   NECESSARY_BYTES_STEP_LAZY * N * K / (dev_ms * 1e-3) / 1e9 / peak}}
 
     if rank == 0:
         cpu = None

@@ -279,6 +279,11 @@ int ws_get_clamped(ws_ctx* ctx, int64_t* out);
 #define WS_N_KERNEL_CLASSES 8
 int ws_kernel_times(ws_ctx* ctx, double* ms_out, int64_t* count_out, int32_t n_classes);
 int ws_reset_kernel_times(ws_ctx* ctx);
+/* resample!(store, indices) is deferred by default: after a resampling step each plane is gathered
+ * through the ancestors by the next kernel that reads it (and never, if it is overwritten first).
+ * on = 0 restores the reference's eager gather of every column inside ws_resample (stores.jl:105-111);
+ * results are identical either way. */
+int ws_set_lazy_gather(ws_ctx* ctx, int on);
 int ws_set_timing(ws_ctx* ctx, int on); /* record per-phase CUDA events (adds syncs; for profiling only) */
 /* raw cudaStream_t of the context (as void*), so a host can bracket calls with its own events */
 int ws_stream(ws_ctx* ctx, void** stream_out);

@@ -143,6 +143,7 @@ SIGNATURES = {
     "ws_kernel_times": (C.c_int, [_ctx, _dp, _i64p, C.c_int32]),
     "ws_reset_kernel_times": (C.c_int, [_ctx]),
     "ws_set_timing": (C.c_int, [_ctx, C.c_int]),
+    "ws_set_lazy_gather": (C.c_int, [_ctx, C.c_int]),
     "ws_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
 }
 

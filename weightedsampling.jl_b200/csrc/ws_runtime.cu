@@ -33,6 +33,10 @@ struct Column {
     std::string name;
     int32_t width;
     std::vector<double*> front, back;
+    // Lazy resample!: after a resampling step the gather of a plane is deferred until the plane is
+    // next read.  stale[k] means "front[k] still holds the pre-resample order; element i of the
+    // current particle set is front[k][d_anc[i]]".
+    std::vector<uint8_t> stale;
 };
 
 struct TimedEvent {
@@ -79,6 +83,8 @@ struct ws_ctx {
 
     // resampling scratch
     int32_t* d_anc = nullptr;
+    bool anc_pending = false;  // some plane is stale w.r.t. d_anc
+    bool lazy_gather = true;
     unsigned long long* d_tile_words = nullptr;
     unsigned int* d_tile_counter = nullptr;  // [0] dynamic tile id, [1] heavy-tile count
     int32_t* d_heavy_F = nullptr;
@@ -118,6 +124,8 @@ struct ws_ctx {
 
     std::string err;
 };
+
+static int materialize_planes(ws_ctx* c);
 
 // ------------------------------------------------------------------------------------------
 // error helpers
@@ -394,16 +402,32 @@ static int flush_window(ws_ctx* c) {
     P.n_loads = (int)w.loads.size();
     P.n_stores = (int)w.dirty.size();
     P.n_regs = std::max(1, w.high_water);
+    // Deferred resample!: a stale plane is read through the ancestors; if the window also writes it,
+    // the new values go to the back buffer (other threads still read the old order) and the buffers
+    // are swapped afterwards.  A stale plane that is only written never needs its gather at all.
+    P.ancestors = c->d_anc;
+    P.load_gather = 0u;
+    std::vector<Plane> swap_after;
     for (int k = 0; k < P.n_loads; ++k) {
-        P.load_ptr[k] = plane_ptr(c, w.loads[k].first);
+        const Plane pl = w.loads[k].first;
+        P.load_ptr[k] = plane_ptr(c, pl);
         P.load_reg[k] = (uint8_t)w.loads[k].second;
+        if (c->cols[pl.col].stale[pl.comp]) P.load_gather |= (1u << k);
     }
     for (int k = 0; k < P.n_stores; ++k) {
-        P.store_ptr[k] = plane_ptr(c, w.dirty[k]);
-        P.store_reg[k] = (uint8_t)w.plane_reg[w.dirty[k]];
+        const Plane pl = w.dirty[k];
+        Column& col = c->cols[pl.col];
+        P.store_reg[k] = (uint8_t)w.plane_reg[pl];
+        bool loaded = false;
+        for (auto& ld : w.loads)
+            if (ld.first == pl) loaded = true;
+        if (col.stale[pl.comp] && loaded) {
+            P.store_ptr[k] = col.back[pl.comp];
+            swap_after.push_back(pl);
+        } else {
+            P.store_ptr[k] = col.front[pl.comp];
+        }
     }
-    P.ancestors = nullptr;
-    P.load_gather = 0u;
     if (w.has_acc) {
         P.logw = c->logw;
         if (c->logw_uniform) {
@@ -429,6 +453,8 @@ static int flush_window(ws_ctx* c) {
     timed_begin(c, KC_VM, te);
     CK(c, ws_launch_vm(P, std::max(1, grid), c->stream));
     timed_end(c, te);
+    for (auto& pl : swap_after) std::swap(c->cols[pl.col].front[pl.comp], c->cols[pl.col].back[pl.comp]);
+    for (auto& pl : w.dirty) c->cols[pl.col].stale[pl.comp] = 0;  // written planes are in the current order
     c->stats.fused_passes++;
     c->stats.fused_statements += w.n_statements;
     if (w.has_acc) {
@@ -581,6 +607,7 @@ extern "C" int ws_col_ensure(ws_ctx* c, const char* name, int32_t width, int32_t
     Column col;
     col.name = name;
     col.width = width;
+    col.stale.assign((size_t)width, 0);
     for (int k = 0; k < width; ++k) {
         double *f = nullptr, *b = nullptr;
         CK(c, cudaMalloc(&f, sizeof(double) * (size_t)c->n));
@@ -626,6 +653,7 @@ extern "C" int ws_col_download(ws_ctx* c, int32_t id, double* host_out) {
     if (!c || !host_out) return WS_EINVAL;
     if (id < 0 || id >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", id);
     TRY(flush_window(c));
+    TRY(materialize_planes(c));
     const Column& col = c->cols[id];
     for (int k = 0; k < col.width; ++k)
         CK(c, cudaMemcpyAsync(host_out + (size_t)k * c->n, col.front[k], sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
@@ -637,7 +665,8 @@ extern "C" int ws_col_upload(ws_ctx* c, int32_t id, const double* host_in) {
     if (!c || !host_in) return WS_EINVAL;
     if (id < 0 || id >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", id);
     TRY(flush_window(c));
-    const Column& col = c->cols[id];
+    Column& col = c->cols[id];
+    for (auto& st : col.stale) st = 0;  // the whole column is overwritten: its deferred gather is moot
     for (int k = 0; k < col.width; ++k)
         CK(c, cudaMemcpyAsync(col.front[k], host_in + (size_t)k * c->n, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -865,28 +894,48 @@ static int ensure_reduced(ws_ctx* c) {
     return WS_OK;
 }
 
-static int gather_all(ws_ctx* c, const int32_t* d_anc) {
-    // resample!(store, indices): every plane front -> back through the ancestors, then swap
-    std::vector<std::pair<const double*, double*>> planes;
-    for (auto& col : c->cols)
-        for (int k = 0; k < col.width; ++k) planes.push_back({col.front[k], col.back[k]});
-    for (size_t p0 = 0; p0 < planes.size(); p0 += WS_GATHER_MAX_PLANES) {
+static int gather_planes(ws_ctx* c, const int32_t* d_anc, const std::vector<Plane>& which) {
+    // resample!(store, indices) for the given planes: front -> back through the ancestors, then swap
+    for (size_t p0 = 0; p0 < which.size(); p0 += WS_GATHER_MAX_PLANES) {
         WsGatherParams G;
         memset(&G, 0, sizeof(G));
         G.n = c->n;
         G.ancestors = d_anc;
-        G.n_planes = (int)std::min((size_t)WS_GATHER_MAX_PLANES, planes.size() - p0);
+        G.n_planes = (int)std::min((size_t)WS_GATHER_MAX_PLANES, which.size() - p0);
         for (int k = 0; k < G.n_planes; ++k) {
-            G.src[k] = planes[p0 + k].first;
-            G.dst[k] = planes[p0 + k].second;
+            const Plane pl = which[p0 + k];
+            G.src[k] = c->cols[pl.col].front[pl.comp];
+            G.dst[k] = c->cols[pl.col].back[pl.comp];
         }
         TimedEvent te;
         timed_begin(c, KC_GATHER, te);
         CK(c, ws_launch_gather(G, grid_for(c, c->n, 256, 8), c->stream));
         timed_end(c, te);
     }
-    for (auto& col : c->cols) std::swap(col.front, col.back);
+    for (auto& pl : which) {
+        std::swap(c->cols[pl.col].front[pl.comp], c->cols[pl.col].back[pl.comp]);
+        c->cols[pl.col].stale[pl.comp] = 0;
+    }
     return WS_OK;
+}
+
+// Apply the deferred gather to every plane that is still in pre-resample order.
+static int materialize_planes(ws_ctx* c) {
+    if (!c->anc_pending) return WS_OK;
+    std::vector<Plane> which;
+    for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
+        for (int32_t k = 0; k < c->cols[ci].width; ++k)
+            if (c->cols[ci].stale[k]) which.push_back(Plane{ci, k});
+    TRY(gather_planes(c, c->d_anc, which));
+    c->anc_pending = false;
+    return WS_OK;
+}
+
+static int gather_all(ws_ctx* c, const int32_t* d_anc) {
+    std::vector<Plane> which;
+    for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
+        for (int32_t k = 0; k < c->cols[ci].width; ++k) which.push_back(Plane{ci, k});
+    return gather_planes(c, d_anc, which);
 }
 
 static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, int64_t n, const double* d_replay_u,
@@ -959,8 +1008,17 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
             c->cur_u += need;
         }
         const uint64_t stream_id = c->next_stream++;
+        // planes still waiting for the PREVIOUS ancestors must be gathered before d_anc is overwritten
+        TRY(materialize_planes(c));
         TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, nullptr, c->d_anc, c->d_tile_words, stream_id, c->d_counters + 0));
-        TRY(gather_all(c, c->d_anc));
+        if (c->lazy_gather) {
+            // resample!(store, indices) is deferred: each plane is gathered when it is next read
+            for (auto& col : c->cols)
+                for (auto& st : col.stale) st = 1;
+            c->anc_pending = !c->cols.empty();
+        } else {
+            TRY(gather_all(c, c->d_anc));
+        }
         // fill!(state.weights, mean_logW): kept symbolic until somebody reads the array
         c->logw_uniform = true;
         c->logw_base = r.log_mean_w;
@@ -984,6 +1042,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
 extern "C" int ws_gather(ws_ctx* c, const int32_t* ancestors_host) {
     if (!c || !ancestors_host) return WS_EINVAL;
     TRY(flush_window(c));
+    TRY(materialize_planes(c));
     CK(c, cudaMemcpyAsync(c->d_anc, ancestors_host, sizeof(int32_t) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
     c->stats.h2d_bytes += (int64_t)sizeof(int32_t) * c->n;
     TRY(gather_all(c, c->d_anc));
@@ -1188,9 +1247,12 @@ extern "C" int ws_expectation(ws_ctx* c, const ws_expr* f, int32_t n_exprs, doub
     P.n_loads = (int)p.loads.size();
     P.n_stores = 0;
     P.n_regs = std::max(1, p.high_water);
+    P.ancestors = c->d_anc;
     for (int k = 0; k < P.n_loads; ++k) {
-        P.load_ptr[k] = plane_ptr(c, p.loads[k].first);
+        const Plane pl = p.loads[k].first;
+        P.load_ptr[k] = plane_ptr(c, pl);
         P.load_reg[k] = (uint8_t)p.loads[k].second;
+        if (c->cols[pl.col].stale[pl.comp]) P.load_gather |= (1u << k);
     }
     P.logw_mode = 0;
     P.logw = c->logw;
@@ -1224,6 +1286,7 @@ extern "C" int ws_col_download_rows(ws_ctx* c, int32_t id, const int64_t* indice
     for (int64_t i = 0; i < n_idx; ++i)
         if (indices[i] < 0 || indices[i] >= c->n) return fail(c, WS_EINVAL, "row index %lld out of range", (long long)indices[i]);
     TRY(flush_window(c));
+    TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
     TempBuf idx, out;
     CK(c, cudaMalloc(&idx.p, sizeof(int64_t) * (size_t)n_idx));
@@ -1394,6 +1457,7 @@ static int fill_score_launch(ws_ctx* c, WsScoreParams& S, int n_ops) {
 extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out) {
     if (!c || !host_out) return WS_EINVAL;
     TRY(flush_window(c));
+    TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
     const int n_ops = score_prefix_ops(c, target_depth);
     TRY(upload_score_program(c));
@@ -1414,6 +1478,7 @@ extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out
 extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t* col, const int32_t* comp, double* out) {
     if (!c || !col || !comp || !out || n_targets < 1) return c ? fail(c, WS_EINVAL, "ws_marginal_diversity: bad arguments") : WS_EINVAL;
     TRY(flush_window(c));
+    TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
     double best = INFINITY;
     for (int t = 0; t < n_targets; ++t) {
@@ -1447,6 +1512,7 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
     if (spec->proposal != WS_PROPOSAL_RW && spec->proposal != WS_PROPOSAL_AUTORW) return fail(c, WS_EINVAL, "ws_move: unknown proposal %d", spec->proposal);
     if (spec->has_bounds && (!spec->lo || !spec->hi)) return fail(c, WS_EINVAL, "ws_move: bounds missing");
     TRY(flush_window(c));
+    TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
     if (info) {
         info->ran = 0;
@@ -1620,6 +1686,13 @@ extern "C" int ws_set_timing(ws_ctx* c, int on) {
     if (!c) return WS_EINVAL;
     resolve_events(c);
     c->timing = on != 0;
+    return WS_OK;
+}
+extern "C" int ws_set_lazy_gather(ws_ctx* c, int on) {
+    if (!c) return WS_EINVAL;
+    TRY(flush_window(c));
+    TRY(materialize_planes(c));
+    c->lazy_gather = on != 0;
     return WS_OK;
 }
 extern "C" int ws_stream(ws_ctx* c, void** stream_out) {
