@@ -111,6 +111,35 @@ def test_systematic_and_multinomial(ws, ctx):
     check_ancestors(a, w, np.sort(u), "multinomial")
 
 
+@pytest.mark.parametrize("n,s,scheme", [(1, 1.0, "stratified"), (257, 2.0, "stratified"), (4096, 0.5, "stratified"),
+                                        (50_001, 3.0, "stratified"), (20_000, 2.0, "systematic")])
+def test_production_integer_search_is_exact(ws, ctx, n, s, scheme):
+    """The Philox (production) path evaluates the stratified search in exact integer arithmetic;
+    reproduce it with Python big integers: every ancestor must match, no exceptions."""
+    import ctypes as C
+    w = cref.exp_norm(skewed_logw(n, s, seed=n))
+    stream, seed = C.c_uint64(), C.c_uint64()
+    ctx.store._call("ws_next_philox_stream", C.byref(stream), C.byref(seed))
+    a, clamped = ws.resample_indices(w, ctx, scheme, return_clamped=True)
+    a_ref, clamped_ref = ref.stratified_ancestors_fixed_point(w, seed.value, stream.value, scheme)
+    np.testing.assert_array_equal(a, a_ref)
+    assert clamped == clamped_ref
+
+
+def test_production_search_one_hot_heavy_family(ws, ctx):
+    import ctypes as C
+    n = 80_000
+    w = np.full(n, 0.02 / (n - 1))
+    w[12345] = 0.98
+    w = w / w.sum()
+    stream, seed = C.c_uint64(), C.c_uint64()
+    ctx.store._call("ws_next_philox_stream", C.byref(stream), C.byref(seed))
+    a = ws.resample_indices(w, ctx, "stratified")
+    a_ref, _ = ref.stratified_ancestors_fixed_point(w, seed.value, stream.value)
+    np.testing.assert_array_equal(a, a_ref)
+    assert (a == 12345).sum() > 0.97 * n
+
+
 def test_resample_philox_statistics(ws, ctx):
     """native (Philox) uniforms: offspring counts of stratified resampling are within 1 of N*w"""
     n = 200_000

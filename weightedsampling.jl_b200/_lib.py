@@ -144,6 +144,7 @@ SIGNATURES = {
     "ws_reset_kernel_times": (C.c_int, [_ctx]),
     "ws_set_timing": (C.c_int, [_ctx, C.c_int]),
     "ws_set_lazy_gather": (C.c_int, [_ctx, C.c_int]),
+    "ws_next_philox_stream": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ws_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
 }
 

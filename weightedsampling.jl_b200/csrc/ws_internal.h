@@ -12,9 +12,9 @@
 #define WS_VM_MAX_REGS 48     // register-file rows per pass (48 * 128 * 4 * 8 B = 192 KB of smem)
 #define WS_SCAN_BLOCK 256
 #define WS_SCAN_ITEMS 8
-#define WS_SCAN_TILE (WS_SCAN_BLOCK * WS_SCAN_ITEMS)
+#define WS_SCAN_TILE (32 * WS_SCAN_ITEMS)  // particles per (warp-granular) scan tile
 #define WS_GATHER_MAX_PLANES 32
-#define WS_HEAVY_TILE_SLOTS (64 * 4096)  // == WS_HEAVY_TILE in ws_kernels.cu
+#define WS_HEAVY_TILE_SLOTS 32768  // a tile with more offspring than this is expanded by the whole grid
 #define WS_MAX_PARTIALS 4096  // upper bound on CTAs that write (m,S,Q) partials
 
 // (m, S, Q) = (max l, sum exp(l-m), sum exp(2(l-m))) — everything exp_norm / ess_perc /
@@ -75,7 +75,7 @@ struct WsScanParams {
     unsigned int* tile_counter;      // dynamic tile ids, zeroed before launch
     unsigned long long* n_clamped;  // += slots beyond the last CDF entry (clamped to the last particle)
     unsigned int* heavy_count;       // number of heavy tiles, zeroed before launch
-    int32_t* heavy_F;                // [n/WS_HEAVY_TILE + 2][WS_SCAN_TILE + 2]: F table, fstart, tile id
+    int32_t* heavy_F;                // [n/WS_HEAVY_TILE_SLOTS + 2][WS_SCAN_TILE + 2]: F table, fstart, tile id
 };
 
 struct WsGatherParams {

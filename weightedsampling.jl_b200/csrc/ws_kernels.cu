@@ -348,25 +348,56 @@ __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double 
     return ws_count_slots_le(C, P.n, inv_n, su);
 }
 
-#define WS_EXPAND_CHUNK 4096   // output slots staged in shared memory per round
-#define WS_DIRECT_MAX 8        // offspring a thread writes itself; larger families are filled by the CTA
-#define WS_HEAVY_TILE (64 * WS_EXPAND_CHUNK)  // tiles with more offspring than this go to the heavy kernel
+// ---- warp-granular tiles -------------------------------------------------------------------------
+// Every WARP owns a tile of WS_SCAN_TILE = 32 x 8 consecutive particles and runs the whole pipeline on
+// it (weights -> fixed point -> warp scan -> decoupled look-back -> F(C_m) -> offspring expansion) with
+// warp-level synchronisation only: no CTA barrier, so a warp that waits in the look-back never stalls
+// the other seven warps of its CTA.  All slot arithmetic is 32-bit (n < 2^31).
+//
+// Two ways to evaluate F(C) = #{slots n : u_n <= C}:
+//   EXACT_FP = true   the reference's floating-point slot uniforms u_n = (n-1)*invN + r_n*invN
+//                     (src/resampling.jl:39-41) with caller-supplied r (replay / icdf / multinomial):
+//                     bit-compatible with the oracle for identical uniforms.
+//   EXACT_FP = false  (Philox draws, the production path) the same stratified grid in exact integer
+//                     arithmetic: with the CDF as a 2^61 fixed-point integer C and r_k a 61-bit Philox
+//                     integer,  u_k <= C  <=>  k*2^61 + r_k <= C*N, so F = k + [r_k <= frac] with
+//                     (k, frac) = divmod(C*N, 2^61) from one 64x32-bit product.  One Philox block and
+//                     no loop per particle; the test-suite checks it against exact big-integer arithmetic.
+#define WS_EXPAND_CHUNK 512    // output slots a warp stages in shared memory per round
+#define WS_DIRECT_MAX 8        // offspring a lane writes itself; larger families are filled by the warp
+#define WS_WARPS_PER_CTA (WS_SCAN_BLOCK / 32)
+#define WS_FXS_FRAC_MASK 0x1FFFFFFFFFFFFFFFull  // 2^61 - 1
 
-__global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __grid_constant__ WsScanParams P) {
+__device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, int scheme, unsigned long long r0,
+                                        uint64_t seed, uint64_t stream) {
+    // T = C * n as a 96-bit number hi:lo
+    const unsigned long long lo = C * (unsigned long long)n;
+    const unsigned long long hi = __umul64hi(C, (unsigned long long)n);
+    const unsigned long long k64 = (hi << 3) | (lo >> 61);
+    if (k64 >= (unsigned long long)n) return (int)n;
+    const unsigned int k = (unsigned int)k64;
+    const unsigned long long frac = lo & WS_FXS_FRAC_MASK;
+    unsigned long long r;
+    if (scheme == 1) {
+        r = r0;
+    } else {
+        const ws_u32x4 b = ws_philox4x32_10((uint64_t)(k >> 1), stream, seed);
+        const unsigned long long v = (k & 1u) ? (((unsigned long long)b.z << 32) | b.w) : (((unsigned long long)b.x << 32) | b.y);
+        r = v >> 3;
+    }
+    return (int)k + (r <= frac ? 1 : 0);
+}
+
+template <bool EXACT_FP>
+__global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_scan_search_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
 
-    __shared__ int32_t Fs[WS_SCAN_TILE];          // F(C_m) for the tile's particles
-    __shared__ int32_t out_s[WS_EXPAND_CHUNK];    // ancestors of one chunk of output slots
-    __shared__ uint16_t big_items[WS_SCAN_TILE];  // items with more than WS_DIRECT_MAX offspring
-    __shared__ unsigned long long warp_tot[WS_SCAN_BLOCK / 32];
-    __shared__ unsigned long long s_excl;         // tile exclusive prefix (fixed point)
-    __shared__ int s_tile;
-    __shared__ int s_nbig;
-    __shared__ int64_t s_fstart;
-
+    __shared__ int32_t out_all[WS_WARPS_PER_CTA][WS_EXPAND_CHUNK];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n = P.n;
-    const int n_tiles = (int)((n + WS_SCAN_TILE - 1) / WS_SCAN_TILE);
+    int32_t* const out_s = out_all[warp];
+
+    const int n = (int)P.n;
+    const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     const double inv_n = 1.0 / (double)n;
     double m = 0.0, Sden = 1.0;
     if (P.mode == 0) {
@@ -380,29 +411,27 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __g
     su.replay = P.replay_u;
     su.r0 = 0.0;
     su.cached_blk = -1;
+    unsigned long long r0_int = 0ull;
     if (P.scheme == 1 && P.sorted_u == nullptr) {
         if (P.replay_u != nullptr) {
             su.r0 = P.replay_u[0];
         } else {
             ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
             su.r0 = ws_u01(r.x, r.y);
+            r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
         }
     }
     const double uniform_w = 1.0 / (double)n;
 
     while (true) {
-        __syncthreads();  // protects the shared arrays across iterations
-        if (threadIdx.x == 0) {
-            s_tile = (int)atomicAdd(P.tile_counter, 1u);
-            s_nbig = 0;
-        }
-        __syncthreads();
-        const int tile = s_tile;
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(P.tile_counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
         if (tile >= n_tiles) break;
-        const int64_t tile_base = (int64_t)tile * WS_SCAN_TILE;
-        const int64_t item0 = tile_base + (int64_t)threadIdx.x * WS_SCAN_ITEMS;
+        const int tile_base = tile * WS_SCAN_TILE;
+        const int item0 = tile_base + lane * WS_SCAN_ITEMS;
 
-        // ---- weights -> fixed point, thread-local inclusive sums -----------------------------
+        // ---- weights -> fixed point, lane-local inclusive sums ---------------------------------------
         unsigned long long q[WS_SCAN_ITEMS];
         if (P.mode == 2) {
 #pragma unroll
@@ -434,149 +463,143 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_scan_search_kernel(const __g
         }
 #pragma unroll
         for (int k = 1; k < WS_SCAN_ITEMS; ++k) q[k] += q[k - 1];
-        const unsigned long long thread_total = q[WS_SCAN_ITEMS - 1];
+        const unsigned long long lane_total = q[WS_SCAN_ITEMS - 1];
 
-        // ---- block exclusive scan of thread totals -----------------------------------------------
-        unsigned long long incl = thread_total;
+        // ---- warp exclusive scan of lane totals ----------------------------------------------------
+        unsigned long long incl = lane_total;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        unsigned long long warp_excl = 0ull, tile_agg = 0ull;
-#pragma unroll
-        for (int w = 0; w < WS_SCAN_BLOCK / 32; ++w) {
-            const unsigned long long t = warp_tot[w];
-            if (w < warp) warp_excl += t;
-            tile_agg += t;
-        }
-        const unsigned long long thread_excl = warp_excl + (incl - thread_total);
+        const unsigned long long tile_agg = __shfl_sync(0xffffffffu, incl, 31);
+        const unsigned long long lane_excl = incl - lane_total;
 
-        // ---- decoupled look-back (warp 0) ------------------------------------------------------
-        if (warp == 0) {
-            unsigned long long excl = 0ull;
-            if (tile == 0) {
-                if (lane == 0) st_relaxed_u64(P.tile_words + 0, (WS_TILE_INCL << 62) | tile_agg);
-            } else {
-                if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_AGG << 62) | tile_agg);
-                int base = tile - 1;
-                while (true) {
-                    const int idx = base - lane;
-                    unsigned long long w;
-                    if (idx >= 0) {
-                        do {
-                            w = ld_relaxed_u64(P.tile_words + idx);
-                        } while ((w >> 62) == 0ull);
-                    } else {
-                        w = (WS_TILE_INCL << 62);  // virtual tile -1: inclusive prefix 0
-                    }
-                    const unsigned incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == WS_TILE_INCL);
-                    unsigned long long val = w & WS_FXS_MASK;
-                    if (incl_mask != 0u) {
-                        const int first = __ffs(incl_mask) - 1;
-                        if (lane > first) val = 0ull;
-                    }
-#pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                    excl += val;
-                    if (incl_mask != 0u) break;
-                    base -= 32;
+        // ---- decoupled look-back: lane l inspects tile (base - l) ---------------------------------------
+        unsigned long long excl = 0ull;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_u64(P.tile_words + 0, (WS_TILE_INCL << 62) | tile_agg);
+        } else {
+            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_AGG << 62) | tile_agg);
+            int base = tile - 1;
+            while (true) {
+                const int idx = base - lane;
+                unsigned long long w;
+                if (idx >= 0) {
+                    do {
+                        w = ld_relaxed_u64(P.tile_words + idx);
+                    } while ((w >> 62) == 0ull);
+                } else {
+                    w = (WS_TILE_INCL << 62);  // virtual tile -1: inclusive prefix 0
                 }
-                if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_INCL << 62) | (excl + tile_agg));
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == WS_TILE_INCL);
+                unsigned long long val = w & WS_FXS_MASK;
+                if (incl_mask != 0u) {
+                    const int first = __ffs(incl_mask) - 1;
+                    if (lane > first) val = 0ull;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
+                excl += val;
+                if (incl_mask != 0u) break;
+                base -= 32;
             }
-            if (lane == 0) {
-                s_excl = excl;
-                // F at the tile's left edge; by definition 0 for the first particle (a slot with
-                // u = 0 belongs to particle 1, as in icdf)
-                s_fstart = (tile == 0) ? 0 : ws_F(P, ws_fxs_to_double(excl), inv_n, su);
-            }
+            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_INCL << 62) | (excl + tile_agg));
         }
-        __syncthreads();
-        const unsigned long long tile_excl = s_excl;
-        const int64_t fstart = s_fstart;
 
-        // ---- per-particle F(C_m) -----------------------------------------------------------------
-        int32_t f[WS_SCAN_ITEMS];
+        // ---- per-particle F(C_m) -----------------------------------------------------------------------
+        // F at the tile's left edge is by definition 0 for the first particle (a slot with u = 0 belongs
+        // to particle 1, as in icdf); elsewhere it is the previous particle's F.
+        int f[WS_SCAN_ITEMS];
 #pragma unroll
         for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-            const int64_t gi = item0 + k;
-            int64_t fk;
+            const int gi = item0 + k;
+            int fk;
             if (gi >= n) {
                 fk = n;
-            } else if (gi == n - 1) {
-                const int64_t ff = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, su);
-                if (ff < n) atomicAdd(P.n_clamped, (unsigned long long)(n - ff));
-                fk = n;  // leftover slots go to the last particle (the reference would throw BoundsError)
             } else {
-                fk = ws_F(P, ws_fxs_to_double(tile_excl + thread_excl + q[k]), inv_n, su);
+                const unsigned long long C = excl + lane_excl + q[k];
+                if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C), inv_n, su);
+                else fk = ws_F_int(C, (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
+                if (gi == n - 1) {
+                    if (fk < n) atomicAdd(P.n_clamped, (unsigned long long)(n - fk));
+                    fk = n;  // leftover slots go to the last particle (the reference would throw BoundsError)
+                }
             }
-            f[k] = (int32_t)fk;
-            Fs[threadIdx.x * WS_SCAN_ITEMS + k] = f[k];
+            f[k] = fk;
         }
-        __syncthreads();
-        const int64_t fend = (int64_t)Fs[WS_SCAN_TILE - 1];
-        const int64_t f_prev0 = (threadIdx.x == 0) ? fstart : (int64_t)Fs[threadIdx.x * WS_SCAN_ITEMS - 1];
+        int fstart = 0;
+        if (lane == 0 && tile != 0) {
+            if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(excl), inv_n, su);
+            else fstart = ws_F_int(excl, (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
+        }
+        fstart = __shfl_sync(0xffffffffu, fstart, 0);
+        int f_prev = __shfl_up_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 1);
+        if (lane == 0) f_prev = fstart;
+        const int fend = __shfl_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 31);
 
-        if (fend - fstart > (int64_t)WS_HEAVY_TILE) {
+        if (fend - fstart > WS_HEAVY_TILE_SLOTS) {
             // a few particles own a huge share of the offspring: publish the tile's F table and let
             // ws_expand_heavy_kernel fill its slots with the whole grid
-            __shared__ unsigned int s_slot;
-            if (threadIdx.x == 0) s_slot = atomicAdd(P.heavy_count, 1u);
-            __syncthreads();
-            const unsigned int slot = s_slot;
+            unsigned int slot = 0;
+            if (lane == 0) slot = atomicAdd(P.heavy_count, 1u);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
             int32_t* dst = P.heavy_F + (size_t)slot * (WS_SCAN_TILE + 2);
-            for (int k = threadIdx.x; k < WS_SCAN_TILE; k += WS_SCAN_BLOCK) dst[k] = Fs[k];
-            if (threadIdx.x == 0) {
-                dst[WS_SCAN_TILE] = (int32_t)fstart;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) dst[lane * WS_SCAN_ITEMS + k] = f[k];
+            if (lane == 0) {
+                dst[WS_SCAN_TILE] = fstart;
                 dst[WS_SCAN_TILE + 1] = tile;
             }
             continue;
         }
 
-        // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m, staged per chunk ------------
-        // register the families too large for one thread
+        // does this lane own a family too large for one lane?
+        bool has_big = false;
         {
-            int64_t lo = f_prev0;
+            int lo = f_prev;
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                const int64_t hi = f[k];
-                if (hi - lo > WS_DIRECT_MAX) {
-                    const int pos = atomicAdd(&s_nbig, 1);
-                    big_items[pos] = (uint16_t)(threadIdx.x * WS_SCAN_ITEMS + k);
-                }
-                lo = hi;
+                if (f[k] - lo > WS_DIRECT_MAX) has_big = true;
+                lo = f[k];
             }
         }
-        for (int64_t chunk = fstart; chunk < fend; chunk += WS_EXPAND_CHUNK) {
-            const int64_t chunk_end = (chunk + WS_EXPAND_CHUNK < fend) ? chunk + WS_EXPAND_CHUNK : fend;
+        const unsigned big_mask = __ballot_sync(0xffffffffu, has_big);
+
+        // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m, staged per chunk --------------
+        for (int chunk = fstart; chunk < fend; chunk += WS_EXPAND_CHUNK) {
+            const int chunk_end = min(chunk + WS_EXPAND_CHUNK, fend);
             {
-                int64_t lo = f_prev0;
+                int lo = f_prev;
 #pragma unroll
                 for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                    const int64_t hi = f[k];
-                    if (hi - lo <= WS_DIRECT_MAX && hi > chunk && lo < chunk_end) {
-                        const int32_t anc = (int32_t)(item0 + k);
-                        for (int64_t pos = (lo > chunk ? lo : chunk); pos < (hi < chunk_end ? hi : chunk_end); ++pos)
-                            out_s[pos - chunk] = anc;
+                    const int hi = f[k];
+                    if (hi - lo <= WS_DIRECT_MAX) {
+                        const int a = max(lo, chunk), e = min(hi, chunk_end);
+                        for (int pos = a; pos < e; ++pos) out_s[pos - chunk] = item0 + k;
                     }
                     lo = hi;
                 }
             }
-            __syncthreads();  // also makes s_nbig / big_items visible
-            const int nbig = s_nbig;
-            for (int b = 0; b < nbig; ++b) {
-                const int it = big_items[b];
-                const int64_t lo = (it == 0) ? fstart : (int64_t)Fs[it - 1];
-                const int64_t hi = (int64_t)Fs[it];
-                const int64_t a = lo > chunk ? lo : chunk, e = hi < chunk_end ? hi : chunk_end;
-                const int32_t anc = (int32_t)(tile_base + it);
-                for (int64_t pos = a + threadIdx.x; pos < e; pos += WS_SCAN_BLOCK) out_s[pos - chunk] = anc;
+            unsigned bm = big_mask;
+            while (bm != 0u) {
+                const int src = __ffs(bm) - 1;
+                bm &= bm - 1u;
+                int lo = __shfl_sync(0xffffffffu, f_prev, src);
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                    const int hi = __shfl_sync(0xffffffffu, f[k], src);
+                    if (hi - lo > WS_DIRECT_MAX) {
+                        const int a = max(lo, chunk), e = min(hi, chunk_end);
+                        const int anc = tile_base + src * WS_SCAN_ITEMS + k;
+                        for (int pos = a + lane; pos < e; pos += 32) out_s[pos - chunk] = anc;
+                    }
+                    lo = hi;
+                }
             }
-            __syncthreads();
-            for (int64_t pos = chunk + threadIdx.x; pos < chunk_end; pos += WS_SCAN_BLOCK) P.ancestors[pos] = out_s[pos - chunk];
-            __syncthreads();
+            __syncwarp();
+            for (int pos = chunk + lane; pos < chunk_end; pos += 32) P.ancestors[pos] = out_s[pos - chunk];
+            __syncwarp();
         }
     }
 }
@@ -611,7 +634,9 @@ __global__ void __launch_bounds__(256) ws_expand_heavy_kernel(const __grid_const
 }
 
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
-    ws_scan_search_kernel<<<grid, WS_SCAN_BLOCK, 0, s>>>(P);
+    const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
+    if (exact_fp) ws_scan_search_kernel<true><<<grid, WS_SCAN_BLOCK, 0, s>>>(P);
+    else ws_scan_search_kernel<false><<<grid, WS_SCAN_BLOCK, 0, s>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);

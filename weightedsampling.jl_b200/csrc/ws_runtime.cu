@@ -262,7 +262,7 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     if (out == nullptr) return fail(nullptr, WS_EINVAL, "ws_create: out is NULL");
     *out = nullptr;
     if (n_global <= 0) return fail(nullptr, WS_EINVAL, "ws_create: n_particles must be positive (got %lld)", (long long)n_global);
-    if (n_global >= (int64_t)2147483647) return fail(nullptr, WS_EINVAL, "ws_create: n_particles must be < 2^31 (Int32 ancestors)");
+    if (n_global >= (int64_t)2147483647 - 65536) return fail(nullptr, WS_EINVAL, "ws_create: n_particles must be < 2^31 - 65536 (Int32 ancestors)");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, WS_EINVAL, "ws_create: bad rank %d of %d", rank, nranks);
     if (nranks > 1) return fail(nullptr, WS_EUNSUPPORTED, "ws_create_sharded: multi-rank resampling is not built yet");
     if (resampler < 0 || resampler > 2) return fail(nullptr, WS_EINVAL, "ws_create: unknown resampler %d", resampler);
@@ -943,7 +943,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
                            unsigned long long* d_clamped) {
     const int64_t n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     if (c->d_heavy_F == nullptr || c->heavy_cap_n < n) {
-        // at most n / WS_HEAVY_TILE_SLOTS tiles can own more than WS_HEAVY_TILE_SLOTS offspring each
+        // at most n / WS_HEAVY_TILE_SLOTS families can own more than WS_HEAVY_TILE_SLOTS offspring each
         if (c->d_heavy_F) {
             CK(c, cudaStreamSynchronize(c->stream));
             CK(c, cudaFree(c->d_heavy_F));
@@ -973,7 +973,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     S.n_clamped = d_clamped;
     S.heavy_count = c->d_tile_counter + 1;
     S.heavy_F = c->d_heavy_F;
-    const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)c->sm_count * 4);
+    const int grid = (int)std::min<int64_t>((n_tiles + WS_SCAN_BLOCK / 32 - 1) / (WS_SCAN_BLOCK / 32), (int64_t)c->sm_count * 4);
     TimedEvent te;
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_scan_search(S, std::max(1, grid), c->stream));
@@ -1168,7 +1168,7 @@ static int resample_host_impl(ws_ctx* c, const double* weights, int64_t n, int s
                               int64_t n_uniforms, bool sorted_mode, int32_t* indices_out, int64_t* n_clamped) {
     TRY(flush_window(c));
     CK(c, cudaSetDevice(c->device));
-    if (n >= (int64_t)2147483647) return fail(c, WS_EINVAL, "n must be < 2^31");
+    if (n >= (int64_t)2147483647 - 65536) return fail(c, WS_EINVAL, "n must be < 2^31 - 65536");
     TempBuf w, u, anc, words;
     const int64_t n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     CK(c, cudaMalloc(&w.p, sizeof(double) * (size_t)n));
@@ -1693,6 +1693,12 @@ extern "C" int ws_set_lazy_gather(ws_ctx* c, int on) {
     TRY(flush_window(c));
     TRY(materialize_planes(c));
     c->lazy_gather = on != 0;
+    return WS_OK;
+}
+extern "C" int ws_next_philox_stream(ws_ctx* c, uint64_t* stream_out, uint64_t* seed_out) {
+    if (!c) return WS_EINVAL;
+    if (stream_out) *stream_out = c->next_stream;
+    if (seed_out) *seed_out = c->seed;
     return WS_OK;
 }
 extern "C" int ws_stream(ws_ctx* c, void** stream_out) {
