@@ -12,7 +12,8 @@
 #define WS_VM_MAX_REGS 48     // register-file rows per pass (48 * 128 * 4 * 8 B = 192 KB of smem)
 #define WS_SCAN_BLOCK 256
 #define WS_SCAN_ITEMS 8
-#define WS_SCAN_TILE (32 * WS_SCAN_ITEMS)  // particles per (warp-granular) scan tile
+#define WS_SCAN_TILE (32 * WS_SCAN_ITEMS)  // particles per warp-granular search tile
+#define WS_CDF_TILE (WS_SCAN_BLOCK * WS_SCAN_ITEMS)  // particles per CTA tile of the CDF pass
 #define WS_GATHER_MAX_PLANES 32
 #define WS_HEAVY_TILE_SLOTS 32768  // a tile with more offspring than this is expanded by the whole grid
 #define WS_MAX_PARTIALS 4096  // upper bound on CTAs that write (m,S,Q) partials
@@ -71,8 +72,9 @@ struct WsScanParams {
     const double* replay_u;    // n uniforms (stratified) / 1 uniform (systematic) or nullptr
     const double* sorted_u;    // multinomial: n sorted uniforms (device)
     int32_t* ancestors;        // out, 0-based
-    unsigned long long* tile_words;  // decoupled look-back descriptors, zeroed before launch
-    unsigned int* tile_counter;      // dynamic tile ids, zeroed before launch
+    unsigned long long* tile_words;  // [n / WS_CDF_TILE]: tile aggregates, then their exclusive scan
+    unsigned long long* cdf_local;   // [n]: tile-local inclusive fixed-point CDF
+    unsigned int* tile_counter;      // unused (kept for layout stability)
     unsigned long long* n_clamped;  // += slots beyond the last CDF entry (clamped to the last particle)
     unsigned int* heavy_count;       // number of heavy tiles, zeroed before launch
     int32_t* heavy_F;                // [n/WS_HEAVY_TILE_SLOTS + 2][WS_SCAN_TILE + 2]: F table, fstart, tile id

@@ -348,11 +348,16 @@ __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double 
     return ws_count_slots_le(C, P.n, inv_n, su);
 }
 
-// ---- warp-granular tiles -------------------------------------------------------------------------
-// Every WARP owns a tile of WS_SCAN_TILE = 32 x 8 consecutive particles and runs the whole pipeline on
-// it (weights -> fixed point -> warp scan -> decoupled look-back -> F(C_m) -> offspring expansion) with
-// warp-level synchronisation only: no CTA barrier, so a warp that waits in the look-back never stalls
-// the other seven warps of its CTA.  All slot arithmetic is 32-bit (n < 2^31).
+// ---- CDF + search in three dependency-free passes ------------------------------------------------
+//   ws_cdf_tiles_kernel    w_i = exp(l_i - m)/S -> fixed point q_i; CTA tile of WS_CDF_TILE particles:
+//                          tile-local inclusive prefix sums (8 B / particle) + one aggregate per tile
+//   ws_cdf_offsets_kernel  one CTA: exclusive scan of the tile aggregates (n / 2048 values)
+//   ws_search_kernel       warp-granular: C_m = offset[tile] + local prefix -> F(C_m) -> offspring slots
+// A single-pass decoupled look-back was measured first (profiles/r1_scan_lookback_*): with thousands of
+// small tiles in flight every tile walks back through all tiles that are still unfinished, and the
+// kernel spent most of its time spinning on predecessor flags.  Materialising the tile-local CDF costs
+// 16 B of extra traffic per particle but removes every inter-tile dependency; the fixed-point sums
+// make the result independent of the summation order either way.
 //
 // Two ways to evaluate F(C) = #{slots n : u_n <= C}:
 //   EXACT_FP = true   the reference's floating-point slot uniforms u_n = (n-1)*invN + r_n*invN
@@ -388,50 +393,20 @@ __device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, in
     return (int)k + (r <= frac ? 1 : 0);
 }
 
-template <bool EXACT_FP>
-__global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_scan_search_kernel(const __grid_constant__ WsScanParams P) {
+__global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
-
-    __shared__ int32_t out_all[WS_WARPS_PER_CTA][WS_EXPAND_CHUNK];
+    __shared__ unsigned long long warp_tot[WS_SCAN_BLOCK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t* const out_s = out_all[warp];
-
     const int n = (int)P.n;
-    const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
-    const double inv_n = 1.0 / (double)n;
+    const int n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     double m = 0.0, Sden = 1.0;
     if (P.mode == 0) {
         m = P.red->m;
         Sden = P.red->S;  // divide (not multiply by a reciprocal): w = e / S as exp_norm does
     }
-    SlotUniform su;
-    su.scheme = (P.scheme == 1) ? 1 : 0;
-    su.seed = P.seed;
-    su.stream = P.stream;
-    su.replay = P.replay_u;
-    su.r0 = 0.0;
-    su.cached_blk = -1;
-    unsigned long long r0_int = 0ull;
-    if (P.scheme == 1 && P.sorted_u == nullptr) {
-        if (P.replay_u != nullptr) {
-            su.r0 = P.replay_u[0];
-        } else {
-            ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
-            su.r0 = ws_u01(r.x, r.y);
-            r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
-        }
-    }
     const double uniform_w = 1.0 / (double)n;
-
-    while (true) {
-        int tile = 0;
-        if (lane == 0) tile = (int)atomicAdd(P.tile_counter, 1u);
-        tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= n_tiles) break;
-        const int tile_base = tile * WS_SCAN_TILE;
-        const int item0 = tile_base + lane * WS_SCAN_ITEMS;
-
-        // ---- weights -> fixed point, lane-local inclusive sums ---------------------------------------
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
         unsigned long long q[WS_SCAN_ITEMS];
         if (P.mode == 2) {
 #pragma unroll
@@ -463,53 +438,124 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_scan_search_kernel(const 
         }
 #pragma unroll
         for (int k = 1; k < WS_SCAN_ITEMS; ++k) q[k] += q[k - 1];
-        const unsigned long long lane_total = q[WS_SCAN_ITEMS - 1];
-
-        // ---- warp exclusive scan of lane totals ----------------------------------------------------
-        unsigned long long incl = lane_total;
+        const unsigned long long thread_total = q[WS_SCAN_ITEMS - 1];
+        unsigned long long incl = thread_total;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
             if (lane >= d) incl += t;
         }
-        const unsigned long long tile_agg = __shfl_sync(0xffffffffu, incl, 31);
-        const unsigned long long lane_excl = incl - lane_total;
-
-        // ---- decoupled look-back: lane l inspects tile (base - l) ---------------------------------------
-        unsigned long long excl = 0ull;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(P.tile_words + 0, (WS_TILE_INCL << 62) | tile_agg);
-        } else {
-            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_AGG << 62) | tile_agg);
-            int base = tile - 1;
-            while (true) {
-                const int idx = base - lane;
-                unsigned long long w;
-                if (idx >= 0) {
-                    do {
-                        w = ld_relaxed_u64(P.tile_words + idx);
-                    } while ((w >> 62) == 0ull);
-                } else {
-                    w = (WS_TILE_INCL << 62);  // virtual tile -1: inclusive prefix 0
-                }
-                const unsigned incl_mask = __ballot_sync(0xffffffffu, (w >> 62) == WS_TILE_INCL);
-                unsigned long long val = w & WS_FXS_MASK;
-                if (incl_mask != 0u) {
-                    const int first = __ffs(incl_mask) - 1;
-                    if (lane > first) val = 0ull;
-                }
+        __syncthreads();  // warp_tot of the previous tile has been consumed
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long warp_excl = 0ull, tile_agg = 0ull;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xffffffffu, val, d);
-                excl += val;
-                if (incl_mask != 0u) break;
-                base -= 32;
+        for (int w = 0; w < WS_SCAN_BLOCK / 32; ++w) {
+            const unsigned long long t = warp_tot[w];
+            if (w < warp) warp_excl += t;
+            tile_agg += t;
+        }
+        const unsigned long long thread_excl = warp_excl + (incl - thread_total);
+        if (item0 + WS_SCAN_ITEMS <= n) {
+            ulonglong2* dst = reinterpret_cast<ulonglong2*>(P.cdf_local + item0);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) dst[k] = make_ulonglong2(thread_excl + q[2 * k], thread_excl + q[2 * k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k)
+                if (item0 + k < n) P.cdf_local[item0 + k] = thread_excl + q[k];
+        }
+        if (threadIdx.x == 0) P.tile_words[tile] = tile_agg;
+    }
+}
+
+// exclusive scan of the tile aggregates, in place, by one CTA of 1024 threads (fixed order)
+__global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_tiles = (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE);
+    if (threadIdx.x == 0) s_carry = 0ull;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const unsigned long long v = (i < n_tiles) ? P.tile_words[i] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long warp_excl = 0ull, total = 0ull;
+        for (int w = 0; w < 32; ++w) {
+            const unsigned long long t = warp_tot[w];
+            if (w < warp) warp_excl += t;
+            total += t;
+        }
+        const unsigned long long carry = s_carry;
+        if (i < n_tiles) P.tile_words[i] = carry + warp_excl + (incl - v);
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + total;
+        __syncthreads();
+    }
+}
+
+template <bool EXACT_FP>
+__global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+
+    __shared__ int32_t out_all[WS_WARPS_PER_CTA][WS_EXPAND_CHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t* const out_s = out_all[warp];
+
+    const int n = (int)P.n;
+    const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    const double inv_n = 1.0 / (double)n;
+    SlotUniform su;
+    su.scheme = (P.scheme == 1) ? 1 : 0;
+    su.seed = P.seed;
+    su.stream = P.stream;
+    su.replay = P.replay_u;
+    su.r0 = 0.0;
+    su.cached_blk = -1;
+    unsigned long long r0_int = 0ull;
+    if (P.scheme == 1 && P.sorted_u == nullptr) {
+        if (P.replay_u != nullptr) {
+            su.r0 = P.replay_u[0];
+        } else {
+            ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
+            su.r0 = ws_u01(r.x, r.y);
+            r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
+        }
+    }
+
+    const int warps_total = gridDim.x * WS_WARPS_PER_CTA;
+    for (int tile = blockIdx.x * WS_WARPS_PER_CTA + warp; tile < n_tiles; tile += warps_total) {
+        const int tile_base = tile * WS_SCAN_TILE;
+        const int item0 = tile_base + lane * WS_SCAN_ITEMS;
+        const unsigned long long offset = __ldg(P.tile_words + tile_base / WS_CDF_TILE);
+
+        // global fixed-point CDF of the lane's 8 consecutive particles
+        unsigned long long C[WS_SCAN_ITEMS];
+        if (item0 + WS_SCAN_ITEMS <= n) {
+            const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(P.cdf_local + item0);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                ulonglong2 v = __ldg(p2 + k);
+                C[2 * k] = offset + v.x;
+                C[2 * k + 1] = offset + v.y;
             }
-            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_INCL << 62) | (excl + tile_agg));
+        } else {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? offset + __ldg(P.cdf_local + item0 + k) : 0ull;
         }
 
         // ---- per-particle F(C_m) -----------------------------------------------------------------------
-        // F at the tile's left edge is by definition 0 for the first particle (a slot with u = 0 belongs
-        // to particle 1, as in icdf); elsewhere it is the previous particle's F.
+        // F at the left edge of the particle set is by definition 0 (a slot with u = 0 belongs to
+        // particle 1, as in icdf); elsewhere it is the previous particle's F.
         int f[WS_SCAN_ITEMS];
 #pragma unroll
         for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
@@ -518,9 +564,8 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_scan_search_kernel(const 
             if (gi >= n) {
                 fk = n;
             } else {
-                const unsigned long long C = excl + lane_excl + q[k];
-                if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C), inv_n, su);
-                else fk = ws_F_int(C, (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
+                if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k]), inv_n, su);
+                else fk = ws_F_int(C[k], (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
                 if (gi == n - 1) {
                     if (fk < n) atomicAdd(P.n_clamped, (unsigned long long)(n - fk));
                     fk = n;  // leftover slots go to the last particle (the reference would throw BoundsError)
@@ -530,8 +575,10 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_scan_search_kernel(const 
         }
         int fstart = 0;
         if (lane == 0 && tile != 0) {
-            if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(excl), inv_n, su);
-            else fstart = ws_F_int(excl, (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
+            const int p = tile_base - 1;
+            const unsigned long long Cp = __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+            if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
+            else fstart = ws_F_int(Cp, (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
         }
         fstart = __shfl_sync(0xffffffffu, fstart, 0);
         int f_prev = __shfl_up_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 1);
@@ -634,10 +681,24 @@ __global__ void __launch_bounds__(256) ws_expand_heavy_kernel(const __grid_const
 }
 
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
-    const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
-    if (exact_fp) ws_scan_search_kernel<true><<<grid, WS_SCAN_BLOCK, 0, s>>>(P);
-    else ws_scan_search_kernel<false><<<grid, WS_SCAN_BLOCK, 0, s>>>(P);
+    (void)grid;
+    const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    const int64_t warp_tiles = (P.n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    int g1 = (int)(cdf_tiles < (int64_t)g_sm_count * 8 ? cdf_tiles : (int64_t)g_sm_count * 8);
+    if (g1 < 1) g1 = 1;
+    ws_cdf_tiles_kernel<<<g1, WS_SCAN_BLOCK, 0, s>>>(P);
     cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ws_cdf_offsets_kernel<<<1, 1024, 0, s>>>(P);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int64_t ctas = (warp_tiles + WS_WARPS_PER_CTA - 1) / WS_WARPS_PER_CTA;
+    int g3 = (int)(ctas < (int64_t)g_sm_count * 6 ? ctas : (int64_t)g_sm_count * 6);
+    if (g3 < 1) g3 = 1;
+    const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
+    if (exact_fp) ws_search_kernel<true><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
+    else ws_search_kernel<false><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);
     return cudaGetLastError();

@@ -86,6 +86,7 @@ struct ws_ctx {
     bool anc_pending = false;  // some plane is stale w.r.t. d_anc
     bool lazy_gather = true;
     unsigned long long* d_tile_words = nullptr;
+    unsigned long long* d_cdf_local = nullptr;  // [n] tile-local fixed-point CDF (scratch of the resampler)
     unsigned int* d_tile_counter = nullptr;  // [0] dynamic tile id, [1] heavy-tile count
     int32_t* d_heavy_F = nullptr;
     int64_t heavy_cap_n = 0;                  // particle count d_heavy_F is sized for
@@ -311,8 +312,9 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     CKC(cudaMallocHost(&c->h_red, sizeof(WsReduceOut)));
     memset(c->h_red, 0, sizeof(WsReduceOut));
     CKC(cudaMalloc(&c->d_anc, sizeof(int32_t) * (size_t)c->n));
-    c->n_tiles = (c->n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    c->n_tiles = (c->n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     CKC(cudaMalloc(&c->d_tile_words, sizeof(unsigned long long) * (size_t)c->n_tiles));
+    CKC(cudaMalloc(&c->d_cdf_local, sizeof(unsigned long long) * (size_t)c->n));
     CKC(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int) * 2));
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 4));
     CKC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
@@ -346,6 +348,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
     if (c->h_red) cudaFreeHost(c->h_red);
     cudaFree(c->d_anc);
     cudaFree(c->d_tile_words);
+    cudaFree(c->d_cdf_local);
     cudaFree(c->d_tile_counter);
     cudaFree(c->d_heavy_F);
     cudaFree(c->d_counters);
@@ -939,9 +942,9 @@ static int gather_all(ws_ctx* c, const int32_t* d_anc) {
 }
 
 static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, int64_t n, const double* d_replay_u,
-                           const double* d_sorted_u, int32_t* d_anc, unsigned long long* d_words, uint64_t stream_id,
-                           unsigned long long* d_clamped) {
-    const int64_t n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+                           const double* d_sorted_u, int32_t* d_anc, unsigned long long* d_words,
+                           unsigned long long* d_cdf_local, uint64_t stream_id, unsigned long long* d_clamped) {
+    const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     if (c->d_heavy_F == nullptr || c->heavy_cap_n < n) {
         // at most n / WS_HEAVY_TILE_SLOTS families can own more than WS_HEAVY_TILE_SLOTS offspring each
         if (c->d_heavy_F) {
@@ -953,7 +956,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
         CK(c, cudaMalloc(&c->d_heavy_F, sizeof(int32_t) * slots * (WS_SCAN_TILE + 2)));
         c->heavy_cap_n = n;
     }
-    CK(c, cudaMemsetAsync(d_words, 0, sizeof(unsigned long long) * (size_t)n_tiles, c->stream));
+    (void)n_tiles;
     CK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int) * 2, c->stream));
     WsScanParams S;
     memset(&S, 0, sizeof(S));
@@ -969,14 +972,15 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     S.sorted_u = d_sorted_u;
     S.ancestors = d_anc;
     S.tile_words = d_words;
+    S.cdf_local = d_cdf_local;
     S.tile_counter = c->d_tile_counter;
     S.n_clamped = d_clamped;
     S.heavy_count = c->d_tile_counter + 1;
     S.heavy_F = c->d_heavy_F;
-    const int grid = (int)std::min<int64_t>((n_tiles + WS_SCAN_BLOCK / 32 - 1) / (WS_SCAN_BLOCK / 32), (int64_t)c->sm_count * 4);
     TimedEvent te;
     timed_begin(c, KC_SCAN, te);
-    CK(c, ws_launch_scan_search(S, std::max(1, grid), c->stream));
+    CK(c, ws_launch_scan_search(S, 0, c->stream));
+    c->stats.kernel_launches += 3;  // cdf tiles, offsets, search, heavy expansion
     timed_end(c, te);
     return WS_OK;
 }
@@ -1010,7 +1014,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
         const uint64_t stream_id = c->next_stream++;
         // planes still waiting for the PREVIOUS ancestors must be gathered before d_anc is overwritten
         TRY(materialize_planes(c));
-        TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, nullptr, c->d_anc, c->d_tile_words, stream_id, c->d_counters + 0));
+        TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, nullptr, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id, c->d_counters + 0));
         if (c->lazy_gather) {
             // resample!(store, indices) is deferred: each plane is gathered when it is next read
             for (auto& col : c->cols)
@@ -1169,11 +1173,12 @@ static int resample_host_impl(ws_ctx* c, const double* weights, int64_t n, int s
     TRY(flush_window(c));
     CK(c, cudaSetDevice(c->device));
     if (n >= (int64_t)2147483647 - 65536) return fail(c, WS_EINVAL, "n must be < 2^31 - 65536");
-    TempBuf w, u, anc, words;
-    const int64_t n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    TempBuf w, u, anc, words, cdf;
+    const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     CK(c, cudaMalloc(&w.p, sizeof(double) * (size_t)n));
     CK(c, cudaMalloc(&anc.p, sizeof(int32_t) * (size_t)n));
     CK(c, cudaMalloc(&words.p, sizeof(unsigned long long) * (size_t)n_tiles));
+    CK(c, cudaMalloc(&cdf.p, sizeof(unsigned long long) * (size_t)n));
     CK(c, cudaMemcpyAsync(w.p, weights, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     if (uniforms != nullptr) {
         CK(c, cudaMalloc(&u.p, sizeof(double) * (size_t)n_uniforms));
@@ -1182,8 +1187,8 @@ static int resample_host_impl(ws_ctx* c, const double* weights, int64_t n, int s
     CK(c, cudaMemsetAsync(c->d_counters + 1, 0, sizeof(unsigned long long), c->stream));
     const uint64_t stream_id = c->next_stream++;
     TRY(run_scan_search(c, (const double*)w.p, 1, scheme, n, sorted_mode ? nullptr : (const double*)u.p,
-                        sorted_mode ? (const double*)u.p : nullptr, (int32_t*)anc.p, (unsigned long long*)words.p, stream_id,
-                        c->d_counters + 1));
+                        sorted_mode ? (const double*)u.p : nullptr, (int32_t*)anc.p, (unsigned long long*)words.p,
+                        (unsigned long long*)cdf.p, stream_id, c->d_counters + 1));
     CK(c, cudaMemcpyAsync(indices_out, anc.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     unsigned long long h_clamped = 0;
     CK(c, cudaMemcpyAsync(&h_clamped, c->d_counters + 1, sizeof(h_clamped), cudaMemcpyDeviceToHost, c->stream));
