@@ -190,7 +190,11 @@ def main():
     obs = synth_obs(W + K)
     build = ws.model(SSM2D_FILTER)
 
-    state = ws.SMCState(N, ess_perc_min=1.0, seed=1234 + rank, device=local_rank)
+    if world > 1:
+        # one GLOBAL filter of N * world particles, sharded by slot range; exact global resampling
+        state = ws.sharded_state(N * world, ess_perc_min=1.0, seed=1234, device=local_rank)
+    else:
+        state = ws.SMCState(N, ess_perc_min=1.0, seed=1234, device=local_rank)
     st = state.store
     import ctypes as C
     sp = C.c_void_p()
@@ -222,6 +226,9 @@ def main():
     st._call("ws_set_timing", 1)
     st._call("ws_reset_kernel_times")
     stats0 = state.stats()
+    mig0c = C.c_int64()
+    st._call("ws_get_migrated", C.byref(mig0c))
+    mig0 = mig0c.value
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -245,11 +252,14 @@ def main():
     clocks = sampler.stop()
     stats1 = state.stats()
     kt = state.kernel_times()
+    mig = C.c_int64()
+    st._call("ws_get_migrated", C.byref(mig))
+    migrated_per_step = (mig.value - mig0) / max(1, K)
 
     if world > 1:
-        t = torch.tensor([dev_ms, wall_ms], device="cuda", dtype=torch.float64)
+        t = torch.tensor([dev_ms, wall_ms, migrated_per_step], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(t[0]), float(t[1])
+        dev_ms, wall_ms, migrated_per_step = float(t[0]), float(t[1]), float(t[2])
 
     total_updates = float(N) * K * world
     value = total_updates / (dev_ms * 1e-3)
@@ -258,7 +268,8 @@ def main():
 
     peak, peak_src = measured_peaks()
     per_kernel = {}
-    pass_bytes = ALG_BYTES_PASS_EAGER if args.eager_gather else ALG_BYTES_PASS_LAZY
+    eager = args.eager_gather or world > 1
+    pass_bytes = ALG_BYTES_PASS_EAGER if eager else ALG_BYTES_PASS_LAZY
     for name, alg in (("gather", ALG_BYTES_GATHER), ("fused_pass", pass_bytes), ("scan_search", ALG_BYTES_SCAN)):
         k = kt[name]
         if k["launches"] > 0 and k["ms"] > 0:
@@ -280,8 +291,8 @@ def main():
                                    "note": "224 B is SURVEY §8(d)'s figure for the reference's order of work (eager "
                                            "6-plane gather); the deferred-gather design only has to move "
                                            f"{NECESSARY_BYTES_STEP_LAZY} B per particle-update",
-                                   "necessary_bytes_per_particle": None if args.eager_gather else NECESSARY_BYTES_STEP_LAZY,
-                                   "frac_of_necessary": None if args.eager_gather else
+                                   "necessary_bytes_per_particle": None if eager else NECESSARY_BYTES_STEP_LAZY,
+                                   "frac_of_necessary": None if eager else
                                    NECESSARY_BYTES_STEP_LAZY * N * K / (dev_ms * 1e-3) / 1e9 / peak}}
 
     if rank == 0:
@@ -299,8 +310,10 @@ def main():
             "config": {"workload": "ssm2d_filter_only_bootstrap (BASELINE configs[1]: examples/2D_ssm.jl with x overwritten), "
                                    "ess_perc_min=1.0 (resample + 6-plane gather every step)",
                        "particles_per_gpu": N, "planes": P_PLANES, "resampler": "stratified",
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent shards (island filters, local resampling; "
-                                                                       "global NCCL exchange not built yet)",
+                       "parallelism": "single GPU" if world == 1 else
+                       f"{world} ranks: ONE filter of {N * world} particles sharded by slot range; exact global stratified "
+                       "resampling (NCCL allgather of weight mass, send/recv migration of offspring)",
+                       "migrated_particles_per_step": migrated_per_step,
                        "l2": "working set 10.4 GB per GPU >> 126 MB L2 (no flush needed)",
                        "log_evidence": le, "log_evidence_after_warmup": le0},
             "roofline": roofline, "cpu_baseline": cpu,

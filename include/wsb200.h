@@ -285,6 +285,8 @@ int ws_reset_kernel_times(ws_ctx* ctx);
  * results are identical either way. */
 int ws_set_lazy_gather(ws_ctx* ctx, int on);
 int ws_set_timing(ws_ctx* ctx, int on); /* record per-phase CUDA events (adds syncs; for profiling only) */
+/* sharded state: particles this rank has received from other ranks in all resampling steps so far */
+int ws_get_migrated(ws_ctx* ctx, int64_t* out);
 /* the Philox stream id the next random statement / resample will use, and the key (tests reproduce draws) */
 int ws_next_philox_stream(ws_ctx* ctx, uint64_t* stream_out, uint64_t* seed_out);
 /* raw cudaStream_t of the context (as void*), so a host can bracket calls with its own events */

@@ -145,6 +145,7 @@ SIGNATURES = {
     "ws_set_timing": (C.c_int, [_ctx, C.c_int]),
     "ws_set_lazy_gather": (C.c_int, [_ctx, C.c_int]),
     "ws_next_philox_stream": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ws_get_migrated": (C.c_int, [_ctx, _i64p]),
     "ws_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
 }
 
@@ -160,6 +161,15 @@ def load():
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(nvcc, sm_100a).  wsb200 has no CPU fallback.")
+    if "WSB200_NCCL_LIB" not in os.environ:
+        # share the process's NCCL (the copy PyTorch bundles) instead of loading a second one
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["WSB200_NCCL_LIB"] = cand
+                break
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -27,7 +27,7 @@ __all__ = [
     "AccessorSample", "Observe", "Weight", "Sequence", "Loop", "Cond", "Resample", "Move", "ScoreCtx", "apply",
     "score", "run", "score_logpdf", "marginal_diversity", "WeightedKernel", "Normal", "MvNormal", "Exponential",
     "importance_kernel", "default_kernels", "RW", "autoRW", "default_proposals", "nparticles", "hascol", "getcol",
-    "colnames", "resample",
+    "colnames", "resample", "nccl_unique_id", "shard_bounds", "sharded_state",
 ]
 
 
@@ -44,16 +44,29 @@ class DeviceColumnStore:
     ``getcol`` returns a host COPY (download); device-resident access is through statements.
     """
 
-    def __init__(self, n, *, device=0, seed=0, ess_perc_min=0.5, resampler="stratified"):
+    def __init__(self, n, *, device=0, seed=0, ess_perc_min=0.5, resampler="stratified", rank=0, nranks=1, nccl_id=None):
+        """``n`` is the GLOBAL particle count; with ``nranks > 1`` this rank owns the slots
+        [rank*n/nranks, (rank+1)*n/nranks) and ``nccl_id`` is the 128-byte id from :func:`nccl_unique_id`."""
         lib = L.load()
         self._lib = lib
         self._ctx = C.c_void_p()
-        rc = lib.ws_create(C.byref(self._ctx), int(n), int(device), int(seed) & (2 ** 64 - 1), float(ess_perc_min),
-                           L.RESAMPLER[resampler])
+        if nranks > 1:
+            if nccl_id is None or len(nccl_id) != 128:
+                raise ValueError("a sharded state needs the 128-byte NCCL unique id created by rank 0")
+            idbuf = C.create_string_buffer(bytes(nccl_id), 128)
+            rc = lib.ws_create_sharded(C.byref(self._ctx), int(n), int(rank), int(nranks), idbuf, int(device),
+                                       int(seed) & (2 ** 64 - 1), float(ess_perc_min), L.RESAMPLER[resampler])
+        else:
+            rc = lib.ws_create(C.byref(self._ctx), int(n), int(device), int(seed) & (2 ** 64 - 1), float(ess_perc_min),
+                               L.RESAMPLER[resampler])
         if rc != 0:
             msg = lib.ws_last_error(None)
             raise WsError(rc, msg.decode() if msg else "")
-        self.n = int(n)
+        nl, ng = C.c_int64(), C.c_int64()
+        check(self._ctx, lib.ws_n_particles(self._ctx, C.byref(nl), C.byref(ng)))
+        self.n = nl.value           # local shard size: every host buffer of this store has this length
+        self.n_global = ng.value
+        self.rank, self.nranks = int(rank), int(nranks)
 
     # -- C-ABI plumbing ---------------------------------------------------------------------------
     def _call(self, name, *args):
@@ -141,6 +154,31 @@ class DeviceColumnStore:
 ColumnStore = DeviceColumnStore
 
 
+def nccl_unique_id():
+    """128-byte ncclUniqueId (create on rank 0, hand to every rank's SMCState)."""
+    buf = C.create_string_buffer(128)
+    rc = L.load().ws_nccl_unique_id(buf)
+    if rc != 0:
+        msg = L.load().ws_last_error(None)
+        raise WsError(rc, msg.decode() if msg else "")
+    return buf.raw
+
+
+def shard_bounds(n_global, rank, nranks):
+    """global slot range [lo, hi) owned by ``rank`` (same arithmetic as ws_create_sharded)."""
+    return (n_global * rank) // nranks, (n_global * (rank + 1)) // nranks
+
+
+def sharded_state(n_global, *, make_id=nccl_unique_id, **kw):
+    """SMCState sharded over the ranks of an initialised ``torch.distributed`` process group (one rank per
+    GPU): rank 0 creates the NCCL id, it is broadcast as an object, every rank builds its shard."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [make_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return SMCState(n_global, rank=rank, nranks=world, nccl_id=box[0], **kw)
+
+
 def nparticles(store): return store.nparticles()
 def hascol(store, name): return store.hascol(name)
 def getcol(store, name): return store.getcol(name)
@@ -155,13 +193,14 @@ class SMCState:
     """``SMCState(n; ess_perc_min=0.5)`` (types.jl:48-78).  Weights, flags and depth live in the C
     context; the attributes below read / write them."""
 
-    def __init__(self, n_or_store, *, ess_perc_min=0.5, seed=0, device=0, resampler="stratified", show_progress=False):
+    def __init__(self, n_or_store, *, ess_perc_min=0.5, seed=0, device=0, resampler="stratified", show_progress=False,
+                 rank=0, nranks=1, nccl_id=None):
         if isinstance(n_or_store, DeviceColumnStore):
             self.store = n_or_store
             self.store._call("ws_set_ess_perc_min", float(ess_perc_min))
         else:
             self.store = DeviceColumnStore(int(n_or_store), device=device, seed=seed, ess_perc_min=ess_perc_min,
-                                           resampler=resampler)
+                                           resampler=resampler, rank=rank, nranks=nranks, nccl_id=nccl_id)
         self._root = None
         self._tape_valid = True  # the recorded tape is the score! walk of `root` up to `depth`
         self.record_tape = True

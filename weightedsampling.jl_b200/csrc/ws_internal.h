@@ -67,7 +67,13 @@ struct WsScanParams {
     const WsReduceOut* red;    // mode 0; also carries do_resample (checked when gate != 0)
     int32_t gate;              // 1: return immediately unless red->do_resample
     int32_t pad;
-    int64_t n;                 // particles == slots (single GPU)
+    int64_t n;                 // local particles (this rank's shard)
+    int64_t n_slots;           // output slots == GLOBAL particle count (== n on one GPU)
+    unsigned long long cdf_offset;  // fixed-point mass of all lower ranks (0 on one GPU)
+    int32_t slot_base;         // global index of the first slot this rank produces; ancestors[slot - slot_base]
+    int32_t last_rank;         // the last particle of the last rank takes the clamped slots
+    int32_t* bounds;           // [2] ws_bounds_kernel: first / end global slot produced by this rank
+    unsigned long long* total; // [1] ws_cdf_offsets_kernel: this rank's fixed-point mass
     uint64_t seed, stream;     // Philox stream for the slot uniforms
     const double* replay_u;    // n uniforms (stratified) / 1 uniform (systematic) or nullptr
     const double* sorted_u;    // multinomial: n sorted uniforms (device)
@@ -95,6 +101,12 @@ cudaError_t ws_launch_reduce_logw(const double* logw, int64_t n, WsLse* partials
 cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min,
                                WsReduceOut* out, cudaStream_t s);
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s);
+// sharded resampling runs the same passes in two halves with collectives in between
+cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s);     // tile CDF + offsets (+ total)
+cudaError_t ws_launch_bounds(const WsScanParams& P, cudaStream_t s);  // first / end slot of this rank
+cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s);  // F(C_m) + expansion (+ heavy tiles)
+cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_t n_global, double ess_perc_min,
+                                      WsReduceOut* out, cudaStream_t s);
 cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s);
 cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStream_t s);
 cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,

@@ -287,6 +287,40 @@ cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_
     return cudaGetLastError();
 }
 
+// Sharded state: combine the ranks' (m, S, Q) triples (allgathered, rank order) into the global
+// reduction.  Every rank runs this on identical inputs in identical order, so the ESS decision and the
+// normalisation constants are bit-identical on all ranks.
+__global__ void ws_finalize_global_kernel(const double* __restrict__ all_msq, int n_ranks, int64_t n_global,
+                                          double ess_perc_min, WsReduceOut* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    WsLse tot;
+    tot.m = -INFINITY;
+    tot.S = 0.0;
+    tot.Q = 0.0;
+    for (int r = 0; r < n_ranks; ++r) {
+        WsLse v;
+        v.m = all_msq[3 * r + 0];
+        v.S = all_msq[3 * r + 1];
+        v.Q = all_msq[3 * r + 2];
+        tot = lse_combine(tot, v);
+    }
+    out->m = tot.m;
+    out->S = tot.S;
+    out->Q = tot.Q;
+    const double lse = tot.m + log(tot.S);
+    out->lse = lse;
+    const double nn = (double)n_global;
+    out->ess_perc = (tot.S * tot.S) / (nn * tot.Q);
+    out->log_mean_w = lse - log(nn);
+    out->do_resample = (out->ess_perc < ess_perc_min) ? 1 : 0;
+}
+
+cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_t n_global, double ess_perc_min,
+                                      WsReduceOut* out, cudaStream_t s) {
+    ws_finalize_global_kernel<<<1, 32, 0, s>>>(all_msq, n_ranks, n_global, ess_perc_min, out);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // CDF scan fused with the ancestor search
 // ------------------------------------------------------------------------------------------
@@ -344,8 +378,8 @@ __device__ __forceinline__ int64_t ws_count_sorted_le(const double* __restrict__
 }
 
 __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double inv_n, SlotUniform& su) {
-    if (P.sorted_u != nullptr) return ws_count_sorted_le(P.sorted_u, P.n, C);
-    return ws_count_slots_le(C, P.n, inv_n, su);
+    if (P.sorted_u != nullptr) return ws_count_sorted_le(P.sorted_u, P.n_slots, C);
+    return ws_count_slots_le(C, P.n_slots, inv_n, su);
 }
 
 // ---- CDF + search in three dependency-free passes ------------------------------------------------
@@ -404,7 +438,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __gri
         m = P.red->m;
         Sden = P.red->S;  // divide (not multiply by a reciprocal): w = e / S as exp_norm does
     }
-    const double uniform_w = 1.0 / (double)n;
+    const double uniform_w = 1.0 / (double)P.n_slots;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
         unsigned long long q[WS_SCAN_ITEMS];
@@ -501,6 +535,45 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
         if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
+    if (threadIdx.x == 0 && P.total != nullptr) *P.total = s_carry;
+}
+
+// first / end global slot produced by this rank: F at the rank's left and right CDF edge
+template <bool EXACT_FP>
+__global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int ns = (int)P.n_slots;
+    const double inv_n = 1.0 / (double)ns;
+    SlotUniform su;
+    su.scheme = (P.scheme == 1) ? 1 : 0;
+    su.seed = P.seed;
+    su.stream = P.stream;
+    su.replay = P.replay_u;
+    su.r0 = 0.0;
+    su.cached_blk = -1;
+    unsigned long long r0_int = 0ull;
+    if (P.scheme == 1 && P.sorted_u == nullptr) {
+        if (P.replay_u != nullptr) {
+            su.r0 = P.replay_u[0];
+        } else {
+            ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
+            su.r0 = ws_u01(r.x, r.y);
+            r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
+        }
+    }
+    const unsigned long long lo = P.cdf_offset, hi = P.cdf_offset + *P.total;
+    int fs, fe;
+    if (EXACT_FP) {
+        fs = (int)ws_F(P, ws_fxs_to_double(lo), inv_n, su);
+        fe = (int)ws_F(P, ws_fxs_to_double(hi), inv_n, su);
+    } else {
+        fs = ws_F_int(lo, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+        fe = ws_F_int(hi, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+    }
+    if (P.cdf_offset == 0ull) fs = 0;  // F(C_0) is 0 by definition for the very first particle
+    if (P.last_rank) fe = ns;
+    P.bounds[0] = fs;
+    P.bounds[1] = fe;
 }
 
 template <bool EXACT_FP>
@@ -511,9 +584,11 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __gri
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int32_t* const out_s = out_all[warp];
 
-    const int n = (int)P.n;
+    const int n = (int)P.n;          // local particles
+    const int ns = (int)P.n_slots;   // global slots
     const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
-    const double inv_n = 1.0 / (double)n;
+    const double inv_n = 1.0 / (double)ns;
+    const int slot_base = P.slot_base;
     SlotUniform su;
     su.scheme = (P.scheme == 1) ? 1 : 0;
     su.seed = P.seed;
@@ -536,7 +611,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __gri
     for (int tile = blockIdx.x * WS_WARPS_PER_CTA + warp; tile < n_tiles; tile += warps_total) {
         const int tile_base = tile * WS_SCAN_TILE;
         const int item0 = tile_base + lane * WS_SCAN_ITEMS;
-        const unsigned long long offset = __ldg(P.tile_words + tile_base / WS_CDF_TILE);
+        const unsigned long long offset = P.cdf_offset + __ldg(P.tile_words + tile_base / WS_CDF_TILE);
 
         // global fixed-point CDF of the lane's 8 consecutive particles
         unsigned long long C[WS_SCAN_ITEMS];
@@ -562,23 +637,30 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __gri
             const int gi = item0 + k;
             int fk;
             if (gi >= n) {
-                fk = n;
+                fk = -1;  // patched below
             } else {
                 if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k]), inv_n, su);
-                else fk = ws_F_int(C[k], (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
-                if (gi == n - 1) {
-                    if (fk < n) atomicAdd(P.n_clamped, (unsigned long long)(n - fk));
-                    fk = n;  // leftover slots go to the last particle (the reference would throw BoundsError)
+                else fk = ws_F_int(C[k], (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+                if (gi == n - 1 && P.last_rank) {
+                    if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
+                    fk = ns;  // leftover slots go to the last particle (the reference would throw BoundsError)
                 }
             }
             f[k] = fk;
         }
-        int fstart = 0;
+        // items beyond the shard produce nothing: they repeat the F of the shard's last particle
+        {
+            const int rank_end = P.bounds != nullptr ? P.bounds[1] : ns;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k)
+                if (f[k] < 0) f[k] = rank_end;
+        }
+        int fstart = slot_base;
         if (lane == 0 && tile != 0) {
             const int p = tile_base - 1;
-            const unsigned long long Cp = __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+            const unsigned long long Cp = P.cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
             if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
-            else fstart = ws_F_int(Cp, (unsigned int)n, su.scheme, r0_int, P.seed, P.stream);
+            else fstart = ws_F_int(Cp, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
         }
         fstart = __shfl_sync(0xffffffffu, fstart, 0);
         int f_prev = __shfl_up_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 1);
@@ -645,7 +727,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __gri
                 }
             }
             __syncwarp();
-            for (int pos = chunk + lane; pos < chunk_end; pos += 32) P.ancestors[pos] = out_s[pos - chunk];
+            for (int pos = chunk + lane; pos < chunk_end; pos += 32) P.ancestors[pos - slot_base] = out_s[pos - chunk];
             __syncwarp();
         }
     }
@@ -675,33 +757,48 @@ __global__ void __launch_bounds__(256) ws_expand_heavy_kernel(const __grid_const
                 const int mid = (lo + hi) >> 1;
                 if ((int64_t)Fs[mid] > j) hi = mid; else lo = mid + 1;
             }
-            P.ancestors[j] = (int32_t)(tile_base + lo);
+            P.ancestors[j - P.slot_base] = (int32_t)(tile_base + lo);
         }
     }
 }
 
-cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
-    (void)grid;
+cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s) {
     const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
-    const int64_t warp_tiles = (P.n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     int g1 = (int)(cdf_tiles < (int64_t)g_sm_count * 8 ? cdf_tiles : (int64_t)g_sm_count * 8);
     if (g1 < 1) g1 = 1;
     ws_cdf_tiles_kernel<<<g1, WS_SCAN_BLOCK, 0, s>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ws_cdf_offsets_kernel<<<1, 1024, 0, s>>>(P);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+cudaError_t ws_launch_bounds(const WsScanParams& P, cudaStream_t s) {
+    const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
+    if (exact_fp) ws_bounds_kernel<true><<<1, 32, 0, s>>>(P);
+    else ws_bounds_kernel<false><<<1, 32, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
+    const int64_t warp_tiles = (P.n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     const int64_t ctas = (warp_tiles + WS_WARPS_PER_CTA - 1) / WS_WARPS_PER_CTA;
     int g3 = (int)(ctas < (int64_t)g_sm_count * 6 ? ctas : (int64_t)g_sm_count * 6);
     if (g3 < 1) g3 = 1;
     const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
     if (exact_fp) ws_search_kernel<true><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
     else ws_search_kernel<false><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);
     return cudaGetLastError();
+}
+
+cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
+    (void)grid;
+    cudaError_t e = ws_launch_cdf(P, s);
+    if (e != cudaSuccess) return e;
+    return ws_launch_search(P, s);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+
 #include "../../include/wsb200.h"
 #include "ws_internal.h"
 #include "ws_lowering.h"
@@ -26,6 +28,65 @@ using wsl::Program;
 using wsl::Val;
 
 static thread_local std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen) so that the library loads on machines without NCCL and shares the
+// process's NCCL instance (e.g. the one PyTorch bundles) instead of linking a second copy.
+// ------------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { WS_NCCL_INT8 = 0, WS_NCCL_UINT8 = 1, WS_NCCL_INT32 = 2, WS_NCCL_UINT32 = 3, WS_NCCL_INT64 = 4, WS_NCCL_UINT64 = 5,
+       WS_NCCL_FLOAT64 = 8 };
+enum { WS_NCCL_SUM = 0 };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static bool load_nccl(std::string& err) {
+    if (g_nccl.handle != nullptr) return true;
+    std::vector<std::string> cand;
+    if (const char* e = getenv("WSB200_NCCL_LIB")) cand.push_back(e);
+    cand.push_back("libnccl.so.2");
+    cand.push_back("libnccl.so");
+    void* h = nullptr;
+    for (auto& c : cand) {
+        h = dlopen(c.c_str(), RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        err = std::string("cannot load NCCL (set WSB200_NCCL_LIB): ") + (dlerror() ? dlerror() : "");
+        return false;
+    }
+#define WS_SYM(field, name)                                                  \
+    *(void**)(&g_nccl.field) = dlsym(h, name);                               \
+    if (!g_nccl.field) {                                                     \
+        err = std::string("NCCL symbol missing: ") + name;                   \
+        return false;                                                        \
+    }
+    WS_SYM(GetUniqueId, "ncclGetUniqueId")
+    WS_SYM(CommInitRank, "ncclCommInitRank")
+    WS_SYM(CommDestroy, "ncclCommDestroy")
+    WS_SYM(AllGather, "ncclAllGather")
+    WS_SYM(AllReduce, "ncclAllReduce")
+    WS_SYM(Send, "ncclSend")
+    WS_SYM(Recv, "ncclRecv")
+    WS_SYM(GroupStart, "ncclGroupStart")
+    WS_SYM(GroupEnd, "ncclGroupEnd")
+    WS_SYM(GetErrorString, "ncclGetErrorString")
+#undef WS_SYM
+    g_nccl.handle = h;
+    return true;
+}
 
 enum WsKernelClass { KC_VM = 0, KC_REDUCE, KC_FINALIZE, KC_SCAN, KC_GATHER, KC_FILL, KC_MOVE, KC_OTHER, KC_COUNT };
 
@@ -115,6 +176,17 @@ struct ws_ctx {
     double* h_scratch = nullptr;  // pinned
     size_t h_scratch_bytes = 0;
 
+    // sharded state (one rank per GPU): NCCL communicator + exchange scratch
+    ncclComm_t comm = nullptr;
+    double* d_all_msq = nullptr;             // [nranks][3] allgathered (m, S, Q)
+    unsigned long long* d_all_tot = nullptr; // [nranks] allgathered fixed-point masses; [nranks] own total staged at the end
+    int32_t* d_all_bounds = nullptr;         // [nranks][2] allgathered (first, end) produced slot; own pair staged at the end
+    int32_t* d_anc_src = nullptr;            // ancestors (local indices) of the slots this rank produces
+    int64_t anc_src_cap = 0;
+    double* d_send = nullptr;                // staging of outgoing offspring, one plane batch at a time
+    int64_t send_cap = 0;
+    int64_t migrated_total = 0;              // particles received from other ranks so far
+
     // stats / timing
     ws_stats stats{};
     bool timing = false;
@@ -151,6 +223,11 @@ static int fail(ws_ctx* c, int code, const char* fmt, ...) {
     do {                          \
         int rc__ = (expr);        \
         if (rc__ != WS_OK) return rc__; \
+    } while (0)
+#define NCK(c, call)                                                                                       \
+    do {                                                                                                   \
+        int r__ = (call);                                                                                  \
+        if (r__ != 0) return fail((c), WS_ENCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r__));      \
     } while (0)
 
 // ------------------------------------------------------------------------------------------
@@ -259,13 +336,16 @@ extern "C" const char* ws_last_error(const ws_ctx* ctx) { return ctx ? ctx->err.
 
 extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int nranks, const void* nccl_unique_id,
                                  int device, uint64_t seed, double ess_perc_min, int resampler) {
-    (void)nccl_unique_id;
     if (out == nullptr) return fail(nullptr, WS_EINVAL, "ws_create: out is NULL");
     *out = nullptr;
     if (n_global <= 0) return fail(nullptr, WS_EINVAL, "ws_create: n_particles must be positive (got %lld)", (long long)n_global);
     if (n_global >= (int64_t)2147483647 - 65536) return fail(nullptr, WS_EINVAL, "ws_create: n_particles must be < 2^31 - 65536 (Int32 ancestors)");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, WS_EINVAL, "ws_create: bad rank %d of %d", rank, nranks);
-    if (nranks > 1) return fail(nullptr, WS_EUNSUPPORTED, "ws_create_sharded: multi-rank resampling is not built yet");
+    if (nranks > 1 && nccl_unique_id == nullptr) return fail(nullptr, WS_EINVAL, "ws_create_sharded: nccl_unique_id is NULL");
+    if (nranks > 1) {
+        std::string err;
+        if (!load_nccl(err)) return fail(nullptr, WS_ENCCL, "%s", err.c_str());
+    }
     if (resampler < 0 || resampler > 2) return fail(nullptr, WS_EINVAL, "ws_create: unknown resampler %d", resampler);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -318,7 +398,21 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     CKC(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int) * 2));
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 4));
     CKC(cudaMemsetAsync(c->d_counters, 0, sizeof(unsigned long long) * 4, c->stream));
+    CKC(cudaMalloc(&c->d_all_msq, sizeof(double) * 3 * (size_t)(nranks + 1)));
+    CKC(cudaMalloc(&c->d_all_tot, sizeof(unsigned long long) * (size_t)(nranks + 1)));
+    CKC(cudaMalloc(&c->d_all_bounds, sizeof(int32_t) * 2 * (size_t)(nranks + 1)));
 #undef CKC
+    if (nranks > 1) {
+        ncclUniqueId id;
+        memcpy(&id, nccl_unique_id, sizeof(id));
+        int r = g_nccl.CommInitRank(&c->comm, nranks, id, rank);
+        if (r != 0) {
+            int rc = fail(nullptr, WS_ENCCL, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(r));
+            ws_destroy(c);
+            return rc;
+        }
+        c->lazy_gather = false;  // offspring are exchanged between ranks inside Resample
+    }
     c->logw_uniform = true;
     c->logw_base = 0.0;
     *out = c;
@@ -330,8 +424,14 @@ extern "C" int ws_create(ws_ctx** out, int64_t n_particles, int device, uint64_t
 }
 
 extern "C" int ws_nccl_unique_id(void* out128) {
-    (void)out128;
-    return fail(nullptr, WS_EUNSUPPORTED, "ws_nccl_unique_id: multi-rank support is not built yet");
+    if (out128 == nullptr) return fail(nullptr, WS_EINVAL, "ws_nccl_unique_id: out is NULL");
+    std::string err;
+    if (!load_nccl(err)) return fail(nullptr, WS_ENCCL, "%s", err.c_str());
+    ncclUniqueId id;
+    int r = g_nccl.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, WS_ENCCL, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+    memcpy(out128, &id, sizeof(id));
+    return WS_OK;
 }
 
 extern "C" int ws_destroy(ws_ctx* c) {
@@ -352,6 +452,12 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_tile_counter);
     cudaFree(c->d_heavy_F);
     cudaFree(c->d_counters);
+    cudaFree(c->d_all_msq);
+    cudaFree(c->d_all_tot);
+    cudaFree(c->d_all_bounds);
+    cudaFree(c->d_anc_src);
+    cudaFree(c->d_send);
+    if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_score_ops);
     cudaFree(c->d_replay_n);
     cudaFree(c->d_replay_u);
@@ -530,6 +636,17 @@ static int tape_statement(ws_ctx* c, F body) {
         return fail(c, WS_EUNSUPPORTED, "score tape references more than %d distinct planes", WS_SCORE_MAX_REGS - WS_SCORE_TEMPS);
     c->score.end_statement();
     c->tape.push_back(TapeEntry{c->depth, (int32_t)c->score.ops.size()});
+    return WS_OK;
+}
+
+// sum a few host doubles over all ranks (NCCL allreduce on a small device buffer)
+static int allreduce_host_doubles(ws_ctx* c, double* v, int n) {
+    if (c->nranks <= 1) return WS_OK;
+    TRY(ensure_scratch(c, sizeof(double) * (size_t)n));
+    CK(c, cudaMemcpyAsync(c->d_scratch, v, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    NCK(c, g_nccl.AllReduce(c->d_scratch, c->d_scratch, (size_t)n, WS_NCCL_FLOAT64, WS_NCCL_SUM, c->comm, c->stream));
+    CK(c, cudaMemcpyAsync(v, c->d_scratch, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
     return WS_OK;
 }
 
@@ -890,6 +1007,13 @@ static int ensure_reduced(ws_ctx* c) {
     timed_begin(c, KC_FINALIZE, te);
     CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream));
     timed_end(c, te);
+    if (c->nranks > 1) {
+        // every rank reduces its shard; the (m, S, Q) triples are allgathered and combined in rank order
+        NCK(c, g_nccl.AllGather(c->d_red, c->d_all_msq, 3, WS_NCCL_FLOAT64, c->comm, c->stream));
+        timed_begin(c, KC_FINALIZE, te);
+        CK(c, ws_launch_finalize_global(c->d_all_msq, c->nranks, c->n_global, c->ess_perc_min, c->d_red, c->stream));
+        timed_end(c, te);
+    }
     CK(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut);
@@ -966,6 +1090,12 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     S.red = c->d_red;
     S.gate = 0;
     S.n = n;
+    S.n_slots = n;
+    S.cdf_offset = 0ull;
+    S.slot_base = 0;
+    S.last_rank = 1;
+    S.bounds = nullptr;
+    S.total = nullptr;
     S.seed = c->seed;
     S.stream = stream_id;
     S.replay_u = d_replay_u;
@@ -982,6 +1112,164 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     CK(c, ws_launch_scan_search(S, 0, c->stream));
     c->stats.kernel_launches += 3;  // cdf tiles, offsets, search, heavy expansion
     timed_end(c, te);
+    return WS_OK;
+}
+
+// Exact GLOBAL stratified resampling of a sharded particle set.
+//   1. tile CDF of the shard with the global (m, S)  ->  this rank's fixed-point mass T_r
+//   2. allgather T_r  ->  CDF offset O_r = sum_{q<r} T_q   (integers: identical on every rank)
+//   3. first / end global slot produced by this rank (F at the shard's CDF edges), allgathered
+//   4. search: ancestors (local indices) of the produced slots [fs_r, fe_r)
+//   5. per plane: gather the offspring in slot order; the part that falls into rank d's slot range
+//      [d N/R, (d+1) N/R) is sent to d (NCCL send/recv = all-to-all-v over NVLink); the part that stays
+//      is gathered straight into the back buffer.  Slot order makes every (source, destination) piece
+//      contiguous on both sides.
+static int resample_sharded(ws_ctx* c, const double* d_ru) {
+    const int R = c->nranks, r = c->rank;
+    const uint64_t stream_id = c->next_stream++;
+    WsScanParams S;
+    memset(&S, 0, sizeof(S));
+    S.logw = c->logw;
+    S.mode = 0;
+    S.scheme = c->resampler;
+    S.red = c->d_red;
+    S.n = c->n;
+    S.n_slots = c->n_global;
+    S.seed = c->seed;
+    S.stream = stream_id;
+    S.replay_u = d_ru;
+    S.ancestors = nullptr;
+    S.tile_words = c->d_tile_words;
+    S.cdf_local = c->d_cdf_local;
+    S.tile_counter = c->d_tile_counter;
+    S.n_clamped = c->d_counters + 0;
+    S.heavy_count = c->d_tile_counter + 1;
+    S.last_rank = (r == R - 1) ? 1 : 0;
+    S.total = c->d_all_tot + R;           // own total staged behind the allgather buffer
+    S.bounds = c->d_all_bounds + 2 * R;   // own (first, end) staged behind the allgather buffer
+    TimedEvent te;
+    timed_begin(c, KC_SCAN, te);
+    CK(c, ws_launch_cdf(S, c->stream));
+    timed_end(c, te);
+    NCK(c, g_nccl.AllGather(c->d_all_tot + R, c->d_all_tot, 1, WS_NCCL_UINT64, c->comm, c->stream));
+    std::vector<unsigned long long> tot(R);
+    CK(c, cudaMemcpyAsync(tot.data(), c->d_all_tot, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    unsigned long long off = 0ull;
+    for (int q = 0; q < r; ++q) off += tot[q];
+    S.cdf_offset = off;
+    CK(c, ws_launch_bounds(S, c->stream));
+    NCK(c, g_nccl.AllGather(c->d_all_bounds + 2 * R, c->d_all_bounds, 2, WS_NCCL_INT32, c->comm, c->stream));
+    std::vector<int32_t> bnd(2 * R);
+    CK(c, cudaMemcpyAsync(bnd.data(), c->d_all_bounds, sizeof(int32_t) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)(sizeof(unsigned long long) * R + sizeof(int32_t) * 2 * R);
+    const int64_t fs = bnd[2 * r], fe = bnd[2 * r + 1];
+    const int64_t produced = fe - fs;
+    if (produced > c->anc_src_cap) {
+        if (c->d_anc_src) CK(c, cudaFree(c->d_anc_src));
+        c->d_anc_src = nullptr;
+        c->anc_src_cap = produced + produced / 8 + 1024;
+        CK(c, cudaMalloc(&c->d_anc_src, sizeof(int32_t) * (size_t)c->anc_src_cap));
+    }
+    // heavy-tile tables are sized for the slots this rank can produce (at most n_global)
+    if (c->d_heavy_F == nullptr || c->heavy_cap_n < c->n_global) {
+        if (c->d_heavy_F) CK(c, cudaFree(c->d_heavy_F));
+        const size_t slots = (size_t)(c->n_global / WS_HEAVY_TILE_SLOTS) + 2;
+        CK(c, cudaMalloc(&c->d_heavy_F, sizeof(int32_t) * slots * (WS_SCAN_TILE + 2)));
+        c->heavy_cap_n = c->n_global;
+    }
+    S.heavy_F = c->d_heavy_F;
+    CK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int) * 2, c->stream));
+    S.ancestors = c->d_anc_src;
+    S.slot_base = (int32_t)fs;
+    timed_begin(c, KC_SCAN, te);
+    CK(c, ws_launch_search(S, c->stream));
+    timed_end(c, te);
+    c->stats.kernel_launches += 4;
+
+    // ---- exchange plan (slot ranges) ------------------------------------------------------------
+    auto rank_lo = [&](int d) { return (c->n_global * (int64_t)d) / R; };
+    const int64_t my_lo = rank_lo(r), my_hi = rank_lo(r + 1);
+    // what I send to d: produced slots in [rank_lo(d), rank_lo(d+1));  what I get from q: q's produced
+    // slots in my range
+    std::vector<int64_t> send_off(R), send_cnt(R), recv_off(R), recv_cnt(R);
+    int64_t max_remote = 0;
+    for (int d = 0; d < R; ++d) {
+        const int64_t a = std::max(fs, rank_lo(d)), e = std::min(fe, rank_lo(d + 1));
+        send_cnt[d] = std::max<int64_t>(0, e - a);
+        send_off[d] = a - fs;
+        const int64_t qa = std::max<int64_t>(bnd[2 * d], my_lo), qe = std::min<int64_t>(bnd[2 * d + 1], my_hi);
+        recv_cnt[d] = std::max<int64_t>(0, qe - qa);
+        recv_off[d] = qa - my_lo;
+        if (d != r) {
+            max_remote = std::max(max_remote, send_off[d] + send_cnt[d]);
+            c->migrated_total += recv_cnt[d];
+        }
+    }
+    // planes in batches: stage the remote part of a batch, exchange it, move on
+    std::vector<Plane> planes;
+    for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
+        for (int32_t k = 0; k < c->cols[ci].width; ++k) planes.push_back(Plane{ci, k});
+    const int BATCH = 8;
+    int64_t remote_total = 0;
+    for (int d = 0; d < R; ++d)
+        if (d != r) remote_total += send_cnt[d];
+    if (remote_total > 0 && produced * BATCH > c->send_cap) {
+        if (c->d_send) CK(c, cudaFree(c->d_send));
+        c->d_send = nullptr;
+        c->send_cap = produced * BATCH;
+        CK(c, cudaMalloc(&c->d_send, sizeof(double) * (size_t)c->send_cap));
+    }
+    for (size_t p0 = 0; p0 < planes.size(); p0 += BATCH) {
+        const int nb = (int)std::min<size_t>(BATCH, planes.size() - p0);
+        // (a) offspring that stay on this rank: gather straight into the back buffers
+        if (send_cnt[r] > 0) {
+            WsGatherParams G;
+            memset(&G, 0, sizeof(G));
+            G.n = send_cnt[r];
+            G.ancestors = c->d_anc_src + send_off[r];
+            G.n_planes = nb;
+            for (int k = 0; k < nb; ++k) {
+                const Plane pl = planes[p0 + k];
+                G.src[k] = c->cols[pl.col].front[pl.comp];
+                G.dst[k] = c->cols[pl.col].back[pl.comp] + recv_off[r];
+            }
+            timed_begin(c, KC_GATHER, te);
+            CK(c, ws_launch_gather(G, grid_for(c, G.n, 256, 8), c->stream));
+            timed_end(c, te);
+        }
+        // (b) offspring that migrate: gather the whole produced range of the batch into the staging
+        //     buffer (slot order), then send each destination its contiguous piece
+        if (remote_total > 0) {
+            WsGatherParams G;
+            memset(&G, 0, sizeof(G));
+            G.n = produced;
+            G.ancestors = c->d_anc_src;
+            G.n_planes = nb;
+            for (int k = 0; k < nb; ++k) {
+                const Plane pl = planes[p0 + k];
+                G.src[k] = c->cols[pl.col].front[pl.comp];
+                G.dst[k] = c->d_send + (size_t)k * produced;
+            }
+            timed_begin(c, KC_GATHER, te);
+            CK(c, ws_launch_gather(G, grid_for(c, G.n, 256, 8), c->stream));
+            timed_end(c, te);
+        }
+        NCK(c, g_nccl.GroupStart());
+        for (int k = 0; k < nb; ++k) {
+            const Plane pl = planes[p0 + k];
+            for (int d = 0; d < R; ++d) {
+                if (d == r) continue;
+                if (send_cnt[d] > 0)
+                    NCK(c, g_nccl.Send(c->d_send + (size_t)k * produced + send_off[d], (size_t)send_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
+                if (recv_cnt[d] > 0)
+                    NCK(c, g_nccl.Recv(c->cols[pl.col].back[pl.comp] + recv_off[d], (size_t)recv_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
+            }
+        }
+        NCK(c, g_nccl.GroupEnd());
+    }
+    for (auto& col : c->cols) std::swap(col.front, col.back);
     return WS_OK;
 }
 
@@ -1010,6 +1298,23 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
                             (long long)(c->cur_u + need), (long long)c->replay_u_len);
             d_ru = c->d_replay_u + c->cur_u;
             c->cur_u += need;
+        }
+        if (c->nranks > 1) {
+            TRY(resample_sharded(c, d_ru));
+            c->logw_uniform = true;
+            c->logw_base = r.log_mean_w;
+            c->partials_valid = false;
+            c->red_valid = false;
+            c->resampled = true;
+            c->stats.resamples_done++;
+            c->weights_changed = false;
+            if (info) {
+                info->fired = 1;
+                info->resampled = 1;
+                info->ess_perc = r.ess_perc;
+                info->log_mean_w = r.log_mean_w;
+            }
+            return WS_OK;
         }
         const uint64_t stream_id = c->next_stream++;
         // planes still waiting for the PREVIOUS ancestors must be gathered before d_anc is overwritten
@@ -1282,6 +1587,7 @@ extern "C" int ws_expectation(ws_ctx* c, const ws_expr* f, int32_t n_exprs, doub
         for (int b = 0; b < grid; ++b) s += c->h_scratch[(size_t)b * n_exprs + k];
         out[k] = s;
     }
+    if (c->nranks > 1) TRY(allreduce_host_doubles(c, out, n_exprs));
     return WS_OK;
 }
 
@@ -1485,6 +1791,8 @@ extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t
     TRY(flush_window(c));
     TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
+    if (c->nranks > 1)
+        return fail(c, WS_EUNSUPPORTED, "marginal_diversity on a sharded state needs a cross-rank distinct count (not built yet)");
     double best = INFINITY;
     for (int t = 0; t < n_targets; ++t) {
         TRY(check_plane(c, col[t], comp[t]));
@@ -1584,6 +1892,7 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
             std::vector<double> tot(n_mom, 0.0);
             for (int b = 0; b < std::max(1, grid); ++b)
                 for (int k = 0; k < n_mom; ++k) tot[k] += c->h_scratch[(size_t)b * n_mom + k];
+            TRY(allreduce_host_doubles(c, tot.data(), n_mom));  // sharded: moments of the GLOBAL particle set
             if (pass == 0) {
                 wsum = tot[0];
                 for (int t = 0; t < d; ++t) mean[t] = tot[1 + t] / wsum;
@@ -1704,6 +2013,11 @@ extern "C" int ws_next_philox_stream(ws_ctx* c, uint64_t* stream_out, uint64_t* 
     if (!c) return WS_EINVAL;
     if (stream_out) *stream_out = c->next_stream;
     if (seed_out) *seed_out = c->seed;
+    return WS_OK;
+}
+extern "C" int ws_get_migrated(ws_ctx* c, int64_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    *out = c->migrated_total;
     return WS_OK;
 }
 extern "C" int ws_stream(ws_ctx* c, void** stream_out) {
