@@ -112,6 +112,8 @@ cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStrea
 cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,
                                cudaStream_t s);
 cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int grid, cudaStream_t s);
+cudaError_t ws_launch_local_ancestors(int32_t* anc, int64_t n, const int32_t* anc_self, int64_t self_lo, int64_t self_hi,
+                                      int grid, cudaStream_t s);
 cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t n_idx, double* dst, cudaStream_t s);
 int ws_vm_max_grid(int n_regs, int sm_count);
 int ws_vm_smem_bytes(int n_regs);

@@ -877,6 +877,26 @@ cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int gr
     return cudaGetLastError();
 }
 
+// Sharded deferred gather: ancestor of local slot i.  Slots [self_lo, self_hi) are filled by this rank's
+// own offspring (anc_self, slot order); the slots below / above were received from lower / higher ranks
+// and sit, in slot order, in the spare rows n, n+1, ... behind every plane.
+__global__ void ws_local_ancestors_kernel(int32_t* __restrict__ anc, int64_t n, const int32_t* __restrict__ anc_self,
+                                          int64_t self_lo, int64_t self_hi) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int32_t a;
+        if (i < self_lo) a = (int32_t)(n + i);
+        else if (i >= self_hi) a = (int32_t)(n + self_lo + (i - self_hi));
+        else a = anc_self[i - self_lo];
+        anc[i] = a;
+    }
+}
+cudaError_t ws_launch_local_ancestors(int32_t* anc, int64_t n, const int32_t* anc_self, int64_t self_lo, int64_t self_hi,
+                                      int grid, cudaStream_t s) {
+    ws_local_ancestors_kernel<<<grid, 256, 0, s>>>(anc, n, anc_self, self_lo, self_hi);
+    return cudaGetLastError();
+}
+
 __global__ void ws_gather_rows_kernel(const double* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_idx,
                                       double* __restrict__ dst) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

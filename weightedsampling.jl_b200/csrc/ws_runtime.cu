@@ -17,6 +17,7 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <chrono>
 
 #include "../../include/wsb200.h"
 #include "ws_internal.h"
@@ -115,6 +116,7 @@ struct ws_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     int64_t n = 0;         // local particles
+    int64_t spare = 0;     // extra rows behind every plane: offspring received from other ranks land here
     int64_t n_global = 0;
     int64_t offset = 0;    // global index of local particle 0
     int rank = 0, nranks = 1;
@@ -186,6 +188,8 @@ struct ws_ctx {
     double* d_send = nullptr;                // staging of outgoing offspring, one plane batch at a time
     int64_t send_cap = 0;
     int64_t migrated_total = 0;              // particles received from other ranks so far
+    double phase_ms[8] = {0};                // WSB200_TRACE=1: host wall time per phase of resample_sharded
+    int64_t phase_n = 0;
 
     // stats / timing
     ws_stats stats{};
@@ -411,7 +415,25 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
             ws_destroy(c);
             return rc;
         }
-        c->lazy_gather = false;  // offspring are exchanged between ranks inside Resample
+        c->spare = std::max<int64_t>(4096, c->n / 32);
+        // NCCL sets up its peer-to-peer channels on first use (hundreds of ms); do that here, not in
+        // the first resampling steps: one 3-double message to and from every peer + the collectives used
+        {
+            bool ok = g_nccl.GroupStart() == 0;
+            for (int d = 0; d < nranks && ok; ++d) {
+                if (d == rank) continue;
+                ok = ok && g_nccl.Send(c->d_all_msq + 3 * nranks, 3, WS_NCCL_FLOAT64, d, c->comm, c->stream) == 0;
+                ok = ok && g_nccl.Recv(c->d_all_msq + 3 * d, 3, WS_NCCL_FLOAT64, d, c->comm, c->stream) == 0;
+            }
+            ok = ok && g_nccl.GroupEnd() == 0;
+            ok = ok && g_nccl.AllGather(c->d_all_tot + nranks, c->d_all_tot, 1, WS_NCCL_UINT64, c->comm, c->stream) == 0;
+            ok = ok && g_nccl.AllReduce(c->d_all_msq, c->d_all_msq, 3, WS_NCCL_FLOAT64, WS_NCCL_SUM, c->comm, c->stream) == 0;
+            if (!ok || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+                int rc = fail(nullptr, WS_ENCCL, "NCCL warm-up exchange failed");
+                ws_destroy(c);
+                return rc;
+            }
+        }
     }
     c->logw_uniform = true;
     c->logw_base = 0.0;
@@ -438,6 +460,12 @@ extern "C" int ws_destroy(ws_ctx* c) {
     if (c == nullptr) return WS_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (getenv("WSB200_TRACE") && c->phase_n > 0)
+        fprintf(stderr, "[wsb200 rank %d] sharded resample host ms/step: cdf+allgather+sync %.3f | bounds+allgather+sync %.3f | "
+                        "search launch %.3f | exchange %.3f (steady %.3f) | local-anc %.3f  (n=%lld)\n",
+                c->rank, c->phase_ms[0] / c->phase_n, c->phase_ms[1] / c->phase_n, c->phase_ms[2] / c->phase_n,
+                c->phase_ms[3] / c->phase_n, c->phase_ms[5] / std::max<int64_t>(1, c->phase_n - 6), c->phase_ms[4] / c->phase_n,
+                (long long)c->phase_n);
     for (auto& col : c->cols) {
         for (auto p : col.front) cudaFree(p);
         for (auto p : col.back) cudaFree(p);
@@ -730,8 +758,8 @@ extern "C" int ws_col_ensure(ws_ctx* c, const char* name, int32_t width, int32_t
     col.stale.assign((size_t)width, 0);
     for (int k = 0; k < width; ++k) {
         double *f = nullptr, *b = nullptr;
-        CK(c, cudaMalloc(&f, sizeof(double) * (size_t)c->n));
-        CK(c, cudaMalloc(&b, sizeof(double) * (size_t)c->n));
+        CK(c, cudaMalloc(&f, sizeof(double) * (size_t)(c->n + c->spare)));
+        CK(c, cudaMalloc(&b, sizeof(double) * (size_t)(c->n + c->spare)));
         CK(c, cudaMemsetAsync(f, 0, sizeof(double) * (size_t)c->n, c->stream));
         col.front.push_back(f);
         col.back.push_back(b);
@@ -1127,6 +1155,9 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
 static int resample_sharded(ws_ctx* c, const double* d_ru) {
     const int R = c->nranks, r = c->rank;
     const uint64_t stream_id = c->next_stream++;
+    auto t_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = t_now();
+    c->phase_n++;
     WsScanParams S;
     memset(&S, 0, sizeof(S));
     S.logw = c->logw;
@@ -1155,6 +1186,8 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     std::vector<unsigned long long> tot(R);
     CK(c, cudaMemcpyAsync(tot.data(), c->d_all_tot, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    c->phase_ms[0] += t_now() - t0;
+    t0 = t_now();
     unsigned long long off = 0ull;
     for (int q = 0; q < r; ++q) off += tot[q];
     S.cdf_offset = off;
@@ -1164,6 +1197,8 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     CK(c, cudaMemcpyAsync(bnd.data(), c->d_all_bounds, sizeof(int32_t) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)(sizeof(unsigned long long) * R + sizeof(int32_t) * 2 * R);
+    c->phase_ms[1] += t_now() - t0;
+    t0 = t_now();
     const int64_t fs = bnd[2 * r], fe = bnd[2 * r + 1];
     const int64_t produced = fe - fs;
     if (produced > c->anc_src_cap) {
@@ -1188,43 +1223,71 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     timed_end(c, te);
     c->stats.kernel_launches += 4;
 
+    c->phase_ms[2] += t_now() - t0;
+    t0 = t_now();
     // ---- exchange plan (slot ranges) ------------------------------------------------------------
     auto rank_lo = [&](int d) { return (c->n_global * (int64_t)d) / R; };
     const int64_t my_lo = rank_lo(r), my_hi = rank_lo(r + 1);
     // what I send to d: produced slots in [rank_lo(d), rank_lo(d+1));  what I get from q: q's produced
-    // slots in my range
+    // slots in my range.  Slot order makes every piece contiguous on both sides.
     std::vector<int64_t> send_off(R), send_cnt(R), recv_off(R), recv_cnt(R);
-    int64_t max_remote = 0;
+    int64_t remote_send = 0, remote_recv = 0;
     for (int d = 0; d < R; ++d) {
         const int64_t a = std::max(fs, rank_lo(d)), e = std::min(fe, rank_lo(d + 1));
         send_cnt[d] = std::max<int64_t>(0, e - a);
-        send_off[d] = a - fs;
+        send_off[d] = std::max<int64_t>(0, a - fs);
         const int64_t qa = std::max<int64_t>(bnd[2 * d], my_lo), qe = std::min<int64_t>(bnd[2 * d + 1], my_hi);
         recv_cnt[d] = std::max<int64_t>(0, qe - qa);
-        recv_off[d] = qa - my_lo;
+        recv_off[d] = std::max<int64_t>(0, qa - my_lo);
         if (d != r) {
-            max_remote = std::max(max_remote, send_off[d] + send_cnt[d]);
-            c->migrated_total += recv_cnt[d];
+            remote_send += send_cnt[d];
+            remote_recv += recv_cnt[d];
         }
     }
-    // planes in batches: stage the remote part of a batch, exchange it, move on
+    c->migrated_total += remote_recv;
+    // every rank must take the same branch: the spare rows are sized from the shard size, so compare
+    // against the worst case over ranks (all bounds are known to everybody)
+    bool fits = true;
+    for (int d = 0; d < R; ++d) {
+        const int64_t dlo = rank_lo(d), dhi = rank_lo(d + 1);
+        const int64_t own = std::max<int64_t>(0, std::min<int64_t>(bnd[2 * d + 1], dhi) - std::max<int64_t>(bnd[2 * d], dlo));
+        const int64_t d_spare = std::max<int64_t>(4096, (dhi - dlo) / 32);
+        if ((dhi - dlo) - own > d_spare) fits = false;
+    }
+    const bool lazy = c->lazy_gather && fits;
+
     std::vector<Plane> planes;
     for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
         for (int32_t k = 0; k < c->cols[ci].width; ++k) planes.push_back(Plane{ci, k});
     const int BATCH = 8;
-    int64_t remote_total = 0;
-    for (int d = 0; d < R; ++d)
-        if (d != r) remote_total += send_cnt[d];
-    if (remote_total > 0 && produced * BATCH > c->send_cap) {
+    // the migrating offspring are the produced slots outside my own range: a prefix [0, pre) (to lower
+    // ranks) and a suffix [suf0, produced) (to higher ranks) of the produced range
+    const int64_t pre = send_off[r] > 0 || send_cnt[r] > 0 ? send_off[r] : produced;
+    const int64_t suf0 = send_cnt[r] > 0 ? send_off[r] + send_cnt[r] : produced;
+    const int64_t n_pre = std::min(pre, produced), n_suf = produced - suf0;
+    if (remote_send * BATCH > c->send_cap) {
         if (c->d_send) CK(c, cudaFree(c->d_send));
         c->d_send = nullptr;
-        c->send_cap = produced * BATCH;
+        c->send_cap = remote_send * BATCH + 4096;
         CK(c, cudaMalloc(&c->d_send, sizeof(double) * (size_t)c->send_cap));
+    }
+    // position of destination d's piece inside one staged plane (prefix pieces first, then suffix pieces)
+    auto stage_pos = [&](int d) { return d < r ? send_off[d] : n_pre + (send_off[d] - suf0); };
+    // where rank q's offspring land on my side: lazily in the spare rows behind the FRONT planes
+    // (lower ranks first), eagerly at their final slots in the BACK planes
+    std::vector<int64_t> spare_pos(R, 0);
+    {
+        int64_t acc = 0;
+        for (int q = 0; q < R; ++q) {
+            if (q == r) continue;
+            spare_pos[q] = acc;
+            acc += recv_cnt[q];
+        }
     }
     for (size_t p0 = 0; p0 < planes.size(); p0 += BATCH) {
         const int nb = (int)std::min<size_t>(BATCH, planes.size() - p0);
-        // (a) offspring that stay on this rank: gather straight into the back buffers
-        if (send_cnt[r] > 0) {
+        if (!lazy && send_cnt[r] > 0) {
+            // offspring that stay: gather straight into the back buffers
             WsGatherParams G;
             memset(&G, 0, sizeof(G));
             G.n = send_cnt[r];
@@ -1239,18 +1302,19 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
             CK(c, ws_launch_gather(G, grid_for(c, G.n, 256, 8), c->stream));
             timed_end(c, te);
         }
-        // (b) offspring that migrate: gather the whole produced range of the batch into the staging
-        //     buffer (slot order), then send each destination its contiguous piece
-        if (remote_total > 0) {
+        // stage the migrating offspring of this batch (slot order)
+        const int64_t seg_start[2] = {0, suf0}, seg_len[2] = {n_pre, n_suf}, seg_dst[2] = {0, n_pre};
+        for (int sgi = 0; sgi < 2; ++sgi) {
+            if (seg_len[sgi] <= 0 || remote_send == 0) continue;
             WsGatherParams G;
             memset(&G, 0, sizeof(G));
-            G.n = produced;
-            G.ancestors = c->d_anc_src;
+            G.n = seg_len[sgi];
+            G.ancestors = c->d_anc_src + seg_start[sgi];
             G.n_planes = nb;
             for (int k = 0; k < nb; ++k) {
                 const Plane pl = planes[p0 + k];
                 G.src[k] = c->cols[pl.col].front[pl.comp];
-                G.dst[k] = c->d_send + (size_t)k * produced;
+                G.dst[k] = c->d_send + (size_t)k * remote_send + seg_dst[sgi];
             }
             timed_begin(c, KC_GATHER, te);
             CK(c, ws_launch_gather(G, grid_for(c, G.n, 256, 8), c->stream));
@@ -1262,12 +1326,31 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
             for (int d = 0; d < R; ++d) {
                 if (d == r) continue;
                 if (send_cnt[d] > 0)
-                    NCK(c, g_nccl.Send(c->d_send + (size_t)k * produced + send_off[d], (size_t)send_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
-                if (recv_cnt[d] > 0)
-                    NCK(c, g_nccl.Recv(c->cols[pl.col].back[pl.comp] + recv_off[d], (size_t)recv_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
+                    NCK(c, g_nccl.Send(c->d_send + (size_t)k * remote_send + stage_pos(d), (size_t)send_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
+                if (recv_cnt[d] > 0) {
+                    double* dst = lazy ? c->cols[pl.col].front[pl.comp] + c->n + spare_pos[d]
+                                       : c->cols[pl.col].back[pl.comp] + recv_off[d];
+                    NCK(c, g_nccl.Recv(dst, (size_t)recv_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
+                }
             }
         }
         NCK(c, g_nccl.GroupEnd());
+    }
+    if (c->phase_n > 6) c->phase_ms[5] += t_now() - t0;  // exchange without the communicator's first-use set-up
+    c->phase_ms[3] += t_now() - t0;
+    t0 = t_now();
+    if (lazy) {
+        // ancestors of my slots: local offspring point at their parent, received offspring at the spare
+        // row they were written to; every plane is now in pre-resample order (+ spare rows) and is
+        // gathered by its next reader, exactly as on one GPU
+        const int64_t self_lo = recv_off[r], self_hi = recv_off[r] + send_cnt[r];
+        CK(c, ws_launch_local_ancestors(c->d_anc, c->n, c->d_anc_src + send_off[r], send_cnt[r] > 0 ? self_lo : c->n,
+                                         send_cnt[r] > 0 ? self_hi : c->n, grid_for(c, c->n, 256, 8), c->stream));
+        c->stats.kernel_launches++;
+        for (auto& col : c->cols)
+            for (auto& stl : col.stale) stl = 1;
+        c->anc_pending = !c->cols.empty();
+        return WS_OK;
     }
     for (auto& col : c->cols) std::swap(col.front, col.back);
     return WS_OK;
@@ -1300,6 +1383,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
             c->cur_u += need;
         }
         if (c->nranks > 1) {
+            TRY(materialize_planes(c));
             TRY(resample_sharded(c, d_ru));
             c->logw_uniform = true;
             c->logw_base = r.log_mean_w;
