@@ -1204,7 +1204,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     if (produced > c->anc_src_cap) {
         if (c->d_anc_src) CK(c, cudaFree(c->d_anc_src));
         c->d_anc_src = nullptr;
-        c->anc_src_cap = produced + produced / 8 + 1024;
+        c->anc_src_cap = produced + produced / 4 + c->spare + 1024;
         CK(c, cudaMalloc(&c->d_anc_src, sizeof(int32_t) * (size_t)c->anc_src_cap));
     }
     // heavy-tile tables are sized for the slots this rank can produce (at most n_global)
@@ -1266,9 +1266,10 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     const int64_t suf0 = send_cnt[r] > 0 ? send_off[r] + send_cnt[r] : produced;
     const int64_t n_pre = std::min(pre, produced), n_suf = produced - suf0;
     if (remote_send * BATCH > c->send_cap) {
+        // grow geometrically (a cudaFree / cudaMalloc pair synchronises the device and costs milliseconds)
         if (c->d_send) CK(c, cudaFree(c->d_send));
         c->d_send = nullptr;
-        c->send_cap = remote_send * BATCH + 4096;
+        c->send_cap = std::max<int64_t>(2 * remote_send * BATCH, 2 * c->spare * BATCH);
         CK(c, cudaMalloc(&c->d_send, sizeof(double) * (size_t)c->send_cap));
     }
     // position of destination d's piece inside one staged plane (prefix pieces first, then suffix pieces)
