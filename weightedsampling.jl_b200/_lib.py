@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwsb200.so")
+LIB_PATH = os.environ.get("WSB200_LIB", os.path.join(_HERE, "lib", "libwsb200.so"))
 
 
 class WsError(RuntimeError):

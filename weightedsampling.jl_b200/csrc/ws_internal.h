@@ -6,10 +6,15 @@
 #include "ws_vm.cuh"
 
 #define WS_VM_BLOCK 128       // threads per CTA of the fused elementwise pass
+#ifndef WS_VM_P
 #define WS_VM_P 4             // particles per thread: one decoded micro-op is applied to all of them
+#endif
+#ifndef WS_VM_MINB
+#define WS_VM_MINB 4          // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB))
+#endif
 #define WS_VM_MAX_IO 24       // planes loaded / stored per fused pass
 #define WS_VM_MAX_OPS 96      // micro-ops per fused pass (program travels in kernel params)
-#define WS_VM_MAX_REGS 48     // register-file rows per pass (48 * 128 * 4 * 8 B = 192 KB of smem)
+#define WS_VM_MAX_REGS ((192 * 1024) / (WS_VM_BLOCK * WS_VM_P * 8))  // register-file rows per pass (<= 192 KB of smem)
 #define WS_SCAN_BLOCK 256
 #define WS_SCAN_ITEMS 8
 #define WS_SCAN_TILE (32 * WS_SCAN_ITEMS)  // particles per warp-granular search tile
