@@ -875,7 +875,18 @@ extern "C" int ws_assign_vec(ws_ctx* c, int32_t col, int32_t d, const ws_expr* r
     if (d != c->cols[col].width) return fail(c, WS_EINVAL, "ws_assign_vec: %d expressions for column %s of width %d", d, c->cols[col].name.c_str(), c->cols[col].width);
     for (int j = 0; j < d; ++j) TRY(check_expr(c, &rhs[j], "ws_assign_vec"));
     if (!c->record_only) {
-        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_assign_vec(p, col, d, rhs); }));
+        bool hazard = false;
+        for (int j = 0; j < d; ++j)
+            for (int i = 0; i < rhs[j].n; ++i)
+                if (rhs[j].toks[i].op == WS_TOK_PLANE && rhs[j].toks[i].col == col && rhs[j].toks[i].comp != j) hazard = true;
+        if (hazard || d <= 8) {
+            TRY(lower_statement(c, [&](Program& p) { wsl::stmt_assign_vec(p, col, d, rhs); }));
+        } else {
+            // wide vectors (theta .= zeros(J)): independent components, lowered one by one so that the
+            // fusion window can be flushed in between
+            for (int j = 0; j < d; ++j)
+                TRY(lower_statement(c, [&](Program& p) { wsl::stmt_assign(p, Plane{col, j}, rhs[j]); }));
+        }
     }
     c->depth++;
     return WS_OK;
