@@ -90,3 +90,60 @@ def test_sharded_equals_single_gpu(world, ess):
         assert abs(o[5] - mx1) <= 1e-9 * (1 + abs(mx1))
         assert o[6] == single.stats()["resamples_done"] and o[6] >= 3
     assert sum(o[7] for o in out) > 0, "some offspring must have crossed the shard boundary"
+
+
+def _worker_schools(rank, world, port, n, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import models
+    import wsb200 as ws
+    st = ws.sharded_state(n, device=rank, seed=5, ess_perc_min=0.5)
+    ws.run(ws.model(models.SCHOOLS)(8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA), st)
+    div = ws.marginal_diversity(st.store, ["μ"])
+    out = (rank, ws.log_evidence(st), ws.E(lambda μ: μ, st), ws.E(lambda τ: τ, st), div, st.stats()["moves_run"],
+           st.stats()["resamples_done"], st["μ"], st["θ"])
+    q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_eight_schools_with_diversity_gated_moves():
+    """BASELINE configs[3] shape: diversity-gated autoRW moves on a sharded state (exact cross-rank distinct
+    count, all-reduced autoRW moments) reproduce the single-GPU run."""
+    world = 2
+    if _ngpu() < world:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import models
+    import wsb200 as ws
+    n = 150_001
+    single = ws.SMCState(n, device=0, seed=5, ess_perc_min=0.5)
+    ws.run(ws.model(models.SCHOOLS)(8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA), single)
+    le1, mu1, tau1 = ws.log_evidence(single), ws.E(lambda μ: μ, single), ws.E(lambda τ: τ, single)
+    div1 = ws.marginal_diversity(single.store, ["μ"])
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_schools, args=(r, world, 29761, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    mus = np.concatenate([o[7] for o in out])
+    th = np.concatenate([o[8] for o in out])
+    differ = int((np.abs(mus - single["μ"]) > 1e-9 * (1 + np.abs(mus))).sum())
+    print(f"eight schools sharded: {differ} of {n} particles differ in mu; diversity {out[0][4]} vs {div1}; "
+          f"moves {out[0][5]} vs {single.stats()['moves_run']}")
+    assert th.shape == (n, 8)
+    for o in out:
+        assert abs(o[1] - le1) < 1e-9 * abs(le1)
+        assert abs(o[2] - mu1) < 1e-3 and abs(o[3] - tau1) < 1e-3
+        assert o[4] == out[0][4]                       # every rank sees the same global diversity
+        assert o[5] == single.stats()["moves_run"] and o[6] == single.stats()["resamples_done"]
+    assert abs(out[0][4] - div1) < 5e-4
+    assert differ < 0.002 * n

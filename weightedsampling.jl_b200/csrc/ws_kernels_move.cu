@@ -216,27 +216,43 @@ __global__ void __launch_bounds__(256) ws_move_moments_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------
 #define WS_SET_EMPTY 0xFFFFFFFFFFFFFFFFull
 
+__device__ __forceinline__ unsigned long long ws_key_of(double v) {
+    return (v != v) ? 0x7FF8000000000000ull : (unsigned long long)__double_as_longlong(v);
+}
+__device__ __forceinline__ unsigned long long ws_key_hash(unsigned long long key) {
+    unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    return h ^ (h >> 29);
+}
+
+// keys_are_bits: the input already holds canonical 64-bit keys (received from other ranks)
+// part_*: when part_base != nullptr every NEW key is also appended to the list of its owner rank
+// (owner = high hash bits mod n_parts), used by the sharded distinct count.
 __global__ void __launch_bounds__(256) ws_unique_count_kernel(const double* __restrict__ plane, int64_t n,
                                                               unsigned long long* __restrict__ table, size_t mask,
-                                                              unsigned long long* __restrict__ counter) {
+                                                              unsigned long long* __restrict__ counter, int keys_are_bits,
+                                                              unsigned long long* __restrict__ part_base, int64_t part_cap,
+                                                              unsigned long long* __restrict__ part_count, int n_parts) {
     unsigned long long fresh = 0ull;
     const int64_t stride = (int64_t)gridDim.x * 256;
+    const unsigned long long* bits = reinterpret_cast<const unsigned long long*>(plane);
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
-        const double v = plane[i];
-        unsigned long long key = (v != v) ? 0x7FF8000000000000ull : (unsigned long long)__double_as_longlong(v);
+        const unsigned long long key = keys_are_bits ? bits[i] : ws_key_of(plane[i]);
         if (i > 0) {
             // resampled copies sit next to each other (ancestors are sorted): skip exact repeats
-            const double pv = plane[i - 1];
-            const unsigned long long pkey = (pv != pv) ? 0x7FF8000000000000ull : (unsigned long long)__double_as_longlong(pv);
+            const unsigned long long pkey = keys_are_bits ? bits[i - 1] : ws_key_of(plane[i - 1]);
             if (pkey == key) continue;
         }
-        unsigned long long h = key * 0x9E3779B97F4A7C15ull;
-        h ^= h >> 29;
+        const unsigned long long h = ws_key_hash(key);
         size_t slot = (size_t)h & mask;
         while (true) {
             const unsigned long long old = atomicCAS(table + slot, WS_SET_EMPTY, key);
             if (old == WS_SET_EMPTY) {
                 ++fresh;
+                if (part_base != nullptr) {
+                    const int owner = (int)((h >> 40) % (unsigned long long)n_parts);
+                    const unsigned long long pos = atomicAdd(part_count + owner, 1ull);
+                    part_base[(size_t)owner * part_cap + pos] = key;
+                }
                 break;
             }
             if (old == key) break;
@@ -280,15 +296,22 @@ cudaError_t ws_launch_move_moments(const WsMoveParams& M, int64_t n, int pass, d
 }
 
 cudaError_t ws_launch_unique_count(const double* plane, int64_t n, unsigned long long* table, size_t slots,
-                                   unsigned long long* counter, int sm_count, cudaStream_t s) {
+                                   unsigned long long* counter, int sm_count, cudaStream_t s, int keys_are_bits,
+                                   unsigned long long* part_base, int64_t part_cap, unsigned long long* part_count,
+                                   int n_parts) {
     cudaError_t e = cudaMemsetAsync(table, 0xFF, sizeof(unsigned long long) * slots, s);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return e;
+    if (part_count != nullptr) {
+        e = cudaMemsetAsync(part_count, 0, sizeof(unsigned long long) * n_parts, s);
+        if (e != cudaSuccess) return e;
+    }
     int64_t g = (n + 255) / 256;
     if (g > (int64_t)sm_count * 8) g = (int64_t)sm_count * 8;
     if (g < 1) g = 1;
-    ws_unique_count_kernel<<<(int)g, 256, 0, s>>>(plane, n, table, slots - 1, counter);
+    ws_unique_count_kernel<<<(int)g, 256, 0, s>>>(plane, n, table, slots - 1, counter, keys_are_bits, part_base, part_cap,
+                                                   part_count, n_parts);
     return cudaGetLastError();
 }
 

@@ -51,4 +51,6 @@ cudaError_t ws_launch_score(const WsScoreParams& S, int sm_count, cudaStream_t s
 cudaError_t ws_launch_move(const WsMoveParams& M, int sm_count, cudaStream_t s);
 cudaError_t ws_launch_move_moments(const WsMoveParams& M, int64_t n, int pass, double* partials, int grid, cudaStream_t s);
 cudaError_t ws_launch_unique_count(const double* plane, int64_t n, unsigned long long* table, size_t slots,
-                                   unsigned long long* counter, int sm_count, cudaStream_t s);
+                                   unsigned long long* counter, int sm_count, cudaStream_t s, int keys_are_bits = 0,
+                                   unsigned long long* part_base = nullptr, int64_t part_cap = 0,
+                                   unsigned long long* part_count = nullptr, int n_parts = 0);

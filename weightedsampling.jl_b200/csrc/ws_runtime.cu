@@ -1887,25 +1887,73 @@ extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t
     TRY(flush_window(c));
     TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
-    if (c->nranks > 1)
-        return fail(c, WS_EUNSUPPORTED, "marginal_diversity on a sharded state needs a cross-rank distinct count (not built yet)");
     double best = INFINITY;
     for (int t = 0; t < n_targets; ++t) {
         TRY(check_plane(c, col[t], comp[t]));
         // open-addressing table with 2N slots (power of two)
         size_t slots = 1;
-        while (slots < (size_t)c->n * 2) slots <<= 1;
-        TRY(ensure_scratch(c, sizeof(unsigned long long) * slots + 64));
+        while (slots < (size_t)std::max<int64_t>(c->n, 1) * 2) slots <<= 1;
+        const int R = c->nranks;
+        // sharded: [table | counter | per-owner counts | per-owner key lists]
+        const size_t part_cap = (R > 1) ? (size_t)c->n : 0;
+        const size_t words = slots + 8 + (size_t)R + (size_t)R * part_cap;
+        TRY(ensure_scratch(c, sizeof(unsigned long long) * words));
         unsigned long long* table = (unsigned long long*)c->d_scratch;
         unsigned long long* counter = table + slots;
+        unsigned long long* part_count = counter + 8;
+        unsigned long long* part_base = part_count + R;
         TimedEvent te;
         timed_begin(c, KC_OTHER, te);
-        CK(c, ws_launch_unique_count(plane_ptr(c, Plane{col[t], comp[t]}), c->n, table, slots, counter, c->sm_count, c->stream));
+        CK(c, ws_launch_unique_count(plane_ptr(c, Plane{col[t], comp[t]}), c->n, table, slots, counter, c->sm_count, c->stream, 0,
+                                     R > 1 ? part_base : nullptr, (int64_t)part_cap, R > 1 ? part_count : nullptr, R));
         timed_end(c, te);
-        unsigned long long h = 0;
-        CK(c, cudaMemcpyAsync(&h, counter, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        CK(c, cudaStreamSynchronize(c->stream));
-        const double frac = (double)h / (double)c->n_global;
+        unsigned long long distinct = 0;
+        if (R == 1) {
+            CK(c, cudaMemcpyAsync(&distinct, counter, sizeof(distinct), cudaMemcpyDeviceToHost, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+        } else {
+            // Exact distinct count over all ranks: every locally-new key goes to the rank that owns its
+            // hash range (all-to-all-v over NVLink), owners count distinct keys, counts are all-reduced.
+            std::vector<unsigned long long> cnt(R), all((size_t)R * R);
+            CK(c, cudaMemcpyAsync(cnt.data(), part_count, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+            unsigned long long* d_cnt = nullptr;
+            TempBuf cntbuf, recvbuf, table2;
+            CK(c, cudaMalloc(&cntbuf.p, sizeof(unsigned long long) * (size_t)R * (R + 1)));
+            d_cnt = (unsigned long long*)cntbuf.p;
+            CK(c, cudaMemcpyAsync(d_cnt + (size_t)R * R, cnt.data(), sizeof(unsigned long long) * R, cudaMemcpyHostToDevice, c->stream));
+            NCK(c, g_nccl.AllGather(d_cnt + (size_t)R * R, d_cnt, (size_t)R, WS_NCCL_UINT64, c->comm, c->stream));
+            CK(c, cudaMemcpyAsync(all.data(), d_cnt, sizeof(unsigned long long) * (size_t)R * R, cudaMemcpyDeviceToHost, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+            size_t n_recv = 0;
+            std::vector<size_t> roff(R);
+            for (int q = 0; q < R; ++q) {
+                roff[q] = n_recv;
+                n_recv += (size_t)all[(size_t)q * R + c->rank];  // what q holds for me
+            }
+            CK(c, cudaMalloc(&recvbuf.p, sizeof(unsigned long long) * std::max<size_t>(n_recv, 1)));
+            unsigned long long* d_recv = (unsigned long long*)recvbuf.p;
+            NCK(c, g_nccl.GroupStart());
+            for (int d = 0; d < R; ++d) {
+                if (cnt[d] > 0) NCK(c, g_nccl.Send(part_base + (size_t)d * part_cap, (size_t)cnt[d], WS_NCCL_UINT64, d, c->comm, c->stream));
+                const size_t rc = (size_t)all[(size_t)d * R + c->rank];
+                if (rc > 0) NCK(c, g_nccl.Recv(d_recv + roff[d], rc, WS_NCCL_UINT64, d, c->comm, c->stream));
+            }
+            NCK(c, g_nccl.GroupEnd());
+            size_t slots2 = 1;
+            while (slots2 < std::max<size_t>(n_recv, 1) * 2) slots2 <<= 1;
+            CK(c, cudaMalloc(&table2.p, sizeof(unsigned long long) * (slots2 + 8)));
+            unsigned long long* t2 = (unsigned long long*)table2.p;
+            CK(c, ws_launch_unique_count((const double*)d_recv, (int64_t)n_recv, t2, slots2, t2 + slots2, c->sm_count, c->stream, 1));
+            c->stats.kernel_launches++;
+            unsigned long long mine = 0;
+            CK(c, cudaMemcpyAsync(&mine, t2 + slots2, sizeof(mine), cudaMemcpyDeviceToHost, c->stream));
+            CK(c, cudaStreamSynchronize(c->stream));
+            double tot = (double)mine;
+            TRY(allreduce_host_doubles(c, &tot, 1));
+            distinct = (unsigned long long)(tot + 0.5);
+        }
+        const double frac = (double)distinct / (double)c->n_global;
         if (frac < best) best = frac;
     }
     *out = best;
