@@ -151,6 +151,113 @@ __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_kernel(const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------
+// Wide tapes (more distinct planes than one register file holds): the move is split into
+//   ws_move_propose_kernel   x' and the log proposal ratio into scratch
+//   ws_move_delta_kernel     one launch per tape SEGMENT: delta += score(segment | x') - score(segment | x)
+//   ws_move_accept_kernel    accept / restore
+// The arithmetic per particle is the same as in ws_move_kernel.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ws_move_propose_kernel(const __grid_constant__ WsMoveParams M, double* __restrict__ x_new,
+                                                              double* __restrict__ lpr_out, double* __restrict__ delta) {
+    const int d = M.d;
+    const int64_t n = M.score.n;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const uint64_t particle = (uint64_t)(M.score.particle_offset + i);
+        double z_old[WS_MOVE_MAX_D], xi[WS_MOVE_MAX_D];
+#pragma unroll
+        for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+            if (t < d) z_old[t] = ws_to_unconstrained(M.target_ptr[t][i], M.lo[t], M.hi[t], M.bound_kind[t]);
+        if (M.rng.replay_n != nullptr) {
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
+                if (t < d) {
+                    const int64_t idx = M.normals_target_major ? (M.replay_n_base + (int64_t)t * M.n_global + (int64_t)particle)
+                                                               : (M.replay_n_base + (int64_t)particle * d + t);
+                    xi[t] = M.rng.replay_n[idx];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; t += 2) {
+                if (t < d) {
+                    double a, b;
+                    ws_randn2(particle, M.stream_normals + (uint64_t)(t >> 1), M.rng.seed, a, b);
+                    xi[t] = a;
+                    if (t + 1 < WS_MOVE_MAX_D) xi[t + 1] = b;
+                }
+            }
+        }
+        double lpr = 0.0;
+#pragma unroll
+        for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
+            if (t < d) {
+                double dl = __dmul_rn(M.L[t * d], xi[0]);
+#pragma unroll
+                for (int k = 1; k < WS_MOVE_MAX_D; ++k)
+                    if (k <= t && k < d) dl = __dadd_rn(dl, __dmul_rn(M.L[t * d + k], xi[k]));
+                const double zn = __dadd_rn(z_old[t], dl);
+                x_new[(size_t)t * n + i] = ws_from_unconstrained(zn, M.lo[t], M.hi[t], M.bound_kind[t]);
+                lpr += ws_log_abs_jacobian(zn, M.lo[t], M.hi[t], M.bound_kind[t]) -
+                       ws_log_abs_jacobian(z_old[t], M.lo[t], M.hi[t], M.bound_kind[t]);
+            }
+        }
+        lpr_out[i] = lpr;
+        delta[i] = 0.0;
+    }
+}
+
+// mode 0: out[i] += fold(segment)                      (score_logpdf)
+// mode 1: out[i] += fold(segment | x_new) - fold(segment | current values)
+__global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_delta_kernel(const __grid_constant__ WsMoveParams M, int mode,
+                                                                      const double* __restrict__ x_new, double* __restrict__ out) {
+    extern __shared__ double ws_score_smem[];
+    double* R = ws_score_smem + threadIdx.x;
+    const WsScoreParams& S = M.score;
+    const int64_t stride = (int64_t)gridDim.x * WS_MOVE_BLOCK;
+    for (int64_t i = (int64_t)blockIdx.x * WS_MOVE_BLOCK + threadIdx.x; i < S.n; i += stride) {
+        const uint64_t particle = (uint64_t)(S.particle_offset + i);
+        ws_score_load_planes(S, R, i);
+        const double s_old = ws_score_fold(S, R, particle);
+        if (mode == 0) {
+            out[i] += s_old;
+        } else {
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+                if (t < M.d && M.target_reg[t] != 0xFF) R[(int)M.target_reg[t] * WS_MOVE_BLOCK] = x_new[(size_t)t * S.n + i];
+            const double s_new = ws_score_fold(S, R, particle);
+            out[i] += s_new - s_old;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) ws_move_accept_kernel(const __grid_constant__ WsMoveParams M, const double* __restrict__ x_new,
+                                                             const double* __restrict__ lpr, const double* __restrict__ delta) {
+    const int64_t n = M.score.n;
+    unsigned long long accepted = 0ull;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+        const uint64_t particle = (uint64_t)(M.score.particle_offset + i);
+        double u;
+        if (M.rng.replay_u != nullptr) {
+            u = M.rng.replay_u[M.replay_u_base + (int64_t)particle];
+        } else {
+            ws_u32x4 r = ws_philox4x32_10(particle, M.stream_uniform, M.rng.seed);
+            u = ws_u01(r.x, r.y);
+        }
+        if (log(u) < lpr[i] + delta[i]) {
+#pragma unroll
+            for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+                if (t < M.d) M.target_ptr[t][i] = x_new[(size_t)t * n + i];
+            ++accepted;
+        }
+    }
+#pragma unroll
+    for (int dlt = 16; dlt > 0; dlt >>= 1) accepted += __shfl_down_sync(0xffffffffu, accepted, dlt);
+    if ((threadIdx.x & 31) == 0 && accepted != 0ull) atomicAdd(M.n_accept, accepted);
+}
+
+// ------------------------------------------------------------------------------------------
 // autoRW moments.  pass 0: [sum w, sum w z_t];  pass 1: [-, -, sum w (z_i - m_i)(z_j - m_j) (j <= i)]
 // Output layout per CTA: n_mom = 1 + d + d(d+1)/2 doubles.
 // ------------------------------------------------------------------------------------------
@@ -290,6 +397,27 @@ cudaError_t ws_launch_move(const WsMoveParams& M, int sm_count, cudaStream_t s) 
     return cudaGetLastError();
 }
 
+cudaError_t ws_launch_move_propose(const WsMoveParams& M, double* x_new, double* lpr, double* delta, int sm_count, cudaStream_t s) {
+    int64_t g = (M.score.n + 255) / 256;
+    if (g > (int64_t)sm_count * 8) g = (int64_t)sm_count * 8;
+    if (g < 1) g = 1;
+    ws_move_propose_kernel<<<(int)g, 256, 0, s>>>(M, x_new, lpr, delta);
+    return cudaGetLastError();
+}
+cudaError_t ws_launch_move_delta(const WsMoveParams& M, int mode, const double* x_new, double* out, int sm_count, cudaStream_t s) {
+    const int smem = M.score.n_regs * WS_MOVE_BLOCK * (int)sizeof(double);
+    ws_move_delta_kernel<<<score_grid(M.score.n_regs, M.score.n, sm_count), WS_MOVE_BLOCK, smem, s>>>(M, mode, x_new, out);
+    return cudaGetLastError();
+}
+cudaError_t ws_launch_move_accept(const WsMoveParams& M, const double* x_new, const double* lpr, const double* delta, int sm_count,
+                                  cudaStream_t s) {
+    int64_t g = (M.score.n + 255) / 256;
+    if (g > (int64_t)sm_count * 8) g = (int64_t)sm_count * 8;
+    if (g < 1) g = 1;
+    ws_move_accept_kernel<<<(int)g, 256, 0, s>>>(M, x_new, lpr, delta);
+    return cudaGetLastError();
+}
+
 cudaError_t ws_launch_move_moments(const WsMoveParams& M, int64_t n, int pass, double* partials, int grid, cudaStream_t s) {
     ws_move_moments_kernel<<<grid, 256, 0, s>>>(M, n, pass, partials);
     return cudaGetLastError();
@@ -318,6 +446,8 @@ cudaError_t ws_launch_unique_count(const double* plane, int64_t n, unsigned long
 cudaError_t ws_move_kernels_init(int device) {
     (void)device;
     cudaError_t e = cudaFuncSetAttribute(ws_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_move_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(ws_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
 }

@@ -49,6 +49,10 @@ struct WsMoveParams {
 cudaError_t ws_move_kernels_init(int device);
 cudaError_t ws_launch_score(const WsScoreParams& S, int sm_count, cudaStream_t s);
 cudaError_t ws_launch_move(const WsMoveParams& M, int sm_count, cudaStream_t s);
+cudaError_t ws_launch_move_propose(const WsMoveParams& M, double* x_new, double* lpr, double* delta, int sm_count, cudaStream_t s);
+cudaError_t ws_launch_move_delta(const WsMoveParams& M, int mode, const double* x_new, double* out, int sm_count, cudaStream_t s);
+cudaError_t ws_launch_move_accept(const WsMoveParams& M, const double* x_new, const double* lpr, const double* delta, int sm_count,
+                                  cudaStream_t s);
 cudaError_t ws_launch_move_moments(const WsMoveParams& M, int64_t n, int pass, double* partials, int grid, cudaStream_t s);
 cudaError_t ws_launch_unique_count(const double* plane, int64_t n, unsigned long long* table, size_t slots,
                                    unsigned long long* counter, int sm_count, cudaStream_t s, int keys_are_bits = 0,

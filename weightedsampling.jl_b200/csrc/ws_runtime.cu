@@ -12,6 +12,8 @@
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
+#include <functional>
+#include <memory>
 #include <map>
 #include <string>
 #include <vector>
@@ -109,6 +111,24 @@ struct TimedEvent {
 struct TapeEntry {
     int64_t depth;   // state.depth before the statement ran (it is scored iff depth < target_depth)
     int32_t op_end;  // score_prog.ops[0 .. op_end) covers the tape up to and including this entry
+    std::function<void(Program&)> lower;  // re-lowers the statement's log-density (owns its expressions)
+    std::vector<Plane> refs;              // planes the log-density reads
+};
+
+// deep copy of caller expressions, so that a tape entry can be lowered again later
+struct OwnedExprs {
+    std::vector<std::vector<ws_tok>> toks;
+    std::vector<ws_expr> ex;
+    explicit OwnedExprs(std::initializer_list<std::pair<const ws_expr*, int>> groups) {
+        for (auto& g : groups)
+            for (int i = 0; i < g.second; ++i) toks.emplace_back(g.first[i].toks, g.first[i].toks + g.first[i].n);
+        for (auto& t : toks) ex.push_back(ws_expr{t.data(), (int32_t)t.size(), 0});
+    }
+    void planes(std::vector<Plane>& out) const {
+        for (auto& t : toks)
+            for (auto& k : t)
+                if (k.op == WS_TOK_PLANE) out.push_back(Plane{k.col, k.comp});
+    }
 };
 
 struct ws_ctx {
@@ -162,8 +182,11 @@ struct ws_ctx {
     std::vector<TapeEntry> tape;
     WsOp* d_score_ops = nullptr;
     size_t d_score_cap = 0, d_score_uploaded = 0;
+    WsOp* d_seg_ops = nullptr;  // micro-ops of the tape segment being folded (wide tapes)
+    size_t d_seg_cap = 0;
     bool record_only = false;
     bool tape_enabled = true;
+    bool score_wide = false;  // the tape reads more planes than one register file holds: fold it in segments
 
     // replay buffers
     double* d_replay_n = nullptr;
@@ -321,6 +344,7 @@ static void reset_score(ws_ctx* c) {
     c->score.max_io = 1 << 30;
     c->tape.clear();
     c->d_score_uploaded = 0;
+    c->score_wide = false;
 }
 
 extern "C" int ws_abi_version(void) { return WSB200_ABI_VERSION; }
@@ -487,6 +511,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_send);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_score_ops);
+    cudaFree(c->d_seg_ops);
     cudaFree(c->d_replay_n);
     cudaFree(c->d_replay_u);
     cudaFree(c->d_replay_e);
@@ -650,20 +675,28 @@ static int lower_statement(ws_ctx* c, F body) {
     return WS_OK;
 }
 
-// Append the log-density of a statement to the score tape (device form of score!).
-template <class F>
-static int tape_statement(ws_ctx* c, F body) {
+// Append the log-density of a statement to the score tape (device form of score!).  `lower` owns copies of
+// the statement's expressions; it is lowered now into the incremental score program and kept so that
+// wide tapes can be re-lowered segment by segment.
+static int tape_statement(ws_ctx* c, std::function<void(Program&)> lower, std::vector<Plane> refs) {
     if (!c->tape_enabled) return WS_OK;
-    body(c->score);
-    if (!c->score.error.empty()) {
-        std::string m = c->score.error;
-        c->score.error.clear();
-        return fail(c, WS_EINVAL, "%s", m.c_str());
+    if (!c->score_wide) {
+        Program snapshot = c->score;
+        lower(c->score);
+        if (!c->score.error.empty()) {
+            std::string m = c->score.error;
+            c->score = snapshot;
+            return fail(c, WS_EINVAL, "%s", m.c_str());
+        }
+        if (c->score.overflow || (int)c->score.loads.size() > WS_SCORE_MAX_LOADS) {
+            // too many distinct planes for one register file: from now on the tape is folded in segments
+            c->score_wide = true;
+            c->score = Program();
+        } else {
+            c->score.end_statement();
+        }
     }
-    if (c->score.overflow)
-        return fail(c, WS_EUNSUPPORTED, "score tape references more than %d distinct planes", WS_SCORE_MAX_REGS - WS_SCORE_TEMPS);
-    c->score.end_statement();
-    c->tape.push_back(TapeEntry{c->depth, (int32_t)c->score.ops.size()});
+    c->tape.push_back(TapeEntry{c->depth, c->score_wide ? 0 : (int32_t)c->score.ops.size(), std::move(lower), std::move(refs)});
     return WS_OK;
 }
 
@@ -902,7 +935,12 @@ extern "C" int ws_sample_normal(ws_ctx* c, int32_t col, int32_t comp, const ws_e
         TRY(lower_statement(c, [&](Program& p) { wsl::stmt_sample_normal(p, rc, Plane{col, comp}, *mu, *sigma); }));
         TRY(check_replay(c));
     }
-    TRY(tape_statement(c, [&](Program& p) { wsl::score_sample_normal(p, Plane{col, comp}, *mu, *sigma); }));
+    {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{mu, 1}, {sigma, 1}});
+        std::vector<Plane> refs{Plane{col, comp}};
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox, col, comp](Program& p) { wsl::score_sample_normal(p, Plane{col, comp}, ox->ex[0], ox->ex[1]); }, refs));
+    }
     c->depth++;
     return WS_OK;
 }
@@ -916,7 +954,12 @@ extern "C" int ws_sample_exponential(ws_ctx* c, int32_t col, int32_t comp, const
         TRY(lower_statement(c, [&](Program& p) { wsl::stmt_sample_exponential(p, rc, Plane{col, comp}, *theta); }));
         TRY(check_replay(c));
     }
-    TRY(tape_statement(c, [&](Program& p) { wsl::score_sample_exponential(p, Plane{col, comp}, *theta); }));
+    {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{theta, 1}});
+        std::vector<Plane> refs{Plane{col, comp}};
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox, col, comp](Program& p) { wsl::score_sample_exponential(p, Plane{col, comp}, ox->ex[0]); }, refs));
+    }
     c->depth++;
     return WS_OK;
 }
@@ -941,7 +984,13 @@ extern "C" int ws_sample_mvnormal(ws_ctx* c, int32_t col, int32_t d, const ws_ex
         TRY(lower_statement(c, [&](Program& p) { wsl::stmt_sample_mvnormal(p, rc, col, d, mu, L); }));
         TRY(check_replay(c));
     }
-    TRY(tape_statement(c, [&](Program& p) { wsl::score_sample_mvnormal(p, col, d, mu, Linv, c0); }));
+    {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{mu, d}});
+        std::vector<Plane> refs;
+        for (int j = 0; j < d; ++j) refs.push_back(Plane{col, j});
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox, col, d, Linv, c0](Program& p) { wsl::score_sample_mvnormal(p, col, d, ox->ex.data(), Linv, c0); }, refs));
+    }
     c->depth++;
     return WS_OK;
 }
@@ -956,7 +1005,12 @@ extern "C" int ws_observe_normal(ws_ctx* c, const ws_expr* obs, const ws_expr* m
         TRY(lower_statement(c, body));
         c->weights_changed = true;
     }
-    TRY(tape_statement(c, body));
+    {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{obs, 1}, {mu, 1}, {sigma, 1}});
+        std::vector<Plane> refs;
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox](Program& p) { wsl::stmt_observe_normal(p, ox->ex[0], ox->ex[1], ox->ex[2]); }, refs));
+    }
     c->depth++;
     return WS_OK;
 }
@@ -970,7 +1024,12 @@ extern "C" int ws_observe_exponential(ws_ctx* c, const ws_expr* obs, const ws_ex
         TRY(lower_statement(c, body));
         c->weights_changed = true;
     }
-    TRY(tape_statement(c, body));
+    {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{obs, 1}, {theta, 1}});
+        std::vector<Plane> refs;
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox](Program& p) { wsl::stmt_observe_exponential(p, ox->ex[0], ox->ex[1]); }, refs));
+    }
     c->depth++;
     return WS_OK;
 }
@@ -989,7 +1048,12 @@ extern "C" int ws_observe_mvnormal(ws_ctx* c, int32_t d, const ws_expr* obs, con
         TRY(lower_statement(c, body));
         c->weights_changed = true;
     }
-    TRY(tape_statement(c, body));
+    {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{obs, d}, {mu, d}});
+        std::vector<Plane> refs;
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox, d, Linv, c0](Program& p) { wsl::stmt_observe_mvnormal(p, d, ox->ex.data(), ox->ex.data() + d, Linv, c0); }, refs));
+    }
     c->depth++;
     return WS_OK;
 }
@@ -1002,7 +1066,12 @@ extern "C" int ws_weight_expr(ws_ctx* c, const ws_expr* term) {
         TRY(lower_statement(c, body));
         c->weights_changed = true;
     }
-    TRY(tape_statement(c, body));
+    {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{term, 1}});
+        std::vector<Plane> refs;
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox](Program& p) { wsl::stmt_weight_expr(p, ox->ex[0]); }, refs));
+    }
     c->depth++;
     return WS_OK;
 }
@@ -1017,9 +1086,9 @@ extern "C" int ws_sample_importance_normal(ws_ctx* c, int32_t col, int32_t comp,
         TRY(check_replay(c));
         c->weights_changed = true;
     }
-    TRY(tape_statement(c, [&](Program& p) {
+    TRY(tape_statement(c, [col, comp, tm, ts](Program& p) {
         p.acc_normal_logpdf(Val::lin(0.0, 1.0, p.reg_for_read(Plane{col, comp})), Val::constant(tm), Val::constant(ts));
-    }));
+    }, std::vector<Plane>{Plane{col, comp}}));
     c->depth++;
     return WS_OK;
 }
@@ -1843,6 +1912,77 @@ static int upload_score_program(ws_ctx* c) {
     return WS_OK;
 }
 
+// Wide tapes: lower the scored prefix of the tape into segments that each fit one register file and hand
+// every segment to `run`.  `only` (may be null) keeps just the entries that read one of those planes:
+// for a move, factors that do not involve a target cancel in s_new - s_old.
+template <class F>
+static int for_each_tape_segment(ws_ctx* c, int64_t target_depth, const std::vector<Plane>* only, F run) {
+    auto fresh = [] {
+        Program p;
+        p.score_mode = true;
+        p.temp_base = 0;
+        p.n_temp_slots = WS_SCORE_TEMPS;
+        p.max_regs = WS_SCORE_MAX_REGS;
+        p.max_ops = 1 << 30;
+        p.max_io = WS_SCORE_MAX_LOADS;
+        return p;
+    };
+    auto launch = [&](Program& seg) -> int {
+        if (seg.ops.empty()) return WS_OK;
+        if (seg.ops.size() > c->d_seg_cap) {
+            if (c->d_seg_ops) {
+                CK(c, cudaStreamSynchronize(c->stream));
+                CK(c, cudaFree(c->d_seg_ops));
+                c->d_seg_ops = nullptr;
+            }
+            c->d_seg_cap = std::max<size_t>(4096, seg.ops.size() * 2);
+            CK(c, cudaMalloc(&c->d_seg_ops, sizeof(WsOp) * c->d_seg_cap));
+        }
+        // the previous segment's kernel may still be reading the buffer: stream order protects it, and the
+        // source vector is pageable (copied before the call returns)
+        CK(c, cudaMemcpyAsync(c->d_seg_ops, seg.ops.data(), sizeof(WsOp) * seg.ops.size(), cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (int64_t)(sizeof(WsOp) * seg.ops.size());
+        return run(seg);
+    };
+    Program seg = fresh();
+    for (auto& e : c->tape) {
+        if (!(e.depth < target_depth)) break;
+        if (only != nullptr) {
+            bool dep = false;
+            for (auto& r : e.refs)
+                for (auto& t : *only)
+                    if (r == t) dep = true;
+            if (!dep) continue;
+        }
+        Program snapshot = seg;
+        e.lower(seg);
+        if (!seg.error.empty()) return fail(c, WS_EINVAL, "%s", seg.error.c_str());
+        if (seg.overflow) {
+            seg = snapshot;
+            TRY(launch(seg));
+            seg = fresh();
+            e.lower(seg);
+            if (seg.overflow) return fail(c, WS_EUNSUPPORTED, "one statement reads more than %d planes", WS_SCORE_MAX_LOADS);
+        }
+        seg.end_statement();
+    }
+    return launch(seg);
+}
+
+static void fill_segment_launch(ws_ctx* c, WsScoreParams& S, Program& seg) {
+    memset(&S, 0, sizeof(S));
+    S.n = c->n;
+    S.particle_offset = c->offset;
+    S.ops = c->d_seg_ops;
+    S.n_ops = (int)seg.ops.size();
+    S.n_regs = std::max(1, seg.high_water);
+    S.n_loads = (int)seg.loads.size();
+    for (int k = 0; k < S.n_loads; ++k) {
+        S.load_ptr[k] = plane_ptr(c, seg.loads[k].first);
+        S.load_reg[k] = (uint8_t)seg.loads[k].second;
+    }
+}
+
 static int fill_score_launch(ws_ctx* c, WsScoreParams& S, int n_ops) {
     memset(&S, 0, sizeof(S));
     S.n = c->n;
@@ -1866,16 +2006,30 @@ extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out
     TRY(flush_window(c));
     TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
-    const int n_ops = score_prefix_ops(c, target_depth);
-    TRY(upload_score_program(c));
     TRY(ensure_scratch(c, sizeof(double) * (size_t)c->n));
-    WsScoreParams S;
-    TRY(fill_score_launch(c, S, n_ops));
-    S.score_out = c->d_scratch;
-    TimedEvent te;
-    timed_begin(c, KC_MOVE, te);
-    CK(c, ws_launch_score(S, c->sm_count, c->stream));
-    timed_end(c, te);
+    if (c->score_wide) {
+        CK(c, cudaMemsetAsync(c->d_scratch, 0, sizeof(double) * (size_t)c->n, c->stream));
+        WsMoveParams M;
+        memset(&M, 0, sizeof(M));
+        TRY(for_each_tape_segment(c, target_depth, nullptr, [&](Program& seg) -> int {
+            fill_segment_launch(c, M.score, seg);
+            TimedEvent te;
+            timed_begin(c, KC_MOVE, te);
+            CK(c, ws_launch_move_delta(M, 0, nullptr, c->d_scratch, c->sm_count, c->stream));
+            timed_end(c, te);
+            return WS_OK;
+        }));
+    } else {
+        const int n_ops = score_prefix_ops(c, target_depth);
+        TRY(upload_score_program(c));
+        WsScoreParams S;
+        TRY(fill_score_launch(c, S, n_ops));
+        S.score_out = c->d_scratch;
+        TimedEvent te;
+        timed_begin(c, KC_MOVE, te);
+        CK(c, ws_launch_score(S, c->sm_count, c->stream));
+        timed_end(c, te);
+    }
     CK(c, cudaMemcpyAsync(host_out, c->d_scratch, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)sizeof(double) * c->n;
@@ -2082,15 +2236,48 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
         if (c->cur_u > c->replay_u_len) return fail(c, WS_EREPLAY, "replay uniforms exhausted in Move");
     }
 
-    const int n_ops = score_prefix_ops(c, target_depth);
-    TRY(upload_score_program(c));
-    TRY(fill_score_launch(c, M.score, n_ops));
     CK(c, cudaMemsetAsync(c->d_counters + 2, 0, sizeof(unsigned long long), c->stream));
     M.n_accept = c->d_counters + 2;
-    TimedEvent te;
-    timed_begin(c, KC_MOVE, te);
-    CK(c, ws_launch_move(M, c->sm_count, c->stream));
-    timed_end(c, te);
+    if (c->score_wide) {
+        // propose -> (delta per tape segment) -> accept
+        TRY(ensure_scratch(c, sizeof(double) * (size_t)c->n * (size_t)(d + 2)));
+        double* x_new = c->d_scratch;
+        double* lpr = x_new + (size_t)d * c->n;
+        double* delta = lpr + c->n;
+        M.score.n = c->n;
+        M.score.particle_offset = c->offset;
+        TimedEvent te;
+        timed_begin(c, KC_MOVE, te);
+        CK(c, ws_launch_move_propose(M, x_new, lpr, delta, c->sm_count, c->stream));
+        timed_end(c, te);
+        std::vector<Plane> targets;
+        for (int t = 0; t < d; ++t) targets.push_back(Plane{spec->col[t], spec->comp[t]});
+        TRY(for_each_tape_segment(c, target_depth, &targets, [&](Program& seg) -> int {
+            fill_segment_launch(c, M.score, seg);
+            for (int t = 0; t < d; ++t) {
+                auto it = seg.plane_reg.find(targets[t]);
+                M.target_reg[t] = (it == seg.plane_reg.end()) ? 0xFF : (uint8_t)it->second;
+            }
+            TimedEvent te2;
+            timed_begin(c, KC_MOVE, te2);
+            CK(c, ws_launch_move_delta(M, 1, x_new, delta, c->sm_count, c->stream));
+            timed_end(c, te2);
+            return WS_OK;
+        }));
+        M.score.n = c->n;
+        M.score.particle_offset = c->offset;
+        timed_begin(c, KC_MOVE, te);
+        CK(c, ws_launch_move_accept(M, x_new, lpr, delta, c->sm_count, c->stream));
+        timed_end(c, te);
+    } else {
+        const int n_ops = score_prefix_ops(c, target_depth);
+        TRY(upload_score_program(c));
+        TRY(fill_score_launch(c, M.score, n_ops));
+        TimedEvent te;
+        timed_begin(c, KC_MOVE, te);
+        CK(c, ws_launch_move(M, c->sm_count, c->stream));
+        timed_end(c, te);
+    }
     c->stats.moves_run++;
     if (info) {
         info->ran = 1;
