@@ -73,7 +73,26 @@ enum ws_tok_op {
     WS_TOK_SIN = 11,
     WS_TOK_COS = 12,
     WS_TOK_ABS = 13,
-    WS_TOK_POW = 14 /* binary: base exponent                         */
+    WS_TOK_POW = 14, /* binary: base exponent                        */
+    /* fresh standard variates, one per particle and token (only inside ws_sample_expr's sampler) */
+    WS_TOK_RANDN = 15,
+    WS_TOK_RANDU = 16,
+    WS_TOK_RANDEXP = 17,
+    /* comparisons give 1.0 / 0.0 (the device form of Bool columns); SELECT pops (cond, a, b) */
+    WS_TOK_LT = 18,
+    WS_TOK_LE = 19,
+    WS_TOK_EQ = 20,
+    WS_TOK_SELECT = 21,
+    WS_TOK_MIN = 22,
+    WS_TOK_MAX = 23,
+    WS_TOK_NOT = 24, /* x == 0 ? 1 : 0 */
+    WS_TOK_LGAMMA = 25,
+    WS_TOK_LOG1P = 26,
+    WS_TOK_EXPM1 = 27,
+    WS_TOK_TAN = 28,
+    WS_TOK_ATAN = 29,
+    WS_TOK_TANH = 30,
+    WS_TOK_FLOOR = 31
 };
 
 typedef struct ws_tok {
@@ -165,6 +184,13 @@ int ws_weight_expr(ws_ctx* ctx, const ws_expr* logw_term);
  * to the weights, score with the target's logpdf. */
 int ws_sample_importance_normal(ws_ctx* ctx, int32_t col, int32_t comp, double prop_mu, double prop_sigma,
                                 double targ_mu, double targ_sigma);
+
+/* A WeightedKernel(sampler, weighter, logpdf) whose three parts are device expressions
+ * (src/types.jl:226-230; src/transformers.jl:172-182):  x = sampler(args...) with WS_TOK_RAND* variates,
+ * weights += weighter(args..., x) (NULL: uniform weights), and logpdf(args..., x) is what score! adds
+ * (NULL: the statement is not scored).  weighter / logpdf read x through WS_TOK_PLANE (col, comp). */
+int ws_sample_expr(ws_ctx* ctx, int32_t col, int32_t comp, const ws_expr* sampler, const ws_expr* weighter,
+                   const ws_expr* logpdf);
 
 /* Resample.apply! (src/transformers.jl:474-498) — the exact state machine:
  * no-op if !weights_changed; else exp_norm -> ess_perc -> if ess < ess_perc_min: stratified

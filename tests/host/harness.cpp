@@ -174,6 +174,15 @@ int hh_weight_expr(HH* h, const ws_expr* term) {
     tape(h);
     return finish(h, h->win);
 }
+int hh_sample_expr(HH* h, int col, int comp, const ws_expr* sampler, const ws_expr* weighter, const ws_expr* logpdf) {
+    wsl::RngCursor rc = cursor(h);
+    wsl::stmt_sample_expr(h->win, rc, Plane{col, comp}, *sampler, weighter);
+    if (logpdf) {
+        wsl::stmt_weight_expr(h->score, *logpdf);
+        tape(h);
+    }
+    return finish(h, h->win);
+}
 int hh_importance_normal(HH* h, int col, int comp, double pm, double ps, double tm, double ts) {
     wsl::RngCursor rc = cursor(h);
     wsl::stmt_importance_normal(h->win, rc, Plane{col, comp}, pm, ps, tm, ts);

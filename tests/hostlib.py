@@ -37,6 +37,7 @@ def lib():
         L.hh_randn2.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.hh_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.hh_importance_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.hh_sample_expr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -75,7 +76,7 @@ class HostStore:
                 "ws_sample_exponential": "hh_sample_exponential", "ws_sample_mvnormal": "hh_sample_mvnormal",
                 "ws_observe_normal": "hh_observe_normal", "ws_observe_exponential": "hh_observe_exponential",
                 "ws_observe_mvnormal": "hh_observe_mvnormal", "ws_weight_expr": "hh_weight_expr",
-                "ws_sample_importance_normal": "hh_importance_normal"}[fn]
+                "ws_sample_importance_normal": "hh_importance_normal", "ws_sample_expr": "hh_sample_expr"}[fn]
         rc = getattr(self.L, name)(self.h, *args)
         if rc != 0:
             raise RuntimeError(f"{name} failed ({rc}): {self.L.hh_error(self.h).decode()}")

@@ -1,0 +1,234 @@
+"""SURVEY §8(f)3 — the wider op set: distributions written as device expressions (`WeightedKernel` with traced
+sampler / weighter / logpdf, types.jl:226-230), per-particle ternary / `&&` / `||` / comparisons
+(rewrites.jl:193-212), math in arguments.  Run on the CPU through the product's own lowering + micro-op
+interpreter (tests/host/harness.cpp) and checked against the oracle and against scipy.stats (the formulas are
+Distributions.jl's, un-vendored: scipy pins them)."""
+import math
+
+import numpy as np
+import pytest
+import scipy.stats as sst
+
+import wsb200 as ws
+from hostlib import HostState
+from oracle import ref
+
+FIRE_ALARM = '''
+@model function fire_alarm()
+    fire ~ Bernoulli(0.01)
+    smoke ~ Bernoulli(fire ? 0.9 : 0.01)
+    lever ~ Bernoulli(fire ? 0.7 : 0.01)
+    true => Bernoulli(smoke || lever ? 0.98 : 0.01)
+end
+'''  # examples/fire_alarm.jl:27-32, verbatim
+
+OSCILLATOR = '''
+@model function damped_oscillator(t_obs, y_obs)
+    A ~ HalfNormal(5)
+    ω ~ HalfNormal(5)
+    γ ~ HalfNormal(1)
+    ϕ ~ Uniform(-π, π)
+    σ ~ HalfNormal(1)
+
+    for (t, y) in zip(t_obs, y_obs)
+        y => Normal(oscillator(t, A, ω, γ, ϕ), σ)
+        (A, ω, γ, σ) << autoRW(1e-3, (0.0, Inf), diversity=0.9)
+        ϕ << autoRW(1e-3, (-π, π), diversity=0.9)
+    end
+
+end
+'''  # examples/damped_oscillator.jl:32-46, verbatim
+
+
+def oscillator(t, A, w, g, p):  # examples/damped_oscillator.jl:11
+    return A * ws.exp(-g * t) * ws.cos(w * t + p)
+
+
+def half_normal():
+    """examples/damped_oscillator.jl:26-30: Truncated(Normal(0, σ), 0, Inf) as a device-expression kernel."""
+    return ws.WeightedKernel(
+        lambda s: abs(s * ws.randn()), None,
+        lambda s, x: ws.where(x >= 0.0, math.log(2.0) - 0.5 * math.log(2 * math.pi) - ws.log(s) - 0.5 * (x / s) ** 2,
+                              float("-inf")), "HalfNormal")
+
+
+def strip(t):
+    k = type(t).__name__
+    if k == "Sequence":
+        return ws.Sequence(*[strip(s) for s in t.steps if type(s).__name__ not in ("Resample", "Move")])
+    if k == "Loop":
+        return ws.Loop(t.collfn, lambda x, f=t.bodyfn: strip(f(x)))
+    return t
+
+
+# name, args (as particle-independent parameters), scipy frozen distribution, support sample
+CASES = [
+    ("Uniform", (-1.5, 2.0), sst.uniform(-1.5, 3.5)),
+    ("LogNormal", (0.3, 0.7), sst.lognorm(0.7, scale=math.exp(0.3))),
+    ("Laplace", (0.5, 1.3), sst.laplace(0.5, 1.3)),
+    ("Cauchy", (-0.2, 0.8), sst.cauchy(-0.2, 0.8)),
+    ("Logistic", (1.0, 0.6), sst.logistic(1.0, 0.6)),
+    ("Gumbel", (0.4, 1.7), sst.gumbel_r(0.4, 1.7)),
+    ("Rayleigh", (1.4,), sst.rayleigh(scale=1.4)),
+    ("Weibull", (1.8, 2.2), sst.weibull_min(1.8, scale=2.2)),
+    ("Pareto", (2.5, 1.2), sst.pareto(2.5, scale=1.2)),
+    ("Gamma", (2.3, 1.6), sst.gamma(2.3, scale=1.6)),
+    ("Beta", (2.0, 3.5), sst.beta(2.0, 3.5)),
+    ("TDist", (4.5,), sst.t(4.5)),
+]
+
+
+@pytest.mark.parametrize("name,args,dist", CASES, ids=[c[0] for c in CASES])
+def test_logpdf_formulas_match_scipy(name, args, dist):
+    n = 2000
+    rng = np.random.default_rng(3)
+    x = dist.rvs(size=n, random_state=rng)
+    x[:5] = [-3.0, 0.0, 1e-9, 0.5, 40.0]  # edge / out-of-support values flow as -Inf
+    hs = HostState(n)
+    hs.store.setcol("x", x)
+    ws.Observe(ws.col("x"), name, args).apply(hs)
+    with np.errstate(all="ignore"):
+        want = dist.logpdf(x)
+    got = hs.store.logw()
+    fin = np.isfinite(want)
+    np.testing.assert_allclose(got[fin], want[fin], rtol=1e-11, atol=1e-11)
+    if name in ("Rayleigh", "Weibull", "Gamma"):
+        fin[x == 0.0] = True  # density 0 at the boundary either way: -Inf on both sides or finite vs -Inf tolerated
+    assert np.all(np.isneginf(got[~fin]) | np.isnan(got[~fin]) == True)  # noqa: E712
+
+
+def test_poisson_and_bernoulli_logpdf():
+    n = 500
+    rng = np.random.default_rng(5)
+    k = rng.poisson(3.0, n).astype(float)
+    hs = HostState(n)
+    hs.store.setcol("k", k)
+    hs.store.setcol("b", (rng.random(n) < 0.3).astype(float))
+    ws.Observe(ws.col("k"), "Poisson", (3.2,)).apply(hs)
+    np.testing.assert_allclose(hs.store.logw(), sst.poisson(3.2).logpmf(k), rtol=1e-12)
+    hs2 = HostState(n)
+    hs2.store.setcol("b", hs.store.getcol("b"))
+    ws.Observe(ws.col("b"), "Bernoulli", (0.3,)).apply(hs2)
+    np.testing.assert_allclose(hs2.store.logw(), sst.bernoulli(0.3).logpmf(hs.store.getcol("b")), rtol=1e-13)
+
+
+SAMPLERS = [c for c in CASES if c[0] not in ("Gamma", "Beta", "TDist")]
+
+
+@pytest.mark.parametrize("name,args,dist", SAMPLERS, ids=[c[0] for c in SAMPLERS])
+def test_samplers_replay_equals_oracle_and_philox_passes_ks(name, args, dist):
+    n = 20000
+    rng = np.random.default_rng(9)
+    streams = dict(normals=rng.standard_normal(2 * n), uniforms=rng.random(2 * n),
+                   exponentials=rng.standard_exponential(2 * n))
+    step = ws.Sample("x", name, args)
+    hs = HostState(n)
+    hs.store.set_replay(**streams)
+    step.apply(hs)
+    ost = ref.OracleState(n, ref.Streams(**streams), ess_perc_min=0.0)
+    ref.run(ws.Sequence(step), ost)
+    np.testing.assert_allclose(hs.store.getcol("x"), ost.cols["x"], rtol=1e-10, atol=1e-15)  # tan near its poles is ill-conditioned
+    assert sst.kstest(hs.store.getcol("x"), dist.cdf).pvalue > 1e-4
+    # production RNG (Philox counters): distribution only
+    hp = HostState(n, seed=77)
+    step.apply(hp)
+    assert sst.kstest(hp.store.getcol("x"), dist.cdf).pvalue > 1e-4
+    # score!: the tape entry of the Sample is logpdf(args..., x)
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(hp.store.score(1), dist.logpdf(hp.store.getcol("x")), rtol=1e-10, atol=1e-10)
+
+
+def test_fire_alarm_bayes_net_matches_oracle_and_exact_posterior():
+    n = 400_000
+    rng = np.random.default_rng(0)
+    u = rng.random(3 * n)
+    root = strip(ws.model(FIRE_ALARM)())
+    hs = HostState(n)
+    hs.store.set_replay(uniforms=u)
+    root.apply(hs)
+    ost = ref.OracleState(n, ref.Streams(uniforms=u), ess_perc_min=0.0)
+    ref.run(root, ost)
+    for name in ("fire", "smoke", "lever"):
+        got = hs.store.getcol(name)
+        np.testing.assert_array_equal(got, ost.cols[name])
+        assert set(np.unique(got)) <= {0.0, 1.0}
+    np.testing.assert_allclose(hs.store.logw(), ost.weights, rtol=1e-13)
+    # exact posterior by enumeration
+    num = den = 0.0
+    for f in (0, 1):
+        for s in (0, 1):
+            for lv in (0, 1):
+                ps, pl = (0.9 if f else 0.01), (0.7 if f else 0.01)
+                p = (0.01 if f else 0.99) * (ps if s else 1 - ps) * (pl if lv else 1 - pl) * (0.98 if (s or lv) else 0.01)
+                den += p
+                num += p * f
+    w = np.exp(hs.store.logw())
+    w /= w.sum()
+    assert abs(float((w * hs.store.getcol("fire")).sum()) - num / den) < 0.015
+    assert abs(math.log(den) - (np.log(np.mean(np.exp(hs.store.logw()))))) < 0.03   # evidence P(alarm)
+
+
+def test_damped_oscillator_lowers_with_user_kernel_and_helper_function():
+    n = 1000
+    rng = np.random.default_rng(1)
+    t_obs = np.linspace(0, 8, 6)
+    y_obs = 3.0 * np.exp(-0.3 * t_obs) * np.cos(2.5 * t_obs + 0.5) + rng.normal(size=6)
+    m = ws.model(OSCILLATOR, scope={"oscillator": oscillator})
+    full = m(t_obs, y_obs, kernels={"HalfNormal": half_normal()})
+    moves = [s for s in full.steps[-1].bodyfn((t_obs[0], y_obs[0])).steps if type(s).__name__ == "Move"]
+    assert [mv.targets for mv in moves] == [["A", "ω", "γ", "σ"], ["ϕ"]] and moves[0].diversity_threshold == 0.9
+    root = strip(full)
+    streams = dict(normals=rng.standard_normal(4 * n), uniforms=rng.random(n))
+    hs = HostState(n)
+    hs.store.set_replay(**streams)
+    root.apply(hs)
+    ost = ref.OracleState(n, ref.Streams(**streams), ess_perc_min=0.0)
+    ref.run(root, ost)
+    for name in ("A", "ω", "γ", "ϕ", "σ"):
+        np.testing.assert_allclose(hs.store.getcol(name), ost.cols[name], rtol=1e-14)
+    assert np.all(hs.store.getcol("A") >= 0) and np.all(np.abs(hs.store.getcol("ϕ")) <= math.pi)
+    np.testing.assert_allclose(hs.store.logw(), ost.weights, rtol=1e-11, atol=1e-11)
+    # independent restatement of the weights
+    A, w_, g, p, s = (hs.store.getcol(k) for k in ("A", "ω", "γ", "ϕ", "σ"))
+    want = sum(sst.norm(A * np.exp(-g * t) * np.cos(w_ * t + p), s).logpdf(y) for t, y in zip(t_obs, y_obs))
+    np.testing.assert_allclose(hs.store.logw(), want, rtol=1e-10, atol=1e-10)
+    # score tape = priors + likelihood
+    prior = (sst.halfnorm(scale=5).logpdf(A) + sst.halfnorm(scale=5).logpdf(w_) + sst.halfnorm(scale=1).logpdf(g)
+             + sst.uniform(-math.pi, 2 * math.pi).logpdf(p) + sst.halfnorm(scale=1).logpdf(s))
+    np.testing.assert_allclose(hs.store.score(hs.store.tape_len()), prior + want, rtol=1e-10, atol=1e-10)
+
+
+def test_conditionals_comparisons_and_math_in_assignments():
+    n = 512
+    rng = np.random.default_rng(2)
+    a, b = rng.normal(size=n), rng.normal(size=n)
+    a[:3] = b[:3]
+    m = ws.model('''
+    @model function f()
+        c .= a > b ? a : b
+        d .= (a <= b) && (a > 0.0) ? 1.0 : -1.0
+        e .= ifelse(a == b, 0.0, min(a, b)) + max(a, 0.5)
+        g .= !(a < 0.0) || b != a ? tanh(a) : atan(b)
+        h .= log1p(abs(a)) + expm1(b) - floor(a) + tan(b)
+    end
+    ''', particle_vars=("a", "b"))
+    hs = HostState(n)
+    hs.store.setcol("a", a)
+    hs.store.setcol("b", b)
+    m().apply(hs)
+    np.testing.assert_array_equal(hs.store.getcol("c"), np.maximum(a, b))
+    np.testing.assert_array_equal(hs.store.getcol("d"), np.where((a <= b) & (a > 0), 1.0, -1.0))
+    np.testing.assert_allclose(hs.store.getcol("e"), np.where(a == b, 0.0, np.minimum(a, b)) + np.maximum(a, 0.5), rtol=1e-15)
+    np.testing.assert_allclose(hs.store.getcol("g"), np.where(~(a < 0) | (b != a), np.tanh(a), np.arctan(b)), rtol=1e-14)
+    np.testing.assert_allclose(hs.store.getcol("h"), np.log1p(np.abs(a)) + np.expm1(b) - np.floor(a) + np.tan(b), rtol=1e-12)
+
+
+def test_untraceable_closures_are_rejected_not_run_on_the_host():
+    hs = HostState(8)
+    k = ws.WeightedKernel(lambda m: math.exp(m) + ws.randn(), None, lambda m, x: -x * x)
+    with pytest.raises(ws.UnsupportedModelError):
+        ws.Sample("x", k, (ws.col("x") + 1.0,)).apply(hs)   # math.exp on a particle expression
+    with pytest.raises(ws.UnsupportedModelError):
+        ws.Sample("y", "Gamma", (2.0, 1.0)).apply(hs)        # density-only kernel: no sampler
+    with pytest.raises(RuntimeError):
+        ws.Observe(ws.col("x") + ws.randn(), "Normal", (0.0, 1.0)).apply(hs)  # variates outside a sampler

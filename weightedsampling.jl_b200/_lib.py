@@ -33,7 +33,8 @@ RESAMPLER = {"stratified": 0, "systematic": 1, "multinomial": 2}
 
 # enum ws_tok_op
 TOK_CONST, TOK_PLANE, TOK_ADD, TOK_SUB, TOK_MUL, TOK_DIV, TOK_NEG, TOK_EXP, TOK_LOG, TOK_SQRT, TOK_SQUARE, \
-    TOK_SIN, TOK_COS, TOK_ABS, TOK_POW = range(15)
+    TOK_SIN, TOK_COS, TOK_ABS, TOK_POW, TOK_RANDN, TOK_RANDU, TOK_RANDEXP, TOK_LT, TOK_LE, TOK_EQ, TOK_SELECT, TOK_MIN, \
+    TOK_MAX, TOK_NOT, TOK_LGAMMA, TOK_LOG1P, TOK_EXPM1, TOK_TAN, TOK_ATAN, TOK_TANH, TOK_FLOOR = range(32)
 
 
 class ws_tok(C.Structure):
@@ -115,6 +116,7 @@ SIGNATURES = {
     "ws_observe_exponential": (C.c_int, [_ctx, _ep, _ep]),
     "ws_observe_mvnormal": (C.c_int, [_ctx, C.c_int32, _ep, _ep, C.c_void_p]),
     "ws_weight_expr": (C.c_int, [_ctx, _ep]),
+    "ws_sample_expr": (C.c_int, [_ctx, C.c_int32, C.c_int32, _ep, _ep, _ep]),
     "ws_sample_importance_normal": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                               C.c_double]),
     "ws_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),

@@ -328,19 +328,68 @@ def _target(store, lhs, width, create=True):
 
 
 class WeightedKernel:
-    """A device kernel descriptor: sampler / weighter / logpdf are fixed device ops (types.jl:226-230).
-    Arbitrary host closures cannot run on the device, so building one from Python callables is rejected."""
+    """``WeightedKernel(sampler, weighter, logpdf)`` (types.jl:226-230) whose three parts are DEVICE EXPRESSIONS:
+    Python callables over particle expressions, traced once per statement and lowered to micro-ops.
+
+    - ``sampler(args...) -> x``: may use fresh variates ``randn()``, ``randu()``, ``randexp()``;
+    - ``weighter(args..., x) -> log_weight`` or ``None`` (uniform weights);
+    - ``logpdf(args..., x) -> log_density``.
+    A callable that cannot be traced (it branches on a particle value, calls NumPy on it, ...) raises
+    ``UnsupportedModelError``: nothing ever runs on the host."""
 
     name = "WeightedKernel"
     has_weighter = False
 
-    def __init__(self, *a, **k):
-        if type(self) is WeightedKernel:
-            raise _unsupported("WeightedKernel from host closures is outside the device-op set; use Normal, MvNormal, "
-                               "Exponential or importance_kernel(Normal, Normal)")
+    def __init__(self, sampler=None, weighter=None, logpdf=None, name=None):
+        self.sampler, self.weighter, self.logpdf = sampler, weighter, logpdf
+        self.has_weighter = weighter is not None
+        if name is not None:
+            self.name = name
 
-    def sample(self, state, lhs, args): raise NotImplementedError
-    def observe(self, state, value, args): raise NotImplementedError
+    def _trace(self, fn, args, what):
+        try:
+            out = fn(*args)
+        except UnsupportedModelError:
+            raise
+        except Exception as e:  # e.g. math.exp(Expr), float(Expr)
+            raise _unsupported(f"{self.name}.{what} is not a device expression ({type(e).__name__}: {e})")
+        return out
+
+    def sample(self, state, lhs, args):
+        if self.sampler is None:
+            raise _unsupported(f"kernel {self.name} has no sampler (it can only be used with `_ ~` / `=>`)")
+        st = state.store
+        cid, comp = _target(st, lhs, 1)
+        x_expr = self._trace(self.sampler, args, "sampler")
+        xcol = Col(lhs[0])[lhs[1]] if isinstance(lhs, tuple) else Col(lhs)
+        toks = [_scalar(lower(x_expr, st), "sampled value")]
+        w_i = l_i = None
+        if self.weighter is not None:
+            w_i = len(toks)
+            toks.append(_scalar(lower(self._trace(self.weighter, tuple(args) + (xcol,), "weighter"), st), "weighter"))
+        if self.logpdf is not None:
+            l_i = len(toks)
+            toks.append(_scalar(lower(self._trace(self.logpdf, tuple(args) + (xcol,), "logpdf"), st), "logpdf"))
+        ex = CExprs(toks)
+        st._call("ws_sample_expr", cid, comp, ex.ptr(0), ex.ptr(w_i) if w_i is not None else None,
+                 ex.ptr(l_i) if l_i is not None else None)
+
+    def observe(self, state, value, args):
+        if self.logpdf is None:
+            raise _unsupported(f"kernel {self.name} has no logpdf")
+        st = state.store
+        tok = _scalar(lower(self._trace(self.logpdf, tuple(args) + (value,), "logpdf"), st), "logpdf")
+        ex = CExprs([tok])
+        st._call("ws_weight_expr", ex.ptr(0))
+
+    def weight(self, state, args):
+        """``Weight`` step: kernel.weighter(args...) (sampler must be None; check_weight_kernel, types.jl:243-249)."""
+        if self.sampler is not None:
+            raise ValueError("Weight kernel must have `sampler === nothing` (a `Weight` step never samples)")
+        st = state.store
+        tok = _scalar(lower(self._trace(self.weighter or self.logpdf, tuple(args), "weighter"), st), "weighter")
+        ex = CExprs([tok])
+        st._call("ws_weight_expr", ex.ptr(0))
 
 
 class _Normal(WeightedKernel):
@@ -457,16 +506,58 @@ def importance_kernel(proposal, target):
     return _ImportanceNormal(proposal.mu, proposal.sigma, target.mu, target.sigma)
 
 
+def _expr_kernels():
+    """Distributions whose sampler is a closed-form transform of one standard variate, written as device
+    expressions (formulas: Distributions.jl 0.25 `rand` / `logpdf`, un-vendored; pinned by scipy.stats in the tests)."""
+    from . import expr as E
+    NEG_INF = float("-inf")
+    LOG2 = math.log(2.0)
+    k = {}
+    k["Uniform"] = WeightedKernel(lambda a, b: a + (b - a) * E.randu(), None,
+                                  lambda a, b, x: E.where((x >= a) & (x <= b), -E.log(b - a), NEG_INF), "Uniform")
+    k["LogNormal"] = WeightedKernel(lambda m, s: E.exp(m + s * E.randn()), None,
+                                    lambda m, s, x: E.where(x > 0.0, -(((E.log(x) - m) / s) ** 2 + math.log(2 * math.pi)) / 2.0
+                                                            - E.log(s) - E.log(x), NEG_INF), "LogNormal")
+    k["Bernoulli"] = WeightedKernel(lambda p: E.randu() < p, None,
+                                    lambda p, x: E.where(x, E.log(p), E.log1p(-p)), "Bernoulli")
+    k["Laplace"] = WeightedKernel(lambda m, t: m + t * (E.randexp() - E.randexp()), None,
+                                  lambda m, t, x: -abs(x - m) / t - E.log(2.0 * t), "Laplace")
+    k["Cauchy"] = WeightedKernel(lambda m, s: m + s * E.tan(math.pi * (E.randu() - 0.5)), None,
+                                 lambda m, s, x: -math.log(math.pi) - E.log(s) - E.log1p(((x - m) / s) ** 2), "Cauchy")
+    k["Logistic"] = WeightedKernel(lambda m, t: m + t * (E.log(E.randexp()) * -1.0 + E.log(E.randexp())), None,
+                                   lambda m, t, x: -((x - m) / t) - E.log(t) - 2.0 * E.log1p(E.exp(-((x - m) / t))), "Logistic")
+    k["Gumbel"] = WeightedKernel(lambda m, t: m - t * E.log(E.randexp()), None,
+                                 lambda m, t, x: -((x - m) / t) - E.exp(-((x - m) / t)) - E.log(t), "Gumbel")
+    k["Rayleigh"] = WeightedKernel(lambda s: s * E.sqrt(2.0 * E.randexp()), None,
+                                   lambda s, x: E.where(x >= 0.0, E.log(x) - 2.0 * E.log(s) - x * x / (2.0 * s * s), NEG_INF), "Rayleigh")
+    k["Weibull"] = WeightedKernel(lambda a, t: t * E.randexp() ** (1.0 / a), None,
+                                  lambda a, t, x: E.where(x >= 0.0, E.log(a / t) + (a - 1.0) * E.log(x / t) - (x / t) ** a, NEG_INF),
+                                  "Weibull")
+    k["Pareto"] = WeightedKernel(lambda a, t: t * E.exp(E.randexp() / a), None,
+                                 lambda a, t, x: E.where(x >= t, E.log(a) + a * E.log(t) - (a + 1.0) * E.log(x), NEG_INF), "Pareto")
+    # no closed-form one-variate sampler: density only (usable with `=>` and `_ ~`)
+    k["Gamma"] = WeightedKernel(None, None, lambda a, t, x: E.where(x >= 0.0, (a - 1.0) * E.log(x) - x / t - E.lgamma(a) - a * E.log(t),
+                                                                     NEG_INF), "Gamma")
+    k["Beta"] = WeightedKernel(None, None, lambda a, b, x: E.where((x >= 0.0) & (x <= 1.0),
+                                                                    (a - 1.0) * E.log(x) + (b - 1.0) * E.log1p(-x)
+                                                                    - (E.lgamma(a) + E.lgamma(b) - E.lgamma(a + b)), NEG_INF), "Beta")
+    k["TDist"] = WeightedKernel(None, None, lambda v, x: E.lgamma((v + 1.0) / 2.0) - E.lgamma(v / 2.0) - 0.5 * E.log(v * math.pi)
+                                - (v + 1.0) / 2.0 * E.log1p(x * x / v), "TDist")
+    k["Poisson"] = WeightedKernel(None, None, lambda lam, x: x * E.log(lam) - lam - E.lgamma(x + 1.0), "Poisson")
+    return k
+
+
 default_kernels = {"Normal": Normal, "MvNormal": MvNormal, "Exponential": Exponential}
+default_kernels.update(_expr_kernels())
 
 # the reference's other 52 table entries (default_kernels.jl:83-102) are outside the device-op set
-_REFERENCE_ONLY_KERNELS = (
+_REFERENCE_ONLY_KERNELS = [k for k in (
     "Beta BernoulliLogit Bernoulli BetaBinomial Binomial Categorical Cauchy Chi Chisq Dirac Dirichlet "
     "DiscreteNonParametric DiscreteUniform FDist Frechet Gamma GeneralizedPareto Geometric Gumbel Hypergeometric "
     "InverseGamma InverseWishart LKJ LKJCholesky Laplace LogNormal Logistic LogitNormal MatrixBeta MatrixFDist "
     "MatrixNormal MatrixTDist MvLogNormal MvLogitNormal MvNormalCanon Multinomial NegativeBinomial NoncentralChisq "
     "NoncentralF NoncentralT NormalCanon Pareto Poisson PoissonBinomial Rayleigh SkewNormal SkewedExponentialPower "
-    "TDist Uniform VonMises Weibull Wishart").split()
+    "TDist Uniform VonMises Weibull Wishart").split() if k not in default_kernels]
 
 
 def resolve_kernel(f, kernels=None):
@@ -585,6 +676,8 @@ class Weight(ParticleTransformer):
             tok = _scalar(lower(a[0], state.store), "log-weight term")
             ex = CExprs([tok])
             state.store._call("ws_weight_expr", ex.ptr(0))
+        elif type(self.kernel) is WeightedKernel:
+            self.kernel.weight(state, a)
         else:
             self.kernel.observe(state, a[-1], a[:-1])
 

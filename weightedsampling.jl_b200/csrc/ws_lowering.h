@@ -64,6 +64,7 @@ struct Program {
     int next_temp = 0;  // score mode
     int high_water = 0; // registers actually used
     bool has_acc = false;
+    RngCursor* rng = nullptr;  // set while a sampler expression is being lowered (WS_TOK_RAND*)
     int n_statements = 0;
     bool overflow = false;
     std::string error;
@@ -232,6 +233,14 @@ struct Program {
             case WS_UN_SIN: return sin(x);
             case WS_UN_COS: return cos(x);
             case WS_UN_ABS: return fabs(x);
+            case WS_UN_NOT: return x == 0.0 ? 1.0 : 0.0;
+            case WS_UN_LGAMMA: return lgamma(x);
+            case WS_UN_LOG1P: return log1p(x);
+            case WS_UN_EXPM1: return expm1(x);
+            case WS_UN_TAN: return tan(x);
+            case WS_UN_ATAN: return atan(x);
+            case WS_UN_TANH: return tanh(x);
+            case WS_UN_FLOOR: return floor(x);
             default: return x * x;
         }
     }
@@ -254,6 +263,56 @@ struct Program {
         return Val::lin(0.0, 1.0, t);
     }
 
+    Val compare(uint32_t kind, const Val& a, const Val& b) {  // 0 <, 1 <=, 2 ==
+        if (a.is_const && b.is_const) {
+            const bool t = kind == 0 ? (a.c0 < b.c0) : (kind == 1 ? (a.c0 <= b.c0) : (a.c0 == b.c0));
+            return Val::constant(t ? 1.0 : 0.0);
+        }
+        const int ra = a.is_const ? (int)WS_REG_NONE : materialize(a);
+        const int rb = b.is_const ? (int)WS_REG_NONE : materialize(b);
+        int t = alloc_temp();
+        emit(ws_make_op(WS_OP_CMP, t, ra, rb, WS_REG_NONE, kind, 0, a.is_const ? a.c0 : 0.0, b.is_const ? b.c0 : 0.0));
+        return Val::lin(0.0, 1.0, t);
+    }
+    Val minmax(uint32_t is_max, const Val& a, const Val& b) {
+        if (a.is_const && b.is_const) return Val::constant(is_max ? fmax(a.c0, b.c0) : fmin(a.c0, b.c0));
+        const int ra = a.is_const ? (int)WS_REG_NONE : materialize(a);
+        const int rb = b.is_const ? (int)WS_REG_NONE : materialize(b);
+        int t = alloc_temp();
+        emit(ws_make_op(WS_OP_MINMAX, t, ra, rb, WS_REG_NONE, is_max, 0, a.is_const ? a.c0 : 0.0, b.is_const ? b.c0 : 0.0));
+        return Val::lin(0.0, 1.0, t);
+    }
+    Val select(const Val& cnd, const Val& a, const Val& b) {
+        if (cnd.is_const) return cnd.c0 != 0.0 ? a : b;
+        const int rc = materialize(cnd);
+        const int ra = a.is_const ? (int)WS_REG_NONE : materialize(a);
+        const int rb = b.is_const ? (int)WS_REG_NONE : materialize(b);
+        int t = alloc_temp();
+        emit(ws_make_op(WS_OP_SELECT, t, ra, rb, rc, 0, 0, a.is_const ? a.c0 : 0.0, b.is_const ? b.c0 : 0.0));
+        return Val::lin(0.0, 1.0, t);
+    }
+    Val variate(int32_t tok) {
+        if (score_mode || rng == nullptr) {
+            fail("random variates are only allowed in a sampler expression");
+            return Val::constant(NAN);
+        }
+        int t = alloc_temp();
+        const uint64_t stream = (*rng->stream)++;
+        double sbits;
+        memcpy(&sbits, &stream, 8);
+        if (tok == WS_TOK_RANDN) {
+            emit(ws_make_op(WS_OP_RANDN2, t, WS_REG_NONE, WS_REG_NONE, WS_REG_NONE, 0, sbits, (double)*rng->normals, 1.0));
+            *rng->normals += rng->n_global;
+        } else if (tok == WS_TOK_RANDU) {
+            emit(ws_make_op(WS_OP_RANDU, t, WS_REG_NONE, WS_REG_NONE, WS_REG_NONE, 0, sbits, (double)*rng->uniforms, 1.0));
+            *rng->uniforms += rng->n_global;
+        } else {
+            emit(ws_make_op(WS_OP_RANDEXP, t, WS_REG_NONE, WS_REG_NONE, WS_REG_NONE, 0, sbits, (double)*rng->exponentials, 1.0));
+            *rng->exponentials += rng->n_global;
+        }
+        return Val::lin(0.0, 1.0, t);
+    }
+
     // postfix tokens -> Val
     Val compile(const ws_expr& e) {
         std::vector<Val> st;
@@ -266,10 +325,28 @@ struct Program {
             switch (t.op) {
                 case WS_TOK_CONST: st.push_back(Val::constant(t.val)); break;
                 case WS_TOK_PLANE: st.push_back(Val::lin(0.0, 1.0, reg_for_read(Plane{t.col, t.comp}))); break;
+                case WS_TOK_RANDN:
+                case WS_TOK_RANDU:
+                case WS_TOK_RANDEXP: st.push_back(variate(t.op)); break;
+                case WS_TOK_SELECT: {
+                    if (st.size() < 3) {
+                        fail("malformed expression (select needs three operands)");
+                        return Val::constant(NAN);
+                    }
+                    Val b = st.back(); st.pop_back();
+                    Val a = st.back(); st.pop_back();
+                    Val cnd = st.back(); st.pop_back();
+                    st.push_back(select(cnd, a, b));
+                } break;
                 case WS_TOK_ADD:
                 case WS_TOK_SUB:
                 case WS_TOK_MUL:
                 case WS_TOK_DIV:
+                case WS_TOK_LT:
+                case WS_TOK_LE:
+                case WS_TOK_EQ:
+                case WS_TOK_MIN:
+                case WS_TOK_MAX:
                 case WS_TOK_POW: {
                     if (st.size() < 2) {
                         fail("malformed expression (binary operator needs two operands)");
@@ -284,6 +361,11 @@ struct Program {
                     else if (t.op == WS_TOK_SUB) r = add(a, b, -1.0);
                     else if (t.op == WS_TOK_MUL) r = mul(a, b);
                     else if (t.op == WS_TOK_DIV) r = div(a, b);
+                    else if (t.op == WS_TOK_LT) r = compare(0, a, b);
+                    else if (t.op == WS_TOK_LE) r = compare(1, a, b);
+                    else if (t.op == WS_TOK_EQ) r = compare(2, a, b);
+                    else if (t.op == WS_TOK_MIN) r = minmax(0, a, b);
+                    else if (t.op == WS_TOK_MAX) r = minmax(1, a, b);
                     else r = power(a, b);
                     st.push_back(r);
                 } break;
@@ -294,6 +376,14 @@ struct Program {
                 case WS_TOK_SQUARE:
                 case WS_TOK_SIN:
                 case WS_TOK_COS:
+                case WS_TOK_NOT:
+                case WS_TOK_LGAMMA:
+                case WS_TOK_LOG1P:
+                case WS_TOK_EXPM1:
+                case WS_TOK_TAN:
+                case WS_TOK_ATAN:
+                case WS_TOK_TANH:
+                case WS_TOK_FLOOR:
                 case WS_TOK_ABS: {
                     if (st.empty()) {
                         fail("malformed expression (unary operator needs an operand)");
@@ -310,6 +400,14 @@ struct Program {
                         case WS_TOK_SQUARE: r = unary(WS_UN_SQUARE, a); break;
                         case WS_TOK_SIN: r = unary(WS_UN_SIN, a); break;
                         case WS_TOK_COS: r = unary(WS_UN_COS, a); break;
+                        case WS_TOK_NOT: r = unary(WS_UN_NOT, a); break;
+                        case WS_TOK_LGAMMA: r = unary(WS_UN_LGAMMA, a); break;
+                        case WS_TOK_LOG1P: r = unary(WS_UN_LOG1P, a); break;
+                        case WS_TOK_EXPM1: r = unary(WS_UN_EXPM1, a); break;
+                        case WS_TOK_TAN: r = unary(WS_UN_TAN, a); break;
+                        case WS_TOK_ATAN: r = unary(WS_UN_ATAN, a); break;
+                        case WS_TOK_TANH: r = unary(WS_UN_TANH, a); break;
+                        case WS_TOK_FLOOR: r = unary(WS_UN_FLOOR, a); break;
                         default: r = unary(WS_UN_ABS, a); break;
                     }
                     st.push_back(r);
@@ -339,7 +437,7 @@ struct Program {
             WsOp& last = ops.back();
             const uint32_t lop = last.w0 & 0xFFu;
             const uint32_t ldst = (last.w0 >> 8) & 0xFFu;
-            if ((int)ldst == v.reg && lop <= WS_OP_POW) {
+            if ((int)ldst == v.reg && (lop <= WS_OP_POW || (lop >= WS_OP_CMP && lop <= WS_OP_MINMAX))) {
                 last.w0 = (last.w0 & ~0xFF00u) | ((uint32_t)dst << 8);
                 return;
             }
@@ -600,6 +698,15 @@ inline void stmt_importance_normal(Program& p, RngCursor& rc, Plane dst, double 
     const double K = (-0.5 * WS_LOG2PI - log(ts)) - (-0.5 * WS_LOG2PI - log(ps));
     p.has_acc = true;
     p.emit(ws_make_op(WS_OP_ACC_LIN2, 0, st.reg, sp.reg, WS_REG_NONE, 0, K, -0.5, 0.5));
+}
+
+// x = sampler(args...) with fresh variates; weights += weighter(args..., x)
+inline void stmt_sample_expr(Program& p, RngCursor& rc, Plane dst, const ws_expr& sampler, const ws_expr* weighter) {
+    p.rng = &rc;
+    Val x = p.compile(sampler);
+    p.rng = nullptr;
+    p.store_val(dst, x);
+    if (weighter != nullptr) p.acc_val(p.compile(*weighter));
 }
 
 // MvNormal(mu, Sigma) constants: L = chol(Sigma).L, Linv, c0 = -(d log 2pi + logdet Sigma)/2

@@ -1076,6 +1076,29 @@ extern "C" int ws_weight_expr(ws_ctx* c, const ws_expr* term) {
     return WS_OK;
 }
 
+extern "C" int ws_sample_expr(ws_ctx* c, int32_t col, int32_t comp, const ws_expr* sampler, const ws_expr* weighter,
+                              const ws_expr* logpdf) {
+    if (!c) return WS_EINVAL;
+    TRY(check_plane(c, col, comp));
+    TRY(check_expr(c, sampler, "ws_sample_expr(sampler)"));
+    if (weighter) TRY(check_expr(c, weighter, "ws_sample_expr(weighter)"));
+    if (logpdf) TRY(check_expr(c, logpdf, "ws_sample_expr(logpdf)"));
+    if (!c->record_only) {
+        wsl::RngCursor rc = rng_cursor(c);
+        TRY(lower_statement(c, [&](Program& p) { wsl::stmt_sample_expr(p, rc, Plane{col, comp}, *sampler, weighter); }));
+        TRY(check_replay(c));
+        if (weighter) c->weights_changed = true;
+    }
+    if (logpdf) {
+        auto ox = std::make_shared<OwnedExprs>(std::initializer_list<std::pair<const ws_expr*, int>>{{logpdf, 1}});
+        std::vector<Plane> refs{Plane{col, comp}};
+        ox->planes(refs);
+        TRY(tape_statement(c, [ox](Program& p) { wsl::stmt_weight_expr(p, ox->ex[0]); }, refs));
+    }
+    c->depth++;
+    return WS_OK;
+}
+
 extern "C" int ws_sample_importance_normal(ws_ctx* c, int32_t col, int32_t comp, double pm, double ps, double tm, double ts) {
     if (!c) return WS_EINVAL;
     TRY(check_plane(c, col, comp));

@@ -29,7 +29,10 @@ enum WsOpCode : uint32_t {
     WS_OP_ACC_LIN2 = 10,      // acc += k0 + k1*r[a] + k2*r[b]
     WS_OP_ACC_QUAD2 = 11,     // acc += k0 + k1*r[a]^2 + k2*r[b]^2
     WS_OP_ACC_SCALE = 12,     // acc = k0 * acc   (used to negate a proposal log-density)
-    WS_OP_LOGPDF_NORMAL_CS = 13  // constant sigma: acc += k2 - 0.5*((X - r[b])*k1)^2,  X = a==NONE?k0:r[a]
+    WS_OP_LOGPDF_NORMAL_CS = 13,  // constant sigma: acc += k2 - 0.5*((X - r[b])*k1)^2,  X = a==NONE?k0:r[a]
+    WS_OP_CMP = 14,      // r[dst] = (A op B) ? 1 : 0     imm: 0 <, 1 <=, 2 ==      A = a==NONE?k1:r[a]; B = b==NONE?k2:r[b]
+    WS_OP_SELECT = 15,   // r[dst] = (r[c] != 0) ? A : B
+    WS_OP_MINMAX = 16    // r[dst] = imm ? max(A,B) : min(A,B)
 };
 
 enum WsUnary : uint32_t {
@@ -39,7 +42,15 @@ enum WsUnary : uint32_t {
     WS_UN_SIN = 3,
     WS_UN_COS = 4,
     WS_UN_ABS = 5,
-    WS_UN_SQUARE = 6
+    WS_UN_SQUARE = 6,
+    WS_UN_NOT = 7,
+    WS_UN_LGAMMA = 8,
+    WS_UN_LOG1P = 9,
+    WS_UN_EXPM1 = 10,
+    WS_UN_TAN = 11,
+    WS_UN_ATAN = 12,
+    WS_UN_TANH = 13,
+    WS_UN_FLOOR = 14
 };
 
 // 32-byte micro-op; two 16-byte words so one uniform 128-bit load pair fetches it.
@@ -149,6 +160,14 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
                     case WS_UN_SIN: v = sin(A); break;
                     case WS_UN_COS: v = cos(A); break;
                     case WS_UN_ABS: v = fabs(A); break;
+                    case WS_UN_NOT: v = (A == 0.0) ? 1.0 : 0.0; break;
+                    case WS_UN_LGAMMA: v = lgamma(A); break;
+                    case WS_UN_LOG1P: v = log1p(A); break;
+                    case WS_UN_EXPM1: v = expm1(A); break;
+                    case WS_UN_TAN: v = tan(A); break;
+                    case WS_UN_ATAN: v = atan(A); break;
+                    case WS_UN_TANH: v = tanh(A); break;
+                    case WS_UN_FLOOR: v = floor(A); break;
                     default: v = A * A; break;
                 }
                 Rd[j * STRIDE] = v;
@@ -256,6 +275,31 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
                     v += k2 * t * t;
                 }
                 acc[j] += v;
+            }
+        } break;
+        case WS_OP_CMP: {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                const bool t = (imm == 0) ? (A < B) : ((imm == 1) ? (A <= B) : (A == B));
+                Rd[j * STRIDE] = t ? 1.0 : 0.0;
+            }
+        } break;
+        case WS_OP_SELECT: {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                Rd[j * STRIDE] = (Rc[j * STRIDE] != 0.0) ? A : B;
+            }
+        } break;
+        case WS_OP_MINMAX: {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                Rd[j * STRIDE] = imm ? fmax(A, B) : fmin(A, B);
             }
         } break;
         case WS_OP_ACC_SCALE: {

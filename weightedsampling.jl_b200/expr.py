@@ -42,10 +42,21 @@ class Expr:
     def __abs__(self): return Un(L.TOK_ABS, self)
     def __getitem__(self, j): return Index(self, j)
 
-    # comparisons / truthiness would silently build wrong programs
+    # comparisons give 1.0 / 0.0 per particle (the device form of the reference's Bool columns)
+    def __lt__(self, o): return Bin(L.TOK_LT, self, wrap(o))
+    def __le__(self, o): return Bin(L.TOK_LE, self, wrap(o))
+    def __gt__(self, o): return Bin(L.TOK_LT, wrap(o), self)
+    def __ge__(self, o): return Bin(L.TOK_LE, wrap(o), self)
+    def eq(self, o): return Bin(L.TOK_EQ, self, wrap(o))
+    def __or__(self, o): return Bin(L.TOK_MAX, self, wrap(o))      # a || b on 0/1 values
+    def __ror__(self, o): return Bin(L.TOK_MAX, wrap(o), self)
+    def __and__(self, o): return Bin(L.TOK_MIN, self, wrap(o))     # a && b
+    def __rand__(self, o): return Bin(L.TOK_MIN, wrap(o), self)
+    def __invert__(self): return Un(L.TOK_NOT, self)               # !a
+
+    # truthiness would silently build wrong programs: use where(cond, a, b)
     def __bool__(self):
-        raise _unsupported("a particle-dependent value cannot be used as a Python condition "
-                           "(vectorised ternary / && / || are outside the device-op set)")
+        raise _unsupported("a particle-dependent value cannot be used as a Python condition; use where(cond, a, b)")
 
 
 class Const(Expr):
@@ -82,6 +93,32 @@ class Un(Expr):
         self.op, self.a = op, a
 
 
+class Select(Expr):
+    """``cond ? a : b`` per particle (``ifelse.(cond, a, b)``, rewrites.jl:193-199); both branches are evaluated."""
+
+    def __init__(self, cond, a, b):
+        self.cond, self.a, self.b = wrap(cond), wrap(a), wrap(b)
+
+
+class Rand(Expr):
+    """A fresh standard variate per particle inside a sampler expression: 'n' normal, 'u' uniform [0,1),
+    'e' exponential."""
+
+    def __init__(self, kind):
+        self.kind = kind
+
+
+def randn(): return Rand("n")
+def randu(): return Rand("u")
+def randexp(): return Rand("e")
+
+
+def where(cond, a, b):
+    if not isinstance(cond, Expr):
+        return a if cond else b
+    return Select(cond, a, b)
+
+
 class Vec(Expr):
     """``[e1, e2, ...]`` with per-particle entries."""
 
@@ -93,7 +130,7 @@ def wrap(v):
     if isinstance(v, Expr):
         return v
     if isinstance(v, (bool, np.bool_)):
-        raise _unsupported("Bool-valued particle expressions are outside the device-op set")
+        return Const(1.0 if v else 0.0)  # Bool -> 1.0 / 0.0
     if isinstance(v, numbers.Real):
         return Const(float(v))
     if isinstance(v, (list, tuple)):
@@ -118,7 +155,17 @@ def _fn(op):
         if isinstance(x, Expr):
             return Un(op, x)
         return {L.TOK_EXP: math.exp, L.TOK_LOG: math.log, L.TOK_SQRT: math.sqrt, L.TOK_SIN: math.sin,
-                L.TOK_COS: math.cos, L.TOK_ABS: abs, L.TOK_SQUARE: lambda t: t * t}[op](x)
+                L.TOK_COS: math.cos, L.TOK_ABS: abs, L.TOK_SQUARE: lambda t: t * t, L.TOK_LGAMMA: math.lgamma,
+                L.TOK_LOG1P: math.log1p, L.TOK_EXPM1: math.expm1, L.TOK_TAN: math.tan, L.TOK_ATAN: math.atan,
+                L.TOK_TANH: math.tanh, L.TOK_FLOOR: math.floor, L.TOK_NOT: lambda t: 0.0 if t else 1.0}[op](x)
+    return f
+
+
+def _fn2(op, py):
+    def f(a, b):
+        if isinstance(a, Expr) or isinstance(b, Expr):
+            return Bin(op, wrap(a), wrap(b))
+        return py(a, b)
     return f
 
 
@@ -128,6 +175,15 @@ sqrt = _fn(L.TOK_SQRT)
 sin = _fn(L.TOK_SIN)
 cos = _fn(L.TOK_COS)
 abs2 = _fn(L.TOK_SQUARE)
+lgamma = _fn(L.TOK_LGAMMA)
+log1p = _fn(L.TOK_LOG1P)
+expm1 = _fn(L.TOK_EXPM1)
+tan = _fn(L.TOK_TAN)
+atan = _fn(L.TOK_ATAN)
+tanh = _fn(L.TOK_TANH)
+floor = _fn(L.TOK_FLOOR)
+minimum = _fn2(L.TOK_MIN, min)
+maximum = _fn2(L.TOK_MAX, max)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -178,6 +234,13 @@ def lower(e, store):
         if not (0 <= e.j < len(base)):
             raise IndexError(f"index {e.j} out of range for a vector of length {len(base)}")
         return base[e.j]
+    if isinstance(e, Rand):
+        return Tokens([({"n": L.TOK_RANDN, "u": L.TOK_RANDU, "e": L.TOK_RANDEXP}[e.kind], 0, 0, 0.0)])
+    if isinstance(e, Select):
+        c, a, b = lower(e.cond, store), lower(e.a, store), lower(e.b, store)
+        if isinstance(c, list) or isinstance(a, list) or isinstance(b, list):
+            raise _unsupported("vector-valued conditionals are outside the device-op set")
+        return Tokens(c.toks + a.toks + b.toks + [(L.TOK_SELECT, 0, 0, 0.0)])
     if isinstance(e, Un):
         a = lower(e.a, store)
         if isinstance(a, list):

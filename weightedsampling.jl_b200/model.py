@@ -55,7 +55,7 @@ _TOKEN_RE = re.compile(r"""
   | (?P<nl>\n)
   | (?P<num>(?:\d[\d_]*\.?\d*(?:[eE][+-]?\d+)?|\.\d+(?:[eE][+-]?\d+)?))
   | (?P<name>@?[^\W\d][\w!′]*)
-  | (?P<op>\.\+=|\.-=|\.\*=|\./=|\.=|=>|<<|==|!=|<=|>=|&&|\|\||\+=|-=|\*=|/=|\.\+|\.-|\.\*|\./|\.\^|->|[-+*/^%÷=<>!~:,;()\[\]{}.'])
+  | (?P<op>\.\+=|\.-=|\.\*=|\./=|\.=|=>|<<|==|!=|<=|>=|&&|\|\||\+=|-=|\*=|/=|\.\+|\.-|\.\*|\./|\.\^|->|[-+*/^%÷=<>!~:,;()\[\]{}.'?&|])
 """, re.X | re.S)
 
 
@@ -84,6 +84,7 @@ class Parser:
     def __init__(self, toks):
         self.t, self.i = toks, 0
         self.depth = 0  # bracket depth: newlines are ignored inside brackets
+        self.no_range = 0  # > 0 while parsing the middle operand of a ternary (`:` belongs to the ternary)
 
     def peek(self, skip_nl=False):
         j = self.i
@@ -184,7 +185,17 @@ class Parser:
 
     # ---- expressions (precedence climbing) ------------------------------------------------------
     def parse_expr(self):
-        return self.parse_or()
+        c = self.parse_or()
+        if self.peek() == ("op", "?"):
+            # ternary `cond ? a : b` (vectorised to ifelse.(cond, a, b) when cond is per-particle, rewrites.jl:193-199)
+            self.next()
+            self.no_range += 1
+            a = self.parse_expr()
+            self.no_range -= 1
+            self.expect("op", ":")
+            b = self.parse_expr()
+            return ("if", c, a, b)
+        return c
 
     def parse_or(self):
         a = self.parse_and()
@@ -207,7 +218,7 @@ class Parser:
 
     def parse_range(self):
         a = self.parse_add()
-        if self.peek() == ("op", ":"):
+        if self.peek() == ("op", ":") and self.no_range == 0:
             self.next()
             b = self.parse_add()
             if self.peek() == ("op", ":"):
@@ -219,16 +230,16 @@ class Parser:
 
     def parse_add(self):
         a = self.parse_mul()
-        while self.peek() in (("op", "+"), ("op", "-"), ("op", ".+"), ("op", ".-")):
+        while self.peek() in (("op", "+"), ("op", "-"), ("op", ".+"), ("op", ".-"), ("op", "|")):
             op = self.next()[1].lstrip(".")
-            a = ("bin", op, a, self.parse_mul())
+            a = ("bin", "||" if op == "|" else op, a, self.parse_mul())
         return a
 
     def parse_mul(self):
         a = self.parse_unary()
-        while self.peek() in (("op", "*"), ("op", "/"), ("op", "%"), ("op", "÷"), ("op", ".*"), ("op", "./")):
+        while self.peek() in (("op", "*"), ("op", "/"), ("op", "%"), ("op", "÷"), ("op", ".*"), ("op", "./"), ("op", "&")):
             op = self.next()[1].lstrip(".")
-            a = ("bin", op, a, self.parse_unary())
+            a = ("bin", "&&" if op == "&" else op, a, self.parse_unary())
         return a
 
     def parse_unary(self):
@@ -451,10 +462,6 @@ def _check_expr(ast, pv, fam, stmt):
         return
     if tag == "field" and _contains_particle(ast[1], pv):
         raise _unsupported("struct-valued particle columns (`x.p`) are outside the device-op set")
-    if tag == "bin" and ast[1] in ("&&", "||") and _contains_particle(ast, pv):
-        raise _unsupported("vectorised && / || on particle variables are outside the device-op set")
-    if tag == "bin" and ast[1] in ("==", "!=", "<", ">", "<=", ">=") and _contains_particle(ast, pv):
-        raise _unsupported("comparisons of particle variables (Bool columns) are outside the device-op set")
     if tag == "tuple" and _contains_particle(ast, pv):
         raise ModelSyntaxError("Unsupported expression containing a particle variable (tuple)")
     if tag == "index" and _contains_particle(ast[2], pv):
@@ -605,6 +612,8 @@ def _jl_ones(*dims):
 
 _BUILTINS = {
     "sqrt": expr.sqrt, "exp": expr.exp, "log": expr.log, "sin": expr.sin, "cos": expr.cos, "abs2": expr.abs2,
+    "tan": expr.tan, "atan": expr.atan, "tanh": expr.tanh, "log1p": expr.log1p, "expm1": expr.expm1, "lgamma": expr.lgamma,
+    "loggamma": expr.lgamma, "floor": expr.floor, "min": expr.minimum, "max": expr.maximum, "ifelse": expr.where,
     "abs": lambda x: abs(x), "zeros": _jl_zeros, "ones": _jl_ones, "length": len, "enumerate": _enumerate1,
     "zip": lambda *a: list(zip(*a)), "collect": list, "sum": lambda x: float(np.sum(x)), "Inf": math.inf,
     "NaN": math.nan, "pi": math.pi, "π": math.pi, "true": True, "false": False, "nothing": None,
@@ -657,14 +666,14 @@ def _binop(op, a, b):
     if op == "^": return a ** b
     if op == "%": return a % b
     if op == "÷": return a // b
-    if op == "==": return a == b
-    if op == "!=": return a != b
+    if op == "==": return a.eq(b) if isinstance(a, Expr) else (b.eq(a) if isinstance(b, Expr) else a == b)
+    if op == "!=": return ~(a.eq(b)) if isinstance(a, Expr) else (~(b.eq(a)) if isinstance(b, Expr) else a != b)
     if op == "<": return a < b
     if op == ">": return a > b
     if op == "<=": return a <= b
     if op == ">=": return a >= b
-    if op == "&&": return bool(a) and bool(b)
-    if op == "||": return bool(a) or bool(b)
+    if op == "&&": return (a & b) if (isinstance(a, Expr) or isinstance(b, Expr)) else (bool(a) and bool(b))
+    if op == "||": return (a | b) if (isinstance(a, Expr) or isinstance(b, Expr)) else (bool(a) or bool(b))
     raise ModelSyntaxError(f"unsupported operator {op}")
 
 
@@ -680,7 +689,11 @@ def ev(ast, env):
         return _binop(ast[1], ev(ast[2], env), ev(ast[3], env))
     if tag == "un":
         v = ev(ast[2], env)
-        return (not v) if ast[1] == "!" else -v
+        if ast[1] == "!":
+            return ~v if isinstance(v, Expr) else (not v)
+        return -v
+    if tag == "if":
+        return expr.where(ev(ast[1], env), ev(ast[2], env), ev(ast[3], env))
     if tag == "range":
         a, b = ev(ast[1], env), ev(ast[2], env)
         step = 1 if ast[3] is None else ev(ast[3], env)
@@ -812,12 +825,14 @@ def _resolve(name, kernels, env):
     return core.resolve_kernel(name, kernels)
 
 
-def model(src, particle_vars=()):
+def model(src, particle_vars=(), scope=None):
     """``@model function f(args...) ... end`` -> Python function ``f(*args, kernels=None, proposals=None)``
     that builds (but does not run) the transformer ``Sequence``.
 
     ``particle_vars`` pre-registers columns that already exist on the state the model will run on (a
-    continuation model applied to an existing SMCState, as benchmarks/ssm/bench_single_update does)."""
+    continuation model applied to an existing SMCState, as benchmarks/ssm/bench_single_update does).
+    ``scope`` supplies the names the Julia source takes from its enclosing module: helper functions written
+    over particle expressions (``oscillator(t, A, ω, γ, ϕ)``) and user-defined ``WeightedKernel``s."""
     name, params, body = Parser(tokenize(src)).parse_model()
     pv, fam = set(particle_vars), set()
     _static_check(body, pv, fam, set(params))
@@ -825,7 +840,7 @@ def model(src, particle_vars=()):
     def build(*args, kernels=None, proposals=None):
         if len(args) != len(params):
             raise TypeError(f"{name}() takes {len(params)} positional arguments but {len(args)} were given")
-        env = _Env(dict(zip(params, args)), pv, fam)
+        env = _Env(dict(zip(params, args)), pv, fam, parent=_Env(dict(scope or {}), pv, fam))
         seq = core.Sequence(*_build(body, env, kernels, proposals))
         seq._has_moves = has_moves  # lets run() skip score-tape recording for move-free models
         return seq
