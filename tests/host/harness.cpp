@@ -7,6 +7,7 @@
 // CPU path.
 #include <stdint.h>
 #include <string.h>
+#include <stdio.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -96,6 +97,26 @@ int hh_flush(HH* h) {
     return 0;
 }
 int hh_n_flush(HH* h) { return h->n_flush; }
+// debugging aid: the queued window as text (op dst a b c imm k0 k1 k2 per line)
+int hh_dump_window(HH* h, char* buf, int cap) {
+    std::string out;
+    char line[256];
+    for (auto& ld : h->win.loads) {
+        snprintf(line, sizeof line, "load  r%d <- col %d comp %d\n", ld.second, ld.first.col, ld.first.comp);
+        out += line;
+    }
+    for (auto& o : h->win.ops) {
+        snprintf(line, sizeof line, "op %2u dst %3u a %3u b %3u c %3u imm %u k0 %.17g k1 %.17g k2 %.17g\n", o.w0 & 0xFFu,
+                 (o.w0 >> 8) & 0xFFu, (o.w0 >> 16) & 0xFFu, (o.w0 >> 24) & 0xFFu, o.w1 & 0xFFu, o.w1 >> 8, o.k0, o.k1, o.k2);
+        out += line;
+    }
+    for (auto& d : h->win.dirty) {
+        snprintf(line, sizeof line, "store col %d comp %d <- r%d\n", d.col, d.comp, h->win.plane_reg[d]);
+        out += line;
+    }
+    snprintf(buf, cap, "%s", out.c_str());
+    return (int)out.size();
+}
 int hh_window_ops(HH* h) { return (int)h->win.ops.size(); }
 int hh_window_regs(HH* h) { return h->win.high_water; }
 int hh_window_loads(HH* h) { return (int)h->win.loads.size(); }
@@ -216,6 +237,13 @@ void hh_philox(uint64_t particle, uint64_t stream, uint64_t seed, uint32_t* out4
     ws_u32x4 r = ws_philox4x32_10(particle, stream, seed);
     out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
 }
+// the custom FP64 routines of ws_math.cuh (host instantiation)
+void hh_exp_nonpos(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ws_exp_nonpos(x[i]); }
+void hh_log_pos(const double* x, const int32_t* kb, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ws_log_pos(x[i], kb[i]); }
+void hh_sqrt_pos(const double* x, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ws_sqrt_pos(x[i]); }
+void hh_div_pos(const double* a, const double* b, double* y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = ws_div_pos(a[i], b[i], 1.0 / b[i]); }
+void hh_sincos_octant(const double* f, double* s, double* c, int64_t n) { for (int64_t i = 0; i < n; ++i) ws_sincos_octant(f[i], s[i], c[i]); }
+void hh_box_muller(const uint64_t* w1, const uint64_t* w2, double* z0, double* z1, int64_t n) { for (int64_t i = 0; i < n; ++i) ws_box_muller(w1[i], w2[i], z0[i], z1[i]); }
 // F(C) for every C in cs against the stratified grid built from r (replay)
 struct RArr {
     const double* r;

@@ -5,7 +5,9 @@
 #include <stdint.h>
 #include "ws_vm.cuh"
 
+#ifndef WS_VM_BLOCK
 #define WS_VM_BLOCK 128       // threads per CTA of the fused elementwise pass
+#endif
 #ifndef WS_VM_P
 #define WS_VM_P 4             // particles per thread: one decoded micro-op is applied to all of them
 #endif
@@ -120,6 +122,6 @@ cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int gr
 cudaError_t ws_launch_local_ancestors(int32_t* anc, int64_t n, const int32_t* anc_self, int64_t self_lo, int64_t self_hi,
                                       int grid, cudaStream_t s);
 cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t n_idx, double* dst, cudaStream_t s);
-int ws_vm_max_grid(int n_regs, int sm_count);
-int ws_vm_smem_bytes(int n_regs);
+int ws_vm_max_grid(int n_regs, int n_loads, int sm_count);
+int ws_vm_smem_bytes(int n_regs, int n_loads);
 cudaError_t ws_kernels_init(int device);

@@ -22,14 +22,38 @@ static int g_sm_count = 148;
 __device__ __forceinline__ void lse_push(WsLse& a, double l) {
     if (l == -INFINITY) return;  // contributes exp(-inf) = 0
     if (l > a.m) {
-        double sc = exp(a.m - l);  // a.m == -inf -> 0
+        double sc = ws_exp_nonpos(a.m - l);  // a.m == -inf -> 0
         a.S = a.S * sc + 1.0;
         a.Q = a.Q * sc * sc + 1.0;
         a.m = l;
     } else {
-        double e = exp(l - a.m);
+        double e = ws_exp_nonpos(l - a.m);
         a.S += e;
         a.Q += e * e;
+    }
+}
+
+// K values at once: raise the running maximum first (one rescale, rarely taken once a thread has seen a
+// few tiles), then K independent exps.  `skip[j]` marks values that do not exist (tail of the last tile).
+template <int K>
+__device__ __forceinline__ void lse_push_many(WsLse& a, const double (&l)[K], const bool (&live)[K]) {
+    double mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < K; ++j)
+        if (live[j]) mx = fmax(mx, l[j]);  // fmax drops NaN here; the NaN still reaches S below
+    if (mx > a.m) {
+        const double sc = ws_exp_nonpos(a.m - mx);  // a.m == -inf -> 0
+        a.S *= sc;
+        a.Q *= sc * sc;
+        a.m = mx;
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+        if (live[j] && l[j] != -INFINITY) {
+            const double e = ws_exp_nonpos(l[j] - a.m);
+            a.S += e;
+            a.Q += e * e;
+        }
     }
 }
 
@@ -38,7 +62,7 @@ __device__ __forceinline__ WsLse lse_combine(const WsLse& a, const WsLse& b) {
     if (a.m == -INFINITY) return b;
     WsLse r;
     r.m = fmax(a.m, b.m);
-    double ea = exp(a.m - r.m), eb = exp(b.m - r.m);
+    double ea = ws_exp_nonpos(a.m - r.m), eb = ws_exp_nonpos(b.m - r.m);
     r.S = a.S * ea + b.S * eb;
     r.Q = a.Q * ea * ea + b.Q * eb * eb;
     return r;
@@ -84,13 +108,28 @@ __device__ __forceinline__ WsLse lse_block_reduce(WsLse v, WsLse* warp_scratch /
 // The register file is a [n_regs][WS_VM_P][WS_VM_BLOCK] array in shared memory: a thread only ever
 // touches its own column, so the pass needs no barrier and shared-memory accesses are conflict-free
 // 64-bit lanes.  Each micro-op is decoded once per thread and applied to its WS_VM_P particles, which
-// amortises the interpreter overhead and gives WS_VM_P independent dependency chains.  Loads are staged
-// through registers in batches so that 4 planes x WS_VM_P particles are in flight per thread.
-__global__ void __launch_bounds__(WS_VM_BLOCK, 4) ws_vm_kernel(const __grid_constant__ WsVmProgram P) {
+// amortises the interpreter overhead and gives WS_VM_P independent dependency chains.
+//
+// STAGED = true (whenever the staging rows fit next to the register file): the plane loads of the NEXT
+// tile are issued as cp.async (LDGSTS, 8 B per particle and plane: the gather through the ancestors is
+// per element, so there is no bulk/TMA shape to use) into [n_loads] staging rows behind the register file
+// while the current tile runs its program, and the ancestors are fetched two tiles ahead.  A thread only
+// reads what it copied itself, so cp.async.wait_group is all the synchronisation there is.  Without this
+// a warp spent a third of its time waiting on ancestor -> plane load chains (profiles/r1_ncu_*_r1e).
+__device__ __forceinline__ void ws_cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void ws_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ws_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <bool STAGED>
+__global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __grid_constant__ WsVmProgram P) {
     extern __shared__ double ws_vm_smem[];
     __shared__ WsLse warp_scratch[WS_VM_BLOCK / 32];
     double* R = ws_vm_smem + threadIdx.x;
     constexpr int RS = WS_VM_P * WS_VM_BLOCK;  // doubles between two registers of the file
+    double* const stage = R + P.n_regs * RS;   // [n_loads][WS_VM_P][WS_VM_BLOCK]   (STAGED only)
 
     WsLse part;
     part.m = -INFINITY;
@@ -105,27 +144,80 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, 4) ws_vm_kernel(const __grid_cons
         red_invS = 1.0 / P.red->S;
     }
 
-    constexpr int64_t TILE = (int64_t)WS_VM_BLOCK * WS_VM_P;
-    const int64_t n_tiles = (P.n + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        int64_t idx[WS_VM_P];   // clamped (always valid) index of the thread's j-th particle
+    // local particle indices fit 32 bits (ws_create: n < 2^31 - 65536), which halves the address arithmetic
+    constexpr int TILE = WS_VM_BLOCK * WS_VM_P;
+    const int n = (int)P.n;
+    const int n_tiles = (n + TILE - 1) / TILE;
+    const bool any_gather = P.load_gather != 0u;
+
+    // clamped index of the thread's j-th particle in a tile (always a valid address)
+    auto tile_index = [&](int tile, int j) -> int {
+        const int i = tile * TILE + (int)threadIdx.x + j * WS_VM_BLOCK;
+        return i < n ? i : n - 1;
+    };
+    // issue the staged loads of `tile` (source rows anc[] for gathered planes)
+    auto issue_stage = [&](int tile, const int (&anc)[WS_VM_P]) {
+        for (int k = 0; k < P.n_loads; ++k) {
+            const bool g = (P.load_gather >> k) & 1u;
+            const double* __restrict__ ptr = P.load_ptr[k];
+            double* dst = stage + k * RS;
+#pragma unroll
+            for (int j = 0; j < WS_VM_P; ++j)
+                ws_cp_async8(dst + j * WS_VM_BLOCK, ptr + (unsigned)(g ? anc[j] : tile_index(tile, j)));
+        }
+        ws_cp_async_commit();
+    };
+
+    int anc_next[WS_VM_P];  // STAGED: ancestors of the tile after the one whose loads are in flight
+    if (STAGED) {
+        const int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+        if (t0 < n_tiles) {
+            int a0[WS_VM_P];
+#pragma unroll
+            for (int j = 0; j < WS_VM_P; ++j) a0[j] = any_gather ? __ldg(P.ancestors + tile_index(t0, j)) : 0;
+            issue_stage(t0, a0);
+        }
+#pragma unroll
+        for (int j = 0; j < WS_VM_P; ++j) anc_next[j] = (any_gather && t1 < n_tiles) ? __ldg(P.ancestors + tile_index(t1, j)) : 0;
+    }
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int idx[WS_VM_P];   // clamped (always valid) index of the thread's j-th particle
         bool live[WS_VM_P];
         uint64_t particle[WS_VM_P];
+        const int first = tile * TILE + (int)threadIdx.x;
 #pragma unroll
         for (int j = 0; j < WS_VM_P; ++j) {
-            const int64_t i = tile * TILE + (int64_t)j * WS_VM_BLOCK + threadIdx.x;
-            live[j] = i < P.n;
-            idx[j] = live[j] ? i : P.n - 1;
-            particle[j] = (uint64_t)(P.particle_offset + idx[j]);
+            const int i = first + j * WS_VM_BLOCK;
+            live[j] = i < n;
+            idx[j] = live[j] ? i : n - 1;
+            particle[j] = (uint64_t)(P.particle_offset + (int64_t)idx[j]);
         }
         // ---- loads ------------------------------------------------------------------------------
-        {
-            int64_t src[WS_VM_P];
+        if (STAGED) {
+            ws_cp_async_wait_all();
+            for (int k = 0; k < P.n_loads; ++k) {
+                const double* srcs = stage + k * RS;
+                double* dst = R + (int)P.load_reg[k] * RS;
+                double t[WS_VM_P];
+#pragma unroll
+                for (int j = 0; j < WS_VM_P; ++j) t[j] = srcs[j * WS_VM_BLOCK];
+#pragma unroll
+                for (int j = 0; j < WS_VM_P; ++j) dst[j * WS_VM_BLOCK] = t[j];
+            }
+            const int tn = tile + gridDim.x, tnn = tn + gridDim.x;
+            if (tn < n_tiles) issue_stage(tn, anc_next);
+            if (any_gather && tnn < n_tiles) {
+#pragma unroll
+                for (int j = 0; j < WS_VM_P; ++j) anc_next[j] = __ldg(P.ancestors + tile_index(tnn, j));
+            }
+        } else {
+            int src[WS_VM_P];
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) src[j] = idx[j];
-            if (P.load_gather != 0u) {
+            if (any_gather) {
 #pragma unroll
-                for (int j = 0; j < WS_VM_P; ++j) src[j] = (int64_t)__ldg(P.ancestors + idx[j]);
+                for (int j = 0; j < WS_VM_P; ++j) src[j] = __ldg(P.ancestors + idx[j]);
             }
             for (int k0 = 0; k0 < P.n_loads; k0 += 4) {
                 double tmp[4][WS_VM_P];
@@ -135,7 +227,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, 4) ws_vm_kernel(const __grid_cons
                         const bool g = (P.load_gather >> (k0 + k)) & 1u;
                         const double* __restrict__ ptr = P.load_ptr[k0 + k];
 #pragma unroll
-                        for (int j = 0; j < WS_VM_P; ++j) tmp[k][j] = __ldg(ptr + (g ? src[j] : idx[j]));
+                        for (int j = 0; j < WS_VM_P; ++j) tmp[k][j] = __ldg(ptr + (unsigned)(g ? src[j] : idx[j]));
                     }
                 }
 #pragma unroll
@@ -153,7 +245,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, 4) ws_vm_kernel(const __grid_cons
         for (int j = 0; j < WS_VM_P; ++j) lw_old[j] = 0.0;
         if (P.logw_mode == 1 || P.n_expect > 0) {
 #pragma unroll
-            for (int j = 0; j < WS_VM_P; ++j) lw_old[j] = P.logw[idx[j]];
+            for (int j = 0; j < WS_VM_P; ++j) lw_old[j] = P.logw[(unsigned)idx[j]];
         }
 
         // ---- program ------------------------------------------------------------------------------
@@ -170,23 +262,22 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, 4) ws_vm_kernel(const __grid_cons
             double* __restrict__ ptr = P.store_ptr[k];
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j)
-                if (live[j]) ptr[idx[j]] = srcr[j * WS_VM_BLOCK];
+                if (live[j]) ptr[(unsigned)idx[j]] = srcr[j * WS_VM_BLOCK];
         }
         if (P.logw_mode != 0) {
+            double lw[WS_VM_P];
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) {
-                if (live[j]) {
-                    const double lw = (P.logw_mode == 1 ? lw_old[j] : P.logw_base) + acc[j];
-                    P.logw[idx[j]] = lw;
-                    lse_push(part, lw);
-                }
+                lw[j] = (P.logw_mode == 1 ? lw_old[j] : P.logw_base) + acc[j];
+                if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
             }
+            lse_push_many<WS_VM_P>(part, lw, live);
         }
         if (P.n_expect > 0) {
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) {
                 if (live[j]) {
-                    const double w = exp(lw_old[j] - red_m) * red_invS;
+                    const double w = ws_exp_nonpos(lw_old[j] - red_m) * red_invS;
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         if (k < P.n_expect) esum[k] += w * R[(int)P.expect_reg[k] * RS + j * WS_VM_BLOCK];
@@ -219,20 +310,28 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, 4) ws_vm_kernel(const __grid_cons
     }
 }
 
-int ws_vm_smem_bytes(int n_regs) { return (n_regs < 1 ? 1 : n_regs) * WS_VM_BLOCK * WS_VM_P * (int)sizeof(double); }
+// rows of the shared-memory register file: n_regs registers (+ n_loads staging rows when they fit)
+static bool ws_vm_staged(int n_regs, int n_loads) {
+    return n_loads > 0 && (size_t)(n_regs + n_loads) * WS_VM_BLOCK * WS_VM_P * sizeof(double) <= (size_t)200 * 1024;
+}
+int ws_vm_smem_bytes(int n_regs, int n_loads) {
+    const int rows = (n_regs < 1 ? 1 : n_regs) + (ws_vm_staged(n_regs < 1 ? 1 : n_regs, n_loads) ? n_loads : 0);
+    return rows * WS_VM_BLOCK * WS_VM_P * (int)sizeof(double);
+}
 
-int ws_vm_max_grid(int n_regs, int sm_count) {
+int ws_vm_max_grid(int n_regs, int n_loads, int sm_count) {
     // resident CTAs per SM limited by the shared-memory register file and 2048 threads / SM
-    const int smem = ws_vm_smem_bytes(n_regs) + 1024;
+    const int smem = ws_vm_smem_bytes(n_regs, n_loads) + 1024;
     int per_sm = (227 * 1024) / smem;
-    if (per_sm > 4) per_sm = 4;  // __launch_bounds__(WS_VM_BLOCK, 4)
+    if (per_sm > WS_VM_MINB) per_sm = WS_VM_MINB;  // __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB)
     if (per_sm < 1) per_sm = 1;
     return per_sm * sm_count;
 }
 
 cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
-    const int smem = ws_vm_smem_bytes(P.n_regs);
-    ws_vm_kernel<<<grid, WS_VM_BLOCK, smem, s>>>(P);
+    const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads);
+    if (ws_vm_staged(P.n_regs, P.n_loads)) ws_vm_kernel<true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
+    else ws_vm_kernel<false><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     return cudaGetLastError();
 }
 
@@ -436,8 +535,9 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __gri
     double m = 0.0, Sden = 1.0;
     if (P.mode == 0) {
         m = P.red->m;
-        Sden = P.red->S;  // divide (not multiply by a reciprocal): w = e / S as exp_norm does
+        Sden = P.red->S;  // w = e / S as exp_norm does (correctly rounded quotient, see ws_div_pos)
     }
+    const double rS = 1.0 / Sden;
     const double uniform_w = 1.0 / (double)P.n_slots;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
@@ -463,7 +563,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __gri
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
                 double w;
                 if (P.mode == 0) {
-                    w = exp(l[k] - m) / Sden;
+                    w = ws_div_pos(ws_exp_nonpos(l[k] - m), Sden, rS);
                 } else {
                     w = (item0 + k < n) ? l[k] : 0.0;
                 }
@@ -503,7 +603,9 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __gri
     }
 }
 
-// exclusive scan of the tile aggregates, in place, by one CTA of 1024 threads (fixed order)
+// exclusive scan of the tile aggregates, in place, by one CTA of 1024 threads (fixed order); every thread
+// takes WS_OFF_ITEMS consecutive words per round so that the loads of a round are all in flight together
+#define WS_OFF_ITEMS 8
 __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
     __shared__ unsigned long long warp_tot[32];
@@ -512,10 +614,15 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
     const int n_tiles = (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE);
     if (threadIdx.x == 0) s_carry = 0ull;
     __syncthreads();
-    for (int base = 0; base < n_tiles; base += 1024) {
-        const int i = base + threadIdx.x;
-        const unsigned long long v = (i < n_tiles) ? P.tile_words[i] : 0ull;
-        unsigned long long incl = v;
+    for (int base = 0; base < n_tiles; base += 1024 * WS_OFF_ITEMS) {
+        const int i0 = base + threadIdx.x * WS_OFF_ITEMS;
+        unsigned long long v[WS_OFF_ITEMS];
+#pragma unroll
+        for (int k = 0; k < WS_OFF_ITEMS; ++k) v[k] = (i0 + k < n_tiles) ? P.tile_words[i0 + k] : 0ull;
+        unsigned long long thread_total = 0ull;
+#pragma unroll
+        for (int k = 0; k < WS_OFF_ITEMS; ++k) thread_total += v[k];
+        unsigned long long incl = thread_total;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -524,13 +631,19 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
         if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
         unsigned long long warp_excl = 0ull, total = 0ull;
+#pragma unroll
         for (int w = 0; w < 32; ++w) {
             const unsigned long long t = warp_tot[w];
             if (w < warp) warp_excl += t;
             total += t;
         }
         const unsigned long long carry = s_carry;
-        if (i < n_tiles) P.tile_words[i] = carry + warp_excl + (incl - v);
+        unsigned long long run = carry + warp_excl + (incl - thread_total);
+#pragma unroll
+        for (int k = 0; k < WS_OFF_ITEMS; ++k) {
+            if (i0 + k < n_tiles) P.tile_words[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
@@ -696,6 +809,29 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __gri
         const unsigned big_mask = __ballot_sync(0xffffffffu, has_big);
 
         // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m, staged per chunk --------------
+        if (fend - fstart <= WS_EXPAND_CHUNK && big_mask == 0u) {
+            // the common case: the whole tile fits one staging window and every family is small
+            int lo = f_prev;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                const int hi = f[k];
+                const int id = item0 + k;
+                int32_t* o = out_s + (lo - fstart);
+                if (hi > lo) {
+                    o[0] = id;
+                    if (hi - lo > 1) {
+                        o[1] = id;
+                        for (int q = 2; q < hi - lo; ++q) o[q] = id;
+                    }
+                }
+                lo = hi;
+            }
+            __syncwarp();
+            int32_t* __restrict__ dst = P.ancestors + (fstart - slot_base);
+            for (int pos = lane; pos < fend - fstart; pos += 32) dst[pos] = out_s[pos];
+            __syncwarp();
+            continue;
+        }
         for (int chunk = fstart; chunk < fend; chunk += WS_EXPAND_CHUNK) {
             const int chunk_end = min(chunk + WS_EXPAND_CHUNK, fend);
             {
@@ -843,8 +979,9 @@ cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStrea
 __global__ void ws_exp_norm_kernel(const double* __restrict__ logw, const WsReduceOut* __restrict__ red,
                                    double* __restrict__ w, int64_t n) {
     const double m = red->m, S = red->S;
+    const double rS = 1.0 / S;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = exp(logw[i] - m) / S;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = ws_div_pos(ws_exp_nonpos(logw[i] - m), S, rS);
 }
 cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,
                                cudaStream_t s) {
@@ -916,6 +1053,8 @@ cudaError_t ws_kernels_init(int device) {
     if (e != cudaSuccess) return e;
     g_sm_count = prop.multiProcessorCount;
     // the register file of the fused pass can take most of the SM's shared memory
-    e = cudaFuncSetAttribute(ws_vm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(ws_vm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_vm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     return e;
 }

@@ -275,9 +275,10 @@ __global__ void __launch_bounds__(256) ws_move_moments_kernel(const __grid_const
         m = M.red->m;
         S = M.red->S;
     }
+    const double rS = 1.0 / S;
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
-        const double w = M.w_uniform ? 1.0 : exp(M.logw[i] - m) / S;
+        const double w = M.w_uniform ? 1.0 : ws_div_pos(ws_exp_nonpos(M.logw[i] - m), S, rS);
         double z[WS_MOVE_MAX_D];
 #pragma unroll
         for (int t = 0; t < WS_MOVE_MAX_D; ++t)

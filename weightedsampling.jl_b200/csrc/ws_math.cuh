@@ -15,6 +15,7 @@
 #pragma once
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define WS_HD __host__ __device__ __forceinline__
@@ -83,21 +84,181 @@ WS_HD double ws_u01_open0(uint32_t hi, uint32_t lo) {
     return (double)v * WS_TWO_M53;
 }
 
+// ---------------------------------------------------------------------------
+// FP64 elementary functions specialised to the arguments this library feeds them.
+// The general-purpose libdevice routines spend half their instructions on special cases and
+// range checks that cannot occur here (profiles/r1_ncu_lines_*: log + sqrt + sincospi + exp were
+// 285 of the 600 instructions per particle of the fused pass).  Coefficients: scripts/fit_math_polys.py
+// (Chebyshev-node interpolation in 60-digit arithmetic); every routine is accurate to ~2 ulp and is
+// checked against mpmath / libm in tests/test_device_math.py through the host instantiation.
+// ---------------------------------------------------------------------------
+WS_HD double ws_bits_to_double(uint64_t b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+#endif
+}
+WS_HD uint64_t ws_double_to_bits(double v) {
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(v);
+#else
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    return b;
+#endif
+}
+WS_HD double ws_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+// ~2^-21-accurate starting values (MUFU.RCP64H / MUFU.RSQ64H on the device)
+WS_HD double ws_rcp_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    return (double)(float)(1.0 / x);
+#endif
+}
+WS_HD double ws_rsqrt_seed(double x) {
+#if defined(__CUDA_ARCH__)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    return (double)(float)(1.0 / sqrt(x));
+#endif
+}
+
+// exp(d) for d <= 0 (log-weight minus its maximum): Cody-Waite reduction, degree-11 polynomial.
+// d < -708 (result below the normal range) and d = -inf give 0; NaN gives NaN.
+WS_HD double ws_exp_nonpos(double d) {
+    const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: fma(d, log2e, MAGIC) holds rint(d*log2e) in its low word
+    const double t = ws_fma(d, 1.4426950408889634, MAGIC);
+    const double kd = t - MAGIC;
+    double r = ws_fma(kd, -6.93147180369123816490e-01, d);   // ln2 hi (32 trailing zero bits)
+    r = ws_fma(kd, -1.90821492927058770002e-10, r);          // ln2 lo
+    double p = 0x1.af631d0059becp-26;
+    p = ws_fma(p, r, 0x1.28b4057f44145p-22);
+    p = ws_fma(p, r, 0x1.71ddf5749d126p-19);
+    p = ws_fma(p, r, 0x1.a01991ac8730ap-16);
+    p = ws_fma(p, r, 0x1.a01a01b14378fp-13);
+    p = ws_fma(p, r, 0x1.6c16c187fbe02p-10);
+    p = ws_fma(p, r, 0x1.111111110f225p-7);
+    p = ws_fma(p, r, 0x1.555555554f0cfp-5);
+    p = ws_fma(p, r, 0x1.555555555555ap-3);
+    p = ws_fma(p, r, 0x1.0000000000011p-1);
+    p = ws_fma(p, r, 1.0);
+    p = ws_fma(p, r, 1.0);
+    const uint64_t k = (uint64_t)(uint32_t)ws_double_to_bits(t);  // low word of t = k as a two's-complement int32
+    const double v = ws_bits_to_double(ws_double_to_bits(p) + (k << 52));
+    return (d > -708.0) ? v : ((d != d) ? d : 0.0);
+}
+
+// a / b for finite a >= 0, b > 0 with rb = RN(1 / b) hoisted by the caller: product, exact residual, one
+// correction (Markstein) — the IEEE quotient without the division subroutine's ~25 instructions.
+WS_HD double ws_div_pos(double a, double b, double rb) {
+    const double q = a * rb;
+    return ws_fma(ws_fma(-q, b, a), rb, q);
+}
+
+// log(x * 2^kbias) for a positive, finite, normal x, without libdevice's special-case paths:
+// x = 2^k z, z in [0.707, 1.414), log z = 2 atanh(s), s = (z-1)/(z+1).  (kbias keeps the result
+// relatively accurate when x * 2^kbias is close to 1, as for a uniform close to 1.)
+WS_HD double ws_log_pos(double x, int kbias = 0) {
+    const uint64_t ix = ws_double_to_bits(x);
+    const uint32_t hi = (uint32_t)(ix >> 32);
+    const uint32_t th = hi - 0x3FE6A09Eu;                   // exponent of x / (sqrt(1/2) .. sqrt(2)) lands in the top bits
+    const int k = (int)th >> 20;
+    const double z = ws_bits_to_double(((uint64_t)(hi - ((uint32_t)k << 20)) << 32) | (ix & 0xFFFFFFFFull));
+    const double f = z - 1.0;                               // exact
+    const double g = z + 1.0;
+    double y = ws_rcp_seed(g);
+    double e = ws_fma(-g, y, 1.0);
+    y = ws_fma(y, e, y);
+    e = ws_fma(-g, y, 1.0);
+    y = ws_fma(y, e, y);                                    // 1/g to ~1 ulp
+    double s = f * y;
+    s = ws_fma(ws_fma(-s, g, f), y, s);                     // f/g correctly rounded (Markstein)
+    const double s2 = s * s;
+    double a = 0x1.2be6c99b32a48p-4;
+    a = ws_fma(a, s2, 0x1.39f2bba043e06p-4);
+    a = ws_fma(a, s2, 0x1.74630f3e18fa7p-4);
+    a = ws_fma(a, s2, 0x1.c71c61a40ddfbp-4);
+    a = ws_fma(a, s2, 0x1.2492492eefe17p-3);
+    a = ws_fma(a, s2, 0x1.99999999949d0p-3);
+    a = ws_fma(a, s2, 0x1.5555555555558p-2);
+    const double kd = (double)(k + kbias);
+    const double s3a = (s * s2) * a;
+    // k ln2 + 2 s + 2 s^3 A(s^2), small terms first
+    const double lo = ws_fma(kd, 1.90821492927058770002e-10, s3a + s3a);
+    return ws_fma(kd, 6.93147180369123816490e-01, (s + s) + lo);
+}
+
+// sqrt(t) for a positive, finite, normal t: MUFU seed, two Newton steps on 1/sqrt, one residual correction.
+WS_HD double ws_sqrt_pos(double t) {
+    double y = ws_rsqrt_seed(t);
+    const double h = 0.5 * t;
+    double e = ws_fma(-(h * y), y, 0.5);
+    y = ws_fma(y, e, y);
+    e = ws_fma(-(h * y), y, 0.5);
+    y = ws_fma(y, e, y);
+    double r = t * y;
+    r = ws_fma(ws_fma(-r, r, t), 0.5 * y, r);
+    return r;
+}
+
+// (sin, cos) of (pi/4) f for f in [0, 1]
+WS_HD void ws_sincos_octant(double f, double& sn, double& cs) {
+    const double f2 = f * f;
+    double p = 0x1.e3f38399551bfp-38;
+    p = ws_fma(p, f2, -0x1.e30071afc3e59p-30);
+    p = ws_fma(p, f2, 0x1.50782fda12d96p-22);
+    p = ws_fma(p, f2, -0x1.32d2cce2e5b19p-15);
+    p = ws_fma(p, f2, 0x1.466bc677587f8p-9);
+    p = ws_fma(p, f2, -0x1.4abbce625be41p-4);
+    p = ws_fma(p, f2, 0x1.921fb54442d18p-1);
+    sn = p * f;
+    double q = -0x1.b264ba152378ap-42;
+    q = ws_fma(q, f2, 0x1.f9cc41140bb60p-34);
+    q = ws_fma(q, f2, -0x1.a6d1ec7906c20p-26);
+    q = ws_fma(q, f2, 0x1.e1f5068355e15p-19);
+    q = ws_fma(q, f2, -0x1.55d3c7e3c90f8p-12);
+    q = ws_fma(q, f2, 0x1.03c1f081b5aacp-6);
+    q = ws_fma(q, f2, -0x1.3bd3cc9be45dep-2);
+    cs = ws_fma(q, f2, 1.0);
+}
+
+// Box-Muller from two 64-bit words:
+//   u1 = (2 k + 1) 2^-53, k = top 52 bits of w1  (open interval: log and sqrt never see 0 or 1)
+//   angle: bits 0..51 of w2 give f in [0,1) (position inside an octant), bits 52..54 pick the octant as
+//   (swap sin/cos, sign of the first, sign of the second) — the eight sign/swap images of the arc
+//   (pi/4) f tile the circle exactly once, so the pair is uniform on the circle.
+WS_HD void ws_box_muller(uint64_t w1, uint64_t w2, double& z0, double& z1) {
+    const double v = ws_bits_to_double(0x4340000000000000ull | (w1 >> 12)) - 9007199254740991.0;  // 2k+1, exact
+    const double t = -2.0 * ws_log_pos(v, -53);  // -2 log u1 in [2^-52, 73.5]
+    const double rad = ws_sqrt_pos(t);
+    const double f = ws_bits_to_double(0x3FF0000000000000ull | (w2 & 0x000FFFFFFFFFFFFFull)) - 1.0;
+    double sn, cs;
+    ws_sincos_octant(f, sn, cs);
+    const bool swap = (w2 >> 52) & 1ull;
+    const double a = swap ? sn : cs, b = swap ? cs : sn;
+    const uint64_t sa = ((w2 >> 53) & 1ull) << 63, sb = ((w2 >> 54) & 1ull) << 63;
+    z0 = ws_bits_to_double(ws_double_to_bits(rad * a) ^ sa);
+    z1 = ws_bits_to_double(ws_double_to_bits(rad * b) ^ sb);
+}
+
 // One Philox block -> two independent standard normals (Box-Muller, FP64).
 WS_HD void ws_randn2(uint64_t particle, uint64_t stream, uint64_t seed, double& z0, double& z1) {
     ws_u32x4 r = ws_philox4x32_10(particle, stream, seed);
-    double u1 = ws_u01_open0(r.x, r.y);
-    double u2 = ws_u01(r.z, r.w);
-    double rad = sqrt(-2.0 * log(u1));
-    double s, c;
-#if defined(__CUDA_ARCH__)
-    sincospi(2.0 * u2, &s, &c);
-#else
-    s = sin(6.283185307179586 * u2);
-    c = cos(6.283185307179586 * u2);
-#endif
-    z0 = rad * c;
-    z1 = rad * s;
+    ws_box_muller(((uint64_t)r.x << 32) | r.y, ((uint64_t)r.z << 32) | r.w, z0, z1);
 }
 
 // One Philox block -> two uniforms in [0,1).
@@ -110,7 +271,8 @@ WS_HD void ws_randu2(uint64_t particle, uint64_t stream, uint64_t seed, double& 
 // Standard exponential variate e = -log(u), u in (0,1].
 WS_HD double ws_randexp(uint64_t particle, uint64_t stream, uint64_t seed) {
     ws_u32x4 r = ws_philox4x32_10(particle, stream, seed);
-    return -log(ws_u01_open0(r.x, r.y));
+    const uint64_t v = ((((uint64_t)r.x << 32) | (uint64_t)r.y) >> 11) + 1ull;  // u = v 2^-53 in (0, 1]
+    return -ws_log_pos((double)v, -53);
 }
 
 // ---------------------------------------------------------------------------

@@ -602,7 +602,7 @@ static int flush_window(ws_ctx* c) {
         P.logw_mode = 0;
     }
     const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
-    const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, c->sm_count), (c->n + vm_tile - 1) / vm_tile);
+    const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, c->sm_count), (c->n + vm_tile - 1) / vm_tile);
     P.partials = w.has_acc ? c->d_partials : nullptr;
     P.n_expect = 0;
     P.rng.seed = c->seed;
@@ -1758,7 +1758,7 @@ extern "C" int ws_expectation(ws_ctx* c, const ws_expr* f, int32_t n_exprs, doub
     for (int k = 0; k < n_exprs; ++k) P.expect_reg[k] = (uint8_t)regs[k];
     P.red = c->d_red;
     const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ws_vm_max_grid(P.n_regs, c->sm_count), (c->n + vm_tile - 1) / vm_tile));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, c->sm_count), (c->n + vm_tile - 1) / vm_tile));
     TRY(ensure_scratch(c, sizeof(double) * (size_t)grid * 8));
     TRY(ensure_h_scratch(c, sizeof(double) * (size_t)grid * 8));
     P.expect_partials = c->d_scratch;
