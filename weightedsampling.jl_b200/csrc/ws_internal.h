@@ -9,10 +9,10 @@
 #define WS_VM_BLOCK 128       // threads per CTA of the fused elementwise pass
 #endif
 #ifndef WS_VM_P
-#define WS_VM_P 4             // particles per thread: one decoded micro-op is applied to all of them
+#define WS_VM_P 3             // particles per thread: one decoded micro-op is applied to all of them
 #endif
 #ifndef WS_VM_MINB
-#define WS_VM_MINB 4          // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB))
+#define WS_VM_MINB 5          // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB))
 #endif
 #define WS_VM_MAX_IO 24       // planes loaded / stored per fused pass
 #define WS_VM_MAX_OPS 96      // micro-ops per fused pass (program travels in kernel params)

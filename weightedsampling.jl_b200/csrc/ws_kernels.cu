@@ -505,6 +505,7 @@ __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double 
 #define WS_DIRECT_MAX 8        // offspring a lane writes itself; larger families are filled by the warp
 #define WS_WARPS_PER_CTA (WS_SCAN_BLOCK / 32)
 #define WS_FXS_FRAC_MASK 0x1FFFFFFFFFFFFFFFull  // 2^61 - 1
+#define WS_RBUF_SLOTS 384      // slot uniforms a warp generates cooperatively per tile (a tile of 256 particles spans ~256 slots)
 
 __device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, int scheme, unsigned long long r0,
                                         uint64_t seed, uint64_t stream) {
@@ -524,6 +525,15 @@ __device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, in
         r = v >> 3;
     }
     return (int)k + (r <= frac ? 1 : 0);
+}
+
+// (k, frac) = divmod(C * n, 2^61), k clipped to n: the slot whose uniform decides F(C), see ws_F_int
+__device__ __forceinline__ void ws_slot_split(unsigned long long C, unsigned int n, unsigned int& k, unsigned long long& frac) {
+    const unsigned long long lo = C * (unsigned long long)n;
+    const unsigned long long hi = __umul64hi(C, (unsigned long long)n);
+    const unsigned long long k64 = (hi << 3) | (lo >> 61);
+    k = (k64 >= (unsigned long long)n) ? n : (unsigned int)k64;
+    frac = lo & WS_FXS_FRAC_MASK;
 }
 
 __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __grid_constant__ WsScanParams P) {
@@ -690,12 +700,19 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
 }
 
 template <bool EXACT_FP>
-__global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __grid_constant__ WsScanParams P) {
+#ifndef WS_SEARCH_MINB
+#define WS_SEARCH_MINB 3
+#endif
+__global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
 
-    __shared__ int32_t out_all[WS_WARPS_PER_CTA][WS_EXPAND_CHUNK];
+    // per-warp window: first the 61-bit slot uniforms of the tile's slot range (Philox mode), then the
+    // staged offspring
+    __shared__ unsigned long long win_all[WS_WARPS_PER_CTA][WS_RBUF_SLOTS];
+    static_assert(WS_RBUF_SLOTS * 8 >= WS_EXPAND_CHUNK * 4, "window too small for the offspring staging");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t* const out_s = out_all[warp];
+    unsigned long long* const rbuf = win_all[warp];
+    int32_t* const out_s = reinterpret_cast<int32_t*>(win_all[warp]);
 
     const int n = (int)P.n;          // local particles
     const int ns = (int)P.n_slots;   // global slots
@@ -745,21 +762,89 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __gri
         // F at the left edge of the particle set is by definition 0 (a slot with u = 0 belongs to
         // particle 1, as in icdf); elsewhere it is the previous particle's F.
         int f[WS_SCAN_ITEMS];
+        int fstart = slot_base;
+        bool coop = false;
+        if (!EXACT_FP && su.scheme == 0) {
+            // Philox-stratified: neighbouring particles ask for neighbouring slots, and one Philox block
+            // serves two slots, so the warp generates the uniforms of the tile's whole slot range once
+            // (half a Philox block per particle instead of one) and every lane looks its slots up.
+            unsigned int kk[WS_SCAN_ITEMS];
+            unsigned long long fr[WS_SCAN_ITEMS];
+            unsigned int kmax = 0u, kmin = 0xFFFFFFFFu;
 #pragma unroll
-        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-            const int gi = item0 + k;
-            int fk;
-            if (gi >= n) {
-                fk = -1;  // patched below
-            } else {
-                if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k]), inv_n, su);
-                else fk = ws_F_int(C[k], (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
-                if (gi == n - 1 && P.last_rank) {
-                    if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
-                    fk = ns;  // leftover slots go to the last particle (the reference would throw BoundsError)
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                ws_slot_split(C[k], (unsigned int)ns, kk[k], fr[k]);
+                if (item0 + k >= n) kk[k] = 0xFFFFFFFFu;  // beyond the shard: patched below
+                if (kk[k] < (unsigned int)ns) {
+                    kmax = max(kmax, kk[k]);
+                    kmin = min(kmin, kk[k]);
                 }
             }
-            f[k] = fk;
+            unsigned int kp = 0u;
+            unsigned long long frp = 0ull;
+            if (lane == 0 && tile != 0) {
+                const int p = tile_base - 1;
+                const unsigned long long Cp = P.cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+                ws_slot_split(Cp, (unsigned int)ns, kp, frp);
+                if (kp < (unsigned int)ns) {
+                    kmax = max(kmax, kp);
+                    kmin = min(kmin, kp);
+                }
+            }
+            kmax = __reduce_max_sync(0xffffffffu, kmax);
+            kmin = __reduce_min_sync(0xffffffffu, kmin);
+            const unsigned int blk0 = kmin >> 1;
+            coop = (kmin == 0xFFFFFFFFu) || ((kmax >> 1) - blk0 < (unsigned int)(WS_RBUF_SLOTS / 2));
+            if (coop) {
+                if (kmin != 0xFFFFFFFFu) {
+                    const unsigned int nblk = (kmax >> 1) - blk0 + 1u;
+                    for (unsigned int b = lane; b < nblk; b += 32u) {
+                        const ws_u32x4 r = ws_philox4x32_10((uint64_t)(blk0 + b), P.stream, P.seed);
+                        rbuf[2u * b] = (((unsigned long long)r.x << 32) | r.y) >> 3;
+                        rbuf[2u * b + 1u] = (((unsigned long long)r.z << 32) | r.w) >> 3;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                    int fk;
+                    if (kk[k] == 0xFFFFFFFFu) fk = -1;
+                    else if (kk[k] >= (unsigned int)ns) fk = ns;
+                    else fk = (int)kk[k] + (rbuf[kk[k] - 2u * blk0] <= fr[k] ? 1 : 0);
+                    if (item0 + k == n - 1 && P.last_rank) {
+                        if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
+                        fk = ns;
+                    }
+                    f[k] = fk;
+                }
+                if (lane == 0 && tile != 0)
+                    fstart = (kp >= (unsigned int)ns) ? ns : (int)kp + (rbuf[kp - 2u * blk0] <= frp ? 1 : 0);
+                __syncwarp();  // the window is reused for the offspring below
+            }
+        }
+        if (!coop) {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                const int gi = item0 + k;
+                int fk;
+                if (gi >= n) {
+                    fk = -1;  // patched below
+                } else {
+                    if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k]), inv_n, su);
+                    else fk = ws_F_int(C[k], (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+                    if (gi == n - 1 && P.last_rank) {
+                        if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
+                        fk = ns;  // leftover slots go to the last particle (the reference would throw BoundsError)
+                    }
+                }
+                f[k] = fk;
+            }
+            if (lane == 0 && tile != 0) {
+                const int p = tile_base - 1;
+                const unsigned long long Cp = P.cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+                if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
+                else fstart = ws_F_int(Cp, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+            }
         }
         // items beyond the shard produce nothing: they repeat the F of the shard's last particle
         {
@@ -767,13 +852,6 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, 3) ws_search_kernel(const __gri
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS; ++k)
                 if (f[k] < 0) f[k] = rank_end;
-        }
-        int fstart = slot_base;
-        if (lane == 0 && tile != 0) {
-            const int p = tile_base - 1;
-            const unsigned long long Cp = P.cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
-            if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
-            else fstart = ws_F_int(Cp, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
         }
         fstart = __shfl_sync(0xffffffffu, fstart, 0);
         int f_prev = __shfl_up_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 1);
