@@ -73,6 +73,20 @@ def synth_obs(T, seed=42):
     return obs
 
 
+def measured_traffic(kernel_prefix, n):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/ncu_traffic.json:
+    dram__bytes_read.sum + dram__bytes_write.sum per particle at N = 2e7), scaled to this run's N."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)["kernels"]
+    for name, k in t.items():
+        if name.startswith(kernel_prefix):
+            return k["bytes_per_particle"] * n
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -283,7 +297,11 @@ def main():
         roofline = {"bound": "hbm", "kernel": {"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",
                                                 "scan_search": "ws_scan_search_kernel"}[dom],
                     "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": per_kernel[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                    "frac": per_kernel[dom]["frac"],
+                    "traffic": measured_traffic({"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",
+                                                 "scan_search": "ws_search_kernel"}[dom], N),
+                    "traffic_source": "profiles/ncu_traffic.json (ncu --set full, bytes per particle at N=2e7) x N",
+                    "peak_source": peak_src,
                     "per_kernel": per_kernel,
                     "whole_step": {"alg_bytes_per_particle": ALG_BYTES_STEP,
                                    "achieved_gbs": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9,

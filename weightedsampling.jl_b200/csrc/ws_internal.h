@@ -76,7 +76,10 @@ struct WsScanParams {
     int32_t pad;
     int64_t n;                 // local particles (this rank's shard)
     int64_t n_slots;           // output slots == GLOBAL particle count (== n on one GPU)
-    unsigned long long cdf_offset;  // fixed-point mass of all lower ranks (0 on one GPU)
+    unsigned long long cdf_offset;  // fixed-point mass of all lower ranks (0 on one GPU) ...
+    const unsigned long long* all_tot;  // ... or, if set, the allgathered per-rank masses: offset = sum of all_tot[0..rank)
+    int32_t rank;
+    int32_t pad2;
     int32_t slot_base;         // global index of the first slot this rank produces; ancestors[slot - slot_base]
     int32_t last_rank;         // the last particle of the last rank takes the clamped slots
     int32_t* bounds;           // [2] ws_bounds_kernel: first / end global slot produced by this rank

@@ -661,6 +661,15 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
     if (threadIdx.x == 0 && P.total != nullptr) *P.total = s_carry;
 }
 
+// fixed-point mass below this rank's shard: given by value, or summed from the allgathered per-rank masses
+// (sharded runs: saves the host a device round trip between the CDF pass and the search)
+__device__ __forceinline__ unsigned long long ws_cdf_offset(const WsScanParams& P) {
+    if (P.all_tot == nullptr) return P.cdf_offset;
+    unsigned long long off = 0ull;
+    for (int q = 0; q < P.rank; ++q) off += P.all_tot[q];
+    return off;
+}
+
 // first / end global slot produced by this rank: F at the rank's left and right CDF edge
 template <bool EXACT_FP>
 __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
@@ -684,7 +693,8 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
             r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
         }
     }
-    const unsigned long long lo = P.cdf_offset, hi = P.cdf_offset + *P.total;
+    const unsigned long long cdf_offset = ws_cdf_offset(P);
+    const unsigned long long lo = cdf_offset, hi = cdf_offset + *P.total;
     int fs, fe;
     if (EXACT_FP) {
         fs = (int)ws_F(P, ws_fxs_to_double(lo), inv_n, su);
@@ -693,7 +703,7 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
         fs = ws_F_int(lo, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
         fe = ws_F_int(hi, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
     }
-    if (P.cdf_offset == 0ull) fs = 0;  // F(C_0) is 0 by definition for the very first particle
+    if (cdf_offset == 0ull) fs = 0;  // F(C_0) is 0 by definition for the very first particle
     if (P.last_rank) fe = ns;
     P.bounds[0] = fs;
     P.bounds[1] = fe;
@@ -714,6 +724,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
     unsigned long long* const rbuf = win_all[warp];
     int32_t* const out_s = reinterpret_cast<int32_t*>(win_all[warp]);
 
+    const unsigned long long cdf_offset = ws_cdf_offset(P);
     const int n = (int)P.n;          // local particles
     const int ns = (int)P.n_slots;   // global slots
     const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
@@ -741,7 +752,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
     for (int tile = blockIdx.x * WS_WARPS_PER_CTA + warp; tile < n_tiles; tile += warps_total) {
         const int tile_base = tile * WS_SCAN_TILE;
         const int item0 = tile_base + lane * WS_SCAN_ITEMS;
-        const unsigned long long offset = P.cdf_offset + __ldg(P.tile_words + tile_base / WS_CDF_TILE);
+        const unsigned long long offset = cdf_offset + __ldg(P.tile_words + tile_base / WS_CDF_TILE);
 
         // global fixed-point CDF of the lane's 8 consecutive particles
         unsigned long long C[WS_SCAN_ITEMS];
@@ -784,7 +795,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
             unsigned long long frp = 0ull;
             if (lane == 0 && tile != 0) {
                 const int p = tile_base - 1;
-                const unsigned long long Cp = P.cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+                const unsigned long long Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
                 ws_slot_split(Cp, (unsigned int)ns, kp, frp);
                 if (kp < (unsigned int)ns) {
                     kmax = max(kmax, kp);
@@ -841,7 +852,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
             }
             if (lane == 0 && tile != 0) {
                 const int p = tile_base - 1;
-                const unsigned long long Cp = P.cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+                const unsigned long long Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
                 if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
                 else fstart = ws_F_int(Cp, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
             }

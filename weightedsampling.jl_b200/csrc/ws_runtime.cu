@@ -1286,21 +1286,17 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     CK(c, ws_launch_cdf(S, c->stream));
     timed_end(c, te);
     NCK(c, g_nccl.AllGather(c->d_all_tot + R, c->d_all_tot, 1, WS_NCCL_UINT64, c->comm, c->stream));
-    std::vector<unsigned long long> tot(R);
-    CK(c, cudaMemcpyAsync(tot.data(), c->d_all_tot, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    c->phase_ms[0] += t_now() - t0;
-    t0 = t_now();
-    unsigned long long off = 0ull;
-    for (int q = 0; q < r; ++q) off += tot[q];
-    S.cdf_offset = off;
+    // the CDF offset of this rank (sum of the lower ranks' masses) is formed on the device from the
+    // allgathered masses, so the host does not have to wait for them
+    S.all_tot = c->d_all_tot;
+    S.rank = r;
     CK(c, ws_launch_bounds(S, c->stream));
     NCK(c, g_nccl.AllGather(c->d_all_bounds + 2 * R, c->d_all_bounds, 2, WS_NCCL_INT32, c->comm, c->stream));
     std::vector<int32_t> bnd(2 * R);
     CK(c, cudaMemcpyAsync(bnd.data(), c->d_all_bounds, sizeof(int32_t) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    c->stats.d2h_bytes += (int64_t)(sizeof(unsigned long long) * R + sizeof(int32_t) * 2 * R);
-    c->phase_ms[1] += t_now() - t0;
+    c->stats.d2h_bytes += (int64_t)(sizeof(int32_t) * 2 * R);
+    c->phase_ms[0] += t_now() - t0;
     t0 = t_now();
     const int64_t fs = bnd[2 * r], fe = bnd[2 * r + 1];
     const int64_t produced = fe - fs;
