@@ -310,6 +310,18 @@ int ws_reset_kernel_times(ws_ctx* ctx);
  * on = 0 restores the reference's eager gather of every column inside ws_resample (stores.jl:105-111);
  * results are identical either way. */
 int ws_set_lazy_gather(ws_ctx* ctx, int on);
+/* Genealogy.  The reference's resample! gathers EVERY column at every resampling step
+ * (src/stores.jl:105-121), so a model that keeps its history (x{t}, examples/1D_ssm.jl, 2D_ssm.jl) pays
+ * O(t) per step.  Here a plane that is not read keeps the order of the event after which it was written;
+ * the per-event ancestor vectors (4 B per particle and event) are kept instead, and a read composes them
+ * (one dependent 4-byte load per event).  on = 0: gather stale planes at the next event, as before.
+ * budget_bytes > 0: retained ancestor vectors above this are released by gathering the oldest planes
+ * (default: a quarter of the device memory; WSB200_GENEALOGY_BYTES).  Single-GPU states only. */
+int ws_set_genealogy(ws_ctx* ctx, int on, int64_t budget_bytes);
+/* retained ancestor vectors, their bytes, and the number of resampling events so far */
+int ws_genealogy_info(ws_ctx* ctx, int64_t* n_vectors, int64_t* bytes, int64_t* events);
+/* how many resampling events a column's oldest plane is behind (0: stored in the current order) */
+int ws_col_events_behind(ws_ctx* ctx, int32_t id, int64_t* out);
 int ws_set_timing(ws_ctx* ctx, int on); /* record per-phase CUDA events (adds syncs; for profiling only) */
 /* sharded state: particles this rank has received from other ranks in all resampling steps so far */
 int ws_get_migrated(ws_ctx* ctx, int64_t* out);

@@ -146,6 +146,9 @@ SIGNATURES = {
     "ws_reset_kernel_times": (C.c_int, [_ctx]),
     "ws_set_timing": (C.c_int, [_ctx, C.c_int]),
     "ws_set_lazy_gather": (C.c_int, [_ctx, C.c_int]),
+    "ws_set_genealogy": (C.c_int, [_ctx, C.c_int, C.c_int64]),
+    "ws_genealogy_info": (C.c_int, [_ctx, _i64p, _i64p, _i64p]),
+    "ws_col_events_behind": (C.c_int, [_ctx, C.c_int32, _i64p]),
     "ws_next_philox_stream": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ws_get_migrated": (C.c_int, [_ctx, _i64p]),
     "ws_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),

@@ -143,9 +143,12 @@ def to_dataframe(state):
     """``DataFrame(state)`` (utils.jl:83-88): every column plus ``log_weight``."""
     import pandas as pd
     st = state.store
-    data = {}
-    for name in st.colnames():
+    got = {}
+    # newest columns first: a column that is several resampling events behind is read through the
+    # composed ancestors, and the composition continues from the one made for the previous (newer) column
+    for name in reversed(st.colnames()):
         v = st.getcol(name)
-        data[name] = v if v.ndim == 1 else list(v)
+        got[name] = v if v.ndim == 1 else list(v)
+    data = {name: got[name] for name in st.colnames()}
     data["log_weight"] = state.weights
     return pd.DataFrame(data)

@@ -283,6 +283,15 @@ class SMCState:
         self.store._call("ws_get_stats", C.byref(s))
         return {f: getattr(s, f) for f, _ in L.ws_stats._fields_}
 
+    def genealogy(self):
+        """Retained per-event ancestor vectors (trajectory storage by genealogy)."""
+        nv, nb, ev = C.c_int64(), C.c_int64(), C.c_int64()
+        self.store._call("ws_genealogy_info", C.byref(nv), C.byref(nb), C.byref(ev))
+        return {"vectors": nv.value, "bytes": nb.value, "events": ev.value}
+
+    def set_genealogy(self, on=True, budget_bytes=0):
+        self.store._call("ws_set_genealogy", int(bool(on)), int(budget_bytes))
+
     def kernel_times(self):
         ms = (C.c_double * 8)()
         cnt = (C.c_int64 * 8)()

@@ -105,6 +105,14 @@ struct WsGatherParams {
     double* dst[WS_GATHER_MAX_PLANES];
 };
 
+#define WS_COMPOSE_MAX_CHAIN 24
+struct WsComposeParams {
+    int64_t n;
+    int32_t n_chain;
+    int32_t pad;
+    const int32_t* chain[WS_COMPOSE_MAX_CHAIN];  // applied in this order: idx = chain[t][idx]
+};
+
 // launchers (ws_kernels.cu)
 cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s);
 cudaError_t ws_launch_reduce_logw(const double* logw, int64_t n, WsLse* partials, int grid, cudaStream_t s);
@@ -125,6 +133,8 @@ cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int gr
 cudaError_t ws_launch_local_ancestors(int32_t* anc, int64_t n, const int32_t* anc_self, int64_t self_lo, int64_t self_hi,
                                       int grid, cudaStream_t s);
 cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t n_idx, double* dst, cudaStream_t s);
+cudaError_t ws_launch_compose(const WsComposeParams& P, int32_t* out, const int32_t* start, cudaStream_t s);
+cudaError_t ws_launch_compose_rows(const WsComposeParams& P, int64_t* out, const int64_t* start, cudaStream_t s);
 int ws_vm_max_grid(int n_regs, int n_loads, int sm_count);
 int ws_vm_smem_bytes(int n_regs, int n_loads);
 cudaError_t ws_kernels_init(int device);

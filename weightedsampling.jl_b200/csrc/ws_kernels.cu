@@ -1136,6 +1136,38 @@ cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// Genealogy: composition of ancestor vectors
+// ------------------------------------------------------------------------------------------
+// A plane that has not been touched for several resampling events is stored in the order of the event
+// after which it was last written; its current content is plane[a_{e+1}[a_{e+2}[... a_E[i]]]].  The chain
+// is applied innermost-last: chain[0] = a_E, chain[1] = a_{E-1}, ...; `start` (optional) continues from a
+// map composed earlier.  One dependent 4-byte load per event and particle, instead of gathering every
+// column at every event as the reference's resample! does (src/stores.jl:105-121).
+template <class I>
+__global__ void __launch_bounds__(256) ws_compose_kernel(const WsComposeParams P, I* __restrict__ out, const I* __restrict__ start) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < P.n; i += stride) {
+        int64_t idx = start != nullptr ? (int64_t)start[i] : i;
+        for (int t = 0; t < P.n_chain; ++t) idx = (int64_t)__ldg(P.chain[t] + idx);
+        out[i] = (I)idx;
+    }
+}
+cudaError_t ws_launch_compose(const WsComposeParams& P, int32_t* out, const int32_t* start, cudaStream_t s) {
+    int grid = (int)((P.n + 255) / 256);
+    if (grid > g_sm_count * 8) grid = g_sm_count * 8;
+    if (grid < 1) grid = 1;
+    ws_compose_kernel<int32_t><<<grid, 256, 0, s>>>(P, out, start);
+    return cudaGetLastError();
+}
+cudaError_t ws_launch_compose_rows(const WsComposeParams& P, int64_t* out, const int64_t* start, cudaStream_t s) {
+    int grid = (int)((P.n + 255) / 256);
+    if (grid > g_sm_count * 8) grid = g_sm_count * 8;
+    if (grid < 1) grid = 1;
+    ws_compose_kernel<int64_t><<<grid, 256, 0, s>>>(P, out, start);
+    return cudaGetLastError();
+}
+
 cudaError_t ws_kernels_init(int device) {
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <functional>
 #include <memory>
+#include <deque>
 #include <map>
 #include <string>
 #include <vector>
@@ -101,6 +102,9 @@ struct Column {
     // next read.  stale[k] means "front[k] still holds the pre-resample order; element i of the
     // current particle set is front[k][d_anc[i]]".
     std::vector<uint8_t> stale;
+    // Genealogy: ep[k] = number of resampling events after which front[k] was last written / gathered.
+    // stale[k] <=> ep[k] < ctx.epoch; the current content is front[k][a_{ep+1}[... a_epoch[i]]].
+    std::vector<int64_t> ep;
 };
 
 struct TimedEvent {
@@ -165,8 +169,21 @@ struct ws_ctx {
     bool red_valid = false;        // h_red/d_red describe the current log-weights
 
     // resampling scratch
-    int32_t* d_anc = nullptr;
-    bool anc_pending = false;  // some plane is stale w.r.t. d_anc
+    int32_t* d_anc = nullptr;  // ancestors of the latest resampling event (== anc_live.back().ptr)
+    bool anc_pending = false;  // some plane is stale
+    // Genealogy: a resampling event no longer forces the gather of the planes that are still
+    // in an older order; their ancestor vectors are kept instead and composed when such a plane is read.
+    struct AncVec {
+        int64_t event;  // maps slots of epoch `event` to slots of epoch `event - 1`
+        int32_t* ptr;
+    };
+    int64_t epoch = 0;                // resampling events so far
+    std::deque<AncVec> anc_live;      // vectors some plane may still need, ascending events
+    std::vector<int32_t*> anc_pool;   // recycled vectors
+    bool genealogy = true;
+    size_t genealogy_budget = 0;      // bytes of retained ancestor vectors before old planes are gathered anyway
+    int32_t* d_map = nullptr;         // cached composition: slot of epoch map_E -> row in the order of epoch map_ep
+    int64_t map_ep = -1, map_E = -1;
     bool lazy_gather = true;
     unsigned long long* d_tile_words = nullptr;
     unsigned long long* d_cdf_local = nullptr;  // [n] tile-local fixed-point CDF (scratch of the resampler)
@@ -225,7 +242,11 @@ struct ws_ctx {
     std::string err;
 };
 
-static int materialize_planes(ws_ctx* c);
+static int materialize_planes(ws_ctx* c, const std::vector<Plane>* only = nullptr);
+static int materialize_deep(ws_ctx* c, const std::vector<Plane>& planes);
+static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out);
+static const int32_t* anc_of_event(const ws_ctx* c, int64_t event);
+static int materialize_tape_planes(ws_ctx* c, int32_t n_extra, const int32_t* col, const int32_t* comp);
 
 // ------------------------------------------------------------------------------------------
 // error helpers
@@ -419,7 +440,15 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     CKC(cudaMemsetAsync(c->d_red, 0, sizeof(WsReduceOut), c->stream));
     CKC(cudaMallocHost(&c->h_red, sizeof(WsReduceOut)));
     memset(c->h_red, 0, sizeof(WsReduceOut));
-    CKC(cudaMalloc(&c->d_anc, sizeof(int32_t) * (size_t)c->n));
+    CKC(cudaMalloc(&c->d_anc, sizeof(int32_t) * (size_t)(c->n + c->spare)));
+    {
+        // genealogy budget: WSB200_GENEALOGY_BYTES, default a quarter of the device memory
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        c->genealogy_budget = total_b / 4;
+        if (const char* e = getenv("WSB200_GENEALOGY_BYTES")) c->genealogy_budget = (size_t)strtoull(e, nullptr, 10);
+        if (const char* e = getenv("WSB200_GENEALOGY")) c->genealogy = atoi(e) != 0;
+    }
     c->n_tiles = (c->n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     CKC(cudaMalloc(&c->d_tile_words, sizeof(unsigned long long) * (size_t)c->n_tiles));
     CKC(cudaMalloc(&c->d_cdf_local, sizeof(unsigned long long) * (size_t)c->n));
@@ -498,7 +527,15 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_partials);
     cudaFree(c->d_red);
     if (c->h_red) cudaFreeHost(c->h_red);
-    cudaFree(c->d_anc);
+    {
+        std::vector<int32_t*> vecs{c->d_anc};
+        for (auto& v : c->anc_live) vecs.push_back(v.ptr);
+        for (auto p : c->anc_pool) vecs.push_back(p);
+        std::sort(vecs.begin(), vecs.end());
+        vecs.erase(std::unique(vecs.begin(), vecs.end()), vecs.end());
+        for (auto p : vecs) cudaFree(p);
+        cudaFree(c->d_map);
+    }
     cudaFree(c->d_tile_words);
     cudaFree(c->d_cdf_local);
     cudaFree(c->d_tile_counter);
@@ -567,6 +604,11 @@ static int flush_window(ws_ctx* c) {
     // Deferred resample!: a stale plane is read through the ancestors; if the window also writes it,
     // the new values go to the back buffer (other threads still read the old order) and the buffers
     // are swapped afterwards.  A stale plane that is only written never needs its gather at all.
+    {
+        std::vector<Plane> loaded;
+        for (auto& ld : w.loads) loaded.push_back(ld.first);
+        TRY(materialize_deep(c, loaded));  // planes older than the latest event are gathered first
+    }
     P.ancestors = c->d_anc;
     P.load_gather = 0u;
     std::vector<Plane> swap_after;
@@ -584,6 +626,7 @@ static int flush_window(ws_ctx* c) {
         for (auto& ld : w.loads)
             if (ld.first == pl) loaded = true;
         if (col.stale[pl.comp] && loaded) {
+            if (col.back[pl.comp] == nullptr) CK(c, cudaMalloc(&col.back[pl.comp], sizeof(double) * (size_t)(c->n + c->spare)));
             P.store_ptr[k] = col.back[pl.comp];
             swap_after.push_back(pl);
         } else {
@@ -616,7 +659,10 @@ static int flush_window(ws_ctx* c) {
     CK(c, ws_launch_vm(P, std::max(1, grid), c->stream));
     timed_end(c, te);
     for (auto& pl : swap_after) std::swap(c->cols[pl.col].front[pl.comp], c->cols[pl.col].back[pl.comp]);
-    for (auto& pl : w.dirty) c->cols[pl.col].stale[pl.comp] = 0;  // written planes are in the current order
+    for (auto& pl : w.dirty) {  // written planes are in the current order
+        c->cols[pl.col].stale[pl.comp] = 0;
+        c->cols[pl.col].ep[pl.comp] = c->epoch;
+    }
     c->stats.fused_passes++;
     c->stats.fused_statements += w.n_statements;
     if (w.has_acc) {
@@ -789,10 +835,13 @@ extern "C" int ws_col_ensure(ws_ctx* c, const char* name, int32_t width, int32_t
     col.name = name;
     col.width = width;
     col.stale.assign((size_t)width, 0);
+    col.ep.assign((size_t)width, c->epoch);
     for (int k = 0; k < width; ++k) {
         double *f = nullptr, *b = nullptr;
         CK(c, cudaMalloc(&f, sizeof(double) * (size_t)(c->n + c->spare)));
-        CK(c, cudaMalloc(&b, sizeof(double) * (size_t)(c->n + c->spare)));
+        // the back buffer (target of a gather) is created on first use, except in sharded runs whose
+        // exchange writes straight into it
+        if (c->nranks > 1) CK(c, cudaMalloc(&b, sizeof(double) * (size_t)(c->n + c->spare)));
         CK(c, cudaMemsetAsync(f, 0, sizeof(double) * (size_t)c->n, c->stream));
         col.front.push_back(f);
         col.back.push_back(b);
@@ -834,10 +883,32 @@ extern "C" int ws_col_download(ws_ctx* c, int32_t id, double* host_out) {
     if (!c || !host_out) return WS_EINVAL;
     if (id < 0 || id >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", id);
     TRY(flush_window(c));
-    TRY(materialize_planes(c));
+    CK(c, cudaSetDevice(c->device));
     const Column& col = c->cols[id];
-    for (int k = 0; k < col.width; ++k)
-        CK(c, cudaMemcpyAsync(host_out + (size_t)k * c->n, col.front[k], sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    for (int k = 0; k < col.width; ++k) {
+        const double* src = col.front[k];
+        if (col.stale[k]) {
+            // read through the (composed) ancestors into scratch: the plane itself stays in its old order,
+            // so exporting a long history costs one 4-byte chain step per event, not a gather of everything
+            const int32_t* map = nullptr;
+            TRY(map_for_epoch(c, col.ep[k], &map));
+            TRY(ensure_scratch(c, sizeof(double) * (size_t)c->n));
+            WsGatherParams G;
+            memset(&G, 0, sizeof(G));
+            G.n = c->n;
+            G.ancestors = map;
+            G.n_planes = 1;
+            G.src[0] = col.front[k];
+            G.dst[0] = c->d_scratch;
+            TimedEvent te;
+            timed_begin(c, KC_GATHER, te);
+            CK(c, ws_launch_gather(G, grid_for(c, c->n, 256, 8), c->stream));
+            timed_end(c, te);
+            src = c->d_scratch;
+        }
+        CK(c, cudaMemcpyAsync(host_out + (size_t)k * c->n, src, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+        if (col.stale[k]) CK(c, cudaStreamSynchronize(c->stream));  // scratch is reused by the next plane
+    }
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)sizeof(double) * c->n * col.width;
     return WS_OK;
@@ -848,6 +919,7 @@ extern "C" int ws_col_upload(ws_ctx* c, int32_t id, const double* host_in) {
     TRY(flush_window(c));
     Column& col = c->cols[id];
     for (auto& st : col.stale) st = 0;  // the whole column is overwritten: its deferred gather is moot
+    for (auto& e : col.ep) e = c->epoch;
     for (int k = 0; k < col.width; ++k)
         CK(c, cudaMemcpyAsync(col.front[k], host_in + (size_t)k * c->n, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -1162,8 +1234,11 @@ static int gather_planes(ws_ctx* c, const int32_t* d_anc, const std::vector<Plan
         G.n_planes = (int)std::min((size_t)WS_GATHER_MAX_PLANES, which.size() - p0);
         for (int k = 0; k < G.n_planes; ++k) {
             const Plane pl = which[p0 + k];
-            G.src[k] = c->cols[pl.col].front[pl.comp];
-            G.dst[k] = c->cols[pl.col].back[pl.comp];
+            Column& col = c->cols[pl.col];
+            if (col.back[pl.comp] == nullptr)  // back buffers are created on first use
+                CK(c, cudaMalloc(&col.back[pl.comp], sizeof(double) * (size_t)(c->n + c->spare)));
+            G.src[k] = col.front[pl.comp];
+            G.dst[k] = col.back[pl.comp];
         }
         TimedEvent te;
         timed_begin(c, KC_GATHER, te);
@@ -1173,20 +1248,166 @@ static int gather_planes(ws_ctx* c, const int32_t* d_anc, const std::vector<Plan
     for (auto& pl : which) {
         std::swap(c->cols[pl.col].front[pl.comp], c->cols[pl.col].back[pl.comp]);
         c->cols[pl.col].stale[pl.comp] = 0;
+        c->cols[pl.col].ep[pl.comp] = c->epoch;
     }
     return WS_OK;
 }
 
-// Apply the deferred gather to every plane that is still in pre-resample order.
-static int materialize_planes(ws_ctx* c) {
-    if (!c->anc_pending) return WS_OK;
-    std::vector<Plane> which;
-    for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
-        for (int32_t k = 0; k < c->cols[ci].width; ++k)
-            if (c->cols[ci].stale[k]) which.push_back(Plane{ci, k});
-    TRY(gather_planes(c, c->d_anc, which));
-    c->anc_pending = false;
+// ---- genealogy ---------------------------------------------------------------------------------------
+static const int32_t* anc_of_event(const ws_ctx* c, int64_t event) {
+    for (auto& v : c->anc_live)
+        if (v.event == event) return v.ptr;
+    return nullptr;
+}
+
+// Device map "slot of the current epoch -> row of a plane stored in the order of epoch `ep`":
+// nullptr for ep == epoch (identity), the latest ancestors for ep == epoch - 1, otherwise the composition
+// a_{ep+1}[... a_epoch[i]], continued from the cached map when that was composed for a later epoch.
+static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out) {
+    *out = nullptr;
+    if (ep >= c->epoch) return WS_OK;
+    if (ep == c->epoch - 1) {
+        *out = c->d_anc;
+        return WS_OK;
+    }
+    if (c->map_E == c->epoch && c->map_ep == ep) {
+        *out = c->d_map;
+        return WS_OK;
+    }
+    if (c->d_map == nullptr) CK(c, cudaMalloc(&c->d_map, sizeof(int32_t) * (size_t)c->n));
+    int64_t from = c->epoch;  // events still to apply: from, from-1, ..., ep+1
+    const int32_t* start = nullptr;
+    if (c->map_E == c->epoch && c->map_ep > ep && c->map_ep < c->epoch) {
+        from = c->map_ep;
+        start = c->d_map;
+    }
+    while (from > ep) {
+        WsComposeParams P;
+        memset(&P, 0, sizeof(P));
+        P.n = c->n;
+        while (from > ep && P.n_chain < WS_COMPOSE_MAX_CHAIN) {
+            const int32_t* a = anc_of_event(c, from);
+            if (a == nullptr) return fail(c, WS_EINVAL, "genealogy: ancestors of event %lld were released", (long long)from);
+            P.chain[P.n_chain++] = a;
+            --from;
+        }
+        CK(c, ws_launch_compose(P, c->d_map, start, c->stream));
+        c->stats.kernel_launches++;
+        start = c->d_map;
+    }
+    c->map_E = c->epoch;
+    c->map_ep = ep;
+    *out = c->d_map;
     return WS_OK;
+}
+
+// Apply the deferred gather to every plane (or to the given ones) that is still in an older order.
+static int materialize_planes(ws_ctx* c, const std::vector<Plane>* only) {
+    if (!c->anc_pending) return WS_OK;
+    std::map<int64_t, std::vector<Plane>, std::greater<int64_t>> by_ep;  // newest first: the map cache continues downwards
+    auto take = [&](Plane pl) {
+        Column& col = c->cols[pl.col];
+        if (col.stale[pl.comp]) {
+            auto& v = by_ep[col.ep[pl.comp]];
+            if (std::find(v.begin(), v.end(), pl) == v.end()) v.push_back(pl);
+        }
+    };
+    if (only) {
+        for (auto& pl : *only) take(pl);
+    } else {
+        for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
+            for (int32_t k = 0; k < c->cols[ci].width; ++k) take(Plane{ci, k});
+    }
+    for (auto& g : by_ep) {
+        const int32_t* map = nullptr;
+        TRY(map_for_epoch(c, g.first, &map));
+        TRY(gather_planes(c, map, g.second));
+    }
+    if (!only) c->anc_pending = false;
+    return WS_OK;
+}
+
+// Score folds and moves read the planes of the score tape (and the move targets), nothing else: a long
+// history of untouched columns stays untouched.
+static int materialize_tape_planes(ws_ctx* c, int32_t n_extra, const int32_t* col, const int32_t* comp) {
+    std::vector<Plane> need;
+    for (auto& ld : c->score.loads) need.push_back(ld.first);
+    for (auto& te : c->tape)
+        for (auto& pl : te.refs) need.push_back(pl);
+    for (int32_t t = 0; t < n_extra; ++t) need.push_back(Plane{col[t], comp[t]});
+    std::vector<Plane> ok;
+    for (auto& pl : need)
+        if (pl.col >= 0 && pl.col < (int32_t)c->cols.size() && pl.comp >= 0 && pl.comp < c->cols[pl.col].width) ok.push_back(pl);
+    return materialize_planes(c, &ok);
+}
+
+// Planes older than the latest event cannot be read through d_anc by the fused pass: gather those first.
+static int materialize_deep(ws_ctx* c, const std::vector<Plane>& planes) {
+    std::vector<Plane> deep;
+    for (auto& pl : planes) {
+        const Column& col = c->cols[pl.col];
+        if (col.stale[pl.comp] && col.ep[pl.comp] < c->epoch - 1) deep.push_back(pl);
+    }
+    if (deep.empty()) return WS_OK;
+    return materialize_planes(c, &deep);
+}
+
+// Called before a resampling event writes a new ancestor vector.  Without genealogy (eager mode, sharded
+// runs) every stale plane is gathered and the single vector is reused.  With it, vectors no plane needs any
+// more are recycled, the retained ones are capped by the byte budget (oldest planes gathered first), and a
+// fresh vector becomes d_anc.
+static int begin_resample_event(ws_ctx* c) {
+    if (!c->genealogy || !c->lazy_gather || c->nranks > 1) {
+        TRY(materialize_planes(c));
+        c->anc_live.clear();
+        c->anc_live.push_back({c->epoch + 1, c->d_anc});
+        return WS_OK;
+    }
+    auto min_ep = [&]() {
+        int64_t m = c->epoch;
+        for (auto& col : c->cols)
+            for (int k = 0; k < col.width; ++k)
+                if (col.stale[k]) m = std::min(m, col.ep[k]);
+        return m;
+    };
+    auto gc = [&]() {
+        const int64_t m = min_ep();  // events <= m are not needed by anybody
+        while (!c->anc_live.empty() && c->anc_live.front().event <= m) {
+            c->anc_pool.push_back(c->anc_live.front().ptr);
+            c->anc_live.pop_front();
+        }
+    };
+    gc();
+    while (!c->anc_live.empty() && (c->anc_live.size() + 1) * sizeof(int32_t) * (size_t)c->n > c->genealogy_budget) {
+        // over budget: bring the oldest planes up to date, which releases the oldest vectors
+        const int64_t m = min_ep();
+        std::vector<Plane> oldest;
+        for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
+            for (int32_t k = 0; k < c->cols[ci].width; ++k)
+                if (c->cols[ci].stale[k] && c->cols[ci].ep[k] == m) oldest.push_back(Plane{ci, k});
+        if (oldest.empty()) break;
+        TRY(materialize_planes(c, &oldest));
+        gc();
+    }
+    if (c->anc_live.empty() && c->anc_pool.empty() && c->d_anc != nullptr) c->anc_pool.push_back(c->d_anc);  // the vector made by ws_create
+    int32_t* fresh = nullptr;
+    if (!c->anc_pool.empty()) {
+        fresh = c->anc_pool.back();
+        c->anc_pool.pop_back();
+    } else {
+        CK(c, cudaMalloc(&fresh, sizeof(int32_t) * (size_t)(c->n + c->spare)));
+    }
+    c->anc_live.push_back({c->epoch + 1, fresh});
+    c->d_anc = fresh;
+    return WS_OK;
+}
+
+// after the ancestors of the new event are in d_anc
+static void end_resample_event(ws_ctx* c) {
+    c->epoch++;
+    for (auto& col : c->cols)
+        for (auto& st : col.stale) st = 1;
+    c->anc_pending = !c->cols.empty();
 }
 
 static int gather_all(ws_ctx* c, const int32_t* d_anc) {
@@ -1447,12 +1668,13 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
         CK(c, ws_launch_local_ancestors(c->d_anc, c->n, c->d_anc_src + send_off[r], send_cnt[r] > 0 ? self_lo : c->n,
                                          send_cnt[r] > 0 ? self_hi : c->n, grid_for(c, c->n, 256, 8), c->stream));
         c->stats.kernel_launches++;
-        for (auto& col : c->cols)
-            for (auto& stl : col.stale) stl = 1;
-        c->anc_pending = !c->cols.empty();
+        end_resample_event(c);
         return WS_OK;
     }
     for (auto& col : c->cols) std::swap(col.front, col.back);
+    c->epoch++;
+    for (auto& col : c->cols)
+        for (auto& e : col.ep) e = c->epoch;
     return WS_OK;
 }
 
@@ -1483,7 +1705,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
             c->cur_u += need;
         }
         if (c->nranks > 1) {
-            TRY(materialize_planes(c));
+            TRY(begin_resample_event(c));
             TRY(resample_sharded(c, d_ru));
             c->logw_uniform = true;
             c->logw_base = r.log_mean_w;
@@ -1501,17 +1723,12 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
             return WS_OK;
         }
         const uint64_t stream_id = c->next_stream++;
-        // planes still waiting for the PREVIOUS ancestors must be gathered before d_anc is overwritten
-        TRY(materialize_planes(c));
+        // planes still in an older order keep their ancestor vectors (genealogy) or are gathered now
+        TRY(begin_resample_event(c));
         TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, nullptr, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id, c->d_counters + 0));
-        if (c->lazy_gather) {
-            // resample!(store, indices) is deferred: each plane is gathered when it is next read
-            for (auto& col : c->cols)
-                for (auto& st : col.stale) st = 1;
-            c->anc_pending = !c->cols.empty();
-        } else {
-            TRY(gather_all(c, c->d_anc));
-        }
+        // resample!(store, indices) is deferred: each plane is gathered when it is next read
+        end_resample_event(c);
+        if (!c->lazy_gather) TRY(materialize_planes(c));
         // fill!(state.weights, mean_logW): kept symbolic until somebody reads the array
         c->logw_uniform = true;
         c->logw_base = r.log_mean_w;
@@ -1741,6 +1958,11 @@ extern "C" int ws_expectation(ws_ctx* c, const ws_expr* f, int32_t n_exprs, doub
     P.n_loads = (int)p.loads.size();
     P.n_stores = 0;
     P.n_regs = std::max(1, p.high_water);
+    {
+        std::vector<Plane> loaded;
+        for (auto& ld : p.loads) loaded.push_back(ld.first);
+        TRY(materialize_deep(c, loaded));
+    }
     P.ancestors = c->d_anc;
     for (int k = 0; k < P.n_loads; ++k) {
         const Plane pl = p.loads[k].first;
@@ -1781,15 +2003,36 @@ extern "C" int ws_col_download_rows(ws_ctx* c, int32_t id, const int64_t* indice
     for (int64_t i = 0; i < n_idx; ++i)
         if (indices[i] < 0 || indices[i] >= c->n) return fail(c, WS_EINVAL, "row index %lld out of range", (long long)indices[i]);
     TRY(flush_window(c));
-    TRY(materialize_planes(c));
     CK(c, cudaSetDevice(c->device));
-    TempBuf idx, out;
+    TempBuf idx, out, rows;
     CK(c, cudaMalloc(&idx.p, sizeof(int64_t) * (size_t)n_idx));
     CK(c, cudaMalloc(&out.p, sizeof(double) * (size_t)n_idx));
     CK(c, cudaMemcpyAsync(idx.p, indices, sizeof(int64_t) * (size_t)n_idx, cudaMemcpyHostToDevice, c->stream));
     const Column& col = c->cols[id];
     for (int k = 0; k < col.width; ++k) {
-        CK(c, ws_launch_gather_rows(col.front[k], (const int64_t*)idx.p, n_idx, (double*)out.p, c->stream));
+        const int64_t* use = (const int64_t*)idx.p;
+        if (col.stale[k]) {
+            // trace the requested rows back through the genealogy (n_idx chains, not n)
+            if (rows.p == nullptr) CK(c, cudaMalloc(&rows.p, sizeof(int64_t) * (size_t)n_idx));
+            const int64_t* start = (const int64_t*)idx.p;
+            int64_t from = c->epoch;
+            while (from > col.ep[k]) {
+                WsComposeParams P;
+                memset(&P, 0, sizeof(P));
+                P.n = n_idx;
+                while (from > col.ep[k] && P.n_chain < WS_COMPOSE_MAX_CHAIN) {
+                    const int32_t* a = anc_of_event(c, from);
+                    if (a == nullptr) return fail(c, WS_EINVAL, "genealogy: ancestors of event %lld were released", (long long)from);
+                    P.chain[P.n_chain++] = a;
+                    --from;
+                }
+                CK(c, ws_launch_compose_rows(P, (int64_t*)rows.p, start, c->stream));
+                c->stats.kernel_launches++;
+                start = (const int64_t*)rows.p;
+            }
+            use = (const int64_t*)rows.p;
+        }
+        CK(c, ws_launch_gather_rows(col.front[k], use, n_idx, (double*)out.p, c->stream));
         c->stats.kernel_launches++;
         CK(c, cudaMemcpyAsync(host_out + (size_t)k * n_idx, out.p, sizeof(double) * (size_t)n_idx, cudaMemcpyDeviceToHost, c->stream));
     }
@@ -2023,7 +2266,7 @@ static int fill_score_launch(ws_ctx* c, WsScoreParams& S, int n_ops) {
 extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out) {
     if (!c || !host_out) return WS_EINVAL;
     TRY(flush_window(c));
-    TRY(materialize_planes(c));
+    TRY(materialize_tape_planes(c, 0, nullptr, nullptr));
     CK(c, cudaSetDevice(c->device));
     TRY(ensure_scratch(c, sizeof(double) * (size_t)c->n));
     if (c->score_wide) {
@@ -2058,7 +2301,12 @@ extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out
 extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t* col, const int32_t* comp, double* out) {
     if (!c || !col || !comp || !out || n_targets < 1) return c ? fail(c, WS_EINVAL, "ws_marginal_diversity: bad arguments") : WS_EINVAL;
     TRY(flush_window(c));
-    TRY(materialize_planes(c));
+    for (int t = 0; t < n_targets; ++t) TRY(check_plane(c, col[t], comp[t]));
+    {
+        std::vector<Plane> tg;
+        for (int t = 0; t < n_targets; ++t) tg.push_back(Plane{col[t], comp[t]});
+        TRY(materialize_planes(c, &tg));
+    }
     CK(c, cudaSetDevice(c->device));
     double best = INFINITY;
     for (int t = 0; t < n_targets; ++t) {
@@ -2142,7 +2390,7 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
     if (spec->proposal != WS_PROPOSAL_RW && spec->proposal != WS_PROPOSAL_AUTORW) return fail(c, WS_EINVAL, "ws_move: unknown proposal %d", spec->proposal);
     if (spec->has_bounds && (!spec->lo || !spec->hi)) return fail(c, WS_EINVAL, "ws_move: bounds missing");
     TRY(flush_window(c));
-    TRY(materialize_planes(c));
+    TRY(materialize_tape_planes(c, d, spec->col, spec->comp));
     CK(c, cudaSetDevice(c->device));
     if (info) {
         info->ran = 0;
@@ -2357,6 +2605,30 @@ extern "C" int ws_set_lazy_gather(ws_ctx* c, int on) {
     TRY(flush_window(c));
     TRY(materialize_planes(c));
     c->lazy_gather = on != 0;
+    return WS_OK;
+}
+extern "C" int ws_set_genealogy(ws_ctx* c, int on, int64_t budget_bytes) {
+    if (!c) return WS_EINVAL;
+    TRY(flush_window(c));
+    if (!on) TRY(materialize_planes(c));
+    c->genealogy = on != 0;
+    if (budget_bytes > 0) c->genealogy_budget = (size_t)budget_bytes;
+    return WS_OK;
+}
+extern "C" int ws_genealogy_info(ws_ctx* c, int64_t* n_vectors, int64_t* bytes, int64_t* events) {
+    if (!c) return WS_EINVAL;
+    if (n_vectors) *n_vectors = (int64_t)c->anc_live.size();
+    if (bytes) *bytes = (int64_t)(c->anc_live.size() * sizeof(int32_t) * (size_t)(c->n + c->spare));
+    if (events) *events = c->epoch;
+    return WS_OK;
+}
+extern "C" int ws_col_events_behind(ws_ctx* c, int32_t id, int64_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    if (id < 0 || id >= (int32_t)c->cols.size()) return fail(c, WS_EINVAL, "unknown column id %d", id);
+    int64_t b = 0;
+    for (int k = 0; k < c->cols[id].width; ++k)
+        if (c->cols[id].stale[k]) b = std::max(b, c->epoch - c->cols[id].ep[k]);
+    *out = b;
     return WS_OK;
 }
 extern "C" int ws_next_philox_stream(ws_ctx* c, uint64_t* stream_out, uint64_t* seed_out) {
