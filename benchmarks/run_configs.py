@@ -83,6 +83,37 @@ def lgssm():
          particle_updates_per_sec=n_cpu * T / dt, post_mean=mean_c, log_evidence=le_c)
 
 
+def c2hist():
+    """examples/2D_ssm.jl VERBATIM (x{t} history kept): the reference gathers all 2(t+3) planes at step t;
+    the genealogy keeps one 4-byte ancestor vector per event instead."""
+    rng = np.random.default_rng(42)
+    T = 100 if QUICK else 400
+    obs = [rng.standard_normal(2) * 0.5 + np.array([t, 0.0]) for t in range(T)]
+    for n in ((1_000_000,) if QUICK else (1_000_000, 10_000_000)):
+        for on in (True, False):
+            if not on and n * T > 5e8:
+                Tn = T // 4   # the eager variant is quadratic in T: shorter run, per-step figure quoted
+            else:
+                Tn = T
+            st = ws.SMCState(n, ess_perc_min=1.0, seed=1)
+            st.set_genealogy(on)
+            root = ws.model(models.SSM2D)(obs[:Tn])
+            st.sync()
+            t0 = time.perf_counter()
+            ws.run(root, st)
+            le = ws.log_evidence(st)
+            st.sync()
+            dt = time.perf_counter() - t0
+            t1 = time.perf_counter()
+            x_mid = st[f"x_{Tn // 2}"]          # a column ~T/2 events behind
+            dt_read = time.perf_counter() - t1
+            emit(config=f"C2-history examples/2D_ssm.jl verbatim N={n} T={Tn} genealogy={'on' if on else 'off'}", seconds=dt,
+                 particle_updates_per_sec=n * Tn / dt, ms_per_step=1e3 * dt / Tn, log_evidence=le,
+                 genealogy=st.genealogy(), read_mid_column_seconds=dt_read, mid_column_mean=float(x_mid[:, 0].mean()),
+                 columns=len(st.store.colnames()))
+            del st
+
+
 def c3():
     rng = np.random.default_rng(42)
     npts = 1000 if QUICK else 10_000
@@ -175,6 +206,6 @@ def c5():
 
 
 if __name__ == "__main__":
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "lgssm", "c3", "c4", "c5"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "lgssm", "c2hist", "c3", "c4", "c5"]
     for w in which:
-        {"c1": c1, "lgssm": lgssm, "c3": c3, "c4": c4, "c5": c5}[w]()
+        {"c1": c1, "lgssm": lgssm, "c2hist": c2hist, "c3": c3, "c4": c4, "c5": c5}[w]()

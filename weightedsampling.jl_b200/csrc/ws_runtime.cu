@@ -182,6 +182,13 @@ struct ws_ctx {
     std::vector<int32_t*> anc_pool;   // recycled vectors
     bool genealogy = true;
     size_t genealogy_budget = 0;      // bytes of retained ancestor vectors before old planes are gathered anyway
+    // planes and ancestor vectors are carved out of slabs: a cudaMalloc per new column costs milliseconds
+    // (models that create a column per time step: x{t}), and nothing is ever freed before ws_destroy
+    struct Slab {
+        char* base;
+        size_t size, used;
+    };
+    std::vector<Slab> slabs;
     int32_t* d_map = nullptr;         // cached composition: slot of epoch map_E -> row in the order of epoch map_ep
     int64_t map_ep = -1, map_E = -1;
     bool lazy_gather = true;
@@ -313,6 +320,34 @@ static void resolve_events(ws_ctx* c) {
     c->pending_events.clear();
 }
 
+static int pool_alloc(ws_ctx* c, void** out, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    for (auto& sl : c->slabs) {
+        if (sl.size - sl.used >= bytes) {
+            *out = sl.base + sl.used;
+            sl.used += bytes;
+            return WS_OK;
+        }
+    }
+    // 32 requests of this size per slab, between 8 MB and 256 MB (never less than the request itself)
+    const size_t slab = std::max(bytes, std::min((size_t)256 << 20, std::max((size_t)8 << 20, 32 * bytes)));
+    char* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, slab);
+    size_t got = slab;
+    if (e != cudaSuccess && slab > bytes) {
+        cudaGetLastError();
+        e = cudaMalloc(&base, bytes);
+        got = bytes;
+    }
+    if (e != cudaSuccess) {
+        c->err = std::string("device allocation failed: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? WS_ENOMEM : WS_ECUDA;
+    }
+    c->slabs.push_back({base, got, bytes});
+    *out = base;
+    return WS_OK;
+}
+
 static int grid_for(const ws_ctx* c, int64_t n, int block, int per_sm) {
     int64_t g = (n + block - 1) / block;
     int64_t cap = (int64_t)c->sm_count * per_sm;
@@ -440,7 +475,11 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     CKC(cudaMemsetAsync(c->d_red, 0, sizeof(WsReduceOut), c->stream));
     CKC(cudaMallocHost(&c->h_red, sizeof(WsReduceOut)));
     memset(c->h_red, 0, sizeof(WsReduceOut));
-    CKC(cudaMalloc(&c->d_anc, sizeof(int32_t) * (size_t)(c->n + c->spare)));
+    if (pool_alloc(c, (void**)&c->d_anc, sizeof(int32_t) * (size_t)(c->n + c->spare)) != WS_OK) {
+        int rc__ = fail(nullptr, WS_ENOMEM, "%s", c->err.c_str());
+        ws_destroy(c);
+        return rc__;
+    }
     {
         // genealogy budget: WSB200_GENEALOGY_BYTES, default a quarter of the device memory
         size_t free_b = 0, total_b = 0;
@@ -519,23 +558,12 @@ extern "C" int ws_destroy(ws_ctx* c) {
                 c->rank, c->phase_ms[0] / c->phase_n, c->phase_ms[1] / c->phase_n, c->phase_ms[2] / c->phase_n,
                 c->phase_ms[3] / c->phase_n, c->phase_ms[5] / std::max<int64_t>(1, c->phase_n - 6), c->phase_ms[4] / c->phase_n,
                 (long long)c->phase_n);
-    for (auto& col : c->cols) {
-        for (auto p : col.front) cudaFree(p);
-        for (auto p : col.back) cudaFree(p);
-    }
+    for (auto& sl : c->slabs) cudaFree(sl.base);  // planes and ancestor vectors
     cudaFree(c->logw);
     cudaFree(c->d_partials);
     cudaFree(c->d_red);
     if (c->h_red) cudaFreeHost(c->h_red);
-    {
-        std::vector<int32_t*> vecs{c->d_anc};
-        for (auto& v : c->anc_live) vecs.push_back(v.ptr);
-        for (auto p : c->anc_pool) vecs.push_back(p);
-        std::sort(vecs.begin(), vecs.end());
-        vecs.erase(std::unique(vecs.begin(), vecs.end()), vecs.end());
-        for (auto p : vecs) cudaFree(p);
-        cudaFree(c->d_map);
-    }
+    cudaFree(c->d_map);
     cudaFree(c->d_tile_words);
     cudaFree(c->d_cdf_local);
     cudaFree(c->d_tile_counter);
@@ -626,7 +654,7 @@ static int flush_window(ws_ctx* c) {
         for (auto& ld : w.loads)
             if (ld.first == pl) loaded = true;
         if (col.stale[pl.comp] && loaded) {
-            if (col.back[pl.comp] == nullptr) CK(c, cudaMalloc(&col.back[pl.comp], sizeof(double) * (size_t)(c->n + c->spare)));
+            if (col.back[pl.comp] == nullptr) TRY(pool_alloc(c, (void**)&col.back[pl.comp], sizeof(double) * (size_t)(c->n + c->spare)));
             P.store_ptr[k] = col.back[pl.comp];
             swap_after.push_back(pl);
         } else {
@@ -838,10 +866,10 @@ extern "C" int ws_col_ensure(ws_ctx* c, const char* name, int32_t width, int32_t
     col.ep.assign((size_t)width, c->epoch);
     for (int k = 0; k < width; ++k) {
         double *f = nullptr, *b = nullptr;
-        CK(c, cudaMalloc(&f, sizeof(double) * (size_t)(c->n + c->spare)));
+        TRY(pool_alloc(c, (void**)&f, sizeof(double) * (size_t)(c->n + c->spare)));
         // the back buffer (target of a gather) is created on first use, except in sharded runs whose
         // exchange writes straight into it
-        if (c->nranks > 1) CK(c, cudaMalloc(&b, sizeof(double) * (size_t)(c->n + c->spare)));
+        if (c->nranks > 1) TRY(pool_alloc(c, (void**)&b, sizeof(double) * (size_t)(c->n + c->spare)));
         CK(c, cudaMemsetAsync(f, 0, sizeof(double) * (size_t)c->n, c->stream));
         col.front.push_back(f);
         col.back.push_back(b);
@@ -1236,7 +1264,7 @@ static int gather_planes(ws_ctx* c, const int32_t* d_anc, const std::vector<Plan
             const Plane pl = which[p0 + k];
             Column& col = c->cols[pl.col];
             if (col.back[pl.comp] == nullptr)  // back buffers are created on first use
-                CK(c, cudaMalloc(&col.back[pl.comp], sizeof(double) * (size_t)(c->n + c->spare)));
+                TRY(pool_alloc(c, (void**)&col.back[pl.comp], sizeof(double) * (size_t)(c->n + c->spare)));
             G.src[k] = col.front[pl.comp];
             G.dst[k] = col.back[pl.comp];
         }
@@ -1395,7 +1423,7 @@ static int begin_resample_event(ws_ctx* c) {
         fresh = c->anc_pool.back();
         c->anc_pool.pop_back();
     } else {
-        CK(c, cudaMalloc(&fresh, sizeof(int32_t) * (size_t)(c->n + c->spare)));
+        TRY(pool_alloc(c, (void**)&fresh, sizeof(int32_t) * (size_t)(c->n + c->spare)));
     }
     c->anc_live.push_back({c->epoch + 1, fresh});
     c->d_anc = fresh;
