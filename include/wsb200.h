@@ -310,6 +310,18 @@ int ws_reset_kernel_times(ws_ctx* ctx);
  * on = 0 restores the reference's eager gather of every column inside ws_resample (stores.jl:105-111);
  * results are identical either way. */
 int ws_set_lazy_gather(ws_ctx* ctx, int on);
+/* describe(state) (src/utils.jl:183-289) for one plane: weighted mean, StatsBase weighted median
+ * (quantile(v, Weights(w), 0.5): sort by (value, weight), h = (wsum - w1)/2 + w1, first k with S_k > h,
+ * linear interpolation from the previous element), uncorrected weighted std, min, max and the weights of the
+ * 8 equal-width bins of [min, max]; weights are exp_norm(state.weights).  The median is found on the device
+ * by an 8-pass radix select over fixed-point weight histograms (no sort, nothing but the 13 numbers comes
+ * back).  Any NaN in the plane makes mean / median / std / min / max NaN, as in the reference. */
+typedef struct ws_plane_stats {
+    double mean, median, std, min, max;
+    double hist[8];
+} ws_plane_stats;
+int ws_describe(ws_ctx* ctx, int32_t n_planes, const int32_t* col, const int32_t* comp, ws_plane_stats* out, double* ess);
+
 /* Genealogy.  The reference's resample! gathers EVERY column at every resampling step
  * (src/stores.jl:105-121), so a model that keeps its history (x{t}, examples/1D_ssm.jl, 2D_ssm.jl) pays
  * O(t) per step.  Here a plane that is not read keeps the order of the event after which it was written;

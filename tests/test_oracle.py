@@ -171,3 +171,19 @@ def test_c_oracle_normals_are_standard():
     le, mean, nres = cref.ssm2d_run(20000, np.zeros((3, 2)) + [[0, 0], [1, 0], [2, 0]], seed=5, ess_perc_min=1.0)
     assert nres == 2 and np.isfinite(le)  # step 1: identical x => ESS% == 1.0, not < 1.0
     assert abs(mean[1]) < 0.2
+
+
+def test_weighted_quantile_pins():
+    """StatsBase weighted quantile: with equal (non-frequency) weights it is the type-7 sample quantile
+    (numpy's default); heavier weights pull it; zero weights are ignored; NaN propagates."""
+    rng = np.random.default_rng(0)
+    v = rng.normal(size=1001)
+    for p in (0.1, 0.5, 0.9):
+        assert abs(ref.weighted_quantile(v, np.full(v.size, 1.0 / v.size), p) - np.quantile(v, p)) < 1e-12
+    v2 = np.array([1.0, 2.0, 3.0, 4.0])
+    assert ref.weighted_quantile(v2, np.array([0.1, 0.1, 0.1, 0.7]), 0.5) > 3.0
+    assert ref.weighted_quantile(v2, np.array([0.0, 0.5, 0.5, 0.0]), 0.5) == ref.weighted_quantile(v2[1:3], np.array([0.5, 0.5]), 0.5)
+    assert np.isnan(ref.weighted_quantile(np.array([1.0, np.nan]), np.array([0.5, 0.5]), 0.5))
+    assert ref.weighted_quantile(np.array([5.0]), np.array([1.0]), 0.5) == 5.0
+    d = ref.describe_column(v, np.full(v.size, 1.0 / v.size))
+    assert abs(d["mean"] - v.mean()) < 1e-12 and abs(d["std"] - v.std()) < 1e-12 and abs(d["hist"].sum() - 1.0) < 1e-12

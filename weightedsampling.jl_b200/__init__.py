@@ -11,6 +11,6 @@ from .expr import (abs2, atan, col, cos, exp, expm1, floor, lgamma, log, log1p, 
                    randu, sin, sqrt, tan, tanh, where)
 from .core import *  # noqa: F401,F403
 from .core import NormalDist  # noqa: F401
-from .analysis import (E, ess_perc, exp_norm, expectation, icdf, log_evidence, logsumexp,  # noqa: F401
+from .analysis import (E, describe, ess_perc, exp_norm, expectation, icdf, log_evidence, logsumexp,  # noqa: F401
                        resample_indices, sample, to_dataframe)
 from .model import model  # noqa: F401

@@ -37,6 +37,11 @@ TOK_CONST, TOK_PLANE, TOK_ADD, TOK_SUB, TOK_MUL, TOK_DIV, TOK_NEG, TOK_EXP, TOK_
     TOK_MAX, TOK_NOT, TOK_LGAMMA, TOK_LOG1P, TOK_EXPM1, TOK_TAN, TOK_ATAN, TOK_TANH, TOK_FLOOR = range(32)
 
 
+class ws_plane_stats(C.Structure):
+    _fields_ = [("mean", C.c_double), ("median", C.c_double), ("std", C.c_double), ("min", C.c_double),
+                ("max", C.c_double), ("hist", C.c_double * 8)]
+
+
 class ws_tok(C.Structure):
     _fields_ = [("op", C.c_int32), ("col", C.c_int32), ("comp", C.c_int32), ("reserved", C.c_int32),
                 ("val", C.c_double)]
@@ -146,6 +151,8 @@ SIGNATURES = {
     "ws_reset_kernel_times": (C.c_int, [_ctx]),
     "ws_set_timing": (C.c_int, [_ctx, C.c_int]),
     "ws_set_lazy_gather": (C.c_int, [_ctx, C.c_int]),
+    "ws_describe": (C.c_int, [_ctx, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(ws_plane_stats),
+                              C.POINTER(C.c_double)]),
     "ws_set_genealogy": (C.c_int, [_ctx, C.c_int, C.c_int64]),
     "ws_genealogy_info": (C.c_int, [_ctx, _i64p, _i64p, _i64p]),
     "ws_col_events_behind": (C.c_int, [_ctx, C.c_int32, _i64p]),

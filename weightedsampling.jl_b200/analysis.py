@@ -152,3 +152,59 @@ def to_dataframe(state):
     data = {name: got[name] for name in st.colnames()}
     data["log_weight"] = state.weights
     return pd.DataFrame(data)
+
+
+_SPARK = "▁▂▃▄▅▆▇█"
+
+
+def _sparkline(counts):
+    """utils.jl:128-133: counts scaled so that the largest maps to a full block."""
+    counts = np.asarray(counts, dtype=np.float64)
+    mx = counts.max() if counts.size else 0.0
+    if not (mx > 0):
+        return _SPARK[0] * len(counts)
+    lv = np.clip(np.ceil(counts / mx * len(_SPARK)).astype(int), 1, len(_SPARK))
+    return "".join(_SPARK[k - 1] for k in lv)
+
+
+def describe(state, cols=None):
+    """``describe(state; cols=nothing)`` (utils.jl:183-289) -> DataFrame(variable, mean, median, std, min, max,
+    hist, ess).  Every number is computed on the device (``ws_describe``: fused weighted moments, a radix select
+    for the StatsBase weighted median, an 8-bin weighted histogram); vector columns are described
+    component-wise and have an empty ``hist``, as in the reference."""
+    import pandas as pd
+    st = state.store
+    if st.n == 0:
+        raise ValueError("Store cannot be empty")
+    names = st.colnames() if cols is None else list(cols)
+    for name in names:
+        if st._lookup(name)[0] < 0:
+            raise ValueError(f"Column {name} not found in store")
+    rows = {k: [] for k in ("variable", "mean", "median", "std", "min", "max", "hist", "ess")}
+    if not names:
+        return pd.DataFrame(rows)
+    planes = []
+    for name in names:
+        cid, width = st._lookup(name)
+        planes += [(cid, k) for k in range(width)]
+    ca = (C.c_int32 * len(planes))(*[p[0] for p in planes])
+    ka = (C.c_int32 * len(planes))(*[p[1] for p in planes])
+    out = (L.ws_plane_stats * len(planes))()
+    ess = C.c_double()
+    st._call("ws_describe", len(planes), ca, ka, out, C.byref(ess))
+    i = 0
+    for name in names:
+        cid, width = st._lookup(name)
+        ps = out[i:i + width]
+        i += width
+        rows["variable"].append(name)
+        for f in ("mean", "median", "std", "min", "max"):
+            rows[f].append(getattr(ps[0], f) if width == 1 else np.array([getattr(p, f) for p in ps]))
+        if width == 1:
+            lo, hi = ps[0].min, ps[0].max
+            h = list(ps[0].hist)
+            rows["hist"].append(_sparkline([sum(h)] * 8 if lo == hi else h))
+        else:
+            rows["hist"].append("")
+        rows["ess"].append(ess.value)
+    return pd.DataFrame(rows)

@@ -26,6 +26,7 @@
 #include "ws_internal.h"
 #include "ws_lowering.h"
 #include "ws_move.h"
+#include "ws_stats.h"
 
 using wsl::Plane;
 using wsl::Program;
@@ -468,6 +469,7 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     c->sm_count = prop.multiProcessorCount;
     CKC(ws_kernels_init(device));
     CKC(ws_move_kernels_init(device));
+    CKC(ws_stats_init(device));
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKC(cudaMalloc(&c->logw, sizeof(double) * (size_t)c->n));
     CKC(cudaMalloc(&c->d_partials, sizeof(WsLse) * WS_MAX_PARTIALS));
@@ -2635,6 +2637,51 @@ extern "C" int ws_set_lazy_gather(ws_ctx* c, int on) {
     c->lazy_gather = on != 0;
     return WS_OK;
 }
+extern "C" int ws_describe(ws_ctx* c, int32_t n_planes, const int32_t* col, const int32_t* comp, ws_plane_stats* out, double* ess) {
+    if (!c || !col || !comp || !out || n_planes < 1) return c ? fail(c, WS_EINVAL, "ws_describe: bad arguments") : WS_EINVAL;
+    if (c->nranks > 1) return fail(c, WS_EUNSUPPORTED, "ws_describe on a sharded state is not built yet (download the shards)");
+    for (int t = 0; t < n_planes; ++t) TRY(check_plane(c, col[t], comp[t]));
+    TRY(ensure_reduced(c));  // flushes the window; (m, S, Q) of the current log-weights
+    CK(c, cudaSetDevice(c->device));
+    static_assert(sizeof(ws_plane_stats) == sizeof(WsPlaneStats), "ws_plane_stats layout");
+    const size_t sb = ws_stats_scratch_bytes(c->n);
+    // scratch: [stats partials | q (8 n) | x through the genealogy (8 n)]
+    const size_t q_off = (sb + 255) & ~(size_t)255;
+    TRY(ensure_scratch(c, q_off + 16 * (size_t)c->n));
+    TRY(ensure_h_scratch(c, sb));
+    unsigned long long* d_q = (unsigned long long*)((char*)c->d_scratch + q_off);
+    double* d_x = (double*)(d_q + c->n);
+    CK(c, ws_stats_weights(c->logw, c->d_red, c->logw_uniform ? 1 : 0, c->n, c->n_global, d_q, c->stream));
+    c->stats.kernel_launches++;
+    for (int t = 0; t < n_planes; ++t) {
+        const Column& cl = c->cols[col[t]];
+        const double* x = cl.front[comp[t]];
+        if (cl.stale[comp[t]]) {
+            const int32_t* map = nullptr;
+            TRY(map_for_epoch(c, cl.ep[comp[t]], &map));
+            WsGatherParams G;
+            memset(&G, 0, sizeof(G));
+            G.n = c->n;
+            G.ancestors = map;
+            G.n_planes = 1;
+            G.src[0] = x;
+            G.dst[0] = d_x;
+            TimedEvent te;
+            timed_begin(c, KC_GATHER, te);
+            CK(c, ws_launch_gather(G, grid_for(c, c->n, 256, 8), c->stream));
+            timed_end(c, te);
+            x = d_x;
+        }
+        int launches = 0;
+        WsPlaneStats ps;
+        CK(c, ws_stats_plane(x, d_q, c->n, c->d_scratch, c->h_scratch, c->stream, &ps, &launches));
+        c->stats.kernel_launches += launches;
+        memcpy(&out[t], &ps, sizeof(ps));
+    }
+    if (ess) *ess = (double)c->n_global * c->h_red->ess_perc;
+    return WS_OK;
+}
+
 extern "C" int ws_set_genealogy(ws_ctx* c, int on, int64_t budget_bytes) {
     if (!c) return WS_EINVAL;
     TRY(flush_window(c));

@@ -1,0 +1,18 @@
+// ws_stats.h — describe(state) on the device (ws_kernels_stats.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "ws_internal.h"
+
+struct WsPlaneStats {
+    double mean, median, std, min, max;
+    double hist[8];
+};
+
+cudaError_t ws_stats_init(int device);
+// q[i] = rint(w_i 2^61), w = exp_norm(logw) (or 1/N when the log-weights are uniform)
+cudaError_t ws_stats_weights(const double* logw, const WsReduceOut* red, int uniform, int64_t n, int64_t n_global,
+                             unsigned long long* q, cudaStream_t s);
+size_t ws_stats_scratch_bytes(int64_t n);
+cudaError_t ws_stats_plane(const double* x, const unsigned long long* q, int64_t n, void* d_scratch, void* h_scratch,
+                           cudaStream_t s, WsPlaneStats* out, int* n_launches);
