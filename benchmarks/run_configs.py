@@ -114,6 +114,26 @@ def c2hist():
             del st
 
 
+def hier():
+    """benchmarks/multilevel (hierarchical regression, the accuracy-matched comparison protocol of
+    run_benchmark.py:90-98): elapsed time, rmse of the posterior-mean alpha_j, particle ESS."""
+    configs = ((20, 10),) if QUICK else ((20, 10), (100, 10), (100, 50))
+    for J, n_obs in configs:
+        groups, a_true = models.simulate_hier(J, n_obs)
+        timed_run((1, [[(0.0, 0.0)]]), models.HIER, 50, 0.5)      # warm-up, as run_ws.jl:50-54
+        for n in ((100_000,) if QUICK else (100_000, 1_000_000)):
+            st, dt, le = timed_run((J, groups), models.HIER, n, 0.5)
+            w = ws.exp_norm(st)
+            a_est = np.array([float(np.sum(w * st[f"alpha_{j + 1}"])) for j in range(J)])
+            s = st.stats()
+            emit(config=f"multilevel hierarchical_regression J={J} n_obs={n_obs} N={n}", seconds=dt,
+                 rmse_alpha=float(np.sqrt(np.mean((a_est - a_true) ** 2))), ess=float(1.0 / np.sum(w * w)),
+                 mu_alpha=float(np.sum(w * st["mu_alpha"])), tau_alpha=float(np.sum(w * st["tau_alpha"])),
+                 beta=float(np.sum(w * st["beta"])), sigma=float(np.sum(w * st["sigma"])), truth=[5.0, 2.0, 3.0, 1.0],
+                 log_evidence=le, resamples=s["resamples_done"], moves=s["moves_run"], launches=s["kernel_launches"])
+            del st
+
+
 def c3():
     rng = np.random.default_rng(42)
     npts = 1000 if QUICK else 10_000
@@ -206,6 +226,6 @@ def c5():
 
 
 if __name__ == "__main__":
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "lgssm", "c2hist", "c3", "c4", "c5"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c1", "lgssm", "c2hist", "c3", "c4", "hier", "c5"]
     for w in which:
-        {"c1": c1, "lgssm": lgssm, "c2hist": c2hist, "c3": c3, "c4": c4, "c5": c5}[w]()
+        {"c1": c1, "lgssm": lgssm, "c2hist": c2hist, "hier": hier, "c3": c3, "c4": c4, "c5": c5}[w]()

@@ -69,3 +69,42 @@ end
 
 SCHOOLS_Y = [28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0]
 SCHOOLS_SIGMA = [15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0]
+
+# benchmarks/multilevel/WeightedSampling/model.jl:20-41, verbatim
+HIER = '''
+@model function hierarchical_regression(J, groups)
+    mu_alpha ~ Normal(0.0, 10.0)
+    tau_alpha ~ Exponential(1.0)
+    beta ~ Normal(0.0, 10.0)
+    sigma ~ Exponential(1.0)
+    for j in 1:J
+        alpha{j} ~ Normal(mu_alpha, tau_alpha)
+        obs = groups[j]
+        for (x, y) in obs
+            y => Normal(alpha{j} + beta * x, sigma)
+            if resampled
+                alpha{j} << autoRW(diversity = 0.1)
+            end
+        end      
+        if j % 10 == 0
+            mu_alpha << autoRW(diversity = 0.1)
+            tau_alpha << autoRW(1e-3, (0.0, Inf); diversity = 0.1)
+            beta << autoRW(diversity = 0.1)
+            sigma << autoRW(1e-3, (0.0, Inf); diversity = 0.1)
+        end
+    end
+end
+'''
+
+
+def simulate_hier(J, n_obs, seed=42, mu_alpha=5.0, tau_alpha=2.0, beta=3.0, sigma=1.0):
+    """benchmarks/multilevel/simulate.jl:21-38 (same generative process; NumPy stream instead of Julia's)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    alpha = mu_alpha + tau_alpha * rng.standard_normal(J)
+    groups = []
+    for j in range(J):
+        xs = rng.standard_normal(n_obs)
+        ys = alpha[j] + beta * xs + sigma * rng.standard_normal(n_obs)
+        groups.append([(float(a), float(b)) for a, b in zip(xs, ys)])
+    return groups, alpha

@@ -302,3 +302,36 @@ def test_wide_tape_segmented_move_and_score(ws):
     s_ref = ref.score_logpdf(ost, ["μ"], ost.depth)
     ok = np.abs(state["μ"] - ost.cols["μ"]) < 1e-9
     np.testing.assert_allclose(s_dev[ok], s_ref[ok], rtol=1e-10)
+
+
+def test_hierarchical_regression_benchmark_model(ws):
+    """benchmarks/multilevel/WeightedSampling/model.jl verbatim: nested loops, a build-time `if j % 10 == 0`,
+    `if resampled`-gated moves on a dynamic family (alpha{j}), four diversity-gated global moves, two of them
+    log-transformed.  Replayed against the oracle, then the benchmark's own quality metric under Philox."""
+    import models
+    J, n_obs, n = 10, 3, 3000
+    groups, alpha_true = models.simulate_hier(J, n_obs)
+    root = ws.model(models.HIER)(J, groups)
+    rng = np.random.default_rng(9)
+    streams = dict(normals=rng.standard_normal(n * (2 + J + J * n_obs + 4 + 8)),
+                   uniforms=rng.random(n * (2 * J * n_obs + 4 + 8)), exponentials=rng.standard_exponential(2 * n))
+    st = ws.SMCState(n, device=0)
+    st.set_replay(**streams)
+    ws.run(root, st)
+    ost = ref.OracleState(n, ref.Streams(**streams))
+    ref.run(root, ost)
+    assert st.store.colnames() == ost.names
+    for name in ost.names:
+        d = np.abs(st[name] - ost.cols[name]) > 1e-8 * (1 + np.abs(ost.cols[name]))
+        assert d.mean() < 0.01, (name, d.mean())
+    assert abs(ws.log_evidence(st) - ref.log_evidence(ost)) < 1e-6 * abs(ref.log_evidence(ost))
+    # benchmark protocol (run_ws.jl:41-75): rmse of the posterior-mean alpha_j against the simulated truth
+    J2, n2 = 20, 10
+    groups2, a_true = models.simulate_hier(J2, n2)
+    sp = ws.SMCState(200_000, seed=1, device=0)
+    ws.run(ws.model(models.HIER)(J2, groups2), sp)
+    w = ws.exp_norm(sp)
+    a_est = np.array([float(np.sum(w * sp[f"alpha_{j + 1}"])) for j in range(J2)])
+    rmse = float(np.sqrt(np.mean((a_est - a_true) ** 2)))
+    assert rmse < 0.6, rmse                                   # posterior sd of alpha_j is ~ sigma / sqrt(10) = 0.32
+    assert abs(float(np.sum(w * sp["beta"])) - 3.0) < 0.3 and abs(float(np.sum(w * sp["sigma"])) - 1.0) < 0.3
