@@ -24,7 +24,11 @@ end
 WsResampleInfo() = WsResampleInfo(0, 0, NaN, NaN, 0)
 
 const TOK_CONST, TOK_PLANE, TOK_ADD, TOK_SUB, TOK_MUL, TOK_DIV, TOK_NEG, TOK_EXP, TOK_LOG, TOK_SQRT, TOK_SQUARE,
-      TOK_SIN, TOK_COS, TOK_ABS, TOK_POW = Int32.(0:14)
+      TOK_SIN, TOK_COS, TOK_ABS, TOK_POW, TOK_RANDN, TOK_RANDU, TOK_RANDEXP, TOK_LT, TOK_LE, TOK_EQ, TOK_SELECT,
+      TOK_MIN, TOK_MAX, TOK_NOT, TOK_LGAMMA, TOK_LOG1P, TOK_EXPM1, TOK_TAN, TOK_ATAN, TOK_TANH, TOK_FLOOR = Int32.(0:31)
+struct WsPlaneStats
+    mean::Float64; median::Float64; std::Float64; min::Float64; max::Float64; hist::NTuple{8,Float64}
+end
 
 function check(ctx, rc)
     rc == 0 && return nothing
@@ -103,6 +107,19 @@ Base.:+(a::DeviceExpr, b::DeviceExpr) = binop(TOK_ADD, a, b)
 Base.:-(a::DeviceExpr, b::DeviceExpr) = binop(TOK_SUB, a, b)
 Base.:*(a::DeviceExpr, b::DeviceExpr) = binop(TOK_MUL, a, b)
 Base.:/(a::DeviceExpr, b::DeviceExpr) = binop(TOK_DIV, a, b)
+unop(op, a::DeviceExpr) = DeviceExpr(vcat(a.toks, WsTok(op, 0, 0, 0, 0.0)))
+Base.exp(a::DeviceExpr) = unop(TOK_EXP, a); Base.log(a::DeviceExpr) = unop(TOK_LOG, a)
+Base.sqrt(a::DeviceExpr) = unop(TOK_SQRT, a); Base.cos(a::DeviceExpr) = unop(TOK_COS, a); Base.sin(a::DeviceExpr) = unop(TOK_SIN, a)
+Base.:<(a::DeviceExpr, b::DeviceExpr) = binop(TOK_LT, a, b)          # Bool columns are 1.0 / 0.0 planes
+Base.:<=(a::DeviceExpr, b::DeviceExpr) = binop(TOK_LE, a, b)
+Base.:|(a::DeviceExpr, b::DeviceExpr) = binop(TOK_MAX, a, b)          # a || b
+Base.:&(a::DeviceExpr, b::DeviceExpr) = binop(TOK_MIN, a, b)          # a && b
+Base.:!(a::DeviceExpr) = unop(TOK_NOT, a)
+# ifelse.(c, a, b): what `vectorize` makes of `c ? a : b` on particle variables (src/rewrites.jl:193-199)
+Base.ifelse(c::DeviceExpr, a::DeviceExpr, b::DeviceExpr) = DeviceExpr(vcat(c.toks, a.toks, b.toks, WsTok(TOK_SELECT, 0, 0, 0, 0.0)))
+randn_tok() = DeviceExpr([WsTok(TOK_RANDN, 0, 0, 0, 0.0)])            # fresh variates inside a sampler expression
+randu_tok() = DeviceExpr([WsTok(TOK_RANDU, 0, 0, 0, 0.0)])
+randexp_tok() = DeviceExpr([WsTok(TOK_RANDEXP, 0, 0, 0, 0.0)])
 cexpr(e::DeviceExpr) = WsExpr(pointer(e.toks), length(e.toks), 0)
 
 # ---- device statements: each apply! is one ccall -----------------------------------------------------------
@@ -135,6 +152,25 @@ function apply!(::Resample, state::SMCState{DeviceColumnStore})                #
     end
     return nothing
 end
+# A WeightedKernel(sampler, weighter, logpdf) (src/types.jl:226-230) whose three parts are device expressions:
+# `x ~ K(args...)` is one ccall; the library samples, weights and records logpdf on its score tape.
+struct DeviceSampleExpr <: ParticleTransformer
+    col::Int32; comp::Int32; sampler::DeviceExpr; weighter::Union{DeviceExpr,Nothing}; logpdf::Union{DeviceExpr,Nothing}
+end
+function apply!(t::DeviceSampleExpr, state::SMCState{DeviceColumnStore})      # src/transformers.jl:172-182
+    GC.@preserve t begin
+        w = t.weighter === nothing ? C_NULL : Ref(cexpr(t.weighter))
+        l = t.logpdf === nothing ? C_NULL : Ref(cexpr(t.logpdf))
+        check(ctx(state), ccall((:ws_sample_expr, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ref{WsExpr}, Ptr{WsExpr}, Ptr{WsExpr}),
+                                ctx(state), t.col, t.comp, cexpr(t.sampler), w, l))
+    end
+    t.weighter === nothing || (state.weights_changed = true)
+    state.depth += 1
+end
+# e.g. default_kernels.Uniform (src/default_kernels.jl:101) as device expressions:
+#   sampler  (a, b)    -> a + (b - a) * randu_tok()
+#   logpdf   (a, b, x) -> ifelse((a <= x) & (x <= b), -log(b - a), DeviceExpr(-Inf))
+
 # score! of the device statements is a no-op on the host: the library records the tape itself and
 # ws_move folds it (device form of the score! walk).
 score!(::Union{DeviceAssign,DeviceSampleNormal,DeviceObserveNormal}, state, c) = (c.depth += 1; nothing)
@@ -150,5 +186,20 @@ function exp_norm(state::SMCState{DeviceColumnStore})
     check(ctx(state), ccall((:ws_exp_norm, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), ctx(state), out))
     out
 end
+
+# describe(state) (src/utils.jl:183-289): every statistic, including the StatsBase weighted median, is computed
+# on the device; 13 numbers per plane come back
+function describe_plane(state::SMCState{DeviceColumnStore}, name::Symbol, comp::Integer=0)
+    id, _ = lookup(state.store, name)
+    out = Ref(WsPlaneStats(0, 0, 0, 0, 0, ntuple(_ -> 0.0, 8))); ess = Ref(0.0)
+    check(ctx(state), ccall((:ws_describe, LIB), Cint, (Ptr{Cvoid}, Int32, Ref{Int32}, Ref{Int32}, Ref{WsPlaneStats}, Ref{Float64}),
+                            ctx(state), 1, Ref(Int32(id)), Ref(Int32(comp)), out, ess))
+    out[], ess[]
+end
+
+# trajectory storage by genealogy: columns that are not read keep their order and the ancestor vectors are kept
+# instead (include/wsb200.h: ws_set_genealogy); on by default, nothing to do for a model that keeps x{t}
+set_genealogy!(state::SMCState{DeviceColumnStore}, on::Bool; budget_bytes::Integer=0) =
+    check(ctx(state), ccall((:ws_set_genealogy, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), ctx(state), on, budget_bytes))
 
 end # module
