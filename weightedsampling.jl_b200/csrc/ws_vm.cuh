@@ -113,25 +113,28 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
     const double* const Rb = R + b * (P * STRIDE);
     const double* const Rc = R + c * (P * STRIDE);
     const double k0 = o.k0, k1 = o.k1, k2 = o.k2;
-    switch (op) {
-        case WS_OP_LIN2: {
-            if (a == WS_REG_NONE && b == WS_REG_NONE) {
+    // r = k0 + k1 a + k2 b is most of every program (sums, affine means, Cholesky rows, residuals): decided
+    // by one compare instead of a walk down the switch's decision tree
+    if (op == WS_OP_LIN2) {
+        if (a == WS_REG_NONE && b == WS_REG_NONE) {
 #pragma unroll
-                for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0;
-            } else if (a == WS_REG_NONE) {
+            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0;
+        } else if (a == WS_REG_NONE) {
 #pragma unroll
-                for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k2 * Rb[j * STRIDE];
-            } else if (b == WS_REG_NONE) {
+            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k2 * Rb[j * STRIDE];
+        } else if (b == WS_REG_NONE) {
 #pragma unroll
-                for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k1 * Ra[j * STRIDE];
-            } else {
+            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k1 * Ra[j * STRIDE];
+        } else {
 #pragma unroll
-                for (int j = 0; j < P; ++j) {
-                    double v = k0 + k1 * Ra[j * STRIDE];
-                    Rd[j * STRIDE] = v + k2 * Rb[j * STRIDE];
-                }
+            for (int j = 0; j < P; ++j) {
+                double v = k0 + k1 * Ra[j * STRIDE];
+                Rd[j * STRIDE] = v + k2 * Rb[j * STRIDE];
             }
-        } break;
+        }
+        return;
+    }
+    switch (op) {
         case WS_OP_MUL: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
