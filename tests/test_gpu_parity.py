@@ -415,3 +415,40 @@ def test_api_surface(ws):
     w = ws.exp_norm(st)
     assert abs(w.sum() - 1.0) < 1e-12 and abs(ws.ess_perc(st) - 1.0) < 1e-12
     assert "SMCState(n_particles=100000" in repr(st)
+
+
+def test_multinomial_resampling_inside_run(ws):
+    """multinomial = icdf over sort(N iid uniforms).  Replay against the oracle, then the
+    Philox path: offspring counts are unbiased and noisier than stratified ones."""
+    n, T = 5000, 8
+    rng = np.random.default_rng(12)
+    ys = list(rng.normal(size=T))
+    import models
+    root = ws.model(models.LGSSM1D)(ys, 0.9, 1.0, 0.5, 1.0)
+    state, ost = _replay_run(ws, root, n, normals=rng.standard_normal(n * (T + 1)), uniforms=rng.random(n * T), ess=1.0,
+                             resampler="multinomial")
+    assert state.stats()["resamples_done"] == sum(1 for e in ost.log if e["resampled"]) == T
+    _compare_states(state, ost, max_bad=3)
+    assert abs(ws.log_evidence(state) - ref.log_evidence(ost)) <= REL * abs(ref.log_evidence(ost))
+    # Philox draws: E[offspring of m] = N w_m; variance of the count of a particle with N w = 1 is ~1 (multinomial)
+    # against < 1/4 for the stratified scheme
+    n2 = 200_000
+    lw = 0.7 * rng.normal(size=n2)
+    counts = {}
+    for scheme in ("multinomial", "stratified"):
+        st = ws.SMCState(n2, ess_perc_min=float("inf"), seed=3, resampler=scheme, device=0)
+        st.store.setcol("id", np.arange(n2, dtype=np.float64))
+        st.weights = lw
+        st.weights_changed = True
+        ws.Resample().apply(st)
+        ids = st["id"].astype(np.int64)
+        assert np.all(np.diff(ids) >= 0)
+        counts[scheme] = np.bincount(ids, minlength=n2)
+    w = ref.exp_norm(lw)
+    for scheme, c in counts.items():
+        assert c.sum() == n2
+        assert abs(np.sum(c * np.arange(n2)) / n2 - np.sum(w * np.arange(n2))) < 600.0     # weighted mean of the index
+    resid_m = counts["multinomial"] - n2 * w
+    resid_s = counts["stratified"] - n2 * w
+    assert 0.7 < resid_m.var() / np.mean(n2 * w * (1 - w)) < 1.3                           # multinomial variance
+    assert resid_s.var() < 0.5 * resid_m.var()

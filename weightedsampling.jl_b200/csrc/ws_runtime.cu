@@ -1718,8 +1718,8 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
         info->n_clamped = -1;  // cumulative count is reported by ws_get_clamped (needs a sync)
     }
     if (!c->weights_changed) return WS_OK;  // `resampled` keeps its previous value (transformers.jl:475-477)
-    if (c->resampler == WS_RESAMPLER_MULTINOMIAL)
-        return fail(c, WS_EUNSUPPORTED, "multinomial resampling inside run! is not built yet (use ws_resample_host)");
+    if (c->resampler == WS_RESAMPLER_MULTINOMIAL && c->nranks > 1)
+        return fail(c, WS_EUNSUPPORTED, "multinomial resampling of a sharded state is not built (stratified / systematic are)");
     TRY(ensure_reduced(c));
     c->stats.resamples_fired++;
     const WsReduceOut r = *c->h_red;
@@ -1755,7 +1755,20 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
         const uint64_t stream_id = c->next_stream++;
         // planes still in an older order keep their ancestor vectors (genealogy) or are gathered now
         TRY(begin_resample_event(c));
-        TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, nullptr, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id, c->d_counters + 0));
+        const double* d_sorted = nullptr;
+        if (c->resampler == WS_RESAMPLER_MULTINOMIAL) {
+            // u = sort(N iid uniforms): replayed or Philox draws, radix-sorted on the device
+            const size_t tb = ws_sort_temp_bytes(c->n);
+            const size_t off = (16 * (size_t)c->n + 255) & ~(size_t)255;
+            TRY(ensure_scratch(c, off + tb));
+            double* raw = c->d_scratch;
+            double* sorted = c->d_scratch + c->n;
+            CK(c, ws_sorted_uniforms(d_ru, raw, sorted, c->n, c->seed, stream_id, (char*)c->d_scratch + off, tb, c->stream));
+            c->stats.kernel_launches += 2;
+            d_sorted = sorted;
+            d_ru = nullptr;
+        }
+        TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, d_sorted, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id, c->d_counters + 0));
         // resample!(store, indices) is deferred: each plane is gathered when it is next read
         end_resample_event(c);
         if (!c->lazy_gather) TRY(materialize_planes(c));
