@@ -25,6 +25,7 @@ struct HH {
     int64_t cur_n = 0, cur_u = 0, cur_e = 0;
     std::vector<double> rn, ru, re;
     std::vector<int32_t> tape_end;
+    std::vector<double> tape_const;  // Program::acc_const after each tape entry
     int n_flush = 0;
     std::string err;
 };
@@ -134,6 +135,7 @@ static int finish(HH* h, Program& p) {
 static void tape(HH* h) {
     h->score.end_statement();
     h->tape_end.push_back((int32_t)h->score.ops.size());
+    h->tape_const.push_back(h->score.acc_const);
 }
 
 int hh_assign(HH* h, int col, int comp, const ws_expr* rhs) {
@@ -218,6 +220,7 @@ void hh_get_logw(HH* h, double* out) {
     memcpy(out, h->logw.data(), sizeof(double) * h->n);
 }
 int hh_tape_len(HH* h) { return (int)h->tape_end.size(); }
+int hh_score_ops(HH* h) { return (int)h->score.ops.size(); }
 // fold the first n_entries tape entries at the current column values
 int hh_score(HH* h, int n_entries, double* out) {
     hh_flush(h);
@@ -228,6 +231,8 @@ int hh_score(HH* h, int n_entries, double* out) {
     Program& p = h->score;
     std::vector<Plane> saved_dirty = p.dirty;
     run_program(h, p, &acc, n_ops);
+    const double konst = n_entries <= 0 ? 0.0 : h->tape_const[(size_t)n_entries - 1];
+    for (auto& v : acc) v += konst;
     memcpy(out, acc.data(), sizeof(double) * h->n);
     return 0;
 }

@@ -134,3 +134,26 @@ def test_golden_ssm2d_without_resampling_prefix():
     ref.run(root, ost)
     np.testing.assert_allclose(hs.store.getcol("x_2"), ost.cols["x_2"], rtol=1e-14)
     np.testing.assert_allclose(hs.store.logw(), ost.weights, rtol=1e-12)
+
+
+def test_score_tape_fuses_normal_terms_into_one_op():
+    """alpha + beta * x_i with constant sigma (C3's likelihood): one ACC_SQLIN2 per observation on the score tape,
+    the constant kept aside; the fold still equals the sum of Normal log-densities."""
+    n = 200
+    rng = np.random.default_rng(5)
+    xs, ys = rng.uniform(0, 10, 7), rng.normal(size=7)
+    root = strip_resample(ws.model(models.LINREG)(xs, ys))
+    normals = rng.standard_normal(2 * n)
+    hs = HostState(n)
+    hs.store.set_replay(normals=normals)
+    root.apply(hs)
+    L, h = hs.store.L, hs.store.h
+    L.hh_score_ops.argtypes = [C.c_void_p]
+    assert L.hh_score_ops(h) == 2 + 7                      # two priors + one op per observation
+    a, b = hs.store.getcol("α"), hs.store.getcol("β")
+    want = ref.normal_logpdf(a, 0.0, 10.0) + ref.normal_logpdf(b, 0.0, 10.0)
+    for x, y in zip(xs, ys):
+        want = want + ref.normal_logpdf(y, a + b * x, 1.0)
+    np.testing.assert_allclose(hs.store.score(hs.store.tape_len()), want, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(hs.store.score(3), ref.normal_logpdf(a, 0.0, 10.0) + ref.normal_logpdf(b, 0.0, 10.0)
+                               + ref.normal_logpdf(ys[0], a + b * xs[0], 1.0), rtol=1e-12, atol=1e-12)

@@ -27,22 +27,26 @@ __device__ __forceinline__ WsOp ws_load_op(const WsOp* __restrict__ ops, int pc)
     return o;
 }
 
-__device__ __forceinline__ void ws_score_load_planes(const WsScoreParams& S, double* R, int64_t i) {
-    int k = 0;
-    for (; k + 4 <= S.n_loads; k += 4) {
-        double t0 = __ldg(S.load_ptr[k] + i), t1 = __ldg(S.load_ptr[k + 1] + i);
-        double t2 = __ldg(S.load_ptr[k + 2] + i), t3 = __ldg(S.load_ptr[k + 3] + i);
-        R[(int)S.load_reg[k] * WS_MOVE_BLOCK] = t0;
-        R[(int)S.load_reg[k + 1] * WS_MOVE_BLOCK] = t1;
-        R[(int)S.load_reg[k + 2] * WS_MOVE_BLOCK] = t2;
-        R[(int)S.load_reg[k + 3] * WS_MOVE_BLOCK] = t3;
+// P particles per thread: particle j of a thread is element tile*P*BLOCK + j*BLOCK + tid (coalesced), register r of
+// particle j lives at R[(r*P + j)*BLOCK].  One decoded tape entry is applied to P particles, which is what makes a
+// long fold cheap: the interpreter's decode (~30 instructions) dwarfs the 3-4 FP64 operations of a term.
+template <int P>
+__device__ __forceinline__ void ws_score_load_planes(const WsScoreParams& S, double* R, const int64_t (&idx)[P]) {
+    for (int k = 0; k < S.n_loads; ++k) {
+        const double* __restrict__ ptr = S.load_ptr[k];
+        double t[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) t[j] = __ldg(ptr + idx[j]);
+        double* dst = R + (int)S.load_reg[k] * (P * WS_MOVE_BLOCK);
+#pragma unroll
+        for (int j = 0; j < P; ++j) dst[j * WS_MOVE_BLOCK] = t[j];
     }
-    for (; k < S.n_loads; ++k) R[(int)S.load_reg[k] * WS_MOVE_BLOCK] = __ldg(S.load_ptr[k] + i);
 }
 
-__device__ __forceinline__ double ws_score_fold(const WsScoreParams& S, double* R, uint64_t particle) {
-    double acc[1] = {0.0};
-    const uint64_t pid[1] = {particle};
+template <int P>
+__device__ __forceinline__ void ws_score_fold(const WsScoreParams& S, double* R, const uint64_t (&pid)[P], double (&acc)[P]) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) acc[j] = 0.0;
     WsRng none;
     none.seed = 0;
     none.replay_n = nullptr;
@@ -50,98 +54,136 @@ __device__ __forceinline__ double ws_score_fold(const WsScoreParams& S, double* 
     none.replay_e = nullptr;
     for (int pc = 0; pc < S.n_ops; ++pc) {
         const WsOp o = ws_load_op(S.ops, pc);
-        ws_vm_exec<WS_MOVE_BLOCK, 1>(o, R, acc, none, pid);
+        ws_vm_exec<WS_MOVE_BLOCK, P>(o, R, acc, none, pid);
     }
-    return acc[0];
 }
 
+template <int P>
+__device__ __forceinline__ void ws_tile_indices(int64_t tile, int64_t n, int64_t offset, int64_t (&idx)[P], bool (&live)[P],
+                                                uint64_t (&pid)[P]) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int64_t i = tile * (P * WS_MOVE_BLOCK) + (int64_t)j * WS_MOVE_BLOCK + threadIdx.x;
+        live[j] = i < n;
+        idx[j] = live[j] ? i : n - 1;
+        pid[j] = (uint64_t)(offset + idx[j]);
+    }
+}
+
+template <int P>
 __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_score_kernel(const __grid_constant__ WsScoreParams S) {
     extern __shared__ double ws_score_smem[];
     double* R = ws_score_smem + threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * WS_MOVE_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * WS_MOVE_BLOCK + threadIdx.x; i < S.n; i += stride) {
-        ws_score_load_planes(S, R, i);
-        S.score_out[i] = ws_score_fold(S, R, (uint64_t)(S.particle_offset + i));
+    const int64_t n_tiles = (S.n + P * WS_MOVE_BLOCK - 1) / (P * WS_MOVE_BLOCK);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t idx[P];
+        bool live[P];
+        uint64_t pid[P];
+        ws_tile_indices<P>(tile, S.n, S.particle_offset, idx, live, pid);
+        ws_score_load_planes<P>(S, R, idx);
+        double acc[P];
+        ws_score_fold<P>(S, R, pid, acc);
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+            if (live[j]) S.score_out[idx[j]] = acc[j] + S.konst;
     }
 }
 
+// Rows [0, n_regs) of the register file are the score program's registers, rows [n_regs, n_regs + d) hold the
+// proposed target values of the thread's P particles.
+template <int P>
 __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_kernel(const __grid_constant__ WsMoveParams M) {
     extern __shared__ double ws_score_smem[];
     double* R = ws_score_smem + threadIdx.x;
+    constexpr int RS = P * WS_MOVE_BLOCK;
     const WsScoreParams& S = M.score;
     const int d = M.d;
+    double* const Xn = R + S.n_regs * RS;
     unsigned long long accepted = 0ull;
-    const int64_t stride = (int64_t)gridDim.x * WS_MOVE_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * WS_MOVE_BLOCK + threadIdx.x; i < S.n; i += stride) {
-        const uint64_t particle = (uint64_t)(S.particle_offset + i);
-        ws_score_load_planes(S, R, i);
+    const int64_t n_tiles = (S.n + RS - 1) / RS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t idx[P];
+        bool live[P];
+        uint64_t pid[P];
+        ws_tile_indices<P>(tile, S.n, S.particle_offset, idx, live, pid);
+        ws_score_load_planes<P>(S, R, idx);
 
-        // ---- current values, unconstrained coordinates, proposal ---------------------------------
-        double x_old[WS_MOVE_MAX_D], z_old[WS_MOVE_MAX_D], xi[WS_MOVE_MAX_D], x_new[WS_MOVE_MAX_D];
+        // ---- current values, unconstrained coordinates, proposal (one particle at a time) -----------
+        double lpr[P];
+#pragma unroll 1
+        for (int j = 0; j < P; ++j) {
+            const int64_t i = idx[j];
+            const uint64_t particle = pid[j];
+            double z_old[WS_MOVE_MAX_D], xi[WS_MOVE_MAX_D];
 #pragma unroll
-        for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
-            if (t < d) {
-                x_old[t] = M.target_ptr[t][i];
-                z_old[t] = ws_to_unconstrained(x_old[t], M.lo[t], M.hi[t], M.bound_kind[t]);
+            for (int t = 0; t < WS_MOVE_MAX_D; ++t)
+                if (t < d) z_old[t] = ws_to_unconstrained(M.target_ptr[t][i], M.lo[t], M.hi[t], M.bound_kind[t]);
+            if (M.rng.replay_n != nullptr) {
+#pragma unroll
+                for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
+                    if (t < d) {
+                        const int64_t ri = M.normals_target_major ? (M.replay_n_base + (int64_t)t * M.n_global + (int64_t)particle)
+                                                                  : (M.replay_n_base + (int64_t)particle * d + t);
+                        xi[t] = M.rng.replay_n[ri];
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int t = 0; t < WS_MOVE_MAX_D; t += 2) {
+                    if (t < d) {
+                        double a, b;
+                        ws_randn2(particle, M.stream_normals + (uint64_t)(t >> 1), M.rng.seed, a, b);
+                        xi[t] = a;
+                        if (t + 1 < WS_MOVE_MAX_D) xi[t + 1] = b;
+                    }
+                }
             }
-        }
-        if (M.rng.replay_n != nullptr) {
+            double l = 0.0;
 #pragma unroll
             for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
                 if (t < d) {
-                    const int64_t idx = M.normals_target_major ? (M.replay_n_base + (int64_t)t * M.n_global + (int64_t)particle)
-                                                               : (M.replay_n_base + (int64_t)particle * d + t);
-                    xi[t] = M.rng.replay_n[idx];
+                    // sequential, un-contracted sum so that a replayed proposal is bit-identical to
+                    // the reference's  z .+ (L * xi)  (no FMA in Julia)
+                    double delta = __dmul_rn(M.L[t * d], xi[0]);
+#pragma unroll
+                    for (int k = 1; k < WS_MOVE_MAX_D; ++k)
+                        if (k <= t && k < d) delta = __dadd_rn(delta, __dmul_rn(M.L[t * d + k], xi[k]));
+                    const double zn = __dadd_rn(z_old[t], delta);
+                    Xn[t * RS + j * WS_MOVE_BLOCK] = ws_from_unconstrained(zn, M.lo[t], M.hi[t], M.bound_kind[t]);
+                    l += ws_log_abs_jacobian(zn, M.lo[t], M.hi[t], M.bound_kind[t]) -
+                         ws_log_abs_jacobian(z_old[t], M.lo[t], M.hi[t], M.bound_kind[t]);
                 }
             }
-        } else {
-#pragma unroll
-            for (int t = 0; t < WS_MOVE_MAX_D; t += 2) {
-                if (t < d) {
-                    double a, b;
-                    ws_randn2(particle, M.stream_normals + (uint64_t)(t >> 1), M.rng.seed, a, b);
-                    xi[t] = a;
-                    if (t + 1 < WS_MOVE_MAX_D) xi[t + 1] = b;
-                }
-            }
-        }
-        double lpr = 0.0;
-#pragma unroll
-        for (int t = 0; t < WS_MOVE_MAX_D; ++t) {
-            if (t < d) {
-                // sequential, un-contracted sum so that a replayed proposal is bit-identical to
-                // the reference's  z .+ (L * xi)  (no FMA in Julia)
-                double delta = __dmul_rn(M.L[t * d], xi[0]);
-#pragma unroll
-                for (int k = 1; k < WS_MOVE_MAX_D; ++k)
-                    if (k <= t && k < d) delta = __dadd_rn(delta, __dmul_rn(M.L[t * d + k], xi[k]));
-                const double zn = __dadd_rn(z_old[t], delta);
-                x_new[t] = ws_from_unconstrained(zn, M.lo[t], M.hi[t], M.bound_kind[t]);
-                lpr += ws_log_abs_jacobian(zn, M.lo[t], M.hi[t], M.bound_kind[t]) -
-                       ws_log_abs_jacobian(z_old[t], M.lo[t], M.hi[t], M.bound_kind[t]);
-            }
+            lpr[j] = l;
         }
 
         // ---- trace density at the old and at the proposed values ------------------------------------
-        const double s_old = ws_score_fold(S, R, particle);
+        double s_old[P], s_new[P];
+        ws_score_fold<P>(S, R, pid, s_old);
+        for (int t = 0; t < d; ++t) {
+            if (M.target_reg[t] != 0xFF) {
+                double* dst = R + (int)M.target_reg[t] * RS;
 #pragma unroll
-        for (int t = 0; t < WS_MOVE_MAX_D; ++t)
-            if (t < d && M.target_reg[t] != 0xFF) R[(int)M.target_reg[t] * WS_MOVE_BLOCK] = x_new[t];
-        const double s_new = ws_score_fold(S, R, particle);
+                for (int j = 0; j < P; ++j) dst[j * WS_MOVE_BLOCK] = Xn[t * RS + j * WS_MOVE_BLOCK];
+            }
+        }
+        ws_score_fold<P>(S, R, pid, s_new);
 
         // ---- accept / reject (NaN ratio rejects: !(log u < ...)) ---------------------------------------
-        double u;
-        if (M.rng.replay_u != nullptr) {
-            u = M.rng.replay_u[M.replay_u_base + (int64_t)particle];
-        } else {
-            ws_u32x4 r = ws_philox4x32_10(particle, M.stream_uniform, M.rng.seed);
-            u = ws_u01(r.x, r.y);
-        }
-        if (log(u) < lpr + s_new - s_old) {
 #pragma unroll
-            for (int t = 0; t < WS_MOVE_MAX_D; ++t)
-                if (t < d) M.target_ptr[t][i] = x_new[t];
-            ++accepted;
+        for (int j = 0; j < P; ++j) {
+            if (!live[j]) continue;
+            double u;
+            if (M.rng.replay_u != nullptr) {
+                u = M.rng.replay_u[M.replay_u_base + (int64_t)pid[j]];
+            } else {
+                ws_u32x4 r = ws_philox4x32_10(pid[j], M.stream_uniform, M.rng.seed);
+                u = ws_u01(r.x, r.y);
+            }
+            if (log(u) < lpr[j] + s_new[j] - s_old[j]) {
+                for (int t = 0; t < d; ++t) M.target_ptr[t][idx[j]] = Xn[t * RS + j * WS_MOVE_BLOCK];
+                ++accepted;
+            }
         }
     }
     // one atomic per warp
@@ -216,17 +258,19 @@ __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_delta_kernel(const __gr
     const WsScoreParams& S = M.score;
     const int64_t stride = (int64_t)gridDim.x * WS_MOVE_BLOCK;
     for (int64_t i = (int64_t)blockIdx.x * WS_MOVE_BLOCK + threadIdx.x; i < S.n; i += stride) {
-        const uint64_t particle = (uint64_t)(S.particle_offset + i);
-        ws_score_load_planes(S, R, i);
-        const double s_old = ws_score_fold(S, R, particle);
+        const uint64_t pid[1] = {(uint64_t)(S.particle_offset + i)};
+        const int64_t idx[1] = {i};
+        ws_score_load_planes<1>(S, R, idx);
+        double s_old[1], s_new[1];
+        ws_score_fold<1>(S, R, pid, s_old);
         if (mode == 0) {
-            out[i] += s_old;
+            out[i] += s_old[0] + S.konst;
         } else {
 #pragma unroll
             for (int t = 0; t < WS_MOVE_MAX_D; ++t)
                 if (t < M.d && M.target_reg[t] != 0xFF) R[(int)M.target_reg[t] * WS_MOVE_BLOCK] = x_new[(size_t)t * S.n + i];
-            const double s_new = ws_score_fold(S, R, particle);
-            out[i] += s_new - s_old;
+            ws_score_fold<1>(S, R, pid, s_new);
+            out[i] += s_new[0] - s_old[0];
         }
     }
 }
@@ -375,26 +419,44 @@ __global__ void __launch_bounds__(256) ws_unique_count_kernel(const double* __re
 // ------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------
-static int score_grid(int n_regs, int64_t n, int sm_count) {
-    const int smem = n_regs * WS_MOVE_BLOCK * (int)sizeof(double) + 256;
+static int score_grid(int rows, int P, int64_t n, int sm_count) {
+    const int smem = rows * P * WS_MOVE_BLOCK * (int)sizeof(double) + 256;
     int per_sm = (227 * 1024) / smem;
     if (per_sm > 2048 / WS_MOVE_BLOCK) per_sm = 2048 / WS_MOVE_BLOCK;
     if (per_sm < 1) per_sm = 1;
-    int64_t g = (n + WS_MOVE_BLOCK - 1) / WS_MOVE_BLOCK;
+    int64_t g = (n + (int64_t)P * WS_MOVE_BLOCK - 1) / ((int64_t)P * WS_MOVE_BLOCK);
     if (g > (int64_t)per_sm * sm_count) g = (int64_t)per_sm * sm_count;
     if (g < 1) g = 1;
     return (int)g;
 }
 
+// particles per thread of a fold: as many as keep at least four CTAs (16 warps) resident per SM
+static int score_particles_per_thread(int rows) {
+    const int row_bytes = WS_MOVE_BLOCK * (int)sizeof(double);
+    if (rows * 4 * row_bytes <= 56 * 1024) return 4;
+    if (rows * 2 * row_bytes <= 56 * 1024) return 2;
+    return 1;
+}
+
 cudaError_t ws_launch_score(const WsScoreParams& S, int sm_count, cudaStream_t s) {
-    const int smem = S.n_regs * WS_MOVE_BLOCK * (int)sizeof(double);
-    ws_score_kernel<<<score_grid(S.n_regs, S.n, sm_count), WS_MOVE_BLOCK, smem, s>>>(S);
+    const int rows = S.n_regs;
+    const int P = score_particles_per_thread(rows);
+    const int smem = rows * P * WS_MOVE_BLOCK * (int)sizeof(double);
+    const int g = score_grid(rows, P, S.n, sm_count);
+    if (P == 4) ws_score_kernel<4><<<g, WS_MOVE_BLOCK, smem, s>>>(S);
+    else if (P == 2) ws_score_kernel<2><<<g, WS_MOVE_BLOCK, smem, s>>>(S);
+    else ws_score_kernel<1><<<g, WS_MOVE_BLOCK, smem, s>>>(S);
     return cudaGetLastError();
 }
 
 cudaError_t ws_launch_move(const WsMoveParams& M, int sm_count, cudaStream_t s) {
-    const int smem = M.score.n_regs * WS_MOVE_BLOCK * (int)sizeof(double);
-    ws_move_kernel<<<score_grid(M.score.n_regs, M.score.n, sm_count), WS_MOVE_BLOCK, smem, s>>>(M);
+    const int rows = M.score.n_regs + M.d;  // score registers + proposed target values
+    const int P = score_particles_per_thread(rows);
+    const int smem = rows * P * WS_MOVE_BLOCK * (int)sizeof(double);
+    const int g = score_grid(rows, P, M.score.n, sm_count);
+    if (P == 4) ws_move_kernel<4><<<g, WS_MOVE_BLOCK, smem, s>>>(M);
+    else if (P == 2) ws_move_kernel<2><<<g, WS_MOVE_BLOCK, smem, s>>>(M);
+    else ws_move_kernel<1><<<g, WS_MOVE_BLOCK, smem, s>>>(M);
     return cudaGetLastError();
 }
 
@@ -407,7 +469,7 @@ cudaError_t ws_launch_move_propose(const WsMoveParams& M, double* x_new, double*
 }
 cudaError_t ws_launch_move_delta(const WsMoveParams& M, int mode, const double* x_new, double* out, int sm_count, cudaStream_t s) {
     const int smem = M.score.n_regs * WS_MOVE_BLOCK * (int)sizeof(double);
-    ws_move_delta_kernel<<<score_grid(M.score.n_regs, M.score.n, sm_count), WS_MOVE_BLOCK, smem, s>>>(M, mode, x_new, out);
+    ws_move_delta_kernel<<<score_grid(M.score.n_regs, 1, M.score.n, sm_count), WS_MOVE_BLOCK, smem, s>>>(M, mode, x_new, out);
     return cudaGetLastError();
 }
 cudaError_t ws_launch_move_accept(const WsMoveParams& M, const double* x_new, const double* lpr, const double* delta, int sm_count,
@@ -446,9 +508,17 @@ cudaError_t ws_launch_unique_count(const double* plane, int64_t n, unsigned long
 
 cudaError_t ws_move_kernels_init(int device) {
     (void)device;
-    cudaError_t e = cudaFuncSetAttribute(ws_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(ws_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_score_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_move_delta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ws_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024);
+    e = cudaFuncSetAttribute(ws_move_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_move_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ws_move_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
 }

@@ -64,6 +64,15 @@ struct Program {
     int next_temp = 0;  // score mode
     int high_water = 0; // registers actually used
     bool has_acc = false;
+    // score programs: particle-independent part of the log-densities lowered so far (kept out of the
+    // micro-ops: it is one scalar per tape prefix, and it cancels in a Metropolis-Hastings ratio)
+    double acc_const = 0.0;
+    // score programs: (1/sigma, log sigma) of a plane used as a Normal's sigma, computed once per fold in
+    // persistent registers (a hierarchical model scores hundreds of terms with the same per-particle sigma)
+    std::map<int, std::pair<int, int>> sigma_cache;
+    std::vector<int> sigma_log;
+    size_t stmt_begin_ops = 0;  // ops.size() when the current statement started
+    int stmt_cache_ops = 0;     // sigma-cache prologue ops of the current statement (kept at its very start)
     RngCursor* rng = nullptr;  // set while a sampler expression is being lowered (WS_TOK_RAND*)
     int n_statements = 0;
     bool overflow = false;
@@ -71,6 +80,35 @@ struct Program {
 
     void fail(const std::string& m) {
         if (error.empty()) error = m;
+    }
+    // cheap roll-back point for score programs (they only grow: ops, loads and their plane registers)
+    struct Mark {
+        size_t n_ops, n_loads, n_sigma;
+        int next_reg, next_temp, high_water;
+        bool has_acc, overflow;
+        double acc_const;
+    };
+    Mark mark() const { return Mark{ops.size(), loads.size(), sigma_log.size(), next_reg, next_temp, high_water, has_acc, overflow, acc_const}; }
+    void rollback(const Mark& m) {
+        ops.resize(m.n_ops);
+        while (loads.size() > m.n_loads) {
+            plane_reg.erase(loads.back().first);
+            loads.pop_back();
+        }
+        while (sigma_log.size() > m.n_sigma) {
+            sigma_cache.erase(sigma_log.back());
+            sigma_log.pop_back();
+        }
+        next_reg = m.next_reg;
+        next_temp = m.next_temp;
+        high_water = m.high_water;
+        has_acc = m.has_acc;
+        overflow = m.overflow;
+        acc_const = m.acc_const;
+        stmt_begin_ops = m.n_ops;
+        stmt_cache_ops = 0;
+        stmt_temps.clear();
+        error.clear();
     }
     void note_reg(int r) {
         if (r + 1 > high_water) high_water = r + 1;
@@ -104,6 +142,8 @@ struct Program {
         return r;
     }
     void end_statement() {
+        stmt_begin_ops = ops.size();
+        stmt_cache_ops = 0;
         if (score_mode) {
             next_temp = 0;
         } else {
@@ -479,6 +519,60 @@ struct Program {
         if (sigma.is_const && sigma.c0 > 0.0 && isfinite(sigma.c0)) {
             const double s = sigma.c0;
             const double K = -0.5 * WS_LOG2PI - log(s);
+            if (score_mode && !(x.is_const && mu.is_const)) {
+                // Score tapes are folded twice per particle and move (k terms each): z = (x - mu)/s is kept
+                // as ONE affine form of at most two registers — the LIN2 that produced an affine mean such
+                // as alpha + beta*x_i is absorbed — and the constant goes to acc_const.
+                const double is = 1.0 / s;
+                double k0 = 0.0, kk[2] = {0.0, 0.0};
+                int rr[2] = {(int)WS_REG_NONE, (int)WS_REG_NONE};
+                int nr = 0;
+                auto absorb = [&](const Val& v, double sign) {  // adds sign * v / s to the form
+                    if (v.is_const) {
+                        k0 += sign * v.c0 * is;
+                        return;
+                    }
+                    if (nr == 0 && !ops.empty() && is_temp(v.reg)) {
+                        const WsOp& last = ops.back();
+                        const uint32_t lop = last.w0 & 0xFFu, ldst = (last.w0 >> 8) & 0xFFu;
+                        if (lop == WS_OP_LIN2 && (int)ldst == v.reg) {
+                            const int la = (int)((last.w0 >> 16) & 0xFFu), lb = (int)((last.w0 >> 24) & 0xFFu);
+                            const double f = sign * v.c1 * is;
+                            k0 += sign * v.c0 * is + f * last.k0;
+                            if (la != (int)WS_REG_NONE) {
+                                rr[nr] = la;
+                                kk[nr++] = f * last.k1;
+                            }
+                            if (lb != (int)WS_REG_NONE) {
+                                rr[nr] = lb;
+                                kk[nr++] = f * last.k2;
+                            }
+                            ops.pop_back();
+                            return;
+                        }
+                    }
+                    k0 += sign * v.c0 * is;
+                    rr[nr] = v.reg;
+                    kk[nr++] = sign * v.c1 * is;
+                };
+                // the side that may be a freshly computed affine temporary first (only the LAST op can be absorbed)
+                if (x.is_const) {
+                    absorb(mu, -1.0);
+                    absorb(x, 1.0);
+                } else if (mu.is_const) {
+                    absorb(x, 1.0);
+                    absorb(mu, -1.0);
+                } else {
+                    k0 = (x.c0 - mu.c0) * is;
+                    rr[0] = x.reg;
+                    kk[0] = x.c1 * is;
+                    rr[1] = mu.reg;
+                    kk[1] = -mu.c1 * is;
+                }
+                emit(ws_make_op(WS_OP_ACC_SQLIN2, 0, rr[0], rr[1], WS_REG_NONE, 0, k0, kk[0], kk[1]));
+                acc_const += K;
+                return;
+            }
             if (x.is_const && mu.is_const) {
                 const double z = (x.c0 - mu.c0) / s;
                 emit(ws_make_op(WS_OP_ACC_LIN2, 0, WS_REG_NONE, WS_REG_NONE, WS_REG_NONE, 0, -(z * z + WS_LOG2PI) / 2.0 - log(s), 0, 0));
@@ -496,6 +590,64 @@ struct Program {
                 int rm = materialize(mu);
                 emit(ws_make_op(WS_OP_LOGPDF_NORMAL_CS, 0, rx, rm, WS_REG_NONE, 0, 0.0, 1.0 / s, K));
             }
+            return;
+        }
+        if (score_mode && sigma.pure() && !is_temp(sigma.reg) && !(x.is_const && mu.is_const)) {
+            // per-particle sigma that is a plane: z = (x - mu) / sigma as an affine form times the cached 1/sigma,
+            // minus the cached log sigma; the LIN2 that produced an affine mean is absorbed as above
+            auto it = sigma_cache.find(sigma.reg);
+            if (it == sigma_cache.end()) {
+                const int ris = alloc_fresh_reg(), rls = alloc_fresh_reg();
+                // the prologue goes to the very start of the statement's ops, so that a move can keep it while
+                // dropping the terms that do not involve its targets
+                const WsOp pro[2] = {ws_make_op(WS_OP_DIV, ris, WS_REG_NONE, sigma.reg, WS_REG_NONE, 0, 1.0, 1.0, 0.0),
+                                     ws_make_op(WS_OP_UNARY, rls, sigma.reg, WS_REG_NONE, WS_REG_NONE, WS_UN_LOG, 0, 0, 0)};
+                ops.insert(ops.begin() + (std::ptrdiff_t)(stmt_begin_ops + (size_t)stmt_cache_ops), pro, pro + 2);
+                stmt_cache_ops += 2;
+                if ((int)ops.size() > max_ops) overflow = true;
+                it = sigma_cache.emplace(sigma.reg, std::make_pair(ris, rls)).first;
+                sigma_log.push_back(sigma.reg);
+            }
+            double k0 = 0.0, kk[2] = {0.0, 0.0};
+            int rr[2] = {(int)WS_REG_NONE, (int)WS_REG_NONE};
+            int nr = 0;
+            if (!x.is_const && !mu.is_const) {
+                // x and mu both per-particle (theta_j ~ Normal(mu, tau)): two registers, nothing to absorb
+                emit(ws_make_op(WS_OP_ACC_SQLIN2_S, it->second.second, x.reg, mu.reg, it->second.first, 0, x.c0 - mu.c0, x.c1, -mu.c1));
+                acc_const += -0.5 * WS_LOG2PI;
+                return;
+            }
+            const Val& v = x.is_const ? mu : x;
+            const double sign = x.is_const ? -1.0 : 1.0;
+            const Val& cst = x.is_const ? x : mu;
+            bool absorbed = false;
+            if (!v.is_const && !ops.empty() && is_temp(v.reg)) {
+                const WsOp& last = ops.back();
+                const uint32_t lop = last.w0 & 0xFFu, ldst = (last.w0 >> 8) & 0xFFu;
+                if (lop == WS_OP_LIN2 && (int)ldst == v.reg) {
+                    const int la = (int)((last.w0 >> 16) & 0xFFu), lb = (int)((last.w0 >> 24) & 0xFFu);
+                    const double f = sign * v.c1;
+                    k0 = sign * v.c0 + f * last.k0;
+                    if (la != (int)WS_REG_NONE) {
+                        rr[nr] = la;
+                        kk[nr++] = f * last.k1;
+                    }
+                    if (lb != (int)WS_REG_NONE) {
+                        rr[nr] = lb;
+                        kk[nr++] = f * last.k2;
+                    }
+                    ops.pop_back();
+                    absorbed = true;
+                }
+            }
+            if (!absorbed) {
+                k0 = sign * v.c0;
+                rr[0] = v.reg;
+                kk[0] = sign * v.c1;
+            }
+            k0 += -sign * cst.c0;
+            emit(ws_make_op(WS_OP_ACC_SQLIN2_S, it->second.second, rr[0], rr[1], it->second.first, 0, k0, kk[0], kk[1]));
+            acc_const += -0.5 * WS_LOG2PI;
             return;
         }
         const int rx = x.is_const ? (int)WS_REG_NONE : materialize(x);

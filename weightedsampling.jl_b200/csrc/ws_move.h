@@ -21,6 +21,7 @@ struct WsScoreParams {
     int32_t n_regs;
     int32_t n_loads;
     int32_t pad;
+    double konst;       // particle-independent part of the folded log-densities (added by ws_score_logpdf; cancels in a move)
     double* score_out;  // ws_score_logpdf only
     const double* load_ptr[WS_SCORE_MAX_LOADS];
     uint8_t load_reg[WS_SCORE_MAX_LOADS];

@@ -116,6 +116,8 @@ struct TimedEvent {
 struct TapeEntry {
     int64_t depth;   // state.depth before the statement ran (it is scored iff depth < target_depth)
     int32_t op_end;  // score_prog.ops[0 .. op_end) covers the tape up to and including this entry
+    int32_t cache_ops;  // leading ops of this entry that are a sigma-cache prologue (needed by later entries too)
+    double konst_end;  // particle-independent part of the log-densities up to and including this entry (Program::acc_const)
     std::function<void(Program&)> lower;  // re-lowers the statement's log-density (owns its expressions)
     std::vector<Plane> refs;              // planes the log-density reads
 };
@@ -757,22 +759,24 @@ static int lower_statement(ws_ctx* c, F body) {
 static int tape_statement(ws_ctx* c, std::function<void(Program&)> lower, std::vector<Plane> refs) {
     if (!c->tape_enabled) return WS_OK;
     if (!c->score_wide) {
-        Program snapshot = c->score;
+        // roll-back point: sizes only (copying the program per statement is quadratic in the tape length)
+        const Program::Mark mark = c->score.mark();
         lower(c->score);
         if (!c->score.error.empty()) {
             std::string m = c->score.error;
-            c->score = snapshot;
+            c->score.rollback(mark);
             return fail(c, WS_EINVAL, "%s", m.c_str());
         }
         if (c->score.overflow || (int)c->score.loads.size() > WS_SCORE_MAX_LOADS) {
             // too many distinct planes for one register file: from now on the tape is folded in segments
             c->score_wide = true;
             c->score = Program();
-        } else {
-            c->score.end_statement();
         }
     }
-    c->tape.push_back(TapeEntry{c->depth, c->score_wide ? 0 : (int32_t)c->score.ops.size(), std::move(lower), std::move(refs)});
+    const int32_t cache_ops = c->score_wide ? 0 : (int32_t)c->score.stmt_cache_ops;
+    if (!c->score_wide) c->score.end_statement();
+    c->tape.push_back(TapeEntry{c->depth, c->score_wide ? 0 : (int32_t)c->score.ops.size(), cache_ops,
+                                c->score_wide ? 0.0 : c->score.acc_const, std::move(lower), std::move(refs)});
     return WS_OK;
 }
 
@@ -2193,6 +2197,14 @@ static int score_prefix_ops(ws_ctx* c, int64_t target_depth) {
     return n_ops;
 }
 
+static double score_prefix_const(ws_ctx* c, int64_t target_depth) {
+    double k = 0.0;
+    for (auto& e : c->tape) {
+        if (e.depth < target_depth) k = e.konst_end; else break;
+    }
+    return k;
+}
+
 static int upload_score_program(ws_ctx* c) {
     const size_t n_ops = c->score.ops.size();
     if (n_ops == 0) return WS_OK;
@@ -2282,6 +2294,7 @@ static void fill_segment_launch(ws_ctx* c, WsScoreParams& S, Program& seg) {
     S.n_ops = (int)seg.ops.size();
     S.n_regs = std::max(1, seg.high_water);
     S.n_loads = (int)seg.loads.size();
+    S.konst = seg.acc_const;
     for (int k = 0; k < S.n_loads; ++k) {
         S.load_ptr[k] = plane_ptr(c, seg.loads[k].first);
         S.load_reg[k] = (uint8_t)seg.loads[k].second;
@@ -2329,6 +2342,7 @@ extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out
         TRY(upload_score_program(c));
         WsScoreParams S;
         TRY(fill_score_launch(c, S, n_ops));
+        S.konst = score_prefix_const(c, target_depth);
         S.score_out = c->d_scratch;
         TimedEvent te;
         timed_begin(c, KC_MOVE, te);
@@ -2583,6 +2597,52 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
         const int n_ops = score_prefix_ops(c, target_depth);
         TRY(upload_score_program(c));
         TRY(fill_score_launch(c, M.score, n_ops));
+        // Terms that do not involve a target cancel in s_new - s_old: fold only the entries that read a target
+        // (plus the sigma-cache prologues later entries rely on), and load only the planes those read.
+        {
+            std::vector<WsOp> sel;
+            std::vector<Plane> need;
+            int begin = 0;
+            for (auto& e : c->tape) {
+                if (!(e.depth < target_depth)) break;
+                const int b = begin, pe = b + e.cache_ops, en = e.op_end;
+                begin = en;
+                bool dep = false;
+                for (auto& r : e.refs)
+                    for (int t = 0; t < d; ++t)
+                        if (r.col == spec->col[t] && r.comp == spec->comp[t]) dep = true;
+                if (e.cache_ops > 0 || dep)
+                    for (auto& r : e.refs) need.push_back(r);
+                if (e.cache_ops > 0) sel.insert(sel.end(), c->score.ops.begin() + b, c->score.ops.begin() + pe);
+                if (dep) sel.insert(sel.end(), c->score.ops.begin() + pe, c->score.ops.begin() + en);
+            }
+            if ((int)sel.size() < n_ops) {
+                if (sel.size() > c->d_seg_cap) {
+                    if (c->d_seg_ops) {
+                        CK(c, cudaStreamSynchronize(c->stream));
+                        CK(c, cudaFree(c->d_seg_ops));
+                        c->d_seg_ops = nullptr;
+                    }
+                    c->d_seg_cap = std::max<size_t>(4096, sel.size() * 2);
+                    CK(c, cudaMalloc(&c->d_seg_ops, sizeof(WsOp) * c->d_seg_cap));
+                }
+                if (!sel.empty()) {
+                    CK(c, cudaMemcpyAsync(c->d_seg_ops, sel.data(), sizeof(WsOp) * sel.size(), cudaMemcpyHostToDevice, c->stream));
+                    c->stats.h2d_bytes += (int64_t)(sizeof(WsOp) * sel.size());
+                }
+                M.score.ops = c->d_seg_ops;
+                M.score.n_ops = (int)sel.size();
+                int k2 = 0;
+                for (int k = 0; k < (int)c->score.loads.size(); ++k) {
+                    const Plane pl = c->score.loads[k].first;
+                    if (std::find(need.begin(), need.end(), pl) == need.end()) continue;
+                    M.score.load_ptr[k2] = plane_ptr(c, pl);
+                    M.score.load_reg[k2] = (uint8_t)c->score.loads[k].second;
+                    ++k2;
+                }
+                M.score.n_loads = k2;
+            }
+        }
         TimedEvent te;
         timed_begin(c, KC_MOVE, te);
         CK(c, ws_launch_move(M, c->sm_count, c->stream));

@@ -32,7 +32,12 @@ enum WsOpCode : uint32_t {
     WS_OP_LOGPDF_NORMAL_CS = 13,  // constant sigma: acc += k2 - 0.5*((X - r[b])*k1)^2,  X = a==NONE?k0:r[a]
     WS_OP_CMP = 14,      // r[dst] = (A op B) ? 1 : 0     imm: 0 <, 1 <=, 2 ==      A = a==NONE?k1:r[a]; B = b==NONE?k2:r[b]
     WS_OP_SELECT = 15,   // r[dst] = (r[c] != 0) ? A : B
-    WS_OP_MINMAX = 16    // r[dst] = imm ? max(A,B) : min(A,B)
+    WS_OP_MINMAX = 16,   // r[dst] = imm ? max(A,B) : min(A,B)
+    WS_OP_ACC_SQLIN2 = 17  // acc -= (k0 + k1*r[a] + k2*r[b])^2 / 2   (a / b == NONE: term absent).  A Normal log-density
+                           // with constant sigma and an affine mean, minus its constant, in ONE op (score tapes)
+    ,
+    WS_OP_ACC_SQLIN2_S = 18  // acc -= ((k0 + k1*r[a] + k2*r[b]) * r[c])^2 / 2 + r[dst]: the same with a per-particle sigma
+                             // whose reciprocal r[c] and logarithm r[dst] were computed once per fold (score tapes)
 };
 
 enum WsUnary : uint32_t {
@@ -303,6 +308,25 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
                 const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
                 const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
                 Rd[j * STRIDE] = imm ? fmax(A, B) : fmin(A, B);
+            }
+        } break;
+        case WS_OP_ACC_SQLIN2: {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double z = k0;
+                if (a != WS_REG_NONE) z += k1 * Ra[j * STRIDE];
+                if (b != WS_REG_NONE) z += k2 * Rb[j * STRIDE];
+                acc[j] -= 0.5 * (z * z);
+            }
+        } break;
+        case WS_OP_ACC_SQLIN2_S: {
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double z = k0;
+                if (a != WS_REG_NONE) z += k1 * Ra[j * STRIDE];
+                if (b != WS_REG_NONE) z += k2 * Rb[j * STRIDE];
+                z *= Rc[j * STRIDE];
+                acc[j] -= 0.5 * (z * z) + Rd[j * STRIDE];
             }
         } break;
         case WS_OP_ACC_SCALE: {
