@@ -1123,6 +1123,24 @@ cudaError_t ws_launch_local_ancestors(int32_t* anc, int64_t n, const int32_t* an
     return cudaGetLastError();
 }
 
+// the same for ancestors that the search already wrote in place: only the received slots are patched
+__global__ void ws_patch_ancestors_kernel(int32_t* __restrict__ anc, int64_t n, int64_t self_lo, int64_t self_hi) {
+    const int64_t n_patch = self_lo + (n - self_hi);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_patch; k += stride) {
+        if (k < self_lo) anc[k] = (int32_t)(n + k);
+        else anc[self_hi + (k - self_lo)] = (int32_t)(n + k);
+    }
+}
+cudaError_t ws_launch_patch_ancestors(int32_t* anc, int64_t n, int64_t self_lo, int64_t self_hi, cudaStream_t s) {
+    const int64_t n_patch = self_lo + (n - self_hi);
+    if (n_patch <= 0) return cudaSuccess;
+    int grid = (int)((n_patch + 255) / 256);
+    if (grid > g_sm_count * 8) grid = g_sm_count * 8;
+    ws_patch_ancestors_kernel<<<grid, 256, 0, s>>>(anc, n, self_lo, self_hi);
+    return cudaGetLastError();
+}
+
 __global__ void ws_gather_rows_kernel(const double* __restrict__ src, const int64_t* __restrict__ idx, int64_t n_idx,
                                       double* __restrict__ dst) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

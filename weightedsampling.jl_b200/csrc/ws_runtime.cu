@@ -479,11 +479,15 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     CKC(cudaMemsetAsync(c->d_red, 0, sizeof(WsReduceOut), c->stream));
     CKC(cudaMallocHost(&c->h_red, sizeof(WsReduceOut)));
     memset(c->h_red, 0, sizeof(WsReduceOut));
-    if (pool_alloc(c, (void**)&c->d_anc, sizeof(int32_t) * (size_t)(c->n + c->spare)) != WS_OK) {
+    if (nranks > 1) c->spare = std::max<int64_t>(4096, c->n / 32);
+    // sharded: a margin of `spare` entries on BOTH sides, so that the search can write the ancestors of the slots
+    // this rank produces for its neighbours in place, next to those of its own slots (resample_sharded)
+    if (pool_alloc(c, (void**)&c->d_anc, sizeof(int32_t) * (size_t)(c->n + 2 * c->spare)) != WS_OK) {
         int rc__ = fail(nullptr, WS_ENOMEM, "%s", c->err.c_str());
         ws_destroy(c);
         return rc__;
     }
+    c->d_anc += c->spare;
     {
         // genealogy budget: WSB200_GENEALOGY_BYTES, default a quarter of the device memory
         size_t free_b = 0, total_b = 0;
@@ -511,7 +515,6 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
             ws_destroy(c);
             return rc;
         }
-        c->spare = std::max<int64_t>(4096, c->n / 32);
         // NCCL sets up its peer-to-peer channels on first use (hundreds of ms); do that here, not in
         // the first resampling steps: one 3-double message to and from every peer + the collectives used
         {
@@ -1570,7 +1573,20 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     }
     S.heavy_F = c->d_heavy_F;
     CK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int) * 2, c->stream));
-    S.ancestors = c->d_anc_src;
+    // Deferred gather + few migrants (the usual case): the search writes the ancestors of global slot s straight to
+    // d_anc[s - my_lo] — own slots in place, the slots produced for the neighbours into the margins on either side —
+    // instead of a staging vector that a second pass copies into place (8 B per particle saved).
+    bool fits_all = true;
+    for (int d = 0; d < R; ++d) {
+        const int64_t dlo = (c->n_global * (int64_t)d) / R, dhi = (c->n_global * (int64_t)(d + 1)) / R;
+        const int64_t own = std::max<int64_t>(0, std::min<int64_t>(bnd[2 * d + 1], dhi) - std::max<int64_t>(bnd[2 * d], dlo));
+        const int64_t d_spare = std::max<int64_t>(4096, (dhi - dlo) / 32);
+        if ((dhi - dlo) - own > d_spare) fits_all = false;
+    }
+    const int64_t lo_r = (c->n_global * (int64_t)r) / R, hi_r = (c->n_global * (int64_t)(r + 1)) / R;
+    const bool inplace = c->lazy_gather && fits_all && (lo_r - fs) <= c->spare && (fe - hi_r) <= c->spare;
+    int32_t* const anc_src = inplace ? c->d_anc + (fs - lo_r) : c->d_anc_src;
+    S.ancestors = anc_src;
     S.slot_base = (int32_t)fs;
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_search(S, c->stream));
@@ -1646,7 +1662,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
             WsGatherParams G;
             memset(&G, 0, sizeof(G));
             G.n = send_cnt[r];
-            G.ancestors = c->d_anc_src + send_off[r];
+            G.ancestors = anc_src + send_off[r];
             G.n_planes = nb;
             for (int k = 0; k < nb; ++k) {
                 const Plane pl = planes[p0 + k];
@@ -1664,7 +1680,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
             WsGatherParams G;
             memset(&G, 0, sizeof(G));
             G.n = seg_len[sgi];
-            G.ancestors = c->d_anc_src + seg_start[sgi];
+            G.ancestors = anc_src + seg_start[sgi];
             G.n_planes = nb;
             for (int k = 0; k < nb; ++k) {
                 const Plane pl = planes[p0 + k];
@@ -1699,8 +1715,14 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
         // row they were written to; every plane is now in pre-resample order (+ spare rows) and is
         // gathered by its next reader, exactly as on one GPU
         const int64_t self_lo = recv_off[r], self_hi = recv_off[r] + send_cnt[r];
-        CK(c, ws_launch_local_ancestors(c->d_anc, c->n, c->d_anc_src + send_off[r], send_cnt[r] > 0 ? self_lo : c->n,
-                                         send_cnt[r] > 0 ? self_hi : c->n, grid_for(c, c->n, 256, 8), c->stream));
+        if (inplace) {
+            // own slots are already in place: only the slots received from other ranks get their spare-row index
+            CK(c, ws_launch_patch_ancestors(c->d_anc, c->n, send_cnt[r] > 0 ? self_lo : c->n, send_cnt[r] > 0 ? self_hi : c->n,
+                                             c->stream));
+        } else {
+            CK(c, ws_launch_local_ancestors(c->d_anc, c->n, anc_src + send_off[r], send_cnt[r] > 0 ? self_lo : c->n,
+                                             send_cnt[r] > 0 ? self_hi : c->n, grid_for(c, c->n, 256, 8), c->stream));
+        }
         c->stats.kernel_launches++;
         end_resample_event(c);
         return WS_OK;
