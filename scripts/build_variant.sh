@@ -3,7 +3,7 @@
 # usage: scripts/build_variant.sh <name> "-DWS_VM_P=4 -DWS_VM_MINB=5"
 set -e
 NAME=$1; DEFS=$2
-D=/root/repo/weightedsampling.jl_b200/csrc
+D=${WS_SRC:-/root/repo/weightedsampling.jl_b200/csrc}
 O=/tmp/wsb200_variant_$NAME
 mkdir -p $O /root/repo/variants
 for f in ws_runtime ws_kernels ws_kernels_move ws_kernels_stats; do

@@ -125,11 +125,15 @@ __device__ __forceinline__ void ws_cp_async_wait_all() { asm volatile("cp.async.
 
 template <bool STAGED>
 __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __grid_constant__ WsVmProgram P) {
-    extern __shared__ double ws_vm_smem[];
+    extern __shared__ __align__(16) double ws_vm_smem[];
     __shared__ WsLse warp_scratch[WS_VM_BLOCK / 32];
     double* R = ws_vm_smem + threadIdx.x;
     constexpr int RS = WS_VM_P * WS_VM_BLOCK;  // doubles between two registers of the file
     double* const stage = R + P.n_regs * RS;   // [n_loads][WS_VM_P][WS_VM_BLOCK]   (STAGED only)
+    // the program, unpacked once per CTA (ws_vm.cuh: WsDop) behind the register file and the staging rows
+    WsDop* const dops = reinterpret_cast<WsDop*>(ws_vm_smem + (P.n_regs + (STAGED ? P.n_loads : 0)) * RS);
+    for (int t = threadIdx.x; t < P.n_ops; t += WS_VM_BLOCK) dops[t] = ws_decode_op<WS_VM_BLOCK, WS_VM_P>(P.ops[t]);
+    __syncthreads();
 
     WsLse part;
     part.m = -INFINITY;
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
 #pragma unroll
         for (int j = 0; j < WS_VM_P; ++j) acc[j] = 0.0;
         for (int pc = 0; pc < P.n_ops; ++pc) {
-            ws_vm_exec<WS_VM_BLOCK, WS_VM_P>(P.ops[pc], R, acc, P.rng, particle);
+            ws_vm_exec_d<WS_VM_BLOCK, WS_VM_P>(dops[pc], R, acc, P.rng, particle);
         }
 
         // ---- stores ---------------------------------------------------------------------------------
@@ -314,14 +318,14 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
 static bool ws_vm_staged(int n_regs, int n_loads) {
     return n_loads > 0 && (size_t)(n_regs + n_loads) * WS_VM_BLOCK * WS_VM_P * sizeof(double) <= (size_t)200 * 1024;
 }
-int ws_vm_smem_bytes(int n_regs, int n_loads) {
+int ws_vm_smem_bytes(int n_regs, int n_loads, int n_ops) {
     const int rows = (n_regs < 1 ? 1 : n_regs) + (ws_vm_staged(n_regs < 1 ? 1 : n_regs, n_loads) ? n_loads : 0);
-    return rows * WS_VM_BLOCK * WS_VM_P * (int)sizeof(double);
+    return rows * WS_VM_BLOCK * WS_VM_P * (int)sizeof(double) + n_ops * (int)sizeof(WsDop);
 }
 
-int ws_vm_max_grid(int n_regs, int n_loads, int sm_count) {
+int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count) {
     // resident CTAs per SM limited by the shared-memory register file and 2048 threads / SM
-    const int smem = ws_vm_smem_bytes(n_regs, n_loads) + 1024;
+    const int smem = ws_vm_smem_bytes(n_regs, n_loads, n_ops) + 1024;
     int per_sm = (227 * 1024) / smem;
     if (per_sm > WS_VM_MINB) per_sm = WS_VM_MINB;  // __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB)
     if (per_sm < 1) per_sm = 1;
@@ -329,7 +333,7 @@ int ws_vm_max_grid(int n_regs, int n_loads, int sm_count) {
 }
 
 cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
-    const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads);
+    const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads, P.n_ops);
     if (ws_vm_staged(P.n_regs, P.n_loads)) ws_vm_kernel<true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     else ws_vm_kernel<false><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     return cudaGetLastError();
@@ -1192,8 +1196,8 @@ cudaError_t ws_kernels_init(int device) {
     if (e != cudaSuccess) return e;
     g_sm_count = prop.multiProcessorCount;
     // the register file of the fused pass can take most of the SM's shared memory
-    e = cudaFuncSetAttribute(ws_vm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(ws_vm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ws_vm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(ws_vm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     return e;
 }

@@ -43,8 +43,13 @@ __device__ __forceinline__ void ws_score_load_planes(const WsScoreParams& S, dou
     }
 }
 
+// The fold: every thread of the CTA walks the same tape, so the CTA stages it through shared memory in chunks of
+// WS_FOLD_CHUNK entries, each entry unpacked once (ws_vm.cuh: WsDop) by one thread instead of by every thread for
+// every tile.  Must be called by all threads of the CTA (two barriers per chunk).
+#define WS_FOLD_CHUNK WS_MOVE_BLOCK
 template <int P>
-__device__ __forceinline__ void ws_score_fold(const WsScoreParams& S, double* R, const uint64_t (&pid)[P], double (&acc)[P]) {
+__device__ __forceinline__ void ws_score_fold(const WsScoreParams& S, double* R, const uint64_t (&pid)[P], double (&acc)[P],
+                                              WsDop* dops /* [WS_FOLD_CHUNK], shared */) {
 #pragma unroll
     for (int j = 0; j < P; ++j) acc[j] = 0.0;
     WsRng none;
@@ -52,9 +57,56 @@ __device__ __forceinline__ void ws_score_fold(const WsScoreParams& S, double* R,
     none.replay_n = nullptr;
     none.replay_u = nullptr;
     none.replay_e = nullptr;
-    for (int pc = 0; pc < S.n_ops; ++pc) {
-        const WsOp o = ws_load_op(S.ops, pc);
-        ws_vm_exec<WS_MOVE_BLOCK, P>(o, R, acc, none, pid);
+    __shared__ unsigned int cont_mask[WS_FOLD_CHUNK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < S.n_ops; base += WS_FOLD_CHUNK) {
+        const int cnt = min(WS_FOLD_CHUNK, S.n_ops - base);
+        __syncthreads();  // the previous chunk (or fold) has been consumed by every warp
+        // thread t unpacks entry t; `cont`: a squared-residual entry over the same registers as its predecessor
+        bool cont = false, runnable = false;
+        if ((int)threadIdx.x < cnt) {
+            const WsOp o = ws_load_op(S.ops, base + (int)threadIdx.x);
+            WsDop dd = ws_decode_op<WS_MOVE_BLOCK, P>(o, S.reg_map);
+            runnable = dd.op == WS_OP_ACC_SQLIN2 || dd.op == WS_OP_ACC_SQLIN2_S;
+            if (runnable && threadIdx.x > 0) {
+                const uint2 pw = __ldg(reinterpret_cast<const uint2*>(S.ops + base + (int)threadIdx.x - 1));
+                cont = pw.x == o.w0 && (pw.y & 0xFFu) == (o.w1 & 0xFFu);
+            }
+            dd.op |= 1u << 8;
+            dops[threadIdx.x] = dd;
+        }
+        const unsigned int cm = __ballot_sync(0xffffffffu, cont);
+        if (lane == 0) cont_mask[warp] = cm;
+        __syncthreads();
+        if (runnable && !cont) {  // head of a run: its length = 1 + the `cont` bits that follow
+            int len = 1, q = (int)threadIdx.x + 1;
+            while (q < WS_FOLD_CHUNK) {
+                const unsigned int inv = ~(cont_mask[q >> 5] >> (q & 31));
+                const int avail = 32 - (q & 31);
+                const int ones = inv ? __ffs((int)inv) - 1 : 32;
+                if (ones >= avail) {
+                    len += avail;
+                    q += avail;
+                } else {
+                    len += ones;
+                    break;
+                }
+            }
+            if (len > 1) dops[threadIdx.x].op = (dops[threadIdx.x].op & 0xFFu) | ((unsigned int)len << 8);
+        }
+        __syncthreads();
+        // the next entry is fetched while the current one executes (the fetch -> dispatch chain is otherwise
+        // exposed: few warps per scheduler)
+        WsDop cur = dops[0];
+        for (int k = 0; k < cnt;) {
+            const int len = (int)(cur.op >> 8);
+            const int kn = k + len;
+            const WsDop nxt = dops[kn < cnt ? kn : k];
+            if (len > 1) ws_vm_exec_sqlin2_run<WS_MOVE_BLOCK, P>(dops + k, len, R, acc);
+            else ws_vm_exec_d<WS_MOVE_BLOCK, P>(cur, R, acc, none, pid);
+            cur = nxt;
+            k = kn;
+        }
     }
 }
 
@@ -73,6 +125,7 @@ __device__ __forceinline__ void ws_tile_indices(int64_t tile, int64_t n, int64_t
 template <int P>
 __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_score_kernel(const __grid_constant__ WsScoreParams S) {
     extern __shared__ double ws_score_smem[];
+    __shared__ WsDop dops[WS_FOLD_CHUNK];
     double* R = ws_score_smem + threadIdx.x;
     const int64_t n_tiles = (S.n + P * WS_MOVE_BLOCK - 1) / (P * WS_MOVE_BLOCK);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -82,7 +135,7 @@ __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_score_kernel(const __grid_co
         ws_tile_indices<P>(tile, S.n, S.particle_offset, idx, live, pid);
         ws_score_load_planes<P>(S, R, idx);
         double acc[P];
-        ws_score_fold<P>(S, R, pid, acc);
+        ws_score_fold<P>(S, R, pid, acc, dops);
 #pragma unroll
         for (int j = 0; j < P; ++j)
             if (live[j]) S.score_out[idx[j]] = acc[j] + S.konst;
@@ -91,9 +144,13 @@ __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_score_kernel(const __grid_co
 
 // Rows [0, n_regs) of the register file are the score program's registers, rows [n_regs, n_regs + d) hold the
 // proposed target values of the thread's P particles.
+#ifndef WS_MOVE_MINB
+#define WS_MOVE_MINB 4   // <= 128 registers: 16 warps per SM (measured against 1 and 3, scripts/ab_move.sh)
+#endif
 template <int P>
-__global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_kernel(const __grid_constant__ WsMoveParams M) {
+__global__ void __launch_bounds__(WS_MOVE_BLOCK, WS_MOVE_MINB) ws_move_kernel(const __grid_constant__ WsMoveParams M) {
     extern __shared__ double ws_score_smem[];
+    __shared__ WsDop dops[WS_FOLD_CHUNK];
     double* R = ws_score_smem + threadIdx.x;
     constexpr int RS = P * WS_MOVE_BLOCK;
     const WsScoreParams& S = M.score;
@@ -159,7 +216,7 @@ __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_kernel(const __grid_con
 
         // ---- trace density at the old and at the proposed values ------------------------------------
         double s_old[P], s_new[P];
-        ws_score_fold<P>(S, R, pid, s_old);
+        ws_score_fold<P>(S, R, pid, s_old, dops);
         for (int t = 0; t < d; ++t) {
             if (M.target_reg[t] != 0xFF) {
                 double* dst = R + (int)M.target_reg[t] * RS;
@@ -167,7 +224,7 @@ __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_kernel(const __grid_con
                 for (int j = 0; j < P; ++j) dst[j * WS_MOVE_BLOCK] = Xn[t * RS + j * WS_MOVE_BLOCK];
             }
         }
-        ws_score_fold<P>(S, R, pid, s_new);
+        ws_score_fold<P>(S, R, pid, s_new, dops);
 
         // ---- accept / reject (NaN ratio rejects: !(log u < ...)) ---------------------------------------
 #pragma unroll
@@ -254,23 +311,27 @@ __global__ void __launch_bounds__(256) ws_move_propose_kernel(const __grid_const
 __global__ void __launch_bounds__(WS_MOVE_BLOCK) ws_move_delta_kernel(const __grid_constant__ WsMoveParams M, int mode,
                                                                       const double* __restrict__ x_new, double* __restrict__ out) {
     extern __shared__ double ws_score_smem[];
+    __shared__ WsDop dops[WS_FOLD_CHUNK];
     double* R = ws_score_smem + threadIdx.x;
     const WsScoreParams& S = M.score;
     const int64_t stride = (int64_t)gridDim.x * WS_MOVE_BLOCK;
-    for (int64_t i = (int64_t)blockIdx.x * WS_MOVE_BLOCK + threadIdx.x; i < S.n; i += stride) {
+    // CTA-uniform trip count (the fold has barriers); threads beyond n work on a clamped index and store nothing
+    for (int64_t base = (int64_t)blockIdx.x * WS_MOVE_BLOCK; base < S.n; base += stride) {
+        const bool live = base + threadIdx.x < S.n;
+        const int64_t i = live ? base + threadIdx.x : S.n - 1;
         const uint64_t pid[1] = {(uint64_t)(S.particle_offset + i)};
         const int64_t idx[1] = {i};
         ws_score_load_planes<1>(S, R, idx);
         double s_old[1], s_new[1];
-        ws_score_fold<1>(S, R, pid, s_old);
+        ws_score_fold<1>(S, R, pid, s_old, dops);
         if (mode == 0) {
-            out[i] += s_old[0] + S.konst;
+            if (live) out[i] += s_old[0] + S.konst;
         } else {
 #pragma unroll
             for (int t = 0; t < WS_MOVE_MAX_D; ++t)
                 if (t < M.d && M.target_reg[t] != 0xFF) R[(int)M.target_reg[t] * WS_MOVE_BLOCK] = x_new[(size_t)t * S.n + i];
-            ws_score_fold<1>(S, R, pid, s_new);
-            out[i] += s_new[0] - s_old[0];
+            ws_score_fold<1>(S, R, pid, s_new, dops);
+            if (live) out[i] += s_new[0] - s_old[0];
         }
     }
 }
@@ -420,7 +481,7 @@ __global__ void __launch_bounds__(256) ws_unique_count_kernel(const double* __re
 // launchers
 // ------------------------------------------------------------------------------------------
 static int score_grid(int rows, int P, int64_t n, int sm_count) {
-    const int smem = rows * P * WS_MOVE_BLOCK * (int)sizeof(double) + 256;
+    const int smem = rows * P * WS_MOVE_BLOCK * (int)sizeof(double) + WS_FOLD_CHUNK * (int)sizeof(WsDop) + 1280;
     int per_sm = (227 * 1024) / smem;
     if (per_sm > 2048 / WS_MOVE_BLOCK) per_sm = 2048 / WS_MOVE_BLOCK;
     if (per_sm < 1) per_sm = 1;
@@ -433,8 +494,8 @@ static int score_grid(int rows, int P, int64_t n, int sm_count) {
 // particles per thread of a fold: as many as keep at least four CTAs (16 warps) resident per SM
 static int score_particles_per_thread(int rows) {
     const int row_bytes = WS_MOVE_BLOCK * (int)sizeof(double);
-    if (rows * 4 * row_bytes <= 56 * 1024) return 4;
-    if (rows * 2 * row_bytes <= 56 * 1024) return 2;
+    if (rows * 4 * row_bytes <= 49 * 1024) return 4;  // + 6 KB of staged tape entries per CTA
+    if (rows * 2 * row_bytes <= 49 * 1024) return 2;
     return 1;
 }
 

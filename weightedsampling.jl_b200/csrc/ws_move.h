@@ -24,7 +24,8 @@ struct WsScoreParams {
     double konst;       // particle-independent part of the folded log-densities (added by ws_score_logpdf; cancels in a move)
     double* score_out;  // ws_score_logpdf only
     const double* load_ptr[WS_SCORE_MAX_LOADS];
-    uint8_t load_reg[WS_SCORE_MAX_LOADS];
+    uint8_t load_reg[WS_SCORE_MAX_LOADS];  // already renumbered
+    uint8_t reg_map[256];  // tape register -> row of this launch's register file (see compact_score_regs)
 };
 
 struct WsMoveParams {

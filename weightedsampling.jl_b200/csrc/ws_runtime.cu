@@ -680,7 +680,7 @@ static int flush_window(ws_ctx* c) {
         P.logw_mode = 0;
     }
     const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
-    const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, c->sm_count), (c->n + vm_tile - 1) / vm_tile);
+    const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, P.n_ops, c->sm_count), (c->n + vm_tile - 1) / vm_tile);
     P.partials = w.has_acc ? c->d_partials : nullptr;
     P.n_expect = 0;
     P.rng.seed = c->seed;
@@ -2045,7 +2045,7 @@ extern "C" int ws_expectation(ws_ctx* c, const ws_expr* f, int32_t n_exprs, doub
     for (int k = 0; k < n_exprs; ++k) P.expect_reg[k] = (uint8_t)regs[k];
     P.red = c->d_red;
     const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, c->sm_count), (c->n + vm_tile - 1) / vm_tile));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, P.n_ops, c->sm_count), (c->n + vm_tile - 1) / vm_tile));
     TRY(ensure_scratch(c, sizeof(double) * (size_t)grid * 8));
     TRY(ensure_h_scratch(c, sizeof(double) * (size_t)grid * 8));
     P.expect_partials = c->d_scratch;
@@ -2308,8 +2308,36 @@ static int for_each_tape_segment(ws_ctx* c, int64_t target_depth, const std::vec
     return launch(seg);
 }
 
+// A launch folds a prefix / a selection of the tape: keep only the register-file rows those entries touch
+// (a tape reserves WS_SCORE_TEMPS temporaries and one register per plane it ever read; fewer rows = more
+// particles per thread and more CTAs per SM in the fold kernels).  The ops stay as they are on the device;
+// the kernels renumber while unpacking them (ws_decode_op).
+static void compact_score_regs(WsScoreParams& S, const WsOp* ops, size_t n_ops, uint8_t* target_reg, int d) {
+    bool used[256] = {false};
+    for (size_t i = 0; i < n_ops; ++i) {
+        const WsOp& o = ops[i];
+        const uint32_t op = o.w0 & 0xFFu;
+        const uint32_t r[4] = {(o.w0 >> 8) & 0xFFu, (o.w0 >> 16) & 0xFFu, (o.w0 >> 24) & 0xFFu, o.w1 & 0xFFu};
+        if (ws_op_dst_is_reg(op)) used[r[0]] = true;
+        used[r[1]] = used[r[2]] = used[r[3]] = true;
+    }
+    for (int k = 0; k < S.n_loads; ++k) used[S.load_reg[k]] = true;
+    for (int t = 0; t < d; ++t) used[target_reg[t]] = true;
+    used[WS_REG_NONE] = false;
+    int next = 0;
+    for (int r = 0; r < 256; ++r) S.reg_map[r] = used[r] ? (uint8_t)next++ : (uint8_t)0;
+    S.reg_map[WS_REG_NONE] = WS_REG_NONE;
+    S.n_regs = std::max(1, next);
+    for (int k = 0; k < S.n_loads; ++k) S.load_reg[k] = S.reg_map[S.load_reg[k]];
+    for (int t = 0; t < d; ++t) target_reg[t] = S.reg_map[target_reg[t]];
+}
+static void identity_reg_map(WsScoreParams& S) {
+    for (int r = 0; r < 256; ++r) S.reg_map[r] = (uint8_t)r;
+}
+
 static void fill_segment_launch(ws_ctx* c, WsScoreParams& S, Program& seg) {
     memset(&S, 0, sizeof(S));
+    identity_reg_map(S);
     S.n = c->n;
     S.particle_offset = c->offset;
     S.ops = c->d_seg_ops;
@@ -2325,6 +2353,7 @@ static void fill_segment_launch(ws_ctx* c, WsScoreParams& S, Program& seg) {
 
 static int fill_score_launch(ws_ctx* c, WsScoreParams& S, int n_ops) {
     memset(&S, 0, sizeof(S));
+    identity_reg_map(S);
     S.n = c->n;
     S.particle_offset = c->offset;
     S.ops = c->d_score_ops;
@@ -2366,6 +2395,7 @@ extern "C" int ws_score_logpdf(ws_ctx* c, int64_t target_depth, double* host_out
         TRY(fill_score_launch(c, S, n_ops));
         S.konst = score_prefix_const(c, target_depth);
         S.score_out = c->d_scratch;
+        compact_score_regs(S, c->score.ops.data(), (size_t)n_ops, nullptr, 0);
         TimedEvent te;
         timed_begin(c, KC_MOVE, te);
         CK(c, ws_launch_score(S, c->sm_count, c->stream));
@@ -2663,6 +2693,9 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
                     ++k2;
                 }
                 M.score.n_loads = k2;
+                compact_score_regs(M.score, sel.data(), sel.size(), M.target_reg, d);
+            } else {
+                compact_score_regs(M.score, c->score.ops.data(), (size_t)n_ops, M.target_reg, d);
             }
         }
         TimedEvent te;

@@ -66,6 +66,12 @@ struct alignas(16) WsOp {
 };
 static_assert(sizeof(WsOp) == 32, "WsOp must be 32 bytes");
 
+// does the op use its dst field as a register?  (the pure accumulate ops leave it unused)
+WS_HD bool ws_op_dst_is_reg(uint32_t op) {
+    return !(op == WS_OP_LOGPDF_NORMAL || op == WS_OP_LOGPDF_EXPON || op == WS_OP_ACC_LIN2 || op == WS_OP_ACC_QUAD2 ||
+             op == WS_OP_ACC_SCALE || op == WS_OP_LOGPDF_NORMAL_CS || op == WS_OP_ACC_SQLIN2);
+}
+
 WS_HD WsOp ws_make_op(uint32_t op, uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t imm, double k0,
                       double k1, double k2) {
     WsOp o;
@@ -98,6 +104,64 @@ WS_HD uint64_t ws_double_bits(double v) {
 #endif
 }
 
+// Decoded micro-op: what the interpreter executes.  The 32-byte WsOp is what the lowering emits and what
+// travels (kernel parameters, the device score tape); unpacking it cost ~25 of the ~40 instructions a
+// thread spent per micro-op outside the arithmetic (shifts, masks, register-row multiplies, the walk down
+// the LIN2 sub-cases), so a CTA unpacks each op ONCE into shared memory (ws_decode_op) and its threads
+// fetch the decoded form with three 16-byte loads:
+//   * dst / a / b / c are element offsets into the thread's register-file column (reg * P * STRIDE),
+//     WS_OFF_NONE where the operand is absent;
+//   * LIN2 is split by operand pattern (constant / one term / two terms) so the hot op is one compare away.
+#define WS_OFF_NONE 0xFFFFFFFFu
+enum WsDopCode : uint32_t {
+    WS_DOP_LIN2_K = 32,   // r[dst] = k0
+    WS_DOP_LIN2_A = 33,   // r[dst] = k0 + k1*r[a]              (a LIN2 with only b present is stored swapped)
+    WS_DOP_LIN2_AB = 34   // r[dst] = (k0 + k1*r[a]) + k2*r[b]
+};
+struct alignas(16) WsDop {
+    uint32_t op, dst, a, b;
+    uint32_t c, imm;
+    double k0;
+    double k1, k2;
+};
+static_assert(sizeof(WsDop) == 48, "WsDop must be 48 bytes");
+
+// `reg_map` (optional): renumbering of the registers, so that a launch that folds part of a tape keeps only
+// the register-file rows that part touches (ws_runtime.cu: compact_score_regs)
+template <int STRIDE, int P>
+WS_HD WsDop ws_decode_op(const WsOp& o, const uint8_t* reg_map = nullptr) {
+    WsDop d;
+    const uint32_t op = o.w0 & 0xFFu;
+    const uint32_t r[4] = {(o.w0 >> 8) & 0xFFu, (o.w0 >> 16) & 0xFFu, (o.w0 >> 24) & 0xFFu, o.w1 & 0xFFu};
+    uint32_t off[4];
+    for (int k = 0; k < 4; ++k)
+        off[k] = (r[k] == WS_REG_NONE) ? WS_OFF_NONE : (uint32_t)(reg_map ? reg_map[r[k]] : r[k]) * (uint32_t)(P * STRIDE);
+    d.op = op;
+    d.dst = off[0];
+    d.a = off[1];
+    d.b = off[2];
+    d.c = off[3];
+    d.imm = o.w1 >> 8;
+    d.k0 = o.k0;
+    d.k1 = o.k1;
+    d.k2 = o.k2;
+    if (op == WS_OP_LIN2) {
+        if (d.a == WS_OFF_NONE && d.b == WS_OFF_NONE) {
+            d.op = WS_DOP_LIN2_K;
+        } else if (d.a == WS_OFF_NONE) {  // k0 + k2*r[b]: the same arithmetic with the operands renamed
+            d.op = WS_DOP_LIN2_A;
+            d.a = d.b;
+            d.k1 = o.k2;
+            d.b = WS_OFF_NONE;
+        } else if (d.b == WS_OFF_NONE) {
+            d.op = WS_DOP_LIN2_A;
+        } else {
+            d.op = WS_DOP_LIN2_AB;
+        }
+    }
+    return d;
+}
+
 // Register file layout: register r of the thread's j-th particle lives at R[(r*P + j)*STRIDE], where R
 // points at this thread's column of the shared-memory register file.  One decoded micro-op is applied
 // to all P particles of the thread, which amortises the (warp-uniform) decode over P particles and
@@ -105,37 +169,30 @@ WS_HD uint64_t ws_double_bits(double v) {
 // (WS_HD: the host instantiation exists only for tests/host/, which runs lowered programs through
 // this very interpreter on the CPU to check the lowering without a GPU.)
 template <int STRIDE, int P>
-WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], const WsRng& rng,
-                      const uint64_t (&particle)[P]) {
-    const uint32_t op = o.w0 & 0xFFu;
-    const uint32_t dst = (o.w0 >> 8) & 0xFFu;
-    const uint32_t a = (o.w0 >> 16) & 0xFFu;
-    const uint32_t b = (o.w0 >> 24) & 0xFFu;
-    const uint32_t c = o.w1 & 0xFFu;
-    const uint32_t imm = o.w1 >> 8;
-    double* const Rd = R + dst * (P * STRIDE);
-    const double* const Ra = R + a * (P * STRIDE);
-    const double* const Rb = R + b * (P * STRIDE);
-    const double* const Rc = R + c * (P * STRIDE);
+WS_HD void ws_vm_exec_d(const WsDop& o, double* __restrict__ R, double (&acc)[P], const WsRng& rng,
+                        const uint64_t (&particle)[P]) {
+    const uint32_t op = o.op & 0xFFu;          // (bits 8.. : run length, see ws_vm_exec_sqlin2_run)
+    const uint32_t a = o.a, b = o.b, c = o.c;  // element offsets (WS_OFF_NONE: operand absent, pointer unused)
+    const uint32_t imm = o.imm;
+    double* const Rd = R + o.dst;
+    const double* const Ra = R + a;
+    const double* const Rb = R + b;
+    const double* const Rc = R + c;
     const double k0 = o.k0, k1 = o.k1, k2 = o.k2;
-    // r = k0 + k1 a + k2 b is most of every program (sums, affine means, Cholesky rows, residuals): decided
-    // by one compare instead of a walk down the switch's decision tree
-    if (op == WS_OP_LIN2) {
-        if (a == WS_REG_NONE && b == WS_REG_NONE) {
-#pragma unroll
-            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0;
-        } else if (a == WS_REG_NONE) {
-#pragma unroll
-            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k2 * Rb[j * STRIDE];
-        } else if (b == WS_REG_NONE) {
-#pragma unroll
-            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k1 * Ra[j * STRIDE];
-        } else {
+    // r = k0 + k1 a + k2 b is most of every program (sums, affine means, Cholesky rows, residuals)
+    if (op >= WS_DOP_LIN2_K) {
+        if (op == WS_DOP_LIN2_AB) {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 double v = k0 + k1 * Ra[j * STRIDE];
                 Rd[j * STRIDE] = v + k2 * Rb[j * STRIDE];
             }
+        } else if (op == WS_DOP_LIN2_A) {
+#pragma unroll
+            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0 + k1 * Ra[j * STRIDE];
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; ++j) Rd[j * STRIDE] = k0;
         }
         return;
     }
@@ -143,23 +200,23 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
         case WS_OP_MUL: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
-                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                const double A = (a == WS_OFF_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_OFF_NONE) ? k2 : Rb[j * STRIDE];
                 Rd[j * STRIDE] = k0 * A * B;
             }
         } break;
         case WS_OP_DIV: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
-                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                const double A = (a == WS_OFF_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_OFF_NONE) ? k2 : Rb[j * STRIDE];
                 Rd[j * STRIDE] = k0 * A / B;
             }
         } break;
         case WS_OP_UNARY: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
+                const double A = (a == WS_OFF_NONE) ? k1 : Ra[j * STRIDE];
                 double v;
                 switch (imm) {
                     case WS_UN_EXP: v = exp(A); break;
@@ -184,8 +241,8 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
         case WS_OP_POW: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
-                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                const double A = (a == WS_OFF_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_OFF_NONE) ? k2 : Rb[j * STRIDE];
                 Rd[j * STRIDE] = pow(A, B);
             }
         } break;
@@ -196,7 +253,7 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
                 for (int j = 0; j < P; ++j) {
                     const int64_t base = (int64_t)k1 + (int64_t)particle[j] * (int64_t)k2 + (int64_t)imm;
                     Rd[j * STRIDE] = rng.replay_n[base];
-                    if (a != WS_REG_NONE) const_cast<double*>(Ra)[j * STRIDE] = rng.replay_n[base + 1];
+                    if (a != WS_OFF_NONE) const_cast<double*>(Ra)[j * STRIDE] = rng.replay_n[base + 1];
                 }
             } else {
                 const uint64_t stream = ws_double_bits(k0);
@@ -205,7 +262,7 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
                     double z0, z1;
                     ws_randn2(particle[j], stream, rng.seed, z0, z1);
                     Rd[j * STRIDE] = z0;
-                    if (a != WS_REG_NONE) const_cast<double*>(Ra)[j * STRIDE] = z1;
+                    if (a != WS_OFF_NONE) const_cast<double*>(Ra)[j * STRIDE] = z1;
                 }
             }
         } break;
@@ -237,9 +294,9 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
         case WS_OP_LOGPDF_NORMAL: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double X = (a == WS_REG_NONE) ? k0 : Ra[j * STRIDE];
-                const double MU = (b == WS_REG_NONE) ? k1 : Rb[j * STRIDE];
-                const double SG = (c == WS_REG_NONE) ? k2 : Rc[j * STRIDE];
+                const double X = (a == WS_OFF_NONE) ? k0 : Ra[j * STRIDE];
+                const double MU = (b == WS_OFF_NONE) ? k1 : Rb[j * STRIDE];
+                const double SG = (c == WS_OFF_NONE) ? k2 : Rc[j * STRIDE];
                 acc[j] += ws_normal_logpdf(X, MU, SG);
             }
         } break;
@@ -248,7 +305,7 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
             // D = X - MU with MU = r[b] (always a register) and X = r[a] or the constant k0.
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double X = (a == WS_REG_NONE) ? k0 : Ra[j * STRIDE];
+                const double X = (a == WS_OFF_NONE) ? k0 : Ra[j * STRIDE];
                 const double z = (X - Rb[j * STRIDE]) * k1;
                 acc[j] += k2 - 0.5 * (z * z);
             }
@@ -256,8 +313,8 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
         case WS_OP_LOGPDF_EXPON: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double X = (a == WS_REG_NONE) ? k0 : Ra[j * STRIDE];
-                const double TH = (b == WS_REG_NONE) ? k1 : Rb[j * STRIDE];
+                const double X = (a == WS_OFF_NONE) ? k0 : Ra[j * STRIDE];
+                const double TH = (b == WS_OFF_NONE) ? k1 : Rb[j * STRIDE];
                 acc[j] += ws_exponential_logpdf(X, TH);
             }
         } break;
@@ -265,8 +322,8 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 double v = k0;
-                if (a != WS_REG_NONE) v += k1 * Ra[j * STRIDE];
-                if (b != WS_REG_NONE) v += k2 * Rb[j * STRIDE];
+                if (a != WS_OFF_NONE) v += k1 * Ra[j * STRIDE];
+                if (b != WS_OFF_NONE) v += k2 * Rb[j * STRIDE];
                 acc[j] += v;
             }
         } break;
@@ -274,11 +331,11 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 double v = k0;
-                if (a != WS_REG_NONE) {
+                if (a != WS_OFF_NONE) {
                     const double t = Ra[j * STRIDE];
                     v += k1 * t * t;
                 }
-                if (b != WS_REG_NONE) {
+                if (b != WS_OFF_NONE) {
                     const double t = Rb[j * STRIDE];
                     v += k2 * t * t;
                 }
@@ -288,8 +345,8 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
         case WS_OP_CMP: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
-                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                const double A = (a == WS_OFF_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_OFF_NONE) ? k2 : Rb[j * STRIDE];
                 const bool t = (imm == 0) ? (A < B) : ((imm == 1) ? (A <= B) : (A == B));
                 Rd[j * STRIDE] = t ? 1.0 : 0.0;
             }
@@ -297,16 +354,16 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
         case WS_OP_SELECT: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
-                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                const double A = (a == WS_OFF_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_OFF_NONE) ? k2 : Rb[j * STRIDE];
                 Rd[j * STRIDE] = (Rc[j * STRIDE] != 0.0) ? A : B;
             }
         } break;
         case WS_OP_MINMAX: {
 #pragma unroll
             for (int j = 0; j < P; ++j) {
-                const double A = (a == WS_REG_NONE) ? k1 : Ra[j * STRIDE];
-                const double B = (b == WS_REG_NONE) ? k2 : Rb[j * STRIDE];
+                const double A = (a == WS_OFF_NONE) ? k1 : Ra[j * STRIDE];
+                const double B = (b == WS_OFF_NONE) ? k2 : Rb[j * STRIDE];
                 Rd[j * STRIDE] = imm ? fmax(A, B) : fmin(A, B);
             }
         } break;
@@ -314,8 +371,8 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 double z = k0;
-                if (a != WS_REG_NONE) z += k1 * Ra[j * STRIDE];
-                if (b != WS_REG_NONE) z += k2 * Rb[j * STRIDE];
+                if (a != WS_OFF_NONE) z += k1 * Ra[j * STRIDE];
+                if (b != WS_OFF_NONE) z += k2 * Rb[j * STRIDE];
                 acc[j] -= 0.5 * (z * z);
             }
         } break;
@@ -323,8 +380,8 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
 #pragma unroll
             for (int j = 0; j < P; ++j) {
                 double z = k0;
-                if (a != WS_REG_NONE) z += k1 * Ra[j * STRIDE];
-                if (b != WS_REG_NONE) z += k2 * Rb[j * STRIDE];
+                if (a != WS_OFF_NONE) z += k1 * Ra[j * STRIDE];
+                if (b != WS_OFF_NONE) z += k2 * Rb[j * STRIDE];
                 z *= Rc[j * STRIDE];
                 acc[j] -= 0.5 * (z * z) + Rd[j * STRIDE];
             }
@@ -335,4 +392,70 @@ WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], c
         } break;
         default: break;
     }
+}
+
+// A run of `len` consecutive ACC_SQLIN2 (or ACC_SQLIN2_S) entries over the SAME registers, e.g. the likelihood
+// of a regression, sum_i logN(y_i; alpha + beta x_i, sigma): the operands are read from the register file once
+// and each entry costs its three coefficients and four FP64 operations per particle, in the same order and
+// with the same roundings as entry-by-entry execution (score-tape folds; run[0].op >> 8 == len).
+template <int STRIDE, int P>
+WS_HD void ws_vm_exec_sqlin2_run(const WsDop* __restrict__ run, int len, const double* __restrict__ R, double (&acc)[P]) {
+    const WsDop& h = run[0];
+    const bool scaled = (h.op & 0xFFu) == WS_OP_ACC_SQLIN2_S;
+    const bool ha = h.a != WS_OFF_NONE, hb = h.b != WS_OFF_NONE;
+    double A[P], B[P], C[P], D[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        A[j] = ha ? R[h.a + j * STRIDE] : 0.0;
+        B[j] = hb ? R[h.b + j * STRIDE] : 0.0;
+        C[j] = scaled ? R[h.c + j * STRIDE] : 1.0;
+        D[j] = scaled ? R[h.dst + j * STRIDE] : 0.0;
+    }
+    if (ha && hb && !scaled) {
+        for (int i = 0; i < len; ++i) {
+            const double k0 = run[i].k0, k1 = run[i].k1, k2 = run[i].k2;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double z = k0;
+                z += k1 * A[j];
+                z += k2 * B[j];
+                acc[j] -= 0.5 * (z * z);
+            }
+        }
+    } else if (ha && hb) {
+        for (int i = 0; i < len; ++i) {
+            const double k0 = run[i].k0, k1 = run[i].k1, k2 = run[i].k2;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double z = k0;
+                z += k1 * A[j];
+                z += k2 * B[j];
+                z *= C[j];
+                acc[j] -= 0.5 * (z * z) + D[j];
+            }
+        }
+    } else {
+        for (int i = 0; i < len; ++i) {
+            const double k0 = run[i].k0, k1 = run[i].k1, k2 = run[i].k2;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                double z = k0;
+                if (ha) z += k1 * A[j];
+                if (hb) z += k2 * B[j];
+                if (scaled) {
+                    z *= C[j];
+                    acc[j] -= 0.5 * (z * z) + D[j];
+                } else {
+                    acc[j] -= 0.5 * (z * z);
+                }
+            }
+        }
+    }
+}
+
+// undecoded form (host harness, kernels that fetch ops per thread)
+template <int STRIDE, int P>
+WS_HD void ws_vm_exec(const WsOp& o, double* __restrict__ R, double (&acc)[P], const WsRng& rng,
+                      const uint64_t (&particle)[P]) {
+    ws_vm_exec_d<STRIDE, P>(ws_decode_op<STRIDE, P>(o), R, acc, rng, particle);
 }
