@@ -722,8 +722,8 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
 
     // per-warp window: first the 61-bit slot uniforms of the tile's slot range (Philox mode), then the
     // staged offspring
-    __shared__ unsigned long long win_all[WS_WARPS_PER_CTA][WS_RBUF_SLOTS];
-    static_assert(WS_RBUF_SLOTS * 8 >= WS_EXPAND_CHUNK * 4, "window too small for the offspring staging");
+    __shared__ __align__(16) unsigned long long win_all[WS_WARPS_PER_CTA][WS_RBUF_SLOTS];
+    static_assert(WS_RBUF_SLOTS * 8 >= (WS_EXPAND_CHUNK + 128) * 4 && (WS_RBUF_SLOTS * 8) % 16 == 0, "window too small for the offspring staging");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long* const rbuf = win_all[warp];
     int32_t* const out_s = reinterpret_cast<int32_t*>(win_all[warp]);
@@ -889,6 +889,58 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
             continue;
         }
 
+        // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m ---------------------------------
+        if (fend - fstart <= WS_EXPAND_CHUNK) {
+            // the common case: the tile's slots fit one staging window.  Every particle with offspring marks
+            // the FIRST of its slots with its index + 1 (one predicated store, no divergence on the family
+            // size); the other slots take the last mark before them (a running maximum: marks increase with
+            // the slot), resolved four slots per lane and round and written as 16-byte stores.
+            int32_t* const gdst = P.ancestors + (fstart - slot_base);
+            const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 2) & 3u);  // window starts 16-byte aligned in global memory
+            const int W = fend - fstart + pad;
+            const int rounds = (W + 127) >> 7;
+            int4* const w4 = reinterpret_cast<int4*>(out_s);
+            for (int r = 0; r < rounds; ++r) w4[r * 32 + lane] = make_int4(0, 0, 0, 0);
+            __syncwarp();
+            {
+                int lo = f_prev;
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                    const int hi = f[k];
+                    if (hi > lo) out_s[lo - fstart + pad] = item0 + k + 1;
+                    lo = hi;
+                }
+            }
+            __syncwarp();
+            int32_t* const dst = gdst - pad;
+            int carry = 0;
+            for (int r = 0; r < rounds; ++r) {
+                const int4 v = w4[r * 32 + lane];
+                const int m0 = v.x, m1 = max(m0, v.y), m2 = max(m1, v.z), m3 = max(m2, v.w);
+                int incl = m3;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl = max(incl, t);
+                }
+                int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 0;
+                excl = max(excl, carry);
+                carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+                const int4 o = make_int4(max(m0, excl) - 1, max(m1, excl) - 1, max(m2, excl) - 1, max(m3, excl) - 1);
+                const int p0 = r * 128 + lane * 4;
+                if (p0 >= pad && p0 + 4 <= W) {
+                    *reinterpret_cast<int4*>(dst + p0) = o;
+                } else {
+                    if (p0 >= pad && p0 < W) dst[p0] = o.x;
+                    if (p0 + 1 >= pad && p0 + 1 < W) dst[p0 + 1] = o.y;
+                    if (p0 + 2 >= pad && p0 + 2 < W) dst[p0 + 2] = o.z;
+                    if (p0 + 3 >= pad && p0 + 3 < W) dst[p0 + 3] = o.w;
+                }
+            }
+            __syncwarp();
+            continue;
+        }
         // does this lane own a family too large for one lane?
         bool has_big = false;
         {
@@ -900,31 +952,6 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
             }
         }
         const unsigned big_mask = __ballot_sync(0xffffffffu, has_big);
-
-        // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m, staged per chunk --------------
-        if (fend - fstart <= WS_EXPAND_CHUNK && big_mask == 0u) {
-            // the common case: the whole tile fits one staging window and every family is small
-            int lo = f_prev;
-#pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                const int hi = f[k];
-                const int id = item0 + k;
-                int32_t* o = out_s + (lo - fstart);
-                if (hi > lo) {
-                    o[0] = id;
-                    if (hi - lo > 1) {
-                        o[1] = id;
-                        for (int q = 2; q < hi - lo; ++q) o[q] = id;
-                    }
-                }
-                lo = hi;
-            }
-            __syncwarp();
-            int32_t* __restrict__ dst = P.ancestors + (fstart - slot_base);
-            for (int pos = lane; pos < fend - fstart; pos += 32) dst[pos] = out_s[pos];
-            __syncwarp();
-            continue;
-        }
         for (int chunk = fstart; chunk < fend; chunk += WS_EXPAND_CHUNK) {
             const int chunk_end = min(chunk + WS_EXPAND_CHUNK, fend);
             {
