@@ -335,3 +335,62 @@ def test_hierarchical_regression_benchmark_model(ws):
     rmse = float(np.sqrt(np.mean((a_est - a_true) ** 2)))
     assert rmse < 0.6, rmse                                   # posterior sd of alpha_j is ~ sigma / sqrt(10) = 0.32
     assert abs(float(np.sum(w * sp["beta"])) - 3.0) < 0.3 and abs(float(np.sum(w * sp["sigma"])) - 1.0) < 0.3
+
+
+@pytest.mark.parametrize("proposal", ["RW", "autoRW"])
+def test_moves_ks_against_exact_posterior_over_seeds(ws, proposal):
+    """north_star: MH moves under Philox must be statistically indistinguishable from the exact target.  Particles
+    start as exact draws of the Normal-Normal posterior; after 10 sweeps every particle must still be an exact
+    draw (invariance): one-sample KS against the analytic posterior CDF for five seeds (Bonferroni: p > 1e-3 / 5),
+    and the pooled posterior moments to 4 standard errors."""
+    import scipy.stats as sst
+    T, tau0, sigma, n = 6, 2.0, 1.0, 100_000
+    rng = np.random.default_rng(7)
+    y = rng.standard_normal(T) * sigma + 0.8
+    post_var = 1.0 / (1.0 / tau0 ** 2 + T / sigma ** 2)
+    post_mean = post_var * y.sum() / sigma ** 2
+    post = sst.norm(post_mean, math.sqrt(post_var))
+    pooled = []
+    for seed in range(1, 6):
+        st = ws.SMCState(n, seed=seed, device=0)
+        st.store.setcol("θ", rng.standard_normal(n) * math.sqrt(post_var) + post_mean)
+        st.root, st.depth = _static_model(ws, y, tau0, sigma), T + 1
+        mv = ws.Move(["θ"], ws.RW, (0.4,)) if proposal == "RW" else ws.Move(["θ"], ws.autoRW, ())
+        for _ in range(10):
+            mv.apply(st)
+        th = st["θ"]
+        assert 0.2 * n < mv.last.n_accepted < 0.95 * n
+        assert sst.kstest(th, post.cdf).pvalue > 1e-3 / 5, (proposal, seed)
+        pooled.append(th)
+    th = np.concatenate(pooled)
+    se = math.sqrt(post_var / th.size)
+    assert abs(th.mean() - post_mean) < 4 * se * 3          # x3: successive sweeps leave particles autocorrelated, not biased
+    assert abs(th.var() - post_var) < 4 * post_var * math.sqrt(2.0 / th.size) * 3
+
+
+def test_c3_philox_matches_oracle_with_numpy_streams_over_seeds(ws):
+    """The whole C3 pipeline (observe / resample / autoRW moves) under the device's Philox streams against the
+    CPU restatement driven by NumPy streams: posterior-mean estimates over seeds must agree within their
+    seed-to-seed scatter, and both with the exact conjugate posterior mean."""
+    n, npts, seeds = 4000, 25, 6
+    rng = np.random.default_rng(11)
+    xs = rng.uniform(0, 10, npts)
+    ys = 1.0 - 0.5 * xs + 0.5 * rng.standard_normal(npts)
+    # exact posterior mean of (α, β): prior N(0, 10² I), noise sd 1 (examples/linear_regression.jl:17-27)
+    X = np.stack([np.ones(npts), xs], axis=1)
+    exact = np.linalg.solve(X.T @ X + np.eye(2) / 100.0, X.T @ ys)
+    dev, cpu = [], []
+    for seed in range(seeds):
+        st = ws.SMCState(n, ess_perc_min=0.5, seed=100 + seed, device=0)
+        ws.run(ws.model(LINREG)(xs, ys), st)
+        dev.append([ws.E(lambda α: α, st), ws.E(lambda β: β, st)])
+        r2 = np.random.default_rng(200 + seed)
+        ost = ref.OracleState(n, ref.Streams(r2.standard_normal(n * (2 + 2 * npts)), r2.random(n * 3 * npts)), ess_perc_min=0.5)
+        ref.run(ws.model(LINREG)(xs, ys), ost)
+        w = ref.exp_norm(ost.weights)
+        cpu.append([float(np.sum(w * ost.cols["α"])), float(np.sum(w * ost.cols["β"]))])
+    dev, cpu = np.array(dev), np.array(cpu)
+    for k in range(2):
+        scatter = math.sqrt(dev[:, k].var(ddof=1) / seeds + cpu[:, k].var(ddof=1) / seeds)
+        assert abs(dev[:, k].mean() - cpu[:, k].mean()) < 5 * scatter + 1e-3, (k, dev[:, k], cpu[:, k])
+        assert abs(dev[:, k].mean() - exact[k]) < 5 * math.sqrt(dev[:, k].var(ddof=1) / seeds) + 5e-3, (k, dev[:, k], exact)
