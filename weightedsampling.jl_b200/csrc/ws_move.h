@@ -7,6 +7,7 @@
 #define WS_MOVE_BLOCK 128
 #define WS_SCORE_TEMPS 12        // registers [0, 12) of a score program are statement temporaries
 #define WS_SCORE_MAX_REGS 200    // 200 * 128 * 8 B = 200 KB of shared memory at most
+#define WS_SCORE_SEG_REGS 64     // register-file rows of one SEGMENT of a wide tape: 64 KB, three CTAs per SM (measured 200: 6.8 s, 96: 4.1 s, 64: 3.4 s, 28: 3.3 s on C4 J=512; env WSB200_SEG_REGS overrides)
 #define WS_SCORE_MAX_LOADS (WS_SCORE_MAX_REGS - WS_SCORE_TEMPS)
 #define WS_MOVE_MAX_D 8
 

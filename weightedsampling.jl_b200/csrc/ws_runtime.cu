@@ -224,6 +224,8 @@ struct ws_ctx {
 
     // scratch for MH / analysis
     double* d_scratch = nullptr;
+    void* d_scratch2 = nullptr;  // second grow-only scratch (sharded distinct count: receive buffer + owner table)
+    size_t scratch2_bytes = 0;
     size_t scratch_bytes = 0;
     double* h_scratch = nullptr;  // pinned
     size_t h_scratch_bytes = 0;
@@ -369,6 +371,19 @@ static int ensure_scratch(ws_ctx* c, size_t bytes) {
     }
     CK(c, cudaMalloc(&c->d_scratch, bytes));
     c->scratch_bytes = bytes;
+    return WS_OK;
+}
+static int ensure_scratch2(ws_ctx* c, size_t bytes) {
+    if (c->scratch2_bytes >= bytes) return WS_OK;
+    if (c->d_scratch2 != nullptr) {
+        CK(c, cudaStreamSynchronize(c->stream));
+        CK(c, cudaFree(c->d_scratch2));
+        c->d_scratch2 = nullptr;
+        c->scratch2_bytes = 0;
+    }
+    bytes += bytes / 4;  // head room: the receive count varies a little from call to call
+    CK(c, cudaMalloc(&c->d_scratch2, bytes));
+    c->scratch2_bytes = bytes;
     return WS_OK;
 }
 static int ensure_h_scratch(ws_ctx* c, size_t bytes) {
@@ -565,6 +580,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
                 c->rank, c->phase_ms[0] / c->phase_n, c->phase_ms[1] / c->phase_n, c->phase_ms[2] / c->phase_n,
                 c->phase_ms[3] / c->phase_n, c->phase_ms[5] / std::max<int64_t>(1, c->phase_n - 6), c->phase_ms[4] / c->phase_n,
                 (long long)c->phase_n);
+    if (c->d_scratch2) cudaFree(c->d_scratch2);
     for (auto& sl : c->slabs) cudaFree(sl.base);  // planes and ancestor vectors
     cudaFree(c->logw);
     cudaFree(c->d_partials);
@@ -2256,12 +2272,17 @@ static int upload_score_program(ws_ctx* c) {
 // for a move, factors that do not involve a target cancel in s_new - s_old.
 template <class F>
 static int for_each_tape_segment(ws_ctx* c, int64_t target_depth, const std::vector<Plane>* only, F run) {
+    static const int seg_regs = [] {
+        const char* e = getenv("WSB200_SEG_REGS");
+        const int v = e ? atoi(e) : WS_SCORE_SEG_REGS;
+        return std::min(WS_SCORE_MAX_REGS, std::max(WS_SCORE_TEMPS + 4, v));
+    }();
     auto fresh = [] {
         Program p;
         p.score_mode = true;
         p.temp_base = 0;
         p.n_temp_slots = WS_SCORE_TEMPS;
-        p.max_regs = WS_SCORE_MAX_REGS;
+        p.max_regs = seg_regs;
         p.max_ops = 1 << 30;
         p.max_io = WS_SCORE_MAX_LOADS;
         return p;
@@ -2447,10 +2468,11 @@ extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t
             std::vector<unsigned long long> cnt(R), all((size_t)R * R);
             CK(c, cudaMemcpyAsync(cnt.data(), part_count, sizeof(unsigned long long) * R, cudaMemcpyDeviceToHost, c->stream));
             CK(c, cudaStreamSynchronize(c->stream));
-            unsigned long long* d_cnt = nullptr;
-            TempBuf cntbuf, recvbuf, table2;
-            CK(c, cudaMalloc(&cntbuf.p, sizeof(unsigned long long) * (size_t)R * (R + 1)));
-            d_cnt = (unsigned long long*)cntbuf.p;
+            // [counts R x (R+1) | received keys | owner table]: one grow-only buffer (a cudaMalloc / cudaFree per
+            // diversity check cost milliseconds each, more than the count itself)
+            const size_t cnt_words = ((size_t)R * (R + 1) + 31) & ~(size_t)31;
+            TRY(ensure_scratch2(c, sizeof(unsigned long long) * cnt_words));
+            unsigned long long* d_cnt = (unsigned long long*)c->d_scratch2;
             CK(c, cudaMemcpyAsync(d_cnt + (size_t)R * R, cnt.data(), sizeof(unsigned long long) * R, cudaMemcpyHostToDevice, c->stream));
             NCK(c, g_nccl.AllGather(d_cnt + (size_t)R * R, d_cnt, (size_t)R, WS_NCCL_UINT64, c->comm, c->stream));
             CK(c, cudaMemcpyAsync(all.data(), d_cnt, sizeof(unsigned long long) * (size_t)R * R, cudaMemcpyDeviceToHost, c->stream));
@@ -2461,8 +2483,11 @@ extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t
                 roff[q] = n_recv;
                 n_recv += (size_t)all[(size_t)q * R + c->rank];  // what q holds for me
             }
-            CK(c, cudaMalloc(&recvbuf.p, sizeof(unsigned long long) * std::max<size_t>(n_recv, 1)));
-            unsigned long long* d_recv = (unsigned long long*)recvbuf.p;
+            size_t slots2 = 1;
+            while (slots2 < std::max<size_t>(n_recv, 1) * 2) slots2 <<= 1;
+            const size_t recv_words = (std::max<size_t>(n_recv, 1) + 31) & ~(size_t)31;
+            TRY(ensure_scratch2(c, sizeof(unsigned long long) * (cnt_words + recv_words + slots2 + 8)));  // nothing in flight uses it yet
+            unsigned long long* d_recv = (unsigned long long*)c->d_scratch2 + cnt_words;
             NCK(c, g_nccl.GroupStart());
             for (int d = 0; d < R; ++d) {
                 if (cnt[d] > 0) NCK(c, g_nccl.Send(part_base + (size_t)d * part_cap, (size_t)cnt[d], WS_NCCL_UINT64, d, c->comm, c->stream));
@@ -2470,10 +2495,7 @@ extern "C" int ws_marginal_diversity(ws_ctx* c, int32_t n_targets, const int32_t
                 if (rc > 0) NCK(c, g_nccl.Recv(d_recv + roff[d], rc, WS_NCCL_UINT64, d, c->comm, c->stream));
             }
             NCK(c, g_nccl.GroupEnd());
-            size_t slots2 = 1;
-            while (slots2 < std::max<size_t>(n_recv, 1) * 2) slots2 <<= 1;
-            CK(c, cudaMalloc(&table2.p, sizeof(unsigned long long) * (slots2 + 8)));
-            unsigned long long* t2 = (unsigned long long*)table2.p;
+            unsigned long long* t2 = d_recv + recv_words;
             CK(c, ws_launch_unique_count((const double*)d_recv, (int64_t)n_recv, t2, slots2, t2 + slots2, c->sm_count, c->stream, 1));
             c->stats.kernel_launches++;
             unsigned long long mine = 0;
