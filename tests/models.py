@@ -29,6 +29,20 @@ SSM2D = '''
 end
 '''
 
+SSM2D_FILTER = '''
+@model function ssm2d_filter(obs)
+    I2 = [1.0 0.0; 0.0 1.0]
+    x .= [0.0, 0.0]
+    v .= [1.0, 0.0]
+    for o in obs
+        x .= x + v
+        dv ~ MvNormal([0.0, 0.0], 0.1 * I2)
+        v .= v + dv
+        o => MvNormal(x, 0.5 * I2)
+    end
+end
+'''
+
 LINREG = '''
 @model function linear_regression(xs, ys)
     α ~ Normal(0.0, 10.0)
