@@ -147,3 +147,53 @@ def test_sharded_eight_schools_with_diversity_gated_moves():
         assert o[5] == single.stats()["moves_run"] and o[6] == single.stats()["resamples_done"]
     assert abs(out[0][4] - div1) < 5e-4
     assert differ < 0.002 * n
+
+
+def _worker_describe(rank, world, port, n, T, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import wsb200 as ws
+    st = ws.sharded_state(n, device=rank, seed=77, ess_perc_min=0.5)
+    ws.run(ws.model(MODEL)(_obs(T)), st)
+    d = ws.describe(st)
+    q.put((rank, d.to_dict("list")))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_describe_equals_single_gpu():
+    """describe (src/utils.jl:183-289) on a sharded state: shard partials merged across ranks, the median's radix select
+    over all-reduced fixed-point histograms.  Every rank must report the single-GPU numbers (the particles are the
+    same, bit for bit; sums differ by their order only, the median and the extrema not at all)."""
+    world = 2
+    if _ngpu() < world:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import wsb200 as ws
+    n, T = 100_003, 9          # ends on a weighted state (ESS gate 0.5): the weights matter
+    single = ws.SMCState(n, device=0, seed=77, ess_perc_min=0.5)
+    ws.run(ws.model(MODEL)(_obs(T)), single)
+    d1 = ws.describe(single).to_dict("list")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_describe, args=(r, world, 29771, n, T, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert out[0][1]["variable"] == d1["variable"]
+    for _, d in out:
+        for f in ("mean", "std", "ess"):
+            for a, b in zip(d[f], d1[f]):
+                np.testing.assert_allclose(np.asarray(a, dtype=float), np.asarray(b, dtype=float), rtol=1e-10, atol=1e-12)
+        for f in ("median", "min", "max"):
+            for a, b in zip(d[f], d1[f]):
+                assert np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float)), (f, a, b)
+        assert d["hist"] == d1["hist"]
+    # ... and the ranks agree with each other to the last bit
+    assert all(np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
+               for f in ("mean", "median", "std", "min", "max") for a, b in zip(out[0][1][f], out[1][1][f]))

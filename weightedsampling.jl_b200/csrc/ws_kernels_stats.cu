@@ -12,6 +12,8 @@
 //   pass F   neighbours of the selected value: largest smaller value, smallest weight at the value
 // All of it is HBM streaming work: 8 (x) + 8 (q) bytes per particle and pass.
 #include <cub/cub.cuh>
+#include <vector>
+#include <string.h>
 #include "ws_internal.h"
 #include "ws_stats.h"
 
@@ -264,8 +266,21 @@ size_t ws_stats_scratch_bytes(int64_t n) {
     return g * sizeof(WsStat1) + g * 9 * sizeof(double) + g * sizeof(WsStatF) + 256 * 8 + 8 * 8 + 256;
 }
 
+static void stat1_merge_host(WsStat1& a, const WsStat1& b) {
+    a.swx += b.swx;
+    a.sw += b.sw;
+    a.mn = fmin(a.mn, b.mn);
+    a.mx = fmax(a.mx, b.mx);
+    a.has_nan |= b.has_nan;
+    if (b.minv_nz < a.minv_nz || (b.minv_nz == a.minv_nz && b.minw_nz < a.minw_nz)) {
+        a.minv_nz = b.minv_nz;
+        a.minw_nz = b.minw_nz;
+    }
+}
+
 cudaError_t ws_stats_plane(const double* x, const unsigned long long* q, int64_t n, void* d_scratch, void* h_scratch,
-                           cudaStream_t s, WsPlaneStats* out, int* n_launches) {
+                           cudaStream_t s, WsPlaneStats* out, int* n_launches, const WsStatsComm* comm) {
+    static_assert(sizeof(WsStat1) % 8 == 0, "WsStat1 travels as 64-bit words");
     const int g = stats_grid(n);
     char* dp = (char*)d_scratch;
     char* hp = (char*)h_scratch;
@@ -285,16 +300,16 @@ cudaError_t ws_stats_plane(const double* x, const unsigned long long* q, int64_t
     if ((e = cudaMemcpyAsync(h1, d1, sizeof(WsStat1) * g, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(s)) != cudaSuccess) return e;
     WsStat1 a = h1[0];
-    for (int k = 1; k < g; ++k) {
-        const WsStat1& b = h1[k];
-        a.swx += b.swx;
-        a.sw += b.sw;
-        a.mn = fmin(a.mn, b.mn);
-        a.mx = fmax(a.mx, b.mx);
-        a.has_nan |= b.has_nan;
-        if (b.minv_nz < a.minv_nz || (b.minv_nz == a.minv_nz && b.minw_nz < a.minw_nz)) {
-            a.minv_nz = b.minv_nz;
-            a.minw_nz = b.minw_nz;
+    for (int k = 1; k < g; ++k) stat1_merge_host(a, h1[k]);
+    if (comm != nullptr) {  // shard partials -> global, merged in rank order on every rank
+        const size_t words = sizeof(WsStat1) / 8;
+        std::vector<unsigned long long> all(words * (size_t)comm->nranks);
+        if (comm->allgather_words(comm->ctx, reinterpret_cast<const unsigned long long*>(&a), words, all.data()) != 0) return cudaErrorUnknown;
+        memcpy(&a, all.data(), sizeof(WsStat1));
+        for (int r = 1; r < comm->nranks; ++r) {
+            WsStat1 b;
+            memcpy(&b, all.data() + words * (size_t)r, sizeof(WsStat1));
+            stat1_merge_host(a, b);
         }
     }
     *n_launches = 1;
@@ -317,6 +332,7 @@ cudaError_t ws_stats_plane(const double* x, const unsigned long long* q, int64_t
     if ((e = cudaMemsetAsync(d_hist, 0, 256 * 8, s)) != cudaSuccess) return e;
     for (int pass = 0; pass < 8; ++pass) {
         ws_stats_hist_kernel<<<g, 256, 0, s>>>(x, q, n, pass, d_state, d_hist);
+        if (comm != nullptr && comm->allreduce_u64_device(comm->ctx, d_hist, 256) != 0) return cudaErrorUnknown;  // exact integer sums
         ws_stats_pick_kernel<<<1, 32, 0, s>>>(pass, d_state, d_hist);
     }
     ws_stats_final_kernel<<<g, 256, 0, s>>>(x, q, n, d_state, dF);
@@ -331,12 +347,28 @@ cudaError_t ws_stats_plane(const double* x, const unsigned long long* q, int64_t
         ss += h2[(size_t)b * 9];
         for (int k = 0; k < 8; ++k) out->hist[k] += h2[(size_t)b * 9 + 1 + k];
     }
+    if (comm != nullptr) {
+        double v[9] = {ss};
+        for (int k = 0; k < 8; ++k) v[1 + k] = out->hist[k];
+        if (comm->allreduce_doubles(comm->ctx, v, 9) != 0) return cudaErrorUnknown;
+        ss = v[0];
+        for (int k = 0; k < 8; ++k) out->hist[k] = v[1 + k];
+    }
     out->std = sqrt(ss / a.sw);
 
     unsigned long long pk = 0ull, mq = ~0ull;
     for (int b = 0; b < g; ++b) {
         pk = hF[b].prev_key > pk ? hF[b].prev_key : pk;
         mq = hF[b].minq_eq < mq ? hF[b].minq_eq : mq;
+    }
+    if (comm != nullptr) {
+        const unsigned long long mine[2] = {pk, mq};
+        std::vector<unsigned long long> all(2 * (size_t)comm->nranks);
+        if (comm->allgather_words(comm->ctx, mine, 2, all.data()) != 0) return cudaErrorUnknown;
+        for (int r = 0; r < comm->nranks; ++r) {
+            pk = all[2 * r] > pk ? all[2 * r] : pk;
+            mq = all[2 * r + 1] < mq ? all[2 * r + 1] : mq;
+        }
     }
     const unsigned long long sel = h_state[0], below = h_state[1];
     auto val = [](unsigned long long k) {

@@ -2787,11 +2787,43 @@ extern "C" int ws_set_lazy_gather(ws_ctx* c, int on) {
     c->lazy_gather = on != 0;
     return WS_OK;
 }
+// cross-rank hooks of a sharded describe (ws_stats.h: WsStatsComm)
+static int stats_allgather_words(void* ctx, const unsigned long long* in, size_t words, unsigned long long* out) {
+    ws_ctx* c = (ws_ctx*)ctx;
+    const size_t R = (size_t)c->nranks;
+    TRY(ensure_scratch2(c, sizeof(unsigned long long) * words * (R + 1)));
+    unsigned long long* d = (unsigned long long*)c->d_scratch2;
+    CK(c, cudaMemcpyAsync(d + words * R, in, sizeof(unsigned long long) * words, cudaMemcpyHostToDevice, c->stream));
+    NCK(c, g_nccl.AllGather(d + words * R, d, words, WS_NCCL_UINT64, c->comm, c->stream));
+    CK(c, cudaMemcpyAsync(out, d, sizeof(unsigned long long) * words * R, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return WS_OK;
+}
+static int stats_allreduce_doubles(void* ctx, double* v, int n) {
+    ws_ctx* c = (ws_ctx*)ctx;
+    TRY(ensure_scratch2(c, sizeof(double) * (size_t)n));
+    CK(c, cudaMemcpyAsync(c->d_scratch2, v, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    NCK(c, g_nccl.AllReduce(c->d_scratch2, c->d_scratch2, (size_t)n, WS_NCCL_FLOAT64, WS_NCCL_SUM, c->comm, c->stream));
+    CK(c, cudaMemcpyAsync(v, c->d_scratch2, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return WS_OK;
+}
+static int stats_allreduce_u64_device(void* ctx, unsigned long long* d, size_t n) {
+    ws_ctx* c = (ws_ctx*)ctx;
+    NCK(c, g_nccl.AllReduce(d, d, n, WS_NCCL_UINT64, WS_NCCL_SUM, c->comm, c->stream));
+    return WS_OK;
+}
+
 extern "C" int ws_describe(ws_ctx* c, int32_t n_planes, const int32_t* col, const int32_t* comp, ws_plane_stats* out, double* ess) {
     if (!c || !col || !comp || !out || n_planes < 1) return c ? fail(c, WS_EINVAL, "ws_describe: bad arguments") : WS_EINVAL;
-    if (c->nranks > 1) return fail(c, WS_EUNSUPPORTED, "ws_describe on a sharded state is not built yet (download the shards)");
     for (int t = 0; t < n_planes; ++t) TRY(check_plane(c, col[t], comp[t]));
-    TRY(ensure_reduced(c));  // flushes the window; (m, S, Q) of the current log-weights
+    TRY(ensure_reduced(c));  // flushes the window; (m, S, Q) of the current log-weights (global on a sharded state)
+    WsStatsComm comm{c, c->nranks, stats_allgather_words, stats_allreduce_doubles, stats_allreduce_u64_device};
+    if (c->nranks > 1) {  // sharded states have no genealogy: bring the planes into the current particle order first
+        std::vector<Plane> pl;
+        for (int t = 0; t < n_planes; ++t) pl.push_back(Plane{col[t], comp[t]});
+        TRY(materialize_planes(c, &pl));
+    }
     CK(c, cudaSetDevice(c->device));
     static_assert(sizeof(ws_plane_stats) == sizeof(WsPlaneStats), "ws_plane_stats layout");
     const size_t sb = ws_stats_scratch_bytes(c->n);
@@ -2824,7 +2856,7 @@ extern "C" int ws_describe(ws_ctx* c, int32_t n_planes, const int32_t* col, cons
         }
         int launches = 0;
         WsPlaneStats ps;
-        CK(c, ws_stats_plane(x, d_q, c->n, c->d_scratch, c->h_scratch, c->stream, &ps, &launches));
+        CK(c, ws_stats_plane(x, d_q, c->n, c->d_scratch, c->h_scratch, c->stream, &ps, &launches, c->nranks > 1 ? &comm : nullptr));
         c->stats.kernel_launches += launches;
         memcpy(&out[t], &ps, sizeof(ps));
     }
