@@ -289,11 +289,11 @@ def main():
         if name == "gather" and not eager:
             continue    # deferred gather: this class only stages the few offspring that migrate between ranks
         if k["launches"] > 0 and k["ms"] > 0:
-            avg_ms = k["ms"] / k["launches"]
+            avg_ms = k["ms"] / max(1, K)     # per step (a sharded step times the search in two regions)
             gbs = alg * N / (avg_ms * 1e-3) / 1e9
             per_kernel[name] = {"avg_ms": avg_ms, "launches": k["launches"], "alg_bytes_per_particle": alg,
                                 "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": k["ms"] / dev_ms}
-    dom = max(per_kernel, key=lambda n: per_kernel[n]["avg_ms"] * per_kernel[n]["launches"]) if per_kernel else None
+    dom = max(per_kernel, key=lambda n: per_kernel[n]["avg_ms"]) if per_kernel else None
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": {"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",
