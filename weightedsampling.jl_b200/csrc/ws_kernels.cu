@@ -540,7 +540,13 @@ __device__ __forceinline__ void ws_slot_split(unsigned long long C, unsigned int
     frac = lo & WS_FXS_FRAC_MASK;
 }
 
-__global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __grid_constant__ WsScanParams P) {
+#ifndef WS_CDF_MINB
+#define WS_CDF_MINB 5   // <= 51 registers: five CTAs per SM (measured against 1 / 4 with grids of 3, 4, 8 CTAs per SM)
+#endif
+#ifndef WS_CDF_GRID
+#define WS_CDF_GRID 5
+#endif
+__global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
     __shared__ unsigned long long warp_tot[WS_SCAN_BLOCK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -553,6 +559,27 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __gri
     }
     const double rS = 1.0 / Sden;
     const double uniform_w = 1.0 / (double)P.n_slots;
+    // the log-weights of the NEXT tile are requested before the current tile is processed: the kernel was waiting on
+    // its loads (long-scoreboard stalls, profiles/r1t_ncu_ws_cdf_tiles_kernel_20M.txt), not on the arithmetic
+    auto load_tile = [&](int tile, double (&l)[WS_SCAN_ITEMS]) {
+        const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
+        if (item0 + WS_SCAN_ITEMS <= n) {
+            const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                double2 v = __ldg(p2 + k);
+                l[2 * k] = v.x;
+                l[2 * k + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : -INFINITY;
+        }
+    };
+    double l_next[WS_SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < WS_SCAN_ITEMS; ++k) l_next[k] = -INFINITY;
+    if (P.mode != 2 && (int)blockIdx.x < n_tiles) load_tile(blockIdx.x, l_next);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
         unsigned long long q[WS_SCAN_ITEMS];
@@ -561,18 +588,9 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_cdf_tiles_kernel(const __gri
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(uniform_w) : 0ull;
         } else {
             double l[WS_SCAN_ITEMS];
-            if (item0 + WS_SCAN_ITEMS <= n) {
-                const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
 #pragma unroll
-                for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
-                    double2 v = __ldg(p2 + k);
-                    l[2 * k] = v.x;
-                    l[2 * k + 1] = v.y;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : -INFINITY;
-            }
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = l_next[k];
+            if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x, l_next);
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
                 double w;
@@ -1020,7 +1038,7 @@ __global__ void __launch_bounds__(256) ws_expand_heavy_kernel(const __grid_const
 
 cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s) {
     const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
-    int g1 = (int)(cdf_tiles < (int64_t)g_sm_count * 8 ? cdf_tiles : (int64_t)g_sm_count * 8);
+    int g1 = (int)(cdf_tiles < (int64_t)g_sm_count * WS_CDF_GRID ? cdf_tiles : (int64_t)g_sm_count * WS_CDF_GRID);
     if (g1 < 1) g1 = 1;
     ws_cdf_tiles_kernel<<<g1, WS_SCAN_BLOCK, 0, s>>>(P);
     cudaError_t e = cudaGetLastError();
