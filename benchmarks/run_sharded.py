@@ -44,6 +44,14 @@ def max_over_ranks(x, world, local):
     return float(t.item())
 
 
+def sum_over_ranks(x, world, local):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=torch.device("cuda", local))
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
 def emit(rank, **kw):
     if rank == 0:
         print(json.dumps(kw), flush=True)
@@ -137,10 +145,64 @@ def c5(rank, world, local):
             del st
 
 
+def c5skew(rank, world, local):
+    """The migration path under load: log-weights fall with the GLOBAL particle index (logw = -lambda i / N), so the
+    low ranks hold almost all of the mass and most offspring must cross shard boundaries over NVLink (SURVEY 8e:
+    worst-case egress of one heavy rank ~ N 8P (R-1)/R bytes).  Reported against the measured NVLink peer bandwidth
+    (770 GB/s per direction, B200_PROFILING.md)."""
+    import ctypes as C
+    if world < 2:
+        return
+    NVLINK = 770.0
+    per_gpu, P = 100_000_000, 6
+    n = per_gpu * world
+    for lam in (2.0, 10.0):
+        st = make_state(n, world, local, ess_perc_min=float("inf"), seed=0x5EED)
+        store = st.store
+        for p in range(P):
+            ws.Sample(f"p{p}", "Normal", (0.0, 1.0)).apply(st)
+        lo, hi = ws.shard_bounds(n, rank, world)
+        g = (np.arange(lo, hi, dtype=np.float64)) / float(n)
+        store._call("ws_set_timing", 1)
+        times, mig = [], []
+        for rep in range(3):
+            store.setcol("g", g)
+            ws.Weight(None, (ws.col("g") * (-lam),)).apply(st)
+            st.sync()
+            m0 = C.c_int64()
+            store._call("ws_get_migrated", C.byref(m0))
+            dist.barrier()
+            t0 = time.perf_counter()
+            r = ws.Resample()
+            r.apply(st)
+            st.sync()
+            dt = max_over_ranks(time.perf_counter() - t0, world, local)
+            m1 = C.c_int64()
+            store._call("ws_get_migrated", C.byref(m1))
+            if rep > 0:
+                times.append(dt * 1e3)
+                mig.append(m1.value - m0.value)
+        ms = float(np.median(times))
+        planes = P + 1
+        sent = float(np.mean(mig))
+        sent_max = max_over_ranks(sent, world, local)     # busiest receiver (ingress)
+        sent_sum = sum_over_ranks(sent, world, local)     # all migrants: with the mass on rank 0 ~ that rank's egress
+        emit(rank, config=f"C5 rank-skewed resample (logw = -{lam} i/N), N={per_gpu} per GPU x {world}, payload={P}+1 planes",
+             ms=ms, ess_perc=r.last.ess_perc, particles_per_sec=n / (ms * 1e-3),
+             received_particles_max_rank=sent_max, received_bytes_max_rank=sent_max * 8 * planes,
+             migrated_particles_total=sent_sum, migrated_bytes_total=sent_sum * 8 * planes,
+             nvlink_ingress_gbs_max_rank=sent_max * 8 * planes / (ms * 1e-3) / 1e9,
+             nvlink_egress_gbs_if_one_source=sent_sum * 8 * planes / (ms * 1e-3) / 1e9,
+             nvlink_frac_of_770=max(sent_max, sent_sum if lam >= 10 else sent_max) * 8 * planes / (ms * 1e-3) / 1e9 / NVLINK, n_gpus=world,
+             timing="host wall clock around Resample incl. migration and gather (sync on both sides), max over ranks; "
+                    "the NVLink figure divides the busiest rank's migrated bytes by the WHOLE step time")
+        del st
+
+
 if __name__ == "__main__":
     rank, world, local = setup()
-    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c4", "c5"]
+    which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c4", "c5", "c5skew"]
     for w in which:
-        {"c4": c4, "c5": c5}[w](rank, world, local)
+        {"c4": c4, "c5": c5, "c5skew": c5skew}[w](rank, world, local)
     if world > 1:
         dist.destroy_process_group()
