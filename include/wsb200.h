@@ -337,6 +337,9 @@ int ws_col_events_behind(ws_ctx* ctx, int32_t id, int64_t* out);
 int ws_set_timing(ws_ctx* ctx, int on); /* record per-phase CUDA events (adds syncs; for profiling only) */
 /* sharded state: particles this rank has received from other ranks in all resampling steps so far */
 int ws_get_migrated(ws_ctx* ctx, int64_t* out);
+/* offspring this rank has written DIRECTLY into other ranks' planes over NVLink (peer mappings; the exchange falls back to
+ * stage + ncclSend / ncclRecv for a handful of migrants, with WSB200_EXCHANGE=nccl, or when ranks share a process) */
+int ws_get_pushed(ws_ctx* ctx, int64_t* out);
 /* the Philox stream id the next random statement / resample will use, and the key (tests reproduce draws) */
 int ws_next_philox_stream(ws_ctx* ctx, uint64_t* stream_out, uint64_t* seed_out);
 /* raw cudaStream_t of the context (as void*), so a host can bracket calls with its own events */

@@ -197,3 +197,69 @@ def test_sharded_describe_equals_single_gpu():
     # ... and the ranks agree with each other to the last bit
     assert all(np.array_equal(np.asarray(a, dtype=float), np.asarray(b, dtype=float))
                for f in ("mean", "median", "std", "min", "max") for a, b in zip(out[0][1][f], out[1][1][f]))
+
+
+def _skew_run(ws, st, n, lo, hi, lam):
+    """p ~ N(0,1); g = global index / n (uploaded); logw = -lam g; Resample; q .= p + g (reads through the ancestors)."""
+    ws.Sample("p", "Normal", (0.0, 1.0)).apply(st)
+    st.store.setcol("g", np.arange(lo, hi, dtype=np.float64) / n)
+    ws.Weight(None, (ws.col("g") * (-lam),)).apply(st)
+    r = ws.Resample()
+    r.apply(st)
+    ws.Assign("q", ws.col("p") + ws.col("g")).apply(st)
+    return r.last.ess_perc
+
+
+def _worker_skew(rank, world, port, n, lam, push_min, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WSB200_PUSH_MIN=str(push_min))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import wsb200 as ws
+    st = ws.sharded_state(n, device=rank, seed=77, ess_perc_min=float("inf"))
+    lo, hi = ws.shard_bounds(n, rank, world)
+    ess = _skew_run(ws, st, n, lo, hi, lam)
+    pushed, mig = ctypes.c_int64(), ctypes.c_int64()
+    st.store._call("ws_get_pushed", ctypes.byref(pushed))
+    st.store._call("ws_get_migrated", ctypes.byref(mig))
+    q.put((rank, st["p"], st["g"], st["q"], ess, pushed.value, mig.value))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("lam,push_min,mode", [(10.0, 1000, "eager"), (0.1, 1000, "lazy"), (10.0, 1 << 40, "nccl")])
+def test_sharded_direct_exchange_equals_single_gpu(lam, push_min, mode):
+    """Migration under load: log-weights fall with the global index, so rank 0 produces offspring for rank 1.  The direct
+    exchange (gather kernels writing into the peer's planes over NVLink, cudaIpc mappings) must give the single-GPU
+    result particle for particle — with heavy migration (eager: final slots of the peer's back planes), with light
+    migration (lazy: the peer's spare rows, read through the ancestors by the next pass) — and so must the
+    stage + ncclSend/ncclRecv path it replaces."""
+    world = 2
+    if _ngpu() < world:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import wsb200 as ws
+    n = 400_001
+    single = ws.SMCState(n, device=0, seed=77, ess_perc_min=float("inf"))
+    ess1 = _skew_run(ws, single, n, 0, n, lam)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_skew, args=(r, world, 29781, n, lam, push_min, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for k, name in ((1, "p"), (2, "g"), (3, "q")):
+        got = np.concatenate([o[k] for o in out])
+        assert np.array_equal(got, single[name]), (mode, name, int((got != single[name]).sum()))
+    assert all(abs(o[4] - ess1) < 1e-12 for o in out)
+    migrated = sum(o[6] for o in out)
+    pushed = sum(o[5] for o in out)
+    print(f"{mode}: {migrated} of {n} particles migrated, {pushed} written directly into the peer")
+    if mode == "nccl":
+        assert pushed == 0 and migrated > 100_000
+    else:
+        assert pushed == migrated > 1000
+        assert (migrated > n // 64) == (mode == "eager")

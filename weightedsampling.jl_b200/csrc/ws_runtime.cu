@@ -20,6 +20,7 @@
 #include <vector>
 
 #include <dlfcn.h>
+#include <unistd.h>
 #include <chrono>
 
 #include "../../include/wsb200.h"
@@ -240,6 +241,14 @@ struct ws_ctx {
     double* d_send = nullptr;                // staging of outgoing offspring, one plane batch at a time
     int64_t send_cap = 0;
     int64_t migrated_total = 0;              // particles received from other ranks so far
+    // direct exchange: migrating offspring are gathered STRAIGHT into the destination rank's planes over NVLink
+    // (peer mappings of the other ranks' slabs, cudaIpc), one kernel per destination instead of stage + ncclSend/Recv
+    bool push_exchange = true;               // env WSB200_EXCHANGE=nccl: always stage + ncclSend / ncclRecv
+    int64_t push_min = 1 << 16;              // migrants over all ranks from which the direct path is used (env WSB200_PUSH_MIN)
+    size_t slabs_published = 0;              // how many of my slabs the other ranks have mapped
+    std::vector<std::vector<char*>> peer_slabs;  // [rank][slab index]: that rank's slabs in this process's address space
+    unsigned long long* d_barrier = nullptr; // 8 bytes all-reduced after the pushes: a stream-ordered barrier over the ranks
+    int64_t pushed_total = 0;                // particles written directly into peers so far
     double phase_ms[8] = {0};                // WSB200_TRACE=1: host wall time per phase of resample_sharded
     int64_t phase_n = 0;
 
@@ -530,6 +539,14 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
             ws_destroy(c);
             return rc;
         }
+        c->peer_slabs.resize((size_t)nranks);
+        if (const char* e = getenv("WSB200_EXCHANGE")) c->push_exchange = strcmp(e, "nccl") != 0;
+        if (const char* e = getenv("WSB200_PUSH_MIN")) c->push_min = strtoll(e, nullptr, 10);
+        if (cudaMalloc(&c->d_barrier, 64) != cudaSuccess || cudaMemset(c->d_barrier, 0, 64) != cudaSuccess) {
+            int rc = fail(nullptr, WS_ECUDA, "cudaMalloc failed (barrier word)");
+            ws_destroy(c);
+            return rc;
+        }
         // NCCL sets up its peer-to-peer channels on first use (hundreds of ms); do that here, not in
         // the first resampling steps: one 3-double message to and from every peer + the collectives used
         {
@@ -597,6 +614,10 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_all_bounds);
     cudaFree(c->d_anc_src);
     cudaFree(c->d_send);
+    for (auto& ps : c->peer_slabs)
+        for (char* b : ps)
+            if (b) cudaIpcCloseMemHandle(b);
+    if (c->d_barrier) cudaFree(c->d_barrier);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_score_ops);
     cudaFree(c->d_seg_ops);
@@ -1529,6 +1550,106 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
 //      [d N/R, (d+1) N/R) is sent to d (NCCL send/recv = all-to-all-v over NVLink); the part that stays
 //      is gathered straight into the back buffer.  Slot order makes every (source, destination) piece
 //      contiguous on both sides.
+// ---- direct (peer-memory) exchange ---------------------------------------------------------------------------
+// host bytes of every rank, in rank order (bytes % 8 == 0)
+static int allgather_host_bytes(ws_ctx* c, const void* mine, size_t bytes, std::vector<char>& all) {
+    const size_t R = (size_t)c->nranks, words = bytes / 8;
+    TRY(ensure_scratch2(c, bytes * (R + 1)));
+    char* d = (char*)c->d_scratch2;
+    CK(c, cudaMemcpyAsync(d + bytes * R, mine, bytes, cudaMemcpyHostToDevice, c->stream));
+    NCK(c, g_nccl.AllGather(d + bytes * R, d, words, WS_NCCL_UINT64, c->comm, c->stream));
+    all.resize(bytes * R);
+    CK(c, cudaMemcpyAsync(all.data(), d, bytes * R, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return WS_OK;
+}
+
+struct PeerPlane {
+    int64_t slab;  // index into the owner's slab list
+    int64_t off;   // byte offset inside the slab
+};
+
+// Every rank announces where (slab, offset) each of `mine` — the buffers its incoming offspring go to, one per plane —
+// lives; slabs the others have not mapped yet are exported (cudaIpcGetMemHandle) and mapped (cudaIpcOpenMemHandle)
+// first.  peer[q][p] = rank q's buffer for plane p as a pointer valid in THIS process.  *usable = false (on every
+// rank alike) when two ranks share a process: IPC mappings need separate processes, the caller then stages + sends.
+static int map_peer_planes(ws_ctx* c, const std::vector<double*>& mine, std::vector<std::vector<double*>>& peer, bool* usable) {
+    const int R = c->nranks, r = c->rank;
+    const size_t P = mine.size();
+    std::vector<int64_t> msg(2 + 2 * P);
+    msg[0] = (int64_t)c->slabs.size();
+    msg[1] = (int64_t)getpid();
+    for (size_t p = 0; p < P; ++p) {
+        int64_t slab = -1, off = 0;
+        for (size_t k = 0; k < c->slabs.size(); ++k) {
+            const char* b = c->slabs[k].base;
+            if ((const char*)mine[p] >= b && (const char*)mine[p] < b + c->slabs[k].size) {
+                slab = (int64_t)k;
+                off = (int64_t)((const char*)mine[p] - b);
+                break;
+            }
+        }
+        if (slab < 0) return fail(c, WS_ECUDA, "direct exchange: a plane buffer is not inside a slab");
+        msg[2 + 2 * p] = slab;
+        msg[3 + 2 * p] = off;
+    }
+    std::vector<char> all;
+    TRY(allgather_host_bytes(c, msg.data(), sizeof(int64_t) * msg.size(), all));
+    auto row = [&](int q) { return reinterpret_cast<const int64_t*>(all.data() + sizeof(int64_t) * msg.size() * (size_t)q); };
+    *usable = true;
+    for (int q = 0; q < R; ++q)
+        for (int q2 = q + 1; q2 < R; ++q2)
+            if (row(q)[1] == row(q2)[1]) *usable = false;
+    if (!*usable) return WS_OK;
+    // map the slabs that are new since the last exchange: rounds of up to H handles per rank (same rounds on every rank)
+    const int H = 32;
+    struct Block {
+        int64_t count;
+        cudaIpcMemHandle_t h[H];
+    };
+    static_assert(sizeof(Block) % 8 == 0, "Block travels as 64-bit words");
+    for (;;) {
+        bool need = false;
+        for (int q = 0; q < R; ++q) {
+            const size_t known = (q == r) ? c->slabs_published : c->peer_slabs[q].size();
+            if ((size_t)row(q)[0] > known) need = true;
+        }
+        if (!need) break;
+        Block b;
+        memset(&b, 0, sizeof(b));
+        const size_t target = (size_t)msg[0];  // the slab count announced above (nothing is allocated in between)
+        while (c->slabs_published + (size_t)b.count < target && b.count < H) {
+            CK(c, cudaIpcGetMemHandle(&b.h[b.count], c->slabs[c->slabs_published + (size_t)b.count].base));
+            b.count++;
+        }
+        c->slabs_published += (size_t)b.count;
+        std::vector<char> hall;
+        TRY(allgather_host_bytes(c, &b, sizeof(b), hall));
+        for (int q = 0; q < R; ++q) {
+            if (q == r) continue;
+            const Block* pb = reinterpret_cast<const Block*>(hall.data() + sizeof(Block) * (size_t)q);
+            for (int64_t k = 0; k < pb->count; ++k) {
+                void* base = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&base, pb->h[k], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess)
+                    return fail(c, WS_ECUDA, "direct exchange: cudaIpcOpenMemHandle failed (%s); set WSB200_EXCHANGE=nccl",
+                                cudaGetErrorString(e));
+                c->peer_slabs[q].push_back((char*)base);
+            }
+        }
+    }
+    peer.assign((size_t)R, std::vector<double*>(P, nullptr));
+    for (int q = 0; q < R; ++q) {
+        if (q == r) continue;
+        for (size_t p = 0; p < P; ++p) {
+            const int64_t slab = row(q)[2 + 2 * p], off = row(q)[3 + 2 * p];
+            if (slab < 0 || (size_t)slab >= c->peer_slabs[q].size()) return fail(c, WS_ECUDA, "direct exchange: unknown peer slab");
+            peer[q][p] = reinterpret_cast<double*>(c->peer_slabs[q][(size_t)slab] + off);
+        }
+    }
+    return WS_OK;
+}
+
 static int resample_sharded(ws_ctx* c, const double* d_ru) {
     const int R = c->nranks, r = c->rank;
     const uint64_t stream_id = c->next_stream++;
@@ -1646,12 +1767,50 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
         for (int32_t k = 0; k < c->cols[ci].width; ++k) planes.push_back(Plane{ci, k});
     const int BATCH = 8;
+    // Direct exchange (enough migrants to pay for the address exchange): the gather kernel that would stage a
+    // destination's offspring writes them straight into that rank's planes over NVLink — into the spare rows behind
+    // its front planes (lazy) or at their final slots of its back planes (eager) — so gather and transfer are ONE
+    // kernel per destination and nothing is staged or received.  Safe without a barrier in front: every rank has
+    // passed the allgather of the bounds, i.e. finished all earlier kernels that touch its planes, and what it
+    // runs meanwhile (search, its own gathers) reads front rows [0, n) and writes its OWN slots only.  A
+    // stream-ordered all-reduce of one word afterwards is the barrier that tells a rank its incoming rows are complete.
+    int64_t total_remote = 0;
+    for (int d = 0; d < R; ++d) {
+        const int64_t dlo = rank_lo(d), dhi = rank_lo(d + 1);
+        total_remote += (dhi - dlo) - std::max<int64_t>(0, std::min<int64_t>(bnd[2 * d + 1], dhi) - std::max<int64_t>(bnd[2 * d], dlo));
+    }
+    bool push = c->push_exchange && total_remote >= c->push_min && !planes.empty();
+    std::vector<std::vector<double*>> peer;
+    if (push) {
+        std::vector<double*> mine(planes.size());
+        for (size_t p = 0; p < planes.size(); ++p) {
+            Column& col = c->cols[planes[p].col];
+            mine[p] = lazy ? col.front[planes[p].comp] : col.back[planes[p].comp];
+            if (mine[p] == nullptr) return fail(c, WS_ECUDA, "direct exchange: plane without a destination buffer");
+        }
+        bool usable = false;
+        TRY(map_peer_planes(c, mine, peer, &usable));
+        if (!usable) {
+            push = false;
+            c->push_exchange = false;  // ranks share a process: stay on ncclSend / ncclRecv (every rank decides alike)
+        }
+    }
+    // first of my offspring's rows among rank d's spare rows (the receiver's spare_pos[r] below)
+    auto spare_pos_on = [&](int d) {
+        int64_t acc = 0;
+        const int64_t lo_d = rank_lo(d), hi_d = rank_lo(d + 1);
+        for (int q = 0; q < r; ++q) {
+            if (q == d) continue;
+            acc += std::max<int64_t>(0, std::min<int64_t>(bnd[2 * q + 1], hi_d) - std::max<int64_t>(bnd[2 * q], lo_d));
+        }
+        return acc;
+    };
     // the migrating offspring are the produced slots outside my own range: a prefix [0, pre) (to lower
     // ranks) and a suffix [suf0, produced) (to higher ranks) of the produced range
     const int64_t pre = send_off[r] > 0 || send_cnt[r] > 0 ? send_off[r] : produced;
     const int64_t suf0 = send_cnt[r] > 0 ? send_off[r] + send_cnt[r] : produced;
     const int64_t n_pre = std::min(pre, produced), n_suf = produced - suf0;
-    if (remote_send * BATCH > c->send_cap) {
+    if (!push && remote_send * BATCH > c->send_cap) {
         // grow geometrically (a cudaFree / cudaMalloc pair synchronises the device and costs milliseconds)
         if (c->d_send) CK(c, cudaFree(c->d_send));
         c->d_send = nullptr;
@@ -1689,6 +1848,27 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
             CK(c, ws_launch_gather(G, grid_for(c, G.n, 256, 8), c->stream));
             timed_end(c, te);
         }
+        if (push) {
+            for (int d = 0; d < R; ++d) {
+                if (d == r || send_cnt[d] <= 0) continue;
+                WsGatherParams G;
+                memset(&G, 0, sizeof(G));
+                G.n = send_cnt[d];
+                G.ancestors = anc_src + send_off[d];
+                G.n_planes = nb;
+                const int64_t n_d = rank_lo(d + 1) - rank_lo(d);
+                const int64_t at = lazy ? n_d + spare_pos_on(d) : std::max<int64_t>(fs, rank_lo(d)) - rank_lo(d);
+                for (int k = 0; k < nb; ++k) {
+                    const Plane pl = planes[p0 + k];
+                    G.src[k] = c->cols[pl.col].front[pl.comp];
+                    G.dst[k] = peer[d][p0 + k] + at;
+                }
+                timed_begin(c, KC_GATHER, te);
+                CK(c, ws_launch_gather(G, grid_for(c, G.n, 256, 8), c->stream));
+                timed_end(c, te);
+            }
+            continue;
+        }
         // stage the migrating offspring of this batch (slot order)
         const int64_t seg_start[2] = {0, suf0}, seg_len[2] = {n_pre, n_suf}, seg_dst[2] = {0, n_pre};
         for (int sgi = 0; sgi < 2; ++sgi) {
@@ -1722,6 +1902,10 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
             }
         }
         NCK(c, g_nccl.GroupEnd());
+    }
+    if (push) {
+        NCK(c, g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, WS_NCCL_UINT64, WS_NCCL_SUM, c->comm, c->stream));
+        c->pushed_total += remote_send;
     }
     if (c->phase_n > 6) c->phase_ms[5] += t_now() - t0;  // exchange without the communicator's first-use set-up
     c->phase_ms[3] += t_now() - t0;
@@ -2892,6 +3076,11 @@ extern "C" int ws_next_philox_stream(ws_ctx* c, uint64_t* stream_out, uint64_t* 
     if (!c) return WS_EINVAL;
     if (stream_out) *stream_out = c->next_stream;
     if (seed_out) *seed_out = c->seed;
+    return WS_OK;
+}
+extern "C" int ws_get_pushed(ws_ctx* c, int64_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    *out = c->pushed_total;
     return WS_OK;
 }
 extern "C" int ws_get_migrated(ws_ctx* c, int64_t* out) {
