@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
     const double rS = 1.0 / Sden;
     const double uniform_w = 1.0 / (double)P.n_slots;
     // the log-weights of the NEXT tile are requested before the current tile is processed: the kernel was waiting on
-    // its loads (long-scoreboard stalls, profiles/r1t_ncu_ws_cdf_tiles_kernel_20M.txt), not on the arithmetic
+    // its loads (long-scoreboard stalls, profiles/r1i_ncu_ws_cdf_tiles_kernel_20M.txt), not on the arithmetic
     auto load_tile = [&](int tile, double (&l)[WS_SCAN_ITEMS]) {
         const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
         if (item0 + WS_SCAN_ITEMS <= n) {
