@@ -164,36 +164,41 @@ def c5skew(rank, world, local):
         lo, hi = ws.shard_bounds(n, rank, world)
         g = (np.arange(lo, hi, dtype=np.float64)) / float(n)
         store._call("ws_set_timing", 1)
-        times, mig = [], []
+        times, mig, sent_direct = [], [], []
         for rep in range(3):
             store.setcol("g", g)
             ws.Weight(None, (ws.col("g") * (-lam),)).apply(st)
             st.sync()
-            m0 = C.c_int64()
+            m0, s0 = C.c_int64(), C.c_int64()
             store._call("ws_get_migrated", C.byref(m0))
+            store._call("ws_get_pushed", C.byref(s0))
             dist.barrier()
             t0 = time.perf_counter()
             r = ws.Resample()
             r.apply(st)
             st.sync()
             dt = max_over_ranks(time.perf_counter() - t0, world, local)
-            m1 = C.c_int64()
+            m1, s1 = C.c_int64(), C.c_int64()
             store._call("ws_get_migrated", C.byref(m1))
+            store._call("ws_get_pushed", C.byref(s1))
             if rep > 0:
                 times.append(dt * 1e3)
                 mig.append(m1.value - m0.value)
+                sent_direct.append(s1.value - s0.value)
         ms = float(np.median(times))
         planes = P + 1
         sent = float(np.mean(mig))
         sent_max = max_over_ranks(sent, world, local)     # busiest receiver (ingress)
-        sent_sum = sum_over_ranks(sent, world, local)     # all migrants: with the mass on rank 0 ~ that rank's egress
+        sent_sum = sum_over_ranks(sent, world, local)     # all migrants
+        egress_max = max_over_ranks(float(np.mean(sent_direct)), world, local)  # busiest sender (direct exchange only; 0 on the NCCL path)
         emit(rank, config=f"C5 rank-skewed resample (logw = -{lam} i/N), N={per_gpu} per GPU x {world}, payload={P}+1 planes",
              ms=ms, ess_perc=r.last.ess_perc, particles_per_sec=n / (ms * 1e-3),
              received_particles_max_rank=sent_max, received_bytes_max_rank=sent_max * 8 * planes,
              migrated_particles_total=sent_sum, migrated_bytes_total=sent_sum * 8 * planes,
              nvlink_ingress_gbs_max_rank=sent_max * 8 * planes / (ms * 1e-3) / 1e9,
-             nvlink_egress_gbs_if_one_source=sent_sum * 8 * planes / (ms * 1e-3) / 1e9,
-             nvlink_frac_of_770=max(sent_max, sent_sum if lam >= 10 else sent_max) * 8 * planes / (ms * 1e-3) / 1e9 / NVLINK, n_gpus=world,
+             sent_particles_max_rank=egress_max, nvlink_egress_gbs_max_rank=egress_max * 8 * planes / (ms * 1e-3) / 1e9,
+             nvlink_total_gbs=sent_sum * 8 * planes / (ms * 1e-3) / 1e9,
+             nvlink_frac_of_770=max(sent_max, egress_max) * 8 * planes / (ms * 1e-3) / 1e9 / NVLINK, n_gpus=world,
              timing="host wall clock around Resample incl. migration and gather (sync on both sides), max over ranks; "
                     "the NVLink figure divides the busiest rank's migrated bytes by the WHOLE step time")
         del st
