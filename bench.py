@@ -297,7 +297,7 @@ def main():
     roofline = None
     if dom:
         roofline = {"bound": "hbm", "kernel": {"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",
-                                                "scan_search": "ws_scan_search_kernel"}[dom],
+                                                "scan_search": "ws_cdf_tiles_kernel + ws_cdf_offsets_kernel + ws_search_kernel"}[dom],
                     "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": per_kernel[dom]["frac"],
                     "traffic": measured_traffic({"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",

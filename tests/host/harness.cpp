@@ -236,6 +236,58 @@ int hh_score(HH* h, int n_entries, double* out) {
     memcpy(out, acc.data(), sizeof(double) * h->n);
     return 0;
 }
+// The same fold the way the move / score kernels run it (ws_kernels_move.cu: ws_score_fold): registers renumbered to
+// the rows the prefix touches, entries unpacked to WsDop, chunks of 128 entries, runs of squared-residual entries over the
+// same registers executed by ws_vm_exec_sqlin2_run.  Must equal hh_score bit for bit.  *n_runs / *n_rows report what
+// the compaction and the run detection found.
+int hh_score_device_order(HH* h, int n_entries, double* out, int* n_runs, int* n_rows) {
+    hh_flush(h);
+    if (h->score.overflow) return -5;
+    if (n_entries > (int)h->tape_end.size()) return -1;
+    const int n_ops = n_entries <= 0 ? 0 : h->tape_end[(size_t)n_entries - 1];
+    Program& p = h->score;
+    std::vector<uint8_t> keep;
+    for (auto& ld : p.loads) keep.push_back((uint8_t)ld.second);
+    uint8_t map[256];
+    const int rows = std::max(1, ws_compact_regs(p.ops.data(), (size_t)n_ops, keep.data(), (int)keep.size(), map));
+    const int CHUNK = 128;
+    std::vector<WsDop> dops((size_t)n_ops);
+    int runs = 0;
+    for (int i = 0; i < n_ops; ++i) {
+        dops[(size_t)i] = ws_decode_op<1, 1>(p.ops[(size_t)i], map);
+        dops[(size_t)i].op |= 1u << 8;
+    }
+    for (int i = 0; i < n_ops; ++i) {
+        const bool cont = (i % CHUNK) != 0 && ws_run_continues(p.ops[(size_t)i - 1], p.ops[(size_t)i]);
+        if (cont) continue;
+        int len = 1;
+        while (i + len < n_ops && ((i + len) % CHUNK) != 0 && ws_run_continues(p.ops[(size_t)(i + len) - 1], p.ops[(size_t)(i + len)])) ++len;
+        if (len > 1) {
+            dops[(size_t)i].op = (dops[(size_t)i].op & 0xFFu) | ((uint32_t)len << 8);
+            ++runs;
+        }
+    }
+    WsRng none;
+    none.seed = 0;
+    none.replay_n = none.replay_u = none.replay_e = nullptr;
+    std::vector<double> R((size_t)rows);
+    const double konst = n_entries <= 0 ? 0.0 : h->tape_const[(size_t)n_entries - 1];
+    for (int64_t i = 0; i < h->n; ++i) {
+        for (auto& ld : p.loads) R[map[ld.second]] = h->cols[ld.first.col][ld.first.comp][(size_t)i];
+        double acc[1] = {0.0};
+        const uint64_t pid[1] = {(uint64_t)i};
+        for (int k = 0; k < n_ops;) {
+            const int len = (int)(dops[(size_t)k].op >> 8);
+            if (len > 1) ws_vm_exec_sqlin2_run<1, 1>(dops.data() + k, len, R.data(), acc);
+            else ws_vm_exec_d<1, 1>(dops[(size_t)k], R.data(), acc, none, pid);
+            k += len;
+        }
+        out[(size_t)i] = acc[0] + konst;
+    }
+    if (n_runs) *n_runs = runs;
+    if (n_rows) *n_rows = rows;
+    return 0;
+}
 // Philox / Box-Muller / slot-count building blocks of ws_math.cuh
 void hh_randn2(uint64_t particle, uint64_t stream, uint64_t seed, double* out2) { ws_randn2(particle, stream, seed, out2[0], out2[1]); }
 void hh_philox(uint64_t particle, uint64_t stream, uint64_t seed, uint32_t* out4) {

@@ -80,6 +80,8 @@ class HostStore:
         rc = getattr(self.L, name)(self.h, *args)
         if rc != 0:
             raise RuntimeError(f"{name} failed ({rc}): {self.L.hh_error(self.h).decode()}")
+        if getattr(self, "autoflush", False):   # long programs: the harness has no overflow-driven flush (the runtime does)
+            self.flush()
 
     def setcol(self, name, v):
         v = np.asarray(v, dtype=np.float64)
@@ -115,6 +117,16 @@ class HostStore:
         rc = self.L.hh_score(self.h, n_entries, out.ctypes.data_as(C.c_void_p))
         assert rc == 0
         return out
+
+    def score_device_order(self, n_entries):
+        """the fold as the move / score kernels run it: renumbered registers, decoded ops, 128-entry chunks, run
+        super-ops.  Returns (scores, number of runs, register-file rows)."""
+        out = np.empty(self.n)
+        runs, rows = C.c_int(), C.c_int()
+        self.L.hh_score_device_order.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        rc = self.L.hh_score_device_order(self.h, n_entries, out.ctypes.data_as(C.c_void_p), C.byref(runs), C.byref(rows))
+        assert rc == 0
+        return out, runs.value, rows.value
 
     def tape_len(self):
         return self.L.hh_tape_len(self.h)

@@ -157,3 +157,52 @@ def test_score_tape_fuses_normal_terms_into_one_op():
     np.testing.assert_allclose(hs.store.score(hs.store.tape_len()), want, rtol=1e-12, atol=1e-12)
     np.testing.assert_allclose(hs.store.score(3), ref.normal_logpdf(a, 0.0, 10.0) + ref.normal_logpdf(b, 0.0, 10.0)
                                + ref.normal_logpdf(ys[0], a + b * xs[0], 1.0), rtol=1e-12, atol=1e-12)
+
+
+HIER_SMALL = '''
+@model function hier(J, groups)
+    mu ~ Normal(0.0, 5.0)
+    sigma ~ Exponential(1.0)
+    beta ~ Normal(0.0, 2.0)
+    for j in 1:J
+        alpha{j} ~ Normal(mu, 1.5)
+        for (x, y) in groups[j]
+            y => Normal(alpha{j} + beta * x, sigma)
+        end
+    end
+end
+'''
+
+
+@pytest.mark.parametrize("which", ["linreg", "hier"])
+def test_device_order_fold_is_bit_identical(which):
+    """The score fold as the kernels execute it (registers renumbered per launch, ops decoded to WsDop, runs of
+    squared-residual entries over the same registers as one super-op, 128-entry chunks) must give the plain
+    entry-by-entry fold bit for bit, at every tape prefix: a move's accept decision depends on it."""
+    n = 64
+    rng = np.random.default_rng(9)
+    if which == "linreg":
+        npts = 300                                             # > 2 chunks of 128 entries: runs are cut at chunk borders
+        xs, ys = rng.uniform(0, 10, npts), rng.normal(size=npts)
+        root = strip_resample(ws.model(models.LINREG)(xs, ys))
+        normals, expo = rng.standard_normal(2 * n), None
+    else:
+        J, n_obs = 5, 40
+        groups = [[(float(rng.uniform(0, 5)), float(rng.normal())) for _ in range(n_obs)] for _ in range(J)]
+        root = strip_resample(ws.model(HIER_SMALL)(J, groups))
+        normals, expo = rng.standard_normal((2 + J) * n), rng.exponential(size=n)
+    hs = HostState(n)
+    hs.store.autoflush = True
+    hs.store.set_replay(normals=normals, exponentials=expo if expo is not None else ())
+    root.apply(hs)
+    T = hs.store.tape_len()
+    assert not np.isnan(hs.store.score(T)).any()
+    for k in sorted({0, 1, 2, 3, T // 3, T // 2, T - 1, T}):
+        plain = hs.store.score(k)
+        dev, runs, rows = hs.store.score_device_order(k)
+        assert np.array_equal(plain, dev), (which, k, float(np.max(np.abs(plain - dev))))
+    dev, runs, rows = hs.store.score_device_order(T)
+    if which == "linreg":
+        assert runs == 3 and rows <= 3          # 300 terms = 126 + 128 + 46 after the two priors; registers: alpha, beta (+0 temporaries)
+    else:
+        assert runs == 5 and rows <= 4 + 5 + 2  # one run per group; mu, sigma, beta, alpha_j and the 1/sigma, log sigma cache

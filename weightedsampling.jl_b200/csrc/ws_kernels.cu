@@ -4,8 +4,10 @@
 //                         (m, S, Q) log-weight reduction folded into its epilogue
 //   ws_reduce_logw_kernel stand-alone (m, S, Q) partials (after an upload)
 //   ws_finalize_kernel    combines partials -> logsumexp, ESS%, resample decision
-//   ws_scan_search_kernel single-pass fixed-point CDF scan (decoupled look-back) fused with the
-//                         stratified / systematic ancestor search
+//   ws_cdf_tiles_kernel   w = exp_norm(logw) in 2^61 fixed point, tile-local inclusive prefix sums
+//   ws_cdf_offsets_kernel exclusive scan of the tile aggregates (one CTA)
+//   ws_search_kernel      per-particle slot counts F(C) on the stratified / systematic grid, offspring
+//                         expansion (ws_expand_heavy_kernel for one-hot weights), ancestors out
 //   ws_gather_kernel      ancestor gather of all planes (resample!)
 //   small helpers         fill, exp_norm write, row gather
 //

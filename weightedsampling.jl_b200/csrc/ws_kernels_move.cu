@@ -70,7 +70,10 @@ __device__ __forceinline__ void ws_score_fold(const WsScoreParams& S, double* R,
             runnable = dd.op == WS_OP_ACC_SQLIN2 || dd.op == WS_OP_ACC_SQLIN2_S;
             if (runnable && threadIdx.x > 0) {
                 const uint2 pw = __ldg(reinterpret_cast<const uint2*>(S.ops + base + (int)threadIdx.x - 1));
-                cont = pw.x == o.w0 && (pw.y & 0xFFu) == (o.w1 & 0xFFu);
+                WsOp prev;
+                prev.w0 = pw.x;
+                prev.w1 = pw.y;
+                cont = ws_run_continues(prev, o);
             }
             dd.op |= 1u << 8;
             dops[threadIdx.x] = dd;

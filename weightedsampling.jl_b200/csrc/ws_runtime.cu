@@ -2522,21 +2522,10 @@ static int for_each_tape_segment(ws_ctx* c, int64_t target_depth, const std::vec
 // particles per thread and more CTAs per SM in the fold kernels).  The ops stay as they are on the device;
 // the kernels renumber while unpacking them (ws_decode_op).
 static void compact_score_regs(WsScoreParams& S, const WsOp* ops, size_t n_ops, uint8_t* target_reg, int d) {
-    bool used[256] = {false};
-    for (size_t i = 0; i < n_ops; ++i) {
-        const WsOp& o = ops[i];
-        const uint32_t op = o.w0 & 0xFFu;
-        const uint32_t r[4] = {(o.w0 >> 8) & 0xFFu, (o.w0 >> 16) & 0xFFu, (o.w0 >> 24) & 0xFFu, o.w1 & 0xFFu};
-        if (ws_op_dst_is_reg(op)) used[r[0]] = true;
-        used[r[1]] = used[r[2]] = used[r[3]] = true;
-    }
-    for (int k = 0; k < S.n_loads; ++k) used[S.load_reg[k]] = true;
-    for (int t = 0; t < d; ++t) used[target_reg[t]] = true;
-    used[WS_REG_NONE] = false;
-    int next = 0;
-    for (int r = 0; r < 256; ++r) S.reg_map[r] = used[r] ? (uint8_t)next++ : (uint8_t)0;
-    S.reg_map[WS_REG_NONE] = WS_REG_NONE;
-    S.n_regs = std::max(1, next);
+    std::vector<uint8_t> keep;
+    for (int k = 0; k < S.n_loads; ++k) keep.push_back(S.load_reg[k]);
+    for (int t = 0; t < d; ++t) keep.push_back(target_reg[t]);
+    S.n_regs = std::max(1, ws_compact_regs(ops, n_ops, keep.data(), (int)keep.size(), S.reg_map));
     for (int k = 0; k < S.n_loads; ++k) S.load_reg[k] = S.reg_map[S.load_reg[k]];
     for (int t = 0; t < d; ++t) target_reg[t] = S.reg_map[target_reg[t]];
 }

@@ -394,6 +394,32 @@ WS_HD void ws_vm_exec_d(const WsDop& o, double* __restrict__ R, double (&acc)[P]
     }
 }
 
+// Renumber the registers that `ops` (and `keep`: load / target registers) touch into 0 .. n-1, ascending; map[r] is the
+// new number of register r (WS_REG_NONE stays).  Returns n.  A score tape reserves temporaries and one register per
+// plane it ever read; a launch that folds part of it keeps only these rows of the register file.
+inline int ws_compact_regs(const WsOp* ops, size_t n_ops, const uint8_t* keep, int n_keep, uint8_t* map /* [256] */) {
+    bool used[256] = {false};
+    for (size_t i = 0; i < n_ops; ++i) {
+        const WsOp& o = ops[i];
+        const uint32_t op = o.w0 & 0xFFu;
+        const uint32_t r[4] = {(o.w0 >> 8) & 0xFFu, (o.w0 >> 16) & 0xFFu, (o.w0 >> 24) & 0xFFu, o.w1 & 0xFFu};
+        if (ws_op_dst_is_reg(op)) used[r[0]] = true;
+        used[r[1]] = used[r[2]] = used[r[3]] = true;
+    }
+    for (int k = 0; k < n_keep; ++k) used[keep[k]] = true;
+    used[WS_REG_NONE] = false;
+    int next = 0;
+    for (int r = 0; r < 256; ++r) map[r] = used[r] ? (uint8_t)next++ : (uint8_t)0;
+    map[WS_REG_NONE] = WS_REG_NONE;
+    return next;
+}
+
+// Is entry i of a tape the continuation of a run (a squared-residual entry over the same registers as entry i-1)?
+WS_HD bool ws_run_continues(const WsOp& prev, const WsOp& cur) {
+    const uint32_t op = cur.w0 & 0xFFu;
+    return (op == WS_OP_ACC_SQLIN2 || op == WS_OP_ACC_SQLIN2_S) && prev.w0 == cur.w0 && (prev.w1 & 0xFFu) == (cur.w1 & 0xFFu);
+}
+
 // A run of `len` consecutive ACC_SQLIN2 (or ACC_SQLIN2_S) entries over the SAME registers, e.g. the likelihood
 // of a regression, sum_i logN(y_i; alpha + beta x_i, sigma): the operands are read from the register file once
 // and each entry costs its three coefficients and four FP64 operations per particle, in the same order and
