@@ -202,4 +202,118 @@ end
 set_genealogy!(state::SMCState{DeviceColumnStore}, on::Bool; budget_bytes::Integer=0) =
     check(ctx(state), ccall((:ws_set_genealogy, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), ctx(state), on, budget_bytes))
 
+# ---- the other default kernels of the configs: MvNormal, Exponential, Weight --------------------------------
+struct DeviceSampleMvNormal <: ParticleTransformer; col::Int32; mu::Vector{DeviceExpr}; cov::Matrix{Float64}; end
+struct DeviceObserveMvNormal <: ParticleTransformer; obs::Vector{DeviceExpr}; mu::Vector{DeviceExpr}; cov::Matrix{Float64}; end
+struct DeviceSampleExponential <: ParticleTransformer; col::Int32; comp::Int32; theta::DeviceExpr; end
+struct DeviceWeight <: ParticleTransformer; term::DeviceExpr; end
+rowmajor(m::Matrix{Float64}) = collect(vec(permutedims(m)))          # the ABI takes the covariance row-major
+
+function apply!(t::DeviceSampleMvNormal, state::SMCState{DeviceColumnStore})   # src/transformers.jl:172-182, default_kernels.jl:93
+    GC.@preserve t begin
+        mus = [cexpr(e) for e in t.mu]
+        check(ctx(state), ccall((:ws_sample_mvnormal, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{WsExpr}, Ptr{Float64}),
+                                ctx(state), t.col, length(t.mu), mus, rowmajor(t.cov)))
+    end
+    state.depth += 1
+end
+function apply!(t::DeviceObserveMvNormal, state::SMCState{DeviceColumnStore})  # src/transformers.jl:228-235
+    GC.@preserve t begin
+        obs = [cexpr(e) for e in t.obs]; mus = [cexpr(e) for e in t.mu]
+        check(ctx(state), ccall((:ws_observe_mvnormal, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{WsExpr}, Ptr{WsExpr}, Ptr{Float64}),
+                                ctx(state), length(t.mu), obs, mus, rowmajor(t.cov)))
+    end
+    state.weights_changed = true
+    state.depth += 1
+end
+function apply!(t::DeviceSampleExponential, state::SMCState{DeviceColumnStore}) # default_kernels.jl:87
+    GC.@preserve t check(ctx(state), ccall((:ws_sample_exponential, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ref{WsExpr}),
+                                           ctx(state), t.col, t.comp, cexpr(t.theta)))
+    state.depth += 1
+end
+function apply!(t::DeviceWeight, state::SMCState{DeviceColumnStore})           # src/transformers.jl:283-289
+    GC.@preserve t check(ctx(state), ccall((:ws_weight_expr, LIB), Cint, (Ptr{Cvoid}, Ref{WsExpr}), ctx(state), cexpr(t.term)))
+    state.weights_changed = true
+    state.depth += 1
+end
+score!(::Union{DeviceSampleMvNormal,DeviceObserveMvNormal,DeviceSampleExponential,DeviceWeight,DeviceSampleExpr}, state, c) =
+    (c.depth += 1; nothing)
+
+# ---- Move (src/transformers.jl:588-623) with the RW / autoRW proposals (src/move_kernels.jl:189-253) -----------
+struct WsMoveSpec
+    n_targets::Int32; col::Ptr{Int32}; comp::Ptr{Int32}; proposal::Int32; has_bounds::Int32
+    lo::Ptr{Float64}; hi::Ptr{Float64}; step::Float64; diversity::Float64; target_depth::Int64
+end
+struct WsMoveInfo
+    ran::Int32; reserved::Int32; diversity::Float64; n_accepted::Int64
+end
+struct DeviceMove <: ParticleTransformer
+    cols::Vector{Int32}; comps::Vector{Int32}
+    proposal::Int32                       # 0 RW, 1 autoRW
+    step::Float64                         # RW: step_size; autoRW: min_step (1e-3)
+    lo::Vector{Float64}; hi::Vector{Float64}   # empty: bounds === nothing
+    diversity::Float64                    # NaN: always move
+end
+function apply!(t::DeviceMove, state::SMCState{DeviceColumnStore})
+    info = Ref(WsMoveInfo(0, 0, NaN, 0))
+    GC.@preserve t begin
+        spec = WsMoveSpec(length(t.cols), pointer(t.cols), pointer(t.comps), t.proposal, isempty(t.lo) ? 0 : 1,
+                          isempty(t.lo) ? C_NULL : pointer(t.lo), isempty(t.hi) ? C_NULL : pointer(t.hi),
+                          t.step, t.diversity, -1)                  # -1: score up to state.depth, as Move.apply! does
+        check(ctx(state), ccall((:ws_move, LIB), Cint, (Ptr{Cvoid}, Ref{WsMoveSpec}, Ref{WsMoveInfo}), ctx(state), spec, info))
+    end
+    return nothing                                                  # depth-neutral, weights untouched (transformers.jl:585-586)
+end
+score!(::DeviceMove, state, c) = nothing
+
+function marginal_diversity(state::SMCState{DeviceColumnStore}, cols::Vector{Int32}, comps::Vector{Int32})
+    out = Ref(0.0)
+    check(ctx(state), ccall((:ws_marginal_diversity, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Int32}, Ref{Float64}),
+                            ctx(state), length(cols), cols, comps, out))
+    out[]
+end
+function score_logpdf(state::SMCState{DeviceColumnStore}, target_depth::Integer)      # src/types.jl:183-206
+    out = Vector{Float64}(undef, state.store.n)
+    check(ctx(state), ccall((:ws_score_logpdf, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), ctx(state), target_depth, out))
+    out
+end
+
+# ---- @E / expectation and sample(state, n) (src/utils.jl:11,45-68,102-118) ------------------------------------
+function expectation(fs::Vector{DeviceExpr}, state::SMCState{DeviceColumnStore})
+    out = Vector{Float64}(undef, length(fs))
+    GC.@preserve fs begin
+        es = [cexpr(f) for f in fs]
+        check(ctx(state), ccall((:ws_expectation, LIB), Cint, (Ptr{Cvoid}, Ptr{WsExpr}, Int32, Ptr{Float64}), ctx(state), es, length(fs), out))
+    end
+    out
+end
+function sample_rows(state::SMCState{DeviceColumnStore}, name::Symbol, n::Integer; replace::Bool=true)
+    idx = Vector{Int64}(undef, n)
+    check(ctx(state), ccall((:ws_sample_indices, LIB), Cint, (Ptr{Cvoid}, Int64, Cint, Ptr{Int64}), ctx(state), n, replace, idx))
+    id, w = lookup(state.store, name)
+    rows = Matrix{Float64}(undef, n, w)
+    check(ctx(state), ccall((:ws_col_download_rows, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Int64}, Int64, Ptr{Float64}),
+                            ctx(state), id, idx, n, rows))
+    idx .+ 1, rows
+end
+
+# ---- replayed standard variates (parity tests: SURVEY 8c consumption order) -------------------------------------
+set_replay_normals(state, v::Vector{Float64}) = check(ctx(state), ccall((:ws_set_replay_normals, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx(state), v, length(v)))
+set_replay_uniforms(state, v::Vector{Float64}) = check(ctx(state), ccall((:ws_set_replay_uniforms, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx(state), v, length(v)))
+set_replay_exponentials(state, v::Vector{Float64}) = check(ctx(state), ccall((:ws_set_replay_exponentials, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx(state), v, length(v)))
+
+# ---- one filter over several GPUs: one Julia process per GPU (INTEGRATION.md) -----------------------------------
+nccl_unique_id() = (buf = zeros(UInt8, 128); check(C_NULL, ccall((:ws_nccl_unique_id, LIB), Cint, (Ptr{UInt8},), buf)); buf)
+function ShardedColumnStore(n_global::Integer, rank::Integer, nranks::Integer, id::Vector{UInt8}; device=rank, seed=0,
+                            ess_perc_min=0.5, resampler=0)
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:ws_create_sharded, LIB), Cint, (Ref{Ptr{Cvoid}}, Int64, Cint, Cint, Ptr{UInt8}, Cint, UInt64, Cdouble, Cint),
+                        ref, n_global, rank, nranks, id, device, seed, ess_perc_min, resampler))
+    nl = Ref{Int64}(0); ng = Ref{Int64}(0)
+    check(ref[], ccall((:ws_n_particles, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), ref[], nl, ng))
+    s = DeviceColumnStore(ref[], Int(nl[]))          # the rank's shard: global slots [rank N / R, (rank + 1) N / R)
+    finalizer(s -> ccall((:ws_destroy, LIB), Cint, (Ptr{Cvoid},), s.ctx), s)
+    return s
+end
+
 end # module
