@@ -338,7 +338,7 @@ int ws_set_timing(ws_ctx* ctx, int on); /* record per-phase CUDA events (adds sy
 /* sharded state: particles this rank has received from other ranks in all resampling steps so far */
 int ws_get_migrated(ws_ctx* ctx, int64_t* out);
 /* offspring this rank has written DIRECTLY into other ranks' planes over NVLink (peer mappings; the exchange falls back to
- * stage + ncclSend / ncclRecv for a handful of migrants, with WSB200_EXCHANGE=nccl, or when ranks share a process) */
+ * stage + ncclSend / ncclRecv with WSB200_EXCHANGE=nccl or when ranks share a process) */
 int ws_get_pushed(ws_ctx* ctx, int64_t* out);
 /* the Philox stream id the next random statement / resample will use, and the key (tests reproduce draws) */
 int ws_next_philox_stream(ws_ctx* ctx, uint64_t* stream_out, uint64_t* seed_out);

@@ -244,12 +244,15 @@ struct ws_ctx {
     // direct exchange: migrating offspring are gathered STRAIGHT into the destination rank's planes over NVLink
     // (peer mappings of the other ranks' slabs, cudaIpc), one kernel per destination instead of stage + ncclSend/Recv
     bool push_exchange = true;               // env WSB200_EXCHANGE=nccl: always stage + ncclSend / ncclRecv
-    int64_t push_min = -1;                   // migrants over all ranks from which the direct path is used (env WSB200_PUSH_MIN);
-                                             // default: 128 MB of migrating plane data — below that the address exchange and the
-                                             // barrier (0.19 ms per step on 2 GPUs) cost more than staging + ncclSend/ncclRecv
+    int64_t push_min = 0;                    // migrants over all ranks from which the direct path is used (env WSB200_PUSH_MIN)
     size_t slabs_published = 0;              // how many of my slabs the other ranks have mapped
     std::vector<std::vector<char*>> peer_slabs;  // [rank][slab index]: that rank's slabs in this process's address space
     unsigned long long* d_barrier = nullptr; // 8 bytes all-reduced after the pushes: a stream-ordered barrier over the ranks
+    // per-step message of a rank, all-gathered once: [(first, end) produced slot | slab count | pid | per plane:
+    // (slab, offset) of the front and of the back buffer].  The bounds are written by ws_bounds_kernel, the rest
+    // by the host; the plane addresses ride along so that the direct exchange needs no round trip of its own.
+    int64_t* d_xmsg = nullptr;
+    size_t xmsg_words = 0;                   // words per rank the buffer was sized for
     int64_t pushed_total = 0;                // particles written directly into peers so far
     double phase_ms[8] = {0};                // WSB200_TRACE=1: host wall time per phase of resample_sharded
     int64_t phase_n = 0;
@@ -620,6 +623,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
         for (char* b : ps)
             if (b) cudaIpcCloseMemHandle(b);
     if (c->d_barrier) cudaFree(c->d_barrier);
+    if (c->d_xmsg) cudaFree(c->d_xmsg);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_score_ops);
     cudaFree(c->d_seg_ops);
@@ -1566,44 +1570,51 @@ static int allgather_host_bytes(ws_ctx* c, const void* mine, size_t bytes, std::
     return WS_OK;
 }
 
-struct PeerPlane {
-    int64_t slab;  // index into the owner's slab list
-    int64_t off;   // byte offset inside the slab
-};
-
-// Every rank announces where (slab, offset) each of `mine` — the buffers its incoming offspring go to, one per plane —
-// lives; slabs the others have not mapped yet are exported (cudaIpcGetMemHandle) and mapped (cudaIpcOpenMemHandle)
-// first.  peer[q][p] = rank q's buffer for plane p as a pointer valid in THIS process.  *usable = false (on every
-// rank alike) when two ranks share a process: IPC mappings need separate processes, the caller then stages + sends.
-static int map_peer_planes(ws_ctx* c, const std::vector<double*>& mine, std::vector<std::vector<double*>>& peer, bool* usable) {
-    const int R = c->nranks, r = c->rank;
-    const size_t P = mine.size();
-    std::vector<int64_t> msg(2 + 2 * P);
-    msg[0] = (int64_t)c->slabs.size();
-    msg[1] = (int64_t)getpid();
-    for (size_t p = 0; p < P; ++p) {
-        int64_t slab = -1, off = 0;
-        for (size_t k = 0; k < c->slabs.size(); ++k) {
-            const char* b = c->slabs[k].base;
-            if ((const char*)mine[p] >= b && (const char*)mine[p] < b + c->slabs[k].size) {
-                slab = (int64_t)k;
-                off = (int64_t)((const char*)mine[p] - b);
-                break;
-            }
+// (slab index, byte offset) of a device pointer inside this rank's slabs; slab = -1 for nullptr
+static int locate_in_slabs(ws_ctx* c, const void* ptr, int64_t* slab, int64_t* off) {
+    *slab = -1;
+    *off = 0;
+    if (ptr == nullptr) return WS_OK;
+    for (size_t k = 0; k < c->slabs.size(); ++k) {
+        const char* b = c->slabs[k].base;
+        if ((const char*)ptr >= b && (const char*)ptr < b + c->slabs[k].size) {
+            *slab = (int64_t)k;
+            *off = (int64_t)((const char*)ptr - b);
+            return WS_OK;
         }
-        if (slab < 0) return fail(c, WS_ECUDA, "direct exchange: a plane buffer is not inside a slab");
-        msg[2 + 2 * p] = slab;
-        msg[3 + 2 * p] = off;
     }
-    std::vector<char> all;
-    TRY(allgather_host_bytes(c, msg.data(), sizeof(int64_t) * msg.size(), all));
-    auto row = [&](int q) { return reinterpret_cast<const int64_t*>(all.data() + sizeof(int64_t) * msg.size() * (size_t)q); };
+    return fail(c, WS_ECUDA, "direct exchange: a plane buffer is not inside a slab");
+}
+
+#define WS_XMSG_HEAD 3  // words before the plane table: packed bounds, slab count, pid
+static size_t xmsg_words(size_t n_planes) { return WS_XMSG_HEAD + 4 * n_planes; }
+
+// host part of this rank's message (words 1 ..): slab count, pid, (slab, offset) of every plane's front and back buffer
+static int fill_xmsg(ws_ctx* c, const std::vector<Plane>& planes, std::vector<int64_t>& w) {
+    w.assign(xmsg_words(planes.size()), 0);
+    w[1] = (int64_t)c->slabs.size();
+    w[2] = (int64_t)getpid();
+    for (size_t p = 0; p < planes.size(); ++p) {
+        const Column& col = c->cols[planes[p].col];
+        TRY(locate_in_slabs(c, col.front[planes[p].comp], &w[WS_XMSG_HEAD + 4 * p], &w[WS_XMSG_HEAD + 4 * p + 1]));
+        TRY(locate_in_slabs(c, col.back[planes[p].comp], &w[WS_XMSG_HEAD + 4 * p + 2], &w[WS_XMSG_HEAD + 4 * p + 3]));
+    }
+    return WS_OK;
+}
+
+// From the all-gathered messages: map the slabs that are new since the last exchange (cudaIpcGetMemHandle /
+// cudaIpcOpenMemHandle, rounds of up to 32 handles per rank, the same rounds on every rank) and resolve
+// peer[q][p] = rank q's front (lazy) or back (eager) buffer of plane p as a pointer valid in THIS process.
+// *usable = false (on every rank alike) when two ranks share a process: IPC mappings need separate processes.
+static int resolve_peer_planes(ws_ctx* c, const std::vector<int64_t>& all, size_t words, size_t P, bool lazy,
+                               std::vector<std::vector<double*>>& peer, bool* usable) {
+    const int R = c->nranks, r = c->rank;
+    auto row = [&](int q) { return all.data() + words * (size_t)q; };
     *usable = true;
     for (int q = 0; q < R; ++q)
         for (int q2 = q + 1; q2 < R; ++q2)
-            if (row(q)[1] == row(q2)[1]) *usable = false;
+            if (row(q)[2] == row(q2)[2]) *usable = false;
     if (!*usable) return WS_OK;
-    // map the slabs that are new since the last exchange: rounds of up to H handles per rank (same rounds on every rank)
     const int H = 32;
     struct Block {
         int64_t count;
@@ -1614,12 +1625,12 @@ static int map_peer_planes(ws_ctx* c, const std::vector<double*>& mine, std::vec
         bool need = false;
         for (int q = 0; q < R; ++q) {
             const size_t known = (q == r) ? c->slabs_published : c->peer_slabs[q].size();
-            if ((size_t)row(q)[0] > known) need = true;
+            if ((size_t)row(q)[1] > known) need = true;
         }
         if (!need) break;
         Block b;
         memset(&b, 0, sizeof(b));
-        const size_t target = (size_t)msg[0];  // the slab count announced above (nothing is allocated in between)
+        const size_t target = (size_t)row(r)[1];  // the slab count announced in the message (nothing is allocated in between)
         while (c->slabs_published + (size_t)b.count < target && b.count < H) {
             CK(c, cudaIpcGetMemHandle(&b.h[b.count], c->slabs[c->slabs_published + (size_t)b.count].base));
             b.count++;
@@ -1644,8 +1655,8 @@ static int map_peer_planes(ws_ctx* c, const std::vector<double*>& mine, std::vec
     for (int q = 0; q < R; ++q) {
         if (q == r) continue;
         for (size_t p = 0; p < P; ++p) {
-            const int64_t slab = row(q)[2 + 2 * p], off = row(q)[3 + 2 * p];
-            if (slab < 0 || (size_t)slab >= c->peer_slabs[q].size()) return fail(c, WS_ECUDA, "direct exchange: unknown peer slab");
+            const int64_t slab = row(q)[WS_XMSG_HEAD + 4 * p + (lazy ? 0 : 2)], off = row(q)[WS_XMSG_HEAD + 4 * p + (lazy ? 1 : 3)];
+            if (slab < 0 || (size_t)slab >= c->peer_slabs[q].size()) return fail(c, WS_ECUDA, "direct exchange: unknown peer buffer");
             peer[q][p] = reinterpret_cast<double*>(c->peer_slabs[q][(size_t)slab] + off);
         }
     }
@@ -1677,7 +1688,25 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     S.heavy_count = c->d_tile_counter + 1;
     S.last_rank = (r == R - 1) ? 1 : 0;
     S.total = c->d_all_tot + R;           // own total staged behind the allgather buffer
-    S.bounds = c->d_all_bounds + 2 * R;   // own (first, end) staged behind the allgather buffer
+    // this rank's message of the step (bounds + plane addresses, see d_xmsg), staged behind the allgather buffer
+    std::vector<Plane> planes;
+    for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
+        for (int32_t k = 0; k < c->cols[ci].width; ++k) planes.push_back(Plane{ci, k});
+    const size_t xw = xmsg_words(planes.size());
+    if (xw > c->xmsg_words) {
+        if (c->d_xmsg) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            CK(c, cudaFree(c->d_xmsg));
+            c->d_xmsg = nullptr;
+        }
+        c->xmsg_words = xw + 64;
+        CK(c, cudaMalloc(&c->d_xmsg, sizeof(int64_t) * c->xmsg_words * (size_t)(R + 1)));
+    }
+    int64_t* const d_xmine = c->d_xmsg + xw * (size_t)R;
+    S.bounds = reinterpret_cast<int32_t*>(d_xmine);   // word 0: (first, end) produced slot, written by ws_bounds_kernel
+    std::vector<int64_t> xmine;
+    TRY(fill_xmsg(c, planes, xmine));
+    CK(c, cudaMemcpyAsync(d_xmine + 1, xmine.data() + 1, sizeof(int64_t) * (xw - 1), cudaMemcpyHostToDevice, c->stream));
     TimedEvent te;
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_cdf(S, c->stream));
@@ -1688,11 +1717,13 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     S.all_tot = c->d_all_tot;
     S.rank = r;
     CK(c, ws_launch_bounds(S, c->stream));
-    NCK(c, g_nccl.AllGather(c->d_all_bounds + 2 * R, c->d_all_bounds, 2, WS_NCCL_INT32, c->comm, c->stream));
-    std::vector<int32_t> bnd(2 * R);
-    CK(c, cudaMemcpyAsync(bnd.data(), c->d_all_bounds, sizeof(int32_t) * 2 * R, cudaMemcpyDeviceToHost, c->stream));
+    NCK(c, g_nccl.AllGather(d_xmine, c->d_xmsg, xw, WS_NCCL_UINT64, c->comm, c->stream));
+    std::vector<int64_t> xall(xw * (size_t)R);
+    CK(c, cudaMemcpyAsync(xall.data(), c->d_xmsg, sizeof(int64_t) * xw * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    c->stats.d2h_bytes += (int64_t)(sizeof(int32_t) * 2 * R);
+    c->stats.d2h_bytes += (int64_t)(sizeof(int64_t) * xw * (size_t)R);
+    std::vector<int32_t> bnd(2 * R);
+    for (int q = 0; q < R; ++q) memcpy(&bnd[2 * q], &xall[xw * (size_t)q], 2 * sizeof(int32_t));
     c->phase_ms[0] += t_now() - t0;
     t0 = t_now();
     const int64_t fs = bnd[2 * r], fe = bnd[2 * r + 1];
@@ -1765,11 +1796,8 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     }
     const bool lazy = c->lazy_gather && fits;
 
-    std::vector<Plane> planes;
-    for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
-        for (int32_t k = 0; k < c->cols[ci].width; ++k) planes.push_back(Plane{ci, k});
     const int BATCH = 8;
-    // Direct exchange (enough migrants to pay for the address exchange): the gather kernel that would stage a
+    // Direct exchange: the gather kernel that would stage a
     // destination's offspring writes them straight into that rank's planes over NVLink — into the spare rows behind
     // its front planes (lazy) or at their final slots of its back planes (eager) — so gather and transfer are ONE
     // kernel per destination and nothing is staged or received.  Safe without a barrier in front: every rank has
@@ -1781,19 +1809,11 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
         const int64_t dlo = rank_lo(d), dhi = rank_lo(d + 1);
         total_remote += (dhi - dlo) - std::max<int64_t>(0, std::min<int64_t>(bnd[2 * d + 1], dhi) - std::max<int64_t>(bnd[2 * d], dlo));
     }
-    const bool enough = c->push_min >= 0 ? total_remote >= c->push_min
-                                         : total_remote * (int64_t)planes.size() * 8 >= ((int64_t)128 << 20);
-    bool push = c->push_exchange && enough && !planes.empty();
+    bool push = c->push_exchange && total_remote > 0 && total_remote >= c->push_min && !planes.empty();
     std::vector<std::vector<double*>> peer;
     if (push) {
-        std::vector<double*> mine(planes.size());
-        for (size_t p = 0; p < planes.size(); ++p) {
-            Column& col = c->cols[planes[p].col];
-            mine[p] = lazy ? col.front[planes[p].comp] : col.back[planes[p].comp];
-            if (mine[p] == nullptr) return fail(c, WS_ECUDA, "direct exchange: plane without a destination buffer");
-        }
         bool usable = false;
-        TRY(map_peer_planes(c, mine, peer, &usable));
+        TRY(resolve_peer_planes(c, xall, xw, planes.size(), lazy, peer, &usable));
         if (!usable) {
             push = false;
             c->push_exchange = false;  // ranks share a process: stay on ncclSend / ncclRecv (every rank decides alike)
