@@ -55,7 +55,7 @@ def _worker(rank, world, port, n, T, ess, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,ess", [(2, 1.0), (2, 0.5)])
+@pytest.mark.parametrize("world,ess", [(2, 1.0), (2, 0.5), (4, 1.0)])
 def test_sharded_equals_single_gpu(world, ess):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
