@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "../../weightedsampling.jl_b200/csrc/ws_lowering.h"
+#include "../../weightedsampling.jl_b200/csrc/ws_exchange.h"
 
 using wsl::Plane;
 using wsl::Program;
@@ -287,6 +288,29 @@ int hh_score_device_order(HH* h, int n_entries, double* out, int* n_runs, int* n
     if (n_runs) *n_runs = runs;
     if (n_rows) *n_rows = rows;
     return 0;
+}
+// The exchange plan of a sharded resampling step (csrc/ws_exchange.h), rank r's view.  out: per rank d
+// [send_off, send_cnt, recv_off, recv_cnt, spare_pos, push_offset_lazy, push_offset_eager] (7 x R), then
+// [fs, fe, remote_send, remote_recv, total_remote, fits].
+void hh_exchange_plan(const int32_t* bnd, int R, int r, int64_t n_global, int64_t* out) {
+    const WsExchangePlan p = ws_exchange_plan(bnd, R, r, n_global);
+    for (int d = 0; d < R; ++d) {
+        int64_t* o = out + 7 * d;
+        o[0] = p.send_off[(size_t)d];
+        o[1] = p.send_cnt[(size_t)d];
+        o[2] = p.recv_off[(size_t)d];
+        o[3] = p.recv_cnt[(size_t)d];
+        o[4] = p.spare_pos[(size_t)d];
+        o[5] = d == r ? -1 : ws_push_offset(bnd, R, r, d, n_global, true);
+        o[6] = d == r ? -1 : ws_push_offset(bnd, R, r, d, n_global, false);
+    }
+    int64_t* t = out + 7 * R;
+    t[0] = p.fs;
+    t[1] = p.fe;
+    t[2] = p.remote_send;
+    t[3] = p.remote_recv;
+    t[4] = p.total_remote;
+    t[5] = p.fits ? 1 : 0;
 }
 // Philox / Box-Muller / slot-count building blocks of ws_math.cuh
 void hh_randn2(uint64_t particle, uint64_t stream, uint64_t seed, double* out2) { ws_randn2(particle, stream, seed, out2[0], out2[1]); }

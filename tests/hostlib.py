@@ -16,7 +16,7 @@ def lib():
     global _lib
     if _lib is None:
         deps = [SRC] + [os.path.join(HERE, "..", "weightedsampling.jl_b200", "csrc", f)
-                        for f in ("ws_lowering.h", "ws_vm.cuh", "ws_math.cuh")]
+                        for f in ("ws_lowering.h", "ws_vm.cuh", "ws_math.cuh", "ws_exchange.h")]
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", SO, SRC],
                            check=True)

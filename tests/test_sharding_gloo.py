@@ -4,11 +4,13 @@ resampler is covered by tests/test_gpu_sharded.py on a multi-GPU box."""
 import os
 import sys
 
+import numpy as np
 import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def _worker(rank, world, port, q):
@@ -65,3 +67,72 @@ def test_shard_bounds_partition():
             assert b[0][0] == 0 and b[-1][1] == n
             assert all(b[i][1] == b[i + 1][0] for i in range(R - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _plan(L, bnd, R, r, n):
+    import ctypes as C
+    out = np.zeros(7 * R + 6, dtype=np.int64)
+    b = np.ascontiguousarray(bnd, dtype=np.int32)
+    L.hh_exchange_plan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+    L.hh_exchange_plan(b.ctypes.data_as(C.c_void_p), R, r, n, out.ctypes.data_as(C.c_void_p))
+    per = out[:7 * R].reshape(R, 7)
+    t = out[7 * R:]
+    return per, dict(fs=t[0], fe=t[1], remote_send=t[2], remote_recv=t[3], total_remote=t[4], fits=bool(t[5]))
+
+
+@pytest.mark.parametrize("R", [2, 3, 4, 8])
+def test_exchange_plan_is_consistent_between_senders_and_receivers(R):
+    """csrc/ws_exchange.h, the host arithmetic of the sharded exchange: for random partitions of the global
+    slots into per-rank produced ranges, what every sender derives (piece sizes, where a piece lands in the receiver's
+    spare rows or back buffer: the direct NVLink exchange writes there without asking) must be what every receiver
+    derives for itself — no overlap, no gap, the same `fits` / migrant totals on every rank."""
+    import hostlib
+    L = hostlib.lib()
+    rng = np.random.default_rng(R)
+    for trial in range(300):
+        n = int(rng.integers(R * 5000, R * 400_000))
+        kind = trial % 4
+        if kind == 0:      # near-uniform weights: bounds close to the shard boundaries
+            cuts = np.array([n * q // R for q in range(1, R)]) + rng.integers(-50, 50, R - 1)
+        elif kind == 1:    # arbitrary masses
+            cuts = np.sort(rng.integers(0, n + 1, R - 1))
+        elif kind == 2:    # one rank holds (almost) everything
+            cuts = np.sort(np.concatenate([rng.integers(0, 20, R - 1 - (R - 1) // 2), n - rng.integers(0, 20, (R - 1) // 2)]))
+        else:              # some ranks produce nothing
+            cuts = np.sort(rng.choice([0, n // 3, n // 2, n], R - 1))
+        cuts = np.clip(np.sort(cuts), 0, n)
+        edges = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+        bnd = np.stack([edges[:-1], edges[1:]], axis=1).reshape(-1)
+        lo = [n * d // R for d in range(R + 1)]
+        plans = [_plan(L, bnd, R, r, n) for r in range(R)]
+        fits0, tot0 = plans[0][1]["fits"], plans[0][1]["total_remote"]
+        for r, (per, t) in enumerate(plans):
+            assert t["fits"] == fits0 and t["total_remote"] == tot0            # every rank decides alike
+            assert per[:, 1].sum() == t["fe"] - t["fs"]                        # every produced slot goes somewhere
+            assert per[:, 3].sum() == lo[r + 1] - lo[r]                        # every one of my slots comes from somewhere
+            assert t["remote_send"] == per[:, 1].sum() - per[r, 1] and t["remote_recv"] == per[:, 3].sum() - per[r, 3]
+        assert tot0 == sum(t["remote_recv"] for _, t in plans) == sum(t["remote_send"] for _, t in plans)
+        for d in range(R):                                                      # receiver d
+            per_d, t_d = plans[d]
+            n_d = lo[d + 1] - lo[d]
+            rows_lazy, rows_eager = [], []
+            for q in range(R):                                                  # sender q
+                per_q, _ = plans[q]
+                assert per_q[d, 1] == per_d[q, 3]                               # piece size: sender == receiver
+                if q == d or per_q[d, 1] == 0:
+                    continue
+                assert per_q[d, 6] == per_d[q, 2]                               # eager: lands at the receiver's recv_off
+                assert per_q[d, 5] == n_d + per_d[q, 4]                         # lazy: lands at the receiver's spare_pos
+                rows_lazy.append((per_q[d, 5], per_q[d, 5] + per_q[d, 1]))
+                rows_eager.append((per_q[d, 6], per_q[d, 6] + per_q[d, 1]))
+            if per_d[d, 3] > 0:
+                rows_eager.append((per_d[d, 2], per_d[d, 2] + per_d[d, 3]))       # the offspring that stay
+            rows_eager.sort()
+            assert rows_eager[0][0] == 0 and rows_eager[-1][1] == n_d
+            assert all(a[1] == b[0] for a, b in zip(rows_eager, rows_eager[1:]))  # eager pieces tile [0, n_d)
+            rows_lazy.sort()
+            assert all(a[1] <= b[0] for a, b in zip(rows_lazy, rows_lazy[1:]))    # spare-row pieces do not overlap
+            if rows_lazy:
+                assert rows_lazy[0][0] == n_d
+                if fits0:
+                    assert rows_lazy[-1][1] <= n_d + max(4096, n_d // 32)         # ... and stay inside the spare rows

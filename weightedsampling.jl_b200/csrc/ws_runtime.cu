@@ -28,6 +28,7 @@
 #include "ws_lowering.h"
 #include "ws_move.h"
 #include "ws_stats.h"
+#include "ws_exchange.h"
 
 using wsl::Plane;
 using wsl::Program;
@@ -1746,13 +1747,9 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     // Deferred gather + few migrants (the usual case): the search writes the ancestors of global slot s straight to
     // d_anc[s - my_lo] — own slots in place, the slots produced for the neighbours into the margins on either side —
     // instead of a staging vector that a second pass copies into place (8 B per particle saved).
-    bool fits_all = true;
-    for (int d = 0; d < R; ++d) {
-        const int64_t dlo = (c->n_global * (int64_t)d) / R, dhi = (c->n_global * (int64_t)(d + 1)) / R;
-        const int64_t own = std::max<int64_t>(0, std::min<int64_t>(bnd[2 * d + 1], dhi) - std::max<int64_t>(bnd[2 * d], dlo));
-        const int64_t d_spare = std::max<int64_t>(4096, (dhi - dlo) / 32);
-        if ((dhi - dlo) - own > d_spare) fits_all = false;
-    }
+    // (ws_exchange.h: every rank derives the whole plan from the all-gathered bounds)
+    const WsExchangePlan plan = ws_exchange_plan(bnd.data(), R, r, c->n_global);
+    const bool fits_all = plan.fits;
     const int64_t lo_r = (c->n_global * (int64_t)r) / R, hi_r = (c->n_global * (int64_t)(r + 1)) / R;
     const bool inplace = c->lazy_gather && fits_all && (lo_r - fs) <= c->spare && (fe - hi_r) <= c->spare;
     int32_t* const anc_src = inplace ? c->d_anc + (fs - lo_r) : c->d_anc_src;
@@ -1766,34 +1763,12 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     c->phase_ms[2] += t_now() - t0;
     t0 = t_now();
     // ---- exchange plan (slot ranges) ------------------------------------------------------------
-    auto rank_lo = [&](int d) { return (c->n_global * (int64_t)d) / R; };
-    const int64_t my_lo = rank_lo(r), my_hi = rank_lo(r + 1);
-    // what I send to d: produced slots in [rank_lo(d), rank_lo(d+1));  what I get from q: q's produced
-    // slots in my range.  Slot order makes every piece contiguous on both sides.
-    std::vector<int64_t> send_off(R), send_cnt(R), recv_off(R), recv_cnt(R);
-    int64_t remote_send = 0, remote_recv = 0;
-    for (int d = 0; d < R; ++d) {
-        const int64_t a = std::max(fs, rank_lo(d)), e = std::min(fe, rank_lo(d + 1));
-        send_cnt[d] = std::max<int64_t>(0, e - a);
-        send_off[d] = std::max<int64_t>(0, a - fs);
-        const int64_t qa = std::max<int64_t>(bnd[2 * d], my_lo), qe = std::min<int64_t>(bnd[2 * d + 1], my_hi);
-        recv_cnt[d] = std::max<int64_t>(0, qe - qa);
-        recv_off[d] = std::max<int64_t>(0, qa - my_lo);
-        if (d != r) {
-            remote_send += send_cnt[d];
-            remote_recv += recv_cnt[d];
-        }
-    }
+    auto rank_lo = [&](int d) { return ws_rank_lo(c->n_global, R, d); };
+    const std::vector<int64_t>&send_off = plan.send_off, &send_cnt = plan.send_cnt, &recv_off = plan.recv_off, &recv_cnt = plan.recv_cnt;
+    const int64_t remote_send = plan.remote_send, remote_recv = plan.remote_recv;
     c->migrated_total += remote_recv;
-    // every rank must take the same branch: the spare rows are sized from the shard size, so compare
-    // against the worst case over ranks (all bounds are known to everybody)
-    bool fits = true;
-    for (int d = 0; d < R; ++d) {
-        const int64_t dlo = rank_lo(d), dhi = rank_lo(d + 1);
-        const int64_t own = std::max<int64_t>(0, std::min<int64_t>(bnd[2 * d + 1], dhi) - std::max<int64_t>(bnd[2 * d], dlo));
-        const int64_t d_spare = std::max<int64_t>(4096, (dhi - dlo) / 32);
-        if ((dhi - dlo) - own > d_spare) fits = false;
-    }
+    // every rank takes the same branch: the spare rows are sized from the shard size and all bounds are known to everybody
+    const bool fits = plan.fits;
     const bool lazy = c->lazy_gather && fits;
 
     const int BATCH = 8;
@@ -1804,11 +1779,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     // passed the allgather of the bounds, i.e. finished all earlier kernels that touch its planes, and what it
     // runs meanwhile (search, its own gathers) reads front rows [0, n) and writes its OWN slots only.  A
     // stream-ordered all-reduce of one word afterwards is the barrier that tells a rank its incoming rows are complete.
-    int64_t total_remote = 0;
-    for (int d = 0; d < R; ++d) {
-        const int64_t dlo = rank_lo(d), dhi = rank_lo(d + 1);
-        total_remote += (dhi - dlo) - std::max<int64_t>(0, std::min<int64_t>(bnd[2 * d + 1], dhi) - std::max<int64_t>(bnd[2 * d], dlo));
-    }
+    const int64_t total_remote = plan.total_remote;
     bool push = c->push_exchange && total_remote > 0 && total_remote >= c->push_min && !planes.empty();
     std::vector<std::vector<double*>> peer;
     if (push) {
@@ -1819,16 +1790,6 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
             c->push_exchange = false;  // ranks share a process: stay on ncclSend / ncclRecv (every rank decides alike)
         }
     }
-    // first of my offspring's rows among rank d's spare rows (the receiver's spare_pos[r] below)
-    auto spare_pos_on = [&](int d) {
-        int64_t acc = 0;
-        const int64_t lo_d = rank_lo(d), hi_d = rank_lo(d + 1);
-        for (int q = 0; q < r; ++q) {
-            if (q == d) continue;
-            acc += std::max<int64_t>(0, std::min<int64_t>(bnd[2 * q + 1], hi_d) - std::max<int64_t>(bnd[2 * q], lo_d));
-        }
-        return acc;
-    };
     // the migrating offspring are the produced slots outside my own range: a prefix [0, pre) (to lower
     // ranks) and a suffix [suf0, produced) (to higher ranks) of the produced range
     const int64_t pre = send_off[r] > 0 || send_cnt[r] > 0 ? send_off[r] : produced;
@@ -1845,15 +1806,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     auto stage_pos = [&](int d) { return d < r ? send_off[d] : n_pre + (send_off[d] - suf0); };
     // where rank q's offspring land on my side: lazily in the spare rows behind the FRONT planes
     // (lower ranks first), eagerly at their final slots in the BACK planes
-    std::vector<int64_t> spare_pos(R, 0);
-    {
-        int64_t acc = 0;
-        for (int q = 0; q < R; ++q) {
-            if (q == r) continue;
-            spare_pos[q] = acc;
-            acc += recv_cnt[q];
-        }
-    }
+    const std::vector<int64_t>& spare_pos = plan.spare_pos;
     for (size_t p0 = 0; p0 < planes.size(); p0 += BATCH) {
         const int nb = (int)std::min<size_t>(BATCH, planes.size() - p0);
         if (!lazy && send_cnt[r] > 0) {
@@ -1880,8 +1833,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
                 G.n = send_cnt[d];
                 G.ancestors = anc_src + send_off[d];
                 G.n_planes = nb;
-                const int64_t n_d = rank_lo(d + 1) - rank_lo(d);
-                const int64_t at = lazy ? n_d + spare_pos_on(d) : std::max<int64_t>(fs, rank_lo(d)) - rank_lo(d);
+                const int64_t at = ws_push_offset(bnd.data(), R, r, d, c->n_global, lazy);
                 for (int k = 0; k < nb; ++k) {
                     const Plane pl = planes[p0 + k];
                     G.src[k] = c->cols[pl.col].front[pl.comp];
