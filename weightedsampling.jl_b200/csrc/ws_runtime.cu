@@ -1622,6 +1622,8 @@ static int resolve_peer_planes(ws_ctx* c, const std::vector<int64_t>& all, size_
         cudaIpcMemHandle_t h[H];
     };
     static_assert(sizeof(Block) % 8 == 0, "Block travels as 64-bit words");
+    bool map_failed = false;
+    int rounds = 0;
     for (;;) {
         bool need = false;
         for (int q = 0; q < R; ++q) {
@@ -1633,7 +1635,11 @@ static int resolve_peer_planes(ws_ctx* c, const std::vector<int64_t>& all, size_
         memset(&b, 0, sizeof(b));
         const size_t target = (size_t)row(r)[1];  // the slab count announced in the message (nothing is allocated in between)
         while (c->slabs_published + (size_t)b.count < target && b.count < H) {
-            CK(c, cudaIpcGetMemHandle(&b.h[b.count], c->slabs[c->slabs_published + (size_t)b.count].base));
+            if (cudaIpcGetMemHandle(&b.h[b.count], c->slabs[c->slabs_published + (size_t)b.count].base) != cudaSuccess) {
+                cudaGetLastError();  // memory that cannot be exported: agreed on below
+                map_failed = true;
+                memset(&b.h[b.count], 0, sizeof(cudaIpcMemHandle_t));
+            }
             b.count++;
         }
         c->slabs_published += (size_t)b.count;
@@ -1645,12 +1651,25 @@ static int resolve_peer_planes(ws_ctx* c, const std::vector<int64_t>& all, size_
             for (int64_t k = 0; k < pb->count; ++k) {
                 void* base = nullptr;
                 cudaError_t e = cudaIpcOpenMemHandle(&base, pb->h[k], cudaIpcMemLazyEnablePeerAccess);
-                if (e != cudaSuccess)
-                    return fail(c, WS_ECUDA, "direct exchange: cudaIpcOpenMemHandle failed (%s); set WSB200_EXCHANGE=nccl",
-                                cudaGetErrorString(e));
+                if (e != cudaSuccess) {
+                    cudaGetLastError();  // no peer access / IPC between these two processes: agreed on below
+                    map_failed = true;
+                    base = nullptr;
+                }
                 c->peer_slabs[q].push_back((char*)base);
             }
         }
+        rounds++;
+    }
+    if (rounds > 0) {
+        // a rank that could not map a peer's memory must not be written to blindly by the others either: everybody
+        // learns of any failure and the whole job stays on ncclSend / ncclRecv (the caller clears push_exchange)
+        const int64_t mine = map_failed ? 1 : 0;
+        std::vector<char> flags;
+        TRY(allgather_host_bytes(c, &mine, sizeof(mine), flags));
+        for (int q = 0; q < R; ++q)
+            if (reinterpret_cast<const int64_t*>(flags.data())[q] != 0) *usable = false;
+        if (!*usable) return WS_OK;
     }
     peer.assign((size_t)R, std::vector<double*>(P, nullptr));
     for (int q = 0; q < R; ++q) {
@@ -1787,7 +1806,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
         TRY(resolve_peer_planes(c, xall, xw, planes.size(), lazy, peer, &usable));
         if (!usable) {
             push = false;
-            c->push_exchange = false;  // ranks share a process: stay on ncclSend / ncclRecv (every rank decides alike)
+            c->push_exchange = false;  // ranks share a process, or no IPC / peer access: stay on ncclSend / ncclRecv (every rank decides alike)
         }
     }
     // the migrating offspring are the produced slots outside my own range: a prefix [0, pre) (to lower
