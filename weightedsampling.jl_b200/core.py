@@ -737,8 +737,17 @@ class Loop(ParticleTransformer):
 class Cond(ParticleTransformer):
     """``if cond ... end`` (transformers.jl:413-444); ``predfn(state) -> bool`` on the host."""
 
-    def __init__(self, predfn, body):
-        self.predfn, self.body = predfn, body
+    def __init__(self, predfn, body=None, lazy_body=None):
+        # ``lazy_body``: zero-argument builder of the body, used by the @model front-end when constructing the body
+        # has no build-time side effects: a loop that rebuilds `if resampled ... end` per iteration (the reference
+        # does, rewrites.jl:671-682) then pays for the body only in the iterations that take the branch
+        self.predfn, self._body, self._lazy = predfn, body, lazy_body
+
+    @property
+    def body(self):
+        if self._body is None:
+            self._body = self._lazy()
+        return self._body
 
     def apply(self, state):
         if self.predfn(state):

@@ -11,6 +11,7 @@ constant).
 from __future__ import annotations
 
 import ctypes as C
+import struct
 import math
 import numbers
 
@@ -268,6 +269,16 @@ def lower(e, store):
     raise _unsupported(f"cannot lower {type(e).__name__}")
 
 
+_tok_structs = {}
+
+
+def _TOK_STRUCT(n):
+    st = _tok_structs.get(n)
+    if st is None:
+        st = _tok_structs[n] = struct.Struct("<" + "iiiid" * n)
+    return st
+
+
 class CExprs:
     """Owns the ctypes arrays behind one or more ``ws_expr`` (keeps them alive for the call)."""
 
@@ -275,9 +286,12 @@ class CExprs:
         self._bufs = []
         self.arr = (L.ws_expr * len(token_lists))()
         for i, t in enumerate(token_lists):
-            buf = (L.ws_tok * len(t.toks))()
-            for k, (op, c, comp, val) in enumerate(t.toks):
-                buf[k].op, buf[k].col, buf[k].comp, buf[k].val = op, c, comp, val
+            # one packed copy instead of four ctypes attribute stores per token (the host walker lowers every
+            # statement of every loop iteration: this is on the per-step path)
+            flat = []
+            for op, c, comp, val in t.toks:
+                flat += (op, c, comp, 0, val)
+            buf = (L.ws_tok * len(t.toks)).from_buffer_copy(_TOK_STRUCT(len(t.toks)).pack(*flat))
             self._bufs.append(buf)
             self.arr[i].toks = C.cast(buf, C.POINTER(L.ws_tok))
             self.arr[i].n = len(t.toks)

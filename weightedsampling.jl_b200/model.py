@@ -644,6 +644,17 @@ class _Env:
     def child(self, values):
         return _Env(dict(values), self.pv, self.fam, self)
 
+    def snapshot(self):
+        """the bindings visible now, frozen: later rebinding of a build-time local does not reach a body built lazily"""
+        chain, e = [], self
+        while e is not None:
+            chain.append(e.values)
+            e = e.parent
+        merged = {}
+        for d in reversed(chain):
+            merged.update(d)
+        return _Env(merged, self.pv, self.fam, None)
+
     def set_local(self, name, v):
         # Julia closure scoping: assigning a name that exists in an enclosing scope rebinds it there
         e = self
@@ -746,6 +757,38 @@ def _lhs_target(lhs, env):
     raise ModelSyntaxError("unsupported assignment target")
 
 
+_ast_cache = {}
+
+
+def _uses_resampled(cond):
+    k = ("r", id(cond))
+    v = _ast_cache.get(k)
+    if v is None:
+        v = _ast_cache[k] = (cond, "resampled" in _names_in(cond)[0])   # the AST is kept alive with its id
+    return v[1]
+
+
+def _build_is_pure(stmts):
+    """True if constructing these statements assigns no build-time local (plain `=`, `+=`, ...), at any depth:
+    then WHEN the transformers are constructed cannot be observed."""
+    k = ("p", id(stmts))
+    v = _ast_cache.get(k)
+    if v is None:
+        def pure(ss):
+            for s in ss:
+                if s[0] == "for":
+                    if not pure(s[3]):
+                        return False
+                elif s[0] == "if":
+                    if not pure(s[2]):
+                        return False
+                elif s[0] != "expr" and s[1] in ("=", "+=", "-=", "*=", "/="):
+                    return False
+            return True
+        v = _ast_cache[k] = (stmts, pure(stmts))
+    return v[1]
+
+
 def _build(stmts, env, kernels, proposals):
     steps = []
     for s in stmts:
@@ -764,13 +807,17 @@ def _build(stmts, env, kernels, proposals):
             _, cond, body = s
             cenv = env
 
-            uses_resampled = "resampled" in _names_in(cond)[0]
+            uses_resampled = _uses_resampled(cond)
 
             def predfn(state, cond=cond, cenv=cenv, uses_resampled=uses_resampled):
                 # `resampled` -> state.resampled (rewrites.jl:360-368); anything else is build-time
                 vals = {"resampled": state.resampled} if uses_resampled else {}
                 return bool(ev(cond, cenv.child(vals)))
-            steps.append(core.Cond(predfn, core.Sequence(*_build(body, env.child({}), kernels, proposals))))
+            if _build_is_pure(body):
+                steps.append(core.Cond(predfn, lazy_body=lambda body=body, benv=env.snapshot(): core.Sequence(
+                    *_build(body, benv, kernels, proposals))))
+            else:   # build-time locals are assigned inside: construct now, as the reference does
+                steps.append(core.Cond(predfn, core.Sequence(*_build(body, env.child({}), kernels, proposals))))
         elif s[0] == "expr":
             steps.append(core.Resample())
         else:
