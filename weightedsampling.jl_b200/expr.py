@@ -270,6 +270,15 @@ def lower(e, store):
 
 
 _tok_structs = {}
+_expr_structs = {}
+_TOK_BYTES = 24   # sizeof(ws_tok): int32 op, col, comp, reserved; double val
+
+
+def _EXPR_STRUCT(n):
+    st = _expr_structs.get(n)
+    if st is None:
+        st = _expr_structs[n] = struct.Struct("<" + "Qii" * n)   # ws_expr: const ws_tok* toks; int32 n, reserved
+    return st
 
 
 def _TOK_STRUCT(n):
@@ -283,18 +292,22 @@ class CExprs:
     """Owns the ctypes arrays behind one or more ``ws_expr`` (keeps them alive for the call)."""
 
     def __init__(self, token_lists):
-        self._bufs = []
-        self.arr = (L.ws_expr * len(token_lists))()
-        for i, t in enumerate(token_lists):
-            # one packed copy instead of four ctypes attribute stores per token (the host walker lowers every
-            # statement of every loop iteration: this is on the per-step path)
-            flat = []
+        # One packed token buffer for all expressions of the statement and one packed ws_expr array pointing into it:
+        # two struct copies instead of four ctypes attribute stores per token and a cast per expression (the host
+        # walker lowers every statement of every loop iteration: this is on the per-step path).
+        flat, counts = [], []
+        for t in token_lists:
             for op, c, comp, val in t.toks:
                 flat += (op, c, comp, 0, val)
-            buf = (L.ws_tok * len(t.toks)).from_buffer_copy(_TOK_STRUCT(len(t.toks)).pack(*flat))
-            self._bufs.append(buf)
-            self.arr[i].toks = C.cast(buf, C.POINTER(L.ws_tok))
-            self.arr[i].n = len(t.toks)
+            counts.append(len(t.toks))
+        n_tok = sum(counts)
+        self._toks = (L.ws_tok * max(1, n_tok)).from_buffer_copy(_TOK_STRUCT(n_tok).pack(*flat) if n_tok else b"\0" * _TOK_BYTES)
+        base = C.addressof(self._toks)
+        head, off = [], 0
+        for k in counts:
+            head += (base + off * _TOK_BYTES, k, 0)
+            off += k
+        self.arr = (L.ws_expr * len(counts)).from_buffer_copy(_EXPR_STRUCT(len(counts)).pack(*head))
 
     def ptr(self, i=0):
         return C.cast(C.byref(self.arr, i * C.sizeof(L.ws_expr)), C.POINTER(L.ws_expr))
