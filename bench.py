@@ -9,11 +9,17 @@ particle-updates/s = N * steps / time.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--particles N] [--impl reference]
 
-* `value`     device time of the K steps (CUDA events on the library's stream).
+* `value`     device time of the K steps (CUDA events on the library's stream), library timing hooks OFF.
 * `e2e`       the same K steps through the public API (wsb200.run of the @model program) with host
               inputs (the observations) and a device->host read of the step result (log-evidence)
               inside the timed region, wall clock.
-* `roofline`  the dominant kernel (ancestor gather) against the measured HBM copy bandwidth.
+* `roofline`  the dominant kernel (the fused propagate + observe pass, which also performs the deferred
+              ancestor gather) against the measured HBM copy bandwidth; per-kernel times come from a SECOND,
+              separately run pass of the same steps with the library's per-kernel CUDA events switched on
+              (`ws_set_timing` adds event records, so it stays out of the headline region).
+* `sharded_parity` (N > 1)  before the timed region the ranks run a small sharded filter (n = 200 003, T = 12)
+              through both exchange paths and rank 0 compares it, particle for particle, with the same filter on
+              one GPU.
 * `cpu_baseline` / `--impl reference`  the C restatement of the reference's run! (oracle/ws_oracle.c:
               orc_ssm2d_run) on one host core (the reference is single-threaded: TODO.md:28).  Julia is
               not available, so this is "kind: port".
@@ -128,6 +134,76 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+PARITY_MODEL = '''
+@model function ssm(obs)
+    I2 = [1.0 0.0; 0.0 1.0]
+    x .= [0.0, 0.0]
+    v .= [1.0, 0.0]
+    for o in obs
+        x .= x + v
+        dv ~ MvNormal([0.0, 0.0], 0.1 * I2)
+        v .= v + dv
+        o => MvNormal(x, 0.5 * I2)
+    end
+end
+'''
+
+
+def sharded_parity(ws, dist, torch, local_rank, rank, world, n=200_003, T=12):
+    """tests/test_gpu_sharded.py::test_sharded_equals_single_gpu inside the bench (the driver's GPU test box has one
+    GPU, so this is where the multi-GPU path is checked on the final code): one global filter sharded over the
+    ranks == the same filter on one GPU, for the direct (peer-store) and the ncclSend/Recv exchange."""
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    obs = [np.array([t, 0.0]) + 0.7 * rng.standard_normal(2) for t in range(T)]
+    root_of = ws.model(PARITY_MODEL)
+    out = {"n": n, "T": T, "world": world, "paths": {}}
+    single = None
+    if rank == 0:
+        st1 = ws.SMCState(n, device=local_rank, seed=77, ess_perc_min=1.0)
+        ws.run(root_of(obs), st1)
+        single = (st1["x"], st1["v"], st1.weights, ws.log_evidence(st1), st1.stats()["resamples_done"])
+        del st1
+    for path in ("push", "nccl"):
+        old = os.environ.get("WSB200_EXCHANGE")
+        if path == "nccl":
+            os.environ["WSB200_EXCHANGE"] = "nccl"
+        else:
+            os.environ.pop("WSB200_EXCHANGE", None)
+        st = ws.sharded_state(n, device=local_rank, seed=77, ess_perc_min=1.0)
+        if old is None:
+            os.environ.pop("WSB200_EXCHANGE", None)
+        else:
+            os.environ["WSB200_EXCHANGE"] = old
+        ws.run(root_of(obs), st)
+        le = ws.log_evidence(st)
+        mig, pushed = C.c_int64(), C.c_int64()
+        st.store._call("ws_get_migrated", C.byref(mig))
+        st.store._call("ws_get_pushed", C.byref(pushed))
+        mine = (rank, st["x"], st["v"], st.weights, le, st.stats()["resamples_done"], mig.value, pushed.value)
+        box = [None] * world if rank == 0 else None
+        dist.gather_object(mine, box, dst=0)
+        del st
+        if rank == 0:
+            box.sort(key=lambda t: t[0])
+            xs = np.concatenate([b[1] for b in box])
+            vs = np.concatenate([b[2] for b in box])
+            wts = np.concatenate([b[3] for b in box])
+            x1, v1, w1, le1, nres1 = single
+            bad = ((np.abs(xs - x1) > 1e-9 * (1 + np.abs(x1))).any(axis=1) |
+                   (np.abs(vs - v1) > 1e-9 * (1 + np.abs(v1))).any(axis=1) |
+                   (np.abs(wts - w1) > 1e-9 * (1 + np.abs(w1))))
+            out["paths"][path] = {
+                "mismatches": int(bad.sum()), "bit_identical_particles": int(((xs == x1).all(axis=1) & (vs == v1).all(axis=1)).sum()),
+                "log_evidence_max_rel_err": float(max(abs(b[4] - le1) for b in box) / abs(le1)),
+                "resamples": [int(b[5]) for b in box], "resamples_single_gpu": int(nres1),
+                "migrated": int(sum(b[6] for b in box)), "pushed": int(sum(b[7] for b in box))}
+    if rank == 0:
+        out["mismatches"] = max(p["mismatches"] for p in out["paths"].values())
+        out["exchange"] = "push" if out["paths"]["push"]["pushed"] > 0 else "nccl"
+    return out
+
+
 def cpu_reference_run(n, steps, seed=1):
     """The reference's run! restated in C (oracle/ws_oracle.c), one core."""
     from oracle import cref
@@ -177,6 +253,8 @@ def main():
     ap.add_argument("--cpu-particles", type=int, default=2_000_000)
     ap.add_argument("--cpu-steps", type=int, default=40)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded == single-GPU check that precedes an N > 1 run")
+    ap.add_argument("--profile-steps", type=int, default=10, help="steps of the second pass that times each kernel class")
     ap.add_argument("--eager-gather", action="store_true", help="gather every column inside Resample (reference order of work)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -199,9 +277,15 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = sharded_parity(ws, dist, torch, local_rank, rank, world)
+        dist.barrier()
+
     N = args.particles
     K, W = args.steps, args.warmup
-    obs = synth_obs(W + K)
+    KP = max(3, min(K, args.profile_steps))        # steps of the per-kernel (timing hooks on) pass
+    obs = synth_obs(W + K + KP)
     build = ws.model(SSM2D_FILTER)
 
     if world > 1:
@@ -237,8 +321,6 @@ def main():
 
     if args.eager_gather:
         st._call("ws_set_lazy_gather", 0)
-    st._call("ws_set_timing", 1)
-    st._call("ws_reset_kernel_times")
     stats0 = state.stats()
     mig0c = C.c_int64()
     st._call("ws_get_migrated", C.byref(mig0c))
@@ -251,21 +333,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the K steps are issued as up to four consecutive run! calls with an event between them: the total is what is
+    # reported, the pieces show the spread inside the timed region
+    n_chunks = min(4, K)
+    cuts = [W + (K * i) // n_chunks for i in range(n_chunks + 1)]
+    roots = [cont(obs[a:b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(n_chunks + 1)]
     barrier()
     t0 = time.perf_counter()
-    ev0.record(stream)
-    ws.run(cont(obs[W:W + K]), state)
+    evs[0].record(stream)
+    for i, root in enumerate(roots):
+        ws.run(root, state)
+        if i + 1 < n_chunks:
+            evs[i + 1].record(stream)
     le = ws.log_evidence(state)          # device -> host read of the step result
-    ev1.record(stream)
+    evs[n_chunks].record(stream)
     state.sync()
     t1 = time.perf_counter()
     barrier()
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = evs[0].elapsed_time(evs[n_chunks])
     wall_ms = (t1 - t0) * 1e3
+    chunk_ms_per_step = [evs[i].elapsed_time(evs[i + 1]) / (cuts[i + 1] - cuts[i]) for i in range(n_chunks)]
     clocks = sampler.stop()
     stats1 = state.stats()
+    # second pass, NOT part of the headline: the same filter continues for KP steps with per-kernel events on
+    st._call("ws_set_timing", 1)
+    st._call("ws_reset_kernel_times")
+    evp0, evp1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    evp0.record(stream)
+    ws.run(cont(obs[W + K:W + K + KP]), state)
+    evp1.record(stream)
+    state.sync()
+    prof_ms = evp0.elapsed_time(evp1)
     kt = state.kernel_times()
+    st._call("ws_set_timing", 0)
     mig = C.c_int64()
     st._call("ws_get_migrated", C.byref(mig))
     migrated_per_step = (mig.value - mig0) / max(1, K)
@@ -289,22 +390,26 @@ def main():
         if name == "gather" and not eager:
             continue    # deferred gather: this class only stages the few offspring that migrate between ranks
         if k["launches"] > 0 and k["ms"] > 0:
-            avg_ms = k["ms"] / max(1, K)     # per step (a sharded step times the search in two regions)
+            avg_ms = k["ms"] / max(1, KP)    # per step (a sharded step times the search in two regions)
             gbs = alg * N / (avg_ms * 1e-3) / 1e9
             per_kernel[name] = {"avg_ms": avg_ms, "launches": k["launches"], "alg_bytes_per_particle": alg,
-                                "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": k["ms"] / dev_ms}
+                                "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": k["ms"] / prof_ms}
     dom = max(per_kernel, key=lambda n: per_kernel[n]["avg_ms"]) if per_kernel else None
     roofline = None
     if dom:
-        roofline = {"bound": "hbm", "kernel": {"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",
-                                                "scan_search": "ws_cdf_tiles_kernel + ws_cdf_offsets_kernel + ws_search_kernel"}[dom],
+        sl = stats1["sl_passes"] - stats0["sl_passes"]
+        vm_name = "ws_vm_sl_kernel<WsSigSsm2d>" if sl > 0 else "ws_vm_kernel"
+        scan_name = "ws_scan_search_kernel" if world == 1 else "ws_cdf_tiles_kernel + ws_cdf_offsets_kernel + ws_search_kernel"
+        roofline = {"bound": "hbm", "kernel": {"gather": "ws_gather_kernel", "fused_pass": vm_name, "scan_search": scan_name}[dom],
                     "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": per_kernel[dom]["frac"],
-                    "traffic": measured_traffic({"gather": "ws_gather_kernel", "fused_pass": "ws_vm_kernel",
-                                                 "scan_search": "ws_search_kernel"}[dom], N),
+                    "traffic": measured_traffic({"gather": "ws_gather_kernel", "fused_pass": vm_name.split("<")[0],
+                                                 "scan_search": scan_name.split(" ")[0]}[dom], N),
                     "traffic_source": "profiles/ncu_traffic.json (ncu --set full, bytes per particle at N=2e7) x N",
                     "peak_source": peak_src,
                     "per_kernel": per_kernel,
+                    "per_kernel_source": f"second pass of {KP} steps with ws_set_timing(1): {prof_ms / KP:.3f} ms/step "
+                                         f"(headline, hooks off: {dev_ms / K:.3f} ms/step)",
                     "whole_step": {"alg_bytes_per_particle": ALG_BYTES_STEP,
                                    "achieved_gbs": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9,
                                    "frac": ALG_BYTES_STEP * N * K / (dev_ms * 1e-3) / 1e9 / peak,
@@ -332,7 +437,8 @@ def main():
                        "particles_per_gpu": N, "planes": P_PLANES, "resampler": "stratified",
                        "parallelism": "single GPU" if world == 1 else
                        f"{world} ranks: ONE filter of {N * world} particles sharded by slot range; exact global stratified "
-                       "resampling (NCCL allgather of weight mass, send/recv migration of offspring)",
+                       "resampling (NCCL allgather of the weight masses; migrating offspring are written straight into the "
+                       "destination rank's planes over NVLink by the gather kernel, ncclSend/Recv as fallback)",
                        "migrated_particles_per_step": migrated_per_step,
                        "l2": "working set 10.4 GB per GPU >> 126 MB L2 (no flush needed)",
                        "log_evidence": le, "log_evidence_after_warmup": le0},
@@ -340,8 +446,10 @@ def main():
             "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": 16,
                     "d2h_bytes_per_step": int((stats1["d2h_bytes"] - stats0["d2h_bytes"]) / max(1, K))},
             "gpu_launches": int(launches), "clocks": clocks,
+            "ms_per_step_chunks": chunk_ms_per_step, "sharded_parity": parity,
             "fusion": {"fused_passes": stats1["fused_passes"] - stats0["fused_passes"],
                        "fused_statements": stats1["fused_statements"] - stats0["fused_statements"],
+                       "straight_line_passes": stats1["sl_passes"] - stats0["sl_passes"],
                        "resamples": stats1["resamples_done"] - stats0["resamples_done"]},
         }
         print(json.dumps(line), flush=True)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define WSB200_ABI_VERSION 1
+#define WSB200_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------- */
 #define WS_OK 0
@@ -294,6 +294,7 @@ typedef struct ws_stats {
     int64_t d2h_bytes;
     double last_resample_ms;   /* device time of the last scan+gather (CUDA events), when timing is on */
     double last_pass_ms;       /* device time of the last fused elementwise pass                     */
+    int64_t sl_passes;         /* ... fusion windows that ran on a straight-line executor (csrc/ws_vm_sl.cuh)  */
 } ws_stats;
 int ws_get_stats(ws_ctx* ctx, ws_stats* out);
 /* cumulative number of output slots whose uniform lay beyond the last CDF entry (clamped to the

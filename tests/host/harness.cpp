@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 #include "../../weightedsampling.jl_b200/csrc/ws_lowering.h"
+#include "../../weightedsampling.jl_b200/csrc/ws_vm_sl.cuh"
 #include "../../weightedsampling.jl_b200/csrc/ws_exchange.h"
 
 using wsl::Plane;
@@ -118,6 +119,25 @@ int hh_dump_window(HH* h, char* buf, int cap) {
     }
     snprintf(buf, cap, "%s", out.c_str());
     return (int)out.size();
+}
+// which straight-line signature (csrc/ws_vm_sl.cuh) the queued window matches: its index, or -1 (interpreter).
+// The view is filled exactly as flush_window (ws_runtime.cu) fills WsVmProgram.
+int hh_window_signature(HH* h) {
+    struct View {
+        int n_ops, n_loads, n_stores, n_expect;
+        uint8_t load_reg[64], store_reg[64];
+        std::vector<WsOp> ops;
+    } v;
+    const Program& w = h->win;
+    if (w.loads.size() > 64 || w.dirty.size() > 64) return -1;
+    v.n_ops = (int)w.ops.size();
+    v.n_loads = (int)w.loads.size();
+    v.n_stores = (int)w.dirty.size();
+    v.n_expect = 0;
+    for (int k = 0; k < v.n_loads; ++k) v.load_reg[k] = (uint8_t)w.loads[k].second;
+    for (int k = 0; k < v.n_stores; ++k) v.store_reg[k] = (uint8_t)w.plane_reg.at(w.dirty[k]);
+    v.ops = w.ops;
+    return ws_sl_find(v);
 }
 int hh_window_ops(HH* h) { return (int)h->win.ops.size(); }
 int hh_window_regs(HH* h) { return h->win.high_water; }

@@ -16,7 +16,7 @@ def lib():
     global _lib
     if _lib is None:
         deps = [SRC] + [os.path.join(HERE, "..", "weightedsampling.jl_b200", "csrc", f)
-                        for f in ("ws_lowering.h", "ws_vm.cuh", "ws_math.cuh", "ws_exchange.h")]
+                        for f in ("ws_lowering.h", "ws_vm.cuh", "ws_math.cuh", "ws_exchange.h", "ws_vm_sl.cuh")]
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
             subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", SO, SRC],
                            check=True)
@@ -25,7 +25,7 @@ def lib():
         L.hh_new.argtypes = [C.c_int64, C.c_uint64]
         L.hh_error.restype = C.c_char_p
         for name in ("hh_free", "hh_error", "hh_flush", "hh_n_flush", "hh_window_ops", "hh_window_regs",
-                     "hh_window_loads", "hh_window_stores", "hh_tape_len"):
+                     "hh_window_loads", "hh_window_stores", "hh_tape_len", "hh_window_signature"):
             getattr(L, name).argtypes = [C.c_void_p]
         L.hh_col.argtypes = [C.c_void_p, C.c_int]
         L.hh_set_plane.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]

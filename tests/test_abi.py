@@ -23,7 +23,7 @@ def test_header_symbols_are_exported_and_bound():
         assert hasattr(lib, s), f"libwsb200.so does not export {s}"
         assert s in wsb200._lib.SIGNATURES, f"python binding misses {s}"
     assert set(wsb200._lib.SIGNATURES) == set(syms)
-    assert lib.ws_abi_version() == 1
+    assert lib.ws_abi_version() == 2
 
 
 def test_no_cpu_fallback():

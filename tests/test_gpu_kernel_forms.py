@@ -1,0 +1,115 @@
+"""Two forms of the same kernel must give the same bits.
+
+* the fused elementwise window: straight-line executors (csrc/ws_vm_sl.cuh: compile-time signatures, register file
+  in registers) against the interpreter (ws_vm_kernel), selected with WSB200_VM=interp at context creation;
+* CDF + ancestor search: the single-pass kernel (ticketed tiles + decoupled look-back, ws_scan_search_kernel)
+  against the three-pass form (WSB200_SCAN=3pass), which sharded runs still use.
+
+Both pairs share their arithmetic by construction (the same ws_vm_exec_d / integer prefix sums), so the comparison
+is exact: every particle, every ancestor.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from models import LGSSM1D, LINREG, SSM1D, SSM2D, SSM2D_FILTER
+
+pytestmark = pytest.mark.gpu
+
+
+class env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        os.environ.update(self.kv)
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _run(ws, src, args, n, seed, ess=1.0, **envkv):
+    with env(**envkv):
+        st = ws.SMCState(n, ess_perc_min=ess, seed=seed, device=0)
+    ws.run(ws.model(src)(*args), st)
+    return st
+
+
+SSM1D_FILTER = '''
+@model function ssm1d_filter(obs)
+    x .= 0.0
+    v .= 0.0
+    for o in obs
+        x .= x + v
+        dv ~ Normal(0.0, 0.1)
+        v .= v + dv
+        o => Normal(x, 1.0)
+    end
+end
+'''
+
+CASES = [
+    ("ssm2d", SSM2D_FILTER, lambda rng: ([rng.standard_normal(2) + np.array([t, 0.0]) for t in range(12)],), ["x", "v", "dv"]),
+    ("ssm2d_hist", SSM2D, lambda rng: ([rng.standard_normal(2) + np.array([t, 0.0]) for t in range(6)],), ["x_7", "x_3", "v"]),
+    ("lgssm1d", LGSSM1D, lambda rng: (list(rng.standard_normal(15)), 0.9, 1.0, 0.5, 1.0), ["x"]),
+    ("ssm1d", SSM1D_FILTER, lambda rng: (list(rng.standard_normal(10)),), ["x", "v", "dv"]),
+    ("ssm1d_hist", SSM1D, lambda rng: (list(rng.standard_normal(8)),), ["x_9", "v"]),
+    ("linreg", LINREG, lambda rng: (list(rng.uniform(0, 10, 30)), list(1 - 0.5 * rng.uniform(0, 10, 30))), ["α", "β"]),
+]
+
+
+@pytest.mark.parametrize("name,src,mk,cols", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("n", [1000, 100_003])
+@pytest.mark.parametrize("ess", [0.5, 1.0])
+def test_straight_line_equals_interpreter(ws, name, src, mk, cols, n, ess):
+    args = mk(np.random.default_rng(3))
+    a = _run(ws, src, args, n, seed=21, ess=ess)
+    b = _run(ws, src, args, n, seed=21, ess=ess, WSB200_VM="interp")
+    sa, sb = a.stats(), b.stats()
+    assert sb["sl_passes"] == 0
+    if name != "ssm1d_hist":   # (its window is not in the signature table: x{t+1} is a new plane and v is stored too)
+        assert sa["sl_passes"] >= sa["fused_passes"] - 2, (sa["sl_passes"], sa["fused_passes"])
+    for c in cols:
+        np.testing.assert_array_equal(a[c], b[c], err_msg=f"{name}: column {c}")
+    np.testing.assert_array_equal(a.weights, b.weights)
+    assert ws.log_evidence(a) == ws.log_evidence(b)
+    assert sa["resamples_done"] == sb["resamples_done"]
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 2048, 2049, 100_003, 3_000_000])
+@pytest.mark.parametrize("s", [0.5, 3.0])
+@pytest.mark.parametrize("scheme", ["stratified", "systematic"])
+def test_single_pass_scan_search_equals_three_pass(ws, n, s, scheme):
+    w = np.exp(s * np.random.default_rng(n).standard_normal(n))
+    w /= w.sum()
+    out = []
+    for kv in ({}, {"WSB200_SCAN": "3pass"}):
+        with env(**kv):
+            st = ws.SMCState(max(n, 2), seed=5, device=0)
+        out.append(ws.resample_indices(w, st, scheme))
+        r = np.random.default_rng(1).random(n if scheme == "stratified" else 1)
+        out.append(ws.resample_indices(w, st, scheme, uniforms=r))
+    np.testing.assert_array_equal(out[0], out[2])   # Philox (integer grid)
+    np.testing.assert_array_equal(out[1], out[3])   # replayed uniforms (reference's floating-point grid)
+
+
+def test_single_pass_one_hot_and_zero_weights(ws):
+    n = 300_000
+    w = np.zeros(n)
+    w[123_456] = 0.97
+    w[::7] += 0.03 / len(w[::7])
+    w /= w.sum()
+    res = []
+    for kv in ({}, {"WSB200_SCAN": "3pass"}):
+        with env(**kv):
+            st = ws.SMCState(n, seed=9, device=0)
+        res.append(ws.resample_indices(w, st, "stratified"))
+    np.testing.assert_array_equal(res[0], res[1])
+    assert (res[0] == 123_456).sum() > 0.96 * n
+    assert np.all(w[res[0]] > 0)

@@ -71,6 +71,47 @@ def test_fusion_window_is_one_pass_for_an_ssm_step():
     assert L.hh_n_flush(h) == 1
 
 
+SL_SIGS = {"ssm2d": 0, "ssm2d_hist": 1, "lgssm1d": 2, "ssm1d": 3, "linreg_obs": 4}
+
+
+def _sig_of(setup, step):
+    hs = HostState(32)
+    for name, v in setup.items():
+        hs.store.setcol(name, v)
+    step.apply(hs)
+    return hs.store.L.hh_window_signature(hs.store.h)
+
+
+def test_benchmark_steps_match_their_straight_line_signatures():
+    """csrc/ws_vm_sl.cuh: the windows that carry the benchmarks run on compile-time executors; the signature is the
+    op pattern in canonical register numbering, so this pins the lowering AND the table (a changed lowering would
+    silently fall back to the interpreter otherwise)."""
+    n = 32
+    z1, z2 = np.zeros(n), np.zeros((n, 2))
+    I2 = np.eye(2)
+    ssm2d = ws.Sequence(ws.Assign("x", ws.col("x") + ws.col("v")), ws.Sample("dv", "MvNormal", ([0.0, 0.0], 0.1 * I2)),
+                        ws.Assign("v", ws.col("v") + ws.col("dv")),
+                        ws.Observe([0.3, -0.2], "MvNormal", (ws.col("x"), 0.5 * I2)))
+    assert _sig_of({"x": z2, "v": z2 + 1}, ssm2d) == SL_SIGS["ssm2d"]
+    # the second and later steps (dv exists already) are the same window
+    assert _sig_of({"x": z2, "v": z2 + 1, "dv": z2}, ssm2d) == SL_SIGS["ssm2d"]
+    hist = ws.Sequence(ws.Assign("x_2", ws.col("x_1") + ws.col("v")), ws.Sample("dv", "MvNormal", ([0.0, 0.0], 0.1 * I2)),
+                       ws.Assign("v", ws.col("v") + ws.col("dv")),
+                       ws.Observe([0.3, -0.2], "MvNormal", (ws.col("x_2"), 0.5 * I2)))
+    assert _sig_of({"x_1": z2, "v": z2 + 1}, hist) == SL_SIGS["ssm2d_hist"]
+    lg = ws.Sequence(ws.Sample("x", "Normal", (0.9 * ws.col("x"), 1.0)), ws.Observe(0.3, "Normal", (ws.col("x"), 0.5)))
+    assert _sig_of({"x": z1}, lg) == SL_SIGS["lgssm1d"]
+    s1 = ws.Sequence(ws.Assign("x", ws.col("x") + ws.col("v")), ws.Sample("dv", "Normal", (0.0, 0.1)),
+                     ws.Assign("v", ws.col("v") + ws.col("dv")), ws.Observe(0.3, "Normal", (ws.col("x"), 1.0)))
+    assert _sig_of({"x": z1, "v": z1}, s1) == SL_SIGS["ssm1d"]
+    obs = ws.Observe(0.3, "Normal", (ws.col("a") + ws.col("b") * 1.7, 1.0))
+    assert _sig_of({"a": z1, "b": z1}, obs) == SL_SIGS["linreg_obs"]
+    # anything else stays on the interpreter
+    other = ws.Sequence(ws.Sample("x", "Normal", (0.9 * ws.col("x"), 1.0)), ws.Observe(0.3, "Normal", (ws.col("x"), ws.col("s"))))
+    assert _sig_of({"x": z1, "s": z1 + 1}, other) == -1
+    assert _sig_of({"x": z1}, ws.Assign("x", ws.col("x") * ws.col("x"))) == -1
+
+
 def test_in_place_updates_and_register_recycling():
     n = 100
     rng = np.random.default_rng(2)

@@ -72,7 +72,7 @@ class ws_stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("fused_passes", C.c_int64), ("fused_statements", C.c_int64),
                 ("resamples_fired", C.c_int64), ("resamples_done", C.c_int64), ("moves_run", C.c_int64),
                 ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64), ("last_resample_ms", C.c_double),
-                ("last_pass_ms", C.c_double)]
+                ("last_pass_ms", C.c_double), ("sl_passes", C.c_int64)]
 
 
 KERNEL_CLASSES = ("fused_pass", "reduce", "finalize", "scan_search", "gather", "fill", "move", "other")
@@ -188,7 +188,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.ws_abi_version() != 1:
+    if lib.ws_abi_version() != 2:
         raise ImportError("libwsb200.so ABI version mismatch")
     _lib = lib
     return lib

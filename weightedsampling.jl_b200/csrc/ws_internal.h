@@ -136,6 +136,7 @@ cudaError_t ws_launch_patch_ancestors(int32_t* anc, int64_t n, int64_t self_lo, 
 cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t n_idx, double* dst, cudaStream_t s);
 cudaError_t ws_launch_compose(const WsComposeParams& P, int32_t* out, const int32_t* start, cudaStream_t s);
 cudaError_t ws_launch_compose_rows(const WsComposeParams& P, int64_t* out, const int64_t* start, cudaStream_t s);
+int ws_vm_sl_grid(const WsVmProgram& P);  // > 0: the window runs on a straight-line executor with this grid
 int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count);
 int ws_vm_smem_bytes(int n_regs, int n_loads, int n_ops);
 cudaError_t ws_kernels_init(int device);

@@ -316,6 +316,137 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Straight-line form of the fused window (ws_vm_sl.cuh): same tiling, staging and epilogue as
+// ws_vm_kernel<true>, but the window is a compile-time signature and its register file lives in registers.
+// Shared memory holds only the staging rows of the next tile's plane loads ([n_loads][PP][WS_VM_BLOCK]).
+// ------------------------------------------------------------------------------------------
+#include "ws_vm_sl.cuh"
+#ifndef WS_SL_P
+#define WS_SL_P 2      // particles per thread
+#endif
+#ifndef WS_SL_MINB
+#define WS_SL_MINB 6   // resident CTAs per SM the kernels are compiled for
+#endif
+template <class Sig, int PP>
+__global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const __grid_constant__ WsVmProgram P) {
+    extern __shared__ __align__(16) double ws_vm_smem[];
+    __shared__ WsLse warp_scratch[WS_VM_BLOCK / 32];
+    constexpr int RS = PP * WS_VM_BLOCK;
+    constexpr int TILE = WS_VM_BLOCK * PP;
+    constexpr int NL = Sig::n_loads, NS = Sig::n_stores;
+    double* const stage = ws_vm_smem + threadIdx.x;  // [NL][PP][WS_VM_BLOCK]
+
+    WsLse part;
+    part.m = -INFINITY;
+    part.S = 0.0;
+    part.Q = 0.0;
+    const int n = (int)P.n;
+    const int n_tiles = (n + TILE - 1) / TILE;
+    const bool any_gather = P.load_gather != 0u;
+
+    auto tile_index = [&](int tile, int j) -> int {
+        const int i = tile * TILE + (int)threadIdx.x + j * WS_VM_BLOCK;
+        return i < n ? i : n - 1;
+    };
+    auto issue_stage = [&](int tile, const int (&anc)[PP]) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const bool g = (P.load_gather >> k) & 1u;
+            const double* __restrict__ ptr = P.load_ptr[k];
+#pragma unroll
+            for (int j = 0; j < PP; ++j)
+                ws_cp_async8(stage + k * RS + j * WS_VM_BLOCK, ptr + (unsigned)(g ? anc[j] : tile_index(tile, j)));
+        }
+        ws_cp_async_commit();
+    };
+
+    int anc_next[PP];
+    {
+        const int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+        if (t0 < n_tiles) {
+            int a0[PP];
+#pragma unroll
+            for (int j = 0; j < PP; ++j) a0[j] = any_gather ? __ldg(P.ancestors + tile_index(t0, j)) : 0;
+            issue_stage(t0, a0);
+        }
+#pragma unroll
+        for (int j = 0; j < PP; ++j) anc_next[j] = (any_gather && t1 < n_tiles) ? __ldg(P.ancestors + tile_index(t1, j)) : 0;
+    }
+
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int idx[PP];
+        bool live[PP];
+        uint64_t particle[PP];
+        const int first = tile * TILE + (int)threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < PP; ++j) {
+            const int i = first + j * WS_VM_BLOCK;
+            live[j] = i < n;
+            idx[j] = live[j] ? i : n - 1;
+            particle[j] = (uint64_t)(P.particle_offset + (int64_t)idx[j]);
+        }
+        double R[Sig::n_regs * PP];
+        if (NL > 0) {
+            ws_cp_async_wait_all();
+            ws_sl_loads<Sig, PP, WS_VM_BLOCK>(R, stage, std::make_integer_sequence<int, NL>{});
+            const int tn = tile + gridDim.x, tnn = tn + gridDim.x;
+            if (tn < n_tiles) issue_stage(tn, anc_next);
+            if (any_gather && tnn < n_tiles) {
+#pragma unroll
+                for (int j = 0; j < PP; ++j) anc_next[j] = __ldg(P.ancestors + tile_index(tnn, j));
+            }
+        }
+        double lw_old[PP];
+#pragma unroll
+        for (int j = 0; j < PP; ++j) lw_old[j] = 0.0;
+        if (P.logw_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < PP; ++j) lw_old[j] = P.logw[(unsigned)idx[j]];
+        }
+
+        double acc[PP];
+#pragma unroll
+        for (int j = 0; j < PP; ++j) acc[j] = 0.0;
+        ws_sl_run<Sig, PP>(R, acc, P, particle, std::make_integer_sequence<int, Sig::n_ops>{});
+
+        ws_sl_stores<Sig, PP>(R, P, idx, live, std::make_integer_sequence<int, NS>{});
+        if (P.logw_mode != 0) {
+            double lw[PP];
+#pragma unroll
+            for (int j = 0; j < PP; ++j) {
+                lw[j] = (P.logw_mode == 1 ? lw_old[j] : P.logw_base) + acc[j];
+                if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
+            }
+            lse_push_many<PP>(part, lw, live);
+        }
+    }
+    if (P.logw_mode != 0 && P.partials != nullptr) {
+        WsLse tot = lse_block_reduce<WS_VM_BLOCK>(part, warp_scratch);
+        if (threadIdx.x == 0) P.partials[blockIdx.x] = tot;
+    }
+}
+
+static bool g_vm_interp_only = false;  // env WSB200_VM=interp: every window on the interpreter (A/B, tests)
+template <class Sig>
+static cudaError_t ws_launch_vm_sl(const WsVmProgram& P, cudaStream_t s) {
+    constexpr int TILE = WS_VM_BLOCK * WS_SL_P;
+    const int64_t tiles = (P.n + TILE - 1) / TILE;
+    int grid = (int)(tiles < (int64_t)g_sm_count * WS_SL_MINB ? tiles : (int64_t)g_sm_count * WS_SL_MINB);
+    if (grid < 1) grid = 1;
+    const int smem = (Sig::n_loads > 0 ? Sig::n_loads : 1) * TILE * (int)sizeof(double);
+    ws_vm_sl_kernel<Sig, WS_SL_P><<<grid, WS_VM_BLOCK, smem, s>>>(P);
+    return cudaGetLastError();
+}
+// (m, S, Q) partials a straight-line launch of this window would write (the runtime sizes n_partials with it)
+int ws_vm_sl_grid(const WsVmProgram& P) {
+    if (g_vm_interp_only || ws_sl_find(P) < 0) return 0;
+    constexpr int TILE = WS_VM_BLOCK * WS_SL_P;
+    const int64_t tiles = (P.n + TILE - 1) / TILE;
+    int grid = (int)(tiles < (int64_t)g_sm_count * WS_SL_MINB ? tiles : (int64_t)g_sm_count * WS_SL_MINB);
+    return grid < 1 ? 1 : grid;
+}
+
 // rows of the shared-memory register file: n_regs registers (+ n_loads staging rows when they fit)
 static bool ws_vm_staged(int n_regs, int n_loads) {
     return n_loads > 0 && (size_t)(n_regs + n_loads) * WS_VM_BLOCK * WS_VM_P * sizeof(double) <= (size_t)200 * 1024;
@@ -335,6 +466,15 @@ int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count) {
 }
 
 cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
+    if (!g_vm_interp_only) {
+        switch (ws_sl_find(P)) {
+#define WS_SL_CASE(idx, Sig) \
+    case idx: return ws_launch_vm_sl<Sig>(P, s);
+            WS_SL_SIGS(WS_SL_CASE)
+#undef WS_SL_CASE
+            default: break;
+        }
+    }
     const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads, P.n_ops);
     if (ws_vm_staged(P.n_regs, P.n_loads)) ws_vm_kernel<true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     else ws_vm_kernel<false><<<grid, WS_VM_BLOCK, smem, s>>>(P);
@@ -733,10 +873,266 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
     P.bounds[1] = fe;
 }
 
+// What every warp of a search needs besides the CDF: the slot-uniform provider and the slot grid.
+struct WsSearchCtx {
+    SlotUniform su;
+    unsigned long long r0_int;
+    int n, ns, slot_base;
+    double inv_n;
+};
+__device__ __forceinline__ void ws_search_setup(const WsScanParams& P, WsSearchCtx& X) {
+    X.n = (int)P.n;          // local particles
+    X.ns = (int)P.n_slots;   // global slots
+    X.inv_n = 1.0 / (double)X.ns;
+    X.slot_base = P.slot_base;
+    X.su.scheme = (P.scheme == 1) ? 1 : 0;
+    X.su.seed = P.seed;
+    X.su.stream = P.stream;
+    X.su.replay = P.replay_u;
+    X.su.r0 = 0.0;
+    X.su.cached_blk = -1;
+    X.r0_int = 0ull;
+    if (P.scheme == 1 && P.sorted_u == nullptr) {
+        if (P.replay_u != nullptr) {
+            X.su.r0 = P.replay_u[0];
+        } else {
+            ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
+            X.su.r0 = ws_u01(r.x, r.y);
+            X.r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
+        }
+    }
+}
+
+// One warp, one tile of WS_SCAN_TILE consecutive particles starting at `tile_base`, lane L holding the global
+// fixed-point CDF C[k] of particles tile_base + 8 L + k: per-particle slot counts F(C_m), then the offspring slots
+// [F(C_{m-1}), F(C_m)) of every particle are written to P.ancestors.  `Cp` (lane 0; valid iff has_prev) is the CDF of
+// the particle in front of the tile.  `rbuf`: the warp's shared-memory window (WS_RBUF_SLOTS words).
 template <bool EXACT_FP>
+__device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSearchCtx& X, unsigned long long* const rbuf,
+                                                    const int lane, const int tile_base,
+                                                    const unsigned long long (&C)[WS_SCAN_ITEMS], const unsigned long long Cp,
+                                                    const bool has_prev) {
+    int32_t* const out_s = reinterpret_cast<int32_t*>(rbuf);
+    SlotUniform& su = X.su;
+    const unsigned long long r0_int = X.r0_int;
+    const int n = X.n, ns = X.ns, slot_base = X.slot_base;
+    const double inv_n = X.inv_n;
+    const int item0 = tile_base + lane * WS_SCAN_ITEMS;
+    // ---- per-particle F(C_m) -----------------------------------------------------------------------
+    // F at the left edge of the particle set is by definition 0 (a slot with u = 0 belongs to
+    // particle 1, as in icdf); elsewhere it is the previous particle's F.
+    int f[WS_SCAN_ITEMS];
+    int fstart = slot_base;
+    bool coop = false;
+    if (!EXACT_FP && su.scheme == 0) {
+        // Philox-stratified: neighbouring particles ask for neighbouring slots, and one Philox block
+        // serves two slots, so the warp generates the uniforms of the tile's whole slot range once
+        // (half a Philox block per particle instead of one) and every lane looks its slots up.
+        unsigned int kk[WS_SCAN_ITEMS];
+        unsigned long long fr[WS_SCAN_ITEMS];
+        unsigned int kmax = 0u, kmin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            ws_slot_split(C[k], (unsigned int)ns, kk[k], fr[k]);
+            if (item0 + k >= n) kk[k] = 0xFFFFFFFFu;  // beyond the shard: patched below
+            if (kk[k] < (unsigned int)ns) {
+                kmax = max(kmax, kk[k]);
+                kmin = min(kmin, kk[k]);
+            }
+        }
+        unsigned int kp = 0u;
+        unsigned long long frp = 0ull;
+        if (lane == 0 && has_prev) {
+            ws_slot_split(Cp, (unsigned int)ns, kp, frp);
+            if (kp < (unsigned int)ns) {
+                kmax = max(kmax, kp);
+                kmin = min(kmin, kp);
+            }
+        }
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        const unsigned int blk0 = kmin >> 1;
+        coop = (kmin == 0xFFFFFFFFu) || ((kmax >> 1) - blk0 < (unsigned int)(WS_RBUF_SLOTS / 2));
+        if (coop) {
+            if (kmin != 0xFFFFFFFFu) {
+                const unsigned int nblk = (kmax >> 1) - blk0 + 1u;
+                for (unsigned int b = lane; b < nblk; b += 32u) {
+                    const ws_u32x4 r = ws_philox4x32_10((uint64_t)(blk0 + b), P.stream, P.seed);
+                    rbuf[2u * b] = (((unsigned long long)r.x << 32) | r.y) >> 3;
+                    rbuf[2u * b + 1u] = (((unsigned long long)r.z << 32) | r.w) >> 3;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                int fk;
+                if (kk[k] == 0xFFFFFFFFu) fk = -1;
+                else if (kk[k] >= (unsigned int)ns) fk = ns;
+                else fk = (int)kk[k] + (rbuf[kk[k] - 2u * blk0] <= fr[k] ? 1 : 0);
+                if (item0 + k == n - 1 && P.last_rank) {
+                    if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
+                    fk = ns;
+                }
+                f[k] = fk;
+            }
+            if (lane == 0 && has_prev)
+                fstart = (kp >= (unsigned int)ns) ? ns : (int)kp + (rbuf[kp - 2u * blk0] <= frp ? 1 : 0);
+            __syncwarp();  // the window is reused for the offspring below
+        }
+    }
+    if (!coop) {
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            const int gi = item0 + k;
+            int fk;
+            if (gi >= n) {
+                fk = -1;  // patched below
+            } else {
+                if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k]), inv_n, su);
+                else fk = ws_F_int(C[k], (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+                if (gi == n - 1 && P.last_rank) {
+                    if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
+                    fk = ns;  // leftover slots go to the last particle (the reference would throw BoundsError)
+                }
+            }
+            f[k] = fk;
+        }
+        if (lane == 0 && has_prev) {
+            if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
+            else fstart = ws_F_int(Cp, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+        }
+    }
+    // items beyond the shard produce nothing: they repeat the F of the shard's last particle
+    {
+        const int rank_end = P.bounds != nullptr ? P.bounds[1] : ns;
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k)
+            if (f[k] < 0) f[k] = rank_end;
+    }
+    fstart = __shfl_sync(0xffffffffu, fstart, 0);
+    int f_prev = __shfl_up_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 1);
+    if (lane == 0) f_prev = fstart;
+    const int fend = __shfl_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 31);
+
+    if (fend - fstart > WS_HEAVY_TILE_SLOTS) {
+        // a few particles own a huge share of the offspring: publish the tile's F table and let
+        // ws_expand_heavy_kernel fill its slots with the whole grid
+        unsigned int slot = 0;
+        if (lane == 0) slot = atomicAdd(P.heavy_count, 1u);
+        slot = __shfl_sync(0xffffffffu, slot, 0);
+        int32_t* dst = P.heavy_F + (size_t)slot * (WS_SCAN_TILE + 2);
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) dst[lane * WS_SCAN_ITEMS + k] = f[k];
+        if (lane == 0) {
+            dst[WS_SCAN_TILE] = fstart;
+            dst[WS_SCAN_TILE + 1] = tile_base / WS_SCAN_TILE;
+        }
+        return;
+    }
+
+    // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m ---------------------------------
+    if (fend - fstart <= WS_EXPAND_CHUNK) {
+        // the common case: the tile's slots fit one staging window.  Every particle with offspring marks
+        // the FIRST of its slots with its index + 1 (one predicated store, no divergence on the family
+        // size); the other slots take the last mark before them (a running maximum: marks increase with
+        // the slot), resolved four slots per lane and round and written as 16-byte stores.
+        int32_t* const gdst = P.ancestors + (fstart - slot_base);
+        const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 2) & 3u);  // window starts 16-byte aligned in global memory
+        const int W = fend - fstart + pad;
+        const int rounds = (W + 127) >> 7;
+        int4* const w4 = reinterpret_cast<int4*>(out_s);
+        for (int r = 0; r < rounds; ++r) w4[r * 32 + lane] = make_int4(0, 0, 0, 0);
+        __syncwarp();
+        {
+            int lo = f_prev;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                const int hi = f[k];
+                if (hi > lo) out_s[lo - fstart + pad] = item0 + k + 1;
+                lo = hi;
+            }
+        }
+        __syncwarp();
+        int32_t* const dst = gdst - pad;
+        int carry = 0;
+        for (int r = 0; r < rounds; ++r) {
+            const int4 v = w4[r * 32 + lane];
+            const int m0 = v.x, m1 = max(m0, v.y), m2 = max(m1, v.z), m3 = max(m2, v.w);
+            int incl = m3;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl = max(incl, t);
+            }
+            int excl = __shfl_up_sync(0xffffffffu, incl, 1);
+            if (lane == 0) excl = 0;
+            excl = max(excl, carry);
+            carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
+            const int4 o = make_int4(max(m0, excl) - 1, max(m1, excl) - 1, max(m2, excl) - 1, max(m3, excl) - 1);
+            const int p0 = r * 128 + lane * 4;
+            if (p0 >= pad && p0 + 4 <= W) {
+                *reinterpret_cast<int4*>(dst + p0) = o;
+            } else {
+                if (p0 >= pad && p0 < W) dst[p0] = o.x;
+                if (p0 + 1 >= pad && p0 + 1 < W) dst[p0 + 1] = o.y;
+                if (p0 + 2 >= pad && p0 + 2 < W) dst[p0 + 2] = o.z;
+                if (p0 + 3 >= pad && p0 + 3 < W) dst[p0 + 3] = o.w;
+            }
+        }
+        __syncwarp();
+        return;
+    }
+    // does this lane own a family too large for one lane?
+    bool has_big = false;
+    {
+        int lo = f_prev;
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            if (f[k] - lo > WS_DIRECT_MAX) has_big = true;
+            lo = f[k];
+        }
+    }
+    const unsigned big_mask = __ballot_sync(0xffffffffu, has_big);
+    for (int chunk = fstart; chunk < fend; chunk += WS_EXPAND_CHUNK) {
+        const int chunk_end = min(chunk + WS_EXPAND_CHUNK, fend);
+        {
+            int lo = f_prev;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                const int hi = f[k];
+                if (hi - lo <= WS_DIRECT_MAX) {
+                    const int a = max(lo, chunk), e = min(hi, chunk_end);
+                    for (int pos = a; pos < e; ++pos) out_s[pos - chunk] = item0 + k;
+                }
+                lo = hi;
+            }
+        }
+        unsigned bm = big_mask;
+        while (bm != 0u) {
+            const int src = __ffs(bm) - 1;
+            bm &= bm - 1u;
+            int lo = __shfl_sync(0xffffffffu, f_prev, src);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                const int hi = __shfl_sync(0xffffffffu, f[k], src);
+                if (hi - lo > WS_DIRECT_MAX) {
+                    const int a = max(lo, chunk), e = min(hi, chunk_end);
+                    const int anc = tile_base + src * WS_SCAN_ITEMS + k;
+                    for (int pos = a + lane; pos < e; pos += 32) out_s[pos - chunk] = anc;
+                }
+                lo = hi;
+            }
+        }
+        __syncwarp();
+        for (int pos = chunk + lane; pos < chunk_end; pos += 32) P.ancestors[pos - slot_base] = out_s[pos - chunk];
+        __syncwarp();
+    }
+}
+
 #ifndef WS_SEARCH_MINB
 #define WS_SEARCH_MINB 3
 #endif
+template <bool EXACT_FP>
 __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
 
@@ -746,31 +1142,12 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
     static_assert(WS_RBUF_SLOTS * 8 >= (WS_EXPAND_CHUNK + 128) * 4 && (WS_RBUF_SLOTS * 8) % 16 == 0, "window too small for the offspring staging");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long* const rbuf = win_all[warp];
-    int32_t* const out_s = reinterpret_cast<int32_t*>(win_all[warp]);
 
     const unsigned long long cdf_offset = ws_cdf_offset(P);
-    const int n = (int)P.n;          // local particles
-    const int ns = (int)P.n_slots;   // global slots
+    WsSearchCtx X;
+    ws_search_setup(P, X);
+    const int n = X.n;
     const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
-    const double inv_n = 1.0 / (double)ns;
-    const int slot_base = P.slot_base;
-    SlotUniform su;
-    su.scheme = (P.scheme == 1) ? 1 : 0;
-    su.seed = P.seed;
-    su.stream = P.stream;
-    su.replay = P.replay_u;
-    su.r0 = 0.0;
-    su.cached_blk = -1;
-    unsigned long long r0_int = 0ull;
-    if (P.scheme == 1 && P.sorted_u == nullptr) {
-        if (P.replay_u != nullptr) {
-            su.r0 = P.replay_u[0];
-        } else {
-            ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
-            su.r0 = ws_u01(r.x, r.y);
-            r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
-        }
-    }
 
     const int warps_total = gridDim.x * WS_WARPS_PER_CTA;
     for (int tile = blockIdx.x * WS_WARPS_PER_CTA + warp; tile < n_tiles; tile += warps_total) {
@@ -792,221 +1169,133 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? offset + __ldg(P.cdf_local + item0 + k) : 0ull;
         }
+        unsigned long long Cp = 0ull;
+        if (lane == 0 && tile != 0) {
+            const int p = tile_base - 1;
+            Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+        }
+        ws_search_warp_tile<EXACT_FP>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0);
+    }
+}
 
-        // ---- per-particle F(C_m) -----------------------------------------------------------------------
-        // F at the left edge of the particle set is by definition 0 (a slot with u = 0 belongs to
-        // particle 1, as in icdf); elsewhere it is the previous particle's F.
-        int f[WS_SCAN_ITEMS];
-        int fstart = slot_base;
-        bool coop = false;
-        if (!EXACT_FP && su.scheme == 0) {
-            // Philox-stratified: neighbouring particles ask for neighbouring slots, and one Philox block
-            // serves two slots, so the warp generates the uniforms of the tile's whole slot range once
-            // (half a Philox block per particle instead of one) and every lane looks its slots up.
-            unsigned int kk[WS_SCAN_ITEMS];
-            unsigned long long fr[WS_SCAN_ITEMS];
-            unsigned int kmax = 0u, kmin = 0xFFFFFFFFu;
-#pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                ws_slot_split(C[k], (unsigned int)ns, kk[k], fr[k]);
-                if (item0 + k >= n) kk[k] = 0xFFFFFFFFu;  // beyond the shard: patched below
-                if (kk[k] < (unsigned int)ns) {
-                    kmax = max(kmax, kk[k]);
-                    kmin = min(kmin, kk[k]);
-                }
-            }
-            unsigned int kp = 0u;
-            unsigned long long frp = 0ull;
-            if (lane == 0 && tile != 0) {
-                const int p = tile_base - 1;
-                const unsigned long long Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
-                ws_slot_split(Cp, (unsigned int)ns, kp, frp);
-                if (kp < (unsigned int)ns) {
-                    kmax = max(kmax, kp);
-                    kmin = min(kmin, kp);
-                }
-            }
-            kmax = __reduce_max_sync(0xffffffffu, kmax);
-            kmin = __reduce_min_sync(0xffffffffu, kmin);
-            const unsigned int blk0 = kmin >> 1;
-            coop = (kmin == 0xFFFFFFFFu) || ((kmax >> 1) - blk0 < (unsigned int)(WS_RBUF_SLOTS / 2));
-            if (coop) {
-                if (kmin != 0xFFFFFFFFu) {
-                    const unsigned int nblk = (kmax >> 1) - blk0 + 1u;
-                    for (unsigned int b = lane; b < nblk; b += 32u) {
-                        const ws_u32x4 r = ws_philox4x32_10((uint64_t)(blk0 + b), P.stream, P.seed);
-                        rbuf[2u * b] = (((unsigned long long)r.x << 32) | r.y) >> 3;
-                        rbuf[2u * b + 1u] = (((unsigned long long)r.z << 32) | r.w) >> 3;
-                    }
-                }
-                __syncwarp();
-#pragma unroll
-                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                    int fk;
-                    if (kk[k] == 0xFFFFFFFFu) fk = -1;
-                    else if (kk[k] >= (unsigned int)ns) fk = ns;
-                    else fk = (int)kk[k] + (rbuf[kk[k] - 2u * blk0] <= fr[k] ? 1 : 0);
-                    if (item0 + k == n - 1 && P.last_rank) {
-                        if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
-                        fk = ns;
-                    }
-                    f[k] = fk;
-                }
-                if (lane == 0 && tile != 0)
-                    fstart = (kp >= (unsigned int)ns) ? ns : (int)kp + (rbuf[kp - 2u * blk0] <= frp ? 1 : 0);
-                __syncwarp();  // the window is reused for the offspring below
-            }
-        }
-        if (!coop) {
-#pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                const int gi = item0 + k;
-                int fk;
-                if (gi >= n) {
-                    fk = -1;  // patched below
-                } else {
-                    if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k]), inv_n, su);
-                    else fk = ws_F_int(C[k], (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
-                    if (gi == n - 1 && P.last_rank) {
-                        if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
-                        fk = ns;  // leftover slots go to the last particle (the reference would throw BoundsError)
-                    }
-                }
-                f[k] = fk;
-            }
-            if (lane == 0 && tile != 0) {
-                const int p = tile_base - 1;
-                const unsigned long long Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
-                if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
-                else fstart = ws_F_int(Cp, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
-            }
-        }
-        // items beyond the shard produce nothing: they repeat the F of the shard's last particle
-        {
-            const int rank_end = P.bounds != nullptr ? P.bounds[1] : ns;
-#pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k)
-                if (f[k] < 0) f[k] = rank_end;
-        }
-        fstart = __shfl_sync(0xffffffffu, fstart, 0);
-        int f_prev = __shfl_up_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 1);
-        if (lane == 0) f_prev = fstart;
-        const int fend = __shfl_sync(0xffffffffu, f[WS_SCAN_ITEMS - 1], 31);
+// ---- CDF + search in ONE pass (single-GPU states) ---------------------------------------------------
+// A CTA takes the next tile of WS_CDF_TILE particles from an atomic ticket (tiles start in ticket order, so every
+// predecessor of a running tile is running or done: the look-back below cannot wait on a tile that has not been
+// scheduled), forms the tile's fixed-point weights and their local prefix sums in registers, publishes the tile
+// aggregate, obtains its exclusive prefix by a decoupled look-back over the predecessors' status words (one warp,
+// 32 predecessors per poll; flag and value travel in the same 64-bit word, so no fence is needed) and goes straight
+// on to the search / offspring expansion of its eight warp tiles.  Nothing but the log-weights is read (8 B) and
+// nothing but the ancestors written (4 B): the three-pass form's 16 B round trip through cdf_local is gone, and
+// the CDF — integer sums — is bit-identical to it.
+#ifndef WS_FUSED_MINB
+#define WS_FUSED_MINB 3
+#endif
+template <bool EXACT_FP>
+__global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+    __shared__ __align__(16) unsigned long long win_all[WS_WARPS_PER_CTA][WS_RBUF_SLOTS];
+    __shared__ unsigned long long warp_tot[WS_WARPS_PER_CTA];
+    __shared__ unsigned long long s_prefix;
+    __shared__ int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
+    WsSearchCtx X;
+    ws_search_setup(P, X);
+    const int n = X.n;
+    double m = 0.0, Sden = 1.0;
+    if (P.mode == 0) {
+        m = P.red->m;
+        Sden = P.red->S;  // w = e / S as exp_norm does (correctly rounded quotient, see ws_div_pos)
+    }
+    const double rS = 1.0 / Sden;
+    __syncthreads();
+    const int tile = s_tile;
+    const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
 
-        if (fend - fstart > WS_HEAVY_TILE_SLOTS) {
-            // a few particles own a huge share of the offspring: publish the tile's F table and let
-            // ws_expand_heavy_kernel fill its slots with the whole grid
-            unsigned int slot = 0;
-            if (lane == 0) slot = atomicAdd(P.heavy_count, 1u);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
-            int32_t* dst = P.heavy_F + (size_t)slot * (WS_SCAN_TILE + 2);
+    // ---- fixed-point weights of the thread's 8 consecutive particles, inclusive sums ----
+    unsigned long long q[WS_SCAN_ITEMS];
+    if (P.mode == 2) {
+        const unsigned long long qu = ws_w_to_fxs(1.0 / (double)P.n_slots);
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) dst[lane * WS_SCAN_ITEMS + k] = f[k];
-            if (lane == 0) {
-                dst[WS_SCAN_TILE] = fstart;
-                dst[WS_SCAN_TILE + 1] = tile;
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? qu : 0ull;
+    } else {
+        double l[WS_SCAN_ITEMS];
+        if (item0 + WS_SCAN_ITEMS <= n) {
+            const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                const double2 v = __ldg(p2 + k);
+                l[2 * k] = v.x;
+                l[2 * k + 1] = v.y;
             }
-            continue;
+        } else {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : -INFINITY;
         }
-
-        // ---- expand: offspring slots [F(C_{m-1}), F(C_m)) of particle m ---------------------------------
-        if (fend - fstart <= WS_EXPAND_CHUNK) {
-            // the common case: the tile's slots fit one staging window.  Every particle with offspring marks
-            // the FIRST of its slots with its index + 1 (one predicated store, no divergence on the family
-            // size); the other slots take the last mark before them (a running maximum: marks increase with
-            // the slot), resolved four slots per lane and round and written as 16-byte stores.
-            int32_t* const gdst = P.ancestors + (fstart - slot_base);
-            const int pad = (int)((reinterpret_cast<uintptr_t>(gdst) >> 2) & 3u);  // window starts 16-byte aligned in global memory
-            const int W = fend - fstart + pad;
-            const int rounds = (W + 127) >> 7;
-            int4* const w4 = reinterpret_cast<int4*>(out_s);
-            for (int r = 0; r < rounds; ++r) w4[r * 32 + lane] = make_int4(0, 0, 0, 0);
-            __syncwarp();
-            {
-                int lo = f_prev;
 #pragma unroll
-                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                    const int hi = f[k];
-                    if (hi > lo) out_s[lo - fstart + pad] = item0 + k + 1;
-                    lo = hi;
-                }
-            }
-            __syncwarp();
-            int32_t* const dst = gdst - pad;
-            int carry = 0;
-            for (int r = 0; r < rounds; ++r) {
-                const int4 v = w4[r * 32 + lane];
-                const int m0 = v.x, m1 = max(m0, v.y), m2 = max(m1, v.z), m3 = max(m2, v.w);
-                int incl = m3;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl = max(incl, t);
-                }
-                int excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                if (lane == 0) excl = 0;
-                excl = max(excl, carry);
-                carry = max(carry, __shfl_sync(0xffffffffu, incl, 31));
-                const int4 o = make_int4(max(m0, excl) - 1, max(m1, excl) - 1, max(m2, excl) - 1, max(m3, excl) - 1);
-                const int p0 = r * 128 + lane * 4;
-                if (p0 >= pad && p0 + 4 <= W) {
-                    *reinterpret_cast<int4*>(dst + p0) = o;
-                } else {
-                    if (p0 >= pad && p0 < W) dst[p0] = o.x;
-                    if (p0 + 1 >= pad && p0 + 1 < W) dst[p0 + 1] = o.y;
-                    if (p0 + 2 >= pad && p0 + 2 < W) dst[p0 + 2] = o.z;
-                    if (p0 + 3 >= pad && p0 + 3 < W) dst[p0 + 3] = o.w;
-                }
-            }
-            __syncwarp();
-            continue;
-        }
-        // does this lane own a family too large for one lane?
-        bool has_big = false;
-        {
-            int lo = f_prev;
-#pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                if (f[k] - lo > WS_DIRECT_MAX) has_big = true;
-                lo = f[k];
-            }
-        }
-        const unsigned big_mask = __ballot_sync(0xffffffffu, has_big);
-        for (int chunk = fstart; chunk < fend; chunk += WS_EXPAND_CHUNK) {
-            const int chunk_end = min(chunk + WS_EXPAND_CHUNK, fend);
-            {
-                int lo = f_prev;
-#pragma unroll
-                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                    const int hi = f[k];
-                    if (hi - lo <= WS_DIRECT_MAX) {
-                        const int a = max(lo, chunk), e = min(hi, chunk_end);
-                        for (int pos = a; pos < e; ++pos) out_s[pos - chunk] = item0 + k;
-                    }
-                    lo = hi;
-                }
-            }
-            unsigned bm = big_mask;
-            while (bm != 0u) {
-                const int src = __ffs(bm) - 1;
-                bm &= bm - 1u;
-                int lo = __shfl_sync(0xffffffffu, f_prev, src);
-#pragma unroll
-                for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                    const int hi = __shfl_sync(0xffffffffu, f[k], src);
-                    if (hi - lo > WS_DIRECT_MAX) {
-                        const int a = max(lo, chunk), e = min(hi, chunk_end);
-                        const int anc = tile_base + src * WS_SCAN_ITEMS + k;
-                        for (int pos = a + lane; pos < e; pos += 32) out_s[pos - chunk] = anc;
-                    }
-                    lo = hi;
-                }
-            }
-            __syncwarp();
-            for (int pos = chunk + lane; pos < chunk_end; pos += 32) P.ancestors[pos - slot_base] = out_s[pos - chunk];
-            __syncwarp();
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            double w;
+            if (P.mode == 0) w = ws_div_pos(ws_exp_nonpos(l[k] - m), Sden, rS);
+            else w = (item0 + k < n) ? l[k] : 0.0;
+            q[k] = (item0 + k < n) ? ws_w_to_fxs(w) : 0ull;
         }
     }
+#pragma unroll
+    for (int k = 1; k < WS_SCAN_ITEMS; ++k) q[k] += q[k - 1];
+    const unsigned long long thread_total = q[WS_SCAN_ITEMS - 1];
+    unsigned long long incl = thread_total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned long long warp_excl = 0ull, tile_agg = 0ull;
+#pragma unroll
+    for (int w = 0; w < WS_WARPS_PER_CTA; ++w) {
+        const unsigned long long t = warp_tot[w];
+        if (w < warp) warp_excl += t;
+        tile_agg += t;
+    }
+
+    // ---- decoupled look-back (warp 0) ----
+    if (warp == 0) {
+        unsigned long long excl = 0ull;
+        if (tile == 0) {
+            if (lane == 0) st_relaxed_u64(P.tile_words, (WS_TILE_INCL << 62) | tile_agg);
+        } else {
+            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_AGG << 62) | tile_agg);
+            int look = tile - 1;
+            while (true) {
+                const int idx = look - lane;
+                unsigned long long word;
+                do {
+                    word = (idx >= 0) ? ld_relaxed_u64(P.tile_words + idx) : (WS_TILE_INCL << 62);
+                } while (__any_sync(0xffffffffu, (word >> 62) == 0ull));
+                const unsigned incl_mask = __ballot_sync(0xffffffffu, (word >> 62) == WS_TILE_INCL);
+                const int first = incl_mask != 0u ? __ffs(incl_mask) - 1 : 31;
+                unsigned long long v = (lane <= first) ? (word & WS_FXS_MASK) : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                excl += v;
+                if (incl_mask != 0u) break;
+                look -= 32;
+            }
+            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_INCL << 62) | (excl + tile_agg));
+        }
+        if (lane == 0) s_prefix = excl;
+    }
+    __syncthreads();
+    const unsigned long long prefix = P.cdf_offset + s_prefix;
+
+    // ---- search: the thread's CDF values are exactly what ws_search_kernel would have read back ----
+    unsigned long long C[WS_SCAN_ITEMS];
+    const unsigned long long thread_excl = prefix + warp_excl + (incl - thread_total);
+#pragma unroll
+    for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? thread_excl + q[k] : 0ull;
+    const int warp_base = tile * WS_CDF_TILE + warp * WS_SCAN_TILE;
+    if (warp_base < n) ws_search_warp_tile<EXACT_FP>(P, X, win_all[warp], lane, warp_base, C, prefix + warp_excl, warp_base != 0);
 }
 
 // Slots of the heavy tiles (see above): every CTA takes an equal slice of each heavy tile's output
@@ -1070,8 +1359,22 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+static bool g_three_pass = false;  // env WSB200_SCAN=3pass: the three-pass form also on one GPU (A/B, tests)
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
     (void)grid;
+    if (!g_three_pass && P.all_tot == nullptr && P.total == nullptr && P.bounds == nullptr) {
+        // single-GPU state: one pass (the caller has zeroed the ticket / heavy-tile counters)
+        const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
+        cudaError_t e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * (size_t)cdf_tiles, s);
+        if (e != cudaSuccess) return e;
+        const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
+        if (exact_fp) ws_scan_search_kernel<true><<<(unsigned)cdf_tiles, WS_SCAN_BLOCK, 0, s>>>(P);
+        else ws_scan_search_kernel<false><<<(unsigned)cdf_tiles, WS_SCAN_BLOCK, 0, s>>>(P);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);
+        return cudaGetLastError();
+    }
     cudaError_t e = ws_launch_cdf(P, s);
     if (e != cudaSuccess) return e;
     return ws_launch_search(P, s);
@@ -1242,6 +1545,12 @@ cudaError_t ws_kernels_init(int device) {
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) return e;
     g_sm_count = prop.multiProcessorCount;
+    {
+        const char* v = getenv("WSB200_SCAN");
+        g_three_pass = v != nullptr && strcmp(v, "3pass") == 0;
+        v = getenv("WSB200_VM");
+        g_vm_interp_only = v != nullptr && strcmp(v, "interp") == 0;
+    }
     // the register file of the fused pass can take most of the SM's shared memory
     e = cudaFuncSetAttribute(ws_vm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;

@@ -733,10 +733,12 @@ static int flush_window(ws_ctx* c) {
     P.rng.replay_e = c->d_replay_e;
     memcpy(P.ops, w.ops.data(), sizeof(WsOp) * w.ops.size());
 
+    const int sl_grid = ws_vm_sl_grid(P);  // straight-line executor (ws_vm_sl.cuh): it sizes its own grid
     TimedEvent te;
     timed_begin(c, KC_VM, te);
     CK(c, ws_launch_vm(P, std::max(1, grid), c->stream));
     timed_end(c, te);
+    if (sl_grid > 0) c->stats.sl_passes++;
     for (auto& pl : swap_after) std::swap(c->cols[pl.col].front[pl.comp], c->cols[pl.col].back[pl.comp]);
     for (auto& pl : w.dirty) {  // written planes are in the current order
         c->cols[pl.col].stale[pl.comp] = 0;
@@ -747,7 +749,7 @@ static int flush_window(ws_ctx* c) {
     if (w.has_acc) {
         c->logw_uniform = false;
         c->partials_valid = true;
-        c->n_partials = std::max(1, grid);
+        c->n_partials = sl_grid > 0 ? sl_grid : std::max(1, grid);
         c->red_valid = false;
     }
     reset_window(c);
