@@ -1,8 +1,10 @@
-"""Generates tests/golden/*.npz from the oracle (oracle/ref.py) on fixed seeds.
+"""Generates tests/golden/*.npz from the oracle (oracle/ref.py) and the oracle's OWN hand-built transformer
+programs (oracle/models.py) on fixed seeds.  Nothing of the product is imported.
 
 The reference is Julia and cannot run here, so these are NOT reference outputs: they freeze the
 oracle's answers (so that a later edit of the oracle or of the product is visible) and give the GPU
 tests size-independent fixtures.  Run:  python tests/golden/make_golden.py
+(oracle/gen_from_reference.jl writes the same files from the real reference where a Julia toolchain exists.)
 """
 import os
 import sys
@@ -13,9 +15,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", ".."))
 sys.path.insert(0, os.path.join(HERE, ".."))
 
-import wsb200 as ws  # noqa: E402  (only the host-side model front-end is used: no device needed)
+from oracle import models as om  # noqa: E402
 from oracle import ref  # noqa: E402
-import models  # noqa: E402
+
+SCHOOLS_Y = [28.0, 8.0, -3.0, 7.0, -1.0, 1.0, 18.0, 12.0]          # examples/eight_schools.jl:19-21
+SCHOOLS_SIGMA = [15.0, 10.0, 16.0, 11.0, 9.0, 11.0, 10.0, 18.0]
 
 
 def resampling_case():
@@ -28,11 +32,10 @@ def resampling_case():
                 ancestors=ref.icdf(w, ref.stratified_us(r)), ancestors_sys=ref.icdf(w, ref.systematic_us(r[0], n)))
 
 
-def run_case(src, args, n, n_normals, n_uniforms, n_expon=0, ess=0.5, seed=1):
+def run_case(root, n, n_normals, n_uniforms, n_expon=0, ess=0.5, seed=1):
     rng = np.random.default_rng(seed)
     normals, uniforms = rng.standard_normal(n_normals), rng.random(n_uniforms)
     expon = rng.standard_exponential(n_expon)
-    root = ws.model(src)(*args)
     st = ref.OracleState(n, ref.Streams(normals, uniforms, expon), ess_perc_min=ess)
     ref.run(root, st)
     out = dict(normals=normals, uniforms=uniforms, exponentials=expon, weights=st.weights,
@@ -47,16 +50,16 @@ def main():
     rng = np.random.default_rng(7)
     obs1 = np.cumsum(rng.standard_normal(12)) * 1.5
     np.savez_compressed(os.path.join(HERE, "ssm1d.npz"), obs=obs1,
-                        **run_case(models.SSM1D, (list(obs1),), 256, 256 * 12, 256 * 12))
+                        **run_case(om.ssm1d(list(obs1)), 256, 256 * 12, 256 * 12))
     obs2 = rng.standard_normal((8, 2)) + np.arange(8)[:, None] * np.array([1.0, 0.0])
     np.savez_compressed(os.path.join(HERE, "ssm2d.npz"), obs=obs2,
-                        **run_case(models.SSM2D, ([o for o in obs2],), 256, 256 * 2 * 8, 256 * 8))
+                        **run_case(om.ssm2d([o for o in obs2]), 256, 256 * 2 * 8, 256 * 8))
     xs = rng.uniform(0, 10, 8)
     ys = 1.0 - 0.5 * xs + 0.5 * rng.standard_normal(8)
     np.savez_compressed(os.path.join(HERE, "linreg.npz"), xs=xs, ys=ys,
-                        **run_case(models.LINREG, (xs, ys), 512, 512 * (2 + 16), 512 * 24))
+                        **run_case(om.linear_regression(xs, ys), 512, 512 * (2 + 16), 512 * 24))
     np.savez_compressed(os.path.join(HERE, "schools.npz"),
-                        **run_case(models.SCHOOLS, (8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA), 512, 512 * 25, 512 * 24, 512))
+                        **run_case(om.eight_schools(8, SCHOOLS_Y, SCHOOLS_SIGMA), 512, 512 * 25, 512 * 24, 512))
     print("golden fixtures written")
 
 

@@ -126,6 +126,7 @@ def test_samplers_replay_equals_oracle_and_philox_passes_ks(name, args, dist):
     hs.store.set_replay(**streams)
     step.apply(hs)
     ost = ref.OracleState(n, ref.Streams(**streams), ess_perc_min=0.0)
+    ost.expr_factory = ws.col
     ref.run(ws.Sequence(step), ost)
     np.testing.assert_allclose(hs.store.getcol("x"), ost.cols["x"], rtol=1e-10, atol=1e-15)  # tan near its poles is ill-conditioned
     assert sst.kstest(hs.store.getcol("x"), dist.cdf).pvalue > 1e-4
@@ -147,6 +148,7 @@ def test_fire_alarm_bayes_net_matches_oracle_and_exact_posterior():
     hs.store.set_replay(uniforms=u)
     root.apply(hs)
     ost = ref.OracleState(n, ref.Streams(uniforms=u), ess_perc_min=0.0)
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     for name in ("fire", "smoke", "lever"):
         got = hs.store.getcol(name)
@@ -183,6 +185,7 @@ def test_damped_oscillator_lowers_with_user_kernel_and_helper_function():
     hs.store.set_replay(**streams)
     root.apply(hs)
     ost = ref.OracleState(n, ref.Streams(**streams), ess_perc_min=0.0)
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     for name in ("A", "ω", "γ", "ϕ", "σ"):
         np.testing.assert_allclose(hs.store.getcol(name), ost.cols[name], rtol=1e-14)

@@ -34,6 +34,7 @@ def test_device_samplers(ws, name, args, dist):
     st.set_replay(**streams)
     ws.run(ws.Sequence(step), st)
     ost = ref.OracleState(n, ref.Streams(**streams))
+    ost.expr_factory = ws.col
     ref.run(ws.Sequence(step), ost)
     np.testing.assert_allclose(st["x"], ost.cols["x"], rtol=1e-9, atol=1e-15)
     sp = ws.SMCState(n, seed=5, device=0)          # Philox
@@ -54,6 +55,7 @@ def test_fire_alarm_end_to_end(ws):
     st.set_replay(uniforms=u)
     ws.run(root, st)
     ost = ref.OracleState(n, ref.Streams(uniforms=u))
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     assert st.resampled and ost.resampled
     bad = 0
@@ -83,6 +85,7 @@ def test_damped_oscillator_with_bounded_multi_target_moves(ws):
     st.set_replay(**streams)
     ws.run(root, st)
     ost = ref.OracleState(n, ref.Streams(**streams))
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     for name in ("A", "ω", "γ", "ϕ", "σ"):
         d = np.abs(st[name] - ost.cols[name]) > 1e-8 * (1 + np.abs(ost.cols[name]))

@@ -27,6 +27,7 @@ def _run_pair(ws, n, T, ess=1.0, **state_kw):
     st = ws.SMCState(n, ess_perc_min=ess, device=0, **state_kw)
     st.set_replay(normals=normals, uniforms=uniforms)
     ost = ref.OracleState(n, ref.Streams(normals, uniforms), ess_perc_min=ess)
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     return root, st, ost
 
@@ -106,6 +107,7 @@ def test_old_planes_in_expressions_moves_and_expectations(ws):
     st.set_replay(normals=normals, uniforms=uniforms)
     ws.run(root, st)
     ost = ref.OracleState(n, ref.Streams(normals, uniforms), ess_perc_min=1.0)
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     for name in ("a", "keep", "x", "b"):
         assert np.sum(np.abs(st[name] - ost.cols[name]) > 1e-9 * (1 + np.abs(ost.cols[name]))) <= 2, name

@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 
 from oracle import cref, ref
+from oracle import models as om
 
 pytestmark = pytest.mark.gpu
 
@@ -181,13 +182,15 @@ def test_store_interface(ws):
     assert st.store.colnames() == ["x", "th"]
 
 
-def _replay_run(ws, root, n, normals=(), uniforms=(), exponentials=(), ess=0.5, resampler="stratified"):
+def _replay_run(ws, root, n, normals=(), uniforms=(), exponentials=(), ess=0.5, resampler="stratified", oracle_root=None):
+    """device: the product's tree (normally `ws.model(source)`); host: `oracle_root`, the oracle's own hand-built
+    program of the same model (oracle/models.py), so the product's @model front-end is part of what is checked"""
     state = ws.SMCState(n, ess_perc_min=ess, device=0, resampler=resampler)
     state.set_replay(normals=normals if len(normals) else None, uniforms=uniforms if len(uniforms) else None,
                      exponentials=exponentials if len(exponentials) else None)
     ws.run(root, state)
     ost = ref.OracleState(n, ref.Streams(normals, uniforms, exponentials), ess_perc_min=ess, resampler=resampler)
-    ref.run(root, ost)
+    ref.run(oracle_root if oracle_root is not None else root, ost)
     return state, ost
 
 
@@ -242,7 +245,7 @@ def test_c1_ssm1d_replay(ws):
         obs.append(x + rng.standard_normal())
         x, v = x + v, v + 0.1 * rng.standard_normal()
     root = ws.model(SSM1D)(obs)
-    state, ost = _replay_run(ws, root, n, normals=rng.standard_normal(n * T), uniforms=rng.random(n * T))
+    state, ost = _replay_run(ws, root, n, normals=rng.standard_normal(n * T), uniforms=rng.random(n * T), oracle_root=om.ssm1d(obs))
     fired = [e for e in ost.log if e["resampled"]]
     assert len(fired) >= 3, "the ESS gate should fire several times in 50 steps"
     assert len(state.store.colnames()) == T + 3
@@ -257,7 +260,7 @@ def test_c2_ssm2d_replay(ws):
     rng = np.random.default_rng(42)
     obs = [rng.standard_normal(2) + np.array([t, 0.0]) for t in range(T)]
     root = ws.model(SSM2D)(obs)
-    state, ost = _replay_run(ws, root, n, normals=rng.standard_normal(2 * n * T), uniforms=rng.random(n * T))
+    state, ost = _replay_run(ws, root, n, normals=rng.standard_normal(2 * n * T), uniforms=rng.random(n * T), oracle_root=om.ssm2d(obs))
     assert sum(e["resampled"] for e in ost.log) >= 3
     _compare_states(state, ost)
     # ancestors of the last firing resample are bit-identical
@@ -426,7 +429,7 @@ def test_multinomial_resampling_inside_run(ws):
     import models
     root = ws.model(models.LGSSM1D)(ys, 0.9, 1.0, 0.5, 1.0)
     state, ost = _replay_run(ws, root, n, normals=rng.standard_normal(n * (T + 1)), uniforms=rng.random(n * T), ess=1.0,
-                             resampler="multinomial")
+                             resampler="multinomial", oracle_root=om.lgssm1d(ys, 0.9, 1.0, 0.5, 1.0))
     assert state.stats()["resamples_done"] == sum(1 for e in ost.log if e["resampled"]) == T
     _compare_states(state, ost, max_bad=3)
     assert abs(ws.log_evidence(state) - ref.log_evidence(ost)) <= REL * abs(ref.log_evidence(ost))

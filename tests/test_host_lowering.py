@@ -42,6 +42,7 @@ def test_models_lower_and_execute_like_the_oracle(src, args, nn, ne):
     hs.store.set_replay(normals=normals, exponentials=expon)
     root.apply(hs)
     ost = ref.OracleState(n, ref.Streams(normals, (), expon), ess_perc_min=0.0)
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     assert hs.store.colnames() == ost.names
     for name in ost.names:
@@ -172,6 +173,7 @@ def test_golden_ssm2d_without_resampling_prefix():
     hs.store.set_replay(normals=g["normals"])
     root.apply(hs)
     ost = ref.OracleState(n, ref.Streams(g["normals"]), ess_perc_min=0.0)
+    ost.expr_factory = ws.col
     ref.run(root, ost)
     np.testing.assert_allclose(hs.store.getcol("x_2"), ost.cols["x_2"], rtol=1e-14)
     np.testing.assert_allclose(hs.store.logw(), ost.weights, rtol=1e-12)

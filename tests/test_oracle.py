@@ -12,6 +12,7 @@ import scipy.stats as sst
 
 import models
 from oracle import cref, ref
+from oracle import models as om
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -140,23 +141,71 @@ def test_weighted_cov_and_transforms():
         np.testing.assert_allclose(ref.log_abs_jacobian(z, lo, hi), num, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["ssm1d", "ssm2d", "linreg", "schools"])
-def test_golden_runs_are_reproduced_by_the_oracle(name):
-    import wsb200 as ws
-    g = np.load(os.path.join(GOLD, name + ".npz"))
-    src, args = {
-        "ssm1d": (models.SSM1D, lambda: (list(g["obs"]),)),
-        "ssm2d": (models.SSM2D, lambda: ([o for o in g["obs"]],)),
-        "linreg": (models.LINREG, lambda: (g["xs"], g["ys"])),
-        "schools": (models.SCHOOLS, lambda: (8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA)),
-    }[name]
+def _golden_case(name, g):
+    """(product @model source + arguments, the oracle's own hand-built program) of a golden fixture"""
+    if name == "ssm1d":
+        return models.SSM1D, (list(g["obs"]),), om.ssm1d(list(g["obs"]))
+    if name == "ssm2d":
+        return models.SSM2D, ([o for o in g["obs"]],), om.ssm2d([o for o in g["obs"]])
+    if name == "linreg":
+        return models.LINREG, (g["xs"], g["ys"]), om.linear_regression(g["xs"], g["ys"])
+    return (models.SCHOOLS, (8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA),
+            om.eight_schools(8, models.SCHOOLS_Y, models.SCHOOLS_SIGMA))
+
+
+def _run_golden(root, g):
     n = g["weights"].shape[0]
     st = ref.OracleState(n, ref.Streams(g["normals"], g["uniforms"], g["exponentials"]), ess_perc_min=0.5)
-    ref.run(ws.model(src)(*args()), st)
+    ref.run(root, st)
+    return st
+
+
+@pytest.mark.parametrize("name", ["ssm1d", "ssm2d", "linreg", "schools"])
+def test_golden_runs_are_reproduced_by_the_oracle(name):
+    """the fixtures are what the oracle's own hand-built programs (oracle/models.py) produce — no product code"""
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    st = _run_golden(_golden_case(name, g)[2], g)
     np.testing.assert_array_equal(st.weights, g["weights"])
     for nm in st.names:
         np.testing.assert_array_equal(st.cols[nm], g["col_" + nm])
     assert int(g["n_resampled"]) >= 1 and st.depth == int(g["depth"])
+
+
+@pytest.mark.parametrize("name", ["ssm1d", "ssm2d", "linreg", "schools"])
+def test_model_frontend_emits_the_hand_built_programs(name):
+    """The product's `@model` front-end (model.py: auto-Resample() after every `~` / `=>`, `x{e}` naming, depth
+    counting, argument order, build-time `if`) against the hand-built programs of SURVEY Appendix A: both trees,
+    interpreted by the oracle on the fixture's streams, must give the fixture bit for bit."""
+    import wsb200 as ws
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    src, args, _ = _golden_case(name, g)
+    st = _run_golden(ws.model(src)(*args), g)
+    np.testing.assert_array_equal(st.weights, g["weights"])
+    assert [("col_" + nm) in g.files for nm in st.names] == [True] * len(st.names)
+    for nm in st.names:
+        np.testing.assert_array_equal(st.cols[nm], g["col_" + nm])
+    assert st.depth == int(g["depth"])
+
+
+def test_model_frontend_hierarchical_and_lgssm_programs():
+    import wsb200 as ws
+    J, n_obs, n = 10, 3, 300
+    groups, _ = models.simulate_hier(J, n_obs)
+    rng = np.random.default_rng(1)
+    N, U, E = rng.standard_normal(n * (2 + J + J * n_obs + 12)), rng.random(n * (2 * J * n_obs + 12)), rng.standard_exponential(2 * n)
+    ys = list(rng.standard_normal(9))
+    for prod, orc in ((ws.model(models.HIER)(J, groups), om.hierarchical_regression(J, groups)),
+                      (ws.model(models.LGSSM1D)(ys, 0.9, 1.0, 0.5, 1.0), om.lgssm1d(ys, 0.9, 1.0, 0.5, 1.0)),
+                      (ws.model(models.SSM2D_FILTER)([np.array([v, -v]) for v in ys]), om.ssm2d_filter([np.array([v, -v]) for v in ys]))):
+        a = ref.OracleState(n, ref.Streams(N, U, E))
+        ref.run(prod, a)
+        b = ref.OracleState(n, ref.Streams(N, U, E))
+        ref.run(orc, b)
+        assert a.names == b.names and a.depth == b.depth
+        for c in a.names:
+            np.testing.assert_array_equal(a.cols[c], b.cols[c])
+        np.testing.assert_array_equal(a.weights, b.weights)
+        assert [e["resampled"] for e in a.log] == [e["resampled"] for e in b.log]
 
 
 def test_golden_resampling_fixture():
