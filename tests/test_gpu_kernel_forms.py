@@ -6,7 +6,7 @@
   against the three-pass form (WSB200_SCAN=3pass), which sharded runs still use.
 
 Both pairs share their arithmetic by construction (the same ws_vm_exec_d / integer prefix sums), so the comparison
-is exact: every particle, every ancestor.
+is exact: every particle, every ancestor (only the grid-shaped (m, S, Q) reduction may differ in the last place).
 """
 import os
 
@@ -77,8 +77,11 @@ def test_straight_line_equals_interpreter(ws, name, src, mk, cols, n, ess):
         assert sa["sl_passes"] >= sa["fused_passes"] - 2, (sa["sl_passes"], sa["fused_passes"])
     for c in cols:
         np.testing.assert_array_equal(a[c], b[c], err_msg=f"{name}: column {c}")
-    np.testing.assert_array_equal(a.weights, b.weights)
-    assert ws.log_evidence(a) == ws.log_evidence(b)
+    # per-particle arithmetic is shared, so the columns agree to the last bit; the (m, S, Q) reduction is combined
+    # per CTA and the two kernels use different grids, so log-sum-exp (hence the weights after a resampling step,
+    # all equal to logsumexp - log N) may differ in the last place
+    np.testing.assert_allclose(a.weights, b.weights, rtol=1e-13, atol=1e-13)
+    assert abs(ws.log_evidence(a) - ws.log_evidence(b)) <= 1e-13 * abs(ws.log_evidence(b))
     assert sa["resamples_done"] == sb["resamples_done"]
 
 
@@ -113,3 +116,27 @@ def test_single_pass_one_hot_and_zero_weights(ws):
     np.testing.assert_array_equal(res[0], res[1])
     assert (res[0] == 123_456).sum() > 0.96 * n
     assert np.all(w[res[0]] > 0)
+
+
+@pytest.mark.parametrize("n,extra", [(50_001, 0), (50_001, 14), (4096, 20), (100_000, 16)])
+def test_integer_slot_grid_small_shift(ws, n, extra):
+    """N > 2^29 particles (eight GPUs) leave fewer than 32 fractional bits per slot and ws_slot_split shifts left;
+    WSB200_FX_EXTRA_BITS shrinks the scale so that this arithmetic runs at test sizes.  Against the big-integer
+    specification, every ancestor, both kernel forms."""
+    import ctypes as C
+    from oracle import ref
+    w = np.exp(2.0 * np.random.default_rng(n + extra).standard_normal(n))
+    w /= w.sum()
+    for kv in ({}, {"WSB200_SCAN": "3pass"}):
+        with env(WSB200_FX_EXTRA_BITS=str(extra), **kv):
+            st = ws.SMCState(n, seed=13, device=0)
+        stream, seed = C.c_uint64(), C.c_uint64()
+        st.store._call("ws_next_philox_stream", C.byref(stream), C.byref(seed))
+        for scheme in ("stratified", "systematic"):
+            a, clamped = ws.resample_indices(w, st, scheme, return_clamped=True)
+            a_ref, clamped_ref = ref.stratified_ancestors_fixed_point(w, seed.value, stream.value, scheme, extra_bits=extra)
+            np.testing.assert_array_equal(a, a_ref)
+            assert clamped == clamped_ref
+            stream.value += 1
+    with env(WSB200_FX_EXTRA_BITS="0"):
+        ws.SMCState(2, device=0)      # back to the default scale for the tests that follow

@@ -90,7 +90,10 @@ struct WsScanParams {
     int32_t* ancestors;        // out, 0-based
     unsigned long long* tile_words;  // [n / WS_CDF_TILE]: tile aggregates, then their exclusive scan
     unsigned long long* cdf_local;   // [n]: tile-local inclusive fixed-point CDF
-    unsigned int* tile_counter;      // unused (kept for layout stability)
+    unsigned int* tile_counter;      // single-pass kernel: the tile ticket, zeroed before launch
+    double fx_scale;                 // fixed-point scale of the CDF and log2 of the units per slot (ws_scan_set_scale)
+    int32_t fx_shift;
+    int32_t pad3;
     unsigned long long* n_clamped;  // += slots beyond the last CDF entry (clamped to the last particle)
     unsigned int* heavy_count;       // number of heavy tiles, zeroed before launch
     int32_t* heavy_F;                // [n/WS_HEAVY_TILE_SLOTS + 2][WS_SCAN_TILE + 2]: F table, fstart, tile id
@@ -118,6 +121,7 @@ cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s);
 cudaError_t ws_launch_reduce_logw(const double* logw, int64_t n, WsLse* partials, int grid, cudaStream_t s);
 cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min,
                                WsReduceOut* out, cudaStream_t s);
+void ws_scan_set_scale(WsScanParams& P);
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s);
 // sharded resampling runs the same passes in two halves with collectives in between
 cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s);     // tile CDF + offsets (+ total)

@@ -574,12 +574,15 @@ cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_
 #define WS_TILE_AGG 1ull
 #define WS_TILE_INCL 2ull
 
-__device__ __forceinline__ unsigned long long ws_w_to_fxs(double w) {
+// Fixed-point weights: q = rint(w * scale), scale <= 2^61 (ws_scan_set_scale): 2^61 for the floating-point slot
+// grid (replayed / caller uniforms), N * 2^S for the integer slot grid of the Philox path, where the slot index of a
+// CDF value is then simply its high bits.
+__device__ __forceinline__ unsigned long long ws_w_to_fxs(double w, double scale) {
     if (!(w > 0.0)) return 0ull;
-    if (w >= 1.0) return 1ull << 61;
-    return __double2ull_rn(w * WS_FXS_SCALE);
+    if (w >= 1.0) return (unsigned long long)scale;
+    return __double2ull_rn(w * scale);
 }
-__device__ __forceinline__ double ws_fxs_to_double(unsigned long long c) { return (double)c * (1.0 / WS_FXS_SCALE); }
+__device__ __forceinline__ double ws_fxs_to_double(unsigned long long c, double scale) { return (double)c / scale; }
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
@@ -650,36 +653,35 @@ __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double 
 #define WS_EXPAND_CHUNK 512    // output slots a warp stages in shared memory per round
 #define WS_DIRECT_MAX 8        // offspring a lane writes itself; larger families are filled by the warp
 #define WS_WARPS_PER_CTA (WS_SCAN_BLOCK / 32)
-#define WS_FXS_FRAC_MASK 0x1FFFFFFFFFFFFFFFull  // 2^61 - 1
 #define WS_RBUF_SLOTS 384      // slot uniforms a warp generates cooperatively per tile (a tile of 256 particles spans ~256 slots)
 
-__device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, int scheme, unsigned long long r0,
+// The integer slot grid (Philox path).  The CDF is an integer C in units of 2^-S slots (scale = N * 2^S), slot k's
+// uniform is u_k = (k + (r_k + 1/2) / 2^32) / N with r_k a 32-bit Philox word (slot k: word k & 3 of block k >> 2;
+// systematic: one word for all slots), so with T = C * 2^(32 - S)
+//      F(C) = #{k : u_k <= C} = hi32(T) + [ r'_k <= lo32(T) ],     r' = r masked to the bits lo32(T) can carry (S < 32)
+// — two shifts, no multiplication.  `sh` = S - 32 (may be negative for N > 2^29), `rmask` = the mask of r'.
+__device__ __forceinline__ void ws_slot_split(unsigned long long C, unsigned int n, int sh, unsigned int& k, unsigned int& frac) {
+    const unsigned long long T = sh >= 0 ? (C >> sh) : (C << (-sh));
+    const unsigned long long k64 = T >> 32;
+    k = (k64 >= (unsigned long long)n) ? n : (unsigned int)k64;
+    frac = (unsigned int)T;
+}
+__device__ __forceinline__ unsigned int ws_slot_word(const ws_u32x4& b, unsigned int k) {
+    const unsigned int j = k & 3u;
+    return j == 0u ? b.x : (j == 1u ? b.y : (j == 2u ? b.z : b.w));
+}
+__device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, int sh, unsigned int rmask, int scheme, unsigned int r0,
                                         uint64_t seed, uint64_t stream) {
-    // T = C * n as a 96-bit number hi:lo
-    const unsigned long long lo = C * (unsigned long long)n;
-    const unsigned long long hi = __umul64hi(C, (unsigned long long)n);
-    const unsigned long long k64 = (hi << 3) | (lo >> 61);
-    if (k64 >= (unsigned long long)n) return (int)n;
-    const unsigned int k = (unsigned int)k64;
-    const unsigned long long frac = lo & WS_FXS_FRAC_MASK;
-    unsigned long long r;
+    unsigned int k, frac;
+    ws_slot_split(C, n, sh, k, frac);
+    if (k >= n) return (int)n;
+    unsigned int r;
     if (scheme == 1) {
         r = r0;
     } else {
-        const ws_u32x4 b = ws_philox4x32_10((uint64_t)(k >> 1), stream, seed);
-        const unsigned long long v = (k & 1u) ? (((unsigned long long)b.z << 32) | b.w) : (((unsigned long long)b.x << 32) | b.y);
-        r = v >> 3;
+        r = ws_slot_word(ws_philox4x32_10((uint64_t)(k >> 2), stream, seed), k);
     }
-    return (int)k + (r <= frac ? 1 : 0);
-}
-
-// (k, frac) = divmod(C * n, 2^61), k clipped to n: the slot whose uniform decides F(C), see ws_F_int
-__device__ __forceinline__ void ws_slot_split(unsigned long long C, unsigned int n, unsigned int& k, unsigned long long& frac) {
-    const unsigned long long lo = C * (unsigned long long)n;
-    const unsigned long long hi = __umul64hi(C, (unsigned long long)n);
-    const unsigned long long k64 = (hi << 3) | (lo >> 61);
-    k = (k64 >= (unsigned long long)n) ? n : (unsigned int)k64;
-    frac = lo & WS_FXS_FRAC_MASK;
+    return (int)k + ((r & rmask) <= frac ? 1 : 0);
 }
 
 #ifndef WS_CDF_MINB
@@ -727,7 +729,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
         unsigned long long q[WS_SCAN_ITEMS];
         if (P.mode == 2) {
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(uniform_w) : 0ull;
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(uniform_w, P.fx_scale) : 0ull;
         } else {
             double l[WS_SCAN_ITEMS];
 #pragma unroll
@@ -741,7 +743,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
                 } else {
                     w = (item0 + k < n) ? l[k] : 0.0;
                 }
-                q[k] = (item0 + k < n) ? ws_w_to_fxs(w) : 0ull;
+                q[k] = (item0 + k < n) ? ws_w_to_fxs(w, P.fx_scale) : 0ull;
             }
         }
 #pragma unroll
@@ -847,25 +849,27 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
     su.replay = P.replay_u;
     su.r0 = 0.0;
     su.cached_blk = -1;
-    unsigned long long r0_int = 0ull;
+    unsigned int r0_int = 0u;
     if (P.scheme == 1 && P.sorted_u == nullptr) {
         if (P.replay_u != nullptr) {
             su.r0 = P.replay_u[0];
         } else {
             ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
             su.r0 = ws_u01(r.x, r.y);
-            r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
+            r0_int = r.x;
         }
     }
+    const int sh = P.fx_shift - 32;
+    const unsigned int rmask = sh >= 0 ? 0xFFFFFFFFu : ~((1u << (-sh)) - 1u);
     const unsigned long long cdf_offset = ws_cdf_offset(P);
     const unsigned long long lo = cdf_offset, hi = cdf_offset + *P.total;
     int fs, fe;
     if (EXACT_FP) {
-        fs = (int)ws_F(P, ws_fxs_to_double(lo), inv_n, su);
-        fe = (int)ws_F(P, ws_fxs_to_double(hi), inv_n, su);
+        fs = (int)ws_F(P, ws_fxs_to_double(lo, P.fx_scale), inv_n, su);
+        fe = (int)ws_F(P, ws_fxs_to_double(hi, P.fx_scale), inv_n, su);
     } else {
-        fs = ws_F_int(lo, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
-        fe = ws_F_int(hi, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+        fs = ws_F_int(lo, (unsigned int)ns, sh, rmask, su.scheme, r0_int, P.seed, P.stream);
+        fe = ws_F_int(hi, (unsigned int)ns, sh, rmask, su.scheme, r0_int, P.seed, P.stream);
     }
     if (cdf_offset == 0ull) fs = 0;  // F(C_0) is 0 by definition for the very first particle
     if (P.last_rank) fe = ns;
@@ -876,9 +880,9 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
 // What every warp of a search needs besides the CDF: the slot-uniform provider and the slot grid.
 struct WsSearchCtx {
     SlotUniform su;
-    unsigned long long r0_int;
-    int n, ns, slot_base;
-    double inv_n;
+    unsigned int r0_int, rmask;
+    int n, ns, slot_base, sh;
+    double inv_n, fx_scale;
 };
 __device__ __forceinline__ void ws_search_setup(const WsScanParams& P, WsSearchCtx& X) {
     X.n = (int)P.n;          // local particles
@@ -891,14 +895,17 @@ __device__ __forceinline__ void ws_search_setup(const WsScanParams& P, WsSearchC
     X.su.replay = P.replay_u;
     X.su.r0 = 0.0;
     X.su.cached_blk = -1;
-    X.r0_int = 0ull;
+    X.r0_int = 0u;
+    X.sh = P.fx_shift - 32;
+    X.rmask = X.sh >= 0 ? 0xFFFFFFFFu : ~((1u << (-X.sh)) - 1u);
+    X.fx_scale = P.fx_scale;
     if (P.scheme == 1 && P.sorted_u == nullptr) {
         if (P.replay_u != nullptr) {
             X.su.r0 = P.replay_u[0];
         } else {
             ws_u32x4 r = ws_philox4x32_10(0ull, P.stream, P.seed);
             X.su.r0 = ws_u01(r.x, r.y);
-            X.r0_int = (((unsigned long long)r.x << 32) | r.y) >> 3;
+            X.r0_int = r.x;
         }
     }
 }
@@ -913,9 +920,10 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
                                                     const unsigned long long (&C)[WS_SCAN_ITEMS], const unsigned long long Cp,
                                                     const bool has_prev) {
     int32_t* const out_s = reinterpret_cast<int32_t*>(rbuf);
+    unsigned int* const rbuf32 = reinterpret_cast<unsigned int*>(rbuf);
     SlotUniform& su = X.su;
-    const unsigned long long r0_int = X.r0_int;
-    const int n = X.n, ns = X.ns, slot_base = X.slot_base;
+    const unsigned int r0_int = X.r0_int, rmask = X.rmask;
+    const int n = X.n, ns = X.ns, slot_base = X.slot_base, sh = X.sh;
     const double inv_n = X.inv_n;
     const int item0 = tile_base + lane * WS_SCAN_ITEMS;
     // ---- per-particle F(C_m) -----------------------------------------------------------------------
@@ -926,14 +934,14 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
     bool coop = false;
     if (!EXACT_FP && su.scheme == 0) {
         // Philox-stratified: neighbouring particles ask for neighbouring slots, and one Philox block
-        // serves two slots, so the warp generates the uniforms of the tile's whole slot range once
-        // (half a Philox block per particle instead of one) and every lane looks its slots up.
+        // serves four slots, so the warp generates the uniforms of the tile's whole slot range once
+        // (a quarter of a Philox block per particle instead of one) and every lane looks its slots up.
         unsigned int kk[WS_SCAN_ITEMS];
-        unsigned long long fr[WS_SCAN_ITEMS];
+        unsigned int fr[WS_SCAN_ITEMS];
         unsigned int kmax = 0u, kmin = 0xFFFFFFFFu;
 #pragma unroll
         for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-            ws_slot_split(C[k], (unsigned int)ns, kk[k], fr[k]);
+            ws_slot_split(C[k], (unsigned int)ns, sh, kk[k], fr[k]);
             if (item0 + k >= n) kk[k] = 0xFFFFFFFFu;  // beyond the shard: patched below
             if (kk[k] < (unsigned int)ns) {
                 kmax = max(kmax, kk[k]);
@@ -941,9 +949,9 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
             }
         }
         unsigned int kp = 0u;
-        unsigned long long frp = 0ull;
+        unsigned int frp = 0u;
         if (lane == 0 && has_prev) {
-            ws_slot_split(Cp, (unsigned int)ns, kp, frp);
+            ws_slot_split(Cp, (unsigned int)ns, sh, kp, frp);
             if (kp < (unsigned int)ns) {
                 kmax = max(kmax, kp);
                 kmin = min(kmin, kp);
@@ -951,15 +959,14 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
         }
         kmax = __reduce_max_sync(0xffffffffu, kmax);
         kmin = __reduce_min_sync(0xffffffffu, kmin);
-        const unsigned int blk0 = kmin >> 1;
-        coop = (kmin == 0xFFFFFFFFu) || ((kmax >> 1) - blk0 < (unsigned int)(WS_RBUF_SLOTS / 2));
+        const unsigned int blk0 = kmin >> 2;
+        coop = (kmin == 0xFFFFFFFFu) || ((kmax >> 2) - blk0 < (unsigned int)(WS_RBUF_SLOTS / 2));
         if (coop) {
             if (kmin != 0xFFFFFFFFu) {
-                const unsigned int nblk = (kmax >> 1) - blk0 + 1u;
+                const unsigned int nblk = (kmax >> 2) - blk0 + 1u;
                 for (unsigned int b = lane; b < nblk; b += 32u) {
                     const ws_u32x4 r = ws_philox4x32_10((uint64_t)(blk0 + b), P.stream, P.seed);
-                    rbuf[2u * b] = (((unsigned long long)r.x << 32) | r.y) >> 3;
-                    rbuf[2u * b + 1u] = (((unsigned long long)r.z << 32) | r.w) >> 3;
+                    reinterpret_cast<uint4*>(rbuf32)[b] = make_uint4(r.x & rmask, r.y & rmask, r.z & rmask, r.w & rmask);
                 }
             }
             __syncwarp();
@@ -968,7 +975,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
                 int fk;
                 if (kk[k] == 0xFFFFFFFFu) fk = -1;
                 else if (kk[k] >= (unsigned int)ns) fk = ns;
-                else fk = (int)kk[k] + (rbuf[kk[k] - 2u * blk0] <= fr[k] ? 1 : 0);
+                else fk = (int)kk[k] + (rbuf32[kk[k] - 4u * blk0] <= fr[k] ? 1 : 0);
                 if (item0 + k == n - 1 && P.last_rank) {
                     if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
                     fk = ns;
@@ -976,7 +983,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
                 f[k] = fk;
             }
             if (lane == 0 && has_prev)
-                fstart = (kp >= (unsigned int)ns) ? ns : (int)kp + (rbuf[kp - 2u * blk0] <= frp ? 1 : 0);
+                fstart = (kp >= (unsigned int)ns) ? ns : (int)kp + (rbuf32[kp - 4u * blk0] <= frp ? 1 : 0);
             __syncwarp();  // the window is reused for the offspring below
         }
     }
@@ -988,8 +995,8 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
             if (gi >= n) {
                 fk = -1;  // patched below
             } else {
-                if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k]), inv_n, su);
-                else fk = ws_F_int(C[k], (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+                if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k], X.fx_scale), inv_n, su);
+                else fk = ws_F_int(C[k], (unsigned int)ns, sh, rmask, su.scheme, r0_int, P.seed, P.stream);
                 if (gi == n - 1 && P.last_rank) {
                     if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
                     fk = ns;  // leftover slots go to the last particle (the reference would throw BoundsError)
@@ -998,8 +1005,8 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
             f[k] = fk;
         }
         if (lane == 0 && has_prev) {
-            if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp), inv_n, su);
-            else fstart = ws_F_int(Cp, (unsigned int)ns, su.scheme, r0_int, P.seed, P.stream);
+            if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp, X.fx_scale), inv_n, su);
+            else fstart = ws_F_int(Cp, (unsigned int)ns, sh, rmask, su.scheme, r0_int, P.seed, P.stream);
         }
     }
     // items beyond the shard produce nothing: they repeat the F of the shard's last particle
@@ -1196,6 +1203,8 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
     __shared__ __align__(16) unsigned long long win_all[WS_WARPS_PER_CTA][WS_RBUF_SLOTS];
     __shared__ unsigned long long warp_tot[WS_WARPS_PER_CTA];
     __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long lb_sum[WS_WARPS_PER_CTA];
+    __shared__ int lb_found[WS_WARPS_PER_CTA];
     __shared__ int s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
@@ -1215,7 +1224,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
     // ---- fixed-point weights of the thread's 8 consecutive particles, inclusive sums ----
     unsigned long long q[WS_SCAN_ITEMS];
     if (P.mode == 2) {
-        const unsigned long long qu = ws_w_to_fxs(1.0 / (double)P.n_slots);
+        const unsigned long long qu = ws_w_to_fxs(1.0 / (double)P.n_slots, P.fx_scale);
 #pragma unroll
         for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? qu : 0ull;
     } else {
@@ -1237,7 +1246,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
             double w;
             if (P.mode == 0) w = ws_div_pos(ws_exp_nonpos(l[k] - m), Sden, rS);
             else w = (item0 + k < n) ? l[k] : 0.0;
-            q[k] = (item0 + k < n) ? ws_w_to_fxs(w) : 0ull;
+            q[k] = (item0 + k < n) ? ws_w_to_fxs(w, P.fx_scale) : 0ull;
         }
     }
 #pragma unroll
@@ -1259,32 +1268,50 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
         tile_agg += t;
     }
 
-    // ---- decoupled look-back (warp 0) ----
-    if (warp == 0) {
-        unsigned long long excl = 0ull;
-        if (tile == 0) {
-            if (lane == 0) st_relaxed_u64(P.tile_words, (WS_TILE_INCL << 62) | tile_agg);
-        } else {
-            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_AGG << 62) | tile_agg);
-            int look = tile - 1;
-            while (true) {
-                const int idx = look - lane;
-                unsigned long long word;
-                do {
-                    word = (idx >= 0) ? ld_relaxed_u64(P.tile_words + idx) : (WS_TILE_INCL << 62);
-                } while (__any_sync(0xffffffffu, (word >> 62) == 0ull));
-                const unsigned incl_mask = __ballot_sync(0xffffffffu, (word >> 62) == WS_TILE_INCL);
-                const int first = incl_mask != 0u ? __ffs(incl_mask) - 1 : 31;
-                unsigned long long v = (lane <= first) ? (word & WS_FXS_MASK) : 0ull;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                excl += v;
-                if (incl_mask != 0u) break;
-                look -= 32;
-            }
-            if (lane == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_INCL << 62) | (excl + tile_agg));
+    // ---- decoupled look-back, by the whole CTA: thread t inspects predecessor tile - 1 - t, so one round covers
+    // 256 predecessors (with one warp, a tile walked back through up to ~450 tiles in flight, 32 per ~1 us round,
+    // while the other seven warps waited at the barrier) ----
+    if (tile == 0) {
+        if (threadIdx.x == 0) {
+            st_relaxed_u64(P.tile_words, (WS_TILE_INCL << 62) | tile_agg);
+            s_prefix = 0ull;
         }
-        if (lane == 0) s_prefix = excl;
+    } else {
+        if (threadIdx.x == 0) st_relaxed_u64(P.tile_words + tile, (WS_TILE_AGG << 62) | tile_agg);
+        unsigned long long excl = 0ull;  // CTA-uniform
+        int look = tile - 1;
+        while (true) {
+            const int idx = look - (int)threadIdx.x;
+            unsigned long long word;
+            do {
+                word = (idx >= 0) ? ld_relaxed_u64(P.tile_words + idx) : (WS_TILE_INCL << 62);
+            } while (__any_sync(0xffffffffu, (word >> 62) == 0ull));
+            const unsigned incl_mask = __ballot_sync(0xffffffffu, (word >> 62) == WS_TILE_INCL);
+            const int first = incl_mask != 0u ? __ffs(incl_mask) - 1 : 31;
+            unsigned long long v = (lane <= first) ? (word & WS_FXS_MASK) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            __syncthreads();  // lb_* of the previous round (and warp_tot) have been consumed
+            if (lane == 0) {
+                lb_sum[warp] = v;
+                lb_found[warp] = incl_mask != 0u ? 1 : 0;
+            }
+            __syncthreads();
+            bool found = false;
+#pragma unroll
+            for (int w = 0; w < WS_WARPS_PER_CTA; ++w) {
+                if (!found) {
+                    excl += lb_sum[w];
+                    found = lb_found[w] != 0;
+                }
+            }
+            if (found) break;
+            look -= WS_SCAN_BLOCK;
+        }
+        if (threadIdx.x == 0) {
+            st_relaxed_u64(P.tile_words + tile, (WS_TILE_INCL << 62) | (excl + tile_agg));
+            s_prefix = excl;
+        }
     }
     __syncthreads();
     const unsigned long long prefix = P.cdf_offset + s_prefix;
@@ -1325,6 +1352,23 @@ __global__ void __launch_bounds__(256) ws_expand_heavy_kernel(const __grid_const
             P.ancestors[j - P.slot_base] = (int32_t)(tile_base + lo);
         }
     }
+}
+
+// env WSB200_FX_EXTRA_BITS (tests): shrink the fixed-point scale by that many bits, so that the S < 32 arithmetic of
+// ws_slot_split (normally only reached by N > 2^29 particles) can be exercised at small N
+static int g_fx_extra_bits = 0;
+// scale of the fixed-point CDF (see ws_w_to_fxs / ws_slot_split); call after n_slots, replay_u, sorted_u are set
+void ws_scan_set_scale(WsScanParams& P) {
+    const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
+    int shift = 61;
+    if (!exact_fp) {
+        int bits = 0;
+        while (((int64_t)1 << bits) < P.n_slots) ++bits;
+        shift = 61 - bits - g_fx_extra_bits;
+        if (shift < 24) shift = 24;
+    }
+    P.fx_shift = shift;
+    P.fx_scale = exact_fp ? 2305843009213693952.0 : ldexp((double)P.n_slots, shift);
 }
 
 cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s) {
@@ -1548,6 +1592,8 @@ cudaError_t ws_kernels_init(int device) {
     {
         const char* v = getenv("WSB200_SCAN");
         g_three_pass = v != nullptr && strcmp(v, "3pass") == 0;
+        v = getenv("WSB200_FX_EXTRA_BITS");
+        g_fx_extra_bits = v != nullptr ? atoi(v) : 0;
         v = getenv("WSB200_VM");
         g_vm_interp_only = v != nullptr && strcmp(v, "interp") == 0;
     }

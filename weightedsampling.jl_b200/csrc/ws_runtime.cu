@@ -1542,6 +1542,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     S.n_clamped = d_clamped;
     S.heavy_count = c->d_tile_counter + 1;
     S.heavy_F = c->d_heavy_F;
+    ws_scan_set_scale(S);
     TimedEvent te;
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_scan_search(S, 0, c->stream));
@@ -1702,6 +1703,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
     S.seed = c->seed;
     S.stream = stream_id;
     S.replay_u = d_ru;
+    ws_scan_set_scale(S);
     S.ancestors = nullptr;
     S.tile_words = c->d_tile_words;
     S.cdf_local = c->d_cdf_local;
