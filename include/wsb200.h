@@ -205,6 +205,15 @@ typedef struct ws_resample_info {
     int64_t n_clamped;  /* slots whose uniform exceeded the last CDF entry (reference would throw BoundsError) */
 } ws_resample_info;
 int ws_resample(ws_ctx* ctx, ws_resample_info* info);
+/* The same step without waiting for its outcome: what depends on the decision (CDF, ancestor search, the weight
+ * reset) runs on the device behind the decision flag, the host only queues it.  `state.resampled` (ws_get_flags with
+ * a non-NULL `resampled`), ws_get_stats, ws_last_resample and every call that reads the log-weights wait for the
+ * pending steps first; a model without `if resampled` never does.  Falls back to ws_resample(ctx, NULL) for replayed
+ * uniforms, sharded states, multinomial resampling and eager gather.  Results are identical to ws_resample's.
+ * (transformers.jl:474-498; env WSB200_ASYNC_RESAMPLE=0 disables it) */
+int ws_resample_async(ws_ctx* ctx);
+/* outcome of the most recent ws_resample / ws_resample_async (waits for it if it is still pending) */
+int ws_last_resample(ws_ctx* ctx, ws_resample_info* info);
 
 /* ---- resampling numerics on their own (src/resampling.jl) -------------------------------- */
 /* exp_norm(state.weights) -> host (src/resampling.jl:72-77). */

@@ -2,8 +2,8 @@
 
 * the fused elementwise window: straight-line executors (csrc/ws_vm_sl.cuh: compile-time signatures, register file
   in registers) against the interpreter (ws_vm_kernel), selected with WSB200_VM=interp at context creation;
-* CDF + ancestor search: the single-pass kernel (ticketed tiles + decoupled look-back, ws_scan_search_kernel)
-  against the three-pass form (WSB200_SCAN=3pass), which sharded runs still use.
+* CDF + ancestor search: the single-pass kernel (ticketed tiles + decoupled look-back, ws_scan_search_kernel,
+  WSB200_SCAN=1pass) against the three-pass form (the default, and what sharded runs use).
 
 Both pairs share their arithmetic by construction (the same ws_vm_exec_d / integer prefix sums), so the comparison
 is exact: every particle, every ancestor (only the grid-shaped (m, S, Q) reduction may differ in the last place).
@@ -92,7 +92,7 @@ def test_single_pass_scan_search_equals_three_pass(ws, n, s, scheme):
     w = np.exp(s * np.random.default_rng(n).standard_normal(n))
     w /= w.sum()
     out = []
-    for kv in ({}, {"WSB200_SCAN": "3pass"}):
+    for kv in ({}, {"WSB200_SCAN": "1pass"}):
         with env(**kv):
             st = ws.SMCState(max(n, 2), seed=5, device=0)
         out.append(ws.resample_indices(w, st, scheme))
@@ -109,7 +109,7 @@ def test_single_pass_one_hot_and_zero_weights(ws):
     w[::7] += 0.03 / len(w[::7])
     w /= w.sum()
     res = []
-    for kv in ({}, {"WSB200_SCAN": "3pass"}):
+    for kv in ({}, {"WSB200_SCAN": "1pass"}):
         with env(**kv):
             st = ws.SMCState(n, seed=9, device=0)
         res.append(ws.resample_indices(w, st, "stratified"))
@@ -127,7 +127,7 @@ def test_integer_slot_grid_small_shift(ws, n, extra):
     from oracle import ref
     w = np.exp(2.0 * np.random.default_rng(n + extra).standard_normal(n))
     w /= w.sum()
-    for kv in ({}, {"WSB200_SCAN": "3pass"}):
+    for kv in ({}, {"WSB200_SCAN": "1pass"}):
         with env(WSB200_FX_EXTRA_BITS=str(extra), **kv):
             st = ws.SMCState(n, seed=13, device=0)
         stream, seed = C.c_uint64(), C.c_uint64()
@@ -140,3 +140,60 @@ def test_integer_slot_grid_small_shift(ws, n, extra):
             stream.value += 1
     with env(WSB200_FX_EXTRA_BITS="0"):
         ws.SMCState(2, device=0)      # back to the default scale for the tests that follow
+
+
+# ------------------------------------------------------------------------------------------------
+# Resample.apply! queued without waiting for its outcome (ws_resample_async) == the synchronous state machine
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,src,mk,cols", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("ess", [0.3, 0.5, 1.0])
+def test_async_resample_equals_sync(ws, name, src, mk, cols, ess):
+    """transformers.jl:474-498 with the decision left on the device: gated scan / search, identity ancestors when
+    the step does not fire, log-weight base chosen by the device flag.  Every particle, the weights, the evidence and
+    the counters must equal the run in which the host waits for every decision (WSB200_ASYNC_RESAMPLE=0)."""
+    args = mk(np.random.default_rng(5))
+    n = 20_011
+    a = _run(ws, src, args, n, seed=33, ess=ess)
+    b = _run(ws, src, args, n, seed=33, ess=ess, WSB200_ASYNC_RESAMPLE="0")
+    for c in cols:
+        np.testing.assert_array_equal(a[c], b[c], err_msg=f"{name}: column {c}")
+    np.testing.assert_array_equal(a.weights, b.weights)
+    assert ws.log_evidence(a) == ws.log_evidence(b)
+    sa, sb = a.stats(), b.stats()
+    for k in ("resamples_fired", "resamples_done", "moves_run", "fused_passes"):
+        assert sa[k] == sb[k], k
+    assert a.resampled == b.resampled
+    if ess == 0.3 and name != "linreg":
+        assert sa["resamples_done"] < sa["resamples_fired"]        # some steps did not fire: the identity path ran
+
+
+def test_async_resample_state_machine(ws):
+    """the flags and `last` of a queued step; a no-op step leaves `resampled` untouched; untouched planes of a
+    step that did not fire stay correct (they are read through identity ancestors)."""
+    n = 5000
+    st = ws.SMCState(n, ess_perc_min=0.5, seed=2, device=0)
+    st.store.setcol("x", np.arange(n, dtype=float))
+    st.store.setcol("keep", np.arange(n, dtype=float) * 2.0)
+    r = ws.Resample()
+    st.resampled = True
+    r.apply(st)
+    assert r.last.fired == 0 and st.resampled is True
+    ws.Observe(0.0, "Normal", (ws.col("x") * 1e-9, 1.0)).apply(st)
+    r.apply(st)                                   # queued; ESS is ~1: does not fire
+    ws.Observe(0.0, "Normal", (ws.col("x") * 1e-9, 1.0)).apply(st)   # next weighting pass runs behind the pending step
+    r.apply(st)
+    assert r.last.fired == 1 and r.last.resampled == 0 and r.last.ess_perc > 0.99
+    assert st.resampled is False and st.stats()["resamples_done"] == 0 and st.stats()["resamples_fired"] == 2
+    np.testing.assert_array_equal(st["keep"], np.arange(n) * 2.0)
+    lw_expected = 2 * (-0.5 * (np.arange(n) * 1e-9) ** 2 - 0.5 * np.log(2 * np.pi))
+    np.testing.assert_allclose(st.weights, lw_expected, rtol=1e-12)
+    ws.Observe(0.0, "Normal", (ws.col("x"), 40.0)).apply(st)
+    le = ws.log_evidence(st)
+    r.apply(st)                                   # fires
+    ws.Assign("y", ws.col("x") + 1.0).apply(st)   # a pass without a weight term behind a pending step
+    assert st.resampled is True and r.last.resampled == 1 and st.stats()["resamples_done"] == 1
+    np.testing.assert_allclose(st.weights, np.full(n, le), rtol=1e-12)
+    x = st["x"]
+    assert np.all(np.diff(x) >= 0) and len(np.unique(x)) < n
+    np.testing.assert_array_equal(st["keep"], 2.0 * x)
+    np.testing.assert_array_equal(st["y"], x + 1.0)

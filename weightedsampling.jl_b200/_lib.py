@@ -125,6 +125,8 @@ SIGNATURES = {
     "ws_sample_importance_normal": (C.c_int, [_ctx, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double,
                                               C.c_double]),
     "ws_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),
+    "ws_resample_async": (C.c_int, [_ctx]),
+    "ws_last_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),
     "ws_exp_norm": (C.c_int, [_ctx, C.c_void_p]),
     "ws_log_evidence": (C.c_int, [_ctx, _dp, _dp]),
     "ws_exp_norm_host": (C.c_int, [_ctx, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -219,13 +219,19 @@ class SMCState:
     def resampled(self, v): self.store._call("ws_set_flags", int(bool(v)), int(self._flags()[1]))
 
     @property
-    def weights_changed(self): return self._flags()[1]
+    def weights_changed(self):
+        w = C.c_int()
+        self.store._call("ws_get_flags", None, C.byref(w), None)   # (asking for `resampled` would wait for pending Resample steps)
+        return bool(w.value)
 
     @weights_changed.setter
     def weights_changed(self, v): self.store._call("ws_set_flags", int(self._flags()[0]), int(bool(v)))
 
     @property
-    def depth(self): return self._flags()[2]
+    def depth(self):
+        d = C.c_int64()
+        self.store._call("ws_get_flags", None, None, C.byref(d))
+        return d.value
 
     @depth.setter
     def depth(self, v):
@@ -762,12 +768,21 @@ class Resample(ParticleTransformer):
     """transformers.jl:461-507 — the whole state machine runs inside ``ws_resample``."""
 
     def __init__(self):
-        self.last = None
+        self._store = None
 
     def apply(self, state):
+        # queued, not awaited: the decision stays on the device until somebody asks (`state.resampled`, `.last`, ...)
+        state.store._call("ws_resample_async")
+        self._store = state.store
+
+    @property
+    def last(self):
+        """outcome of the most recent application (fired, resampled, ess_perc, log_mean_w); waits for it if needed"""
+        if self._store is None:
+            return None
         info = L.ws_resample_info()
-        state.store._call("ws_resample", C.byref(info))
-        self.last = info
+        self._store._call("ws_last_resample", C.byref(info))
+        return info
 
     def score(self, state, ctx):
         return None

@@ -54,7 +54,9 @@ struct WsVmProgram {
     const int32_t* ancestors;
     uint32_t load_gather;
     // log-weight accumulation of the window's Observe / Weight / weighter terms
-    int32_t logw_mode;  // 0: window has no weight term; 1: logw[i] += acc; 2: logw[i] = logw_base + acc
+    int32_t logw_mode;  // 0: window has no weight term; 1: logw[i] += acc; 2: logw[i] = logw_base + acc;
+                        // 3: decided by red->do_resample (a Resample step still pending on the host): 2 with
+                        //    logw_base = red->log_mean_w if it fired, else 1 — and the gathered loads read straight
     double* logw;
     double logw_base;
     WsLse* partials;  // per-CTA (m,S,Q) of the NEW log-weights (nullptr: skip)
@@ -130,6 +132,7 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s);  // F(C_m) 
 cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_t n_global, double ess_perc_min,
                                       WsReduceOut* out, cudaStream_t s);
 cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s);
+cudaError_t ws_launch_identity_unless_fired(const WsReduceOut* red, int32_t* anc, int64_t n, int grid, cudaStream_t s);
 cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStream_t s);
 cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,
                                cudaStream_t s);

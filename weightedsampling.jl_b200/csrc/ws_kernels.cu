@@ -154,7 +154,11 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
     constexpr int TILE = WS_VM_BLOCK * WS_VM_P;
     const int n = (int)P.n;
     const int n_tiles = (n + TILE - 1) / TILE;
-    const bool any_gather = P.load_gather != 0u;
+    // logw_mode 3: the Resample step in front of this pass is still pending on the host; its flag decides
+    const bool fired = (P.logw_mode != 3) || P.red->do_resample != 0;
+    const int lmode = (P.logw_mode == 3) ? (fired ? 2 : 1) : P.logw_mode;
+    const double lbase = (P.logw_mode == 3) ? P.red->log_mean_w : P.logw_base;
+    const bool any_gather = P.load_gather != 0u && fired;  // not fired: the ancestors are the identity
 
     // clamped index of the thread's j-th particle in a tile (always a valid address)
     auto tile_index = [&](int tile, int j) -> int {
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
     // issue the staged loads of `tile` (source rows anc[] for gathered planes)
     auto issue_stage = [&](int tile, const int (&anc)[WS_VM_P]) {
         for (int k = 0; k < P.n_loads; ++k) {
-            const bool g = (P.load_gather >> k) & 1u;
+            const bool g = any_gather && ((P.load_gather >> k) & 1u);
             const double* __restrict__ ptr = P.load_ptr[k];
             double* dst = stage + k * RS;
 #pragma unroll
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     if (k0 + k < P.n_loads) {
-                        const bool g = (P.load_gather >> (k0 + k)) & 1u;
+                        const bool g = any_gather && ((P.load_gather >> (k0 + k)) & 1u);
                         const double* __restrict__ ptr = P.load_ptr[k0 + k];
 #pragma unroll
                         for (int j = 0; j < WS_VM_P; ++j) tmp[k][j] = __ldg(ptr + (unsigned)(g ? src[j] : idx[j]));
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
         double lw_old[WS_VM_P];
 #pragma unroll
         for (int j = 0; j < WS_VM_P; ++j) lw_old[j] = 0.0;
-        if (P.logw_mode == 1 || P.n_expect > 0) {
+        if (lmode == 1 || P.n_expect > 0) {
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) lw_old[j] = P.logw[(unsigned)idx[j]];
         }
@@ -274,7 +278,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
             double lw[WS_VM_P];
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) {
-                lw[j] = (P.logw_mode == 1 ? lw_old[j] : P.logw_base) + acc[j];
+                lw[j] = (lmode == 1 ? lw_old[j] : lbase) + acc[j];
                 if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
             }
             lse_push_many<WS_VM_P>(part, lw, live);
@@ -343,7 +347,11 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
     part.Q = 0.0;
     const int n = (int)P.n;
     const int n_tiles = (n + TILE - 1) / TILE;
-    const bool any_gather = P.load_gather != 0u;
+    // logw_mode 3: the Resample step in front of this pass is still pending on the host; its flag decides
+    const bool fired = (P.logw_mode != 3) || P.red->do_resample != 0;
+    const int lmode = (P.logw_mode == 3) ? (fired ? 2 : 1) : P.logw_mode;
+    const double lbase = (P.logw_mode == 3) ? P.red->log_mean_w : P.logw_base;
+    const bool any_gather = P.load_gather != 0u && fired;  // not fired: the ancestors are the identity
 
     auto tile_index = [&](int tile, int j) -> int {
         const int i = tile * TILE + (int)threadIdx.x + j * WS_VM_BLOCK;
@@ -352,7 +360,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
     auto issue_stage = [&](int tile, const int (&anc)[PP]) {
 #pragma unroll
         for (int k = 0; k < NL; ++k) {
-            const bool g = (P.load_gather >> k) & 1u;
+            const bool g = any_gather && ((P.load_gather >> k) & 1u);
             const double* __restrict__ ptr = P.load_ptr[k];
 #pragma unroll
             for (int j = 0; j < PP; ++j)
@@ -400,7 +408,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
         double lw_old[PP];
 #pragma unroll
         for (int j = 0; j < PP; ++j) lw_old[j] = 0.0;
-        if (P.logw_mode == 1) {
+        if (lmode == 1) {
 #pragma unroll
             for (int j = 0; j < PP; ++j) lw_old[j] = P.logw[(unsigned)idx[j]];
         }
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
             double lw[PP];
 #pragma unroll
             for (int j = 0; j < PP; ++j) {
-                lw[j] = (P.logw_mode == 1 ? lw_old[j] : P.logw_base) + acc[j];
+                lw[j] = (lmode == 1 ? lw_old[j] : lbase) + acc[j];
                 if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
             }
             lse_push_many<PP>(part, lw, live);
@@ -1403,7 +1411,9 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-static bool g_three_pass = false;  // env WSB200_SCAN=3pass: the three-pass form also on one GPU (A/B, tests)
+// The single-pass kernel saves the 16 B round trip through cdf_local but, as measured on B200 (profiles/r2b_*), loses
+// more than that waiting in the look-back, so the three-pass form stays the default; env WSB200_SCAN=1pass selects it.
+static bool g_three_pass = true;
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
     (void)grid;
     if (!g_three_pass && P.all_tot == nullptr && P.total == nullptr && P.bounds == nullptr) {
@@ -1453,6 +1463,17 @@ cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s) 
 // ------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------
+// ancestors of a Resample step that turned out not to fire: the identity (see ws_resample_async)
+__global__ void ws_identity_unless_fired_kernel(const WsReduceOut* __restrict__ red, int32_t* __restrict__ anc, int64_t n) {
+    if (red->do_resample != 0) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) anc[i] = (int32_t)i;
+}
+cudaError_t ws_launch_identity_unless_fired(const WsReduceOut* red, int32_t* anc, int64_t n, int grid, cudaStream_t s) {
+    ws_identity_unless_fired_kernel<<<grid, 256, 0, s>>>(red, anc, n);
+    return cudaGetLastError();
+}
+
 __global__ void ws_fill_kernel(double* __restrict__ dst, double v, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
@@ -1591,7 +1612,7 @@ cudaError_t ws_kernels_init(int device) {
     g_sm_count = prop.multiProcessorCount;
     {
         const char* v = getenv("WSB200_SCAN");
-        g_three_pass = v != nullptr && strcmp(v, "3pass") == 0;
+        g_three_pass = !(v != nullptr && strcmp(v, "1pass") == 0);
         v = getenv("WSB200_FX_EXTRA_BITS");
         g_fx_extra_bits = v != nullptr ? atoi(v) : 0;
         v = getenv("WSB200_VM");

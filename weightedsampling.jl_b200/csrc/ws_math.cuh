@@ -137,24 +137,121 @@ WS_HD double ws_rsqrt_seed(double x) {
 #endif
 }
 
+// Polynomial coefficients and reduction constants of the routines below.  On the device they live in constant
+// memory and are consumed as constant-bank operands of the DFMAs: as 64-bit immediates the compiler built each one
+// with two UMOVs in front of its DFMA — ~70 of the ~410 instructions per particle of the fused 2-D SSM step
+// (profiles/r2b_ncu_ws_vm_sl_kernel_20M.txt).
+#define WS_MATH_COEFS(X) \
+    X(EXP_LOG2E, 1.4426950408889634) \
+    X(EXP_NLN2HI, -6.93147180369123816490e-01) \
+    X(EXP_NLN2LO, -1.90821492927058770002e-10) \
+    X(EXP_P0, 0x1.af631d0059becp-26) \
+    X(EXP_P1, 0x1.28b4057f44145p-22) \
+    X(EXP_P2, 0x1.71ddf5749d126p-19) \
+    X(EXP_P3, 0x1.a01991ac8730ap-16) \
+    X(EXP_P4, 0x1.a01a01b14378fp-13) \
+    X(EXP_P5, 0x1.6c16c187fbe02p-10) \
+    X(EXP_P6, 0x1.111111110f225p-7) \
+    X(EXP_P7, 0x1.555555554f0cfp-5) \
+    X(EXP_P8, 0x1.555555555555ap-3) \
+    X(EXP_P9, 0x1.0000000000011p-1) \
+    X(LOG_A0, 0x1.2be6c99b32a48p-4) \
+    X(LOG_A1, 0x1.39f2bba043e06p-4) \
+    X(LOG_A2, 0x1.74630f3e18fa7p-4) \
+    X(LOG_A3, 0x1.c71c61a40ddfbp-4) \
+    X(LOG_A4, 0x1.2492492eefe17p-3) \
+    X(LOG_A5, 0x1.99999999949d0p-3) \
+    X(LOG_A6, 0x1.5555555555558p-2) \
+    X(LOG_LN2LO, 1.90821492927058770002e-10) \
+    X(LOG_LN2HI, 6.93147180369123816490e-01) \
+    X(SIN_P0, 0x1.e3f38399551bfp-38) \
+    X(SIN_P1, -0x1.e30071afc3e59p-30) \
+    X(SIN_P2, 0x1.50782fda12d96p-22) \
+    X(SIN_P3, -0x1.32d2cce2e5b19p-15) \
+    X(SIN_P4, 0x1.466bc677587f8p-9) \
+    X(SIN_P5, -0x1.4abbce625be41p-4) \
+    X(SIN_P6, 0x1.921fb54442d18p-1) \
+    X(COS_Q0, -0x1.b264ba152378ap-42) \
+    X(COS_Q1, 0x1.f9cc41140bb60p-34) \
+    X(COS_Q2, -0x1.a6d1ec7906c20p-26) \
+    X(COS_Q3, 0x1.e1f5068355e15p-19) \
+    X(COS_Q4, -0x1.55d3c7e3c90f8p-12) \
+    X(COS_Q5, 0x1.03c1f081b5aacp-6) \
+    X(COS_Q6, -0x1.3bd3cc9be45dep-2)
+enum WsCoefIndex {
+#define WS_COEF_ENUM(name, value) WS_CI_##name,
+    WS_MATH_COEFS(WS_COEF_ENUM)
+#undef WS_COEF_ENUM
+    WS_CI_COUNT
+};
+#define WS_COEF_VALUE(name, value) value,
+#if defined(__CUDACC__)
+static __constant__ double ws_coef_dev[WS_CI_COUNT] = {WS_MATH_COEFS(WS_COEF_VALUE)};
+#endif
+static const double ws_coef_host[WS_CI_COUNT] = {WS_MATH_COEFS(WS_COEF_VALUE)};
+#undef WS_COEF_VALUE
+#if defined(WS_COEF_IMM)   // A/B switch: the coefficients as immediates again
+#define WS_KV_EXP_LOG2E 1.4426950408889634
+#define WS_KV_EXP_NLN2HI -6.93147180369123816490e-01
+#define WS_KV_EXP_NLN2LO -1.90821492927058770002e-10
+#define WS_KV_EXP_P0 0x1.af631d0059becp-26
+#define WS_KV_EXP_P1 0x1.28b4057f44145p-22
+#define WS_KV_EXP_P2 0x1.71ddf5749d126p-19
+#define WS_KV_EXP_P3 0x1.a01991ac8730ap-16
+#define WS_KV_EXP_P4 0x1.a01a01b14378fp-13
+#define WS_KV_EXP_P5 0x1.6c16c187fbe02p-10
+#define WS_KV_EXP_P6 0x1.111111110f225p-7
+#define WS_KV_EXP_P7 0x1.555555554f0cfp-5
+#define WS_KV_EXP_P8 0x1.555555555555ap-3
+#define WS_KV_EXP_P9 0x1.0000000000011p-1
+#define WS_KV_LOG_A0 0x1.2be6c99b32a48p-4
+#define WS_KV_LOG_A1 0x1.39f2bba043e06p-4
+#define WS_KV_LOG_A2 0x1.74630f3e18fa7p-4
+#define WS_KV_LOG_A3 0x1.c71c61a40ddfbp-4
+#define WS_KV_LOG_A4 0x1.2492492eefe17p-3
+#define WS_KV_LOG_A5 0x1.99999999949d0p-3
+#define WS_KV_LOG_A6 0x1.5555555555558p-2
+#define WS_KV_LOG_LN2LO 1.90821492927058770002e-10
+#define WS_KV_LOG_LN2HI 6.93147180369123816490e-01
+#define WS_KV_SIN_P0 0x1.e3f38399551bfp-38
+#define WS_KV_SIN_P1 -0x1.e30071afc3e59p-30
+#define WS_KV_SIN_P2 0x1.50782fda12d96p-22
+#define WS_KV_SIN_P3 -0x1.32d2cce2e5b19p-15
+#define WS_KV_SIN_P4 0x1.466bc677587f8p-9
+#define WS_KV_SIN_P5 -0x1.4abbce625be41p-4
+#define WS_KV_SIN_P6 0x1.921fb54442d18p-1
+#define WS_KV_COS_Q0 -0x1.b264ba152378ap-42
+#define WS_KV_COS_Q1 0x1.f9cc41140bb60p-34
+#define WS_KV_COS_Q2 -0x1.a6d1ec7906c20p-26
+#define WS_KV_COS_Q3 0x1.e1f5068355e15p-19
+#define WS_KV_COS_Q4 -0x1.55d3c7e3c90f8p-12
+#define WS_KV_COS_Q5 0x1.03c1f081b5aacp-6
+#define WS_KV_COS_Q6 -0x1.3bd3cc9be45dep-2
+#define WS_K(name) WS_KV_##name
+#elif defined(__CUDA_ARCH__)
+#define WS_K(name) ws_coef_dev[WS_CI_##name]
+#else
+#define WS_K(name) ws_coef_host[WS_CI_##name]
+#endif
+
 // exp(d) for d <= 0 (log-weight minus its maximum): Cody-Waite reduction, degree-11 polynomial.
 // d < -708 (result below the normal range) and d = -inf give 0; NaN gives NaN.
 WS_HD double ws_exp_nonpos(double d) {
     const double MAGIC = 6755399441055744.0;  // 1.5 * 2^52: fma(d, log2e, MAGIC) holds rint(d*log2e) in its low word
-    const double t = ws_fma(d, 1.4426950408889634, MAGIC);
+    const double t = ws_fma(d, WS_K(EXP_LOG2E), MAGIC);
     const double kd = t - MAGIC;
-    double r = ws_fma(kd, -6.93147180369123816490e-01, d);   // ln2 hi (32 trailing zero bits)
-    r = ws_fma(kd, -1.90821492927058770002e-10, r);          // ln2 lo
-    double p = 0x1.af631d0059becp-26;
-    p = ws_fma(p, r, 0x1.28b4057f44145p-22);
-    p = ws_fma(p, r, 0x1.71ddf5749d126p-19);
-    p = ws_fma(p, r, 0x1.a01991ac8730ap-16);
-    p = ws_fma(p, r, 0x1.a01a01b14378fp-13);
-    p = ws_fma(p, r, 0x1.6c16c187fbe02p-10);
-    p = ws_fma(p, r, 0x1.111111110f225p-7);
-    p = ws_fma(p, r, 0x1.555555554f0cfp-5);
-    p = ws_fma(p, r, 0x1.555555555555ap-3);
-    p = ws_fma(p, r, 0x1.0000000000011p-1);
+    double r = ws_fma(kd, WS_K(EXP_NLN2HI), d);   // ln2 hi (32 trailing zero bits)
+    r = ws_fma(kd, WS_K(EXP_NLN2LO), r);          // ln2 lo
+    double p = WS_K(EXP_P0);
+    p = ws_fma(p, r, WS_K(EXP_P1));
+    p = ws_fma(p, r, WS_K(EXP_P2));
+    p = ws_fma(p, r, WS_K(EXP_P3));
+    p = ws_fma(p, r, WS_K(EXP_P4));
+    p = ws_fma(p, r, WS_K(EXP_P5));
+    p = ws_fma(p, r, WS_K(EXP_P6));
+    p = ws_fma(p, r, WS_K(EXP_P7));
+    p = ws_fma(p, r, WS_K(EXP_P8));
+    p = ws_fma(p, r, WS_K(EXP_P9));
     p = ws_fma(p, r, 1.0);
     p = ws_fma(p, r, 1.0);
     const uint64_t k = (uint64_t)(uint32_t)ws_double_to_bits(t);  // low word of t = k as a two's-complement int32
@@ -188,18 +285,18 @@ WS_HD double ws_log_pos(double x, int kbias = 0) {
     double s = f * y;
     s = ws_fma(ws_fma(-s, g, f), y, s);                     // f/g correctly rounded (Markstein)
     const double s2 = s * s;
-    double a = 0x1.2be6c99b32a48p-4;
-    a = ws_fma(a, s2, 0x1.39f2bba043e06p-4);
-    a = ws_fma(a, s2, 0x1.74630f3e18fa7p-4);
-    a = ws_fma(a, s2, 0x1.c71c61a40ddfbp-4);
-    a = ws_fma(a, s2, 0x1.2492492eefe17p-3);
-    a = ws_fma(a, s2, 0x1.99999999949d0p-3);
-    a = ws_fma(a, s2, 0x1.5555555555558p-2);
+    double a = WS_K(LOG_A0);
+    a = ws_fma(a, s2, WS_K(LOG_A1));
+    a = ws_fma(a, s2, WS_K(LOG_A2));
+    a = ws_fma(a, s2, WS_K(LOG_A3));
+    a = ws_fma(a, s2, WS_K(LOG_A4));
+    a = ws_fma(a, s2, WS_K(LOG_A5));
+    a = ws_fma(a, s2, WS_K(LOG_A6));
     const double kd = (double)(k + kbias);
     const double s3a = (s * s2) * a;
     // k ln2 + 2 s + 2 s^3 A(s^2), small terms first
-    const double lo = ws_fma(kd, 1.90821492927058770002e-10, s3a + s3a);
-    return ws_fma(kd, 6.93147180369123816490e-01, (s + s) + lo);
+    const double lo = ws_fma(kd, WS_K(LOG_LN2LO), s3a + s3a);
+    return ws_fma(kd, WS_K(LOG_LN2HI), (s + s) + lo);
 }
 
 // sqrt(t) for a positive, finite, normal t: MUFU seed, two Newton steps on 1/sqrt, one residual correction.
@@ -218,21 +315,21 @@ WS_HD double ws_sqrt_pos(double t) {
 // (sin, cos) of (pi/4) f for f in [0, 1]
 WS_HD void ws_sincos_octant(double f, double& sn, double& cs) {
     const double f2 = f * f;
-    double p = 0x1.e3f38399551bfp-38;
-    p = ws_fma(p, f2, -0x1.e30071afc3e59p-30);
-    p = ws_fma(p, f2, 0x1.50782fda12d96p-22);
-    p = ws_fma(p, f2, -0x1.32d2cce2e5b19p-15);
-    p = ws_fma(p, f2, 0x1.466bc677587f8p-9);
-    p = ws_fma(p, f2, -0x1.4abbce625be41p-4);
-    p = ws_fma(p, f2, 0x1.921fb54442d18p-1);
+    double p = WS_K(SIN_P0);
+    p = ws_fma(p, f2, WS_K(SIN_P1));
+    p = ws_fma(p, f2, WS_K(SIN_P2));
+    p = ws_fma(p, f2, WS_K(SIN_P3));
+    p = ws_fma(p, f2, WS_K(SIN_P4));
+    p = ws_fma(p, f2, WS_K(SIN_P5));
+    p = ws_fma(p, f2, WS_K(SIN_P6));
     sn = p * f;
-    double q = -0x1.b264ba152378ap-42;
-    q = ws_fma(q, f2, 0x1.f9cc41140bb60p-34);
-    q = ws_fma(q, f2, -0x1.a6d1ec7906c20p-26);
-    q = ws_fma(q, f2, 0x1.e1f5068355e15p-19);
-    q = ws_fma(q, f2, -0x1.55d3c7e3c90f8p-12);
-    q = ws_fma(q, f2, 0x1.03c1f081b5aacp-6);
-    q = ws_fma(q, f2, -0x1.3bd3cc9be45dep-2);
+    double q = WS_K(COS_Q0);
+    q = ws_fma(q, f2, WS_K(COS_Q1));
+    q = ws_fma(q, f2, WS_K(COS_Q2));
+    q = ws_fma(q, f2, WS_K(COS_Q3));
+    q = ws_fma(q, f2, WS_K(COS_Q4));
+    q = ws_fma(q, f2, WS_K(COS_Q5));
+    q = ws_fma(q, f2, WS_K(COS_Q6));
     cs = ws_fma(q, f2, 1.0);
 }
 

@@ -172,6 +172,19 @@ struct ws_ctx {
     WsReduceOut* d_red = nullptr;
     WsReduceOut* h_red = nullptr;  // pinned
     bool red_valid = false;        // h_red/d_red describe the current log-weights
+    // Resample steps whose decision the host has not looked at yet (ws_resample_async): the (m, S, Q, ESS, decision)
+    // record of each is copied, stream-ordered, into a pinned ring; the scan / search kernels run gated on the device
+    // flag, the host books the event as if it had fired (if it did not, the ancestors are the identity) and learns the
+    // truth when somebody asks (resolve_spec).  logw_spec: the LAST such step has not been followed by a weighting pass
+    // yet, i.e. the log-weights are "all equal to d_red->log_mean_w if it fired, else the array as it is".
+    static constexpr int SPEC_RING = 512;
+    WsReduceOut* h_ring = nullptr;  // pinned [SPEC_RING]
+    int64_t spec_head = 0;          // records [spec_head - spec_pending, spec_head) are unresolved
+    int spec_pending = 0;
+    bool logw_spec = false;
+    bool async_resample = true;     // env WSB200_ASYNC_RESAMPLE=0: ws_resample_async behaves like ws_resample
+    ws_resample_info last_info{};   // outcome of the most recent Resample step (ws_last_resample)
+    bool last_info_pending = false; // ... which is the newest unresolved record
 
     // resampling scratch
     int32_t* d_anc = nullptr;  // ancestors of the latest resampling event (== anc_live.back().ptr)
@@ -274,6 +287,7 @@ static int materialize_deep(ws_ctx* c, const std::vector<Plane>& planes);
 static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out);
 static const int32_t* anc_of_event(const ws_ctx* c, int64_t event);
 static int materialize_tape_planes(ws_ctx* c, int32_t n_extra, const int32_t* col, const int32_t* comp);
+static int resolve_spec(ws_ctx* c);
 
 // ------------------------------------------------------------------------------------------
 // error helpers
@@ -509,6 +523,11 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     CKC(cudaMemsetAsync(c->d_red, 0, sizeof(WsReduceOut), c->stream));
     CKC(cudaMallocHost(&c->h_red, sizeof(WsReduceOut)));
     memset(c->h_red, 0, sizeof(WsReduceOut));
+    CKC(cudaMallocHost(&c->h_ring, sizeof(WsReduceOut) * ws_ctx::SPEC_RING));
+    {
+        const char* v = getenv("WSB200_ASYNC_RESAMPLE");
+        c->async_resample = !(v != nullptr && strcmp(v, "0") == 0);
+    }
     if (nranks > 1) c->spare = std::max<int64_t>(4096, c->n / 32);
     // sharded: a margin of `spare` entries on BOTH sides, so that the search can write the ancestors of the slots
     // this rank produces for its neighbours in place, next to those of its own slots (resample_sharded)
@@ -609,6 +628,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_partials);
     cudaFree(c->d_red);
     if (c->h_red) cudaFreeHost(c->h_red);
+    if (c->h_ring) cudaFreeHost(c->h_ring);
     cudaFree(c->d_map);
     cudaFree(c->d_tile_words);
     cudaFree(c->d_cdf_local);
@@ -714,7 +734,10 @@ static int flush_window(ws_ctx* c) {
     }
     if (w.has_acc) {
         P.logw = c->logw;
-        if (c->logw_uniform) {
+        if (c->logw_spec) {
+            P.logw_mode = 3;  // decided on the device: base = red->log_mean_w if the pending Resample fired, else read logw
+            P.red = c->d_red;
+        } else if (c->logw_uniform) {
             P.logw_mode = 2;
             P.logw_base = c->logw_base;
         } else {
@@ -748,6 +771,7 @@ static int flush_window(ws_ctx* c) {
     c->stats.fused_statements += w.n_statements;
     if (w.has_acc) {
         c->logw_uniform = false;
+        c->logw_spec = false;
         c->partials_valid = true;
         c->n_partials = sl_grid > 0 ? sl_grid : std::max(1, grid);
         c->red_valid = false;
@@ -764,6 +788,7 @@ extern "C" int ws_sync(ws_ctx* c) {
     if (!c) return WS_EINVAL;
     TRY(flush_window(c));
     CK(c, cudaStreamSynchronize(c->stream));
+    TRY(resolve_spec(c));
     return WS_OK;
 }
 
@@ -865,6 +890,7 @@ extern "C" int ws_n_particles(const ws_ctx* c, int64_t* n_local, int64_t* n_glob
 }
 extern "C" int ws_get_flags(ws_ctx* c, int* resampled, int* weights_changed, int64_t* depth) {
     if (!c) return WS_EINVAL;
+    if (resampled) TRY(resolve_spec(c));   // `if resampled` is host control flow: this is where a pending decision is awaited
     if (resampled) *resampled = c->resampled ? 1 : 0;
     if (weights_changed) *weights_changed = c->weights_changed ? 1 : 0;
     if (depth) *depth = c->depth;
@@ -872,6 +898,7 @@ extern "C" int ws_get_flags(ws_ctx* c, int* resampled, int* weights_changed, int
 }
 extern "C" int ws_set_flags(ws_ctx* c, int resampled, int weights_changed) {
     if (!c) return WS_EINVAL;
+    TRY(resolve_spec(c));
     c->resampled = resampled != 0;
     c->weights_changed = weights_changed != 0;
     return WS_OK;
@@ -1011,6 +1038,7 @@ extern "C" int ws_col_upload(ws_ctx* c, int32_t id, const double* host_in) {
 }
 
 static int materialize_logw(ws_ctx* c) {
+    TRY(resolve_spec(c));
     if (!c->logw_uniform) return WS_OK;
     TimedEvent te;
     timed_begin(c, KC_FILL, te);
@@ -1033,6 +1061,7 @@ extern "C" int ws_weights_download(ws_ctx* c, double* host_out) {
 extern "C" int ws_weights_upload(ws_ctx* c, const double* host_in, int mark_changed) {
     if (!c || !host_in) return WS_EINVAL;
     TRY(flush_window(c));
+    TRY(resolve_spec(c));
     CK(c, cudaMemcpyAsync(c->logw, host_in, sizeof(double) * (size_t)c->n, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (int64_t)sizeof(double) * c->n;
@@ -1274,9 +1303,54 @@ extern "C" int ws_sample_importance_normal(ws_ctx* c, int32_t col, int32_t comp,
 // ------------------------------------------------------------------------------------------
 // reductions / resampling
 // ------------------------------------------------------------------------------------------
+// Bring the host's view up to date with the Resample steps it issued without looking at their outcome
+// (ws_resample_async): wait for the stream, read their records from the pinned ring in order.
+static int resolve_spec(ws_ctx* c) {
+    if (c->spec_pending == 0) return WS_OK;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut) * c->spec_pending;
+    WsReduceOut last{};
+    for (int64_t k = c->spec_head - c->spec_pending; k < c->spec_head; ++k) {
+        last = c->h_ring[k % ws_ctx::SPEC_RING];
+        if (last.do_resample) {
+            c->resampled = true;
+            c->stats.resamples_done++;
+        } else {
+            c->resampled = false;
+        }
+    }
+    c->spec_pending = 0;
+    if (c->last_info_pending) {
+        c->last_info.fired = 1;
+        c->last_info.resampled = last.do_resample ? 1 : 0;
+        c->last_info.ess_perc = last.ess_perc;
+        c->last_info.log_mean_w = last.log_mean_w;
+        c->last_info.n_clamped = -1;
+        c->last_info_pending = false;
+    }
+    if (c->logw_spec) {
+        // no weighting pass has run since the last of them: its outcome decides what the log-weights are
+        c->logw_spec = false;
+        if (last.do_resample) {
+            c->logw_uniform = true;   // fill!(weights, mean_logW), kept symbolic
+            c->logw_base = last.log_mean_w;
+            c->partials_valid = false;
+            c->red_valid = false;
+        } else {
+            c->logw_uniform = false;  // the array and the reduction of it that decided are both still current
+            *c->h_red = last;
+            c->partials_valid = true;
+            c->red_valid = true;
+        }
+    }
+    return WS_OK;
+}
+
 // Make d_red / h_red describe the current log-weights (m, S, Q, lse, ESS%, decision).
 static int ensure_reduced(ws_ctx* c) {
     TRY(flush_window(c));
+    TRY(resolve_spec(c));
     if (c->red_valid) return WS_OK;
     CK(c, cudaSetDevice(c->device));
     if (c->logw_uniform) TRY(materialize_logw(c));
@@ -1502,7 +1576,7 @@ static int gather_all(ws_ctx* c, const int32_t* d_anc) {
 
 static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, int64_t n, const double* d_replay_u,
                            const double* d_sorted_u, int32_t* d_anc, unsigned long long* d_words,
-                           unsigned long long* d_cdf_local, uint64_t stream_id, unsigned long long* d_clamped) {
+                           unsigned long long* d_cdf_local, uint64_t stream_id, unsigned long long* d_clamped, int gate = 0) {
     const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     if (c->d_heavy_F == nullptr || c->heavy_cap_n < n) {
         // at most n / WS_HEAVY_TILE_SLOTS families can own more than WS_HEAVY_TILE_SLOTS offspring each
@@ -1523,7 +1597,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     S.mode = mode;
     S.scheme = scheme;
     S.red = c->d_red;
-    S.gate = 0;
+    S.gate = gate;
     S.n = n;
     S.n_slots = n;
     S.cdf_offset = 0ull;
@@ -1547,6 +1621,10 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_scan_search(S, 0, c->stream));
     c->stats.kernel_launches += 3;  // cdf tiles, offsets, search, heavy expansion
+    if (gate) {  // a step that does not fire leaves the identity in the ancestor vector (ws_resample_async)
+        CK(c, ws_launch_identity_unless_fired(c->d_red, d_anc, n, grid_for(c, n, 256, 8), c->stream));
+        c->stats.kernel_launches++;
+    }
     timed_end(c, te);
     return WS_OK;
 }
@@ -1686,9 +1764,8 @@ static int resolve_peer_planes(ws_ctx* c, const std::vector<int64_t>& all, size_
     return WS_OK;
 }
 
-static int resample_sharded(ws_ctx* c, const double* d_ru) {
+static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id) {
     const int R = c->nranks, r = c->rank;
-    const uint64_t stream_id = c->next_stream++;
     auto t_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = t_now();
     c->phase_n++;
@@ -1936,18 +2013,26 @@ static int resample_sharded(ws_ctx* c, const double* d_ru) {
 extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
     if (!c) return WS_EINVAL;
     if (info) {
+        TRY(resolve_spec(c));  // the caller wants the outcome, including the current value of `resampled`
         info->fired = 0;
         info->resampled = c->resampled ? 1 : 0;
         info->ess_perc = NAN;
         info->log_mean_w = NAN;
         info->n_clamped = -1;  // cumulative count is reported by ws_get_clamped (needs a sync)
     }
-    if (!c->weights_changed) return WS_OK;  // `resampled` keeps its previous value (transformers.jl:475-477)
+    if (!c->weights_changed) {  // `resampled` keeps its previous value (transformers.jl:475-477)
+        c->last_info = ws_resample_info{0, -1, NAN, NAN, -1};  // resampled: filled in by ws_last_resample
+        c->last_info_pending = false;
+        return WS_OK;
+    }
     if (c->resampler == WS_RESAMPLER_MULTINOMIAL && c->nranks > 1)
         return fail(c, WS_EUNSUPPORTED, "multinomial resampling of a sharded state is not built (stratified / systematic are)");
     TRY(ensure_reduced(c));
     c->stats.resamples_fired++;
     const WsReduceOut r = *c->h_red;
+    // the Philox stream of this step's slot uniforms is taken whether or not the step fires, so that the streams of
+    // everything that follows do not depend on how (or when) the decision is learnt
+    const uint64_t step_stream = c->next_stream++;
     if (r.do_resample) {
         // slot uniforms: one per slot (stratified) or one in total (systematic), in replay order
         const double* d_ru = nullptr;
@@ -1961,7 +2046,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
         }
         if (c->nranks > 1) {
             TRY(begin_resample_event(c));
-            TRY(resample_sharded(c, d_ru));
+            TRY(resample_sharded(c, d_ru, step_stream));
             c->logw_uniform = true;
             c->logw_base = r.log_mean_w;
             c->partials_valid = false;
@@ -1969,15 +2054,12 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
             c->resampled = true;
             c->stats.resamples_done++;
             c->weights_changed = false;
-            if (info) {
-                info->fired = 1;
-                info->resampled = 1;
-                info->ess_perc = r.ess_perc;
-                info->log_mean_w = r.log_mean_w;
-            }
+            c->last_info = ws_resample_info{1, 1, r.ess_perc, r.log_mean_w, -1};
+            c->last_info_pending = false;
+            if (info) *info = c->last_info;
             return WS_OK;
         }
-        const uint64_t stream_id = c->next_stream++;
+        const uint64_t stream_id = step_stream;
         // planes still in an older order keep their ancestor vectors (genealogy) or are gathered now
         TRY(begin_resample_event(c));
         const double* d_sorted = nullptr;
@@ -2008,12 +2090,77 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
         c->resampled = false;
     }
     c->weights_changed = false;
-    if (info) {
-        info->fired = 1;
-        info->resampled = c->resampled ? 1 : 0;
-        info->ess_perc = r.ess_perc;
-        info->log_mean_w = r.log_mean_w;
+    c->last_info = ws_resample_info{1, c->resampled ? 1 : 0, r.ess_perc, r.log_mean_w, -1};
+    c->last_info_pending = false;
+    if (info) *info = c->last_info;
+    return WS_OK;
+}
+
+// Resample.apply! without waiting for its outcome.  The reference's state machine (transformers.jl:474-498) needs
+// ESS% < ess_perc_min on the host only to decide what to launch; here everything that depends on the decision runs
+// on the device behind the decision flag, so the host issues the step and goes on:
+//   * (m, S, Q) partials -> ws_finalize_kernel -> d_red (+ a stream-ordered copy into the pinned ring);
+//   * CDF + ancestor search gated on d_red->do_resample; if the step does not fire the same kernel writes the
+//     identity into the ancestor vector;
+//   * the host books the event as fired (new ancestor vector, every plane one event behind): the deferred gather
+//     of the next pass reads through the ancestors either way, and that pass takes its old log-weights from
+//     d_red->log_mean_w or from the array according to the same flag (logw_mode 3).
+// `state.resampled`, the counters and anything that reads the log-weights resolve the pending records first
+// (resolve_spec), which is the only place the host waits.  Not taken (falls back to ws_resample): replayed
+// uniforms (the cursor advances only on a firing step), sharded states, multinomial, eager gather.
+extern "C" int ws_resample_async(ws_ctx* c) {
+    if (!c) return WS_EINVAL;
+    if (!c->weights_changed) {
+        c->last_info = ws_resample_info{0, -1, NAN, NAN, -1};
+        c->last_info_pending = false;
+        return WS_OK;
     }
+    if (!c->async_resample || c->d_replay_u != nullptr || c->nranks > 1 || c->resampler == WS_RESAMPLER_MULTINOMIAL ||
+        !c->lazy_gather || c->cols.empty())
+        return ws_resample(c, nullptr);
+    TRY(flush_window(c));
+    if (c->red_valid || c->logw_uniform || c->logw_spec) return ws_resample(c, nullptr);  // nothing new was weighted on the device
+    CK(c, cudaSetDevice(c->device));
+    if (c->spec_pending >= ws_ctx::SPEC_RING - 1) TRY(resolve_spec(c));
+    if (!c->partials_valid) {
+        const int grid = std::min(grid_for(c, c->n, 256, 8), WS_MAX_PARTIALS);
+        TimedEvent te;
+        timed_begin(c, KC_REDUCE, te);
+        CK(c, ws_launch_reduce_logw(c->logw, c->n, c->d_partials, grid, c->stream));
+        timed_end(c, te);
+        c->n_partials = grid;
+        c->partials_valid = true;
+    }
+    TimedEvent te;
+    timed_begin(c, KC_FINALIZE, te);
+    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream));
+    timed_end(c, te);
+    CK(c, cudaMemcpyAsync(&c->h_ring[c->spec_head % ws_ctx::SPEC_RING], c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
+    c->spec_head++;
+    c->spec_pending++;
+    c->stats.resamples_fired++;
+    const uint64_t stream_id = c->next_stream++;
+    TRY(begin_resample_event(c));
+    TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, nullptr, nullptr, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id,
+                        c->d_counters + 0, /*gate=*/1));
+    end_resample_event(c);
+    c->logw_uniform = false;
+    c->logw_spec = true;
+    c->partials_valid = false;
+    c->red_valid = false;
+    c->weights_changed = false;
+    c->last_info_pending = true;
+    return WS_OK;
+}
+
+extern "C" int ws_last_resample(ws_ctx* c, ws_resample_info* info) {
+    if (!c || !info) return WS_EINVAL;
+    if (c->last_info_pending) TRY(resolve_spec(c));
+    if (c->last_info.resampled < 0) {  // a no-op step: `resampled` is whatever the steps before it left
+        TRY(resolve_spec(c));
+        c->last_info.resampled = c->resampled ? 1 : 0;
+    }
+    *info = c->last_info;
     return WS_OK;
 }
 
@@ -2040,6 +2187,7 @@ extern "C" int ws_ancestors_download(ws_ctx* c, int32_t* host_out) {
 extern "C" int ws_log_evidence(ws_ctx* c, double* log_evidence, double* ess_perc) {
     if (!c) return WS_EINVAL;
     TRY(flush_window(c));
+    TRY(resolve_spec(c));
     if (c->logw_uniform) {  // logsumexp(fill(c, N)) - log N = c ; ESS% = 1
         if (log_evidence) *log_evidence = c->logw_base;
         if (ess_perc) *ess_perc = 1.0;
@@ -2074,6 +2222,7 @@ struct TempBuf {
 };
 
 static int reduce_host_array(ws_ctx* c, const double* d_logw, int64_t n) {
+    TRY(resolve_spec(c));  // d_partials / d_red are reused as scratch below
     const int grid = std::min(grid_for(c, n, 256, 8), WS_MAX_PARTIALS);
     TimedEvent te;
     timed_begin(c, KC_REDUCE, te);
@@ -2145,6 +2294,7 @@ extern "C" int ws_ess_perc_host(ws_ctx* c, const double* w, int64_t n, double* o
 static int resample_host_impl(ws_ctx* c, const double* weights, int64_t n, int scheme, const double* uniforms,
                               int64_t n_uniforms, bool sorted_mode, int32_t* indices_out, int64_t* n_clamped) {
     TRY(flush_window(c));
+    TRY(resolve_spec(c));
     CK(c, cudaSetDevice(c->device));
     if (n >= (int64_t)2147483647 - 65536) return fail(c, WS_EINVAL, "n must be < 2^31 - 65536");
     TempBuf w, u, anc, words, cdf;
@@ -2355,6 +2505,7 @@ extern "C" int ws_sample_indices(ws_ctx* c, int64_t n_draws, int replace, int64_
 // ------------------------------------------------------------------------------------------
 static int set_replay(ws_ctx* c, double** dptr, int64_t* dlen, int64_t* cursor, const double* host, int64_t len) {
     TRY(flush_window(c));
+    TRY(resolve_spec(c));
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     if (*dptr) {
@@ -2693,6 +2844,7 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
     if (spec->proposal != WS_PROPOSAL_RW && spec->proposal != WS_PROPOSAL_AUTORW) return fail(c, WS_EINVAL, "ws_move: unknown proposal %d", spec->proposal);
     if (spec->has_bounds && (!spec->lo || !spec->hi)) return fail(c, WS_EINVAL, "ws_move: bounds missing");
     TRY(flush_window(c));
+    TRY(resolve_spec(c));
     TRY(materialize_tape_planes(c, d, spec->col, spec->comp));
     CK(c, cudaSetDevice(c->device));
     if (info) {
@@ -2922,6 +3074,7 @@ extern "C" int ws_get_clamped(ws_ctx* c, int64_t* out) {
 
 extern "C" int ws_get_stats(ws_ctx* c, ws_stats* out) {
     if (!c || !out) return WS_EINVAL;
+    TRY(resolve_spec(c));
     resolve_events(c);
     c->stats.last_pass_ms = c->kc_ms[KC_VM];
     c->stats.last_resample_ms = c->kc_ms[KC_SCAN] + c->kc_ms[KC_GATHER];
@@ -2955,6 +3108,7 @@ extern "C" int ws_set_timing(ws_ctx* c, int on) {
 extern "C" int ws_set_lazy_gather(ws_ctx* c, int on) {
     if (!c) return WS_EINVAL;
     TRY(flush_window(c));
+    TRY(resolve_spec(c));
     TRY(materialize_planes(c));
     c->lazy_gather = on != 0;
     return WS_OK;

@@ -13,6 +13,7 @@
 // Constants (k0, k1, k2), plane pointers, ancestors and the RNG description still come from the WsVmProgram of
 // the launch.  A window that matches no signature runs on the interpreter as before.
 #pragma once
+#include <cmath>
 #include <utility>
 #include "ws_vm.cuh"
 #if defined(__CUDACC__)
@@ -29,7 +30,15 @@
 struct WsSlOp {
     uint8_t op, dst, a, b, c;
     uint32_t imm;
+    uint8_t kflags;   // WS_SL_K*: constants whose VALUE is part of the signature (0 or 1), see ws_sl_step
 };
+// `x .= x + v` lowers to LIN2 with (k0, k1, k2) = (0, 1, 1) and `dv = L z` to (0, L, -): when the signature pins those
+// values the executor sees literal 0.0 / 1.0 and the op is one DADD / DMUL instead of two DFMAs whose constants are
+// fetched from the launch parameters every tile (IEEE-identical: 1*a and fma(k, a, 0) are exact)
+#define WS_SL_K0Z 1u     // k0 == 0.0
+#define WS_SL_K1ONE 2u   // k1 == 1.0
+#define WS_SL_K2ONE 4u   // k2 == 1.0
+#define WS_SL_ADD (WS_SL_K0Z | WS_SL_K1ONE | WS_SL_K2ONE)
 
 WS_SL_CX bool ws_sl_dst_is_reg(uint32_t op) {
     return !(op == WS_OP_LOGPDF_NORMAL || op == WS_OP_LOGPDF_EXPON || op == WS_OP_ACC_LIN2 || op == WS_OP_ACC_QUAD2 ||
@@ -47,13 +56,13 @@ struct WsSigSsm2d {
     static constexpr uint8_t load_reg[4] = {0, 1, 2, 3};            // x1 v1 x2 v2
     static constexpr uint8_t store_reg[6] = {0, 2, 6, 7, 1, 3};     // x1 x2 dv1 dv2 v1 v2
     static constexpr WsSlOp ops[10] = {
-        {WS_OP_LIN2, 0, 0, 1, WS_SL_N, 0},        // x1 += v1
-        {WS_OP_LIN2, 2, 2, 3, WS_SL_N, 0},        // x2 += v2
+        {WS_OP_LIN2, 0, 0, 1, WS_SL_N, 0, WS_SL_ADD},        // x1 += v1
+        {WS_OP_LIN2, 2, 2, 3, WS_SL_N, 0, WS_SL_ADD},        // x2 += v2
         {WS_OP_RANDN2, 4, 5, WS_SL_N, WS_SL_N, 0},  // z1, z2
-        {WS_OP_LIN2, 6, 4, WS_SL_N, WS_SL_N, 0},  // dv1 = L11 z1
-        {WS_OP_LIN2, 7, 5, WS_SL_N, WS_SL_N, 0},  // dv2 = L22 z2
-        {WS_OP_LIN2, 1, 1, 6, WS_SL_N, 0},        // v1 += dv1
-        {WS_OP_LIN2, 3, 3, 7, WS_SL_N, 0},        // v2 += dv2
+        {WS_OP_LIN2, 6, 4, WS_SL_N, WS_SL_N, 0, WS_SL_K0Z},  // dv1 = L11 z1
+        {WS_OP_LIN2, 7, 5, WS_SL_N, WS_SL_N, 0, WS_SL_K0Z},  // dv2 = L22 z2
+        {WS_OP_LIN2, 1, 1, 6, WS_SL_N, 0, WS_SL_ADD},        // v1 += dv1
+        {WS_OP_LIN2, 3, 3, 7, WS_SL_N, 0, WS_SL_ADD},        // v2 += dv2
         {WS_OP_LIN2, 4, 0, WS_SL_N, WS_SL_N, 0},  // whitened residual 1
         {WS_OP_LIN2, 5, 2, WS_SL_N, WS_SL_N, 0},  // whitened residual 2
         {WS_OP_ACC_QUAD2, WS_SL_N, 4, 5, WS_SL_N, 0},
@@ -65,13 +74,13 @@ struct WsSigSsm2dHist {
     static constexpr uint8_t load_reg[4] = {0, 1, 2, 3};            // x{t}1 v1 x{t}2 v2
     static constexpr uint8_t store_reg[6] = {4, 5, 8, 9, 1, 3};     // x{t+1}1 x{t+1}2 dv1 dv2 v1 v2
     static constexpr WsSlOp ops[10] = {
-        {WS_OP_LIN2, 4, 0, 1, WS_SL_N, 0},
-        {WS_OP_LIN2, 5, 2, 3, WS_SL_N, 0},
+        {WS_OP_LIN2, 4, 0, 1, WS_SL_N, 0, WS_SL_ADD},
+        {WS_OP_LIN2, 5, 2, 3, WS_SL_N, 0, WS_SL_ADD},
         {WS_OP_RANDN2, 6, 7, WS_SL_N, WS_SL_N, 0},
-        {WS_OP_LIN2, 8, 6, WS_SL_N, WS_SL_N, 0},
-        {WS_OP_LIN2, 9, 7, WS_SL_N, WS_SL_N, 0},
-        {WS_OP_LIN2, 1, 1, 8, WS_SL_N, 0},
-        {WS_OP_LIN2, 3, 3, 9, WS_SL_N, 0},
+        {WS_OP_LIN2, 8, 6, WS_SL_N, WS_SL_N, 0, WS_SL_K0Z},
+        {WS_OP_LIN2, 9, 7, WS_SL_N, WS_SL_N, 0, WS_SL_K0Z},
+        {WS_OP_LIN2, 1, 1, 8, WS_SL_N, 0, WS_SL_ADD},
+        {WS_OP_LIN2, 3, 3, 9, WS_SL_N, 0, WS_SL_ADD},
         {WS_OP_LIN2, 6, 4, WS_SL_N, WS_SL_N, 0},
         {WS_OP_LIN2, 7, 5, WS_SL_N, WS_SL_N, 0},
         {WS_OP_ACC_QUAD2, WS_SL_N, 6, 7, WS_SL_N, 0},
@@ -84,7 +93,7 @@ struct WsSigLgssm1d {
     static constexpr uint8_t store_reg[1] = {0};
     static constexpr WsSlOp ops[3] = {
         {WS_OP_RANDN2, 1, WS_SL_N, WS_SL_N, WS_SL_N, 0},
-        {WS_OP_LIN2, 0, 0, 1, WS_SL_N, 0},
+        {WS_OP_LIN2, 0, 0, 1, WS_SL_N, 0, WS_SL_K0Z},
         {WS_OP_LOGPDF_NORMAL_CS, WS_SL_N, WS_SL_N, 0, WS_SL_N, 0},
     };
 };
@@ -94,10 +103,10 @@ struct WsSigSsm1d {
     static constexpr uint8_t load_reg[2] = {0, 1};
     static constexpr uint8_t store_reg[3] = {0, 3, 1};
     static constexpr WsSlOp ops[5] = {
-        {WS_OP_LIN2, 0, 0, 1, WS_SL_N, 0},
+        {WS_OP_LIN2, 0, 0, 1, WS_SL_N, 0, WS_SL_ADD},
         {WS_OP_RANDN2, 2, WS_SL_N, WS_SL_N, WS_SL_N, 0},
-        {WS_OP_LIN2, 3, 2, WS_SL_N, WS_SL_N, 0},
-        {WS_OP_LIN2, 1, 1, 3, WS_SL_N, 0},
+        {WS_OP_LIN2, 3, 2, WS_SL_N, WS_SL_N, 0, WS_SL_K0Z},
+        {WS_OP_LIN2, 1, 1, 3, WS_SL_N, 0, WS_SL_ADD},
         {WS_OP_LOGPDF_NORMAL_CS, WS_SL_N, WS_SL_N, 0, WS_SL_N, 0},
     };
 };
@@ -107,7 +116,7 @@ struct WsSigLinregObs {
     static constexpr uint8_t load_reg[2] = {0, 1};
     static constexpr uint8_t store_reg[1] = {0};
     static constexpr WsSlOp ops[2] = {
-        {WS_OP_LIN2, 2, 0, 1, WS_SL_N, 0},
+        {WS_OP_LIN2, 2, 0, 1, WS_SL_N, 0, WS_SL_K0Z | WS_SL_K1ONE},
         {WS_OP_LOGPDF_NORMAL_CS, WS_SL_N, WS_SL_N, 2, WS_SL_N, 0},
     };
 };
@@ -152,6 +161,9 @@ inline bool ws_sl_matches(const Prog& P, const uint8_t (&map)[256]) {
         if (ws_sl_dst_is_reg(op) && canon((o.w0 >> 8) & 0xFFu) != s.dst) return false;
         if (canon((o.w0 >> 16) & 0xFFu) != s.a || canon((o.w0 >> 24) & 0xFFu) != s.b || canon(o.w1 & 0xFFu) != s.c) return false;
         if (!ws_sl_imm_is_runtime(op) && (o.w1 >> 8) != s.imm) return false;
+        if ((s.kflags & WS_SL_K0Z) && !(o.k0 == 0.0 && !std::signbit(o.k0))) return false;
+        if ((s.kflags & WS_SL_K1ONE) && o.k1 != 1.0) return false;
+        if ((s.kflags & WS_SL_K2ONE) && o.k2 != 1.0) return false;
     }
     return true;
 }
@@ -186,9 +198,10 @@ __device__ __forceinline__ void ws_sl_step(double* __restrict__ R, double (&acc)
     d.c = (s.c == WS_SL_N) ? WS_OFF_NONE : (uint32_t)s.c * PP;
     constexpr bool rt_imm = ws_sl_imm_is_runtime(s.op);
     d.imm = rt_imm ? (o.w1 >> 8) : s.imm;
-    d.k0 = o.k0;
-    d.k1 = swap ? o.k2 : o.k1;
-    d.k2 = o.k2;
+    // (a swapped LIN2 carries no value flags in any signature)
+    d.k0 = (s.kflags & WS_SL_K0Z) ? 0.0 : o.k0;
+    d.k1 = (s.kflags & WS_SL_K1ONE) ? 1.0 : (swap ? o.k2 : o.k1);
+    d.k2 = (s.kflags & WS_SL_K2ONE) ? 1.0 : o.k2;
     ws_vm_exec_d<1, PP>(d, R, acc, rng, particle);
 }
 // register <- staging row K (the plane loads of this tile), and plane <- register for store K: the register numbers
