@@ -92,7 +92,12 @@ enum ws_tok_op {
     WS_TOK_TAN = 28,
     WS_TOK_ATAN = 29,
     WS_TOK_TANH = 30,
-    WS_TOK_FLOOR = 31
+    WS_TOK_FLOOR = 31,
+    /* variates with a parameter (unary: pop the parameter, push the draw), sampler expressions only:
+     * standard Gamma(shape) (Marsaglia-Tsang) and Poisson(rate) (inversion / PTRS) — the building blocks of the
+     * reference's Gamma, Beta, TDist, Chisq, InverseGamma, Poisson kernels (src/default_kernels.jl:83-102) */
+    WS_TOK_RANDGAMMA = 32,
+    WS_TOK_RANDPOISSON = 33
 };
 
 typedef struct ws_tok {
@@ -290,6 +295,9 @@ int ws_tape_enable(ws_ctx* ctx, int on);
 int ws_set_replay_normals(ws_ctx* ctx, const double* host, int64_t len);
 int ws_set_replay_uniforms(ws_ctx* ctx, const double* host, int64_t len);
 int ws_set_replay_exponentials(ws_ctx* ctx, const double* host, int64_t len);
+/* already-accepted variates of WS_TOK_RANDGAMMA / WS_TOK_RANDPOISSON draws (one per particle and draw, in statement
+ * order): standard Gamma(a_i) / Poisson(lam_i) values produced by the caller with the particle's own parameter */
+int ws_set_replay_variates(ws_ctx* ctx, const double* host, int64_t len);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 typedef struct ws_stats {

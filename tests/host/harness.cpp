@@ -24,8 +24,8 @@ struct HH {
     std::vector<double> logw;
     Program win, score;
     uint64_t next_stream = 1, seed = 0;
-    int64_t cur_n = 0, cur_u = 0, cur_e = 0;
-    std::vector<double> rn, ru, re;
+    int64_t cur_n = 0, cur_u = 0, cur_e = 0, cur_v = 0;
+    std::vector<double> rn, ru, re, rv;
     std::vector<int32_t> tape_end;
     std::vector<double> tape_const;  // Program::acc_const after each tape entry
     int n_flush = 0;
@@ -74,6 +74,7 @@ static void run_program(HH* h, Program& p, std::vector<double>* acc_out, int n_o
     rng.replay_n = h->rn.empty() ? nullptr : h->rn.data();
     rng.replay_u = h->ru.empty() ? nullptr : h->ru.data();
     rng.replay_e = h->re.empty() ? nullptr : h->re.data();
+    rng.replay_v = h->rv.empty() ? nullptr : h->rv.data();
     std::vector<double> R((size_t)std::max(1, p.high_water));
     for (int64_t i = 0; i < h->n; ++i) {
         for (auto& ld : p.loads) R[ld.second] = h->cols[ld.first.col][ld.first.comp][(size_t)i];
@@ -144,7 +145,7 @@ int hh_window_regs(HH* h) { return h->win.high_water; }
 int hh_window_loads(HH* h) { return (int)h->win.loads.size(); }
 int hh_window_stores(HH* h) { return (int)h->win.dirty.size(); }
 
-static wsl::RngCursor cursor(HH* h) { return wsl::RngCursor{&h->next_stream, &h->cur_n, &h->cur_u, &h->cur_e, h->n}; }
+static wsl::RngCursor cursor(HH* h) { return wsl::RngCursor{&h->next_stream, &h->cur_n, &h->cur_u, &h->cur_e, h->n, &h->cur_v}; }
 static int finish(HH* h, Program& p) {
     if (!p.error.empty()) {
         h->err = p.error;
@@ -290,7 +291,7 @@ int hh_score_device_order(HH* h, int n_entries, double* out, int* n_runs, int* n
     }
     WsRng none;
     none.seed = 0;
-    none.replay_n = none.replay_u = none.replay_e = nullptr;
+    none.replay_n = none.replay_u = none.replay_e = none.replay_v = nullptr;
     std::vector<double> R((size_t)rows);
     const double konst = n_entries <= 0 ? 0.0 : h->tape_const[(size_t)n_entries - 1];
     for (int64_t i = 0; i < h->n; ++i) {
@@ -333,6 +334,14 @@ void hh_exchange_plan(const int32_t* bnd, int R, int r, int64_t n_global, int64_
     t[5] = p.fits ? 1 : 0;
 }
 // Philox / Box-Muller / slot-count building blocks of ws_math.cuh
+void hh_set_replay_variates(HH* h, const double* v, int64_t nv) { h->rv.assign(v, v + nv); }
+// the rejection samplers of ws_math.cuh: n draws with particle = first + i
+void hh_rand_gamma(double a, uint64_t first, uint64_t stream, uint64_t seed, double* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = ws_rand_gamma(a, first + (uint64_t)i, stream, seed);
+}
+void hh_rand_poisson(double lam, uint64_t first, uint64_t stream, uint64_t seed, double* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = ws_rand_poisson(lam, first + (uint64_t)i, stream, seed);
+}
 void hh_randn2(uint64_t particle, uint64_t stream, uint64_t seed, double* out2) { ws_randn2(particle, stream, seed, out2[0], out2[1]); }
 void hh_philox(uint64_t particle, uint64_t stream, uint64_t seed, uint32_t* out4) {
     ws_u32x4 r = ws_philox4x32_10(particle, stream, seed);

@@ -35,6 +35,9 @@ def lib():
         L.hh_score.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_count_slots_le.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.hh_randn2.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.hh_set_replay_variates.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.hh_rand_gamma.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]
+        L.hh_rand_poisson.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]
         L.hh_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
         L.hh_importance_normal.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
         L.hh_sample_expr.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -105,8 +108,10 @@ class HostStore:
         self.L.hh_get_logw(self.h, out.ctypes.data_as(C.c_void_p))
         return out
 
-    def set_replay(self, normals=(), uniforms=(), exponentials=()):
+    def set_replay(self, normals=(), uniforms=(), exponentials=(), variates=()):
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (normals, uniforms, exponentials)]
+        v = np.ascontiguousarray(variates, dtype=np.float64)
+        self.L.hh_set_replay_variates(self.h, v.ctypes.data_as(C.c_void_p), v.size)
         self._keep = arrs
         self.L.hh_set_replay(self.h, arrs[0].ctypes.data_as(C.c_void_p), arrs[0].size,
                              arrs[1].ctypes.data_as(C.c_void_p), arrs[1].size,

@@ -75,6 +75,8 @@ CASES = [
     ("Gamma", (2.3, 1.6), sst.gamma(2.3, scale=1.6)),
     ("Beta", (2.0, 3.5), sst.beta(2.0, 3.5)),
     ("TDist", (4.5,), sst.t(4.5)),
+    ("Chisq", (3.7,), sst.chi2(3.7)),
+    ("InverseGamma", (3.2, 1.9), sst.invgamma(3.2, scale=1.9)),
 ]
 
 
@@ -112,7 +114,8 @@ def test_poisson_and_bernoulli_logpdf():
     np.testing.assert_allclose(hs2.store.logw(), sst.bernoulli(0.3).logpmf(hs.store.getcol("b")), rtol=1e-13)
 
 
-SAMPLERS = [c for c in CASES if c[0] not in ("Gamma", "Beta", "TDist")]
+REJECTION = ("Gamma", "Beta", "TDist", "Chisq", "InverseGamma")      # built on the device's Gamma variate
+SAMPLERS = [c for c in CASES if c[0] not in REJECTION]
 
 
 @pytest.mark.parametrize("name,args,dist", SAMPLERS, ids=[c[0] for c in SAMPLERS])
@@ -137,6 +140,121 @@ def test_samplers_replay_equals_oracle_and_philox_passes_ks(name, args, dist):
     # score!: the tape entry of the Sample is logpdf(args..., x)
     with np.errstate(all="ignore"):
         np.testing.assert_allclose(hp.store.score(1), dist.logpdf(hp.store.getcol("x")), rtol=1e-10, atol=1e-10)
+
+
+def _gamma_replay(name, args, n, rng):
+    """(normals, accepted variates) that reproduce `name(args...)` under replay, and the value they must give:
+    the device takes the standard Gamma(a_i) variate from the replay stream where it would run Marsaglia-Tsang."""
+    if name == "Gamma":
+        g = rng.gamma(args[0], size=n)
+        return (), g, args[1] * g
+    if name == "Chisq":
+        g = rng.gamma(args[0] / 2.0, size=n)
+        return (), g, 2.0 * g
+    if name == "InverseGamma":
+        g = rng.gamma(args[0], size=n)
+        return (), g, args[1] / g
+    if name == "Beta":            # 1 / (1 + Y / X): Y ~ Gamma(b) is drawn first, then X ~ Gamma(a)
+        y, x = rng.gamma(args[1], size=n), rng.gamma(args[0], size=n)
+        return (), np.concatenate([y, x]), 1.0 / (1.0 + y / x)
+    z, g = rng.standard_normal(n), rng.gamma(args[0] / 2.0, size=n)       # TDist: Z / sqrt(Chisq(v) / v)
+    return z, g, z / np.sqrt(2.0 * g / args[0])
+
+
+REJ_CASES = [c for c in CASES if c[0] in REJECTION]
+
+
+@pytest.mark.parametrize("name,args,dist", REJ_CASES, ids=[c[0] for c in REJ_CASES])
+def test_rejection_samplers_replay_philox_ks_and_symmetry(name, args, dist):
+    """src/default_kernels.jl:83-102 entries whose sampler needs a rejection loop: replayed accepted
+    variates reproduce the construction exactly (device lowering == oracle == closed form); under Philox the draws
+    pass a KS test against scipy for five seeds; and `x ~ D(...)` followed by score! gives logpdf(D, x) — the same
+    number `x => D(...)` adds to the weights (the `~` / `=>` symmetry of transformers.jl:172-182,228-235)."""
+    n = 20000
+    rng = np.random.default_rng(21)
+    normals, variates, want = _gamma_replay(name, args, n, rng)
+    step = ws.Sample("x", name, args)
+    hs = HostState(n)
+    hs.store.set_replay(normals=normals, variates=variates)
+    step.apply(hs)
+    np.testing.assert_allclose(hs.store.getcol("x"), want, rtol=1e-12)
+    ost = ref.OracleState(n, ref.Streams(normals=normals, variates=variates), ess_perc_min=0.0)
+    ost.expr_factory = ws.col
+    ref.run(ws.Sequence(step), ost)
+    np.testing.assert_allclose(hs.store.getcol("x"), ost.cols["x"], rtol=1e-12)
+    for seed in range(1, 6):
+        hp = HostState(n, seed=seed)
+        step.apply(hp)
+        x = hp.store.getcol("x")
+        assert np.all(np.isfinite(x))
+        assert sst.kstest(x, dist.cdf).pvalue > 1e-3 / 5, (name, seed)
+    with np.errstate(all="ignore"):
+        np.testing.assert_allclose(hp.store.score(1), dist.logpdf(x), rtol=1e-9, atol=1e-9)
+    ho = HostState(n)
+    ho.store.setcol("x", x)
+    ws.Observe(ws.col("x"), name, args).apply(ho)
+    np.testing.assert_allclose(ho.store.logw(), hp.store.score(1), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("a", [0.05, 0.4, 1.0, 2.5, 40.0, 3000.0])
+def test_gamma_variate_all_shapes(a):
+    """Marsaglia-Tsang for a >= 1 and the U^(1/a) boost below 1, through the host instantiation of csrc/ws_math.cuh"""
+    import ctypes as C
+    from hostlib import lib
+    n = 40000
+    for seed in (1, 2, 3):
+        out = np.empty(n)
+        lib().hh_rand_gamma(a, 0, 7, seed, out.ctypes.data_as(C.c_void_p), n)
+        assert np.all(out > 0) and np.all(np.isfinite(out))
+        assert sst.kstest(out, sst.gamma(a).cdf).pvalue > 1e-3 / 3, (a, seed)
+    out = np.empty(4)
+    lib().hh_rand_gamma(-1.0, 0, 7, 1, out.ctypes.data_as(C.c_void_p), 4)
+    assert np.all(np.isnan(out))
+
+
+@pytest.mark.parametrize("lam", [0.0, 0.3, 4.0, 9.99, 10.0, 37.5, 1200.0, 3e6])
+def test_poisson_variate_inversion_and_ptrs(lam):
+    """Poisson: sequential inversion below 10, PTRS (Hormann 1993) above; chi-square against the exact pmf"""
+    import ctypes as C
+    from hostlib import lib
+    n = 60000
+    out = np.empty(n)
+    lib().hh_rand_poisson(lam, 0, 11, 5, out.ctypes.data_as(C.c_void_p), n)
+    assert np.all(out >= 0) and np.all(out == np.floor(out))
+    if lam == 0.0:
+        assert np.all(out == 0)
+        return
+    assert abs(out.mean() - lam) < 5 * math.sqrt(lam / n) and abs(out.var() / lam - 1.0) < 0.05
+    lo, hi = int(max(0, lam - 4 * math.sqrt(lam))), int(lam + 4 * math.sqrt(lam)) + 1
+    edges = np.unique(np.linspace(lo, hi, 25).astype(int))
+    obs = np.histogram(out, bins=np.concatenate([[-0.5], edges + 0.5, [np.inf]]))[0]
+    cdf = sst.poisson(lam).cdf(edges)
+    exp = n * np.diff(np.concatenate([[0.0], cdf, [1.0]]))
+    keep = exp > 5
+    chi2 = float(np.sum((obs[keep] - exp[keep]) ** 2 / exp[keep]))
+    assert chi2 < sst.chi2(int(keep.sum()) - 1).ppf(1 - 1e-4), (lam, chi2)
+
+
+def test_poisson_kernel_sample_score_and_replay():
+    n = 20000
+    step = ws.Sample("k", "Poisson", (6.5,))
+    hp = HostState(n, seed=3)
+    step.apply(hp)
+    k = hp.store.getcol("k")
+    np.testing.assert_allclose(hp.store.score(1), sst.poisson(6.5).logpmf(k), rtol=1e-10)
+    assert abs(k.mean() - 6.5) < 0.1
+    kr = np.random.default_rng(2).poisson(6.5, n).astype(float)
+    hs = HostState(n)
+    hs.store.set_replay(variates=kr)
+    step.apply(hs)
+    np.testing.assert_array_equal(hs.store.getcol("k"), kr)
+    # a per-particle rate: lam_i = exp(z_i)
+    hv = HostState(n, seed=4)
+    hv.store.setcol("lam", np.linspace(0.1, 60.0, n))
+    ws.Sample("k", "Poisson", (ws.col("lam"),)).apply(hv)
+    kk, lam = hv.store.getcol("k"), np.linspace(0.1, 60.0, n)
+    zscore = (kk - lam) / np.sqrt(lam)
+    assert abs(zscore.mean()) < 0.03 and abs(zscore.var() - 1.0) < 0.05
 
 
 def test_fire_alarm_bayes_net_matches_oracle_and_exact_posterior():
@@ -232,6 +350,6 @@ def test_untraceable_closures_are_rejected_not_run_on_the_host():
     with pytest.raises(ws.UnsupportedModelError):
         ws.Sample("x", k, (ws.col("x") + 1.0,)).apply(hs)   # math.exp on a particle expression
     with pytest.raises(ws.UnsupportedModelError):
-        ws.Sample("y", "Gamma", (2.0, 1.0)).apply(hs)        # density-only kernel: no sampler
+        ws.Sample("y", "Wishart", (2.0, 1.0)).apply(hs)      # in the reference's table, outside the device-op set
     with pytest.raises(RuntimeError):
         ws.Observe(ws.col("x") + ws.randn(), "Normal", (0.0, 1.0)).apply(hs)  # variates outside a sampler

@@ -34,7 +34,8 @@ RESAMPLER = {"stratified": 0, "systematic": 1, "multinomial": 2}
 # enum ws_tok_op
 TOK_CONST, TOK_PLANE, TOK_ADD, TOK_SUB, TOK_MUL, TOK_DIV, TOK_NEG, TOK_EXP, TOK_LOG, TOK_SQRT, TOK_SQUARE, \
     TOK_SIN, TOK_COS, TOK_ABS, TOK_POW, TOK_RANDN, TOK_RANDU, TOK_RANDEXP, TOK_LT, TOK_LE, TOK_EQ, TOK_SELECT, TOK_MIN, \
-    TOK_MAX, TOK_NOT, TOK_LGAMMA, TOK_LOG1P, TOK_EXPM1, TOK_TAN, TOK_ATAN, TOK_TANH, TOK_FLOOR = range(32)
+    TOK_MAX, TOK_NOT, TOK_LGAMMA, TOK_LOG1P, TOK_EXPM1, TOK_TAN, TOK_ATAN, TOK_TANH, TOK_FLOOR, TOK_RANDGAMMA, \
+    TOK_RANDPOISSON = range(34)
 
 
 class ws_plane_stats(C.Structure):
@@ -147,6 +148,7 @@ SIGNATURES = {
     "ws_set_replay_normals": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "ws_set_replay_uniforms": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "ws_set_replay_exponentials": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
+    "ws_set_replay_variates": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "ws_get_stats": (C.c_int, [_ctx, C.POINTER(ws_stats)]),
     "ws_get_clamped": (C.c_int, [_ctx, _i64p]),
     "ws_kernel_times": (C.c_int, [_ctx, _dp, _i64p, C.c_int32]),

@@ -275,9 +275,9 @@ class SMCState:
         self.store._call("ws_sync")
 
     # replay hooks (parity tests) -------------------------------------------------------------------
-    def set_replay(self, normals=None, uniforms=None, exponentials=None):
+    def set_replay(self, normals=None, uniforms=None, exponentials=None, variates=None):
         for arr, fn in ((normals, "ws_set_replay_normals"), (uniforms, "ws_set_replay_uniforms"),
-                        (exponentials, "ws_set_replay_exponentials")):
+                        (exponentials, "ws_set_replay_exponentials"), (variates, "ws_set_replay_variates")):
             if arr is None:
                 self.store._call(fn, None, 0)
             else:
@@ -521,6 +521,13 @@ def importance_kernel(proposal, target):
     return _ImportanceNormal(proposal.mu, proposal.sigma, target.mu, target.sigma)
 
 
+def _beta_sampler(a, b):
+    from . import expr as E
+    # X / (X + Y) with each variate appearing ONCE (an expression is a tree: a node used twice would be drawn twice);
+    # evaluation order, hence replay order: Y ~ Gamma(b) first, then X ~ Gamma(a)
+    return 1.0 / (1.0 + E.randgamma(b) / E.randgamma(a))
+
+
 def _expr_kernels():
     """Distributions whose sampler is a closed-form transform of one standard variate, written as device
     expressions (formulas: Distributions.jl 0.25 `rand` / `logpdf`, un-vendored; pinned by scipy.stats in the tests)."""
@@ -550,15 +557,24 @@ def _expr_kernels():
                                   "Weibull")
     k["Pareto"] = WeightedKernel(lambda a, t: t * E.exp(E.randexp() / a), None,
                                  lambda a, t, x: E.where(x >= t, E.log(a) + a * E.log(t) - (a + 1.0) * E.log(x), NEG_INF), "Pareto")
-    # no closed-form one-variate sampler: density only (usable with `=>` and `_ ~`)
-    k["Gamma"] = WeightedKernel(None, None, lambda a, t, x: E.where(x >= 0.0, (a - 1.0) * E.log(x) - x / t - E.lgamma(a) - a * E.log(t),
+    # samplers that need a rejection loop: device variates with a parameter (expr.randgamma / randpoisson: Marsaglia-Tsang
+    # and inversion / PTRS on Philox sub-counters, csrc/ws_math.cuh); the constructions are Distributions.jl's own
+    # (Beta = X / (X + Y) from two Gammas, TDist = Z / sqrt(Chisq(v) / v), Chisq(v) = Gamma(v / 2, 2), InverseGamma = 1 / Gamma)
+    k["Gamma"] = WeightedKernel(lambda a, t: t * E.randgamma(a), None, lambda a, t, x: E.where(x >= 0.0, (a - 1.0) * E.log(x) - x / t - E.lgamma(a) - a * E.log(t),
                                                                      NEG_INF), "Gamma")
-    k["Beta"] = WeightedKernel(None, None, lambda a, b, x: E.where((x >= 0.0) & (x <= 1.0),
+    k["Beta"] = WeightedKernel(_beta_sampler, None, lambda a, b, x: E.where((x >= 0.0) & (x <= 1.0),
                                                                     (a - 1.0) * E.log(x) + (b - 1.0) * E.log1p(-x)
                                                                     - (E.lgamma(a) + E.lgamma(b) - E.lgamma(a + b)), NEG_INF), "Beta")
-    k["TDist"] = WeightedKernel(None, None, lambda v, x: E.lgamma((v + 1.0) / 2.0) - E.lgamma(v / 2.0) - 0.5 * E.log(v * math.pi)
+    k["TDist"] = WeightedKernel(lambda v: E.randn() / E.sqrt(2.0 * E.randgamma(v / 2.0) / v), None, lambda v, x: E.lgamma((v + 1.0) / 2.0) - E.lgamma(v / 2.0) - 0.5 * E.log(v * math.pi)
                                 - (v + 1.0) / 2.0 * E.log1p(x * x / v), "TDist")
-    k["Poisson"] = WeightedKernel(None, None, lambda lam, x: x * E.log(lam) - lam - E.lgamma(x + 1.0), "Poisson")
+    k["Poisson"] = WeightedKernel(lambda lam: E.randpoisson(lam), None,
+                                  lambda lam, x: E.where(x >= 0.0, x * E.log(lam) - lam - E.lgamma(x + 1.0), NEG_INF), "Poisson")
+    k["Chisq"] = WeightedKernel(lambda v: 2.0 * E.randgamma(v / 2.0), None,
+                                lambda v, x: E.where(x >= 0.0, (v / 2.0 - 1.0) * E.log(x) - x / 2.0 - E.lgamma(v / 2.0) - (v / 2.0) * LOG2,
+                                                     NEG_INF), "Chisq")
+    k["InverseGamma"] = WeightedKernel(lambda a, t: t / E.randgamma(a), None,
+                                       lambda a, t, x: E.where(x > 0.0, a * E.log(t) - E.lgamma(a) - (a + 1.0) * E.log(x) - t / x, NEG_INF),
+                                       "InverseGamma")
     return k
 
 

@@ -57,6 +57,7 @@ __device__ __forceinline__ void ws_score_fold(const WsScoreParams& S, double* R,
     none.replay_n = nullptr;
     none.replay_u = nullptr;
     none.replay_e = nullptr;
+    none.replay_v = nullptr;
     __shared__ unsigned int cont_mask[WS_FOLD_CHUNK / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < S.n_ops; base += WS_FOLD_CHUNK) {

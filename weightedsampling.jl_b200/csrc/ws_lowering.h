@@ -45,6 +45,7 @@ struct RngCursor {
     int64_t* uniforms;
     int64_t* exponentials;
     int64_t n_global;     // particles (global): one statement consumes n_global * d variates
+    int64_t* variates = nullptr;  // replay cursor of the WS_OP_RANDV ops (accepted Gamma / Poisson variates)
 };
 
 // One fusion window (or the persistent score program): micro-ops + register allocation.
@@ -353,6 +354,26 @@ struct Program {
         return Val::lin(0.0, 1.0, t);
     }
 
+    // Gamma(shape) / Poisson(rate) variate with a per-particle or constant parameter (WS_OP_RANDV)
+    Val variate_param(uint32_t kind, const Val& a) {
+        if (score_mode || rng == nullptr) {
+            fail("random variates are only allowed in a sampler expression");
+            return Val::constant(NAN);
+        }
+        const int ra = a.is_const ? (int)WS_REG_NONE : materialize(a);
+        int t = alloc_temp();
+        const uint64_t stream = (*rng->stream)++;
+        double sbits;
+        memcpy(&sbits, &stream, 8);
+        int64_t base = 0;
+        if (rng->variates != nullptr) {
+            base = *rng->variates;
+            *rng->variates += rng->n_global;
+        }
+        emit(ws_make_op(WS_OP_RANDV, t, ra, WS_REG_NONE, WS_REG_NONE, kind, sbits, (double)base, a.is_const ? a.c0 : 0.0));
+        return Val::lin(0.0, 1.0, t);
+    }
+
     // postfix tokens -> Val
     Val compile(const ws_expr& e) {
         std::vector<Val> st;
@@ -408,6 +429,16 @@ struct Program {
                     else if (t.op == WS_TOK_MAX) r = minmax(1, a, b);
                     else r = power(a, b);
                     st.push_back(r);
+                } break;
+                case WS_TOK_RANDGAMMA:
+                case WS_TOK_RANDPOISSON: {
+                    if (st.empty()) {
+                        fail("malformed expression (variate needs its parameter)");
+                        return Val::constant(NAN);
+                    }
+                    Val a = st.back();
+                    st.pop_back();
+                    st.push_back(variate_param(t.op == WS_TOK_RANDGAMMA ? 0u : 1u, a));
                 } break;
                 case WS_TOK_NEG:
                 case WS_TOK_EXP:

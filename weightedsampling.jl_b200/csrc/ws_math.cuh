@@ -372,6 +372,81 @@ WS_HD double ws_randexp(uint64_t particle, uint64_t stream, uint64_t seed) {
     return -ws_log_pos((double)v, -53);
 }
 
+
+// ---------------------------------------------------------------------------
+// Variates that need a rejection loop (the reference draws them with Distributions.jl's samplers,
+// src/default_kernels.jl:83-102: Gamma, and through it Beta, TDist, Chisq, InverseGamma; Poisson).  Trial t of a
+// particle takes Philox blocks (particle, stream | (2t) << 40) and (particle, stream | (2t+1) << 40): counters, not
+// state, so a draw does not depend on what other threads do, and stream ids stay below 2^40.
+// ---------------------------------------------------------------------------
+#define WS_TRIAL_SHIFT 40
+#define WS_MAX_TRIALS 64
+WS_HD uint64_t ws_trial_stream(uint64_t stream, uint32_t k) { return stream | ((uint64_t)(k + 1u) << WS_TRIAL_SHIFT); }
+
+// Standard Gamma(shape a > 0, scale 1): Marsaglia & Tsang (2000): d = a - 1/3, c = 1/sqrt(9 d), v = (1 + c z)^3,
+// accept if log u < z^2/2 + d - d v + d log v; a < 1 through Gamma(a + 1) U^(1/a).  a <= 0 or NaN gives NaN.
+WS_HD double ws_rand_gamma(double a, uint64_t particle, uint64_t stream, uint64_t seed) {
+    if (!(a > 0.0)) return NAN;
+    const bool boost = a < 1.0;
+    const double aa = boost ? a + 1.0 : a;
+    const double d = aa - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    double g = d;  // (returned only if WS_MAX_TRIALS trials in a row are rejected: probability < 1e-80)
+    double u_boost = 0.5;
+    for (uint32_t t = 0; t < WS_MAX_TRIALS; ++t) {
+        double z, z1, u, u1;
+        ws_randn2(particle, ws_trial_stream(stream, 2u * t), seed, z, z1);
+        const ws_u32x4 r = ws_philox4x32_10(particle, ws_trial_stream(stream, 2u * t + 1u), seed);
+        u = ws_u01_open0(r.x, r.y);
+        u1 = ws_u01_open0(r.z, r.w);
+        const double w = 1.0 + c * z;
+        if (w <= 0.0) continue;
+        const double v = w * w * w;
+        if (log(u) < 0.5 * z * z + d - d * v + d * log(v)) {
+            g = d * v;
+            u_boost = u1;
+            break;
+        }
+    }
+    return boost ? g * pow(u_boost, 1.0 / a) : g;
+}
+
+// Poisson(lam >= 0): inversion by sequential search for lam < 10, PTRS (Hormann 1993, "The transformed rejection
+// method for generating Poisson random variables") otherwise.  lam < 0 or NaN gives NaN.
+WS_HD double ws_rand_poisson(double lam, uint64_t particle, uint64_t stream, uint64_t seed) {
+    if (!(lam >= 0.0)) return NAN;
+    if (lam == 0.0) return 0.0;
+    if (lam < 10.0) {
+        const ws_u32x4 r = ws_philox4x32_10(particle, ws_trial_stream(stream, 0u), seed);
+        const double u = ws_u01(r.x, r.y);
+        double p = exp(-lam), F = p;
+        int k = 0;
+        while (u > F && k < 200) {
+            ++k;
+            p *= lam / (double)k;
+            F += p;
+        }
+        return (double)k;
+    }
+    const double slam = sqrt(lam), loglam = log(lam);
+    const double b = 0.931 + 2.53 * slam;
+    const double a = -0.059 + 0.02483 * b;
+    const double inv_alpha = 1.1239 + 1.1328 / (b - 3.4);
+    const double vr = 0.9277 - 3.6224 / (b - 2.0);
+    double k = floor(lam);
+    for (uint32_t t = 0; t < WS_MAX_TRIALS; ++t) {
+        const ws_u32x4 r = ws_philox4x32_10(particle, ws_trial_stream(stream, t), seed);
+        const double U = ws_u01(r.x, r.y) - 0.5;
+        const double V = ws_u01_open0(r.z, r.w);
+        const double us = 0.5 - fabs(U);
+        k = floor((2.0 * a / us + b) * U + lam + 0.43);
+        if (us >= 0.07 && V <= vr) break;
+        if (k < 0.0 || (us < 0.013 && V > us)) continue;
+        if (log(V) + log(inv_alpha) - log(a / (us * us) + b) <= -lam + k * loglam - lgamma(k + 1.0)) break;
+    }
+    return k < 0.0 ? 0.0 : k;
+}
+
 // ---------------------------------------------------------------------------
 // log densities
 // ---------------------------------------------------------------------------

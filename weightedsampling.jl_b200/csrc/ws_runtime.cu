@@ -179,12 +179,17 @@ struct ws_ctx {
     // yet, i.e. the log-weights are "all equal to d_red->log_mean_w if it fired, else the array as it is".
     static constexpr int SPEC_RING = 512;
     WsReduceOut* h_ring = nullptr;  // pinned [SPEC_RING]
+    int64_t ring_event[SPEC_RING] = {0};  // resampling event booked for each record
     int64_t spec_head = 0;          // records [spec_head - spec_pending, spec_head) are unresolved
     int spec_pending = 0;
     bool logw_spec = false;
     bool async_resample = true;     // env WSB200_ASYNC_RESAMPLE=0: ws_resample_async behaves like ws_resample
     ws_resample_info last_info{};   // outcome of the most recent Resample step (ws_last_resample)
     bool last_info_pending = false; // ... which is the newest unresolved record
+    // A model that reads `resampled` after every step (`if resampled ... end`, examples/linear_regression.jl:22)
+    // waits for each decision anyway; queueing the step then only adds the gated launches and a resampling event
+    // per non-firing step.  Two steps in a row resolved before anything else was queued switch the run to ws_resample.
+    int spec_immediate = 0;
 
     // resampling scratch
     int32_t* d_anc = nullptr;  // ancestors of the latest resampling event (== anc_live.back().ptr)
@@ -194,6 +199,7 @@ struct ws_ctx {
     struct AncVec {
         int64_t event;  // maps slots of epoch `event` to slots of epoch `event - 1`
         int32_t* ptr;
+        bool identity = false;  // a queued step that turned out not to fire (resolve_spec): the map is the identity
     };
     int64_t epoch = 0;                // resampling events so far
     std::deque<AncVec> anc_live;      // vectors some plane may still need, ascending events
@@ -234,6 +240,8 @@ struct ws_ctx {
     double* d_replay_n = nullptr;
     double* d_replay_u = nullptr;
     double* d_replay_e = nullptr;
+    double* d_replay_v = nullptr;
+    int64_t replay_v_len = 0, cur_v = 0;
     int64_t replay_n_len = 0, replay_u_len = 0, replay_e_len = 0;
     int64_t cur_n = 0, cur_u = 0, cur_e = 0;
 
@@ -651,6 +659,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_replay_n);
     cudaFree(c->d_replay_u);
     cudaFree(c->d_replay_e);
+    cudaFree(c->d_replay_v);
     cudaFree(c->d_scratch);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
     for (auto& te : c->pending_events) {
@@ -754,6 +763,7 @@ static int flush_window(ws_ctx* c) {
     P.rng.replay_n = c->d_replay_n;
     P.rng.replay_u = c->d_replay_u;
     P.rng.replay_e = c->d_replay_e;
+    P.rng.replay_v = c->d_replay_v;
     memcpy(P.ops, w.ops.data(), sizeof(WsOp) * w.ops.size());
 
     const int sl_grid = ws_vm_sl_grid(P);  // straight-line executor (ws_vm_sl.cuh): it sizes its own grid
@@ -799,7 +809,7 @@ static int lower_statement(ws_ctx* c, F body) {
     for (int attempt = 0; attempt < 2; ++attempt) {
         Program snapshot = c->win;
         const uint64_t s_stream = c->next_stream;
-        const int64_t s_n = c->cur_n, s_u = c->cur_u, s_e = c->cur_e;
+        const int64_t s_n = c->cur_n, s_u = c->cur_u, s_e = c->cur_e, s_v = c->cur_v;
         body(c->win);
         if (!c->win.error.empty()) {
             std::string m = c->win.error;
@@ -808,6 +818,8 @@ static int lower_statement(ws_ctx* c, F body) {
             c->cur_n = s_n;
             c->cur_u = s_u;
             c->cur_e = s_e;
+        c->cur_v = s_v;
+            c->cur_v = s_v;
             return fail(c, WS_EINVAL, "%s", m.c_str());
         }
         if (!c->win.overflow) {
@@ -819,6 +831,7 @@ static int lower_statement(ws_ctx* c, F body) {
         c->cur_n = s_n;
         c->cur_u = s_u;
         c->cur_e = s_e;
+        c->cur_v = s_v;
         if (attempt == 1 || (snapshot.ops.empty() && snapshot.dirty.empty()))
             return fail(c, WS_EUNSUPPORTED, "statement does not fit one device pass (more than %d micro-ops, %d planes or %d registers)",
                         WS_VM_MAX_OPS, WS_VM_MAX_IO, WS_VM_MAX_REGS);
@@ -866,7 +879,7 @@ static int allreduce_host_doubles(ws_ctx* c, double* v, int n) {
 }
 
 static wsl::RngCursor rng_cursor(ws_ctx* c) {
-    return wsl::RngCursor{&c->next_stream, &c->cur_n, &c->cur_u, &c->cur_e, c->n_global};
+    return wsl::RngCursor{&c->next_stream, &c->cur_n, &c->cur_u, &c->cur_e, c->n_global, &c->cur_v};
 }
 
 static int check_replay(ws_ctx* c) {
@@ -874,6 +887,8 @@ static int check_replay(ws_ctx* c) {
         return fail(c, WS_EREPLAY, "replay normals exhausted (%lld needed, %lld installed)", (long long)c->cur_n, (long long)c->replay_n_len);
     if (c->d_replay_e != nullptr && c->cur_e > c->replay_e_len)
         return fail(c, WS_EREPLAY, "replay exponentials exhausted (%lld needed, %lld installed)", (long long)c->cur_e, (long long)c->replay_e_len);
+    if (c->d_replay_v != nullptr && c->cur_v > c->replay_v_len)
+        return fail(c, WS_EREPLAY, "replay variates exhausted (%lld needed, %lld installed)", (long long)c->cur_v, (long long)c->replay_v_len);
     if (c->d_replay_u != nullptr && c->cur_u > c->replay_u_len)
         return fail(c, WS_EREPLAY, "replay uniforms exhausted (%lld needed, %lld installed)", (long long)c->cur_u, (long long)c->replay_u_len);
     return WS_OK;
@@ -923,6 +938,7 @@ extern "C" int ws_begin_run(ws_ctx* c) {
     if (!c) return WS_EINVAL;
     TRY(flush_window(c));
     c->depth = 0;
+    c->spec_immediate = 0;
     reset_score(c);
     return WS_OK;
 }
@@ -1307,6 +1323,7 @@ extern "C" int ws_sample_importance_normal(ws_ctx* c, int32_t col, int32_t comp,
 // (ws_resample_async): wait for the stream, read their records from the pinned ring in order.
 static int resolve_spec(ws_ctx* c) {
     if (c->spec_pending == 0) return WS_OK;
+    c->spec_immediate = (c->spec_pending == 1 && c->logw_spec) ? c->spec_immediate + 1 : 0;
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut) * c->spec_pending;
@@ -1318,6 +1335,8 @@ static int resolve_spec(ws_ctx* c) {
             c->stats.resamples_done++;
         } else {
             c->resampled = false;
+            for (auto& v : c->anc_live)  // reads of planes that are behind this event skip it from now on
+                if (v.event == c->ring_event[k % ws_ctx::SPEC_RING]) v.identity = true;
         }
     }
     c->spec_pending = 0;
@@ -1423,6 +1442,13 @@ static const int32_t* anc_of_event(const ws_ctx* c, int64_t event) {
 static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out) {
     *out = nullptr;
     if (ep >= c->epoch) return WS_OK;
+    auto is_identity = [&](int64_t event) {
+        for (auto& v : c->anc_live)
+            if (v.event == event) return v.identity;
+        return false;
+    };
+    while (ep < c->epoch && is_identity(ep + 1)) ++ep;  // leading identity events: the plane is effectively newer
+    if (ep >= c->epoch) return WS_OK;
     if (ep == c->epoch - 1) {
         *out = c->d_anc;
         return WS_OK;
@@ -1445,8 +1471,13 @@ static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out) {
         while (from > ep && P.n_chain < WS_COMPOSE_MAX_CHAIN) {
             const int32_t* a = anc_of_event(c, from);
             if (a == nullptr) return fail(c, WS_EINVAL, "genealogy: ancestors of event %lld were released", (long long)from);
-            P.chain[P.n_chain++] = a;
+            if (!is_identity(from)) P.chain[P.n_chain++] = a;
             --from;
+        }
+        if (P.n_chain == 0 && start == nullptr) {  // nothing but identities so far: keep walking, or the map is the identity
+            if (from > ep) continue;
+            c->map_E = -1;
+            return WS_OK;
         }
         CK(c, ws_launch_compose(P, c->d_map, start, c->stream));
         c->stats.kernel_launches++;
@@ -2116,7 +2147,7 @@ extern "C" int ws_resample_async(ws_ctx* c) {
         return WS_OK;
     }
     if (!c->async_resample || c->d_replay_u != nullptr || c->nranks > 1 || c->resampler == WS_RESAMPLER_MULTINOMIAL ||
-        !c->lazy_gather || c->cols.empty())
+        !c->lazy_gather || c->cols.empty() || c->spec_immediate >= 2)
         return ws_resample(c, nullptr);
     TRY(flush_window(c));
     if (c->red_valid || c->logw_uniform || c->logw_spec) return ws_resample(c, nullptr);  // nothing new was weighted on the device
@@ -2136,6 +2167,7 @@ extern "C" int ws_resample_async(ws_ctx* c) {
     CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream));
     timed_end(c, te);
     CK(c, cudaMemcpyAsync(&c->h_ring[c->spec_head % ws_ctx::SPEC_RING], c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
+    c->ring_event[c->spec_head % ws_ctx::SPEC_RING] = c->epoch + 1;
     c->spec_head++;
     c->spec_pending++;
     c->stats.resamples_fired++;
@@ -2528,6 +2560,10 @@ extern "C" int ws_set_replay_normals(ws_ctx* c, const double* host, int64_t len)
 extern "C" int ws_set_replay_uniforms(ws_ctx* c, const double* host, int64_t len) {
     if (!c) return WS_EINVAL;
     return set_replay(c, &c->d_replay_u, &c->replay_u_len, &c->cur_u, host, len);
+}
+extern "C" int ws_set_replay_variates(ws_ctx* c, const double* host, int64_t len) {
+    if (!c) return WS_EINVAL;
+    return set_replay(c, &c->d_replay_v, &c->replay_v_len, &c->cur_v, host, len);
 }
 extern "C" int ws_set_replay_exponentials(ws_ctx* c, const double* host, int64_t len) {
     if (!c) return WS_EINVAL;
@@ -2943,6 +2979,7 @@ extern "C" int ws_move(ws_ctx* c, const ws_move_spec* spec, ws_move_info* info) 
     M.rng.replay_n = c->d_replay_n;
     M.rng.replay_u = c->d_replay_u;
     M.rng.replay_e = nullptr;
+    M.rng.replay_v = nullptr;
     M.stream_normals = c->next_stream;
     c->next_stream += (uint64_t)((d + 1) / 2);
     M.stream_uniform = c->next_stream++;

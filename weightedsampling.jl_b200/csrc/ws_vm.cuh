@@ -38,6 +38,9 @@ enum WsOpCode : uint32_t {
     ,
     WS_OP_ACC_SQLIN2_S = 18  // acc -= ((k0 + k1*r[a] + k2*r[b]) * r[c])^2 / 2 + r[dst]: the same with a per-particle sigma
                              // whose reciprocal r[c] and logarithm r[dst] were computed once per fold (score tapes)
+    ,
+    WS_OP_RANDV = 19  // r[dst] = variate with a parameter A = a==NONE ? k2 : r[a];  imm: 0 standard Gamma(shape A),
+                      // 1 Poisson(A).  k0 = Philox stream; replay: r[dst] = replay_v[(int64)k1 + particle]
 };
 
 enum WsUnary : uint32_t {
@@ -92,6 +95,7 @@ struct WsRng {
     const double* replay_n;  // standard normals or nullptr
     const double* replay_u;  // uniforms or nullptr
     const double* replay_e;  // standard exponentials or nullptr
+    const double* replay_v;  // already-accepted variates of the WS_OP_RANDV ops (standard Gamma(a_i) / Poisson(lam_i)) or nullptr
 };
 
 WS_HD uint64_t ws_double_bits(double v) {
@@ -289,6 +293,20 @@ WS_HD void ws_vm_exec_d(const WsDop& o, double* __restrict__ R, double (&acc)[P]
                     ws_randu2(particle[j], ws_double_bits(k0), rng.seed, u, u1);
                 }
                 Rd[j * STRIDE] = u;
+            }
+        } break;
+        case WS_OP_RANDV: {
+#pragma unroll 1
+            for (int j = 0; j < P; ++j) {
+                double v;
+                if (rng.replay_v != nullptr) {
+                    v = rng.replay_v[(int64_t)k1 + (int64_t)particle[j]];
+                } else {
+                    const double A = (a == WS_OFF_NONE) ? k2 : Ra[j * STRIDE];
+                    v = (imm == 0u) ? ws_rand_gamma(A, particle[j], ws_double_bits(k0), rng.seed)
+                                    : ws_rand_poisson(A, particle[j], ws_double_bits(k0), rng.seed);
+                }
+                Rd[j * STRIDE] = v;
             }
         } break;
         case WS_OP_LOGPDF_NORMAL: {

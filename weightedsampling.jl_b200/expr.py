@@ -109,6 +109,16 @@ class Rand(Expr):
         self.kind = kind
 
 
+class RandP(Expr):
+    """A variate with a (per-particle) parameter inside a sampler expression: kind 'gamma' = standard
+    Gamma(shape), 'poisson' = Poisson(rate) (device rejection samplers on Philox sub-counters)."""
+
+    def __init__(self, kind, arg):
+        self.kind, self.arg = kind, wrap(arg)
+
+
+def randgamma(shape): return RandP("gamma", shape)
+def randpoisson(rate): return RandP("poisson", rate)
 def randn(): return Rand("n")
 def randu(): return Rand("u")
 def randexp(): return Rand("e")
@@ -237,6 +247,11 @@ def lower(e, store):
         return base[e.j]
     if isinstance(e, Rand):
         return Tokens([({"n": L.TOK_RANDN, "u": L.TOK_RANDU, "e": L.TOK_RANDEXP}[e.kind], 0, 0, 0.0)])
+    if isinstance(e, RandP):
+        a = lower(e.arg, store)
+        if isinstance(a, list):
+            raise _unsupported("vector-valued distribution parameters are outside the device-op set")
+        return Tokens(a.toks + [({"gamma": L.TOK_RANDGAMMA, "poisson": L.TOK_RANDPOISSON}[e.kind], 0, 0, 0.0)])
     if isinstance(e, Select):
         c, a, b = lower(e.cond, store), lower(e.a, store), lower(e.b, store)
         if isinstance(c, list) or isinstance(a, list) or isinstance(b, list):
