@@ -45,7 +45,29 @@ def run_case(root, n, n_normals, n_uniforms, n_expon=0, ess=0.5, seed=1):
     return out
 
 
+def abi_smoke_fixture(path):
+    """inputs and expected outputs of tests/host/abi_smoke.c (a plain C consumer of include/wsb200.h), little-endian:
+    int64 n, T, n_normals, n_uniforms | doubles a q r x0_std step ess_perc_min | obs[T] | normals | uniforms |
+    log_evidence | x[n] | weights[n] | int64 resamples, accepted, depth"""
+    from oracle.trees import Move, RW
+    n, T = 512, 6
+    a, q, r, x0, step, ess = 0.9, 1.0, 0.5, 1.0, 0.3, 1.0
+    rng = np.random.default_rng(31)
+    obs = rng.standard_normal(T)
+    normals, uniforms = rng.standard_normal(n * (T + 2)), rng.random(n * (T + 1))
+    root = om.lgssm1d(list(obs), a, q, r, x0, tail=(Move(["x"], RW, (step,)),))
+    st = ref.OracleState(n, ref.Streams(normals, uniforms), ess_perc_min=ess)
+    ref.run(root, st)
+    with open(path, "wb") as f:
+        np.array([n, T, normals.size, uniforms.size], dtype="<i8").tofile(f)
+        np.array([a, q, r, x0, step, ess], dtype="<f8").tofile(f)
+        for arr in (obs, normals, uniforms, [ref.log_evidence(st)], st.cols["x"], st.weights):
+            np.asarray(arr, dtype="<f8").tofile(f)
+        np.array([sum(e["resampled"] for e in st.log), int(st.last_accept.sum()), st.depth], dtype="<i8").tofile(f)
+
+
 def main():
+    abi_smoke_fixture(os.path.join(HERE, "abi_smoke.bin"))
     np.savez_compressed(os.path.join(HERE, "resampling.npz"), **resampling_case())
     rng = np.random.default_rng(7)
     obs1 = np.cumsum(rng.standard_normal(12)) * 1.5

@@ -47,3 +47,37 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not pat.search(txt), f
+
+
+def _build_abi_smoke(tmp_path):
+    """tests/host/abi_smoke.c: plain C99 against include/wsb200.h and libwsb200.so only"""
+    import subprocess
+    exe = os.path.join(str(tmp_path), "abi_smoke")
+    libdir = os.path.join(ROOT, "weightedsampling.jl_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "host", "abi_smoke.c"), "-L" + libdir, "-lwsb200", "-lm",
+                    "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    return exe
+
+
+def test_header_is_self_sufficient_for_a_plain_c_consumer(tmp_path):
+    """the header compiles as C99 with -Wall -Wextra -Werror and links against the library: everything a binding
+    needs (types, enums, prototypes) is in include/wsb200.h.  Without a GPU the program must fail loudly."""
+    import subprocess
+    exe = _build_abi_smoke(tmp_path)
+    fixture = os.path.join(ROOT, "tests", "golden", "abi_smoke.bin")
+    p = subprocess.run([exe, fixture], capture_output=True, text=True)
+    if p.returncode != 0:
+        assert p.returncode == 2 and "no CUDA device" in p.stderr, (p.returncode, p.stdout, p.stderr)
+
+
+@pytest.mark.gpu
+def test_plain_c_consumer_reproduces_the_oracle(tmp_path):
+    """LGSSM + Resample every step + a RW move through the C ABI from C, on replayed streams, against the numbers the
+    oracle's hand-built program wrote (tests/golden/make_golden.py: abi_smoke_fixture)."""
+    import subprocess
+    exe = _build_abi_smoke(tmp_path)
+    p = subprocess.run([exe, os.path.join(ROOT, "tests", "golden", "abi_smoke.bin")], capture_output=True, text=True)
+    print(p.stdout, p.stderr)
+    assert p.returncode == 0, (p.stdout, p.stderr)
+    assert "mismatching values 0" in p.stdout
