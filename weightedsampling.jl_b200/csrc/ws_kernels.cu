@@ -1582,7 +1582,7 @@ cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t
 // map composed earlier.  One dependent 4-byte load per event and particle, instead of gathering every
 // column at every event as the reference's resample! does (src/stores.jl:105-121).
 template <class I>
-__global__ void __launch_bounds__(256) ws_compose_kernel(const WsComposeParams P, I* __restrict__ out, const I* __restrict__ start) {
+__global__ void __launch_bounds__(256) ws_compose_kernel(const WsComposeParams P, I* out, const I* start) {  // (out may alias start: element-wise)
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < P.n; i += stride) {
         int64_t idx = start != nullptr ? (int64_t)start[i] : i;

@@ -2490,13 +2490,18 @@ extern "C" int ws_col_download_rows(ws_ctx* c, int32_t id, const int64_t* indice
     return WS_OK;
 }
 
-// sample(state, n; replace): indices drawn with probability exp_norm(weights).  With replacement the
-// draw is n sorted Philox uniforms pushed through the same scan+search kernel (multinomial);
-// without replacement it is the Efraimidis-Spirakis exponential-key selection done on the host
-// over the downloaded normalised weights (n <= N draws; analysis path, not the hot path).
+// sample(state, n; replace) (src/utils.jl:102-118): n indices drawn with probability exp_norm(weights).  An analysis
+// call, not the hot path: the normalised weights are downloaded once and the draw is made on the host — with
+// replacement by inverting the sequential CDF at n Philox uniforms, without replacement by the Efraimidis-Spirakis
+// exponential-key selection.  Single-GPU states only: on a sharded state the indices would have to name (rank, row)
+// pairs of the GLOBAL posterior, which this interface cannot express, so the call is rejected instead of silently
+// sampling the local shard.
 extern "C" int ws_sample_indices(ws_ctx* c, int64_t n_draws, int replace, int64_t* indices_out) {
     if (!c || !indices_out) return WS_EINVAL;
     if (n_draws <= 0) return fail(c, WS_EINVAL, "Number of samples must be positive");
+    if (c->nranks > 1)
+        return fail(c, WS_EUNSUPPORTED, "sample(state, n) on a sharded state: local row indices cannot describe a draw from the global "
+                                        "posterior (use ws_expectation / ws_describe, or download the shards)");
     if (!replace && n_draws > c->n) return fail(c, WS_EINVAL, "Cannot sample %lld particles without replacement from %lld particles", (long long)n_draws, (long long)c->n);
     std::vector<double> w((size_t)c->n);
     TRY(ws_exp_norm(c, w.data()));
