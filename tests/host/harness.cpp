@@ -342,6 +342,10 @@ void hh_rand_gamma(double a, uint64_t first, uint64_t stream, uint64_t seed, dou
 void hh_rand_poisson(double lam, uint64_t first, uint64_t stream, uint64_t seed, double* out, int64_t n) {
     for (int64_t i = 0; i < n; ++i) out[i] = ws_rand_poisson(lam, first + (uint64_t)i, stream, seed);
 }
+// fixed-point exponential spacings of slots 0 .. n_all-1 (multinomial resampling without a sort)
+void hh_spacings(int64_t n_all, int mn_shift, uint64_t seed, uint64_t stream, uint64_t* out) {
+    for (int64_t k = 0; k < n_all; ++k) out[k] = ws_spacing_of_slot((uint64_t)k, mn_shift, seed, stream);
+}
 void hh_randn2(uint64_t particle, uint64_t stream, uint64_t seed, double* out2) { ws_randn2(particle, stream, seed, out2[0], out2[1]); }
 void hh_philox(uint64_t particle, uint64_t stream, uint64_t seed, uint32_t* out4) {
     ws_u32x4 r = ws_philox4x32_10(particle, stream, seed);

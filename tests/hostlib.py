@@ -35,6 +35,7 @@ def lib():
         L.hh_score.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hh_count_slots_le.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
         L.hh_randn2.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.hh_spacings.argtypes = [C.c_int64, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]
         L.hh_set_replay_variates.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.hh_rand_gamma.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]
         L.hh_rand_poisson.argtypes = [C.c_double, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int64]

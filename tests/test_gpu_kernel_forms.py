@@ -197,3 +197,59 @@ def test_async_resample_state_machine(ws):
     assert np.all(np.diff(x) >= 0) and len(np.unique(x)) < n
     np.testing.assert_array_equal(st["keep"], 2.0 * x)
     np.testing.assert_array_equal(st["y"], x + 1.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# multinomial resampling without a sort (exponential spacings regenerated blockwise from Philox)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,s", [(1, 1.0), (2, 1.0), (255, 0.5), (256, 2.0), (257, 2.0), (2048, 1.0), (2049, 3.0), (50_001, 0.5),
+                                 (50_001, 3.0), (300_000, 1.5)])
+def test_multinomial_spacings_match_the_big_integer_specification(ws, n, s):
+    """every ancestor against oracle/ref.py: multinomial_ancestors_fixed_point, with the spacings regenerated by the
+    host instantiation of the device routine (csrc/ws_math.cuh: ws_spacing_of_slot)"""
+    import ctypes as C
+    from hostlib import lib
+    from oracle import ref
+    w = np.exp(s * np.random.default_rng(n).standard_normal(n))
+    w /= w.sum()
+    st = ws.SMCState(max(n, 2), seed=19, device=0)
+    stream, seed = C.c_uint64(), C.c_uint64()
+    st.store._call("ws_next_philox_stream", C.byref(stream), C.byref(seed))
+    a, clamped = ws.resample_indices(w, st, "multinomial", return_clamped=True)
+    e = np.empty(n + 1, dtype=np.uint64)
+    lib().hh_spacings(n + 1, ref.multinomial_mn_shift(n), seed.value, stream.value, e.ctypes.data_as(C.c_void_p))
+    a_ref, clamped_ref = ref.multinomial_ancestors_fixed_point(w, e)
+    np.testing.assert_array_equal(a, a_ref)
+    assert clamped == clamped_ref
+
+
+def test_multinomial_one_hot_and_statistics(ws):
+    """a heavy particle (its slots span many blocks: the per-lane fallback and the heavy-tile expansion) and the
+    multinomial variance of the offspring counts"""
+    import ctypes as C
+    from hostlib import lib
+    from oracle import ref
+    n = 120_000
+    w = np.full(n, 0.03 / (n - 1))
+    w[77_777] = 0.97
+    w /= w.sum()
+    st = ws.SMCState(n, seed=23, device=0)
+    stream, seed = C.c_uint64(), C.c_uint64()
+    st.store._call("ws_next_philox_stream", C.byref(stream), C.byref(seed))
+    a = ws.resample_indices(w, st, "multinomial")
+    e = np.empty(n + 1, dtype=np.uint64)
+    lib().hh_spacings(n + 1, ref.multinomial_mn_shift(n), seed.value, stream.value, e.ctypes.data_as(C.c_void_p))
+    a_ref, _ = ref.multinomial_ancestors_fixed_point(w, e)
+    np.testing.assert_array_equal(a, a_ref)
+    assert (a == 77_777).sum() > 0.96 * n
+    # statistics over fresh draws: E[count] = N w, Var[count] = N w (1 - w) (multinomial), unlike stratified (< 1/4)
+    n2 = 200_000
+    w2 = np.exp(0.7 * np.random.default_rng(4).standard_normal(n2))
+    w2 /= w2.sum()
+    st2 = ws.SMCState(n2, seed=5, device=0)
+    counts = np.bincount(ws.resample_indices(w2, st2, "multinomial"), minlength=n2)
+    assert counts.sum() == n2
+    resid = counts - n2 * w2
+    assert abs(resid.mean()) < 1e-9 and 0.9 < resid.var() / np.mean(n2 * w2 * (1 - w2)) < 1.1
+    again = ws.resample_indices(w2, st2, "multinomial")
+    assert np.any(np.bincount(again, minlength=n2) != counts)

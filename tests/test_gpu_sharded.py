@@ -38,13 +38,13 @@ def _obs(T):
     return [np.array([t, 0.0]) + 0.7 * rng.standard_normal(2) for t in range(T)]
 
 
-def _worker(rank, world, port, n, T, ess, q):
+def _worker(rank, world, port, n, T, ess, q, resampler="stratified"):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import wsb200 as ws
-    st = ws.sharded_state(n, device=rank, seed=77, ess_perc_min=ess)
+    st = ws.sharded_state(n, device=rank, seed=77, ess_perc_min=ess, resampler=resampler)
     ws.run(ws.model(MODEL)(_obs(T)), st)
     le = ws.log_evidence(st)
     mx = ws.E(lambda x: x[0], st)
@@ -55,20 +55,22 @@ def _worker(rank, world, port, n, T, ess, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,ess", [(2, 1.0), (2, 0.5), (4, 1.0)])
-def test_sharded_equals_single_gpu(world, ess):
+@pytest.mark.parametrize("world,ess,resampler", [(2, 1.0, "stratified"), (2, 0.5, "stratified"), (4, 1.0, "stratified"),
+                                                 (2, 1.0, "systematic"), (2, 1.0, "multinomial"), (4, 0.5, "multinomial")])
+def test_sharded_equals_single_gpu(world, ess, resampler):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     import wsb200 as ws
     n, T = 200_003, 12
-    single = ws.SMCState(n, device=0, seed=77, ess_perc_min=ess)
+    single = ws.SMCState(n, device=0, seed=77, ess_perc_min=ess, resampler=resampler)
     ws.run(ws.model(MODEL)(_obs(T)), single)
     x1, v1, w1 = single["x"], single["v"], single.weights
     le1, mx1 = ws.log_evidence(single), ws.E(lambda x: x[0], single)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, 29741 + int(ess * 10), n, T, ess, q)) for r in range(world)]
+    port = 29741 + int(ess * 10) + 20 * ["stratified", "systematic", "multinomial"].index(resampler) + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, T, ess, q, resampler)) for r in range(world)]
     for p in procs:
         p.start()
     out = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
@@ -82,7 +84,7 @@ def test_sharded_equals_single_gpu(world, ess):
     # same Philox counters (global indices) and an order-independent fixed-point CDF: the sharded run is
     # the single-GPU run, up to the rounding of the (m, S) reduction
     bad = (np.abs(xs - x1) > 1e-9 * (1 + np.abs(x1))).any(axis=1) | (np.abs(vs - v1) > 1e-9 * (1 + np.abs(v1))).any(axis=1)
-    print(f"world={world} ess={ess}: {int(bad.sum())} of {n} particles differ; migrated {[o[7] for o in out]}")
+    print(f"world={world} ess={ess} {resampler}: {int(bad.sum())} of {n} particles differ; migrated {[o[7] for o in out]}")
     assert bad.sum() <= 5
     np.testing.assert_allclose(wsum, w1, rtol=1e-9, atol=1e-9)
     for o in out:

@@ -95,7 +95,14 @@ struct WsScanParams {
     unsigned int* tile_counter;      // single-pass kernel: the tile ticket, zeroed before launch
     double fx_scale;                 // fixed-point scale of the CDF and log2 of the units per slot (ws_scan_set_scale)
     int32_t fx_shift;
-    int32_t pad3;
+    int32_t mn_shift;                // multinomial: fixed-point scale 2^mn_shift of the exponential spacings
+    // Multinomial resampling without a sort (scheme 2, Philox draws): the order statistics of n_slots iid uniforms are
+    // u_k = S_k / S_total with S_k the running sum of n_slots + 1 iid exponential spacings (slot k's spacing is
+    // Philox(k)); only coarse prefixes are stored — per tile of WS_CDF_TILE slots (exclusive, scanned) and per block
+    // of WS_SCAN_TILE slots (tile-local, exclusive) — and the search regenerates the spacings of the blocks it needs.
+    unsigned long long* mn_tile_off;     // [ceil((n_slots + 1) / WS_CDF_TILE)]
+    unsigned long long* mn_block_local;  // [ceil((n_slots + 1) / WS_SCAN_TILE)]
+    unsigned long long* mn_total;        // [1] S_total
     unsigned long long* n_clamped;  // += slots beyond the last CDF entry (clamped to the last particle)
     unsigned int* heavy_count;       // number of heavy tiles, zeroed before launch
     int32_t* heavy_F;                // [n/WS_HEAVY_TILE_SLOTS + 2][WS_SCAN_TILE + 2]: F table, fstart, tile id
@@ -126,6 +133,7 @@ cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_
 void ws_scan_set_scale(WsScanParams& P);
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s);
 // sharded resampling runs the same passes in two halves with collectives in between
+cudaError_t ws_launch_spacings(const WsScanParams& P, cudaStream_t s);  // multinomial: spacing prefixes of all global slots
 cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s);     // tile CDF + offsets (+ total)
 cudaError_t ws_launch_bounds(const WsScanParams& P, cudaStream_t s);  // first / end slot of this rank
 cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s);  // F(C_m) + expansion (+ heavy tiles)

@@ -661,7 +661,8 @@ __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double 
 #define WS_EXPAND_CHUNK 512    // output slots a warp stages in shared memory per round
 #define WS_DIRECT_MAX 8        // offspring a lane writes itself; larger families are filled by the warp
 #define WS_WARPS_PER_CTA (WS_SCAN_BLOCK / 32)
-#define WS_RBUF_SLOTS 384      // slot uniforms a warp generates cooperatively per tile (a tile of 256 particles spans ~256 slots)
+#define WS_RBUF_SLOTS 512      // 8-byte words of a warp's window: slot uniforms of the tile's slot range (stratified), running spacing
+                               // sums of two blocks of slots (multinomial), then the staged offspring
 
 // The integer slot grid (Philox path).  The CDF is an integer C in units of 2^-S slots (scale = N * 2^S), slot k's
 // uniform is u_k = (k + (r_k + 1/2) / 2^32) / N with r_k a 32-bit Philox word (slot k: word k & 3 of block k >> 2;
@@ -835,6 +836,86 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
     if (threadIdx.x == 0 && P.total != nullptr) *P.total = s_carry;
 }
 
+// ---- multinomial without a sort: exponential spacings ------------------------------------------------------------
+// T = floor(C * S_total / 2^61): the threshold of a CDF value in the units of the spacing sums
+__device__ __forceinline__ unsigned long long ws_mn_threshold(unsigned long long C, unsigned long long S_total) {
+    const unsigned long long lo = C * S_total, hi = __umul64hi(C, S_total);
+    return (hi << 3) | (lo >> 61);
+}
+// global exclusive prefix of block b (WS_SCAN_TILE slots)
+__device__ __forceinline__ unsigned long long ws_mn_block_prefix(const WsScanParams& P, int b) {
+    return __ldg(P.mn_tile_off + b / (WS_CDF_TILE / WS_SCAN_TILE)) + __ldg(P.mn_block_local + b);
+}
+// the block whose slots contain the first running sum > T: largest b with prefix(b) <= T (two-level binary search)
+__device__ __forceinline__ int ws_mn_find_block(const WsScanParams& P, unsigned long long T) {
+    constexpr int BPT = WS_CDF_TILE / WS_SCAN_TILE;
+    const int n_all = (int)P.n_slots + 1;
+    const int n_tiles = (n_all + WS_CDF_TILE - 1) / WS_CDF_TILE, n_blocks = (n_all + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    int lo = 0, hi = n_tiles - 1;  // largest tile with tile_off <= T
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(P.mn_tile_off + mid) <= T) lo = mid; else hi = mid - 1;
+    }
+    const unsigned long long base = __ldg(P.mn_tile_off + lo);
+    int b = lo * BPT;
+    const int b_end = min(b + BPT, n_blocks);
+    for (int j = b + 1; j < b_end; ++j)
+        if (base + __ldg(P.mn_block_local + j) <= T) b = j;
+    return b;
+}
+// F(C) = #{slots k < n_slots : S_k <= T} by one thread (rank edges, heavy tiles): find the block, walk its spacings
+__device__ __forceinline__ int ws_F_mn(const WsScanParams& P, unsigned long long C) {
+    const int ns = (int)P.n_slots;
+    const unsigned long long T = ws_mn_threshold(C, *P.mn_total);
+    const int b = ws_mn_find_block(P, T);
+    unsigned long long S = ws_mn_block_prefix(P, b);
+    int k = b * WS_SCAN_TILE;
+    const int k_end = min(k + WS_SCAN_TILE, ns);
+    while (k < k_end) {
+        S += ws_spacing_of_slot((uint64_t)k, P.mn_shift, P.seed, P.stream);
+        if (S > T) break;
+        ++k;
+    }
+    return k;
+}
+
+// spacing prefixes of all n_slots + 1 global slots: one CTA tile of WS_CDF_TILE slots, one warp per block
+__global__ void __launch_bounds__(WS_SCAN_BLOCK) ws_spacing_tiles_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+    __shared__ unsigned long long warp_tot[WS_SCAN_BLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_all = (int)P.n_slots + 1;
+    const int n_tiles = (n_all + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int k0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;   // 8 consecutive slots = 4 Philox blocks
+        unsigned long long sum = 0ull;
+#pragma unroll
+        for (int j = 0; j < WS_SCAN_ITEMS / 2; ++j) {
+            const int k = k0 + 2 * j;
+            if (k < n_all) {
+                const ws_u32x4 r = ws_philox4x32_10((uint64_t)(k >> 1), P.stream, P.seed);
+                sum += ws_spacing_fx(r.x, r.y, P.mn_shift);
+                if (k + 1 < n_all) sum += ws_spacing_fx(r.z, r.w, P.mn_shift);
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        __syncthreads();
+        if (lane == 0) warp_tot[warp] = sum;
+        __syncthreads();
+        unsigned long long excl = 0ull, agg = 0ull;
+#pragma unroll
+        for (int w = 0; w < WS_SCAN_BLOCK / 32; ++w) {
+            const unsigned long long t = warp_tot[w];
+            if (w < warp) excl += t;
+            agg += t;
+        }
+        const int b = tile * (WS_CDF_TILE / WS_SCAN_TILE) + warp;
+        if (lane == 0 && b * WS_SCAN_TILE < n_all) P.mn_block_local[b] = excl;
+        if (threadIdx.x == 0) P.mn_tile_off[tile] = agg;
+    }
+}
+
 // fixed-point mass below this rank's shard: given by value, or summed from the allgathered per-rank masses
 // (sharded runs: saves the host a device round trip between the CDF pass and the search)
 __device__ __forceinline__ unsigned long long ws_cdf_offset(const WsScanParams& P) {
@@ -872,7 +953,10 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
     const unsigned long long cdf_offset = ws_cdf_offset(P);
     const unsigned long long lo = cdf_offset, hi = cdf_offset + *P.total;
     int fs, fe;
-    if (EXACT_FP) {
+    if (!EXACT_FP && P.scheme == 2) {
+        fs = ws_F_mn(P, lo);
+        fe = ws_F_mn(P, hi);
+    } else if (EXACT_FP) {
         fs = (int)ws_F(P, ws_fxs_to_double(lo, P.fx_scale), inv_n, su);
         fe = (int)ws_F(P, ws_fxs_to_double(hi, P.fx_scale), inv_n, su);
     } else {
@@ -922,7 +1006,7 @@ __device__ __forceinline__ void ws_search_setup(const WsScanParams& P, WsSearchC
 // fixed-point CDF C[k] of particles tile_base + 8 L + k: per-particle slot counts F(C_m), then the offspring slots
 // [F(C_{m-1}), F(C_m)) of every particle are written to P.ancestors.  `Cp` (lane 0; valid iff has_prev) is the CDF of
 // the particle in front of the tile.  `rbuf`: the warp's shared-memory window (WS_RBUF_SLOTS words).
-template <bool EXACT_FP>
+template <bool EXACT_FP, bool MN>
 __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSearchCtx& X, unsigned long long* const rbuf,
                                                     const int lane, const int tile_base,
                                                     const unsigned long long (&C)[WS_SCAN_ITEMS], const unsigned long long Cp,
@@ -940,7 +1024,88 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
     int f[WS_SCAN_ITEMS];
     int fstart = slot_base;
     bool coop = false;
-    if (!EXACT_FP && su.scheme == 0) {
+    if (!EXACT_FP && MN) {
+        // Multinomial: thresholds T_m of the lane's particles in the units of the spacing sums; the warp finds the
+        // blocks of slots the tile can reach, regenerates their spacings once (running sums in the shared window)
+        // and every lane counts the sums below its thresholds by binary search.
+        const unsigned long long S_total = *P.mn_total;
+        unsigned long long T[WS_SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) T[k] = ws_mn_threshold(C[k], S_total);
+        unsigned long long Tp = has_prev ? ws_mn_threshold(Cp, S_total) : 0ull;
+        Tp = __shfl_sync(0xffffffffu, Tp, 0);
+        // the last particle of the shard present in this tile bounds the range from above
+        const int n_in_tile = min(WS_SCAN_TILE, n - tile_base);
+        const int last_lane = (n_in_tile - 1) / WS_SCAN_ITEMS, last_k = (n_in_tile - 1) % WS_SCAN_ITEMS;
+        unsigned long long Tmax = 0ull;
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k)
+            if (k == last_k) Tmax = T[k];
+        Tmax = __shfl_sync(0xffffffffu, Tmax, last_lane);
+        int b_lo = 0, b_hi = 0;
+        if (lane == 0) b_lo = ws_mn_find_block(P, has_prev ? Tp : 0ull);
+        if (lane == 1) b_hi = ws_mn_find_block(P, Tmax);
+        b_lo = __shfl_sync(0xffffffffu, b_lo, 0);
+        b_hi = __shfl_sync(0xffffffffu, b_hi, 1);
+        const int k_lo = b_lo * WS_SCAN_TILE;
+        const int k_hi = min((b_hi + 1) * WS_SCAN_TILE, ns);       // slots [k_lo, k_hi) are regenerated
+        coop = (k_hi - k_lo) <= WS_RBUF_SLOTS;
+        if (coop) {
+            constexpr int PER = WS_RBUF_SLOTS / 32;                 // consecutive slots per lane
+            unsigned long long lane_sum = 0ull;
+            for (int j = 0; j < PER; j += 2) {                      // spacings into the window, lane totals in registers
+                const int k = k_lo + lane * PER + j;
+                unsigned long long e0 = 0ull, e1 = 0ull;
+                if (k < k_hi) {
+                    const ws_u32x4 r = ws_philox4x32_10((uint64_t)(k >> 1), P.stream, P.seed);
+                    e0 = ws_spacing_fx(r.x, r.y, P.mn_shift);
+                    if (k + 1 < k_hi) e1 = ws_spacing_fx(r.z, r.w, P.mn_shift);
+                }
+                rbuf[lane * PER + j] = e0;
+                rbuf[lane * PER + j + 1] = e1;
+                lane_sum += e0 + e1;
+            }
+            unsigned long long incl = lane_sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            unsigned long long run = ws_mn_block_prefix(P, b_lo) + (incl - lane_sum);
+            for (int j = 0; j < PER; ++j) {                         // ... and in place into running sums
+                run += rbuf[lane * PER + j];
+                const int k = k_lo + lane * PER + j;
+                rbuf[lane * PER + j] = (k < k_hi) ? run : ~0ull;    // beyond the range: larger than any threshold
+            }
+            __syncwarp();
+            const int n_win = k_hi - k_lo;
+            auto count_le = [&](unsigned long long t) -> int {     // #{j < n_win : rbuf[j] <= t}
+                int lo = 0, hi = n_win;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (rbuf[mid] <= t) lo = mid + 1; else hi = mid;
+                }
+                return lo;
+            };
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+                int fk;
+                if (item0 + k >= n) {
+                    fk = -1;  // patched below
+                } else {
+                    fk = k_lo + count_le(T[k]);
+                    if (item0 + k == n - 1 && P.last_rank) {
+                        if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
+                        fk = ns;
+                    }
+                }
+                f[k] = fk;
+            }
+            if (lane == 0 && has_prev) fstart = k_lo + count_le(Tp);
+            __syncwarp();  // the window is reused for the offspring below
+        }
+    }
+    if (!EXACT_FP && !MN && su.scheme == 0) {
         // Philox-stratified: neighbouring particles ask for neighbouring slots, and one Philox block
         // serves four slots, so the warp generates the uniforms of the tile's whole slot range once
         // (a quarter of a Philox block per particle instead of one) and every lane looks its slots up.
@@ -1004,6 +1169,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
                 fk = -1;  // patched below
             } else {
                 if (EXACT_FP) fk = (int)ws_F(P, ws_fxs_to_double(C[k], X.fx_scale), inv_n, su);
+                else if (MN) fk = ws_F_mn(P, C[k]);
                 else fk = ws_F_int(C[k], (unsigned int)ns, sh, rmask, su.scheme, r0_int, P.seed, P.stream);
                 if (gi == n - 1 && P.last_rank) {
                     if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
@@ -1014,6 +1180,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
         }
         if (lane == 0 && has_prev) {
             if (EXACT_FP) fstart = (int)ws_F(P, ws_fxs_to_double(Cp, X.fx_scale), inv_n, su);
+            else if (MN) fstart = ws_F_mn(P, Cp);
             else fstart = ws_F_int(Cp, (unsigned int)ns, sh, rmask, su.scheme, r0_int, P.seed, P.stream);
         }
     }
@@ -1147,7 +1314,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
 #ifndef WS_SEARCH_MINB
 #define WS_SEARCH_MINB 3
 #endif
-template <bool EXACT_FP>
+template <bool EXACT_FP, bool MN>
 __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
 
@@ -1189,7 +1356,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
             const int p = tile_base - 1;
             Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
         }
-        ws_search_warp_tile<EXACT_FP>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0);
+        ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0);
     }
 }
 
@@ -1330,7 +1497,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
 #pragma unroll
     for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? thread_excl + q[k] : 0ull;
     const int warp_base = tile * WS_CDF_TILE + warp * WS_SCAN_TILE;
-    if (warp_base < n) ws_search_warp_tile<EXACT_FP>(P, X, win_all[warp], lane, warp_base, C, prefix + warp_excl, warp_base != 0);
+    if (warp_base < n) ws_search_warp_tile<EXACT_FP, false>(P, X, win_all[warp], lane, warp_base, C, prefix + warp_excl, warp_base != 0);
 }
 
 // Slots of the heavy tiles (see above): every CTA takes an equal slice of each heavy tile's output
@@ -1369,7 +1536,12 @@ static int g_fx_extra_bits = 0;
 void ws_scan_set_scale(WsScanParams& P) {
     const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
     int shift = 61;
-    if (!exact_fp) {
+    {   // multinomial: spacings of mean 2^mn_shift, so that the sum of n_slots + 1 of them stays below 2^61
+        int bits = 0;
+        while (((int64_t)1 << bits) < P.n_slots + 1) ++bits;
+        P.mn_shift = 60 - bits;
+    }
+    if (!exact_fp && P.scheme != 2) {
         int bits = 0;
         while (((int64_t)1 << bits) < P.n_slots) ++bits;
         shift = 61 - bits - g_fx_extra_bits;
@@ -1377,6 +1549,23 @@ void ws_scan_set_scale(WsScanParams& P) {
     }
     P.fx_shift = shift;
     P.fx_scale = exact_fp ? 2305843009213693952.0 : ldexp((double)P.n_slots, shift);
+}
+
+// multinomial (Philox): tile / block prefixes of the exponential spacings of ALL global slots and their total.
+// On a sharded state every rank computes the same table (counter-based draws: no exchange needed).
+cudaError_t ws_launch_spacings(const WsScanParams& P, cudaStream_t s) {
+    const int64_t n_all = P.n_slots + 1;
+    const int64_t tiles = (n_all + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    int g = (int)(tiles < (int64_t)g_sm_count * 8 ? tiles : (int64_t)g_sm_count * 8);
+    ws_spacing_tiles_kernel<<<g < 1 ? 1 : g, WS_SCAN_BLOCK, 0, s>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    WsScanParams Q = P;   // exclusive scan of the tile sums, in place, with the existing single-CTA kernel
+    Q.n = n_all;
+    Q.tile_words = P.mn_tile_off;
+    Q.total = P.mn_total;
+    ws_cdf_offsets_kernel<<<1, 1024, 0, s>>>(Q);
+    return cudaGetLastError();
 }
 
 cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s) {
@@ -1403,8 +1592,9 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
     int g3 = (int)(ctas < (int64_t)g_sm_count * 6 ? ctas : (int64_t)g_sm_count * 6);
     if (g3 < 1) g3 = 1;
     const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
-    if (exact_fp) ws_search_kernel<true><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
-    else ws_search_kernel<false><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
+    if (exact_fp) ws_search_kernel<true, false><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
+    else if (P.scheme == 2) ws_search_kernel<false, true><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
+    else ws_search_kernel<false, false><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);
@@ -1416,7 +1606,7 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
 static bool g_three_pass = true;
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
     (void)grid;
-    if (!g_three_pass && P.all_tot == nullptr && P.total == nullptr && P.bounds == nullptr) {
+    if (!g_three_pass && P.all_tot == nullptr && P.total == nullptr && P.bounds == nullptr && P.scheme != 2) {
         // single-GPU state: one pass (the caller has zeroed the ticket / heavy-tile counters)
         const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
         cudaError_t e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * (size_t)cdf_tiles, s);

@@ -11,7 +11,6 @@
 //   8 x (histogram of the next key byte | pick the byte where the running mass first exceeds h)
 //   pass F   neighbours of the selected value: largest smaller value, smallest weight at the value
 // All of it is HBM streaming work: 8 (x) + 8 (q) bytes per particle and pass.
-#include <cub/cub.cuh>
 #include <vector>
 #include <string.h>
 #include "ws_internal.h"
@@ -392,34 +391,3 @@ cudaError_t ws_stats_plane(const double* x, const unsigned long long* q, int64_t
 }
 
 
-// ---- multinomial resampling: N iid uniforms, sorted ------------------------------------------------------
-// u = sort(N iid U[0,1)) fed to icdf.  The draws are Philox(slot >> 1) (two per block) or
-// the caller's replayed uniforms; the sort is a CUB radix sort (library code, like calling cuBLAS: it is not
-// on the stratified / systematic path the benchmarks run).
-__global__ void __launch_bounds__(256) ws_fill_uniforms_kernel(double* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream) {
-    const int64_t stride = (int64_t)gridDim.x * 256;
-    const int64_t n_blk = (n + 1) / 2;
-    for (int64_t b = (int64_t)blockIdx.x * 256 + threadIdx.x; b < n_blk; b += stride) {
-        const ws_u32x4 r = ws_philox4x32_10((uint64_t)b, stream, seed);
-        out[2 * b] = ws_u01(r.x, r.y);
-        if (2 * b + 1 < n) out[2 * b + 1] = ws_u01(r.z, r.w);
-    }
-}
-
-size_t ws_sort_temp_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, bytes, (const double*)nullptr, (double*)nullptr, (int)n);
-    return bytes;
-}
-
-// out = sort(in or fresh Philox uniforms); `in` may be nullptr (then `raw` receives the draws first)
-cudaError_t ws_sorted_uniforms(const double* in, double* raw, double* out, int64_t n, uint64_t seed, uint64_t stream_id,
-                               void* temp, size_t temp_bytes, cudaStream_t s) {
-    if (in == nullptr) {
-        ws_fill_uniforms_kernel<<<stats_grid((n + 1) / 2), 256, 0, s>>>(raw, n, seed, stream_id);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        in = raw;
-    }
-    return cub::DeviceRadixSort::SortKeys(temp, temp_bytes, in, out, (int)n, 0, 64, s);
-}

@@ -447,6 +447,22 @@ WS_HD double ws_rand_poisson(double lam, uint64_t particle, uint64_t stream, uin
     return k < 0.0 ? 0.0 : k;
 }
 
+// Multinomial resampling without a sort (csrc/ws_kernels.cu): the order statistics of N iid uniforms are running sums
+// of N + 1 iid exponential spacings divided by their total.  Slot k's spacing in fixed point:
+// e_k = max(1, rint(Exp(1) * 2^mn_shift)), the exponential from words (2(k&1), 2(k&1)+1) of Philox block k >> 1.
+// Host and device evaluate the same code (ws_log_pos is built from explicit fmas), so the tests regenerate the
+// spacings bit for bit through the CPU harness.
+WS_HD unsigned long long ws_spacing_fx(uint32_t hi, uint32_t lo, int mn_shift) {
+    const uint64_t v = ((((uint64_t)hi << 32) | (uint64_t)lo) >> 11) + 1ull;  // u = v 2^-53 in (0, 1]
+    const double e = -ws_log_pos((double)v, -53);
+    const unsigned long long q = (unsigned long long)llrint(ldexp(e, mn_shift));
+    return q < 1ull ? 1ull : q;
+}
+WS_HD unsigned long long ws_spacing_of_slot(uint64_t k, int mn_shift, uint64_t seed, uint64_t stream) {
+    const ws_u32x4 r = ws_philox4x32_10(k >> 1, stream, seed);
+    return (k & 1ull) ? ws_spacing_fx(r.z, r.w, mn_shift) : ws_spacing_fx(r.x, r.y, mn_shift);
+}
+
 // ---------------------------------------------------------------------------
 // log densities
 // ---------------------------------------------------------------------------

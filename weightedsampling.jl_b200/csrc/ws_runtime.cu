@@ -220,6 +220,9 @@ struct ws_ctx {
     unsigned long long* d_cdf_local = nullptr;  // [n] tile-local fixed-point CDF (scratch of the resampler)
     unsigned int* d_tile_counter = nullptr;  // [0] dynamic tile id, [1] heavy-tile count
     int32_t* d_heavy_F = nullptr;
+    // multinomial without a sort: coarse prefixes of the exponential spacings of all global slots (ws_launch_spacings)
+    unsigned long long* d_mn = nullptr;       // [tile offsets | block-local prefixes | total]
+    int64_t mn_cap_slots = 0;
     int64_t heavy_cap_n = 0;                  // particle count d_heavy_F is sized for
     int64_t n_tiles = 0;
     unsigned long long* d_counters = nullptr;  // [0] clamped slots (cumulative), [1] clamped (host-array calls), [2] MH accepts
@@ -659,6 +662,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaFree(c->d_replay_n);
     cudaFree(c->d_replay_u);
     cudaFree(c->d_replay_e);
+    cudaFree(c->d_mn);
     cudaFree(c->d_replay_v);
     cudaFree(c->d_scratch);
     if (c->h_scratch) cudaFreeHost(c->h_scratch);
@@ -1013,11 +1017,11 @@ extern "C" int ws_col_download(ws_ctx* c, int32_t id, double* host_out) {
     const Column& col = c->cols[id];
     for (int k = 0; k < col.width; ++k) {
         const double* src = col.front[k];
-        if (col.stale[k]) {
+        const int32_t* map = nullptr;
+        if (col.stale[k]) TRY(map_for_epoch(c, col.ep[k], &map));   // nullptr: only identity events in between
+        if (map != nullptr) {
             // read through the (composed) ancestors into scratch: the plane itself stays in its old order,
             // so exporting a long history costs one 4-byte chain step per event, not a gather of everything
-            const int32_t* map = nullptr;
-            TRY(map_for_epoch(c, col.ep[k], &map));
             TRY(ensure_scratch(c, sizeof(double) * (size_t)c->n));
             WsGatherParams G;
             memset(&G, 0, sizeof(G));
@@ -1033,7 +1037,7 @@ extern "C" int ws_col_download(ws_ctx* c, int32_t id, double* host_out) {
             src = c->d_scratch;
         }
         CK(c, cudaMemcpyAsync(host_out + (size_t)k * c->n, src, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
-        if (col.stale[k]) CK(c, cudaStreamSynchronize(c->stream));  // scratch is reused by the next plane
+        if (map != nullptr) CK(c, cudaStreamSynchronize(c->stream));  // scratch is reused by the next plane
     }
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)sizeof(double) * c->n * col.width;
@@ -1509,6 +1513,14 @@ static int materialize_planes(ws_ctx* c, const std::vector<Plane>* only) {
     for (auto& g : by_ep) {
         const int32_t* map = nullptr;
         TRY(map_for_epoch(c, g.first, &map));
+        if (map == nullptr) {
+            // every event these planes are behind was a queued step that did not fire (identity): nothing to move
+            for (auto& pl : g.second) {
+                c->cols[pl.col].stale[pl.comp] = 0;
+                c->cols[pl.col].ep[pl.comp] = c->epoch;
+            }
+            continue;
+        }
         TRY(gather_planes(c, map, g.second));
     }
     if (!only) c->anc_pending = false;
@@ -1605,6 +1617,44 @@ static int gather_all(ws_ctx* c, const int32_t* d_anc) {
     return gather_planes(c, d_anc, which);
 }
 
+// Multinomial resampling with Philox draws: point S at the spacing tables (sized for S.n_slots) and fill them.
+static int prepare_multinomial(ws_ctx* c, WsScanParams& S) {
+    const int64_t n_all = S.n_slots + 1;
+    const int64_t tiles = (n_all + WS_CDF_TILE - 1) / WS_CDF_TILE, blocks = (n_all + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    if (c->d_mn == nullptr || c->mn_cap_slots < n_all) {
+        if (c->d_mn) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            CK(c, cudaFree(c->d_mn));
+            c->d_mn = nullptr;
+        }
+        CK(c, cudaMalloc(&c->d_mn, sizeof(unsigned long long) * (size_t)(tiles + blocks + 2)));
+        c->mn_cap_slots = n_all;
+    }
+    S.mn_tile_off = c->d_mn;
+    S.mn_block_local = c->d_mn + tiles;
+    S.mn_total = c->d_mn + tiles + blocks;
+    TimedEvent te;
+    timed_begin(c, KC_SCAN, te);
+    CK(c, ws_launch_spacings(S, c->stream));
+    timed_end(c, te);
+    c->stats.kernel_launches += 1;
+    return WS_OK;
+}
+
+// Multinomial resampling with REPLAYED uniforms (parity tests): u = sort(N iid uniforms), sorted
+// on the host — a test path; production draws need no sort (prepare_multinomial).
+static int sorted_replay_uniforms(ws_ctx* c, const double* d_ru, int64_t n, const double** d_sorted) {
+    std::vector<double> u((size_t)n);
+    CK(c, cudaMemcpyAsync(u.data(), d_ru, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    std::sort(u.begin(), u.end());
+    TRY(ensure_scratch(c, sizeof(double) * (size_t)n));
+    CK(c, cudaMemcpyAsync(c->d_scratch, u.data(), sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *d_sorted = c->d_scratch;
+    return WS_OK;
+}
+
 static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, int64_t n, const double* d_replay_u,
                            const double* d_sorted_u, int32_t* d_anc, unsigned long long* d_words,
                            unsigned long long* d_cdf_local, uint64_t stream_id, unsigned long long* d_clamped, int gate = 0) {
@@ -1648,6 +1698,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     S.heavy_count = c->d_tile_counter + 1;
     S.heavy_F = c->d_heavy_F;
     ws_scan_set_scale(S);
+    if (scheme == WS_RESAMPLER_MULTINOMIAL && d_sorted_u == nullptr && d_replay_u == nullptr) TRY(prepare_multinomial(c, S));
     TimedEvent te;
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_scan_search(S, 0, c->stream));
@@ -1812,6 +1863,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id) {
     S.stream = stream_id;
     S.replay_u = d_ru;
     ws_scan_set_scale(S);
+    if (c->resampler == WS_RESAMPLER_MULTINOMIAL) TRY(prepare_multinomial(c, S));   // every rank: the same table of all global slots
     S.ancestors = nullptr;
     S.tile_words = c->d_tile_words;
     S.cdf_local = c->d_cdf_local;
@@ -2056,8 +2108,8 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
         c->last_info_pending = false;
         return WS_OK;
     }
-    if (c->resampler == WS_RESAMPLER_MULTINOMIAL && c->nranks > 1)
-        return fail(c, WS_EUNSUPPORTED, "multinomial resampling of a sharded state is not built (stratified / systematic are)");
+    if (c->resampler == WS_RESAMPLER_MULTINOMIAL && c->nranks > 1 && c->d_replay_u != nullptr)
+        return fail(c, WS_EUNSUPPORTED, "multinomial resampling of a sharded state with replayed uniforms (Philox draws are supported)");
     TRY(ensure_reduced(c));
     c->stats.resamples_fired++;
     const WsReduceOut r = *c->h_red;
@@ -2094,16 +2146,8 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
         // planes still in an older order keep their ancestor vectors (genealogy) or are gathered now
         TRY(begin_resample_event(c));
         const double* d_sorted = nullptr;
-        if (c->resampler == WS_RESAMPLER_MULTINOMIAL) {
-            // u = sort(N iid uniforms): replayed or Philox draws, radix-sorted on the device
-            const size_t tb = ws_sort_temp_bytes(c->n);
-            const size_t off = (16 * (size_t)c->n + 255) & ~(size_t)255;
-            TRY(ensure_scratch(c, off + tb));
-            double* raw = c->d_scratch;
-            double* sorted = c->d_scratch + c->n;
-            CK(c, ws_sorted_uniforms(d_ru, raw, sorted, c->n, c->seed, stream_id, (char*)c->d_scratch + off, tb, c->stream));
-            c->stats.kernel_launches += 2;
-            d_sorted = sorted;
+        if (c->resampler == WS_RESAMPLER_MULTINOMIAL && d_ru != nullptr) {
+            TRY(sorted_replay_uniforms(c, d_ru, c->n, &d_sorted));   // replayed draws (tests): sorted on the host
             d_ru = nullptr;
         }
         TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, d_sorted, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id, c->d_counters + 0));
@@ -2366,7 +2410,7 @@ extern "C" int ws_resample_host(ws_ctx* c, const double* weights, int64_t n, int
     if (scheme == WS_RESAMPLER_STRATIFIED) return resample_host_impl(c, weights, n, scheme, uniforms, n, false, indices_out, n_clamped);
     if (scheme == WS_RESAMPLER_SYSTEMATIC) return resample_host_impl(c, weights, n, scheme, uniforms, 1, false, indices_out, n_clamped);
     if (scheme == WS_RESAMPLER_MULTINOMIAL) {
-        if (uniforms == nullptr) return fail(c, WS_EUNSUPPORTED, "multinomial resampling needs caller uniforms for now");
+        if (uniforms == nullptr) return resample_host_impl(c, weights, n, scheme, nullptr, 0, false, indices_out, n_clamped);  // Philox: no sort
         std::vector<double> su(uniforms, uniforms + n);
         std::sort(su.begin(), su.end());
         return resample_host_impl(c, weights, n, scheme, su.data(), n, true, indices_out, n_clamped);
@@ -3206,9 +3250,9 @@ extern "C" int ws_describe(ws_ctx* c, int32_t n_planes, const int32_t* col, cons
     for (int t = 0; t < n_planes; ++t) {
         const Column& cl = c->cols[col[t]];
         const double* x = cl.front[comp[t]];
-        if (cl.stale[comp[t]]) {
-            const int32_t* map = nullptr;
-            TRY(map_for_epoch(c, cl.ep[comp[t]], &map));
+        const int32_t* map = nullptr;
+        if (cl.stale[comp[t]]) TRY(map_for_epoch(c, cl.ep[comp[t]], &map));
+        if (map != nullptr) {
             WsGatherParams G;
             memset(&G, 0, sizeof(G));
             G.n = c->n;

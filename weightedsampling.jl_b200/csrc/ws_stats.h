@@ -28,6 +28,4 @@ cudaError_t ws_stats_plane(const double* x, const unsigned long long* q, int64_t
                            cudaStream_t s, WsPlaneStats* out, int* n_launches, const WsStatsComm* comm = nullptr);
 
 // multinomial resampling: sorted iid uniforms (Philox draws when `in` is nullptr)
-size_t ws_sort_temp_bytes(int64_t n);
-cudaError_t ws_sorted_uniforms(const double* in, double* raw, double* out, int64_t n, uint64_t seed, uint64_t stream_id,
-                               void* temp, size_t temp_bytes, cudaStream_t s);
+
