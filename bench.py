@@ -447,6 +447,7 @@ def main():
                     "d2h_bytes_per_step": int((stats1["d2h_bytes"] - stats0["d2h_bytes"]) / max(1, K))},
             "gpu_launches": int(launches), "clocks": clocks,
             "ms_per_step_chunks": chunk_ms_per_step, "sharded_parity": parity,
+            "ess_knife_edge_steps": state.ess_ties(),
             "fusion": {"fused_passes": stats1["fused_passes"] - stats0["fused_passes"],
                        "fused_statements": stats1["fused_statements"] - stats0["fused_statements"],
                        "straight_line_passes": stats1["sl_passes"] - stats0["sl_passes"],

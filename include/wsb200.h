@@ -317,6 +317,11 @@ int ws_get_stats(ws_ctx* ctx, ws_stats* out);
 /* cumulative number of output slots whose uniform lay beyond the last CDF entry (clamped to the
  * last particle; the reference's icdf would throw BoundsError there) */
 int ws_get_clamped(ws_ctx* ctx, int64_t* out);
+/* Resample steps whose ESS% equalled ess_perc_min to within 8 ulp.  The reference computes 1 / (N sum w^2)
+ * (src/resampling.jl:51-54, src/transformers.jl:484), the device S^2 / (N Q): for such a step (exactly equal weights
+ * with ess_perc_min = 1.0 is the one that occurs) the two can fall on different sides of the threshold, so whether it
+ * fires is rounding noise in both; the count makes the deviation visible. */
+int ws_get_ess_ties(ws_ctx* ctx, int64_t* out);
 /* per kernel class device time (ms, CUDA events on the context's stream; needs ws_set_timing(1)) and
  * launch counts.  Classes: 0 fused elementwise pass, 1 stand-alone reduce, 2 finalize, 3 scan+search,
  * 4 gather, 5 fill, 6 MH / score, 7 other. */

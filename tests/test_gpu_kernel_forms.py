@@ -253,3 +253,18 @@ def test_multinomial_one_hot_and_statistics(ws):
     assert abs(resid.mean()) < 1e-9 and 0.9 < resid.var() / np.mean(n2 * w2 * (1 - w2)) < 1.1
     again = ws.resample_indices(w2, st2, "multinomial")
     assert np.any(np.bincount(again, minlength=n2) != counts)
+
+
+def test_ess_knife_edge_is_counted(ws):
+    """exactly equal weights with ess_perc_min = 1.0: the reference's 1/(N sum w^2) lands on either side of 1.0
+    depending on N; the device's S^2/(N Q) is exactly 1.0 (no resample).  Such steps are counted, not hidden."""
+    n = 2000
+    st = ws.SMCState(n, ess_perc_min=1.0, seed=1, device=0)
+    st.store.setcol("x", np.zeros(n))
+    ws.Observe(0.5, "Normal", (ws.col("x"), 1.0)).apply(st)     # identical log-weights
+    ws.Resample().apply(st)
+    assert st.ess_ties() == 1 and st.stats()["resamples_done"] == 0
+    st.store.setcol("x", np.arange(n) * 1e-3)
+    ws.Observe(0.5, "Normal", (ws.col("x"), 1.0)).apply(st)
+    ws.Resample().apply(st)
+    assert st.ess_ties() == 1 and st.stats()["resamples_done"] == 1

@@ -151,6 +151,7 @@ SIGNATURES = {
     "ws_set_replay_variates": (C.c_int, [_ctx, C.c_void_p, C.c_int64]),
     "ws_get_stats": (C.c_int, [_ctx, C.POINTER(ws_stats)]),
     "ws_get_clamped": (C.c_int, [_ctx, _i64p]),
+    "ws_get_ess_ties": (C.c_int, [_ctx, _i64p]),
     "ws_kernel_times": (C.c_int, [_ctx, _dp, _i64p, C.c_int32]),
     "ws_reset_kernel_times": (C.c_int, [_ctx]),
     "ws_set_timing": (C.c_int, [_ctx, C.c_int]),

@@ -289,6 +289,12 @@ class SMCState:
         self.store._call("ws_get_stats", C.byref(s))
         return {f: getattr(s, f) for f, _ in L.ws_stats._fields_}
 
+    def ess_ties(self):
+        """Resample steps decided on a knife edge (ESS% == ess_perc_min to a few ulp; see ws_get_ess_ties)."""
+        v = C.c_int64()
+        self.store._call("ws_get_ess_ties", C.byref(v))
+        return v.value
+
     def genealogy(self):
         """Retained per-event ancestor vectors (trajectory storage by genealogy)."""
         nv, nb, ev = C.c_int64(), C.c_int64(), C.c_int64()

@@ -129,7 +129,7 @@ struct WsComposeParams {
 cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s);
 cudaError_t ws_launch_reduce_logw(const double* logw, int64_t n, WsLse* partials, int grid, cudaStream_t s);
 cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min,
-                               WsReduceOut* out, cudaStream_t s);
+                               WsReduceOut* out, cudaStream_t s, unsigned long long* ties = nullptr);
 void ws_scan_set_scale(WsScanParams& P);
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s);
 // sharded resampling runs the same passes in two halves with collectives in between
@@ -138,7 +138,7 @@ cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s);     // tile CD
 cudaError_t ws_launch_bounds(const WsScanParams& P, cudaStream_t s);  // first / end slot of this rank
 cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s);  // F(C_m) + expansion (+ heavy tiles)
 cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_t n_global, double ess_perc_min,
-                                      WsReduceOut* out, cudaStream_t s);
+                                      WsReduceOut* out, cudaStream_t s, unsigned long long* ties = nullptr);
 cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s);
 cudaError_t ws_launch_identity_unless_fired(const WsReduceOut* red, int32_t* anc, int64_t n, int grid, cudaStream_t s);
 cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStream_t s);

@@ -369,6 +369,10 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
         ws_cp_async_commit();
     };
 
+    WsSlConsts<Sig> K;
+    ws_sl_load_consts<Sig>(K, P, std::make_integer_sequence<int, Sig::n_ops>{});
+    const bool replay = P.rng.replay_n != nullptr || P.rng.replay_u != nullptr || P.rng.replay_e != nullptr;
+
     int anc_next[PP];
     {
         const int t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
@@ -416,7 +420,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
         double acc[PP];
 #pragma unroll
         for (int j = 0; j < PP; ++j) acc[j] = 0.0;
-        ws_sl_run<Sig, PP>(R, acc, P, particle, std::make_integer_sequence<int, Sig::n_ops>{});
+        ws_sl_run<Sig, PP>(R, acc, P, K, replay, particle, std::make_integer_sequence<int, Sig::n_ops>{});
 
         ws_sl_stores<Sig, PP>(R, P, idx, live, std::make_integer_sequence<int, NS>{});
         if (P.logw_mode != 0) {
@@ -511,9 +515,15 @@ cudaError_t ws_launch_reduce_logw(const double* logw, int64_t n, WsLse* partials
 }
 
 // One CTA; fixed combination order => the decision is deterministic for a given grid size.
+// ESS% == ess_perc_min to within a few ulp: the reference's 1 / (N sum w^2) and this S^2 / (N Q) round differently
+// there (for exactly equal weights and ess_perc_min = 1.0 the reference fires for some N and not for others), so the
+// decision of such a step is rounding noise on both sides; they are counted (ws_get_ess_ties).
+__device__ __forceinline__ void ws_count_ess_tie(double ess, double ess_min, unsigned long long* ties) {
+    if (ties != nullptr && fabs(ess - ess_min) <= 8.0 * 2.220446049250313e-16 * fabs(ess_min)) atomicAdd(ties, 1ull);
+}
 __global__ void __launch_bounds__(256) ws_finalize_kernel(const WsLse* __restrict__ partials, int n_partials,
                                                           int64_t n_global, double ess_perc_min,
-                                                          WsReduceOut* __restrict__ out) {
+                                                          WsReduceOut* __restrict__ out, unsigned long long* ties) {
     __shared__ WsLse warp_scratch[8];
     WsLse part;
     part.m = -INFINITY;
@@ -531,12 +541,13 @@ __global__ void __launch_bounds__(256) ws_finalize_kernel(const WsLse* __restric
         out->ess_perc = (tot.S * tot.S) / (nn * tot.Q);  // 1 / (N * sum w^2), w = e / S
         out->log_mean_w = lse - log(nn);
         out->do_resample = (out->ess_perc < ess_perc_min) ? 1 : 0;  // NaN compares false, as in Julia
+        ws_count_ess_tie(out->ess_perc, ess_perc_min, ties);
     }
 }
 
 cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min,
-                               WsReduceOut* out, cudaStream_t s) {
-    ws_finalize_kernel<<<1, 256, 0, s>>>(partials, n_partials, n_global, ess_perc_min, out);
+                               WsReduceOut* out, cudaStream_t s, unsigned long long* ties) {
+    ws_finalize_kernel<<<1, 256, 0, s>>>(partials, n_partials, n_global, ess_perc_min, out, ties);
     return cudaGetLastError();
 }
 
@@ -544,7 +555,7 @@ cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_
 // reduction.  Every rank runs this on identical inputs in identical order, so the ESS decision and the
 // normalisation constants are bit-identical on all ranks.
 __global__ void ws_finalize_global_kernel(const double* __restrict__ all_msq, int n_ranks, int64_t n_global,
-                                          double ess_perc_min, WsReduceOut* __restrict__ out) {
+                                          double ess_perc_min, WsReduceOut* __restrict__ out, unsigned long long* ties) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     WsLse tot;
     tot.m = -INFINITY;
@@ -566,11 +577,12 @@ __global__ void ws_finalize_global_kernel(const double* __restrict__ all_msq, in
     out->ess_perc = (tot.S * tot.S) / (nn * tot.Q);
     out->log_mean_w = lse - log(nn);
     out->do_resample = (out->ess_perc < ess_perc_min) ? 1 : 0;
+    ws_count_ess_tie(out->ess_perc, ess_perc_min, ties);
 }
 
 cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_t n_global, double ess_perc_min,
-                                      WsReduceOut* out, cudaStream_t s) {
-    ws_finalize_global_kernel<<<1, 32, 0, s>>>(all_msq, n_ranks, n_global, ess_perc_min, out);
+                                      WsReduceOut* out, cudaStream_t s, unsigned long long* ties) {
+    ws_finalize_global_kernel<<<1, 32, 0, s>>>(all_msq, n_ranks, n_global, ess_perc_min, out, ties);
     return cudaGetLastError();
 }
 

@@ -1371,7 +1371,7 @@ static int resolve_spec(ws_ctx* c) {
 }
 
 // Make d_red / h_red describe the current log-weights (m, S, Q, lse, ESS%, decision).
-static int ensure_reduced(ws_ctx* c) {
+static int ensure_reduced(ws_ctx* c, bool for_resample = false) {
     TRY(flush_window(c));
     TRY(resolve_spec(c));
     if (c->red_valid) return WS_OK;
@@ -1388,13 +1388,14 @@ static int ensure_reduced(ws_ctx* c) {
     }
     TimedEvent te;
     timed_begin(c, KC_FINALIZE, te);
-    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream));
+    unsigned long long* ties = for_resample ? c->d_counters + 3 : nullptr;   // knife-edge decisions (ws_get_ess_ties)
+    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream, c->nranks > 1 ? nullptr : ties));
     timed_end(c, te);
     if (c->nranks > 1) {
         // every rank reduces its shard; the (m, S, Q) triples are allgathered and combined in rank order
         NCK(c, g_nccl.AllGather(c->d_red, c->d_all_msq, 3, WS_NCCL_FLOAT64, c->comm, c->stream));
         timed_begin(c, KC_FINALIZE, te);
-        CK(c, ws_launch_finalize_global(c->d_all_msq, c->nranks, c->n_global, c->ess_perc_min, c->d_red, c->stream));
+        CK(c, ws_launch_finalize_global(c->d_all_msq, c->nranks, c->n_global, c->ess_perc_min, c->d_red, c->stream, ties));
         timed_end(c, te);
     }
     CK(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
@@ -2110,7 +2111,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
     }
     if (c->resampler == WS_RESAMPLER_MULTINOMIAL && c->nranks > 1 && c->d_replay_u != nullptr)
         return fail(c, WS_EUNSUPPORTED, "multinomial resampling of a sharded state with replayed uniforms (Philox draws are supported)");
-    TRY(ensure_reduced(c));
+    TRY(ensure_reduced(c, true));
     c->stats.resamples_fired++;
     const WsReduceOut r = *c->h_red;
     // the Philox stream of this step's slot uniforms is taken whether or not the step fires, so that the streams of
@@ -2208,7 +2209,7 @@ extern "C" int ws_resample_async(ws_ctx* c) {
     }
     TimedEvent te;
     timed_begin(c, KC_FINALIZE, te);
-    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream));
+    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream, c->d_counters + 3));
     timed_end(c, te);
     CK(c, cudaMemcpyAsync(&c->h_ring[c->spec_head % ws_ctx::SPEC_RING], c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
     c->ring_event[c->spec_head % ws_ctx::SPEC_RING] = c->epoch + 1;
@@ -3158,6 +3159,15 @@ extern "C" int ws_get_clamped(ws_ctx* c, int64_t* out) {
     return WS_OK;
 }
 
+extern "C" int ws_get_ess_ties(ws_ctx* c, int64_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    TRY(flush_window(c));
+    unsigned long long v = 0;
+    CK(c, cudaMemcpyAsync(&v, c->d_counters + 3, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    *out = (int64_t)v;
+    return WS_OK;
+}
 extern "C" int ws_get_stats(ws_ctx* c, ws_stats* out) {
     if (!c || !out) return WS_EINVAL;
     TRY(resolve_spec(c));

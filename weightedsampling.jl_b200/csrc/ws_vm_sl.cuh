@@ -182,9 +182,51 @@ inline int ws_sl_find(const Prog& P) {
 #if defined(__CUDACC__)
 // ---- execution (device) -----------------------------------------------------------------------------------------
 // op I of the signature applied to the thread's PP particles; R = [n_regs][PP] doubles, all indices constant
+// Does op `s` read constant k_j (0, 1, 2) at run time?  (not pinned by a value flag, and actually used by the op's form)
+WS_SL_CX bool ws_sl_uses_k(const WsSlOp& s, int j) {
+    const bool has_a = s.a != WS_SL_N, has_b = s.b != WS_SL_N;
+    switch (s.op) {
+        case WS_OP_LIN2:
+            if (j == 0) return !(s.kflags & WS_SL_K0Z);
+            if (j == 1) return (has_a && !(s.kflags & WS_SL_K1ONE));
+            return has_b && !(s.kflags & WS_SL_K2ONE);       // (k2 of a b-only LIN2 is read as k1 after the swap)
+        case WS_OP_RANDN2:
+        case WS_OP_RANDEXP:
+        case WS_OP_RANDU: return j == 0;                      // the Philox stream; replay offsets (k1, k2) stay in the parameters
+        case WS_OP_LOGPDF_NORMAL_CS: return j != 0 || !has_a;
+        case WS_OP_ACC_QUAD2:
+        case WS_OP_ACC_LIN2:
+        case WS_OP_ACC_SQLIN2: return j == 0 || (j == 1 && has_a) || (j == 2 && has_b);
+        default: return true;
+    }
+}
+// The constants of the window, read from the launch parameters ONCE per thread and pinned in registers: inside the tile
+// loop the compiler otherwise re-fetches them from the (3.6 KB) parameter block every tile, and the constant-cache
+// miss of one such fetch was the largest single stall of the kernel (profiles/r2d_ncu_ws_vm_sl_kernel_20M.txt:
+// LDCU.64 -> DFMA, 29 % of the samples).
+template <class Sig>
+struct WsSlConsts {
+    double k[Sig::n_ops][3];
+};
+template <class Sig, int I>
+__device__ __forceinline__ void ws_sl_load_const1(WsSlConsts<Sig>& K, const WsVmProgram& P) {
+    constexpr WsSlOp s = Sig::ops[I];
+    constexpr bool u0 = ws_sl_uses_k(s, 0), u1 = ws_sl_uses_k(s, 1), u2 = ws_sl_uses_k(s, 2);
+    K.k[I][0] = u0 ? P.ops[I].k0 : 0.0;
+    K.k[I][1] = u1 ? P.ops[I].k1 : 0.0;
+    K.k[I][2] = u2 ? P.ops[I].k2 : 0.0;
+    if (u0) asm volatile("" : "+d"(K.k[I][0]));   // opaque from here on: cannot be rematerialised from constant memory
+    if (u1) asm volatile("" : "+d"(K.k[I][1]));
+    if (u2) asm volatile("" : "+d"(K.k[I][2]));
+}
+template <class Sig, int... I>
+__device__ __forceinline__ void ws_sl_load_consts(WsSlConsts<Sig>& K, const WsVmProgram& P, std::integer_sequence<int, I...>) {
+    (ws_sl_load_const1<Sig, I>(K, P), ...);
+}
+
 template <class Sig, int I, int PP>
-__device__ __forceinline__ void ws_sl_step(double* __restrict__ R, double (&acc)[PP], const WsOp& o, const WsRng& rng,
-                                           const uint64_t (&particle)[PP]) {
+__device__ __forceinline__ void ws_sl_step(double* __restrict__ R, double (&acc)[PP], const WsOp& o, const double (&kk)[3],
+                                           const bool replay, const WsRng& rng, const uint64_t (&particle)[PP]) {
     constexpr WsSlOp s = Sig::ops[I];
     constexpr bool lin2 = s.op == WS_OP_LIN2;
     constexpr bool swap = lin2 && s.a == WS_SL_N && s.b != WS_SL_N;  // k0 + k2*r[b]: executed as k0 + k1'*r[a'] (ws_decode_op)
@@ -199,9 +241,14 @@ __device__ __forceinline__ void ws_sl_step(double* __restrict__ R, double (&acc)
     constexpr bool rt_imm = ws_sl_imm_is_runtime(s.op);
     d.imm = rt_imm ? (o.w1 >> 8) : s.imm;
     // (a swapped LIN2 carries no value flags in any signature)
-    d.k0 = (s.kflags & WS_SL_K0Z) ? 0.0 : o.k0;
-    d.k1 = (s.kflags & WS_SL_K1ONE) ? 1.0 : (swap ? o.k2 : o.k1);
-    d.k2 = (s.kflags & WS_SL_K2ONE) ? 1.0 : o.k2;
+    constexpr bool rnd = ws_sl_imm_is_runtime(s.op);
+    d.k0 = (s.kflags & WS_SL_K0Z) ? 0.0 : kk[0];
+    d.k1 = (s.kflags & WS_SL_K1ONE) ? 1.0 : (swap ? kk[2] : kk[1]);
+    d.k2 = (s.kflags & WS_SL_K2ONE) ? 1.0 : kk[2];
+    if (rnd && replay) {          // replayed draws (tests): offsets of the draw in the replay buffers
+        d.k1 = o.k1;
+        d.k2 = o.k2;
+    }
     ws_vm_exec_d<1, PP>(d, R, acc, rng, particle);
 }
 // register <- staging row K (the plane loads of this tile), and plane <- register for store K: the register numbers
@@ -230,8 +277,8 @@ __device__ __forceinline__ void ws_sl_stores(const double* __restrict__ R, const
     (ws_sl_store1<Sig, PP, K>(R, P, idx, live), ...);
 }
 template <class Sig, int PP, int... I>
-__device__ __forceinline__ void ws_sl_run(double* __restrict__ R, double (&acc)[PP], const WsVmProgram& P,
-                                          const uint64_t (&particle)[PP], std::integer_sequence<int, I...>) {
-    (ws_sl_step<Sig, I, PP>(R, acc, P.ops[I], P.rng, particle), ...);
+__device__ __forceinline__ void ws_sl_run(double* __restrict__ R, double (&acc)[PP], const WsVmProgram& P, const WsSlConsts<Sig>& K,
+                                          const bool replay, const uint64_t (&particle)[PP], std::integer_sequence<int, I...>) {
+    (ws_sl_step<Sig, I, PP>(R, acc, P.ops[I], K.k[I], replay, P.rng, particle), ...);
 }
 #endif
