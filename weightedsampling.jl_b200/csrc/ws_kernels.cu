@@ -1560,7 +1560,7 @@ void ws_scan_set_scale(WsScanParams& P) {
         if (shift < 24) shift = 24;
     }
     P.fx_shift = shift;
-    P.fx_scale = exact_fp ? 2305843009213693952.0 : ldexp((double)P.n_slots, shift);
+    P.fx_scale = (exact_fp || P.scheme == 2) ? 2305843009213693952.0 : ldexp((double)P.n_slots, shift);   // multinomial: 2^61 (ws_mn_threshold)
 }
 
 // multinomial (Philox): tile / block prefixes of the exponential spacings of ALL global slots and their total.

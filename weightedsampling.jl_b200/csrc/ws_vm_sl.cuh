@@ -215,9 +215,11 @@ __device__ __forceinline__ void ws_sl_load_const1(WsSlConsts<Sig>& K, const WsVm
     K.k[I][0] = u0 ? P.ops[I].k0 : 0.0;
     K.k[I][1] = u1 ? P.ops[I].k1 : 0.0;
     K.k[I][2] = u2 ? P.ops[I].k2 : 0.0;
+#ifndef WS_SL_NOPIN   // (A/B switch)
     if (u0) asm volatile("" : "+d"(K.k[I][0]));   // opaque from here on: cannot be rematerialised from constant memory
     if (u1) asm volatile("" : "+d"(K.k[I][1]));
     if (u2) asm volatile("" : "+d"(K.k[I][2]));
+#endif
 }
 template <class Sig, int... I>
 __device__ __forceinline__ void ws_sl_load_consts(WsSlConsts<Sig>& K, const WsVmProgram& P, std::integer_sequence<int, I...>) {
