@@ -255,6 +255,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the sharded == single-GPU check that precedes an N > 1 run")
     ap.add_argument("--profile-steps", type=int, default=10, help="steps of the second pass that times each kernel class")
+    ap.add_argument("--skew", type=float, default=2.0, help="N > 1: rank skew of the extra migration-heavy Resample (0 = skip it)")
     ap.add_argument("--eager-gather", action="store_true", help="gather every column inside Resample (reference order of work)")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -367,6 +368,45 @@ def main():
     prof_ms = evp0.elapsed_time(evp1)
     kt = state.kernel_times()
     st._call("ws_set_timing", 0)
+
+    # N > 1: one more step, NOT part of the headline, with the weights skewed ACROSS ranks (rank r's log-weights are
+    # lowered by skew * r, so the low ranks hold almost all of the mass): most offspring of the following Resample
+    # must cross shard boundaries, which the near-uniform weights of the filter never make them do.  Reported against
+    # the NVLink peer bandwidth (770 GB/s per direction, B200_PROFILING.md).
+    migration = None
+    if world > 1 and args.skew > 0:
+        p0, m0 = C.c_int64(), C.c_int64()
+        st._call("ws_get_pushed", C.byref(p0))
+        st._call("ws_get_migrated", C.byref(m0))
+        ws.Weight(None, (ws.col("x")[0] * 0.0 - args.skew * rank,)).apply(state)
+        state.sync()
+        barrier()
+        evm0, evm1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        evm0.record(stream)
+        ws.Resample().apply(state)
+        state.store._call("ws_flush")
+        evm1.record(stream)
+        state.sync()
+        barrier()
+        p1, m1 = C.c_int64(), C.c_int64()
+        st._call("ws_get_pushed", C.byref(p1))
+        st._call("ws_get_migrated", C.byref(m1))
+        t = torch.tensor([evm0.elapsed_time(evm1), float(p1.value - p0.value), float(m1.value - m0.value)], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        mig_ms, sent_max, recv_max = float(tmax[0]), float(tmax[1]), float(tmax[2])
+        bytes_per_particle = 8 * P_PLANES
+        busiest = max(sent_max, recv_max) * bytes_per_particle
+        migration = {"skew": args.skew, "ms": mig_ms, "migrated_particles_total": float(tsum[2]),
+                     "sent_particles_busiest_rank": sent_max, "received_particles_busiest_rank": recv_max,
+                     "bytes_per_particle": bytes_per_particle,
+                     "nvlink_gbs_busiest_rank": busiest / (mig_ms * 1e-3) / 1e9 if mig_ms > 0 else None,
+                     "nvlink_peak_gbs_per_direction": 770.0,
+                     "nvlink_frac": busiest / (mig_ms * 1e-3) / 1e9 / 770.0 if mig_ms > 0 else None,
+                     "note": "one Resample (scan, search, exchange, gather of 6 planes) after rank-skewed weights; the NVLink "
+                             "figure divides the busiest rank's migrated bytes by the WHOLE step time"}
     mig = C.c_int64()
     st._call("ws_get_migrated", C.byref(mig))
     migrated_per_step = (mig.value - mig0) / max(1, K)
@@ -447,7 +487,7 @@ def main():
                     "d2h_bytes_per_step": int((stats1["d2h_bytes"] - stats0["d2h_bytes"]) / max(1, K))},
             "gpu_launches": int(launches), "clocks": clocks,
             "ms_per_step_chunks": chunk_ms_per_step, "sharded_parity": parity,
-            "ess_knife_edge_steps": state.ess_ties(),
+            "ess_knife_edge_steps": state.ess_ties(), "migration": migration,
             "fusion": {"fused_passes": stats1["fused_passes"] - stats0["fused_passes"],
                        "fused_statements": stats1["fused_statements"] - stats0["fused_statements"],
                        "straight_line_passes": stats1["sl_passes"] - stats0["sl_passes"],

@@ -422,13 +422,13 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
         for (int j = 0; j < PP; ++j) acc[j] = 0.0;
         ws_sl_run<Sig, PP>(R, acc, P, K, replay, particle, std::make_integer_sequence<int, Sig::n_ops>{});
 
-        ws_sl_stores<Sig, PP>(R, P, idx, live, std::make_integer_sequence<int, NS>{});
+        ws_sl_stores<Sig, PP, WS_VM_BLOCK>(R, P, (unsigned)first, live, std::make_integer_sequence<int, NS>{});
         if (P.logw_mode != 0) {
             double lw[PP];
 #pragma unroll
             for (int j = 0; j < PP; ++j) {
                 lw[j] = (lmode == 1 ? lw_old[j] : lbase) + acc[j];
-                if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
+                if (live[j]) P.logw[(unsigned)first + j * WS_VM_BLOCK] = lw[j];
             }
             lse_push_many<PP>(part, lw, live);
         }

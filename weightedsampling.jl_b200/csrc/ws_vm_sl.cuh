@@ -265,18 +265,19 @@ template <class Sig, int PP, int BLOCK, int... K>
 __device__ __forceinline__ void ws_sl_loads(double* __restrict__ R, const double* __restrict__ stage, std::integer_sequence<int, K...>) {
     (ws_sl_load1<Sig, PP, BLOCK, K>(R, stage), ...);
 }
-template <class Sig, int PP, int K>
-__device__ __forceinline__ void ws_sl_store1(const double* __restrict__ R, const WsVmProgram& P, const int (&idx)[PP], const bool (&live)[PP]) {
+// plane K <- register: the thread's particles sit BLOCK apart, so one address per plane and constant offsets
+template <class Sig, int PP, int BLOCK, int K>
+__device__ __forceinline__ void ws_sl_store1(const double* __restrict__ R, const WsVmProgram& P, const unsigned first, const bool (&live)[PP]) {
     constexpr int r = Sig::store_reg[K];
-    double* __restrict__ ptr = P.store_ptr[K];
+    double* __restrict__ ptr = P.store_ptr[K] + first;
 #pragma unroll
     for (int j = 0; j < PP; ++j)
-        if (live[j]) ptr[(unsigned)idx[j]] = R[r * PP + j];
+        if (live[j]) ptr[j * BLOCK] = R[r * PP + j];
 }
-template <class Sig, int PP, int... K>
-__device__ __forceinline__ void ws_sl_stores(const double* __restrict__ R, const WsVmProgram& P, const int (&idx)[PP], const bool (&live)[PP],
+template <class Sig, int PP, int BLOCK, int... K>
+__device__ __forceinline__ void ws_sl_stores(const double* __restrict__ R, const WsVmProgram& P, const unsigned first, const bool (&live)[PP],
                                              std::integer_sequence<int, K...>) {
-    (ws_sl_store1<Sig, PP, K>(R, P, idx, live), ...);
+    (ws_sl_store1<Sig, PP, BLOCK, K>(R, P, first, live), ...);
 }
 template <class Sig, int PP, int... I>
 __device__ __forceinline__ void ws_sl_run(double* __restrict__ R, double (&acc)[PP], const WsVmProgram& P, const WsSlConsts<Sig>& K,
