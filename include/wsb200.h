@@ -97,7 +97,10 @@ enum ws_tok_op {
      * standard Gamma(shape) (Marsaglia-Tsang) and Poisson(rate) (inversion / PTRS) — the building blocks of the
      * reference's Gamma, Beta, TDist, Chisq, InverseGamma, Poisson kernels (src/default_kernels.jl:83-102) */
     WS_TOK_RANDGAMMA = 32,
-    WS_TOK_RANDPOISSON = 33
+    WS_TOK_RANDPOISSON = 33,
+    /* a constant supplied later: only inside the expressions of a ws_exec command list, where it is replaced by
+     * params[col] before the statement is issued */
+    WS_TOK_PARAM = 34
 };
 
 typedef struct ws_tok {
@@ -196,6 +199,36 @@ int ws_sample_importance_normal(ws_ctx* ctx, int32_t col, int32_t comp, double p
  * (NULL: the statement is not scored).  weighter / logpdf read x through WS_TOK_PLANE (col, comp). */
 int ws_sample_expr(ws_ctx* ctx, int32_t col, int32_t comp, const ws_expr* sampler, const ws_expr* weighter,
                    const ws_expr* logpdf);
+
+/* ---- statement lists -----------------------------------------------------------------------
+ * Loop.apply! (src/transformers.jl:378-383) rebuilds and applies the loop body once per element; in a filter the
+ * bodies differ only in constants (the observation).  A host can describe the body ONCE as a list of the statement
+ * calls above, with WS_TOK_PARAM tokens where the element's values go, and replay it per element with one call:
+ * ws_exec substitutes params[] and issues the statements exactly as the individual calls would (same fusion, same
+ * depth and tape bookkeeping, same results).  `i0, i1` are the call's integer arguments in order, `e[k]` its
+ * expression arguments in order with `n_e[k]` expressions behind each (0: the argument is NULL), `mat` the constant
+ * covariance of the MvNormal calls. */
+enum ws_cmd_fn {
+    WS_CMD_ASSIGN = 0,            /* ws_assign(i0 = col, i1 = comp, e[0])                         */
+    WS_CMD_ASSIGN_VEC = 1,        /* ws_assign_vec(i0 = col, i1 = d, e[0][d])                     */
+    WS_CMD_SAMPLE_NORMAL = 2,     /* ws_sample_normal(i0 = col, i1 = comp, e[0], e[1])            */
+    WS_CMD_SAMPLE_EXPONENTIAL = 3,/* ws_sample_exponential(i0 = col, i1 = comp, e[0])             */
+    WS_CMD_SAMPLE_MVNORMAL = 4,   /* ws_sample_mvnormal(i0 = col, i1 = d, e[0][d], mat)           */
+    WS_CMD_OBSERVE_NORMAL = 5,    /* ws_observe_normal(e[0], e[1], e[2])                          */
+    WS_CMD_OBSERVE_EXPONENTIAL = 6,/* ws_observe_exponential(e[0], e[1])                          */
+    WS_CMD_OBSERVE_MVNORMAL = 7,  /* ws_observe_mvnormal(i0 = d, e[0][d], e[1][d], mat)           */
+    WS_CMD_WEIGHT_EXPR = 8,       /* ws_weight_expr(e[0])                                         */
+    WS_CMD_SAMPLE_EXPR = 9,       /* ws_sample_expr(i0 = col, i1 = comp, e[0], e[1] | NULL, e[2] | NULL) */
+    WS_CMD_RESAMPLE = 10          /* ws_resample_async()                                          */
+};
+typedef struct ws_cmd {
+    int32_t fn; /* enum ws_cmd_fn */
+    int32_t i0, i1;
+    int32_t n_e[3];
+    const ws_expr* e[3];
+    const double* mat;
+} ws_cmd;
+int ws_exec(ws_ctx* ctx, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params);
 
 /* Resample.apply! (src/transformers.jl:474-498) — the exact state machine:
  * no-op if !weights_changed; else exp_norm -> ess_perc -> if ess < ess_perc_min: stratified

@@ -268,3 +268,35 @@ def test_ess_knife_edge_is_counted(ws):
     ws.Observe(0.5, "Normal", (ws.col("x"), 1.0)).apply(st)
     ws.Resample().apply(st)
     assert st.ess_ties() == 1 and st.stats()["resamples_done"] == 1
+
+
+# ------------------------------------------------------------------------------------------------
+# loop bodies described once and replayed per element (ws_exec) == the per-element rebuild
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,src,mk,cols", [c for c in CASES if c[0] in ("ssm2d", "lgssm1d", "ssm1d")], ids=["ssm2d", "lgssm1d", "ssm1d"])
+@pytest.mark.parametrize("ess", [0.5, 1.0])
+def test_loop_template_equals_per_element_rebuild(ws, name, src, mk, cols, ess):
+    import subprocess
+    import sys
+    args = mk(np.random.default_rng(8))
+    n = 30_011
+    a = _run(ws, src, args, n, seed=44, ess=ess)
+    # the switch is read when the package is imported: run the reference configuration in a fresh interpreter
+    code = f"""
+import sys, pickle, numpy as np
+sys.path.insert(0, {os.path.dirname(os.path.dirname(os.path.abspath(__file__)))!r}); sys.path.insert(0, {os.path.dirname(os.path.abspath(__file__))!r})
+import wsb200 as ws
+from wsb200 import core
+assert core.LOOP_TEMPLATES is False
+import test_gpu_kernel_forms as t
+case = [c for c in t.CASES if c[0] == {name!r}][0]
+st = t._run(ws, case[1], case[2](np.random.default_rng(8)), {n}, seed=44, ess={ess})
+pickle.dump(({{c: st[c] for c in case[3]}}, st.weights, ws.log_evidence(st), st.stats()["fused_passes"]), sys.stdout.buffer)
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, env=dict(os.environ, WSB200_LOOP_TEMPLATE="0"), check=True)
+    import pickle
+    cols_b, w_b, le_b, passes_b = pickle.loads(out.stdout)
+    for c in cols:
+        np.testing.assert_array_equal(a[c], cols_b[c], err_msg=f"{name}: column {c}")
+    np.testing.assert_array_equal(a.weights, w_b)
+    assert ws.log_evidence(a) == le_b and a.stats()["fused_passes"] == passes_b

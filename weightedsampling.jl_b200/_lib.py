@@ -35,7 +35,7 @@ RESAMPLER = {"stratified": 0, "systematic": 1, "multinomial": 2}
 TOK_CONST, TOK_PLANE, TOK_ADD, TOK_SUB, TOK_MUL, TOK_DIV, TOK_NEG, TOK_EXP, TOK_LOG, TOK_SQRT, TOK_SQUARE, \
     TOK_SIN, TOK_COS, TOK_ABS, TOK_POW, TOK_RANDN, TOK_RANDU, TOK_RANDEXP, TOK_LT, TOK_LE, TOK_EQ, TOK_SELECT, TOK_MIN, \
     TOK_MAX, TOK_NOT, TOK_LGAMMA, TOK_LOG1P, TOK_EXPM1, TOK_TAN, TOK_ATAN, TOK_TANH, TOK_FLOOR, TOK_RANDGAMMA, \
-    TOK_RANDPOISSON = range(34)
+    TOK_RANDPOISSON, TOK_PARAM = range(35)
 
 
 class ws_plane_stats(C.Structure):
@@ -55,6 +55,17 @@ class ws_expr(C.Structure):
 class ws_resample_info(C.Structure):
     _fields_ = [("fired", C.c_int32), ("resampled", C.c_int32), ("ess_perc", C.c_double),
                 ("log_mean_w", C.c_double), ("n_clamped", C.c_int64)]
+
+
+class ws_cmd(C.Structure):
+    _fields_ = [("fn", C.c_int32), ("i0", C.c_int32), ("i1", C.c_int32), ("n_e", C.c_int32 * 3),
+                ("e", C.POINTER(ws_expr) * 3), ("mat", C.POINTER(C.c_double))]
+
+
+# statement call -> (ws_cmd_fn code, how its arguments map onto a ws_cmd): see include/wsb200.h `enum ws_cmd_fn`
+CMD_FN = {"ws_assign": 0, "ws_assign_vec": 1, "ws_sample_normal": 2, "ws_sample_exponential": 3, "ws_sample_mvnormal": 4,
+          "ws_observe_normal": 5, "ws_observe_exponential": 6, "ws_observe_mvnormal": 7, "ws_weight_expr": 8,
+          "ws_sample_expr": 9, "ws_resample_async": 10}
 
 
 class ws_move_spec(C.Structure):
@@ -127,6 +138,7 @@ SIGNATURES = {
                                               C.c_double]),
     "ws_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),
     "ws_resample_async": (C.c_int, [_ctx]),
+    "ws_exec": (C.c_int, [_ctx, C.POINTER(ws_cmd), C.c_int32, C.POINTER(C.c_double), C.c_int32]),
     "ws_last_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),
     "ws_exp_norm": (C.c_int, [_ctx, C.c_void_p]),
     "ws_log_evidence": (C.c_int, [_ctx, _dp, _dp]),

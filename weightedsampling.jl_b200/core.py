@@ -14,6 +14,7 @@ the ``ccall`` shim with the same structure.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -742,8 +743,180 @@ class Sequence(ParticleTransformer):
             s.score(state, ctx)
 
 
+# -- loop bodies described once, replayed per element (include/wsb200.h: ws_exec) ---------------------------------
+class _Recorder:
+    """Stands in for the store while a loop body built over SYMBOLIC element values is applied: statement calls are
+    recorded as ws_cmd entries instead of being issued; anything else a body might do aborts the recording."""
+
+    # (i0, i1 positions among the call's integer arguments come first, then the expression pointers in order)
+    def __init__(self, store):
+        self.store, self.cmds, self.keep = store, [], []
+        self.n = store.n
+
+    def _lookup(self, name):
+        return self.store._lookup(name)
+
+    def _ensure(self, name, width):
+        cid, w = self.store._lookup(name)
+        if cid < 0 or w != width:
+            raise _NoTemplate("the body creates a column")      # columns must exist before the body is templated
+        return cid
+
+    def colnames(self):
+        return self.store.colnames()
+
+    def _call(self, name, *args):
+        fn = L.CMD_FN.get(name)
+        if fn is None:
+            raise _NoTemplate(f"{name} inside a loop body")
+        ints = [a for a in args if isinstance(a, int)]
+        ptrs = [a for a in args if not isinstance(a, int)]
+        d = 1
+        if name in ("ws_assign_vec", "ws_sample_mvnormal"):
+            d = ints[1]
+        elif name == "ws_observe_mvnormal":
+            d = ints[0]
+        mat = None
+        if name in ("ws_sample_mvnormal", "ws_observe_mvnormal"):
+            mat = ptrs.pop()
+        self.cmds.append((fn, ints, ptrs, d, mat))
+        self.keep.append(args)
+
+
+class _NoTemplate(Exception):
+    pass
+
+
+class _RecState:
+    """what a statement's ``apply`` touches of an SMCState, over a recorder"""
+
+    def __init__(self, store):
+        self.store = store
+
+
+def _symbolic_like(x):
+    """(symbolic stand-in for the loop element x with Param leaves, flatten(x') -> list of floats or None)"""
+    from .expr import Param
+    counter = [0]
+
+    def sym(v):
+        if isinstance(v, (bool, np.bool_)):
+            raise _NoTemplate("a Bool loop element")
+        if isinstance(v, (int, np.integer)):
+            raise _NoTemplate("an integer loop element (it may index or name something at build time)")
+        if isinstance(v, (float, np.floating)):
+            counter[0] += 1
+            return Param(counter[0] - 1)
+        if isinstance(v, np.ndarray):
+            if v.ndim != 1 or v.dtype.kind != "f":
+                raise _NoTemplate("a non-vector array loop element")
+            return [sym(float(t)) for t in v]
+        if isinstance(v, (tuple, list)):
+            out = [sym(t) for t in v]
+            return tuple(out) if isinstance(v, tuple) else out
+        raise _NoTemplate(f"a loop element of type {type(v).__name__}")
+
+    def shape(v):
+        if isinstance(v, (float, np.floating)) and not isinstance(v, (bool, np.bool_)):
+            return "f"
+        if isinstance(v, np.ndarray) and v.ndim == 1 and v.dtype.kind == "f":
+            return ("a", v.shape[0])
+        if isinstance(v, (tuple, list)):
+            return (type(v).__name__, tuple(shape(t) for t in v))
+        return None
+
+    s = sym(x)
+    want = shape(x)
+
+    def flatten(v):
+        if shape(v) != want:
+            return None
+        out = []
+
+        def walk(t):
+            if isinstance(t, (tuple, list)):
+                for u in t:
+                    walk(u)
+            elif isinstance(t, np.ndarray):
+                out.extend(float(u) for u in t)
+            else:
+                out.append(float(t))
+        walk(v)
+        return out
+    return s, flatten, counter[0]
+
+
+_TEMPLATE_OK = ("Sequence", "Assign", "Sample", "Observe", "Weight", "Resample")
+
+
+def _only_statements(t):
+    k = type(t).__name__
+    if k not in _TEMPLATE_OK:
+        return False
+    return all(_only_statements(s) for s in t.steps) if k == "Sequence" else True
+
+
+class _LoopTemplate:
+    """The body of a loop as one ws_cmd array with WS_TOK_PARAM holes for the element's values."""
+
+    def __init__(self, bodyfn, x, store):
+        sym, self.flatten, self.n_params = _symbolic_like(x)
+        try:
+            body = bodyfn(sym)
+        except (UnsupportedModelError, _NoTemplate):
+            raise
+        except Exception as e:          # the body uses the element at build time (indexing, names, arithmetic on it, ...)
+            raise _NoTemplate(f"{type(e).__name__}: {e}")
+        if not _only_statements(body):
+            raise _NoTemplate("the body contains control flow or moves")
+        rec = _Recorder(store)
+        try:
+            body.apply(_RecState(rec))
+        except (UnsupportedModelError, _NoTemplate):
+            raise
+        except Exception as e:
+            raise _NoTemplate(f"{type(e).__name__}: {e}")
+        if not rec.cmds:
+            raise _NoTemplate("empty body")
+        self.keep = rec.keep
+        self.arr = (L.ws_cmd * len(rec.cmds))()
+        for c, (fn, ints, ptrs, d, mat) in zip(self.arr, rec.cmds):
+            c.fn = fn
+            c.i0 = ints[0] if len(ints) > 0 else 0
+            c.i1 = ints[1] if len(ints) > 1 else 0
+            for k, p in enumerate(ptrs):
+                if p is None:
+                    c.n_e[k] = 0
+                else:
+                    c.n_e[k] = d
+                    c.e[k] = p
+            if mat is not None:
+                c.mat = C.cast(mat, C.POINTER(C.c_double))
+        self.n = len(rec.cmds)
+        self.store = store
+        self._params = (C.c_double * max(1, self.n_params))()
+
+    def run(self, x):
+        vals = self.flatten(x)
+        if vals is None:
+            return False
+        self._params[:len(vals)] = vals
+        self.store._call("ws_exec", self.arr, self.n, self._params, self.n_params)
+        return True
+
+
+LOOP_TEMPLATES = os.environ.get("WSB200_LOOP_TEMPLATE", "1") != "0"
+
+
 class Loop(ParticleTransformer):
-    """``for x in coll ... end`` (transformers.jl:367-398); the body is rebuilt per iteration."""
+    """``for x in coll ... end`` (transformers.jl:367-398); the body is rebuilt per iteration.
+
+    When the elements are plain numbers / vectors and the body is a straight list of statements that uses them only
+    as constants (a filter step: ``o => Normal(x, r)``), rebuilding it per element would produce the same statement
+    calls with different constants.  From the second element on such a body is described ONCE (built over symbolic
+    element values, recorded instead of issued) and replayed per element with one C call (``ws_exec``): the
+    statements issued, their order and their results are those of the per-element rebuild; a body that does anything
+    else with its element (an index, a column name ``x{t}``, ``if``, ``<<``) is rebuilt per element as before."""
 
     def __init__(self, collfn, bodyfn):
         self.collfn, self.bodyfn = collfn, bodyfn
@@ -752,8 +925,22 @@ class Loop(ParticleTransformer):
         return self.collfn(state) if callable(self.collfn) else self.collfn
 
     def apply(self, state):
-        for x in self._coll(state):
-            self.bodyfn(x).apply(state)
+        coll = self._coll(state)
+        if not LOOP_TEMPLATES or not isinstance(state.store, DeviceColumnStore) or not hasattr(coll, "__len__") or len(coll) < 4:
+            for x in coll:
+                self.bodyfn(x).apply(state)
+            return
+        it = iter(coll)
+        self.bodyfn(next(it)).apply(state)          # the first element runs as written (it may create the columns)
+        tmpl = None
+        for x in it:
+            if tmpl is None:
+                try:
+                    tmpl = _LoopTemplate(self.bodyfn, x, state.store)
+                except _NoTemplate:
+                    tmpl = False
+            if tmpl is False or not tmpl.run(x):
+                self.bodyfn(x).apply(state)
 
     def score(self, state, ctx):
         for x in self._coll(state):

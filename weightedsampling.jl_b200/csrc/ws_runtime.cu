@@ -2230,6 +2230,61 @@ extern "C" int ws_resample_async(ws_ctx* c) {
     return WS_OK;
 }
 
+// A statement list with parameters (Loop bodies): substitute, then issue each statement through its own entry point.
+extern "C" int ws_exec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params) {
+    if (!c || (!cmds && n_cmds > 0) || n_cmds < 0) return WS_EINVAL;
+    std::vector<ws_tok> toks;
+    std::vector<ws_expr> ex;
+    for (int32_t k = 0; k < n_cmds; ++k) {
+        const ws_cmd& cm = cmds[k];
+        // copy the command's expressions with the parameters filled in (offsets first: the pool may reallocate)
+        toks.clear();
+        ex.clear();
+        size_t first[3] = {0, 0, 0};
+        std::vector<size_t> off;
+        for (int a = 0; a < 3; ++a) {
+            first[a] = ex.size();
+            if (cm.n_e[a] < 0 || (cm.n_e[a] > 0 && cm.e[a] == nullptr)) return fail(c, WS_EINVAL, "ws_exec: command %d has a bad expression list", k);
+            for (int32_t j = 0; j < cm.n_e[a]; ++j) {
+                const ws_expr& src = cm.e[a][j];
+                if (src.toks == nullptr || src.n <= 0) return fail(c, WS_EINVAL, "ws_exec: command %d has an empty expression", k);
+                off.push_back(toks.size());
+                for (int32_t i = 0; i < src.n; ++i) {
+                    ws_tok t = src.toks[i];
+                    if (t.op == WS_TOK_PARAM) {
+                        if (t.col < 0 || t.col >= n_params || params == nullptr)
+                            return fail(c, WS_EINVAL, "ws_exec: parameter %d of %d", t.col, n_params);
+                        t.op = WS_TOK_CONST;
+                        t.val = params[t.col];
+                        t.col = 0;
+                    }
+                    toks.push_back(t);
+                }
+                ex.push_back(ws_expr{nullptr, src.n, 0});
+            }
+        }
+        for (size_t j = 0; j < ex.size(); ++j) ex[j].toks = toks.data() + off[j];
+        const ws_expr* e0 = cm.n_e[0] > 0 ? &ex[first[0]] : nullptr;
+        const ws_expr* e1 = cm.n_e[1] > 0 ? &ex[first[1]] : nullptr;
+        const ws_expr* e2 = cm.n_e[2] > 0 ? &ex[first[2]] : nullptr;
+        switch (cm.fn) {
+            case WS_CMD_ASSIGN: TRY(ws_assign(c, cm.i0, cm.i1, e0)); break;
+            case WS_CMD_ASSIGN_VEC: TRY(ws_assign_vec(c, cm.i0, cm.i1, e0)); break;
+            case WS_CMD_SAMPLE_NORMAL: TRY(ws_sample_normal(c, cm.i0, cm.i1, e0, e1)); break;
+            case WS_CMD_SAMPLE_EXPONENTIAL: TRY(ws_sample_exponential(c, cm.i0, cm.i1, e0)); break;
+            case WS_CMD_SAMPLE_MVNORMAL: TRY(ws_sample_mvnormal(c, cm.i0, cm.i1, e0, cm.mat)); break;
+            case WS_CMD_OBSERVE_NORMAL: TRY(ws_observe_normal(c, e0, e1, e2)); break;
+            case WS_CMD_OBSERVE_EXPONENTIAL: TRY(ws_observe_exponential(c, e0, e1)); break;
+            case WS_CMD_OBSERVE_MVNORMAL: TRY(ws_observe_mvnormal(c, cm.i0, e0, e1, cm.mat)); break;
+            case WS_CMD_WEIGHT_EXPR: TRY(ws_weight_expr(c, e0)); break;
+            case WS_CMD_SAMPLE_EXPR: TRY(ws_sample_expr(c, cm.i0, cm.i1, e0, e1, e2)); break;
+            case WS_CMD_RESAMPLE: TRY(ws_resample_async(c)); break;
+            default: return fail(c, WS_EINVAL, "ws_exec: unknown command %d", cm.fn);
+        }
+    }
+    return WS_OK;
+}
+
 extern "C" int ws_last_resample(ws_ctx* c, ws_resample_info* info) {
     if (!c || !info) return WS_EINVAL;
     if (c->last_info_pending) TRY(resolve_spec(c));

@@ -109,6 +109,14 @@ class Rand(Expr):
         self.kind = kind
 
 
+class Param(Expr):
+    """Placeholder for a build-time constant that is supplied later (``WS_TOK_PARAM``): the loop variable of a loop
+    body that is described once and replayed per element (core.Loop / ``ws_exec``)."""
+
+    def __init__(self, index):
+        self.index = int(index)
+
+
 class RandP(Expr):
     """A variate with a (per-particle) parameter inside a sampler expression: kind 'gamma' = standard
     Gamma(shape), 'poisson' = Poisson(rate) (device rejection samplers on Philox sub-counters)."""
@@ -247,6 +255,8 @@ def lower(e, store):
         return base[e.j]
     if isinstance(e, Rand):
         return Tokens([({"n": L.TOK_RANDN, "u": L.TOK_RANDU, "e": L.TOK_RANDEXP}[e.kind], 0, 0, 0.0)])
+    if isinstance(e, Param):
+        return Tokens([(L.TOK_PARAM, e.index, 0, 0.0)])
     if isinstance(e, RandP):
         a = lower(e.arg, store)
         if isinstance(a, list):
@@ -325,4 +335,6 @@ class CExprs:
         self.arr = (L.ws_expr * len(counts)).from_buffer_copy(_EXPR_STRUCT(len(counts)).pack(*head))
 
     def ptr(self, i=0):
-        return C.cast(C.byref(self.arr, i * C.sizeof(L.ws_expr)), C.POINTER(L.ws_expr))
+        p = C.cast(C.byref(self.arr, i * C.sizeof(L.ws_expr)), C.POINTER(L.ws_expr))
+        p._owner = self      # whoever keeps the pointer (a recorded loop body) keeps the token buffers alive
+        return p
