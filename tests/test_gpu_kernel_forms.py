@@ -300,3 +300,41 @@ pickle.dump(({{c: st[c] for c in case[3]}}, st.weights, ws.log_evidence(st), st.
         np.testing.assert_array_equal(a[c], cols_b[c], err_msg=f"{name}: column {c}")
     np.testing.assert_array_equal(a.weights, w_b)
     assert ws.log_evidence(a) == le_b and a.stats()["fused_passes"] == passes_b
+
+
+# ------------------------------------------------------------------------------------------------
+# small particle sets: the Resample step as ONE kernel == the multi-kernel resampler
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,src,mk,cols", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("n", [1, 2, 300, 2049, 16_384])
+@pytest.mark.parametrize("ess", [0.5, 1.0])
+def test_single_kernel_resample_equals_multi_kernel(ws, name, src, mk, cols, n, ess):
+    args = mk(np.random.default_rng(6))
+    a = _run(ws, src, args, n, seed=55, ess=ess)
+    b = _run(ws, src, args, n, seed=55, ess=ess, WSB200_SMALL_RESAMPLE="0")
+    for c in cols:
+        np.testing.assert_array_equal(a[c], b[c], err_msg=f"{name}: column {c}")
+    np.testing.assert_array_equal(a.weights, b.weights)
+    assert ws.log_evidence(a) == ws.log_evidence(b)
+    assert a.stats()["resamples_done"] == b.stats()["resamples_done"]
+    assert a.stats()["kernel_launches"] < b.stats()["kernel_launches"] or a.stats()["resamples_fired"] == 0
+
+
+@pytest.mark.parametrize("scheme", ["stratified", "systematic"])
+def test_single_kernel_resample_one_hot_and_spec(ws, scheme):
+    """ancestors of the one-kernel step against the big-integer specification, inside a run (ids through the gather)"""
+    import ctypes as C
+    from oracle import ref
+    n = 5000
+    for s in (0.5, 3.0, None):
+        st = ws.SMCState(n, ess_perc_min=float("inf"), seed=3, resampler=scheme, device=0)
+        st.store.setcol("id", np.arange(n, dtype=np.float64))
+        lw = s * np.random.default_rng(2).standard_normal(n) if s is not None else np.where(np.arange(n) == 1234, 0.0, -12.0)
+        st.weights = lw
+        st.weights_changed = True
+        stream, seed = C.c_uint64(), C.c_uint64()
+        st.store._call("ws_next_philox_stream", C.byref(stream), C.byref(seed))
+        ws.Resample().apply(st)
+        ids = st["id"].astype(np.int64)
+        a_ref, _ = ref.stratified_ancestors_fixed_point(ref.exp_norm(lw), seed.value, stream.value, scheme)
+        np.testing.assert_array_equal(ids, a_ref)

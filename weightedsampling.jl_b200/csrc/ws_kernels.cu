@@ -1512,6 +1512,119 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
     if (warp_base < n) ws_search_warp_tile<EXACT_FP, false>(P, X, win_all[warp], lane, warp_base, C, prefix + warp_excl, warp_base != 0);
 }
 
+// ---- small particle sets: the whole Resample step in ONE kernel --------------------------------------------------
+// Below WS_SMALL_N particles a step is launch-latency bound: finalize, two memsets, tile CDF, offsets, search, heavy
+// expansion and the identity fill are eight stream operations of a few microseconds each.  One CTA does all of it:
+// the (m, S, Q) combination (the very code of ws_finalize_kernel: same order, same bits), the decision, the
+// fixed-point CDF in chunks with a running carry, F(C_m) per particle through the same ws_F_int, and the expansion by a
+// binary search of every slot in the F table.  Ancestors are bit-identical to the large-N kernels (integer sums).
+__global__ void __launch_bounds__(256) ws_resample_small_kernel(const __grid_constant__ WsScanParams P, const WsLse* __restrict__ partials,
+                                                                int n_partials, double ess_perc_min, WsReduceOut* __restrict__ out,
+                                                                unsigned long long* ties, int do_finalize, int32_t* __restrict__ Ftab) {
+    __shared__ WsLse warp_scratch[8];
+    __shared__ unsigned long long warp_tot[8];
+    __shared__ unsigned long long s_carry;
+    __shared__ int s_fire;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (do_finalize) {
+        WsLse part;
+        part.m = -INFINITY;
+        part.S = 0.0;
+        part.Q = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += 256) part = lse_combine(part, partials[i]);
+        WsLse tot = lse_block_reduce<256>(part, warp_scratch);
+        if (threadIdx.x == 0) {
+            out->m = tot.m;
+            out->S = tot.S;
+            out->Q = tot.Q;
+            const double lse = tot.m + log(tot.S);
+            out->lse = lse;
+            const double nn = (double)P.n_slots;
+            out->ess_perc = (tot.S * tot.S) / (nn * tot.Q);
+            out->log_mean_w = lse - log(nn);
+            out->do_resample = (out->ess_perc < ess_perc_min) ? 1 : 0;
+            ws_count_ess_tie(out->ess_perc, ess_perc_min, ties);
+            __threadfence_block();
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        s_fire = (P.gate == 0 || out->do_resample != 0) ? 1 : 0;
+        s_carry = 0ull;
+    }
+    __syncthreads();
+    const int n = (int)P.n, ns = (int)P.n_slots;
+    if (!s_fire) {
+        for (int i = threadIdx.x; i < n; i += 256) P.ancestors[i] = i;   // a step that does not fire: the identity
+        return;
+    }
+    const double m = out->m, Sden = out->S, rS = 1.0 / out->S;
+    const int sh = P.fx_shift - 32;
+    const unsigned int rmask = sh >= 0 ? 0xFFFFFFFFu : ~((1u << (-sh)) - 1u);
+    unsigned int r0 = 0u;
+    if (P.scheme == 1) r0 = ws_philox4x32_10(0ull, P.stream, P.seed).x;
+    for (int base = 0; base < n; base += 256 * WS_SCAN_ITEMS) {
+        const int item0 = base + threadIdx.x * WS_SCAN_ITEMS;
+        unsigned long long q[WS_SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            const int i = item0 + k;
+            q[k] = (i < n) ? ws_w_to_fxs(ws_div_pos(ws_exp_nonpos(P.logw[i] - m), Sden, rS), P.fx_scale) : 0ull;
+        }
+#pragma unroll
+        for (int k = 1; k < WS_SCAN_ITEMS; ++k) q[k] += q[k - 1];
+        const unsigned long long thread_total = q[WS_SCAN_ITEMS - 1];
+        unsigned long long incl = thread_total;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        __syncthreads();   // warp_tot / s_carry of the previous chunk have been consumed
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        unsigned long long warp_excl = 0ull, chunk_tot = 0ull;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const unsigned long long t = warp_tot[w];
+            if (w < warp) warp_excl += t;
+            chunk_tot += t;
+        }
+        const unsigned long long excl = s_carry + warp_excl + (incl - thread_total);
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            const int i = item0 + k;
+            if (i < n) {
+                int fk = ws_F_int(excl + q[k], (unsigned int)ns, sh, rmask, P.scheme == 1 ? 1 : 0, r0, P.seed, P.stream);
+                if (i == n - 1) {
+                    if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
+                    fk = ns;   // leftover slots go to the last particle
+                }
+                Ftab[i] = fk;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += chunk_tot;
+    }
+    __syncthreads();
+    // slot j belongs to the first particle m with F(C_m) > j
+    for (int j = threadIdx.x; j < ns; j += 256) {
+        int lo = 0, hi = n - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (Ftab[mid] > j) hi = mid; else lo = mid + 1;
+        }
+        P.ancestors[j] = lo;
+    }
+}
+
+cudaError_t ws_launch_resample_small(const WsScanParams& P, const WsLse* partials, int n_partials, double ess_perc_min, WsReduceOut* out,
+                                     unsigned long long* ties, int do_finalize, cudaStream_t s) {
+    ws_resample_small_kernel<<<1, 256, 0, s>>>(P, partials, n_partials, ess_perc_min, out, ties, do_finalize,
+                                               reinterpret_cast<int32_t*>(P.cdf_local));
+    return cudaGetLastError();
+}
+
 // Slots of the heavy tiles (see above): every CTA takes an equal slice of each heavy tile's output
 // window and finds the ancestors by binary search in the tile's F table.
 __global__ void __launch_bounds__(256) ws_expand_heavy_kernel(const __grid_constant__ WsScanParams P) {

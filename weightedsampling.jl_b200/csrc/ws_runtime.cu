@@ -184,6 +184,7 @@ struct ws_ctx {
     int spec_pending = 0;
     bool logw_spec = false;
     bool async_resample = true;     // env WSB200_ASYNC_RESAMPLE=0: ws_resample_async behaves like ws_resample
+    bool small_resample = true;     // env WSB200_SMALL_RESAMPLE=0: small particle sets use the multi-kernel resampler too
     ws_resample_info last_info{};   // outcome of the most recent Resample step (ws_last_resample)
     bool last_info_pending = false; // ... which is the newest unresolved record
     // A model that reads `resampled` after every step (`if resampled ... end`, examples/linear_regression.jl:22)
@@ -538,6 +539,8 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     {
         const char* v = getenv("WSB200_ASYNC_RESAMPLE");
         c->async_resample = !(v != nullptr && strcmp(v, "0") == 0);
+        v = getenv("WSB200_SMALL_RESAMPLE");
+        c->small_resample = !(v != nullptr && strcmp(v, "0") == 0);
     }
     if (nranks > 1) c->spare = std::max<int64_t>(4096, c->n / 32);
     // sharded: a margin of `spare` entries on BOTH sides, so that the search can write the ancestors of the slots
@@ -1618,6 +1621,34 @@ static int gather_all(ws_ctx* c, const int32_t* d_anc) {
     return gather_planes(c, d_anc, which);
 }
 
+// Small particle sets: reduce-finalize (optional), CDF, search and expansion of a Resample step in one kernel.
+static bool small_resample_ok(const ws_ctx* c, const double* d_ru) {
+    return c->small_resample && c->nranks == 1 && c->n <= WS_SMALL_N && d_ru == nullptr && c->resampler != WS_RESAMPLER_MULTINOMIAL;
+}
+static int run_small_resample(ws_ctx* c, uint64_t stream_id, int gate, int do_finalize) {
+    WsScanParams S;
+    memset(&S, 0, sizeof(S));
+    S.logw = c->logw;
+    S.mode = 0;
+    S.scheme = c->resampler;
+    S.red = c->d_red;
+    S.gate = gate;
+    S.n = c->n;
+    S.n_slots = c->n;
+    S.last_rank = 1;
+    S.seed = c->seed;
+    S.stream = stream_id;
+    S.ancestors = c->d_anc;
+    S.cdf_local = c->d_cdf_local;
+    S.n_clamped = c->d_counters + 0;
+    ws_scan_set_scale(S);
+    TimedEvent te;
+    timed_begin(c, KC_SCAN, te);
+    CK(c, ws_launch_resample_small(S, c->d_partials, c->n_partials, c->ess_perc_min, c->d_red, c->d_counters + 3, do_finalize, c->stream));
+    timed_end(c, te);
+    return WS_OK;
+}
+
 // Multinomial resampling with Philox draws: point S at the spacing tables (sized for S.n_slots) and fill them.
 static int prepare_multinomial(ws_ctx* c, WsScanParams& S) {
     const int64_t n_all = S.n_slots + 1;
@@ -2151,7 +2182,11 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
             TRY(sorted_replay_uniforms(c, d_ru, c->n, &d_sorted));   // replayed draws (tests): sorted on the host
             d_ru = nullptr;
         }
-        TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, d_sorted, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id, c->d_counters + 0));
+        if (small_resample_ok(c, d_ru) && d_sorted == nullptr) {
+            TRY(run_small_resample(c, stream_id, 0, 0));
+        } else {
+            TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, d_ru, d_sorted, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id, c->d_counters + 0));
+        }
         // resample!(store, indices) is deferred: each plane is gathered when it is next read
         end_resample_event(c);
         if (!c->lazy_gather) TRY(materialize_planes(c));
@@ -2207,20 +2242,29 @@ extern "C" int ws_resample_async(ws_ctx* c) {
         c->n_partials = grid;
         c->partials_valid = true;
     }
-    TimedEvent te;
-    timed_begin(c, KC_FINALIZE, te);
-    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream, c->d_counters + 3));
-    timed_end(c, te);
-    CK(c, cudaMemcpyAsync(&c->h_ring[c->spec_head % ws_ctx::SPEC_RING], c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
-    c->ring_event[c->spec_head % ws_ctx::SPEC_RING] = c->epoch + 1;
+    const uint64_t stream_id = c->next_stream++;
+    if (small_resample_ok(c, nullptr)) {
+        // one kernel: finalize + decision + CDF + search + expansion (or the identity); then the record for the host
+        TRY(begin_resample_event(c));
+        TRY(run_small_resample(c, stream_id, /*gate=*/1, /*do_finalize=*/1));
+        CK(c, cudaMemcpyAsync(&c->h_ring[c->spec_head % ws_ctx::SPEC_RING], c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
+        c->ring_event[c->spec_head % ws_ctx::SPEC_RING] = c->epoch + 1;
+        end_resample_event(c);
+    } else {
+        TimedEvent te;
+        timed_begin(c, KC_FINALIZE, te);
+        CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream, c->d_counters + 3));
+        timed_end(c, te);
+        CK(c, cudaMemcpyAsync(&c->h_ring[c->spec_head % ws_ctx::SPEC_RING], c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
+        c->ring_event[c->spec_head % ws_ctx::SPEC_RING] = c->epoch + 1;
+        TRY(begin_resample_event(c));
+        TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, nullptr, nullptr, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id,
+                            c->d_counters + 0, /*gate=*/1));
+        end_resample_event(c);
+    }
     c->spec_head++;
     c->spec_pending++;
     c->stats.resamples_fired++;
-    const uint64_t stream_id = c->next_stream++;
-    TRY(begin_resample_event(c));
-    TRY(run_scan_search(c, c->logw, 0, c->resampler, c->n, nullptr, nullptr, c->d_anc, c->d_tile_words, c->d_cdf_local, stream_id,
-                        c->d_counters + 0, /*gate=*/1));
-    end_resample_event(c);
     c->logw_uniform = false;
     c->logw_spec = true;
     c->partials_valid = false;
