@@ -3,7 +3,8 @@
 * the fused elementwise window: straight-line executors (csrc/ws_vm_sl.cuh: compile-time signatures, register file
   in registers) against the interpreter (ws_vm_kernel), selected with WSB200_VM=interp at context creation;
 * CDF + ancestor search: the single-pass kernel (ticketed tiles + decoupled look-back, ws_scan_search_kernel,
-  WSB200_SCAN=1pass) against the three-pass form (the default, and what sharded runs use).
+  WSB200_SCAN=1pass) and the chain form (persistent CTAs, look-back deferred by one tile, ws_chain_kernel,
+  WSB200_SCAN=chain) against the three-pass form (WSB200_SCAN=3pass, what sharded runs use).
 
 Both pairs share their arithmetic by construction (the same ws_vm_exec_d / integer prefix sums), so the comparison
 is exact: every particle, every ancestor (only the grid-shaped (m, S, Q) reduction may differ in the last place).
@@ -85,6 +86,9 @@ def test_straight_line_equals_interpreter(ws, name, src, mk, cols, n, ess):
     assert sa["resamples_done"] == sb["resamples_done"]
 
 
+SCAN_FORMS = ({"WSB200_SCAN": "3pass"}, {"WSB200_SCAN": "1pass"}, {"WSB200_SCAN": "chain"})
+
+
 @pytest.mark.parametrize("n", [1, 2, 255, 2048, 2049, 100_003, 3_000_000])
 @pytest.mark.parametrize("s", [0.5, 3.0])
 @pytest.mark.parametrize("scheme", ["stratified", "systematic"])
@@ -92,14 +96,30 @@ def test_single_pass_scan_search_equals_three_pass(ws, n, s, scheme):
     w = np.exp(s * np.random.default_rng(n).standard_normal(n))
     w /= w.sum()
     out = []
-    for kv in ({}, {"WSB200_SCAN": "1pass"}):
+    for kv in SCAN_FORMS:
         with env(**kv):
             st = ws.SMCState(max(n, 2), seed=5, device=0)
         out.append(ws.resample_indices(w, st, scheme))
         r = np.random.default_rng(1).random(n if scheme == "stratified" else 1)
         out.append(ws.resample_indices(w, st, scheme, uniforms=r))
-    np.testing.assert_array_equal(out[0], out[2])   # Philox (integer grid)
-    np.testing.assert_array_equal(out[1], out[3])   # replayed uniforms (reference's floating-point grid)
+    for f in range(1, len(SCAN_FORMS)):
+        np.testing.assert_array_equal(out[0], out[2 * f], err_msg=str(SCAN_FORMS[f]))       # Philox (integer grid)
+        np.testing.assert_array_equal(out[1], out[2 * f + 1], err_msg=str(SCAN_FORMS[f]))   # replayed uniforms (reference's floating-point grid)
+
+
+@pytest.mark.parametrize("n", [5000, 100_003, 2_000_000])
+@pytest.mark.parametrize("ess", [0.5, 1.0])
+@pytest.mark.parametrize("form", ["1pass", "chain"])
+def test_scan_forms_inside_a_filter(ws, n, ess, form):
+    """the whole filter (log-weights -> exp_norm weights -> fixed point inside the scan kernels, mode 0), every column"""
+    args = ([np.random.default_rng(2).standard_normal(2) + np.array([t, 0.0]) for t in range(10)],)
+    a = _run(ws, SSM2D_FILTER, args, n, seed=17, ess=ess, WSB200_SCAN="3pass", WSB200_SMALL_RESAMPLE="0")
+    b = _run(ws, SSM2D_FILTER, args, n, seed=17, ess=ess, WSB200_SCAN=form, WSB200_SMALL_RESAMPLE="0")
+    for c in ("x", "v"):
+        np.testing.assert_array_equal(a[c], b[c], err_msg=c)
+    np.testing.assert_array_equal(a.weights, b.weights)
+    assert ws.log_evidence(a) == ws.log_evidence(b)
+    assert a.stats()["resamples_done"] == b.stats()["resamples_done"] > 0
 
 
 def test_single_pass_one_hot_and_zero_weights(ws):
@@ -109,11 +129,12 @@ def test_single_pass_one_hot_and_zero_weights(ws):
     w[::7] += 0.03 / len(w[::7])
     w /= w.sum()
     res = []
-    for kv in ({}, {"WSB200_SCAN": "1pass"}):
+    for kv in SCAN_FORMS:
         with env(**kv):
             st = ws.SMCState(n, seed=9, device=0)
         res.append(ws.resample_indices(w, st, "stratified"))
-    np.testing.assert_array_equal(res[0], res[1])
+    for r in res[1:]:
+        np.testing.assert_array_equal(res[0], r)
     assert (res[0] == 123_456).sum() > 0.96 * n
     assert np.all(w[res[0]] > 0)
 
@@ -127,7 +148,7 @@ def test_integer_slot_grid_small_shift(ws, n, extra):
     from oracle import ref
     w = np.exp(2.0 * np.random.default_rng(n + extra).standard_normal(n))
     w /= w.sum()
-    for kv in ({}, {"WSB200_SCAN": "1pass"}):
+    for kv in SCAN_FORMS:
         with env(WSB200_FX_EXTRA_BITS=str(extra), **kv):
             st = ws.SMCState(n, seed=13, device=0)
         stream, seed = C.c_uint64(), C.c_uint64()

@@ -134,6 +134,7 @@ cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_
 cudaError_t ws_launch_resample_small(const WsScanParams& P, const WsLse* partials, int n_partials, double ess_perc_min, WsReduceOut* out,
                                      unsigned long long* ties, int do_finalize, cudaStream_t s);
 void ws_scan_set_scale(WsScanParams& P);
+size_t ws_scan_words(int64_t n);  // 8-byte words of WsScanParams::tile_words for n particles (tile words + the chain form's group words)
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s);
 // sharded resampling runs the same passes in two halves with collectives in between
 cudaError_t ws_launch_spacings(const WsScanParams& P, cudaStream_t s);  // multinomial: spacing prefixes of all global slots

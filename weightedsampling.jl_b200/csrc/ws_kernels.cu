@@ -1014,6 +1014,9 @@ __device__ __forceinline__ void ws_search_setup(const WsScanParams& P, WsSearchC
     }
 }
 
+#ifndef WS_INTERIOR_FAST
+#define WS_INTERIOR_FAST 1   // 0: every tile takes the range-checked search (A/B)
+#endif
 // One warp, one tile of WS_SCAN_TILE consecutive particles starting at `tile_base`, lane L holding the global
 // fixed-point CDF C[k] of particles tile_base + 8 L + k: per-particle slot counts F(C_m), then the offspring slots
 // [F(C_{m-1}), F(C_m)) of every particle are written to P.ancestors.  `Cp` (lane 0; valid iff has_prev) is the CDF of
@@ -1022,7 +1025,7 @@ template <bool EXACT_FP, bool MN>
 __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSearchCtx& X, unsigned long long* const rbuf,
                                                     const int lane, const int tile_base,
                                                     const unsigned long long (&C)[WS_SCAN_ITEMS], const unsigned long long Cp,
-                                                    const bool has_prev) {
+                                                    const bool has_prev, const bool interior = false) {
     int32_t* const out_s = reinterpret_cast<int32_t*>(rbuf);
     unsigned int* const rbuf32 = reinterpret_cast<unsigned int*>(rbuf);
     SlotUniform& su = X.su;
@@ -1117,7 +1120,51 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
             __syncwarp();  // the window is reused for the offspring below
         }
     }
-    if (!EXACT_FP && !MN && su.scheme == 0) {
+    if (!EXACT_FP && !MN && su.scheme == 0 && interior) {
+        // The same as the branch below for a tile that lies inside the particle set and does not hold its last
+        // particle (warp-uniform, said by the caller; no rank bounds): no per-item range checks, and — the CDF being
+        // non-decreasing — the slot range comes from the two ends of the tile instead of a min / max over all items.
+        // A CDF value at or beyond the scale (zero-weight tail behind a total that rounded up) owns every slot: it is
+        // looked up as the last slot with an always-true comparison.
+        unsigned int kk[WS_SCAN_ITEMS];
+        unsigned int fr[WS_SCAN_ITEMS];
+        const unsigned int last = (unsigned int)ns - 1u;
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
+            const unsigned long long T = sh >= 0 ? (C[k] >> sh) : (C[k] << (-sh));
+            kk[k] = (unsigned int)(T >> 32);
+            fr[k] = (unsigned int)T;
+            if (kk[k] > last) {
+                kk[k] = last;
+                fr[k] = 0xFFFFFFFFu;
+            }
+        }
+        unsigned int kp = kk[0], frp = 0u;
+        if (lane == 0 && has_prev) {
+            const unsigned long long T = sh >= 0 ? (Cp >> sh) : (Cp << (-sh));
+            kp = (unsigned int)(T >> 32);
+            frp = (unsigned int)T;
+            if (kp > last) {
+                kp = last;
+                frp = 0xFFFFFFFFu;
+            }
+        }
+        const unsigned int blk0 = __shfl_sync(0xffffffffu, kp, 0) >> 2;
+        const unsigned int nblk = (__shfl_sync(0xffffffffu, kk[WS_SCAN_ITEMS - 1], 31) >> 2) - blk0 + 1u;
+        coop = nblk <= (unsigned int)(WS_RBUF_SLOTS / 2);
+        if (coop) {
+            for (unsigned int b = lane; b < nblk; b += 32u) {
+                const ws_u32x4 r = ws_philox4x32_10((uint64_t)(blk0 + b), P.stream, P.seed);
+                reinterpret_cast<uint4*>(rbuf32)[b] = make_uint4(r.x & rmask, r.y & rmask, r.z & rmask, r.w & rmask);
+            }
+            __syncwarp();
+            const unsigned int* const rb = rbuf32 - 4u * blk0;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) f[k] = (int)kk[k] + (rb[kk[k]] <= fr[k] ? 1 : 0);
+            if (lane == 0 && has_prev) fstart = (int)kp + (rb[kp] <= frp ? 1 : 0);
+            __syncwarp();  // the window is reused for the offspring below
+        }
+    } else if (!EXACT_FP && !MN && su.scheme == 0) {
         // Philox-stratified: neighbouring particles ask for neighbouring slots, and one Philox block
         // serves four slots, so the warp generates the uniforms of the tile's whole slot range once
         // (a quarter of a Philox block per particle instead of one) and every lane looks its slots up.
@@ -1197,7 +1244,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
         }
     }
     // items beyond the shard produce nothing: they repeat the F of the shard's last particle
-    {
+    if (!interior) {
         const int rank_end = P.bounds != nullptr ? P.bounds[1] : ns;
 #pragma unroll
         for (int k = 0; k < WS_SCAN_ITEMS; ++k)
@@ -1368,7 +1415,8 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
             const int p = tile_base - 1;
             Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
         }
-        ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0);
+        ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0,
+                                          WS_INTERIOR_FAST && P.bounds == nullptr && tile_base + WS_SCAN_TILE < n);
     }
 }
 
@@ -1510,6 +1558,224 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
     for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? thread_excl + q[k] : 0ull;
     const int warp_base = tile * WS_CDF_TILE + warp * WS_SCAN_TILE;
     if (warp_base < n) ws_search_warp_tile<EXACT_FP, false>(P, X, win_all[warp], lane, warp_base, C, prefix + warp_excl, warp_base != 0);
+}
+
+// ---- CDF + search in ONE pass, look-back deferred by one tile ("chain") ------------------------------------------
+// The single-pass kernel above loses to the three passes because a tile looks back right after publishing its own
+// aggregate, i.e. while the ~40 predecessors that started together with it are still forming theirs.  Here a CTA is
+// persistent and keeps TWO tiles in flight: it forms the fixed-point weights and local sums of tile t1 (phase 1,
+// FP64), publishes t1's aggregate, and only then looks back for the tile t0 it took one round earlier and runs t0's
+// search / expansion (phase 2, integer) from sums parked in shared memory.  By then every predecessor of t0 —
+// ticketed before t0, published one phase earlier — is visible, so the look-back is one poll, not a spin.  Depth is
+// bounded by a second level: tiles form groups of WS_CHAIN_GROUP; a tile adds its aggregate to its group's two
+// accumulators (low / high 31 bits, each with a tile count in its top bits: one fire-and-forget atomic each, no fence,
+// no return value), the first tile of a group publishes the group's exclusive prefix, and a look-back reads at most
+// 31 tile words (warp 0) and a few group words (warp 1).  Integer sums: ancestors are bit-identical to the other forms.
+#define WS_CHAIN_GROUP 32
+#ifndef WS_CHAIN_MINB
+#define WS_CHAIN_MINB 3
+#endif
+#define WS_CHAIN_CNT_SHIFT 40
+#define WS_CHAIN_PART_MASK ((1ull << WS_CHAIN_CNT_SHIFT) - 1ull)
+#define WS_CHAIN_SMEM_BYTES ((WS_WARPS_PER_CTA * WS_RBUF_SLOTS + WS_CDF_TILE) * 8)
+
+size_t ws_scan_words(int64_t n) {
+    const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    const int64_t n_groups = (n_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP;
+    return (size_t)(n_tiles + 3 * n_groups + 2);
+}
+
+template <bool EXACT_FP>
+__global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+    extern __shared__ __align__(16) unsigned long long chain_smem[];
+    __shared__ unsigned long long warp_tot[WS_WARPS_PER_CTA];
+    __shared__ unsigned long long s_wexcl[WS_WARPS_PER_CTA];
+    __shared__ unsigned long long lb_part[2];
+    __shared__ int s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long* const win = chain_smem + warp * WS_RBUF_SLOTS;
+    // parked tile-local CDF of the deferred tile: [WS_SCAN_ITEMS / 2][WS_SCAN_BLOCK] 16-byte words, thread-private slots
+    ulonglong2* const stash = reinterpret_cast<ulonglong2*>(chain_smem + WS_WARPS_PER_CTA * WS_RBUF_SLOTS) + tid;
+    const int n = (int)P.n;
+    const int n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    const int n_groups = (n_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP;
+    unsigned long long* const grp_lo = P.tile_words + n_tiles;
+    unsigned long long* const grp_hi = grp_lo + n_groups;
+    unsigned long long* const grp_incl = grp_hi + n_groups;
+    WsSearchCtx X;
+    ws_search_setup(P, X);
+    double m = 0.0, Sden = 1.0;
+    if (P.mode == 0) {
+        m = P.red->m;
+        Sden = P.red->S;
+    }
+    const double rS = 1.0 / Sden;
+    const double uniform_w = 1.0 / (double)P.n_slots;
+    int t0 = -1;
+    while (true) {
+        if (tid == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
+        __syncthreads();
+        const int t1 = s_tile;
+        const bool have1 = t1 < n_tiles;
+        // ---- phase 1 of t1: fixed-point weights, inclusive sums within the thread, then within the warp ----
+        unsigned long long q[WS_SCAN_ITEMS];
+        unsigned long long incl = 0ull, thread_total = 0ull;
+        if (have1) {
+            const int base = t1 * WS_CDF_TILE;
+            const int item0 = base + tid * WS_SCAN_ITEMS;
+            if (P.mode == 2) {
+                const unsigned long long qu = ws_w_to_fxs(uniform_w, P.fx_scale);
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? qu : 0ull;
+            } else {
+                double l[WS_SCAN_ITEMS];
+                if (base + WS_CDF_TILE <= n) {
+                    const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
+#pragma unroll
+                    for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                        const double2 v = __ldg(p2 + k);
+                        l[2 * k] = v.x;
+                        l[2 * k + 1] = v.y;
+                    }
+                } else {
+                    const double pad = (P.mode == 0) ? -INFINITY : 0.0;
+#pragma unroll
+                    for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : pad;
+                }
+                if (P.mode == 0) {
+                    // e <= 1 and S >= 1, so w in [0, 1] or NaN: the saturating conversion (NaN -> 0) is ws_w_to_fxs
+                    // without its two compares
+#pragma unroll
+                    for (int k = 0; k < WS_SCAN_ITEMS; ++k)
+                        q[k] = __double2ull_rn(ws_div_pos(ws_exp_nonpos(l[k] - m), Sden, rS) * P.fx_scale);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = ws_w_to_fxs(l[k], P.fx_scale);
+                }
+            }
+#pragma unroll
+            for (int k = 1; k < WS_SCAN_ITEMS; ++k) q[k] += q[k - 1];
+            thread_total = q[WS_SCAN_ITEMS - 1];
+            incl = thread_total;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+        }
+        __syncthreads();
+        // ---- swap: take the deferred tile's sums out of the parking slots, park t1's ----
+        unsigned long long C0[WS_SCAN_ITEMS];
+        unsigned long long wexcl0 = 0ull;
+        if (t0 >= 0) {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                const ulonglong2 v = stash[k * WS_SCAN_BLOCK];
+                C0[2 * k] = v.x;
+                C0[2 * k + 1] = v.y;
+            }
+            wexcl0 = s_wexcl[warp];
+        }
+        __syncwarp();
+        if (have1) {
+            unsigned long long warp_excl = 0ull, tile_agg = 0ull;
+#pragma unroll
+            for (int w = 0; w < WS_WARPS_PER_CTA; ++w) {
+                const unsigned long long t = warp_tot[w];
+                if (w < warp) warp_excl += t;
+                tile_agg += t;
+            }
+            if (tid == 0) {
+                st_relaxed_u64(P.tile_words + t1, (WS_TILE_AGG << 62) | tile_agg);
+                const int g = t1 / WS_CHAIN_GROUP;
+                atomicAdd(grp_lo + g, (1ull << WS_CHAIN_CNT_SHIFT) | (tile_agg & 0x7FFFFFFFull));
+                atomicAdd(grp_hi + g, (1ull << WS_CHAIN_CNT_SHIFT) | (tile_agg >> 31));
+            }
+            const unsigned long long thread_excl = warp_excl + (incl - thread_total);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k)
+                stash[k * WS_SCAN_BLOCK] = make_ulonglong2(thread_excl + q[2 * k], thread_excl + q[2 * k + 1]);
+            if (lane == 0) s_wexcl[warp] = warp_excl;
+        }
+        if (t0 < 0) {  // first round: nothing deferred yet
+            if (!have1) break;
+            t0 = t1;
+            continue;
+        }
+        // ---- look-back for t0: tiles of its own group (warp 0), whole groups before it (warp 1) ----
+        const int g0 = t0 / WS_CHAIN_GROUP;
+        if (warp == 0) {
+            const int idx = g0 * WS_CHAIN_GROUP + lane;
+            unsigned long long v = 0ull;
+            if (idx < t0) {
+                unsigned long long word;
+                do {
+                    word = ld_relaxed_u64(P.tile_words + idx);
+                } while ((word >> 62) == 0ull);
+                v = word & WS_FXS_MASK;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) lb_part[0] = v;
+        } else if (warp == 1) {
+            unsigned long long acc = 0ull;
+            int look = g0 - 1;
+            while (true) {
+                const int gi = look - lane;
+                unsigned long long v;
+                bool has_incl;
+                unsigned int first;
+                while (true) {
+                    bool ready = true;
+                    has_incl = true;
+                    v = 0ull;
+                    if (gi >= 0) {
+                        const unsigned long long inc = ld_relaxed_u64(grp_incl + gi);
+                        has_incl = (inc >> 62) == WS_TILE_INCL;
+                        if (has_incl) {
+                            v = inc & WS_FXS_MASK;
+                        } else {
+                            const unsigned long long lo = ld_relaxed_u64(grp_lo + gi), hi = ld_relaxed_u64(grp_hi + gi);
+                            ready = (lo >> WS_CHAIN_CNT_SHIFT) == WS_CHAIN_GROUP && (hi >> WS_CHAIN_CNT_SHIFT) == WS_CHAIN_GROUP;
+                            v = ((hi & WS_CHAIN_PART_MASK) << 31) + (lo & WS_CHAIN_PART_MASK);
+                        }
+                    }
+                    const unsigned int incl_mask = __ballot_sync(0xffffffffu, has_incl);
+                    const unsigned int wait_mask = __ballot_sync(0xffffffffu, !ready);
+                    first = incl_mask != 0u ? (unsigned int)(__ffs(incl_mask) - 1) : 32u;
+                    const unsigned int need = first >= 31u ? 0xFFFFFFFFu : ((2u << first) - 1u);
+                    if ((wait_mask & need) == 0u) break;
+                }
+                if ((unsigned int)lane > first) v = 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                acc += v;
+                if (first < 32u) break;
+                look -= 32;
+            }
+            if (lane == 0) {
+                lb_part[1] = acc;
+                // the first tile of a group hands the group's exclusive prefix to everybody behind it
+                if (g0 > 0 && t0 == g0 * WS_CHAIN_GROUP) st_relaxed_u64(grp_incl + (g0 - 1), (WS_TILE_INCL << 62) | acc);
+            }
+        }
+        __syncthreads();
+        // ---- phase 2 of t0: search + offspring expansion, one warp tile per warp ----
+        const unsigned long long prefix = P.cdf_offset + lb_part[0] + lb_part[1];
+        {
+            const int item0 = t0 * WS_CDF_TILE + tid * WS_SCAN_ITEMS;
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C0[k] = (item0 + k < n) ? prefix + C0[k] : 0ull;
+        }
+        const int warp_base = t0 * WS_CDF_TILE + warp * WS_SCAN_TILE;
+        if (warp_base < n)
+            ws_search_warp_tile<EXACT_FP, false>(P, X, win, lane, warp_base, C0, prefix + wexcl0, warp_base != 0,
+                                                 WS_INTERIOR_FAST && P.bounds == nullptr && warp_base + WS_SCAN_TILE < n);
+        if (!have1) break;
+        t0 = t1;
+    }
 }
 
 // ---- small particle sets: the whole Resample step in ONE kernel --------------------------------------------------
@@ -1726,19 +1992,36 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
     return cudaGetLastError();
 }
 
-// The single-pass kernel saves the 16 B round trip through cdf_local but, as measured on B200 (profiles/r2b_*), loses
-// more than that waiting in the look-back, so the three-pass form stays the default; env WSB200_SCAN=1pass selects it.
-static bool g_three_pass = true;
+// Three forms of CDF + search on a single-GPU state (env WSB200_SCAN = 3pass | 1pass | chain):
+//   3pass  tile CDF -> offsets -> search through cdf_local (also what sharded runs use: the ranks' masses are exchanged
+//          between the CDF and the search)
+//   1pass  one CTA per ticketed tile, look-back right after the tile's own aggregate: saves the 16 B round trip but, as
+//          measured on B200 (profiles/r2b_*), loses more than that waiting in the look-back
+//   chain  persistent CTAs, look-back deferred by one tile, two-level aggregates (ws_chain_kernel)
+#ifndef WS_SCAN_DEFAULT_FORM
+#define WS_SCAN_DEFAULT_FORM 0
+#endif
+static int g_scan_form = WS_SCAN_DEFAULT_FORM;  // 0 three passes, 1 single pass, 2 chain
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
     (void)grid;
-    if (!g_three_pass && P.all_tot == nullptr && P.total == nullptr && P.bounds == nullptr && P.scheme != 2) {
+    if (g_scan_form != 0 && P.all_tot == nullptr && P.total == nullptr && P.bounds == nullptr && P.scheme != 2) {
         // single-GPU state: one pass (the caller has zeroed the ticket / heavy-tile counters)
         const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
-        cudaError_t e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * (size_t)cdf_tiles, s);
-        if (e != cudaSuccess) return e;
         const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
-        if (exact_fp) ws_scan_search_kernel<true><<<(unsigned)cdf_tiles, WS_SCAN_BLOCK, 0, s>>>(P);
-        else ws_scan_search_kernel<false><<<(unsigned)cdf_tiles, WS_SCAN_BLOCK, 0, s>>>(P);
+        cudaError_t e;
+        if (g_scan_form == 2) {
+            e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * ws_scan_words(P.n), s);
+            if (e != cudaSuccess) return e;
+            int g = (int)(cdf_tiles < (int64_t)g_sm_count * WS_CHAIN_MINB ? cdf_tiles : (int64_t)g_sm_count * WS_CHAIN_MINB);
+            if (g < 1) g = 1;
+            if (exact_fp) ws_chain_kernel<true><<<g, WS_SCAN_BLOCK, WS_CHAIN_SMEM_BYTES, s>>>(P);
+            else ws_chain_kernel<false><<<g, WS_SCAN_BLOCK, WS_CHAIN_SMEM_BYTES, s>>>(P);
+        } else {
+            e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * (size_t)cdf_tiles, s);
+            if (e != cudaSuccess) return e;
+            if (exact_fp) ws_scan_search_kernel<true><<<(unsigned)cdf_tiles, WS_SCAN_BLOCK, 0, s>>>(P);
+            else ws_scan_search_kernel<false><<<(unsigned)cdf_tiles, WS_SCAN_BLOCK, 0, s>>>(P);
+        }
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);
@@ -1927,13 +2210,18 @@ cudaError_t ws_kernels_init(int device) {
     g_sm_count = prop.multiProcessorCount;
     {
         const char* v = getenv("WSB200_SCAN");
-        g_three_pass = !(v != nullptr && strcmp(v, "1pass") == 0);
+        if (v != nullptr) g_scan_form = strcmp(v, "1pass") == 0 ? 1 : (strcmp(v, "chain") == 0 ? 2 : (strcmp(v, "3pass") == 0 ? 0 : WS_SCAN_DEFAULT_FORM));
+        else g_scan_form = WS_SCAN_DEFAULT_FORM;
         v = getenv("WSB200_FX_EXTRA_BITS");
         g_fx_extra_bits = v != nullptr ? atoi(v) : 0;
         v = getenv("WSB200_VM");
         g_vm_interp_only = v != nullptr && strcmp(v, "interp") == 0;
     }
     // the register file of the fused pass can take most of the SM's shared memory
+    e = cudaFuncSetAttribute(ws_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_vm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_vm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);

@@ -560,7 +560,7 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
         if (const char* e = getenv("WSB200_GENEALOGY")) c->genealogy = atoi(e) != 0;
     }
     c->n_tiles = (c->n + WS_CDF_TILE - 1) / WS_CDF_TILE;
-    CKC(cudaMalloc(&c->d_tile_words, sizeof(unsigned long long) * (size_t)c->n_tiles));
+    CKC(cudaMalloc(&c->d_tile_words, sizeof(unsigned long long) * ws_scan_words(c->n)));
     CKC(cudaMalloc(&c->d_cdf_local, sizeof(unsigned long long) * (size_t)c->n));
     CKC(cudaMalloc(&c->d_tile_counter, sizeof(unsigned int) * 2));
     CKC(cudaMalloc(&c->d_counters, sizeof(unsigned long long) * 4));
@@ -2477,7 +2477,7 @@ static int resample_host_impl(ws_ctx* c, const double* weights, int64_t n, int s
     const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     CK(c, cudaMalloc(&w.p, sizeof(double) * (size_t)n));
     CK(c, cudaMalloc(&anc.p, sizeof(int32_t) * (size_t)n));
-    CK(c, cudaMalloc(&words.p, sizeof(unsigned long long) * (size_t)n_tiles));
+    CK(c, cudaMalloc(&words.p, sizeof(unsigned long long) * ws_scan_words(n)));
     CK(c, cudaMalloc(&cdf.p, sizeof(unsigned long long) * (size_t)n));
     CK(c, cudaMemcpyAsync(w.p, weights, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     if (uniforms != nullptr) {
