@@ -670,6 +670,7 @@ __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double 
 //                     integer,  u_k <= C  <=>  k*2^61 + r_k <= C*N, so F = k + [r_k <= frac] with
 //                     (k, frac) = divmod(C*N, 2^61) from one 64x32-bit product.  One Philox block and
 //                     no loop per particle; the test-suite checks it against exact big-integer arithmetic.
+#define WS_TILE_GROUP 32       // CDF tiles per group of the two-level tile offsets
 #define WS_EXPAND_CHUNK 512    // output slots a warp stages in shared memory per round
 #define WS_DIRECT_MAX 8        // offspring a lane writes itself; larger families are filled by the warp
 #define WS_WARPS_PER_CTA (WS_SCAN_BLOCK / 32)
@@ -756,15 +757,15 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = l_next[k];
             if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x, l_next);
+            if (P.mode == 0) {
+                // items beyond the shard were loaded as -inf: e = 0.  e <= 1 and S >= 1, so w is in [0, 1] or NaN and the
+                // saturating conversion (NaN -> 0) is ws_w_to_fxs without its two compares
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
-                double w;
-                if (P.mode == 0) {
-                    w = ws_div_pos(ws_exp_nonpos(l[k] - m), Sden, rS);
-                } else {
-                    w = (item0 + k < n) ? l[k] : 0.0;
-                }
-                q[k] = (item0 + k < n) ? ws_w_to_fxs(w, P.fx_scale) : 0ull;
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k)
+                    q[k] = __double2ull_rn(ws_div_pos(ws_exp_nonpos(l[k] - m), Sden, rS) * P.fx_scale);
+            } else {
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(l[k], P.fx_scale) : 0ull;
             }
         }
 #pragma unroll
@@ -796,26 +797,29 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
             for (int k = 0; k < WS_SCAN_ITEMS; ++k)
                 if (item0 + k < n) P.cdf_local[item0 + k] = thread_excl + q[k];
         }
-        if (threadIdx.x == 0) P.tile_words[tile] = tile_agg;
+        if (threadIdx.x == 0) {
+            // the tile's aggregate, and its share of the aggregate of its group of WS_TILE_GROUP tiles: the offsets
+            // pass scans the group sums (n / 65 536 words) and the search adds the <= 31 tile words in front of its tile
+            P.tile_words[tile] = tile_agg;
+            atomicAdd(P.tile_words + n_tiles + tile / WS_TILE_GROUP, tile_agg);
+        }
     }
 }
 
-// exclusive scan of the tile aggregates, in place, by one CTA of 1024 threads (fixed order); every thread
+// exclusive scan of `count` words, in place, by one CTA of 1024 threads (fixed order); every thread
 // takes WS_OFF_ITEMS consecutive words per round so that the loads of a round are all in flight together
 #define WS_OFF_ITEMS 8
-__global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_constant__ WsScanParams P) {
-    if (P.gate != 0 && P.red->do_resample == 0) return;
+__device__ __forceinline__ void ws_scan_words_cta(unsigned long long* __restrict__ words, const int n_tiles, unsigned long long* total_out) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned long long s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_tiles = (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE);
     if (threadIdx.x == 0) s_carry = 0ull;
     __syncthreads();
     for (int base = 0; base < n_tiles; base += 1024 * WS_OFF_ITEMS) {
         const int i0 = base + threadIdx.x * WS_OFF_ITEMS;
         unsigned long long v[WS_OFF_ITEMS];
 #pragma unroll
-        for (int k = 0; k < WS_OFF_ITEMS; ++k) v[k] = (i0 + k < n_tiles) ? P.tile_words[i0 + k] : 0ull;
+        for (int k = 0; k < WS_OFF_ITEMS; ++k) v[k] = (i0 + k < n_tiles) ? words[i0 + k] : 0ull;
         unsigned long long thread_total = 0ull;
 #pragma unroll
         for (int k = 0; k < WS_OFF_ITEMS; ++k) thread_total += v[k];
@@ -838,14 +842,34 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
         unsigned long long run = carry + warp_excl + (incl - thread_total);
 #pragma unroll
         for (int k = 0; k < WS_OFF_ITEMS; ++k) {
-            if (i0 + k < n_tiles) P.tile_words[i0 + k] = run;
+            if (i0 + k < n_tiles) words[i0 + k] = run;
             run += v[k];
         }
         __syncthreads();
         if (threadIdx.x == 0) s_carry = carry + total;
         __syncthreads();
     }
-    if (threadIdx.x == 0 && P.total != nullptr) *P.total = s_carry;
+    if (threadIdx.x == 0 && total_out != nullptr) *total_out = s_carry;
+}
+// multinomial: the tile sums of the exponential spacings
+__global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+    ws_scan_words_cta(P.tile_words, (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE), P.total);
+}
+// the CDF: the group sums behind the tile words (see ws_cdf_tiles_kernel), and the shard's total mass
+__global__ void __launch_bounds__(1024) ws_cdf_group_offsets_kernel(const __grid_constant__ WsScanParams P) {
+    if (P.gate != 0 && P.red->do_resample == 0) return;
+    const int n_tiles = (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE);
+    ws_scan_words_cta(P.tile_words + n_tiles, (n_tiles + WS_TILE_GROUP - 1) / WS_TILE_GROUP, P.total);
+}
+// exclusive prefix of CDF tile `ct` (all lanes of a warp call; every lane gets the result)
+__device__ __forceinline__ unsigned long long ws_tile_offset(const WsScanParams& P, const int n_tiles, const int ct, const int lane) {
+    const int g = ct / WS_TILE_GROUP, idx = g * WS_TILE_GROUP + lane;
+    unsigned long long v = idx < ct ? __ldg(P.tile_words + idx) : 0ull;
+    if (lane == 31) v = __ldg(P.tile_words + n_tiles + g);   // (idx = 32 g + 31 >= ct always: the lane is free for the group's prefix)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
 }
 
 // ---- multinomial without a sort: exponential spacings ------------------------------------------------------------
@@ -1122,7 +1146,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
     }
     if (!EXACT_FP && !MN && su.scheme == 0 && interior) {
         // The same as the branch below for a tile that lies inside the particle set and does not hold its last
-        // particle (warp-uniform, said by the caller; no rank bounds): no per-item range checks, and — the CDF being
+        // particle (warp-uniform, said by the caller): no per-item range checks, and — the CDF being
         // non-decreasing — the slot range comes from the two ends of the tile instead of a min / max over all items.
         // A CDF value at or beyond the scale (zero-weight tail behind a total that rounded up) owns every slot: it is
         // looked up as the last slot with an always-true comparison.
@@ -1389,12 +1413,14 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
     ws_search_setup(P, X);
     const int n = X.n;
     const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
+    const int n_ctiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
 
     const int warps_total = gridDim.x * WS_WARPS_PER_CTA;
     for (int tile = blockIdx.x * WS_WARPS_PER_CTA + warp; tile < n_tiles; tile += warps_total) {
         const int tile_base = tile * WS_SCAN_TILE;
         const int item0 = tile_base + lane * WS_SCAN_ITEMS;
-        const unsigned long long offset = cdf_offset + __ldg(P.tile_words + tile_base / WS_CDF_TILE);
+        const int ct = tile_base / WS_CDF_TILE;
+        const unsigned long long offset = cdf_offset + ws_tile_offset(P, n_ctiles, ct, lane);
 
         // global fixed-point CDF of the lane's 8 consecutive particles
         unsigned long long C[WS_SCAN_ITEMS];
@@ -1413,10 +1439,11 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
         unsigned long long Cp = 0ull;
         if (lane == 0 && tile != 0) {
             const int p = tile_base - 1;
-            Cp = cdf_offset + __ldg(P.tile_words + p / WS_CDF_TILE) + __ldg(P.cdf_local + p);
+            // (the particle in front of the first warp tile of a CDF tile lies in the previous CDF tile)
+            Cp = (p / WS_CDF_TILE == ct ? offset : offset - __ldg(P.tile_words + ct - 1)) + __ldg(P.cdf_local + p);
         }
         ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0,
-                                          WS_INTERIOR_FAST && P.bounds == nullptr && tile_base + WS_SCAN_TILE < n);
+                                          WS_INTERIOR_FAST && tile_base + WS_SCAN_TILE < n);
     }
 }
 
@@ -1571,18 +1598,23 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
 // accumulators (low / high 31 bits, each with a tile count in its top bits: one fire-and-forget atomic each, no fence,
 // no return value), the first tile of a group publishes the group's exclusive prefix, and a look-back reads at most
 // 31 tile words (warp 0) and a few group words (warp 1).  Integer sums: ancestors are bit-identical to the other forms.
-#define WS_CHAIN_GROUP 32
+#define WS_CHAIN_GROUP WS_TILE_GROUP
 #ifndef WS_CHAIN_MINB
 #define WS_CHAIN_MINB 3
 #endif
 #define WS_CHAIN_CNT_SHIFT 40
 #define WS_CHAIN_PART_MASK ((1ull << WS_CHAIN_CNT_SHIFT) - 1ull)
-#define WS_CHAIN_SMEM_BYTES ((WS_WARPS_PER_CTA * WS_RBUF_SLOTS + WS_CDF_TILE) * 8)
+#define WS_CHAIN_SMEM_BYTES ((WS_WARPS_PER_CTA * WS_RBUF_SLOTS + 2 * WS_CDF_TILE) * 8)
 
 size_t ws_scan_words(int64_t n) {
     const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     const int64_t n_groups = (n_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP;
     return (size_t)(n_tiles + 3 * n_groups + 2);
+}
+
+__device__ __forceinline__ void ws_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 template <bool EXACT_FP>
@@ -1597,6 +1629,8 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
     unsigned long long* const win = chain_smem + warp * WS_RBUF_SLOTS;
     // parked tile-local CDF of the deferred tile: [WS_SCAN_ITEMS / 2][WS_SCAN_BLOCK] 16-byte words, thread-private slots
     ulonglong2* const stash = reinterpret_cast<ulonglong2*>(chain_smem + WS_WARPS_PER_CTA * WS_RBUF_SLOTS) + tid;
+    // log-weights of the tile after next, copied asynchronously while this round computes (same layout, thread-private)
+    double2* const lbuf = reinterpret_cast<double2*>(chain_smem + WS_WARPS_PER_CTA * WS_RBUF_SLOTS + WS_CDF_TILE) + tid;
     const int n = (int)P.n;
     const int n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     const int n_groups = (n_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP;
@@ -1612,12 +1646,41 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
     }
     const double rS = 1.0 / Sden;
     const double uniform_w = 1.0 / (double)P.n_slots;
+    // a full tile's log-weights are prefetched; the ragged last tile is loaded with guards when its turn comes
+    auto prefetch = [&](int tile) {
+        if (P.mode != 2 && tile < n_tiles && (tile + 1) * WS_CDF_TILE <= n) {
+            const double2* p2 = reinterpret_cast<const double2*>(P.logw + (size_t)tile * WS_CDF_TILE + tid * WS_SCAN_ITEMS);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) ws_cp_async16(lbuf + k * WS_SCAN_BLOCK, p2 + k);
+        }
+        ws_cp_async_commit();
+    };
+    if (tid == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
+    __syncthreads();
+    int t1 = s_tile;
+    prefetch(t1);
+    __syncthreads();  // s_tile has been read by everybody
     int t0 = -1;
     while (true) {
-        if (tid == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);
-        __syncthreads();
-        const int t1 = s_tile;
         const bool have1 = t1 < n_tiles;
+        if (tid == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);  // the tile after t1: known to all after the next barrier
+        // the look-back words of t0 are requested now and looked at after phase 1 of t1: their latency is off the
+        // path between the two barriers (they are polled again there if a predecessor was late)
+        unsigned long long lbw0 = 0ull, lbw1 = 0ull, lbw2 = 0ull;
+        if (t0 >= 0) {
+            const int g0 = t0 / WS_CHAIN_GROUP;
+            if (warp == 0) {
+                const int idx = g0 * WS_CHAIN_GROUP + lane;
+                if (idx < t0) lbw0 = ld_relaxed_u64(P.tile_words + idx);
+            } else if (warp == 1) {
+                const int gi = g0 - 1 - lane;
+                if (gi >= 0) {
+                    lbw0 = ld_relaxed_u64(grp_incl + gi);
+                    lbw1 = ld_relaxed_u64(grp_lo + gi);
+                    lbw2 = ld_relaxed_u64(grp_hi + gi);
+                }
+            }
+        }
         // ---- phase 1 of t1: fixed-point weights, inclusive sums within the thread, then within the warp ----
         unsigned long long q[WS_SCAN_ITEMS];
         unsigned long long incl = 0ull, thread_total = 0ull;
@@ -1631,10 +1694,10 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
             } else {
                 double l[WS_SCAN_ITEMS];
                 if (base + WS_CDF_TILE <= n) {
-                    const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
+                    ws_cp_async_wait_all();
 #pragma unroll
                     for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
-                        const double2 v = __ldg(p2 + k);
+                        const double2 v = lbuf[k * WS_SCAN_BLOCK];
                         l[2 * k] = v.x;
                         l[2 * k + 1] = v.y;
                     }
@@ -1666,6 +1729,8 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
             if (lane == 31) warp_tot[warp] = incl;
         }
         __syncthreads();
+        const int t2 = s_tile;
+        prefetch(t2);  // (the thread's parking slots in lbuf were consumed above)
         // ---- swap: take the deferred tile's sums out of the parking slots, park t1's ----
         unsigned long long C0[WS_SCAN_ITEMS];
         unsigned long long wexcl0 = 0ull;
@@ -1699,83 +1764,85 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
                 stash[k * WS_SCAN_BLOCK] = make_ulonglong2(thread_excl + q[2 * k], thread_excl + q[2 * k + 1]);
             if (lane == 0) s_wexcl[warp] = warp_excl;
         }
-        if (t0 < 0) {  // first round: nothing deferred yet
-            if (!have1) break;
-            t0 = t1;
-            continue;
-        }
-        // ---- look-back for t0: tiles of its own group (warp 0), whole groups before it (warp 1) ----
-        const int g0 = t0 / WS_CHAIN_GROUP;
-        if (warp == 0) {
-            const int idx = g0 * WS_CHAIN_GROUP + lane;
-            unsigned long long v = 0ull;
-            if (idx < t0) {
-                unsigned long long word;
-                do {
-                    word = ld_relaxed_u64(P.tile_words + idx);
-                } while ((word >> 62) == 0ull);
-                v = word & WS_FXS_MASK;
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-            if (lane == 0) lb_part[0] = v;
-        } else if (warp == 1) {
-            unsigned long long acc = 0ull;
-            int look = g0 - 1;
-            while (true) {
-                const int gi = look - lane;
-                unsigned long long v;
-                bool has_incl;
-                unsigned int first;
-                while (true) {
-                    bool ready = true;
-                    has_incl = true;
-                    v = 0ull;
-                    if (gi >= 0) {
-                        const unsigned long long inc = ld_relaxed_u64(grp_incl + gi);
-                        has_incl = (inc >> 62) == WS_TILE_INCL;
-                        if (has_incl) {
-                            v = inc & WS_FXS_MASK;
-                        } else {
-                            const unsigned long long lo = ld_relaxed_u64(grp_lo + gi), hi = ld_relaxed_u64(grp_hi + gi);
-                            ready = (lo >> WS_CHAIN_CNT_SHIFT) == WS_CHAIN_GROUP && (hi >> WS_CHAIN_CNT_SHIFT) == WS_CHAIN_GROUP;
-                            v = ((hi & WS_CHAIN_PART_MASK) << 31) + (lo & WS_CHAIN_PART_MASK);
-                        }
-                    }
-                    const unsigned int incl_mask = __ballot_sync(0xffffffffu, has_incl);
-                    const unsigned int wait_mask = __ballot_sync(0xffffffffu, !ready);
-                    first = incl_mask != 0u ? (unsigned int)(__ffs(incl_mask) - 1) : 32u;
-                    const unsigned int need = first >= 31u ? 0xFFFFFFFFu : ((2u << first) - 1u);
-                    if ((wait_mask & need) == 0u) break;
+        if (t0 >= 0) {
+            // ---- look-back for t0: tiles of its own group (warp 0), whole groups before it (warp 1) ----
+            const int g0 = t0 / WS_CHAIN_GROUP;
+            if (warp == 0) {
+                const int idx = g0 * WS_CHAIN_GROUP + lane;
+                unsigned long long v = 0ull;
+                if (idx < t0) {
+                    unsigned long long word = lbw0;
+                    while ((word >> 62) == 0ull) word = ld_relaxed_u64(P.tile_words + idx);
+                    v = word & WS_FXS_MASK;
                 }
-                if ((unsigned int)lane > first) v = 0ull;
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                acc += v;
-                if (first < 32u) break;
-                look -= 32;
-            }
-            if (lane == 0) {
-                lb_part[1] = acc;
-                // the first tile of a group hands the group's exclusive prefix to everybody behind it
-                if (g0 > 0 && t0 == g0 * WS_CHAIN_GROUP) st_relaxed_u64(grp_incl + (g0 - 1), (WS_TILE_INCL << 62) | acc);
-            }
-        }
-        __syncthreads();
-        // ---- phase 2 of t0: search + offspring expansion, one warp tile per warp ----
-        const unsigned long long prefix = P.cdf_offset + lb_part[0] + lb_part[1];
-        {
-            const int item0 = t0 * WS_CDF_TILE + tid * WS_SCAN_ITEMS;
+                if (lane == 0) lb_part[0] = v;
+            } else if (warp == 1) {
+                unsigned long long acc = 0ull;
+                int look = g0 - 1;
+                bool fresh = true;   // first round, first look: the words requested at the top of the iteration
+                while (true) {
+                    const int gi = look - lane;
+                    unsigned long long v;
+                    bool has_incl;
+                    unsigned int first;
+                    while (true) {
+                        bool ready = true;
+                        has_incl = true;
+                        v = 0ull;
+                        if (gi >= 0) {
+                            const unsigned long long inc = fresh ? lbw0 : ld_relaxed_u64(grp_incl + gi);
+                            const unsigned long long lo = fresh ? lbw1 : ld_relaxed_u64(grp_lo + gi);
+                            const unsigned long long hi = fresh ? lbw2 : ld_relaxed_u64(grp_hi + gi);
+                            has_incl = (inc >> 62) == WS_TILE_INCL;
+                            if (has_incl) {
+                                v = inc & WS_FXS_MASK;
+                            } else {
+                                ready = (lo >> WS_CHAIN_CNT_SHIFT) == WS_CHAIN_GROUP && (hi >> WS_CHAIN_CNT_SHIFT) == WS_CHAIN_GROUP;
+                                v = ((hi & WS_CHAIN_PART_MASK) << 31) + (lo & WS_CHAIN_PART_MASK);
+                            }
+                        }
+                        fresh = false;
+                        const unsigned int incl_mask = __ballot_sync(0xffffffffu, has_incl);
+                        const unsigned int wait_mask = __ballot_sync(0xffffffffu, !ready);
+                        first = incl_mask != 0u ? (unsigned int)(__ffs(incl_mask) - 1) : 32u;
+                        const unsigned int need = first >= 31u ? 0xFFFFFFFFu : ((2u << first) - 1u);
+                        if ((wait_mask & need) == 0u) break;
+                    }
+                    if ((unsigned int)lane > first) v = 0ull;
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C0[k] = (item0 + k < n) ? prefix + C0[k] : 0ull;
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    acc += v;
+                    if (first < 32u) break;
+                    look -= 32;
+                }
+                if (lane == 0) {
+                    lb_part[1] = acc;
+                    // the first tile of a group hands the group's exclusive prefix to everybody behind it
+                    if (g0 > 0 && t0 == g0 * WS_CHAIN_GROUP) st_relaxed_u64(grp_incl + (g0 - 1), (WS_TILE_INCL << 62) | acc);
+                }
+            }
         }
-        const int warp_base = t0 * WS_CDF_TILE + warp * WS_SCAN_TILE;
-        if (warp_base < n)
-            ws_search_warp_tile<EXACT_FP, false>(P, X, win, lane, warp_base, C0, prefix + wexcl0, warp_base != 0,
-                                                 WS_INTERIOR_FAST && P.bounds == nullptr && warp_base + WS_SCAN_TILE < n);
+        __syncthreads();  // look-back result; s_tile and warp_tot have been read by everybody
+        if (t0 >= 0) {
+            // ---- phase 2 of t0: search + offspring expansion, one warp tile per warp ----
+            const unsigned long long prefix = P.cdf_offset + lb_part[0] + lb_part[1];
+            {
+                const int item0 = t0 * WS_CDF_TILE + tid * WS_SCAN_ITEMS;
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) C0[k] = (item0 + k < n) ? prefix + C0[k] : 0ull;
+            }
+            const int warp_base = t0 * WS_CDF_TILE + warp * WS_SCAN_TILE;
+            if (warp_base < n)
+                ws_search_warp_tile<EXACT_FP, false>(P, X, win, lane, warp_base, C0, prefix + wexcl0, warp_base != 0,
+                                                     WS_INTERIOR_FAST && warp_base + WS_SCAN_TILE < n);
+        }
         if (!have1) break;
         t0 = t1;
+        t1 = t2;
     }
+    ws_cp_async_wait_all();
 }
 
 // ---- small particle sets: the whole Resample step in ONE kernel --------------------------------------------------
@@ -1963,10 +2030,13 @@ cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s) {
     const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     int g1 = (int)(cdf_tiles < (int64_t)g_sm_count * WS_CDF_GRID ? cdf_tiles : (int64_t)g_sm_count * WS_CDF_GRID);
     if (g1 < 1) g1 = 1;
-    ws_cdf_tiles_kernel<<<g1, WS_SCAN_BLOCK, 0, s>>>(P);
-    cudaError_t e = cudaGetLastError();
+    const int64_t groups = (cdf_tiles + WS_TILE_GROUP - 1) / WS_TILE_GROUP;
+    cudaError_t e = cudaMemsetAsync(P.tile_words + cdf_tiles, 0, sizeof(unsigned long long) * (size_t)groups, s);
     if (e != cudaSuccess) return e;
-    ws_cdf_offsets_kernel<<<1, 1024, 0, s>>>(P);
+    ws_cdf_tiles_kernel<<<g1, WS_SCAN_BLOCK, 0, s>>>(P);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ws_cdf_group_offsets_kernel<<<1, 1024, 0, s>>>(P);
     return cudaGetLastError();
 }
 
