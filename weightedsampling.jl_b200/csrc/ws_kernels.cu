@@ -122,6 +122,10 @@ __device__ __forceinline__ void ws_cp_async8(double* smem_dst, const double* gsr
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void ws_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void ws_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ws_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -725,27 +729,20 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
     }
     const double rS = 1.0 / Sden;
     const double uniform_w = 1.0 / (double)P.n_slots;
-    // the log-weights of the NEXT tile are requested before the current tile is processed: the kernel was waiting on
-    // its loads (long-scoreboard stalls, profiles/r1i_ncu_ws_cdf_tiles_kernel_20M.txt), not on the arithmetic
-    auto load_tile = [&](int tile, double (&l)[WS_SCAN_ITEMS]) {
-        const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
-        if (item0 + WS_SCAN_ITEMS <= n) {
-            const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
+    // the log-weights of the NEXT tile are requested before the current tile is processed (the kernel was waiting on
+    // its loads, not on the arithmetic: profiles/r1i_ncu_ws_cdf_tiles_kernel_20M.txt) — by cp.async into thread-private
+    // slots of shared memory rather than into registers, which the FP64 part needs (ptxas spilled them)
+    __shared__ __align__(16) double2 lbuf_all[WS_SCAN_ITEMS / 2][WS_SCAN_BLOCK];
+    double2* const lbuf = &lbuf_all[0][threadIdx.x];
+    auto request = [&](int tile) {
+        if (P.mode != 2 && (tile + 1) * WS_CDF_TILE <= n) {
+            const double2* p2 = reinterpret_cast<const double2*>(P.logw + (size_t)tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS);
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
-                double2 v = __ldg(p2 + k);
-                l[2 * k] = v.x;
-                l[2 * k + 1] = v.y;
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : -INFINITY;
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) ws_cp_async16(lbuf + k * WS_SCAN_BLOCK, p2 + k);
         }
+        ws_cp_async_commit();
     };
-    double l_next[WS_SCAN_ITEMS];
-#pragma unroll
-    for (int k = 0; k < WS_SCAN_ITEMS; ++k) l_next[k] = -INFINITY;
-    if (P.mode != 2 && (int)blockIdx.x < n_tiles) load_tile(blockIdx.x, l_next);
+    if ((int)blockIdx.x < n_tiles) request(blockIdx.x);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
         unsigned long long q[WS_SCAN_ITEMS];
@@ -754,9 +751,19 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(uniform_w, P.fx_scale) : 0ull;
         } else {
             double l[WS_SCAN_ITEMS];
+            ws_cp_async_wait_all();
+            if ((tile + 1) * WS_CDF_TILE <= n) {
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = l_next[k];
-            if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x, l_next);
+                for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                    const double2 v = lbuf[k * WS_SCAN_BLOCK];
+                    l[2 * k] = v.x;
+                    l[2 * k + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : -INFINITY;
+            }
+            if (tile + (int)gridDim.x < n_tiles) request(tile + gridDim.x);   // (the thread's slots of lbuf were read above)
             if (P.mode == 0) {
                 // items beyond the shard were loaded as -inf: e = 0.  e <= 1 and S >= 1, so w is in [0, 1] or NaN and the
                 // saturating conversion (NaN -> 0) is ws_w_to_fxs without its two compares
@@ -1397,16 +1404,22 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
 #ifndef WS_SEARCH_MINB
 #define WS_SEARCH_MINB 3
 #endif
+#ifndef WS_SEARCH_GRID
+#define WS_SEARCH_GRID 3   // CTAs per SM launched: persistent warps, each pipelining its tiles (next tile requested while this one is searched)
+#endif
+#define WS_SEARCH_SMEM_BYTES ((WS_WARPS_PER_CTA * WS_RBUF_SLOTS + WS_CDF_TILE) * 8)
 template <bool EXACT_FP, bool MN>
 __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kernel(const __grid_constant__ WsScanParams P) {
     if (P.gate != 0 && P.red->do_resample == 0) return;
 
-    // per-warp window: first the 61-bit slot uniforms of the tile's slot range (Philox mode), then the
-    // staged offspring
-    __shared__ __align__(16) unsigned long long win_all[WS_WARPS_PER_CTA][WS_RBUF_SLOTS];
+    // per-warp window: first the slot uniforms of the tile's slot range (Philox mode), then the staged offspring;
+    // behind the windows, per warp, the tile-local CDF of the warp's NEXT tile, copied asynchronously while the current
+    // one is searched (the kernel was waiting on these loads: profiles/r2m_ncu_ws_search_kernel_20M.txt)
+    extern __shared__ __align__(16) unsigned long long search_smem[];
     static_assert(WS_RBUF_SLOTS * 8 >= (WS_EXPAND_CHUNK + 128) * 4 && (WS_RBUF_SLOTS * 8) % 16 == 0, "window too small for the offspring staging");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long* const rbuf = win_all[warp];
+    unsigned long long* const rbuf = search_smem + warp * WS_RBUF_SLOTS;
+    ulonglong2* const cbuf = reinterpret_cast<ulonglong2*>(search_smem + WS_WARPS_PER_CTA * WS_RBUF_SLOTS + warp * WS_SCAN_TILE) + lane;
 
     const unsigned long long cdf_offset = ws_cdf_offset(P);
     WsSearchCtx X;
@@ -1414,35 +1427,54 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
     const int n = X.n;
     const int n_tiles = (n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     const int n_ctiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
-
     const int warps_total = gridDim.x * WS_WARPS_PER_CTA;
-    for (int tile = blockIdx.x * WS_WARPS_PER_CTA + warp; tile < n_tiles; tile += warps_total) {
+
+    // what a tile needs from memory besides its CDF values: the lane's word of the tile-offset sum (ws_tile_offset) and
+    // the local CDF of the particle in front of the tile (lane 0; zero when that particle closes the previous CDF tile:
+    // its global CDF is then exactly this tile's offset)
+    unsigned long long ow = 0ull, pw = 0ull;
+    auto request = [&](int tile) {
+        const int tile_base = tile * WS_SCAN_TILE;
+        const int ct = tile_base / WS_CDF_TILE;
+        if (tile_base + WS_SCAN_TILE <= n) {
+            const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(P.cdf_local + tile_base + lane * WS_SCAN_ITEMS);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) ws_cp_async16(cbuf + k * 32, p2 + k);
+        }
+        ws_cp_async_commit();
+        const int idx = (ct / WS_TILE_GROUP) * WS_TILE_GROUP + lane;
+        ow = idx < ct ? __ldg(P.tile_words + idx) : 0ull;
+        if (lane == 31) ow = __ldg(P.tile_words + n_ctiles + ct / WS_TILE_GROUP);   // (32 g + 31 >= ct: the lane is free for the group's prefix)
+        pw = (lane == 0 && tile_base % WS_CDF_TILE != 0) ? __ldg(P.cdf_local + tile_base - 1) : 0ull;
+    };
+    int tile = blockIdx.x * WS_WARPS_PER_CTA + warp;
+    if (tile < n_tiles) request(tile);
+    for (; tile < n_tiles; tile += warps_total) {
         const int tile_base = tile * WS_SCAN_TILE;
         const int item0 = tile_base + lane * WS_SCAN_ITEMS;
-        const int ct = tile_base / WS_CDF_TILE;
-        const unsigned long long offset = cdf_offset + ws_tile_offset(P, n_ctiles, ct, lane);
-
         // global fixed-point CDF of the lane's 8 consecutive particles
         unsigned long long C[WS_SCAN_ITEMS];
-        if (item0 + WS_SCAN_ITEMS <= n) {
-            const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(P.cdf_local + item0);
+        ws_cp_async_wait_all();
+        if (tile_base + WS_SCAN_TILE <= n) {
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
-                ulonglong2 v = __ldg(p2 + k);
-                C[2 * k] = offset + v.x;
-                C[2 * k + 1] = offset + v.y;
+                const ulonglong2 v = cbuf[k * 32];
+                C[2 * k] = v.x;
+                C[2 * k + 1] = v.y;
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? offset + __ldg(P.cdf_local + item0 + k) : 0ull;
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? __ldg(P.cdf_local + item0 + k) : 0ull;
         }
-        unsigned long long Cp = 0ull;
-        if (lane == 0 && tile != 0) {
-            const int p = tile_base - 1;
-            // (the particle in front of the first warp tile of a CDF tile lies in the previous CDF tile)
-            Cp = (p / WS_CDF_TILE == ct ? offset : offset - __ldg(P.tile_words + ct - 1)) + __ldg(P.cdf_local + p);
-        }
-        ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0,
+        unsigned long long off = ow;
+        const unsigned long long pl = pw;
+        if (tile + warps_total < n_tiles) request(tile + warps_total);   // (the lane's slots of cbuf were read above)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) off += __shfl_xor_sync(0xffffffffu, off, d);
+        off += cdf_offset;
+#pragma unroll
+        for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? off + C[k] : 0ull;
+        ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, off + pl, tile != 0,
                                           WS_INTERIOR_FAST && tile_base + WS_SCAN_TILE < n);
     }
 }
@@ -1610,11 +1642,6 @@ size_t ws_scan_words(int64_t n) {
     const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     const int64_t n_groups = (n_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP;
     return (size_t)(n_tiles + 3 * n_groups + 2);
-}
-
-__device__ __forceinline__ void ws_cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
 template <bool EXACT_FP>
@@ -2050,12 +2077,12 @@ cudaError_t ws_launch_bounds(const WsScanParams& P, cudaStream_t s) {
 cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
     const int64_t warp_tiles = (P.n + WS_SCAN_TILE - 1) / WS_SCAN_TILE;
     const int64_t ctas = (warp_tiles + WS_WARPS_PER_CTA - 1) / WS_WARPS_PER_CTA;
-    int g3 = (int)(ctas < (int64_t)g_sm_count * 6 ? ctas : (int64_t)g_sm_count * 6);
+    int g3 = (int)(ctas < (int64_t)g_sm_count * WS_SEARCH_GRID ? ctas : (int64_t)g_sm_count * WS_SEARCH_GRID);
     if (g3 < 1) g3 = 1;
     const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
-    if (exact_fp) ws_search_kernel<true, false><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
-    else if (P.scheme == 2) ws_search_kernel<false, true><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
-    else ws_search_kernel<false, false><<<g3, WS_SCAN_BLOCK, 0, s>>>(P);
+    if (exact_fp) ws_search_kernel<true, false><<<g3, WS_SCAN_BLOCK, WS_SEARCH_SMEM_BYTES, s>>>(P);
+    else if (P.scheme == 2) ws_search_kernel<false, true><<<g3, WS_SCAN_BLOCK, WS_SEARCH_SMEM_BYTES, s>>>(P);
+    else ws_search_kernel<false, false><<<g3, WS_SCAN_BLOCK, WS_SEARCH_SMEM_BYTES, s>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ws_expand_heavy_kernel<<<g_sm_count * 4, 256, 0, s>>>(P);
@@ -2288,6 +2315,12 @@ cudaError_t ws_kernels_init(int device) {
         g_vm_interp_only = v != nullptr && strcmp(v, "interp") == 0;
     }
     // the register file of the fused pass can take most of the SM's shared memory
+    e = cudaFuncSetAttribute(ws_search_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SEARCH_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_search_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SEARCH_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SEARCH_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES);
