@@ -331,10 +331,10 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
 // ------------------------------------------------------------------------------------------
 #include "ws_vm_sl.cuh"
 #ifndef WS_SL_P
-#define WS_SL_P 2      // particles per thread
+#define WS_SL_P 4      // particles per thread (measured on B200, profiles/r2n_sl_shape_sweep.txt: 2x6 1.72 ms, 3x4 1.58, 3x5 1.72, 4x4 1.70, 4x3 1.51)
 #endif
 #ifndef WS_SL_MINB
-#define WS_SL_MINB 6   // resident CTAs per SM the kernels are compiled for
+#define WS_SL_MINB 3   // resident CTAs per SM the kernels are compiled for
 #endif
 template <class Sig, int PP>
 __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const __grid_constant__ WsVmProgram P) {
@@ -710,6 +710,9 @@ __device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, in
     return (int)k + ((r & rmask) <= frac ? 1 : 0);
 }
 
+#ifndef WS_CDF_ASYNC
+#define WS_CDF_ASYNC 1   // next tile's log-weights by cp.async into shared memory (1) or by plain loads into registers (0)
+#endif
 #ifndef WS_CDF_MINB
 #define WS_CDF_MINB 5   // <= 51 registers: five CTAs per SM (measured against 1 / 4 with grids of 3, 4, 8 CTAs per SM)
 #endif
@@ -729,6 +732,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
     }
     const double rS = 1.0 / Sden;
     const double uniform_w = 1.0 / (double)P.n_slots;
+#if WS_CDF_ASYNC
     // the log-weights of the NEXT tile are requested before the current tile is processed (the kernel was waiting on
     // its loads, not on the arithmetic: profiles/r1i_ncu_ws_cdf_tiles_kernel_20M.txt) — by cp.async into thread-private
     // slots of shared memory rather than into registers, which the FP64 part needs (ptxas spilled them)
@@ -775,6 +779,51 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
                 for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(l[k], P.fx_scale) : 0ull;
             }
         }
+#else
+    // the log-weights of the NEXT tile are requested before the current tile is processed: the kernel was waiting on
+    // its loads (long-scoreboard stalls, profiles/r1i_ncu_ws_cdf_tiles_kernel_20M.txt), not on the arithmetic
+    auto load_tile = [&](int tile, double (&l)[WS_SCAN_ITEMS]) {
+        const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
+        if (item0 + WS_SCAN_ITEMS <= n) {
+            const double2* p2 = reinterpret_cast<const double2*>(P.logw + item0);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                double2 v = __ldg(p2 + k);
+                l[2 * k] = v.x;
+                l[2 * k + 1] = v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = (item0 + k < n) ? __ldg(P.logw + item0 + k) : -INFINITY;
+        }
+    };
+    double l_next[WS_SCAN_ITEMS];
+#pragma unroll
+    for (int k = 0; k < WS_SCAN_ITEMS; ++k) l_next[k] = -INFINITY;
+    if (P.mode != 2 && (int)blockIdx.x < n_tiles) load_tile(blockIdx.x, l_next);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int item0 = tile * WS_CDF_TILE + threadIdx.x * WS_SCAN_ITEMS;
+        unsigned long long q[WS_SCAN_ITEMS];
+        if (P.mode == 2) {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(uniform_w, P.fx_scale) : 0ull;
+        } else {
+            double l[WS_SCAN_ITEMS];
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) l[k] = l_next[k];
+            if (tile + (int)gridDim.x < n_tiles) load_tile(tile + gridDim.x, l_next);
+            if (P.mode == 0) {
+                // items beyond the shard were loaded as -inf: e = 0.  e <= 1 and S >= 1, so w is in [0, 1] or NaN and the
+                // saturating conversion (NaN -> 0) is ws_w_to_fxs without its two compares
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k)
+                    q[k] = __double2ull_rn(ws_div_pos(ws_exp_nonpos(l[k] - m), Sden, rS) * P.fx_scale);
+            } else {
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? ws_w_to_fxs(l[k], P.fx_scale) : 0ull;
+            }
+        }
+#endif
 #pragma unroll
         for (int k = 1; k < WS_SCAN_ITEMS; ++k) q[k] += q[k - 1];
         const unsigned long long thread_total = q[WS_SCAN_ITEMS - 1];
@@ -1401,6 +1450,9 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
     }
 }
 
+#ifndef WS_SEARCH_ASYNC
+#define WS_SEARCH_ASYNC 1   // next tile's CDF by cp.async into shared memory while this one is searched (1) or loaded when needed (0)
+#endif
 #ifndef WS_SEARCH_MINB
 #define WS_SEARCH_MINB 3
 #endif
@@ -1429,6 +1481,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
     const int n_ctiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     const int warps_total = gridDim.x * WS_WARPS_PER_CTA;
 
+#if WS_SEARCH_ASYNC
     // what a tile needs from memory besides its CDF values: the lane's word of the tile-offset sum (ws_tile_offset) and
     // the local CDF of the particle in front of the tile (lane 0; zero when that particle closes the previous CDF tile:
     // its global CDF is then exactly this tile's offset)
@@ -1477,6 +1530,37 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
         ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, off + pl, tile != 0,
                                           WS_INTERIOR_FAST && tile_base + WS_SCAN_TILE < n);
     }
+#else
+    for (int tile = blockIdx.x * WS_WARPS_PER_CTA + warp; tile < n_tiles; tile += warps_total) {
+        const int tile_base = tile * WS_SCAN_TILE;
+        const int item0 = tile_base + lane * WS_SCAN_ITEMS;
+        const int ct = tile_base / WS_CDF_TILE;
+        const unsigned long long offset = cdf_offset + ws_tile_offset(P, n_ctiles, ct, lane);
+
+        // global fixed-point CDF of the lane's 8 consecutive particles
+        unsigned long long C[WS_SCAN_ITEMS];
+        if (item0 + WS_SCAN_ITEMS <= n) {
+            const ulonglong2* p2 = reinterpret_cast<const ulonglong2*>(P.cdf_local + item0);
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
+                ulonglong2 v = __ldg(p2 + k);
+                C[2 * k] = offset + v.x;
+                C[2 * k + 1] = offset + v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? offset + __ldg(P.cdf_local + item0 + k) : 0ull;
+        }
+        unsigned long long Cp = 0ull;
+        if (lane == 0 && tile != 0) {
+            const int p = tile_base - 1;
+            // (the particle in front of the first warp tile of a CDF tile lies in the previous CDF tile)
+            Cp = (p / WS_CDF_TILE == ct ? offset : offset - __ldg(P.tile_words + ct - 1)) + __ldg(P.cdf_local + p);
+        }
+        ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, Cp, tile != 0,
+                                          WS_INTERIOR_FAST && tile_base + WS_SCAN_TILE < n);
+    }
+#endif
 }
 
 // ---- CDF + search in ONE pass (single-GPU states) ---------------------------------------------------
@@ -1634,32 +1718,39 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_k
 #ifndef WS_CHAIN_MINB
 #define WS_CHAIN_MINB 3
 #endif
+#ifndef WS_CHAIN_MAXREG
+#define WS_CHAIN_MAXREG 80    // 65 536 / (WS_CHAIN_MINB x 256 threads) = 85, whatever the CTA size (ptxas does not derive it from small CTAs)
+#endif
 #define WS_CHAIN_CNT_SHIFT 40
 #define WS_CHAIN_PART_MASK ((1ull << WS_CHAIN_CNT_SHIFT) - 1ull)
-#define WS_CHAIN_SMEM_BYTES ((WS_WARPS_PER_CTA * WS_RBUF_SLOTS + 2 * WS_CDF_TILE) * 8)
+#define WS_CHAIN_SMEM_BYTES(BLOCK) ((((BLOCK) / 32) * WS_RBUF_SLOTS + 2 * (BLOCK) * WS_SCAN_ITEMS) * 8)
+#define WS_CHAIN_MIN_TILE (32 * WS_SCAN_ITEMS)   // smallest chain tile (one warp per CTA): sizes the tile words
 
 size_t ws_scan_words(int64_t n) {
-    const int64_t n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    const int64_t n_tiles = (n + WS_CHAIN_MIN_TILE - 1) / WS_CHAIN_MIN_TILE;
     const int64_t n_groups = (n_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP;
     return (size_t)(n_tiles + 3 * n_groups + 2);
 }
 
-template <bool EXACT_FP>
-__global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(const __grid_constant__ WsScanParams P) {
+template <bool EXACT_FP, int BLOCK>
+__global__ void __maxnreg__(WS_CHAIN_MAXREG) ws_chain_kernel(const __grid_constant__ WsScanParams P) {
+    constexpr int TILE = BLOCK * WS_SCAN_ITEMS;   // particles per chain tile
+    constexpr int WARPS = BLOCK / 32;
+    constexpr int GRP_WARP = WARPS > 1 ? 1 : 0;    // the warp that looks back over the groups (warp 0: the tiles of its own group)
     if (P.gate != 0 && P.red->do_resample == 0) return;
     extern __shared__ __align__(16) unsigned long long chain_smem[];
-    __shared__ unsigned long long warp_tot[WS_WARPS_PER_CTA];
-    __shared__ unsigned long long s_wexcl[WS_WARPS_PER_CTA];
+    __shared__ unsigned long long warp_tot[WARPS];
+    __shared__ unsigned long long s_wexcl[WARPS];
     __shared__ unsigned long long lb_part[2];
     __shared__ int s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long* const win = chain_smem + warp * WS_RBUF_SLOTS;
-    // parked tile-local CDF of the deferred tile: [WS_SCAN_ITEMS / 2][WS_SCAN_BLOCK] 16-byte words, thread-private slots
-    ulonglong2* const stash = reinterpret_cast<ulonglong2*>(chain_smem + WS_WARPS_PER_CTA * WS_RBUF_SLOTS) + tid;
+    // parked tile-local CDF of the deferred tile: [WS_SCAN_ITEMS / 2][BLOCK] 16-byte words, thread-private slots
+    ulonglong2* const stash = reinterpret_cast<ulonglong2*>(chain_smem + WARPS * WS_RBUF_SLOTS) + tid;
     // log-weights of the tile after next, copied asynchronously while this round computes (same layout, thread-private)
-    double2* const lbuf = reinterpret_cast<double2*>(chain_smem + WS_WARPS_PER_CTA * WS_RBUF_SLOTS + WS_CDF_TILE) + tid;
+    double2* const lbuf = reinterpret_cast<double2*>(chain_smem + WARPS * WS_RBUF_SLOTS + TILE) + tid;
     const int n = (int)P.n;
-    const int n_tiles = (n + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    const int n_tiles = (n + TILE - 1) / TILE;
     const int n_groups = (n_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP;
     unsigned long long* const grp_lo = P.tile_words + n_tiles;
     unsigned long long* const grp_hi = grp_lo + n_groups;
@@ -1675,10 +1766,10 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
     const double uniform_w = 1.0 / (double)P.n_slots;
     // a full tile's log-weights are prefetched; the ragged last tile is loaded with guards when its turn comes
     auto prefetch = [&](int tile) {
-        if (P.mode != 2 && tile < n_tiles && (tile + 1) * WS_CDF_TILE <= n) {
-            const double2* p2 = reinterpret_cast<const double2*>(P.logw + (size_t)tile * WS_CDF_TILE + tid * WS_SCAN_ITEMS);
+        if (P.mode != 2 && tile < n_tiles && (tile + 1) * TILE <= n) {
+            const double2* p2 = reinterpret_cast<const double2*>(P.logw + (size_t)tile * TILE + tid * WS_SCAN_ITEMS);
 #pragma unroll
-            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) ws_cp_async16(lbuf + k * WS_SCAN_BLOCK, p2 + k);
+            for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) ws_cp_async16(lbuf + k * BLOCK, p2 + k);
         }
         ws_cp_async_commit();
     };
@@ -1693,13 +1784,14 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
         if (tid == 0) s_tile = (int)atomicAdd(P.tile_counter, 1u);  // the tile after t1: known to all after the next barrier
         // the look-back words of t0 are requested now and looked at after phase 1 of t1: their latency is off the
         // path between the two barriers (they are polled again there if a predecessor was late)
-        unsigned long long lbw0 = 0ull, lbw1 = 0ull, lbw2 = 0ull;
+        unsigned long long lbt = 0ull, lbw0 = 0ull, lbw1 = 0ull, lbw2 = 0ull;
         if (t0 >= 0) {
             const int g0 = t0 / WS_CHAIN_GROUP;
             if (warp == 0) {
                 const int idx = g0 * WS_CHAIN_GROUP + lane;
-                if (idx < t0) lbw0 = ld_relaxed_u64(P.tile_words + idx);
-            } else if (warp == 1) {
+                if (idx < t0) lbt = ld_relaxed_u64(P.tile_words + idx);
+            }
+            if (warp == GRP_WARP) {
                 const int gi = g0 - 1 - lane;
                 if (gi >= 0) {
                     lbw0 = ld_relaxed_u64(grp_incl + gi);
@@ -1712,7 +1804,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
         unsigned long long q[WS_SCAN_ITEMS];
         unsigned long long incl = 0ull, thread_total = 0ull;
         if (have1) {
-            const int base = t1 * WS_CDF_TILE;
+            const int base = t1 * TILE;
             const int item0 = base + tid * WS_SCAN_ITEMS;
             if (P.mode == 2) {
                 const unsigned long long qu = ws_w_to_fxs(uniform_w, P.fx_scale);
@@ -1720,11 +1812,11 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
                 for (int k = 0; k < WS_SCAN_ITEMS; ++k) q[k] = (item0 + k < n) ? qu : 0ull;
             } else {
                 double l[WS_SCAN_ITEMS];
-                if (base + WS_CDF_TILE <= n) {
+                if (base + TILE <= n) {
                     ws_cp_async_wait_all();
 #pragma unroll
                     for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
-                        const double2 v = lbuf[k * WS_SCAN_BLOCK];
+                        const double2 v = lbuf[k * BLOCK];
                         l[2 * k] = v.x;
                         l[2 * k + 1] = v.y;
                     }
@@ -1764,7 +1856,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
         if (t0 >= 0) {
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k) {
-                const ulonglong2 v = stash[k * WS_SCAN_BLOCK];
+                const ulonglong2 v = stash[k * BLOCK];
                 C0[2 * k] = v.x;
                 C0[2 * k + 1] = v.y;
             }
@@ -1774,7 +1866,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
         if (have1) {
             unsigned long long warp_excl = 0ull, tile_agg = 0ull;
 #pragma unroll
-            for (int w = 0; w < WS_WARPS_PER_CTA; ++w) {
+            for (int w = 0; w < WARPS; ++w) {
                 const unsigned long long t = warp_tot[w];
                 if (w < warp) warp_excl += t;
                 tile_agg += t;
@@ -1788,7 +1880,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
             const unsigned long long thread_excl = warp_excl + (incl - thread_total);
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS / 2; ++k)
-                stash[k * WS_SCAN_BLOCK] = make_ulonglong2(thread_excl + q[2 * k], thread_excl + q[2 * k + 1]);
+                stash[k * BLOCK] = make_ulonglong2(thread_excl + q[2 * k], thread_excl + q[2 * k + 1]);
             if (lane == 0) s_wexcl[warp] = warp_excl;
         }
         if (t0 >= 0) {
@@ -1798,14 +1890,15 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
                 const int idx = g0 * WS_CHAIN_GROUP + lane;
                 unsigned long long v = 0ull;
                 if (idx < t0) {
-                    unsigned long long word = lbw0;
+                    unsigned long long word = lbt;
                     while ((word >> 62) == 0ull) word = ld_relaxed_u64(P.tile_words + idx);
                     v = word & WS_FXS_MASK;
                 }
 #pragma unroll
                 for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
                 if (lane == 0) lb_part[0] = v;
-            } else if (warp == 1) {
+            }
+            if (warp == GRP_WARP) {
                 unsigned long long acc = 0ull;
                 int look = g0 - 1;
                 bool fresh = true;   // first round, first look: the words requested at the top of the iteration
@@ -1856,11 +1949,11 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CHAIN_MINB) ws_chain_kernel(
             // ---- phase 2 of t0: search + offspring expansion, one warp tile per warp ----
             const unsigned long long prefix = P.cdf_offset + lb_part[0] + lb_part[1];
             {
-                const int item0 = t0 * WS_CDF_TILE + tid * WS_SCAN_ITEMS;
+                const int item0 = t0 * TILE + tid * WS_SCAN_ITEMS;
 #pragma unroll
                 for (int k = 0; k < WS_SCAN_ITEMS; ++k) C0[k] = (item0 + k < n) ? prefix + C0[k] : 0ull;
             }
-            const int warp_base = t0 * WS_CDF_TILE + warp * WS_SCAN_TILE;
+            const int warp_base = t0 * TILE + warp * WS_SCAN_TILE;
             if (warp_base < n)
                 ws_search_warp_tile<EXACT_FP, false>(P, X, win, lane, warp_base, C0, prefix + wexcl0, warp_base != 0,
                                                      WS_INTERIOR_FAST && warp_base + WS_SCAN_TILE < n);
@@ -2099,6 +2192,20 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s) {
 #define WS_SCAN_DEFAULT_FORM 0
 #endif
 static int g_scan_form = WS_SCAN_DEFAULT_FORM;  // 0 three passes, 1 single pass, 2 chain
+#ifndef WS_CHAIN_DEFAULT_BLOCK
+#define WS_CHAIN_DEFAULT_BLOCK WS_SCAN_BLOCK
+#endif
+static int g_chain_block = WS_CHAIN_DEFAULT_BLOCK;   // threads per CTA of the chain form (env WSB200_CHAIN_BLOCK = 32 | 64 | 256): tile = 8 x that
+template <int BLOCK>
+static cudaError_t ws_launch_chain(const WsScanParams& P, bool exact_fp, cudaStream_t s) {
+    const int64_t tiles = (P.n + BLOCK * WS_SCAN_ITEMS - 1) / (BLOCK * WS_SCAN_ITEMS);
+    const int64_t resident = (int64_t)g_sm_count * WS_CHAIN_MINB * (WS_SCAN_BLOCK / BLOCK);
+    int g = (int)(tiles < resident ? tiles : resident);
+    if (g < 1) g = 1;
+    if (exact_fp) ws_chain_kernel<true, BLOCK><<<g, BLOCK, WS_CHAIN_SMEM_BYTES(BLOCK), s>>>(P);
+    else ws_chain_kernel<false, BLOCK><<<g, BLOCK, WS_CHAIN_SMEM_BYTES(BLOCK), s>>>(P);
+    return cudaGetLastError();
+}
 cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t s) {
     (void)grid;
     if (g_scan_form != 0 && P.all_tot == nullptr && P.total == nullptr && P.bounds == nullptr && P.scheme != 2) {
@@ -2107,12 +2214,11 @@ cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t 
         const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
         cudaError_t e;
         if (g_scan_form == 2) {
-            e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * ws_scan_words(P.n), s);
+            const int64_t ch_tiles = (P.n + g_chain_block * WS_SCAN_ITEMS - 1) / (g_chain_block * WS_SCAN_ITEMS);
+            e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * (size_t)(ch_tiles + 3 * ((ch_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP)), s);
             if (e != cudaSuccess) return e;
-            int g = (int)(cdf_tiles < (int64_t)g_sm_count * WS_CHAIN_MINB ? cdf_tiles : (int64_t)g_sm_count * WS_CHAIN_MINB);
-            if (g < 1) g = 1;
-            if (exact_fp) ws_chain_kernel<true><<<g, WS_SCAN_BLOCK, WS_CHAIN_SMEM_BYTES, s>>>(P);
-            else ws_chain_kernel<false><<<g, WS_SCAN_BLOCK, WS_CHAIN_SMEM_BYTES, s>>>(P);
+            e = g_chain_block == 32 ? ws_launch_chain<32>(P, exact_fp, s) : (g_chain_block == 64 ? ws_launch_chain<64>(P, exact_fp, s) : ws_launch_chain<WS_SCAN_BLOCK>(P, exact_fp, s));
+            if (e != cudaSuccess) return e;
         } else {
             e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * (size_t)cdf_tiles, s);
             if (e != cudaSuccess) return e;
@@ -2309,6 +2415,9 @@ cudaError_t ws_kernels_init(int device) {
         const char* v = getenv("WSB200_SCAN");
         if (v != nullptr) g_scan_form = strcmp(v, "1pass") == 0 ? 1 : (strcmp(v, "chain") == 0 ? 2 : (strcmp(v, "3pass") == 0 ? 0 : WS_SCAN_DEFAULT_FORM));
         else g_scan_form = WS_SCAN_DEFAULT_FORM;
+        v = getenv("WSB200_CHAIN_BLOCK");
+        g_chain_block = v != nullptr ? atoi(v) : WS_CHAIN_DEFAULT_BLOCK;
+        if (g_chain_block != 32 && g_chain_block != 64) g_chain_block = WS_SCAN_BLOCK;
         v = getenv("WSB200_FX_EXTRA_BITS");
         g_fx_extra_bits = v != nullptr ? atoi(v) : 0;
         v = getenv("WSB200_VM");
@@ -2321,9 +2430,9 @@ cudaError_t ws_kernels_init(int device) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_search_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SEARCH_SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ws_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES);
+    e = cudaFuncSetAttribute(ws_chain_kernel<true, WS_SCAN_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES(WS_SCAN_BLOCK));
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(ws_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES);
+    e = cudaFuncSetAttribute(ws_chain_kernel<false, WS_SCAN_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES(WS_SCAN_BLOCK));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_vm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;
