@@ -181,8 +181,8 @@ def c5():
             if n * P * 16 > 120e9:
                 continue
             for label, s in (("s=0.5", 0.5), ("s=2", 2.0), ("s=4", 4.0), ("one-hot", None)):
-                for scheme in ("stratified", "systematic"):
-                    if scheme == "systematic" and (label != "s=2" or P != 6):
+                for scheme in ("stratified", "systematic", "multinomial"):
+                    if scheme != "stratified" and (label not in ("s=2", "one-hot") or P != 6):
                         continue
                     st = ws.SMCState(n, ess_perc_min=float("inf"), seed=0x5EED, resampler=scheme)
                     store = st.store

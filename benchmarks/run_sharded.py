@@ -104,9 +104,11 @@ def c5(rank, world, local):
     the global slot grid, NCCL migration of the offspring that cross a shard boundary, eager gather)."""
     import ctypes as C
     per_gpu = 100_000_000
-    for P in (1, 6):
-        for label, s in (("s=0.5", 0.5), ("s=2", 2.0)):
-            st = make_state(per_gpu * world, world, local, ess_perc_min=float("inf"), seed=0x5EED)
+    cases = [(P, label, s, "stratified") for P in (1, 6) for label, s in (("s=0.5", 0.5), ("s=2", 2.0), ("s=4", 4.0))]
+    cases += [(6, "s=2", 2.0, "systematic"), (6, "s=2", 2.0, "multinomial"), (16, "s=2", 2.0, "stratified")]
+    if True:
+        for P, label, s, scheme in cases:
+            st = make_state(per_gpu * world, world, local, ess_perc_min=float("inf"), seed=0x5EED, resampler=scheme)
             store = st.store
             store._call("ws_set_lazy_gather", 0)
             for p in range(P):
@@ -137,7 +139,7 @@ def c5(rank, world, local):
             planes = P + 1
             alg = 32 + 16 * planes
             n = per_gpu * world
-            emit(rank, config=f"C5 sharded resample N={per_gpu} per GPU x {world}, payload={P}+1 planes {label} stratified",
+            emit(rank, config=f"C5 sharded resample N={per_gpu} per GPU x {world}, payload={P}+1 planes {label} {scheme}",
                  ms=ms, ess_perc=ess, particles_per_sec=n / (ms * 1e-3), alg_bytes_per_particle=alg,
                  achieved_gbs_per_gpu=alg * per_gpu / (ms * 1e-3) / 1e9, hbm_frac_per_gpu=alg * per_gpu / (ms * 1e-3) / 1e9 / HBM,
                  migrated_particles_rank0=float(np.mean(mig)), migrated_bytes_rank0=float(np.mean(mig)) * 8 * planes,

@@ -711,7 +711,7 @@ __device__ __forceinline__ int ws_F_int(unsigned long long C, unsigned int n, in
 }
 
 #ifndef WS_CDF_ASYNC
-#define WS_CDF_ASYNC 1   // next tile's log-weights by cp.async into shared memory (1) or by plain loads into registers (0)
+#define WS_CDF_ASYNC 0   // (measured, profiles/r2o_scan_variants.txt: registers 0.74 ms, cp.async 0.81 ms for scan + search at N = 1e8) next tile's log-weights by cp.async into shared memory (1) or by plain loads into registers (0)
 #endif
 #ifndef WS_CDF_MINB
 #define WS_CDF_MINB 5   // <= 51 registers: five CTAs per SM (measured against 1 / 4 with grids of 3, 4, 8 CTAs per SM)
