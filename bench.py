@@ -439,7 +439,9 @@ def main():
     if dom:
         sl = stats1["sl_passes"] - stats0["sl_passes"]
         vm_name = "ws_vm_sl_kernel<WsSigSsm2d>" if sl > 0 else "ws_vm_kernel"
-        scan_name = "ws_scan_search_kernel" if world == 1 else "ws_cdf_tiles_kernel + ws_cdf_offsets_kernel + ws_search_kernel"
+        scan_form = os.environ.get("WSB200_SCAN", "3pass") if world == 1 else "3pass"
+        scan_name = {"chain": "ws_chain_kernel", "1pass": "ws_scan_search_kernel"}.get(
+            scan_form, "ws_cdf_tiles_kernel + ws_cdf_group_offsets_kernel + ws_search_kernel")
         roofline = {"bound": "hbm", "kernel": {"gather": "ws_gather_kernel", "fused_pass": vm_name, "scan_search": scan_name}[dom],
                     "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                     "frac": per_kernel[dom]["frac"],
