@@ -15,6 +15,7 @@
 #define WS_VM_MINB 5          // resident CTAs per SM the kernel is compiled for (register cap 65536/(128*MINB))
 #endif
 #define WS_VM_MAX_IO 24       // planes loaded / stored per fused pass
+#define WS_VM_MAX_CKPT 16     // checkpoints per fused pass (speculative blocks)
 #define WS_VM_MAX_OPS 96      // micro-ops per fused pass (program travels in kernel params)
 #define WS_VM_MAX_REGS ((192 * 1024) / (WS_VM_BLOCK * WS_VM_P * 8))  // register-file rows per pass (<= 192 KB of smem)
 #define WS_SCAN_BLOCK 256
@@ -65,6 +66,13 @@ struct WsVmProgram {
     uint8_t expect_reg[8];
     const WsReduceOut* red;  // (m,S) for expectation mode
     double* expect_partials; // [gridDim.x][n_expect]
+    // Checkpoints (speculative blocks of weighting statements, ws_exec_spec): after micro-op ckpt_pc[j] the weight
+    // terms accumulated so far are folded into the running log-weight — the log-weight the statement-by-statement
+    // passes would have stored at that point, same association — and pushed into the j-th (m, S, Q) state, so ONE
+    // pass yields the ESS after each of its statements.  Interpreter only (ws_vm_kernel).
+    int32_t n_ckpt;
+    uint8_t ckpt_pc[WS_VM_MAX_CKPT];
+    WsLse* ckpt_partials;    // [n_ckpt][gridDim.x]
     WsRng rng;
     WsOp ops[WS_VM_MAX_OPS];
 };
@@ -156,6 +164,6 @@ cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t
 cudaError_t ws_launch_compose(const WsComposeParams& P, int32_t* out, const int32_t* start, cudaStream_t s);
 cudaError_t ws_launch_compose_rows(const WsComposeParams& P, int64_t* out, const int64_t* start, cudaStream_t s);
 int ws_vm_sl_grid(const WsVmProgram& P);  // > 0: the window runs on a straight-line executor with this grid
-int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count);
-int ws_vm_smem_bytes(int n_regs, int n_loads, int n_ops);
+int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count, int n_ckpt = 0);
+int ws_vm_smem_bytes(int n_regs, int n_loads, int n_ops, int n_ckpt = 0);
 cudaError_t ws_kernels_init(int device);

@@ -139,6 +139,13 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
     // the program, unpacked once per CTA (ws_vm.cuh: WsDop) behind the register file and the staging rows
     WsDop* const dops = reinterpret_cast<WsDop*>(ws_vm_smem + (P.n_regs + (STAGED ? P.n_loads : 0)) * RS);
     for (int t = threadIdx.x; t < P.n_ops; t += WS_VM_BLOCK) dops[t] = ws_decode_op<WS_VM_BLOCK, WS_VM_P>(P.ops[t]);
+    // per-thread (m, S, Q) states of the checkpoints: [n_ckpt][3][WS_VM_BLOCK] behind the decoded program
+    double* const ck = reinterpret_cast<double*>(dops + P.n_ops) + threadIdx.x;
+    for (int c = 0; c < P.n_ckpt; ++c) {
+        ck[(c * 3 + 0) * WS_VM_BLOCK] = -INFINITY;
+        ck[(c * 3 + 1) * WS_VM_BLOCK] = 0.0;
+        ck[(c * 3 + 2) * WS_VM_BLOCK] = 0.0;
+    }
     __syncthreads();
 
     WsLse part;
@@ -264,10 +271,37 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
 
         // ---- program ------------------------------------------------------------------------------
         double acc[WS_VM_P];
+        double lw_run[WS_VM_P];   // log-weight the window started from (+ the terms folded in at checkpoints)
 #pragma unroll
-        for (int j = 0; j < WS_VM_P; ++j) acc[j] = 0.0;
-        for (int pc = 0; pc < P.n_ops; ++pc) {
-            ws_vm_exec_d<WS_VM_BLOCK, WS_VM_P>(dops[pc], R, acc, P.rng, particle);
+        for (int j = 0; j < WS_VM_P; ++j) {
+            acc[j] = 0.0;
+            lw_run[j] = lmode == 1 ? lw_old[j] : lbase;
+        }
+        if (P.n_ckpt == 0) {
+            for (int pc = 0; pc < P.n_ops; ++pc) {
+                ws_vm_exec_d<WS_VM_BLOCK, WS_VM_P>(dops[pc], R, acc, P.rng, particle);
+            }
+        } else {
+            int next = 0;
+            for (int pc = 0; pc < P.n_ops; ++pc) {
+                ws_vm_exec_d<WS_VM_BLOCK, WS_VM_P>(dops[pc], R, acc, P.rng, particle);
+                if (next < P.n_ckpt && pc == (int)P.ckpt_pc[next]) {
+#pragma unroll
+                    for (int j = 0; j < WS_VM_P; ++j) {
+                        lw_run[j] += acc[j];
+                        acc[j] = 0.0;
+                    }
+                    WsLse st;
+                    st.m = ck[(next * 3 + 0) * WS_VM_BLOCK];
+                    st.S = ck[(next * 3 + 1) * WS_VM_BLOCK];
+                    st.Q = ck[(next * 3 + 2) * WS_VM_BLOCK];
+                    lse_push_many<WS_VM_P>(st, lw_run, live);
+                    ck[(next * 3 + 0) * WS_VM_BLOCK] = st.m;
+                    ck[(next * 3 + 1) * WS_VM_BLOCK] = st.S;
+                    ck[(next * 3 + 2) * WS_VM_BLOCK] = st.Q;
+                    ++next;
+                }
+            }
         }
 
         // ---- stores ---------------------------------------------------------------------------------
@@ -282,7 +316,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
             double lw[WS_VM_P];
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) {
-                lw[j] = (lmode == 1 ? lw_old[j] : lbase) + acc[j];
+                lw[j] = lw_run[j] + acc[j];
                 if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
             }
             lse_push_many<WS_VM_P>(part, lw, live);
@@ -304,6 +338,15 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
     if (P.logw_mode != 0 && P.partials != nullptr) {
         WsLse tot = lse_block_reduce<WS_VM_BLOCK>(part, warp_scratch);
         if (threadIdx.x == 0) P.partials[blockIdx.x] = tot;
+    }
+    for (int c = 0; c < P.n_ckpt; ++c) {
+        WsLse st;
+        st.m = ck[(c * 3 + 0) * WS_VM_BLOCK];
+        st.S = ck[(c * 3 + 1) * WS_VM_BLOCK];
+        st.Q = ck[(c * 3 + 2) * WS_VM_BLOCK];
+        __syncthreads();  // warp_scratch of the previous reduction has been read
+        WsLse tot = lse_block_reduce<WS_VM_BLOCK>(st, warp_scratch);
+        if (threadIdx.x == 0) P.ckpt_partials[(size_t)c * gridDim.x + blockIdx.x] = tot;
     }
     if (P.n_expect > 0) {
         __shared__ double esc[WS_VM_BLOCK / 32][8];
@@ -456,7 +499,7 @@ static cudaError_t ws_launch_vm_sl(const WsVmProgram& P, cudaStream_t s) {
 }
 // (m, S, Q) partials a straight-line launch of this window would write (the runtime sizes n_partials with it)
 int ws_vm_sl_grid(const WsVmProgram& P) {
-    if (g_vm_interp_only || ws_sl_find(P) < 0) return 0;
+    if (g_vm_interp_only || P.n_ckpt != 0 || ws_sl_find(P) < 0) return 0;
     constexpr int TILE = WS_VM_BLOCK * WS_SL_P;
     const int64_t tiles = (P.n + TILE - 1) / TILE;
     int grid = (int)(tiles < (int64_t)g_sm_count * WS_SL_MINB ? tiles : (int64_t)g_sm_count * WS_SL_MINB);
@@ -467,14 +510,14 @@ int ws_vm_sl_grid(const WsVmProgram& P) {
 static bool ws_vm_staged(int n_regs, int n_loads) {
     return n_loads > 0 && (size_t)(n_regs + n_loads) * WS_VM_BLOCK * WS_VM_P * sizeof(double) <= (size_t)200 * 1024;
 }
-int ws_vm_smem_bytes(int n_regs, int n_loads, int n_ops) {
+int ws_vm_smem_bytes(int n_regs, int n_loads, int n_ops, int n_ckpt) {
     const int rows = (n_regs < 1 ? 1 : n_regs) + (ws_vm_staged(n_regs < 1 ? 1 : n_regs, n_loads) ? n_loads : 0);
-    return rows * WS_VM_BLOCK * WS_VM_P * (int)sizeof(double) + n_ops * (int)sizeof(WsDop);
+    return rows * WS_VM_BLOCK * WS_VM_P * (int)sizeof(double) + n_ops * (int)sizeof(WsDop) + n_ckpt * 3 * WS_VM_BLOCK * (int)sizeof(double);
 }
 
-int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count) {
+int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count, int n_ckpt) {
     // resident CTAs per SM limited by the shared-memory register file and 2048 threads / SM
-    const int smem = ws_vm_smem_bytes(n_regs, n_loads, n_ops) + 1024;
+    const int smem = ws_vm_smem_bytes(n_regs, n_loads, n_ops, n_ckpt) + 1024;
     int per_sm = (227 * 1024) / smem;
     if (per_sm > WS_VM_MINB) per_sm = WS_VM_MINB;  // __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB)
     if (per_sm < 1) per_sm = 1;
@@ -482,7 +525,7 @@ int ws_vm_max_grid(int n_regs, int n_loads, int n_ops, int sm_count) {
 }
 
 cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
-    if (!g_vm_interp_only) {
+    if (!g_vm_interp_only && P.n_ckpt == 0) {
         switch (ws_sl_find(P)) {
 #define WS_SL_CASE(idx, Sig) \
     case idx: return ws_launch_vm_sl<Sig>(P, s);
@@ -491,7 +534,7 @@ cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
             default: break;
         }
     }
-    const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads, P.n_ops);
+    const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads, P.n_ops, P.n_ckpt);
     if (ws_vm_staged(P.n_regs, P.n_loads)) ws_vm_kernel<true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     else ws_vm_kernel<false><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     return cudaGetLastError();
