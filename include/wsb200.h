@@ -229,6 +229,19 @@ typedef struct ws_cmd {
     const double* mat;
 } ws_cmd;
 int ws_exec(ws_ctx* ctx, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params);
+/* The same list run for up to n_steps consecutive loop elements (params[step][n_params]) as ONE device pass, for
+ * bodies of the form "weighting statements, Resample(), if resampled ... end" (examples/linear_regression.jl:20-26:
+ * the reference's Resample.apply!, src/transformers.jl:474-498, needs the ESS after every observation, i.e. one pass
+ * and one host round trip per statement).  The pass records the (m, S, Q) of the log-weights after each step; if no
+ * step's ESS falls below the threshold all of them are done (*n_done = steps issued — possibly fewer than n_steps, a
+ * pass holds a bounded number — *fired = 0); otherwise the steps behind the first firing one are rolled back, that
+ * step's Resample runs as ws_resample would have, and *n_done counts the steps up to and including it, *fired = 1:
+ * the caller applies the `if resampled` body and goes on with the next element.  Log-weights, tape, depth and Philox
+ * stream numbering are those of the statement-by-statement run; the (m, S, Q) sums are grouped differently, so an
+ * ESS within an ulp of the threshold may decide differently (as between any two kernel shapes; ws_get_ess_ties).
+ * WS_EUNSUPPORTED (nothing changed): sharded or replayed states, statements that write columns or draw variates. */
+int ws_exec_spec(ws_ctx* ctx, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params, int32_t n_steps,
+                 int32_t* n_done, int32_t* fired);
 
 /* Resample.apply! (src/transformers.jl:474-498) — the exact state machine:
  * no-op if !weights_changed; else exp_norm -> ess_perc -> if ess < ess_perc_min: stratified

@@ -359,3 +359,50 @@ def test_single_kernel_resample_one_hot_and_spec(ws, scheme):
         ids = st["id"].astype(np.int64)
         a_ref, _ = ref.stratified_ancestors_fixed_point(ref.exp_norm(lw), seed.value, stream.value, scheme)
         np.testing.assert_array_equal(ids, a_ref)
+
+
+# ------------------------------------------------------------------------------------------------
+# Loop steps run in speculative blocks (ws_exec_spec: K observations in one pass, the ESS after each from the
+# pass's checkpoints, roll-back to the first step that resamples) == the same steps run one by one
+# ------------------------------------------------------------------------------------------------
+OBS_ONLY = '''
+@model function obs_only(xs, ys)
+    α ~ Normal(0.0, 10.0)
+    β ~ Normal(0.0, 10.0)
+    for (x, y) in zip(xs, ys)
+        y => Normal(α + β * x, 1.0)
+        if resampled
+            α .= α + 0.0
+        end
+    end
+end
+'''
+
+
+@pytest.mark.parametrize("src", ["linreg", "obs_only"])
+@pytest.mark.parametrize("n", [20_011, 300_000])
+@pytest.mark.parametrize("ess", [0.5, 0.9])
+def test_speculative_blocks_equal_stepwise(ws, src, n, ess):
+    rng = np.random.default_rng(5)
+    xs = rng.uniform(0, 10, 150)
+    ys = 1 - 0.5 * xs + rng.standard_normal(150)
+    runs = []
+    try:
+        for spec in (False, True):
+            ws.core.SPEC_BLOCKS = spec
+            runs.append(_run(ws, LINREG if src == "linreg" else OBS_ONLY, (list(xs), list(ys)), n, seed=31, ess=ess))
+    finally:
+        ws.core.SPEC_BLOCKS = True
+    a, b = runs
+    sa, sb = a.stats(), b.stats()
+    assert sa["resamples_done"] == sb["resamples_done"] > 0
+    assert sa["resamples_fired"] == sb["resamples_fired"] >= 150
+    assert sa["moves_run"] == sb["moves_run"]
+    assert sb["fused_passes"] < sa["fused_passes"] / 2, (sa["fused_passes"], sb["fused_passes"])
+    # same association of the log-weight sums and the same Philox stream numbering: only the grouping of the
+    # (m, S, Q) partials differs (different kernel shapes), i.e. log-sum-exp in the last place
+    for c in ("α", "β"):
+        np.testing.assert_allclose(a[c], b[c], rtol=1e-9, atol=1e-12, err_msg=c)
+    np.testing.assert_allclose(a.weights, b.weights, rtol=1e-10, atol=1e-10)
+    assert abs(ws.log_evidence(a) - ws.log_evidence(b)) <= 1e-11 * abs(ws.log_evidence(b))
+    assert a.depth == b.depth

@@ -139,6 +139,8 @@ SIGNATURES = {
     "ws_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),
     "ws_resample_async": (C.c_int, [_ctx]),
     "ws_exec": (C.c_int, [_ctx, C.POINTER(ws_cmd), C.c_int32, C.POINTER(C.c_double), C.c_int32]),
+    "ws_exec_spec": (C.c_int, [_ctx, C.POINTER(ws_cmd), C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_int32,
+                               C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ws_last_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),
     "ws_exp_norm": (C.c_int, [_ctx, C.c_void_p]),
     "ws_log_evidence": (C.c_int, [_ctx, _dp, _dp]),

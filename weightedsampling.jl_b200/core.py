@@ -867,8 +867,18 @@ class _LoopTemplate:
             raise
         except Exception as e:          # the body uses the element at build time (indexing, names, arithmetic on it, ...)
             raise _NoTemplate(f"{type(e).__name__}: {e}")
+        # "weighting statements, Resample(), if resampled ... end" (examples/linear_regression.jl:20-26): the statements
+        # are templated and run in speculative blocks (ws_exec_spec); the `if` body is built for the element that fires
+        self.spec = False
         if not _only_statements(body):
-            raise _NoTemplate("the body contains control flow or moves")
+            steps = getattr(body, "steps", ())
+            if (SPEC_BLOCKS and type(body).__name__ == "Sequence" and len(steps) >= 3 and type(steps[-1]).__name__ == "Cond"
+                    and getattr(steps[-1].predfn, "only_resampled", False) and type(steps[-2]).__name__ == "Resample"
+                    and all(type(t).__name__ in ("Observe", "Weight") for t in steps[:-2])):
+                body = Sequence(*steps[:-1])
+                self.spec = True
+            else:
+                raise _NoTemplate("the body contains control flow or moves")
         rec = _Recorder(store)
         try:
             body.apply(_RecState(rec))
@@ -904,8 +914,24 @@ class _LoopTemplate:
         self.store._call("ws_exec", self.arr, self.n, self._params, self.n_params)
         return True
 
+    def run_block(self, xs):
+        """up to len(xs) consecutive elements as one speculative block -> (elements done, the last of them resampled);
+        None if an element does not have the template's shape"""
+        flat = []
+        for x in xs:
+            vals = self.flatten(x)
+            if vals is None:
+                return None
+            flat.extend(vals)
+        buf = (C.c_double * max(1, len(flat)))(*flat)
+        n_done, fired = C.c_int32(), C.c_int32()
+        self.store._call("ws_exec_spec", self.arr, self.n, buf, self.n_params, len(xs), C.byref(n_done), C.byref(fired))
+        return n_done.value, bool(fired.value)
+
 
 LOOP_TEMPLATES = os.environ.get("WSB200_LOOP_TEMPLATE", "1") != "0"
+SPEC_BLOCKS = os.environ.get("WSB200_SPEC_BLOCKS", "1") != "0"
+SPEC_BLOCK_STEPS = int(os.environ.get("WSB200_SPEC_BLOCK_STEPS", "16"))
 
 
 class Loop(ParticleTransformer):
@@ -930,17 +956,35 @@ class Loop(ParticleTransformer):
             for x in coll:
                 self.bodyfn(x).apply(state)
             return
-        it = iter(coll)
-        self.bodyfn(next(it)).apply(state)          # the first element runs as written (it may create the columns)
+        if not hasattr(coll, "__getitem__"):
+            coll = list(coll)
+        self.bodyfn(coll[0]).apply(state)           # the first element runs as written (it may create the columns)
         tmpl = None
-        for x in it:
+        i, n = 1, len(coll)
+        while i < n:
+            x = coll[i]
             if tmpl is None:
                 try:
                     tmpl = _LoopTemplate(self.bodyfn, x, state.store)
                 except _NoTemplate:
                     tmpl = False
+            if tmpl is not False and tmpl.spec:
+                # blocks of steps in one pass; a step that resamples ends its block and runs its `if resampled` body
+                try:
+                    r = tmpl.run_block([coll[k] for k in range(i, min(n, i + SPEC_BLOCK_STEPS))])
+                except UnsupportedModelError:
+                    r = None
+                if r is None:
+                    tmpl = False        # (sharded / replayed state, an element of another shape): element by element
+                    continue
+                done, fired = r
+                if fired:
+                    self.bodyfn(coll[i + done - 1]).steps[-1].body.apply(state)
+                i += done
+                continue
             if tmpl is False or not tmpl.run(x):
                 self.bodyfn(x).apply(state)
+            i += 1
 
     def score(self, state, ctx):
         for x in self._coll(state):

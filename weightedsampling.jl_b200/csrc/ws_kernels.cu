@@ -129,7 +129,7 @@ __device__ __forceinline__ void ws_cp_async16(void* smem_dst, const void* gsrc) 
 __device__ __forceinline__ void ws_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ws_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <bool STAGED>
+template <bool STAGED, bool CKPT = false>
 __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __grid_constant__ WsVmProgram P) {
     extern __shared__ __align__(16) double ws_vm_smem[];
     __shared__ WsLse warp_scratch[WS_VM_BLOCK / 32];
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
     for (int t = threadIdx.x; t < P.n_ops; t += WS_VM_BLOCK) dops[t] = ws_decode_op<WS_VM_BLOCK, WS_VM_P>(P.ops[t]);
     // per-thread (m, S, Q) states of the checkpoints: [n_ckpt][3][WS_VM_BLOCK] behind the decoded program
     double* const ck = reinterpret_cast<double*>(dops + P.n_ops) + threadIdx.x;
-    for (int c = 0; c < P.n_ckpt; ++c) {
+    for (int c = 0; CKPT && c < P.n_ckpt; ++c) {
         ck[(c * 3 + 0) * WS_VM_BLOCK] = -INFINITY;
         ck[(c * 3 + 1) * WS_VM_BLOCK] = 0.0;
         ck[(c * 3 + 2) * WS_VM_BLOCK] = 0.0;
@@ -271,13 +271,13 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
 
         // ---- program ------------------------------------------------------------------------------
         double acc[WS_VM_P];
-        double lw_run[WS_VM_P];   // log-weight the window started from (+ the terms folded in at checkpoints)
+        double lw_run[WS_VM_P];   // CKPT: log-weight the window started from (+ the terms folded in at checkpoints)
 #pragma unroll
         for (int j = 0; j < WS_VM_P; ++j) {
             acc[j] = 0.0;
             lw_run[j] = lmode == 1 ? lw_old[j] : lbase;
         }
-        if (P.n_ckpt == 0) {
+        if (!CKPT) {
             for (int pc = 0; pc < P.n_ops; ++pc) {
                 ws_vm_exec_d<WS_VM_BLOCK, WS_VM_P>(dops[pc], R, acc, P.rng, particle);
             }
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
             double lw[WS_VM_P];
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) {
-                lw[j] = lw_run[j] + acc[j];
+                lw[j] = (CKPT ? lw_run[j] : (lmode == 1 ? lw_old[j] : lbase)) + acc[j];
                 if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
             }
             lse_push_many<WS_VM_P>(part, lw, live);
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
         WsLse tot = lse_block_reduce<WS_VM_BLOCK>(part, warp_scratch);
         if (threadIdx.x == 0) P.partials[blockIdx.x] = tot;
     }
-    for (int c = 0; c < P.n_ckpt; ++c) {
+    for (int c = 0; CKPT && c < P.n_ckpt; ++c) {
         WsLse st;
         st.m = ck[(c * 3 + 0) * WS_VM_BLOCK];
         st.S = ck[(c * 3 + 1) * WS_VM_BLOCK];
@@ -535,7 +535,10 @@ cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
         }
     }
     const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads, P.n_ops, P.n_ckpt);
-    if (ws_vm_staged(P.n_regs, P.n_loads)) ws_vm_kernel<true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
+    if (P.n_ckpt > 0) {
+        if (ws_vm_staged(P.n_regs, P.n_loads)) ws_vm_kernel<true, true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
+        else ws_vm_kernel<false, true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
+    } else if (ws_vm_staged(P.n_regs, P.n_loads)) ws_vm_kernel<true><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     else ws_vm_kernel<false><<<grid, WS_VM_BLOCK, smem, s>>>(P);
     return cudaGetLastError();
 }
@@ -2476,6 +2479,10 @@ cudaError_t ws_kernels_init(int device) {
     e = cudaFuncSetAttribute(ws_chain_kernel<true, WS_SCAN_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES(WS_SCAN_BLOCK));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_chain_kernel<false, WS_SCAN_BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_CHAIN_SMEM_BYTES(WS_SCAN_BLOCK));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_vm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(ws_vm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ws_vm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
     if (e != cudaSuccess) return e;

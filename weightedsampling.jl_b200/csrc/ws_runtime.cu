@@ -191,6 +191,21 @@ struct ws_ctx {
     // waits for each decision anyway; queueing the step then only adds the gated launches and a resampling event
     // per non-firing step.  Two steps in a row resolved before anything else was queued switch the run to ws_resample.
     int spec_immediate = 0;
+    // Speculative block (ws_exec_spec): K consecutive (weighting statements, Resample) steps issued as ONE pass whose
+    // checkpoints give the ESS after each step; spec_block is set while the steps are being queued.
+    struct SpecStep {
+        size_t tape_size;           // tape / score program right after the step's statements
+        Program::Mark score_mark;
+        int64_t depth;
+        uint64_t stream_before;     // next_stream before the step's Resample took its Philox stream
+        int32_t ckpt_pc;            // last micro-op of the step in the window
+    };
+    bool spec_block = false, spec_flushing = false;
+    std::vector<SpecStep> spec_steps;
+    double* d_logw_bak = nullptr;       // log-weights before the block (restored when a step fires)
+    WsLse* d_ck_partials = nullptr;     // [WS_VM_MAX_CKPT][WS_MAX_PARTIALS]
+    WsReduceOut* d_ck_red = nullptr;    // [WS_VM_MAX_CKPT]
+    WsReduceOut* h_ck_red = nullptr;    // pinned
 
     // resampling scratch
     int32_t* d_anc = nullptr;  // ancestors of the latest resampling event (== anc_live.back().ptr)
@@ -645,6 +660,10 @@ extern "C" int ws_destroy(ws_ctx* c) {
     if (c->h_ring) cudaFreeHost(c->h_ring);
     cudaFree(c->d_map);
     cudaFree(c->d_tile_words);
+    cudaFree(c->d_logw_bak);
+    cudaFree(c->d_ck_partials);
+    cudaFree(c->d_ck_red);
+    if (c->h_ck_red) cudaFreeHost(c->h_ck_red);
     cudaFree(c->d_cdf_local);
     cudaFree(c->d_tile_counter);
     cudaFree(c->d_heavy_F);
@@ -707,6 +726,8 @@ static int flush_window(ws_ctx* c) {
         reset_window(c);
         return WS_OK;
     }
+    if (c->spec_block && !c->spec_flushing)
+        return fail(c, WS_EUNSUPPORTED, "a speculative block was interrupted by a flush of the statement window");
     CK(c, cudaSetDevice(c->device));
     WsVmProgram P;
     memset(&P, 0, sizeof(P));
@@ -762,8 +783,13 @@ static int flush_window(ws_ctx* c) {
     } else {
         P.logw_mode = 0;
     }
+    if (c->spec_flushing) {
+        P.n_ckpt = (int32_t)c->spec_steps.size();
+        for (int32_t j = 0; j < P.n_ckpt; ++j) P.ckpt_pc[j] = (uint8_t)c->spec_steps[j].ckpt_pc;
+        P.ckpt_partials = c->d_ck_partials;
+    }
     const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
-    const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, P.n_ops, c->sm_count), (c->n + vm_tile - 1) / vm_tile);
+    const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, P.n_ops, c->sm_count, P.n_ckpt), (c->n + vm_tile - 1) / vm_tile);
     P.partials = w.has_acc ? c->d_partials : nullptr;
     P.n_expect = 0;
     P.rng.seed = c->seed;
@@ -2125,8 +2151,11 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id) {
     return WS_OK;
 }
 
+static int spec_checkpoint(ws_ctx* c);
+
 extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
     if (!c) return WS_EINVAL;
+    if (c->spec_block && !c->spec_flushing) return info ? fail(c, WS_EUNSUPPORTED, "ws_resample with an outcome inside a speculative block") : spec_checkpoint(c);
     if (info) {
         TRY(resolve_spec(c));  // the caller wants the outcome, including the current value of `resampled`
         info->fired = 0;
@@ -2221,6 +2250,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
 // uniforms (the cursor advances only on a firing step), sharded states, multinomial, eager gather.
 extern "C" int ws_resample_async(ws_ctx* c) {
     if (!c) return WS_EINVAL;
+    if (c->spec_block && !c->spec_flushing) return spec_checkpoint(c);
     if (!c->weights_changed) {
         c->last_info = ws_resample_info{0, -1, NAN, NAN, -1};
         c->last_info_pending = false;
@@ -2326,6 +2356,169 @@ extern "C" int ws_exec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const doub
             default: return fail(c, WS_EINVAL, "ws_exec: unknown command %d", cm.fn);
         }
     }
+    return WS_OK;
+}
+
+// ---- speculative blocks of (weighting statements, Resample) steps --------------------------------------------------
+// A model that only observes between resampling events (examples/linear_regression.jl: y => Normal(alpha + beta x_i, 1)
+// and `if resampled` moves, 12 events in 10 000 steps) pays, statement by statement, one pass over the particles and
+// one host round trip per observation, because Resample.apply! needs the ESS after every one.  Here K steps are issued
+// as ONE pass: the Resample of each step becomes a checkpoint of the window (ws_vm_kernel<.., true>: the terms so far
+// are folded into the running log-weight — same association as the separate passes — and pushed into that step's
+// (m, S, Q) state), K finalize kernels give the K decisions, and the host looks at them once.
+//   * none fires: the K steps are done (log-weights, tape, depth, Philox stream numbering as if run one by one);
+//   * step k is the first to fire: everything after step k is rolled back (log-weights from the copy taken before the
+//     block, tape / score program / depth / stream numbering from the marks of step k), the first k + 1 steps are run
+//     again as a plain window, and the Resample of step k goes through ws_resample itself.
+// Statements that write planes or draw variates are refused (nothing but log-weights may change inside a block).
+static int spec_checkpoint(ws_ctx* c) {
+    if (!c->weights_changed) return WS_OK;   // Resample is a no-op (transformers.jl:475-477): no decision to record
+    if (c->win.ops.empty() || !c->win.has_acc) return fail(c, WS_EUNSUPPORTED, "speculative block: a step without a weighting term");
+    if (!c->win.dirty.empty()) return fail(c, WS_EUNSUPPORTED, "speculative block: a statement writes a column");
+    if (c->spec_steps.size() >= WS_VM_MAX_CKPT) return fail(c, WS_EUNSUPPORTED, "speculative block: more than %d steps", WS_VM_MAX_CKPT);
+    if (c->win.ops.size() > 255) return fail(c, WS_EUNSUPPORTED, "speculative block: window too long");
+    ws_ctx::SpecStep st;
+    st.tape_size = c->tape.size();
+    st.score_mark = c->score.mark();
+    st.depth = c->depth;
+    st.stream_before = c->next_stream;
+    st.ckpt_pc = (int32_t)c->win.ops.size() - 1;
+    c->spec_steps.push_back(st);
+    c->next_stream++;            // the step's Philox stream is taken whether or not it fires (ws_resample)
+    c->weights_changed = false;
+    return WS_OK;
+}
+
+extern "C" int ws_exec_spec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params, int32_t n_steps,
+                            int32_t* n_done, int32_t* fired) {
+    if (!c || !n_done || !fired || n_steps < 1 || (n_params > 0 && !params)) return WS_EINVAL;
+    *n_done = 0;
+    *fired = 0;
+    if (c->nranks > 1 || c->d_replay_u != nullptr || c->d_replay_n != nullptr || !c->lazy_gather || c->cols.empty() || !c->async_resample)
+        return fail(c, WS_EUNSUPPORTED, "speculative blocks need a single-GPU state without replayed streams");
+    TRY(flush_window(c));
+    TRY(resolve_spec(c));
+    CK(c, cudaSetDevice(c->device));
+    if (c->d_ck_partials == nullptr) {
+        CK(c, cudaMalloc(&c->d_ck_partials, sizeof(WsLse) * WS_MAX_PARTIALS * WS_VM_MAX_CKPT));
+        CK(c, cudaMalloc(&c->d_ck_red, sizeof(WsReduceOut) * WS_VM_MAX_CKPT));
+        CK(c, cudaMallocHost(&c->h_ck_red, sizeof(WsReduceOut) * WS_VM_MAX_CKPT));
+        CK(c, cudaMalloc(&c->d_logw_bak, sizeof(double) * (size_t)c->n));
+    }
+    // ---- snapshot ----
+    const bool s_uniform = c->logw_uniform, s_partials = c->partials_valid, s_red = c->red_valid, s_resampled = c->resampled,
+               s_changed = c->weights_changed, s_wide = c->score_wide;
+    const double s_base = c->logw_base;
+    const int s_npart = c->n_partials;
+    const size_t s_tape = c->tape.size();
+    const Program::Mark s_score = c->score.mark();
+    const int64_t s_depth = c->depth;
+    const uint64_t s_stream = c->next_stream;
+    const ws_stats s_stats = c->stats;
+    if (!s_uniform) CK(c, cudaMemcpyAsync(c->d_logw_bak, c->logw, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    auto restore = [&](size_t tape_size, const Program::Mark& score_mark, int64_t depth, uint64_t stream) {
+        reset_window(c);
+        c->tape.resize(tape_size);
+        if (c->score_wide != s_wide) {
+            c->score = Program();   // the tape went wide inside the block: it is folded from its entries anyway
+        } else if (!c->score_wide) {
+            c->score.rollback(score_mark);
+            c->d_score_uploaded = std::min(c->d_score_uploaded, c->score.ops.size());
+        }
+        c->depth = depth;
+        c->next_stream = stream;
+    };
+    // ---- queue the steps ----
+    c->spec_block = true;
+    c->spec_steps.clear();
+    int rc = WS_OK;
+    int32_t issued = 0;
+    for (; issued < n_steps; ++issued) {
+        // room for one more step?  (every step of a block lowers to the same number of micro-ops)
+        if (issued > 0) {
+            const size_t per = (size_t)c->spec_steps[0].ckpt_pc + 1;
+            if (c->win.ops.size() + per > (size_t)std::min(WS_VM_MAX_OPS, 255) || (int)c->spec_steps.size() >= WS_VM_MAX_CKPT) break;
+        }
+        const size_t before = c->spec_steps.size();
+        rc = ws_exec(c, cmds, n_cmds, params + (size_t)issued * (size_t)n_params, n_params);
+        if (rc != WS_OK) break;
+        if (c->spec_steps.size() != before + 1) {
+            rc = fail(c, WS_EUNSUPPORTED, "speculative block: a step must end in exactly one Resample that has something to decide");
+            break;
+        }
+    }
+    if (rc != WS_OK) {
+        const std::string msg = c->err;
+        c->spec_block = false;
+        c->spec_steps.clear();
+        restore(s_tape, s_score, s_depth, s_stream);
+        c->weights_changed = s_changed;
+        c->stats = s_stats;
+        c->err = msg;
+        return rc;
+    }
+    // ---- one pass, K decisions ----
+    const int32_t K = (int32_t)c->spec_steps.size();
+    Program saved = c->win;
+    c->spec_flushing = true;
+    rc = flush_window(c);
+    c->spec_flushing = false;
+    c->spec_block = false;
+    if (rc != WS_OK) return rc;
+    const int grid = c->n_partials;
+    for (int32_t j = 0; j < K; ++j)
+        CK(c, ws_launch_finalize(c->d_ck_partials + (size_t)j * grid, grid, c->n_global, c->ess_perc_min, c->d_ck_red + j, c->stream));
+    CK(c, cudaMemcpyAsync(c->h_ck_red, c->d_ck_red, sizeof(WsReduceOut) * (size_t)K, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    c->stats.kernel_launches += K;
+    c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut) * K;
+    int32_t first = K;
+    for (int32_t j = 0; j < K; ++j)
+        if (c->h_ck_red[j].do_resample) {
+            first = j;
+            break;
+        }
+    if (first == K) {
+        // nothing fired: the block is done
+        const WsReduceOut& last = c->h_ck_red[K - 1];
+        *c->h_red = last;
+        CK(c, cudaMemcpyAsync(c->d_red, c->d_ck_red + (K - 1), sizeof(WsReduceOut), cudaMemcpyDeviceToDevice, c->stream));
+        c->red_valid = true;
+        c->resampled = false;
+        c->weights_changed = false;
+        c->stats.resamples_fired += K;
+        c->last_info = ws_resample_info{1, 0, last.ess_perc, last.log_mean_w, -1};
+        c->last_info_pending = false;
+        c->spec_steps.clear();
+        *n_done = K;
+        *fired = 0;
+        return WS_OK;
+    }
+    // ---- step `first` fires: back to the state before the block, the first `first + 1` steps again as a plain window ----
+    const ws_ctx::SpecStep st = c->spec_steps[first];
+    c->spec_steps.clear();
+    if (s_uniform) {
+        c->logw_uniform = true;
+        c->logw_base = s_base;
+    } else {
+        CK(c, cudaMemcpyAsync(c->logw, c->d_logw_bak, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+        c->logw_uniform = false;
+    }
+    c->logw_spec = false;
+    c->partials_valid = false;
+    c->red_valid = false;
+    (void)s_partials; (void)s_red; (void)s_npart;
+    c->resampled = s_resampled;
+    restore(st.tape_size, st.score_mark, st.depth, st.stream_before);
+    saved.ops.resize((size_t)st.ckpt_pc + 1);
+    c->win = saved;
+    TRY(flush_window(c));
+    c->stats.resamples_fired += first;   // the steps before it were evaluated and did not fire
+    c->weights_changed = true;
+    ws_resample_info info{};
+    TRY(ws_resample(c, &info));
+    *n_done = first + 1;
+    *fired = info.resampled;
     return WS_OK;
 }
 

@@ -813,6 +813,7 @@ def _build(stmts, env, kernels, proposals):
                 # `resampled` -> state.resampled (rewrites.jl:360-368); anything else is build-time
                 vals = {"resampled": state.resampled} if uses_resampled else {}
                 return bool(ev(cond, cenv.child(vals)))
+            predfn.only_resampled = cond == ("name", "resampled")   # `if resampled`: lets a loop run its steps in blocks (core.Loop)
             if _build_is_pure(body):
                 steps.append(core.Cond(predfn, lazy_body=lambda body=body, benv=env.snapshot(): core.Sequence(
                     *_build(body, benv, kernels, proposals))))
