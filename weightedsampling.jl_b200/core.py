@@ -931,7 +931,7 @@ class _LoopTemplate:
 
 LOOP_TEMPLATES = os.environ.get("WSB200_LOOP_TEMPLATE", "1") != "0"
 SPEC_BLOCKS = os.environ.get("WSB200_SPEC_BLOCKS", "1") != "0"
-SPEC_BLOCK_STEPS = int(os.environ.get("WSB200_SPEC_BLOCK_STEPS", "16"))
+SPEC_BLOCK_STEPS = int(os.environ.get("WSB200_SPEC_BLOCK_STEPS", "8"))   # what the register-resident block kernel holds (WS_SLCK_N)
 
 
 class Loop(ParticleTransformer):

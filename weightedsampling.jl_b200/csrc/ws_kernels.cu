@@ -486,6 +486,130 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SL_MINB) ws_vm_sl_kernel(const
     }
 }
 
+// ---- straight-line form of a checkpointed window (speculative blocks, ws_exec_spec) ------------------------------
+// The window is a signature's window repeated n_ckpt <= NCK times with other constants (the K observations of a block
+// of examples/linear_regression.jl's loop), a checkpoint behind every repetition.  The planes are loaded once, every
+// repetition runs the signature's micro-ops (the interpreter's own arithmetic, as in ws_vm_sl_kernel), folds its
+// terms into the running log-weight and pushes it into that repetition's (m, S, Q) state — NCK states in registers.
+// The interpreter's checkpoints (ws_vm_kernel<., true>) keep their states in shared memory, which costs it its
+// occupancy: 65 us per observation at N = 1e7 against 20 here.
+#ifndef WS_SLCK_N
+#define WS_SLCK_N 8      // checkpoints per pass
+#endif
+#ifndef WS_SLCK_P
+#define WS_SLCK_P 2      // particles per thread
+#endif
+#ifndef WS_SLCK_MINB
+#define WS_SLCK_MINB 4
+#endif
+template <class Sig, int PP, int NCK>
+__global__ void __launch_bounds__(WS_VM_BLOCK, WS_SLCK_MINB) ws_vm_sl_ckpt_kernel(const __grid_constant__ WsVmProgram P) {
+    extern __shared__ __align__(16) double ws_vm_smem[];
+    __shared__ WsLse warp_scratch[WS_VM_BLOCK / 32];
+    __shared__ double kc[NCK][Sig::n_ops][3];   // constants of the repetitions
+    constexpr int RS = PP * WS_VM_BLOCK;
+    constexpr int TILE = WS_VM_BLOCK * PP;
+    constexpr int NL = Sig::n_loads;
+    double* const stage = ws_vm_smem + threadIdx.x;  // [NL][PP][WS_VM_BLOCK]
+    const int reps = P.n_ckpt;
+    for (int t = threadIdx.x; t < reps * Sig::n_ops; t += WS_VM_BLOCK) {
+        kc[t / Sig::n_ops][t % Sig::n_ops][0] = P.ops[t].k0;
+        kc[t / Sig::n_ops][t % Sig::n_ops][1] = P.ops[t].k1;
+        kc[t / Sig::n_ops][t % Sig::n_ops][2] = P.ops[t].k2;
+    }
+    __syncthreads();
+    WsLse st[NCK];
+#pragma unroll
+    for (int c = 0; c < NCK; ++c) {
+        st[c].m = -INFINITY;
+        st[c].S = 0.0;
+        st[c].Q = 0.0;
+    }
+    const int n = (int)P.n;
+    const int n_tiles = (n + TILE - 1) / TILE;
+    const int lmode = P.logw_mode;          // 1 or 2 (a block starts from resolved log-weights)
+    const double lbase = P.logw_base;
+    const bool any_gather = P.load_gather != 0u;
+    auto tile_index = [&](int tile, int j) -> int {
+        const int i = tile * TILE + (int)threadIdx.x + j * WS_VM_BLOCK;
+        return i < n ? i : n - 1;
+    };
+    auto issue_stage = [&](int tile) {
+#pragma unroll
+        for (int k = 0; k < NL; ++k) {
+            const bool g = any_gather && ((P.load_gather >> k) & 1u);
+            const double* __restrict__ ptr = P.load_ptr[k];
+#pragma unroll
+            for (int j = 0; j < PP; ++j) {
+                const int i = tile_index(tile, j);
+                ws_cp_async8(stage + k * RS + j * WS_VM_BLOCK, ptr + (unsigned)(g ? __ldg(P.ancestors + i) : i));
+            }
+        }
+        ws_cp_async_commit();
+    };
+    if ((int)blockIdx.x < n_tiles) issue_stage(blockIdx.x);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        bool live[PP];
+        uint64_t particle[PP];
+        const int first = tile * TILE + (int)threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < PP; ++j) {
+            const int i = first + j * WS_VM_BLOCK;
+            live[j] = i < n;
+            particle[j] = (uint64_t)(P.particle_offset + (int64_t)(live[j] ? i : n - 1));
+        }
+        double R[Sig::n_regs * PP];
+        ws_cp_async_wait_all();
+        ws_sl_loads<Sig, PP, WS_VM_BLOCK>(R, stage, std::make_integer_sequence<int, NL>{});
+        if (tile + (int)gridDim.x < n_tiles) issue_stage(tile + gridDim.x);
+        double lw[PP];
+#pragma unroll
+        for (int j = 0; j < PP; ++j) lw[j] = lmode == 1 ? P.logw[(unsigned)tile_index(tile, j)] : lbase;
+#pragma unroll
+        for (int c = 0; c < NCK; ++c) {
+            if (c < reps) {
+                WsSlConsts<Sig> K;
+#pragma unroll
+                for (int i = 0; i < Sig::n_ops; ++i) {
+                    K.k[i][0] = kc[c][i][0];
+                    K.k[i][1] = kc[c][i][1];
+                    K.k[i][2] = kc[c][i][2];
+                }
+                double acc[PP];
+#pragma unroll
+                for (int j = 0; j < PP; ++j) acc[j] = 0.0;
+                ws_sl_run_at<Sig, PP>(R, acc, P, P.ops + c * Sig::n_ops, K, particle, std::make_integer_sequence<int, Sig::n_ops>{});
+#pragma unroll
+                for (int j = 0; j < PP; ++j) lw[j] += acc[j];
+                lse_push_many<PP>(st[c], lw, live);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < PP; ++j)
+            if (live[j]) P.logw[(unsigned)first + j * WS_VM_BLOCK] = lw[j];
+    }
+#pragma unroll
+    for (int c = 0; c < NCK; ++c) {
+        if (c < reps) {
+            __syncthreads();  // warp_scratch of the previous reduction has been read
+            WsLse tot = lse_block_reduce<WS_VM_BLOCK>(st[c], warp_scratch);
+            if (threadIdx.x == 0) {
+                P.ckpt_partials[(size_t)c * gridDim.x + blockIdx.x] = tot;
+                if (c == reps - 1 && P.partials != nullptr) P.partials[blockIdx.x] = tot;   // the log-weights the pass leaves behind
+            }
+        }
+    }
+}
+static bool ws_slck_ok(const WsVmProgram& P) {
+    return P.n_ckpt > 0 && P.n_expect == 0 && (P.logw_mode == 1 || P.logw_mode == 2) && ws_sl_matches_repeated<WsSigLinregObs>(P, WS_SLCK_N);
+}
+static int ws_slck_grid(const WsVmProgram& P) {
+    constexpr int TILE = WS_VM_BLOCK * WS_SLCK_P;
+    const int64_t tiles = (P.n + TILE - 1) / TILE;
+    const int grid = (int)(tiles < (int64_t)g_sm_count * WS_SLCK_MINB ? tiles : (int64_t)g_sm_count * WS_SLCK_MINB);
+    return grid < 1 ? 1 : grid;
+}
+
 static bool g_vm_interp_only = false;  // env WSB200_VM=interp: every window on the interpreter (A/B, tests)
 template <class Sig>
 static cudaError_t ws_launch_vm_sl(const WsVmProgram& P, cudaStream_t s) {
@@ -499,6 +623,7 @@ static cudaError_t ws_launch_vm_sl(const WsVmProgram& P, cudaStream_t s) {
 }
 // (m, S, Q) partials a straight-line launch of this window would write (the runtime sizes n_partials with it)
 int ws_vm_sl_grid(const WsVmProgram& P) {
+    if (!g_vm_interp_only && P.n_ckpt != 0 && ws_slck_ok(P)) return ws_slck_grid(P);
     if (g_vm_interp_only || P.n_ckpt != 0 || ws_sl_find(P) < 0) return 0;
     constexpr int TILE = WS_VM_BLOCK * WS_SL_P;
     const int64_t tiles = (P.n + TILE - 1) / TILE;
@@ -533,6 +658,11 @@ cudaError_t ws_launch_vm(const WsVmProgram& P, int grid, cudaStream_t s) {
 #undef WS_SL_CASE
             default: break;
         }
+    }
+    if (!g_vm_interp_only && P.n_ckpt != 0 && ws_slck_ok(P)) {
+        constexpr int smem_ck = WsSigLinregObs::n_loads * WS_VM_BLOCK * WS_SLCK_P * (int)sizeof(double);
+        ws_vm_sl_ckpt_kernel<WsSigLinregObs, WS_SLCK_P, WS_SLCK_N><<<ws_slck_grid(P), WS_VM_BLOCK, smem_ck, s>>>(P);
+        return cudaGetLastError();
     }
     const int smem = ws_vm_smem_bytes(P.n_regs, P.n_loads, P.n_ops, P.n_ckpt);
     if (P.n_ckpt > 0) {
@@ -593,6 +723,36 @@ __global__ void __launch_bounds__(256) ws_finalize_kernel(const WsLse* __restric
         out->do_resample = (out->ess_perc < ess_perc_min) ? 1 : 0;  // NaN compares false, as in Julia
         ws_count_ess_tie(out->ess_perc, ess_perc_min, ties);
     }
+}
+
+// K reductions at once (the checkpoints of a speculative block): CTA j finalizes partials[j * n_partials ...] into out[j]
+__global__ void __launch_bounds__(256) ws_finalize_multi_kernel(const WsLse* __restrict__ partials, int n_partials, int64_t n_global,
+                                                                double ess_perc_min, WsReduceOut* __restrict__ out) {
+    __shared__ WsLse warp_scratch[8];
+    const WsLse* mine = partials + (size_t)blockIdx.x * n_partials;
+    WsLse part;
+    part.m = -INFINITY;
+    part.S = 0.0;
+    part.Q = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += 256) part = lse_combine(part, mine[i]);
+    WsLse tot = lse_block_reduce<256>(part, warp_scratch);
+    if (threadIdx.x == 0) {
+        WsReduceOut* o = out + blockIdx.x;
+        o->m = tot.m;
+        o->S = tot.S;
+        o->Q = tot.Q;
+        const double lse = tot.m + log(tot.S);
+        o->lse = lse;
+        const double nn = (double)n_global;
+        o->ess_perc = (tot.S * tot.S) / (nn * tot.Q);
+        o->log_mean_w = lse - log(nn);
+        o->do_resample = (o->ess_perc < ess_perc_min) ? 1 : 0;
+    }
+}
+cudaError_t ws_launch_finalize_multi(const WsLse* partials, int n_partials, int k, int64_t n_global, double ess_perc_min, WsReduceOut* out,
+                                     cudaStream_t s) {
+    ws_finalize_multi_kernel<<<k, 256, 0, s>>>(partials, n_partials, n_global, ess_perc_min, out);
+    return cudaGetLastError();
 }
 
 cudaError_t ws_launch_finalize(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min,
@@ -1571,8 +1731,13 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) off += __shfl_xor_sync(0xffffffffu, off, d);
         off += cdf_offset;
+        if (tile_base + WS_SCAN_TILE <= n) {
 #pragma unroll
-        for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? off + C[k] : 0ull;
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] += off;
+        } else {
+#pragma unroll
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) C[k] = (item0 + k < n) ? off + C[k] : 0ull;
+        }
         ws_search_warp_tile<EXACT_FP, MN>(P, X, rbuf, lane, tile_base, C, off + pl, tile != 0,
                                           WS_INTERIOR_FAST && tile_base + WS_SCAN_TILE < n);
     }

@@ -2466,11 +2466,10 @@ extern "C" int ws_exec_spec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const
     c->spec_block = false;
     if (rc != WS_OK) return rc;
     const int grid = c->n_partials;
-    for (int32_t j = 0; j < K; ++j)
-        CK(c, ws_launch_finalize(c->d_ck_partials + (size_t)j * grid, grid, c->n_global, c->ess_perc_min, c->d_ck_red + j, c->stream));
+    CK(c, ws_launch_finalize_multi(c->d_ck_partials, grid, K, c->n_global, c->ess_perc_min, c->d_ck_red, c->stream));
     CK(c, cudaMemcpyAsync(c->h_ck_red, c->d_ck_red, sizeof(WsReduceOut) * (size_t)K, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    c->stats.kernel_launches += K;
+    c->stats.kernel_launches += 1;
     c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut) * K;
     int32_t first = K;
     for (int32_t j = 0; j < K; ++j)

@@ -168,6 +168,30 @@ inline bool ws_sl_matches(const Prog& P, const uint8_t (&map)[256]) {
     return true;
 }
 
+// A checkpointed window (speculative block) that is the signature's window repeated n_ckpt times, a checkpoint behind
+// every repetition: each repetition is matched on its own under the register numbering of the first.
+template <class Sig, class Prog>
+inline bool ws_sl_matches_repeated(const Prog& P, int max_reps) {
+    struct View {
+        int n_ops, n_loads, n_stores, n_expect;
+        const uint8_t* load_reg;
+        const uint8_t* store_reg;
+        const WsOp* ops;
+    };
+    const int r = P.n_ckpt;
+    if (r < 1 || r > max_reps || Sig::n_stores != 0 || P.n_stores != 0 || P.n_ops != r * Sig::n_ops) return false;
+    for (int j = 0; j < r; ++j)
+        if ((int)P.ckpt_pc[j] != (j + 1) * Sig::n_ops - 1) return false;
+    View v{Sig::n_ops, P.n_loads, 0, P.n_expect, P.load_reg, P.store_reg, P.ops};
+    uint8_t map[256];
+    ws_sl_canonical(v, map);
+    for (int j = 0; j < r; ++j) {
+        v.ops = P.ops + j * Sig::n_ops;
+        if (!ws_sl_matches<Sig>(v, map)) return false;
+    }
+    return true;
+}
+
 template <class Prog>
 inline int ws_sl_find(const Prog& P) {
     uint8_t map[256];
@@ -283,5 +307,11 @@ template <class Sig, int PP, int... I>
 __device__ __forceinline__ void ws_sl_run(double* __restrict__ R, double (&acc)[PP], const WsVmProgram& P, const WsSlConsts<Sig>& K,
                                           const bool replay, const uint64_t (&particle)[PP], std::integer_sequence<int, I...>) {
     (ws_sl_step<Sig, I, PP>(R, acc, P.ops[I], K.k[I], replay, P.rng, particle), ...);
+}
+// the same for one repetition of a repeated window: its micro-ops start at `ops`
+template <class Sig, int PP, int... I>
+__device__ __forceinline__ void ws_sl_run_at(double* __restrict__ R, double (&acc)[PP], const WsVmProgram& P, const WsOp* ops,
+                                             const WsSlConsts<Sig>& K, const uint64_t (&particle)[PP], std::integer_sequence<int, I...>) {
+    (ws_sl_step<Sig, I, PP>(R, acc, ops[I], K.k[I], false, P.rng, particle), ...);
 }
 #endif
