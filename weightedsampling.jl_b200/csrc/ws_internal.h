@@ -73,6 +73,7 @@ struct WsVmProgram {
     int32_t n_ckpt;
     uint8_t ckpt_pc[WS_VM_MAX_CKPT];
     WsLse* ckpt_partials;    // [n_ckpt][gridDim.x]
+    double* logw_out;        // checkpointed windows write the new log-weights here (the old array is the roll-back copy); nullptr: in place
     WsRng rng;
     WsOp ops[WS_VM_MAX_OPS];
 };

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_VM_MINB) ws_vm_kernel(const __
 #pragma unroll
             for (int j = 0; j < WS_VM_P; ++j) {
                 lw[j] = (CKPT ? lw_run[j] : (lmode == 1 ? lw_old[j] : lbase)) + acc[j];
-                if (live[j]) P.logw[(unsigned)idx[j]] = lw[j];
+                if (live[j]) (CKPT && P.logw_out != nullptr ? P.logw_out : P.logw)[(unsigned)idx[j]] = lw[j];
             }
             lse_push_many<WS_VM_P>(part, lw, live);
         }
@@ -584,9 +584,10 @@ __global__ void __launch_bounds__(WS_VM_BLOCK, WS_SLCK_MINB) ws_vm_sl_ckpt_kerne
                 lse_push_many<PP>(st[c], lw, live);
             }
         }
+        double* const lout = P.logw_out != nullptr ? P.logw_out : P.logw;
 #pragma unroll
         for (int j = 0; j < PP; ++j)
-            if (live[j]) P.logw[(unsigned)first + j * WS_VM_BLOCK] = lw[j];
+            if (live[j]) lout[(unsigned)first + j * WS_VM_BLOCK] = lw[j];
     }
 #pragma unroll
     for (int c = 0; c < NCK; ++c) {

@@ -787,6 +787,7 @@ static int flush_window(ws_ctx* c) {
         P.n_ckpt = (int32_t)c->spec_steps.size();
         for (int32_t j = 0; j < P.n_ckpt; ++j) P.ckpt_pc[j] = (uint8_t)c->spec_steps[j].ckpt_pc;
         P.ckpt_partials = c->d_ck_partials;
+        P.logw_out = c->d_logw_bak;   // ping-pong: the array the block started from stays intact (ws_exec_spec swaps the two)
     }
     const int64_t vm_tile = (int64_t)WS_VM_BLOCK * WS_VM_P;
     const int grid = (int)std::min<int64_t>(ws_vm_max_grid(P.n_regs, P.n_loads, P.n_ops, c->sm_count, P.n_ckpt), (c->n + vm_tile - 1) / vm_tile);
@@ -2415,7 +2416,6 @@ extern "C" int ws_exec_spec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const
     const int64_t s_depth = c->depth;
     const uint64_t s_stream = c->next_stream;
     const ws_stats s_stats = c->stats;
-    if (!s_uniform) CK(c, cudaMemcpyAsync(c->d_logw_bak, c->logw, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
     auto restore = [&](size_t tape_size, const Program::Mark& score_mark, int64_t depth, uint64_t stream) {
         reset_window(c);
         c->tape.resize(tape_size);
@@ -2465,6 +2465,7 @@ extern "C" int ws_exec_spec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const
     c->spec_flushing = false;
     c->spec_block = false;
     if (rc != WS_OK) return rc;
+    std::swap(c->logw, c->d_logw_bak);   // the pass wrote the other array: c->logw = after the block, d_logw_bak = before it
     const int grid = c->n_partials;
     CK(c, ws_launch_finalize_multi(c->d_ck_partials, grid, K, c->n_global, c->ess_perc_min, c->d_ck_red, c->stream));
     CK(c, cudaMemcpyAsync(c->h_ck_red, c->d_ck_red, sizeof(WsReduceOut) * (size_t)K, cudaMemcpyDeviceToHost, c->stream));
@@ -2495,23 +2496,25 @@ extern "C" int ws_exec_spec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const
     }
     // ---- step `first` fires: back to the state before the block, the first `first + 1` steps again as a plain window ----
     const ws_ctx::SpecStep st = c->spec_steps[first];
-    c->spec_steps.clear();
-    if (s_uniform) {
-        c->logw_uniform = true;
-        c->logw_base = s_base;
-    } else {
-        CK(c, cudaMemcpyAsync(c->logw, c->d_logw_bak, sizeof(double) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
-        c->logw_uniform = false;
-    }
+    std::swap(c->logw, c->d_logw_bak);   // back to the array the block started from
+    c->logw_uniform = s_uniform;
+    c->logw_base = s_base;
     c->logw_spec = false;
     c->partials_valid = false;
     c->red_valid = false;
     (void)s_partials; (void)s_red; (void)s_npart;
     c->resampled = s_resampled;
     restore(st.tape_size, st.score_mark, st.depth, st.stream_before);
+    // steps 0 .. first again, as the same kind of pass (its checkpoints are simply not looked at)
     saved.ops.resize((size_t)st.ckpt_pc + 1);
     c->win = saved;
-    TRY(flush_window(c));
+    c->spec_steps.resize((size_t)first + 1);
+    c->spec_flushing = true;
+    rc = flush_window(c);
+    c->spec_flushing = false;
+    c->spec_steps.clear();
+    if (rc != WS_OK) return rc;
+    std::swap(c->logw, c->d_logw_bak);
     c->stats.resamples_fired += first;   // the steps before it were evaluated and did not fire
     c->weights_changed = true;
     ws_resample_info info{};
