@@ -35,10 +35,16 @@ class env:
                 os.environ[k] = v
 
 
-def _run(ws, src, args, n, seed, ess=1.0, **envkv):
+def _run(ws, src, args, n, seed, ess=1.0, spec_blocks=None, **envkv):
     with env(**envkv):
         st = ws.SMCState(n, ess_perc_min=ess, seed=seed, device=0)
-    ws.run(ws.model(src)(*args), st)
+    old = ws.core.SPEC_BLOCKS
+    if spec_blocks is not None:      # loops of "observe; Resample; if resampled" element by element (False) or in blocks (True)
+        ws.core.SPEC_BLOCKS = spec_blocks
+    try:
+        ws.run(ws.model(src)(*args), st)
+    finally:
+        ws.core.SPEC_BLOCKS = old
     return st
 
 
@@ -70,8 +76,8 @@ CASES = [
 @pytest.mark.parametrize("ess", [0.5, 1.0])
 def test_straight_line_equals_interpreter(ws, name, src, mk, cols, n, ess):
     args = mk(np.random.default_rng(3))
-    a = _run(ws, src, args, n, seed=21, ess=ess)
-    b = _run(ws, src, args, n, seed=21, ess=ess, WSB200_VM="interp")
+    a = _run(ws, src, args, n, seed=21, ess=ess, spec_blocks=False)
+    b = _run(ws, src, args, n, seed=21, ess=ess, spec_blocks=False, WSB200_VM="interp")
     sa, sb = a.stats(), b.stats()
     assert sb["sl_passes"] == 0
     if name != "ssm1d_hist":   # (its window is not in the signature table: x{t+1} is a new plane and v is stored too)
@@ -174,8 +180,8 @@ def test_async_resample_equals_sync(ws, name, src, mk, cols, ess):
     the counters must equal the run in which the host waits for every decision (WSB200_ASYNC_RESAMPLE=0)."""
     args = mk(np.random.default_rng(5))
     n = 20_011
-    a = _run(ws, src, args, n, seed=33, ess=ess)
-    b = _run(ws, src, args, n, seed=33, ess=ess, WSB200_ASYNC_RESAMPLE="0")
+    a = _run(ws, src, args, n, seed=33, ess=ess, spec_blocks=False)
+    b = _run(ws, src, args, n, seed=33, ess=ess, spec_blocks=False, WSB200_ASYNC_RESAMPLE="0")
     for c in cols:
         np.testing.assert_array_equal(a[c], b[c], err_msg=f"{name}: column {c}")
     np.testing.assert_array_equal(a.weights, b.weights)
@@ -387,15 +393,9 @@ def test_speculative_blocks_equal_stepwise(ws, src, n, ess, vm):
     rng = np.random.default_rng(5)
     xs = rng.uniform(0, 10, 150)
     ys = 1 - 0.5 * xs + rng.standard_normal(150)
-    runs = []
-    try:
-        for spec in (False, True):
-            ws.core.SPEC_BLOCKS = spec
-            kv = {"WSB200_VM": "interp"} if vm == "interp" else {}
-            runs.append(_run(ws, LINREG if src == "linreg" else OBS_ONLY, (list(xs), list(ys)), n, seed=31, ess=ess, **kv))
-    finally:
-        ws.core.SPEC_BLOCKS = True
-    a, b = runs
+    kv = {"WSB200_VM": "interp"} if vm == "interp" else {}
+    a, b = [_run(ws, LINREG if src == "linreg" else OBS_ONLY, (list(xs), list(ys)), n, seed=31, ess=ess, spec_blocks=spec, **kv)
+            for spec in (False, True)]
     sa, sb = a.stats(), b.stats()
     assert sa["resamples_done"] == sb["resamples_done"] > 0
     assert sa["resamples_fired"] == sb["resamples_fired"] >= 150
