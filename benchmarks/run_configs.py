@@ -221,8 +221,9 @@ def c5():
                     emit(config=f"C5 resample N={n} payload={P}+1 planes {label} {scheme}", ms=ms, ess_perc=ess,
                          particles_per_sec=n / (ms * 1e-3), alg_bytes_per_particle=alg,
                          achieved_gbs=alg * n / (ms * 1e-3) / 1e9, hbm_frac=alg * n / (ms * 1e-3) / 1e9 / HBM)
+                    r = None            # (the transformer keeps its store alive)
+                    st.store.close()    # free the device memory before the next state is created (N = 1e9 fills the GPU)
                     del st
-                    torch.cuda.empty_cache() if False else None
 
 
 if __name__ == "__main__":

@@ -885,6 +885,7 @@ __device__ __forceinline__ int64_t ws_F(const WsScanParams& P, double C, double 
 #define WS_EXPAND_CHUNK 512    // output slots a warp stages in shared memory per round
 #define WS_DIRECT_MAX 8        // offspring a lane writes itself; larger families are filled by the warp
 #define WS_WARPS_PER_CTA (WS_SCAN_BLOCK / 32)
+#define WS_MN_MAX_WINDOWS 64   // multinomial: windows of WS_RBUF_SLOTS slots a warp works through before the tile counts as heavy
 #define WS_RBUF_SLOTS 512      // 8-byte words of a warp's window: slot uniforms of the tile's slot range (stratified), running spacing
                                // sums of two blocks of slots (multinomial), then the staged offspring
 
@@ -1351,51 +1352,68 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
         b_hi = __shfl_sync(0xffffffffu, b_hi, 1);
         const int k_lo = b_lo * WS_SCAN_TILE;
         const int k_hi = min((b_hi + 1) * WS_SCAN_TILE, ns);       // slots [k_lo, k_hi) are regenerated
-        coop = (k_hi - k_lo) <= WS_RBUF_SLOTS;
+        // the range is worked through in windows of WS_RBUF_SLOTS slots (two blocks): a tile with more offspring than one
+        // window — any tile of skewed weights — used to fall back to one block walk per PARTICLE (44 ms at N = 1e8)
+        coop = (k_hi - k_lo) <= WS_RBUF_SLOTS * WS_MN_MAX_WINDOWS;
         if (coop) {
             constexpr int PER = WS_RBUF_SLOTS / 32;                 // consecutive slots per lane
-            unsigned long long lane_sum = 0ull;
-            for (int j = 0; j < PER; j += 2) {                      // spacings into the window, lane totals in registers
-                const int k = k_lo + lane * PER + j;
-                unsigned long long e0 = 0ull, e1 = 0ull;
-                if (k < k_hi) {
-                    const ws_u32x4 r = ws_philox4x32_10((uint64_t)(k >> 1), P.stream, P.seed);
-                    e0 = ws_spacing_fx(r.x, r.y, P.mn_shift);
-                    if (k + 1 < k_hi) e1 = ws_spacing_fx(r.z, r.w, P.mn_shift);
-                }
-                rbuf[lane * PER + j] = e0;
-                rbuf[lane * PER + j + 1] = e1;
-                lane_sum += e0 + e1;
-            }
-            unsigned long long incl = lane_sum;
+            int cnt[WS_SCAN_ITEMS];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += t;
-            }
-            unsigned long long run = ws_mn_block_prefix(P, b_lo) + (incl - lane_sum);
-            for (int j = 0; j < PER; ++j) {                         // ... and in place into running sums
-                run += rbuf[lane * PER + j];
-                const int k = k_lo + lane * PER + j;
-                rbuf[lane * PER + j] = (k < k_hi) ? run : ~0ull;    // beyond the range: larger than any threshold
-            }
-            __syncwarp();
-            const int n_win = k_hi - k_lo;
-            auto count_le = [&](unsigned long long t) -> int {     // #{j < n_win : rbuf[j] <= t}
-                int lo = 0, hi = n_win;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (rbuf[mid] <= t) lo = mid + 1; else hi = mid;
+            for (int k = 0; k < WS_SCAN_ITEMS; ++k) cnt[k] = 0;
+            int cnt_p = 0;
+            unsigned long long carry = ws_mn_block_prefix(P, b_lo);
+            for (int k_win = k_lo; k_win < k_hi; k_win += WS_RBUF_SLOTS) {
+                const int n_win = min(WS_RBUF_SLOTS, k_hi - k_win);
+                unsigned long long lane_sum = 0ull;
+                for (int j = 0; j < PER; j += 2) {                      // spacings into the window, lane totals in registers
+                    const int k = k_win + lane * PER + j;
+                    unsigned long long e0 = 0ull, e1 = 0ull;
+                    if (k < k_hi) {
+                        const ws_u32x4 r = ws_philox4x32_10((uint64_t)(k >> 1), P.stream, P.seed);
+                        e0 = ws_spacing_fx(r.x, r.y, P.mn_shift);
+                        if (k + 1 < k_hi) e1 = ws_spacing_fx(r.z, r.w, P.mn_shift);
+                    }
+                    rbuf[lane * PER + j] = e0;
+                    rbuf[lane * PER + j + 1] = e1;
+                    lane_sum += e0 + e1;
                 }
-                return lo;
-            };
+                unsigned long long incl = lane_sum;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                unsigned long long run = carry + (incl - lane_sum);
+                for (int j = 0; j < PER; ++j) {                         // ... and in place into running sums
+                    run += rbuf[lane * PER + j];
+                    const int k = k_win + lane * PER + j;
+                    rbuf[lane * PER + j] = (k < k_hi) ? run : ~0ull;    // beyond the range: larger than any threshold
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+                __syncwarp();
+                const unsigned long long s_first = rbuf[0], s_last = rbuf[n_win - 1];
+                auto count_le = [&](unsigned long long t) -> int {     // #{j < n_win : rbuf[j] <= t}
+                    if (t < s_first) return 0;
+                    if (t >= s_last) return n_win;
+                    int lo = 0, hi = n_win;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (rbuf[mid] <= t) lo = mid + 1; else hi = mid;
+                    }
+                    return lo;
+                };
+#pragma unroll
+                for (int k = 0; k < WS_SCAN_ITEMS; ++k) cnt[k] += count_le(T[k]);
+                if (lane == 0 && has_prev) cnt_p += count_le(Tp);
+                __syncwarp();  // the window is refilled (and finally reused for the offspring below)
+            }
 #pragma unroll
             for (int k = 0; k < WS_SCAN_ITEMS; ++k) {
                 int fk;
                 if (item0 + k >= n) {
                     fk = -1;  // patched below
                 } else {
-                    fk = k_lo + count_le(T[k]);
+                    fk = k_lo + cnt[k];
                     if (item0 + k == n - 1 && P.last_rank) {
                         if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
                         fk = ns;
@@ -1403,8 +1421,7 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
                 }
                 f[k] = fk;
             }
-            if (lane == 0 && has_prev) fstart = k_lo + count_le(Tp);
-            __syncwarp();  // the window is reused for the offspring below
+            if (lane == 0 && has_prev) fstart = k_lo + cnt_p;
         }
     }
     if (!EXACT_FP && !MN && su.scheme == 0 && interior) {
