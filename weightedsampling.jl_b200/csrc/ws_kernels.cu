@@ -1061,12 +1061,9 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_CDF_MINB) ws_cdf_tiles_kerne
             for (int k = 0; k < WS_SCAN_ITEMS; ++k)
                 if (item0 + k < n) P.cdf_local[item0 + k] = thread_excl + q[k];
         }
-        if (threadIdx.x == 0) {
-            // the tile's aggregate, and its share of the aggregate of its group of WS_TILE_GROUP tiles: the offsets
-            // pass scans the group sums (n / 65 536 words) and the search adds the <= 31 tile words in front of its tile
-            P.tile_words[tile] = tile_agg;
-            atomicAdd(P.tile_words + n_tiles + tile / WS_TILE_GROUP, tile_agg);
-        }
+        // the tile's aggregate: the offsets pass sums them per group of WS_TILE_GROUP tiles and scans the group sums
+        // (n / 65 536 words); the search adds the <= 31 tile words in front of its tile to its group's prefix
+        if (threadIdx.x == 0) P.tile_words[tile] = tile_agg;
     }
 }
 
@@ -1122,9 +1119,22 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
 }
 // the CDF: the group sums behind the tile words (see ws_cdf_tiles_kernel), and the shard's total mass
 __global__ void __launch_bounds__(1024) ws_cdf_group_offsets_kernel(const __grid_constant__ WsScanParams P) {
+    if (threadIdx.x == 0 && P.heavy_count != nullptr) *P.heavy_count = 0u;   // (the search that follows counts its heavy tiles here)
     if (P.gate != 0 && P.red->do_resample == 0) return;
     const int n_tiles = (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE);
-    ws_scan_words_cta(P.tile_words + n_tiles, (n_tiles + WS_TILE_GROUP - 1) / WS_TILE_GROUP, P.total);
+    const int n_groups = (n_tiles + WS_TILE_GROUP - 1) / WS_TILE_GROUP;
+    unsigned long long* const grp = P.tile_words + n_tiles;
+    // group sums: a warp per group, a tile word per lane (coalesced 256-byte reads out of L2)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int g = warp; g < n_groups; g += 32) {
+        const int idx = g * WS_TILE_GROUP + lane;
+        unsigned long long v = idx < n_tiles ? P.tile_words[idx] : 0ull;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) grp[g] = v;
+    }
+    __syncthreads();
+    ws_scan_words_cta(grp, n_groups, P.total);
 }
 // exclusive prefix of CDF tile `ct` (all lanes of a warp call; every lane gets the result)
 __device__ __forceinline__ unsigned long long ws_tile_offset(const WsScanParams& P, const int n_tiles, const int ct, const int lane) {
@@ -1683,10 +1693,18 @@ __device__ __forceinline__ void ws_search_warp_tile(const WsScanParams& P, WsSea
 #ifndef WS_SEARCH_GRID
 #define WS_SEARCH_GRID 3   // CTAs per SM launched: persistent warps, each pipelining its tiles (next tile requested while this one is searched)
 #endif
+// A gated step that does not fire (ws_resample_async): the search-type kernels leave the identity in the ancestor
+// vector themselves (single-GPU states: slot i <- particle i) instead of a separate launch.
+__device__ __forceinline__ bool ws_gate_closed_identity(const WsScanParams& P) {
+    if (P.gate == 0 || P.red->do_resample != 0) return false;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += stride) P.ancestors[i] = (int32_t)i;
+    return true;
+}
 #define WS_SEARCH_SMEM_BYTES ((WS_WARPS_PER_CTA * WS_RBUF_SLOTS + WS_CDF_TILE) * 8)
 template <bool EXACT_FP, bool MN>
 __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kernel(const __grid_constant__ WsScanParams P) {
-    if (P.gate != 0 && P.red->do_resample == 0) return;
+    if (ws_gate_closed_identity(P)) return;
 
     // per-warp window: first the slot uniforms of the tile's slot range (Philox mode), then the staged offspring;
     // behind the windows, per warp, the tile-local CDF of the warp's NEXT tile, copied asynchronously while the current
@@ -1806,7 +1824,7 @@ __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_SEARCH_MINB) ws_search_kerne
 #endif
 template <bool EXACT_FP>
 __global__ void __launch_bounds__(WS_SCAN_BLOCK, WS_FUSED_MINB) ws_scan_search_kernel(const __grid_constant__ WsScanParams P) {
-    if (P.gate != 0 && P.red->do_resample == 0) return;
+    if (ws_gate_closed_identity(P)) return;
     __shared__ __align__(16) unsigned long long win_all[WS_WARPS_PER_CTA][WS_RBUF_SLOTS];
     __shared__ unsigned long long warp_tot[WS_WARPS_PER_CTA];
     __shared__ unsigned long long s_prefix;
@@ -1966,7 +1984,7 @@ __global__ void __maxnreg__(WS_CHAIN_MAXREG) ws_chain_kernel(const __grid_consta
     constexpr int TILE = BLOCK * WS_SCAN_ITEMS;   // particles per chain tile
     constexpr int WARPS = BLOCK / 32;
     constexpr int GRP_WARP = WARPS > 1 ? 1 : 0;    // the warp that looks back over the groups (warp 0: the tiles of its own group)
-    if (P.gate != 0 && P.red->do_resample == 0) return;
+    if (ws_gate_closed_identity(P)) return;
     extern __shared__ __align__(16) unsigned long long chain_smem[];
     __shared__ unsigned long long warp_tot[WARPS];
     __shared__ unsigned long long s_wexcl[WARPS];
@@ -2379,11 +2397,8 @@ cudaError_t ws_launch_cdf(const WsScanParams& P, cudaStream_t s) {
     const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
     int g1 = (int)(cdf_tiles < (int64_t)g_sm_count * WS_CDF_GRID ? cdf_tiles : (int64_t)g_sm_count * WS_CDF_GRID);
     if (g1 < 1) g1 = 1;
-    const int64_t groups = (cdf_tiles + WS_TILE_GROUP - 1) / WS_TILE_GROUP;
-    cudaError_t e = cudaMemsetAsync(P.tile_words + cdf_tiles, 0, sizeof(unsigned long long) * (size_t)groups, s);
-    if (e != cudaSuccess) return e;
     ws_cdf_tiles_kernel<<<g1, WS_SCAN_BLOCK, 0, s>>>(P);
-    e = cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     ws_cdf_group_offsets_kernel<<<1, 1024, 0, s>>>(P);
     return cudaGetLastError();
@@ -2441,7 +2456,8 @@ cudaError_t ws_launch_scan_search(const WsScanParams& P, int grid, cudaStream_t 
         // single-GPU state: one pass (the caller has zeroed the ticket / heavy-tile counters)
         const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
         const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
-        cudaError_t e;
+        cudaError_t e = cudaMemsetAsync(P.tile_counter, 0, sizeof(unsigned int) * 2, s);   // ticket, heavy-tile count
+        if (e != cudaSuccess) return e;
         if (g_scan_form == 2) {
             const int64_t ch_tiles = (P.n + g_chain_block * WS_SCAN_ITEMS - 1) / (g_chain_block * WS_SCAN_ITEMS);
             e = cudaMemsetAsync(P.tile_words, 0, sizeof(unsigned long long) * (size_t)(ch_tiles + 3 * ((ch_tiles + WS_CHAIN_GROUP - 1) / WS_CHAIN_GROUP)), s);

@@ -1730,8 +1730,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
         c->heavy_cap_n = n;
     }
     (void)n_tiles;
-    CK(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int) * 2, c->stream));
-    WsScanParams S;
+    WsScanParams S;   // (the ticket / heavy-tile counters are zeroed by the launch itself)
     memset(&S, 0, sizeof(S));
     S.logw = d_w;
     S.mode = mode;
@@ -1762,10 +1761,7 @@ static int run_scan_search(ws_ctx* c, const double* d_w, int mode, int scheme, i
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_scan_search(S, 0, c->stream));
     c->stats.kernel_launches += 3;  // cdf tiles, offsets, search, heavy expansion
-    if (gate) {  // a step that does not fire leaves the identity in the ancestor vector (ws_resample_async)
-        CK(c, ws_launch_identity_unless_fired(c->d_red, d_anc, n, grid_for(c, n, 256, 8), c->stream));
-        c->stats.kernel_launches++;
-    }
+    // (a gated step that does not fire: the search kernel itself leaves the identity in the ancestor vector)
     timed_end(c, te);
     return WS_OK;
 }
