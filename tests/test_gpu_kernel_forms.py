@@ -385,7 +385,7 @@ end
 '''
 
 
-@pytest.mark.parametrize("vm", ["sl", "interp"])   # register-resident block kernel / the interpreter's checkpoints
+@pytest.mark.parametrize("vm", ["sl", "interp", "interp16"])   # register-resident block kernel / the interpreter's checkpoints (8 or 16 steps per block)
 @pytest.mark.parametrize("src", ["linreg", "obs_only"])
 @pytest.mark.parametrize("n", [20_011, 300_000])
 @pytest.mark.parametrize("ess", [0.5, 0.9])
@@ -393,9 +393,14 @@ def test_speculative_blocks_equal_stepwise(ws, src, n, ess, vm):
     rng = np.random.default_rng(5)
     xs = rng.uniform(0, 10, 150)
     ys = 1 - 0.5 * xs + rng.standard_normal(150)
-    kv = {"WSB200_VM": "interp"} if vm == "interp" else {}
-    a, b = [_run(ws, LINREG if src == "linreg" else OBS_ONLY, (list(xs), list(ys)), n, seed=31, ess=ess, spec_blocks=spec, **kv)
-            for spec in (False, True)]
+    kv = {"WSB200_VM": "interp"} if vm != "sl" else {}
+    steps = ws.core.SPEC_BLOCK_STEPS
+    ws.core.SPEC_BLOCK_STEPS = 16 if vm == "interp16" else steps
+    try:
+        a, b = [_run(ws, LINREG if src == "linreg" else OBS_ONLY, (list(xs), list(ys)), n, seed=31, ess=ess, spec_blocks=spec, **kv)
+                for spec in (False, True)]
+    finally:
+        ws.core.SPEC_BLOCK_STEPS = steps
     sa, sb = a.stats(), b.stats()
     assert sa["resamples_done"] == sb["resamples_done"] > 0
     assert sa["resamples_fired"] == sb["resamples_fired"] >= 150
