@@ -155,7 +155,6 @@ cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s);  // F(C_m) 
 cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_t n_global, double ess_perc_min,
                                       WsReduceOut* out, cudaStream_t s, unsigned long long* ties = nullptr);
 cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s);
-cudaError_t ws_launch_identity_unless_fired(const WsReduceOut* red, int32_t* anc, int64_t n, int grid, cudaStream_t s);
 cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStream_t s);
 cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,
                                cudaStream_t s);

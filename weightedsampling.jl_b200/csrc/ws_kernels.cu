@@ -2510,16 +2510,6 @@ cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s) 
 // helpers
 // ------------------------------------------------------------------------------------------
 // ancestors of a Resample step that turned out not to fire: the identity (see ws_resample_async)
-__global__ void ws_identity_unless_fired_kernel(const WsReduceOut* __restrict__ red, int32_t* __restrict__ anc, int64_t n) {
-    if (red->do_resample != 0) return;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) anc[i] = (int32_t)i;
-}
-cudaError_t ws_launch_identity_unless_fired(const WsReduceOut* red, int32_t* anc, int64_t n, int grid, cudaStream_t s) {
-    ws_identity_unless_fired_kernel<<<grid, 256, 0, s>>>(red, anc, n);
-    return cudaGetLastError();
-}
-
 __global__ void ws_fill_kernel(double* __restrict__ dst, double v, int64_t n) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = v;
