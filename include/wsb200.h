@@ -229,6 +229,9 @@ typedef struct ws_cmd {
     const double* mat;
 } ws_cmd;
 int ws_exec(ws_ctx* ctx, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params);
+/* ws_exec once per element for n_elems consecutive loop elements (params[e][n_params]): the host's loop over a block of
+ * elements moved behind the boundary (one foreign call instead of n_elems). */
+int ws_exec_n(ws_ctx* ctx, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params, int32_t n_elems);
 /* The same list run for up to n_steps consecutive loop elements (params[step][n_params]) as ONE device pass, for
  * bodies of the form "weighting statements, Resample(), if resampled ... end" (examples/linear_regression.jl:20-26:
  * the reference's Resample.apply!, src/transformers.jl:474-498, needs the ESS after every observation, i.e. one pass

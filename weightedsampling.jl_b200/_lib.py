@@ -139,6 +139,7 @@ SIGNATURES = {
     "ws_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),
     "ws_resample_async": (C.c_int, [_ctx]),
     "ws_exec": (C.c_int, [_ctx, C.POINTER(ws_cmd), C.c_int32, C.POINTER(C.c_double), C.c_int32]),
+    "ws_exec_n": (C.c_int, [_ctx, C.POINTER(ws_cmd), C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_int32]),
     "ws_exec_spec": (C.c_int, [_ctx, C.POINTER(ws_cmd), C.c_int32, C.POINTER(C.c_double), C.c_int32, C.c_int32,
                                C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "ws_last_resample": (C.c_int, [_ctx, C.POINTER(ws_resample_info)]),

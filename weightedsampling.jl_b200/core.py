@@ -914,6 +914,21 @@ class _LoopTemplate:
         self.store._call("ws_exec", self.arr, self.n, self._params, self.n_params)
         return True
 
+    def run_many(self, coll, i, limit=512):
+        """elements coll[i], coll[i + 1], ... (up to `limit`, up to the first one of another shape) with one C call
+        -> number of elements done"""
+        flat, j, n = [], i, len(coll)
+        while j < n and j - i < limit:
+            vals = self.flatten(coll[j])
+            if vals is None:
+                break
+            flat.extend(vals)
+            j += 1
+        if j > i:
+            buf = (C.c_double * max(1, len(flat)))(*flat)
+            self.store._call("ws_exec_n", self.arr, self.n, buf, self.n_params, j - i)
+        return j - i
+
     def run_block(self, xs):
         """up to len(xs) consecutive elements as one speculative block -> (elements done, the last of them resampled);
         None if an element does not have the template's shape"""
@@ -982,8 +997,12 @@ class Loop(ParticleTransformer):
                     self.bodyfn(coll[i + done - 1]).steps[-1].body.apply(state)
                 i += done
                 continue
-            if tmpl is False or not tmpl.run(x):
-                self.bodyfn(x).apply(state)
+            if tmpl is not False:
+                done = tmpl.run_many(coll, i)
+                if done > 0:
+                    i += done
+                    continue
+            self.bodyfn(x).apply(state)
             i += 1
 
     def score(self, state, ctx):

@@ -2356,6 +2356,13 @@ extern "C" int ws_exec(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const doub
     return WS_OK;
 }
 
+// the list once per element, for n_elems consecutive elements (params[e][n_params]): one call per block of loop elements
+extern "C" int ws_exec_n(ws_ctx* c, const ws_cmd* cmds, int32_t n_cmds, const double* params, int32_t n_params, int32_t n_elems) {
+    if (!c || n_elems < 0 || (n_params > 0 && n_elems > 0 && !params)) return WS_EINVAL;
+    for (int32_t e = 0; e < n_elems; ++e) TRY(ws_exec(c, cmds, n_cmds, params + (size_t)e * (size_t)n_params, n_params));
+    return WS_OK;
+}
+
 // ---- speculative blocks of (weighting statements, Resample) steps --------------------------------------------------
 // A model that only observes between resampling events (examples/linear_regression.jl: y => Normal(alpha + beta x_i, 1)
 // and `if resampled` moves, 12 events in 10 000 steps) pays, statement by statement, one pass over the particles and
