@@ -2225,6 +2225,8 @@ __global__ void __launch_bounds__(256) ws_resample_small_kernel(const __grid_con
     __shared__ unsigned long long warp_tot[8];
     __shared__ unsigned long long s_carry;
     __shared__ int s_fire;
+    __shared__ int32_t Fs[WS_SMALL_N];   // F(C_m) of every particle: the expansion searches it 12 steps per slot
+    (void)Ftab;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (do_finalize) {
         WsLse part;
@@ -2300,7 +2302,7 @@ __global__ void __launch_bounds__(256) ws_resample_small_kernel(const __grid_con
                     if (fk < ns) atomicAdd(P.n_clamped, (unsigned long long)(ns - fk));
                     fk = ns;   // leftover slots go to the last particle
                 }
-                Ftab[i] = fk;
+                Fs[i] = fk;
             }
         }
         __syncthreads();
@@ -2312,7 +2314,7 @@ __global__ void __launch_bounds__(256) ws_resample_small_kernel(const __grid_con
         int lo = 0, hi = n - 1;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            if (Ftab[mid] > j) hi = mid; else lo = mid + 1;
+            if (Fs[mid] > j) hi = mid; else lo = mid + 1;
         }
         P.ancestors[j] = lo;
     }
