@@ -388,7 +388,7 @@ end
 @pytest.mark.parametrize("vm", ["sl", "interp", "interp16"])   # register-resident block kernel / the interpreter's checkpoints (8 or 16 steps per block)
 @pytest.mark.parametrize("src", ["linreg", "obs_only"])
 @pytest.mark.parametrize("n", [20_011, 300_000])
-@pytest.mark.parametrize("ess", [0.5, 0.9])
+@pytest.mark.parametrize("ess", [0.5, 0.9, 1.0])     # 1.0: every step resamples, the blocks shrink to single steps
 def test_speculative_blocks_equal_stepwise(ws, src, n, ess, vm):
     rng = np.random.default_rng(5)
     xs = rng.uniform(0, 10, 150)
@@ -405,7 +405,10 @@ def test_speculative_blocks_equal_stepwise(ws, src, n, ess, vm):
     assert sa["resamples_done"] == sb["resamples_done"] > 0
     assert sa["resamples_fired"] == sb["resamples_fired"] >= 150
     assert sa["moves_run"] == sb["moves_run"]
-    assert sb["fused_passes"] < sa["fused_passes"], (sa["fused_passes"], sb["fused_passes"])
+    if ess < 1.0:
+        assert sb["fused_passes"] < sa["fused_passes"], (sa["fused_passes"], sb["fused_passes"])
+    else:
+        assert sb["fused_passes"] < sa["fused_passes"] + 16, (sa["fused_passes"], sb["fused_passes"])   # only the first blocks speculate
     if vm == "sl":
         assert sb["sl_passes"] > 0
     # same association of the log-weight sums and the same Philox stream numbering: only the grouping of the

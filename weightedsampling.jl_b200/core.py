@@ -976,6 +976,7 @@ class Loop(ParticleTransformer):
         self.bodyfn(coll[0]).apply(state)           # the first element runs as written (it may create the columns)
         tmpl = None
         i, n = 1, len(coll)
+        k_cur = SPEC_BLOCK_STEPS        # steps per speculative block: halved when blocks end early, doubled when they run through
         while i < n:
             x = coll[i]
             if tmpl is None:
@@ -984,9 +985,18 @@ class Loop(ParticleTransformer):
                 except _NoTemplate:
                     tmpl = False
             if tmpl is not False and tmpl.spec:
-                # blocks of steps in one pass; a step that resamples ends its block and runs its `if resampled` body
+                # blocks of steps in one pass; a step that resamples ends its block and runs its `if resampled` body.
+                # A block that ends early has computed the steps behind the firing one for nothing, so where steps
+                # resample often (a high threshold, the first observations of a diffuse prior) the blocks shrink, down
+                # to plain element-by-element execution, and grow again once steps stop firing.
+                if k_cur <= 1:
+                    self.bodyfn(x).apply(state)
+                    i += 1
+                    if not state.resampled:
+                        k_cur = 2
+                    continue
                 try:
-                    r = tmpl.run_block([coll[k] for k in range(i, min(n, i + SPEC_BLOCK_STEPS))])
+                    r = tmpl.run_block([coll[k] for k in range(i, min(n, i + k_cur))])
                 except UnsupportedModelError:
                     r = None
                 if r is None:
@@ -995,6 +1005,10 @@ class Loop(ParticleTransformer):
                 done, fired = r
                 if fired:
                     self.bodyfn(coll[i + done - 1]).steps[-1].body.apply(state)
+                    if done <= k_cur // 2:
+                        k_cur = max(1, k_cur // 2)
+                else:
+                    k_cur = min(SPEC_BLOCK_STEPS, k_cur * 2)
                 i += done
                 continue
             if tmpl is not False:
