@@ -3031,11 +3031,11 @@ static int for_each_tape_segment(ws_ctx* c, int64_t target_depth, const std::vec
                     if (r == t) dep = true;
             if (!dep) continue;
         }
-        Program snapshot = seg;
+        const Program::Mark mk = seg.mark();   // (sizes only: copying the segment per entry made a move's host side quadratic)
         e.lower(seg);
         if (!seg.error.empty()) return fail(c, WS_EINVAL, "%s", seg.error.c_str());
         if (seg.overflow) {
-            seg = snapshot;
+            seg.rollback(mk);
             TRY(launch(seg));
             seg = fresh();
             e.lower(seg);
