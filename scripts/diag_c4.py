@@ -1,6 +1,6 @@
 """C4 synthetic (J schools, wide score tape): time per config; env WSB200_SEG_REGS tunes the segment size."""
 import sys, time, os
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
 import numpy as np, wsb200 as ws, models
 J = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
