@@ -1239,6 +1239,7 @@ __device__ __forceinline__ unsigned long long ws_cdf_offset(const WsScanParams& 
 template <bool EXACT_FP>
 __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (P.gate != 0 && P.red->do_resample == 0) return;   // queued before the decision was read (sharded steps): nothing to bound
     const int ns = (int)P.n_slots;
     const double inv_n = 1.0 / (double)ns;
     SlotUniform su;

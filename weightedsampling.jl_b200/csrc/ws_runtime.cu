@@ -184,6 +184,7 @@ struct ws_ctx {
     int spec_pending = 0;
     bool logw_spec = false;
     bool async_resample = true;     // env WSB200_ASYNC_RESAMPLE=0: ws_resample_async behaves like ws_resample
+    bool merged_decision_wait = true;  // sharded steps: the decision is read with the slot bounds (env WSB200_MERGED_WAIT=0: two waits)
     bool small_resample = true;     // env WSB200_SMALL_RESAMPLE=0: small particle sets use the multi-kernel resampler too
     ws_resample_info last_info{};   // outcome of the most recent Resample step (ws_last_resample)
     bool last_info_pending = false; // ... which is the newest unresolved record
@@ -554,6 +555,8 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
     {
         const char* v = getenv("WSB200_ASYNC_RESAMPLE");
         c->async_resample = !(v != nullptr && strcmp(v, "0") == 0);
+        v = getenv("WSB200_MERGED_WAIT");
+        c->merged_decision_wait = !(v != nullptr && strcmp(v, "0") == 0);
         v = getenv("WSB200_SMALL_RESAMPLE");
         c->small_resample = !(v != nullptr && strcmp(v, "0") == 0);
     }
@@ -1401,7 +1404,7 @@ static int resolve_spec(ws_ctx* c) {
 }
 
 // Make d_red / h_red describe the current log-weights (m, S, Q, lse, ESS%, decision).
-static int ensure_reduced(ws_ctx* c, bool for_resample = false) {
+static int ensure_reduced(ws_ctx* c, bool for_resample = false, bool wait = true) {
     TRY(flush_window(c));
     TRY(resolve_spec(c));
     if (c->red_valid) return WS_OK;
@@ -1429,8 +1432,9 @@ static int ensure_reduced(ws_ctx* c, bool for_resample = false) {
         timed_end(c, te);
     }
     CK(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut);
+    if (!wait) return WS_OK;   // the caller's next wait on the stream delivers *h_red (it then sets red_valid)
+    CK(c, cudaStreamSynchronize(c->stream));
     c->red_valid = true;
     return WS_OK;
 }
@@ -1901,7 +1905,10 @@ static int resolve_peer_planes(ws_ctx* c, const std::vector<int64_t>& all, size_
     return WS_OK;
 }
 
-static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id) {
+// `fired` != nullptr: the decision of this step has not been read yet (ensure_reduced(.., wait = false)): the kernels in
+// front of the one host wait this function needs anyway (for the slot bounds) run gated on the device flag, the wait
+// delivers the decision together with the bounds, and a step that does not fire returns there (*fired = 0).
+static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, int* fired = nullptr) {
     const int R = c->nranks, r = c->rank;
     auto t_now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t0 = t_now();
@@ -1912,6 +1919,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id) {
     S.mode = 0;
     S.scheme = c->resampler;
     S.red = c->d_red;
+    S.gate = fired != nullptr ? 1 : 0;
     S.n = c->n;
     S.n_slots = c->n_global;
     S.seed = c->seed;
@@ -1961,6 +1969,14 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id) {
     CK(c, cudaMemcpyAsync(xall.data(), c->d_xmsg, sizeof(int64_t) * xw * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     c->stats.d2h_bytes += (int64_t)(sizeof(int64_t) * xw * (size_t)R);
+    if (fired != nullptr) {
+        c->red_valid = true;              // *h_red arrived with the same wait
+        *fired = c->h_red->do_resample ? 1 : 0;
+        if (!*fired) return WS_OK;        // (the gated kernels did nothing; every rank reads the same decision)
+        c->anc_live.clear();              // the rest of begin_resample_event for a sharded state
+        c->anc_live.push_back({c->epoch + 1, c->d_anc});
+        S.gate = 0;
+    }
     std::vector<int32_t> bnd(2 * R);
     for (int q = 0; q < R; ++q) memcpy(&bnd[2 * q], &xall[xw * (size_t)q], 2 * sizeof(int32_t));
     c->phase_ms[0] += t_now() - t0;
@@ -2168,6 +2184,39 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
     }
     if (c->resampler == WS_RESAMPLER_MULTINOMIAL && c->nranks > 1 && c->d_replay_u != nullptr)
         return fail(c, WS_EUNSUPPORTED, "multinomial resampling of a sharded state with replayed uniforms (Philox draws are supported)");
+    if (c->nranks > 1 && c->d_replay_u == nullptr && c->merged_decision_wait) {
+        // Sharded step: the decision travels with the slot bounds (one host wait per step instead of two).
+        TRY(ensure_reduced(c, true, /*wait=*/false));
+        c->stats.resamples_fired++;
+        const uint64_t step_stream = c->next_stream++;
+        int fired = 0;
+        if (c->red_valid) {   // (nothing was weighted on the device since the last reduction: *h_red is current)
+            fired = c->h_red->do_resample ? 1 : 0;
+            if (fired) {
+                TRY(begin_resample_event(c));
+                TRY(resample_sharded(c, nullptr, step_stream));
+            }
+        } else {
+            TRY(materialize_planes(c));   // what begin_resample_event does first on a sharded state (harmless if the step does not fire)
+            TRY(resample_sharded(c, nullptr, step_stream, &fired));
+        }
+        const WsReduceOut r = *c->h_red;
+        if (fired) {
+            c->logw_uniform = true;
+            c->logw_base = r.log_mean_w;
+            c->partials_valid = false;
+            c->red_valid = false;
+            c->resampled = true;
+            c->stats.resamples_done++;
+        } else {
+            c->resampled = false;
+        }
+        c->weights_changed = false;
+        c->last_info = ws_resample_info{1, fired, r.ess_perc, r.log_mean_w, -1};
+        c->last_info_pending = false;
+        if (info) *info = c->last_info;
+        return WS_OK;
+    }
     TRY(ensure_reduced(c, true));
     c->stats.resamples_fired++;
     const WsReduceOut r = *c->h_red;
