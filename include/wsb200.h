@@ -412,6 +412,10 @@ int ws_get_migrated(ws_ctx* ctx, int64_t* out);
 /* offspring this rank has written DIRECTLY into other ranks' planes over NVLink (peer mappings; the exchange falls back to
  * stage + ncclSend / ncclRecv with WSB200_EXCHANGE=nccl or when ranks share a process) */
 int ws_get_pushed(ws_ctx* ctx, int64_t* out);
+/* small exchanges of sharded steps ((m, S, Q) triples, masses, slot bounds, barriers) that the kernels made themselves by
+ * storing into the other ranks' mailboxes over NVLink instead of going through an NCCL collective (0: ranks share a
+ * process, no peer mappings, or WSB200_MAILBOX=0) */
+int ws_get_mailbox_exchanges(ws_ctx* ctx, int64_t* out);
 /* the Philox stream id the next random statement / resample will use, and the key (tests reproduce draws) */
 int ws_next_philox_stream(ws_ctx* ctx, uint64_t* stream_out, uint64_t* seed_out);
 /* raw cudaStream_t of the context (as void*), so a host can bracket calls with its own events */

@@ -38,9 +38,9 @@ def _obs(T):
     return [np.array([t, 0.0]) + 0.7 * rng.standard_normal(2) for t in range(T)]
 
 
-def _worker(rank, world, port, n, T, ess, q, resampler="stratified"):
+def _worker(rank, world, port, n, T, ess, q, resampler="stratified", mailbox="1"):
     sys.path.insert(0, ROOT)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WSB200_MAILBOX=mailbox)
     import torch.distributed as dist
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import wsb200 as ws
@@ -48,16 +48,20 @@ def _worker(rank, world, port, n, T, ess, q, resampler="stratified"):
     ws.run(ws.model(MODEL)(_obs(T)), st)
     le = ws.log_evidence(st)
     mx = ws.E(lambda x: x[0], st)
-    mig = ctypes.c_int64()
+    mig, mbx = ctypes.c_int64(), ctypes.c_int64()
     st.store._call("ws_get_migrated", ctypes.byref(mig))
-    q.put((rank, st["x"], st["v"], st.weights, le, mx, st.stats()["resamples_done"], mig.value))
+    st.store._call("ws_get_mailbox_exchanges", ctypes.byref(mbx))
+    q.put((rank, st["x"], st["v"], st.weights, le, mx, st.stats()["resamples_done"], mig.value, mbx.value))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,ess,resampler", [(2, 1.0, "stratified"), (2, 0.5, "stratified"), (4, 1.0, "stratified"),
-                                                 (2, 1.0, "systematic"), (2, 1.0, "multinomial"), (4, 0.5, "multinomial")])
-def test_sharded_equals_single_gpu(world, ess, resampler):
+@pytest.mark.parametrize("world,ess,resampler,mailbox", [(2, 1.0, "stratified", "1"), (2, 0.5, "stratified", "1"), (4, 1.0, "stratified", "1"),
+                                                         (2, 1.0, "systematic", "1"), (2, 1.0, "multinomial", "1"), (4, 0.5, "multinomial", "1"),
+                                                         (2, 0.5, "stratified", "0"), (4, 1.0, "systematic", "0")])
+def test_sharded_equals_single_gpu(world, ess, resampler, mailbox):
+    """mailbox = "1": the step's small exchanges are made by the kernels themselves through peer-mapped mailboxes
+    (csrc/ws_mailbox.cuh); "0": the NCCL collectives they replace.  Both must reproduce the single-GPU run."""
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -69,8 +73,8 @@ def test_sharded_equals_single_gpu(world, ess, resampler):
     le1, mx1 = ws.log_evidence(single), ws.E(lambda x: x[0], single)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29741 + int(ess * 10) + 20 * ["stratified", "systematic", "multinomial"].index(resampler) + world
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, T, ess, q, resampler)) for r in range(world)]
+    port = 29741 + int(ess * 10) + 20 * ["stratified", "systematic", "multinomial"].index(resampler) + world + 100 * (mailbox == "0")
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, T, ess, q, resampler, mailbox)) for r in range(world)]
     for p in procs:
         p.start()
     out = sorted((q.get(timeout=300) for _ in range(world)), key=lambda t: t[0])
@@ -84,7 +88,10 @@ def test_sharded_equals_single_gpu(world, ess, resampler):
     # same Philox counters (global indices) and an order-independent fixed-point CDF: the sharded run is
     # the single-GPU run, up to the rounding of the (m, S) reduction
     bad = (np.abs(xs - x1) > 1e-9 * (1 + np.abs(x1))).any(axis=1) | (np.abs(vs - v1) > 1e-9 * (1 + np.abs(v1))).any(axis=1)
-    print(f"world={world} ess={ess} {resampler}: {int(bad.sum())} of {n} particles differ; migrated {[o[7] for o in out]}")
+    print(f"world={world} ess={ess} {resampler} mailbox={mailbox}: {int(bad.sum())} of {n} particles differ; migrated {[o[7] for o in out]}; "
+          f"mailbox exchanges {[o[8] for o in out]}")
+    # every Resample statement: one exchange for the decision; a step that fires: two more (+ the barrier behind pushed offspring)
+    assert all((o[8] >= T + 2 * o[6]) if mailbox == "1" else (o[8] == 0) for o in out)
     assert bad.sum() <= 5
     np.testing.assert_allclose(wsum, w1, rtol=1e-9, atol=1e-9)
     for o in out:

@@ -179,6 +179,7 @@ SIGNATURES = {
     "ws_next_philox_stream": (C.c_int, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "ws_get_migrated": (C.c_int, [_ctx, _i64p]),
     "ws_get_pushed": (C.c_int, [_ctx, _i64p]),
+    "ws_get_mailbox_exchanges": (C.c_int, [_ctx, _i64p]),
     "ws_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
 }
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "ws_vm.cuh"
+#include "ws_mailbox.cuh"
 
 #ifndef WS_VM_BLOCK
 #define WS_VM_BLOCK 128       // threads per CTA of the fused elementwise pass
@@ -155,6 +156,13 @@ cudaError_t ws_launch_bounds(const WsScanParams& P, cudaStream_t s);  // first /
 cudaError_t ws_launch_search(const WsScanParams& P, cudaStream_t s);  // F(C_m) + expansion (+ heavy tiles)
 cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_t n_global, double ess_perc_min,
                                       WsReduceOut* out, cudaStream_t s, unsigned long long* ties = nullptr);
+// mailbox forms (ws_mailbox.cuh): the small exchanges of a sharded step done by the kernels themselves over peer memory
+cudaError_t ws_launch_finalize_mbox(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min, WsReduceOut* out,
+                                    double* all_msq, unsigned long long* ties, const WsMailbox& M, cudaStream_t s);
+cudaError_t ws_launch_cdf_tiles(const WsScanParams& P, cudaStream_t s);
+cudaError_t ws_launch_offsets_bounds_mbox(const WsScanParams& P, const WsMailbox& M, unsigned long long* all_tot, const unsigned long long* xmine,
+                                          int xw, unsigned long long* xall, cudaStream_t s);
+cudaError_t ws_launch_barrier_mbox(const WsMailbox& M, cudaStream_t s);
 cudaError_t ws_launch_gather(const WsGatherParams& P, int grid, cudaStream_t s);
 cudaError_t ws_launch_fill(double* dst, double v, int64_t n, int grid, cudaStream_t s);
 cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, double* w, int64_t n, int grid,

@@ -797,6 +797,71 @@ cudaError_t ws_launch_finalize_global(const double* all_msq, int n_ranks, int64_
     return cudaGetLastError();
 }
 
+// Sharded state, mailbox form (ws_mailbox.cuh): the shard's partials are reduced, the (m, S, Q) triple is stored into
+// every rank's mailbox, and as soon as all R triples are here they are combined in rank order — ws_finalize_kernel,
+// ncclAllGather and ws_finalize_global_kernel in one launch, same operations in the same order (bit-identical result).
+__global__ void __launch_bounds__(WS_MBOX_THREADS) ws_finalize_mbox_kernel(const WsLse* __restrict__ partials, int n_partials, int64_t n_global,
+                                                                           double ess_perc_min, WsReduceOut* __restrict__ out,
+                                                                           double* __restrict__ all_msq, unsigned long long* ties,
+                                                                           const __grid_constant__ WsMailbox M) {
+    __shared__ WsLse warp_scratch[WS_MBOX_THREADS / 32];
+    __shared__ unsigned long long mine[3];
+    __shared__ unsigned long long all[3 * WS_MBOX_MAX_RANKS];
+    WsLse part;
+    part.m = -INFINITY;
+    part.S = 0.0;
+    part.Q = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += WS_MBOX_THREADS) part = lse_combine(part, partials[i]);
+    const WsLse loc = lse_block_reduce<WS_MBOX_THREADS>(part, warp_scratch);
+    if (threadIdx.x == 0) {
+        mine[0] = (unsigned long long)__double_as_longlong(loc.m);
+        mine[1] = (unsigned long long)__double_as_longlong(loc.S);
+        mine[2] = (unsigned long long)__double_as_longlong(loc.Q);
+    }
+    __syncthreads();
+    ws_mbox_allgather(M, M.seq, mine, 3, all);
+    if (threadIdx.x != 0) return;
+    WsLse tot;
+    tot.m = -INFINITY;
+    tot.S = 0.0;
+    tot.Q = 0.0;
+    for (int r = 0; r < M.nranks; ++r) {
+        WsLse v;
+        v.m = __longlong_as_double((long long)all[3 * r + 0]);
+        v.S = __longlong_as_double((long long)all[3 * r + 1]);
+        v.Q = __longlong_as_double((long long)all[3 * r + 2]);
+        all_msq[3 * r + 0] = v.m;
+        all_msq[3 * r + 1] = v.S;
+        all_msq[3 * r + 2] = v.Q;
+        tot = lse_combine(tot, v);
+    }
+    out->m = tot.m;
+    out->S = tot.S;
+    out->Q = tot.Q;
+    const double lse = tot.m + log(tot.S);
+    out->lse = lse;
+    const double nn = (double)n_global;
+    out->ess_perc = (tot.S * tot.S) / (nn * tot.Q);
+    out->log_mean_w = lse - log(nn);
+    out->do_resample = (out->ess_perc < ess_perc_min) ? 1 : 0;
+    ws_count_ess_tie(out->ess_perc, ess_perc_min, ties);
+}
+cudaError_t ws_launch_finalize_mbox(const WsLse* partials, int n_partials, int64_t n_global, double ess_perc_min, WsReduceOut* out,
+                                    double* all_msq, unsigned long long* ties, const WsMailbox& M, cudaStream_t s) {
+    ws_finalize_mbox_kernel<<<1, WS_MBOX_THREADS, 0, s>>>(partials, n_partials, n_global, ess_perc_min, out, all_msq, ties, M);
+    return cudaGetLastError();
+}
+
+// The barrier behind the offspring pushed into the peers' planes by earlier kernels of the stream.
+__global__ void __launch_bounds__(64) ws_barrier_mbox_kernel(const __grid_constant__ WsMailbox M) {
+    __shared__ unsigned long long got[WS_MBOX_MAX_RANKS];
+    ws_mbox_barrier(M, M.seq, got);
+}
+cudaError_t ws_launch_barrier_mbox(const WsMailbox& M, cudaStream_t s) {
+    ws_barrier_mbox_kernel<<<1, 64, 0, s>>>(M);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------
 // CDF scan fused with the ancestor search
 // ------------------------------------------------------------------------------------------
@@ -1118,7 +1183,7 @@ __global__ void __launch_bounds__(1024) ws_cdf_offsets_kernel(const __grid_const
     ws_scan_words_cta(P.tile_words, (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE), P.total);
 }
 // the CDF: the group sums behind the tile words (see ws_cdf_tiles_kernel), and the shard's total mass
-__global__ void __launch_bounds__(1024) ws_cdf_group_offsets_kernel(const __grid_constant__ WsScanParams P) {
+__device__ __forceinline__ void ws_cdf_group_offsets_body(const WsScanParams& P) {   // one CTA of 1024 threads
     if (threadIdx.x == 0 && P.heavy_count != nullptr) *P.heavy_count = 0u;   // (the search that follows counts its heavy tiles here)
     if (P.gate != 0 && P.red->do_resample == 0) return;
     const int n_tiles = (int)((P.n + WS_CDF_TILE - 1) / WS_CDF_TILE);
@@ -1136,6 +1201,7 @@ __global__ void __launch_bounds__(1024) ws_cdf_group_offsets_kernel(const __grid
     __syncthreads();
     ws_scan_words_cta(grp, n_groups, P.total);
 }
+__global__ void __launch_bounds__(1024) ws_cdf_group_offsets_kernel(const __grid_constant__ WsScanParams P) { ws_cdf_group_offsets_body(P); }
 // exclusive prefix of CDF tile `ct` (all lanes of a warp call; every lane gets the result)
 __device__ __forceinline__ unsigned long long ws_tile_offset(const WsScanParams& P, const int n_tiles, const int ct, const int lane) {
     const int g = ct / WS_TILE_GROUP, idx = g * WS_TILE_GROUP + lane;
@@ -1237,9 +1303,7 @@ __device__ __forceinline__ unsigned long long ws_cdf_offset(const WsScanParams& 
 
 // first / end global slot produced by this rank: F at the rank's left and right CDF edge
 template <bool EXACT_FP>
-__global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (P.gate != 0 && P.red->do_resample == 0) return;   // queued before the decision was read (sharded steps): nothing to bound
+__device__ __forceinline__ void ws_bounds_body(const WsScanParams& P) {   // one thread
     const int ns = (int)P.n_slots;
     const double inv_n = 1.0 / (double)ns;
     SlotUniform su;
@@ -1278,6 +1342,27 @@ __global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
     if (P.last_rank) fe = ns;
     P.bounds[0] = fs;
     P.bounds[1] = fe;
+}
+template <bool EXACT_FP>
+__global__ void ws_bounds_kernel(const __grid_constant__ WsScanParams P) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (P.gate != 0 && P.red->do_resample == 0) return;   // queued before the decision was read (sharded steps): nothing to bound
+    ws_bounds_body<EXACT_FP>(P);
+}
+// Mailbox form of a sharded step's middle part (ws_mailbox.cuh), one launch instead of two kernels and two collectives:
+// group offsets of the tile CDF and the shard's mass -> the masses of all ranks (exchange 1) -> this rank's slot bounds
+// -> everybody's bounds + plane addresses, the exchange plan's input (exchange 2; P.bounds is word 0 of `xmine`).
+template <bool EXACT_FP>
+__global__ void __launch_bounds__(1024) ws_offsets_bounds_mbox_kernel(const __grid_constant__ WsScanParams P, const __grid_constant__ WsMailbox M,
+                                                                      unsigned long long* all_tot, const unsigned long long* xmine, int xw,
+                                                                      unsigned long long* xall) {
+    ws_cdf_group_offsets_body(P);
+    if (P.gate != 0 && P.red->do_resample == 0) return;   // (every rank reads the same decision: nobody sends, nobody waits)
+    __syncthreads();   // *P.total
+    ws_mbox_allgather(M, M.seq, P.total, 1, all_tot);
+    if (threadIdx.x == 0) ws_bounds_body<EXACT_FP>(P);
+    __syncthreads();
+    ws_mbox_allgather(M, M.seq + 1u, xmine, xw, xall);
 }
 
 // What every warp of a search needs besides the CDF: the slot-uniform provider and the slot grid.
@@ -2411,6 +2496,21 @@ cudaError_t ws_launch_bounds(const WsScanParams& P, cudaStream_t s) {
     const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
     if (exact_fp) ws_bounds_kernel<true><<<1, 32, 0, s>>>(P);
     else ws_bounds_kernel<false><<<1, 32, 0, s>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t ws_launch_cdf_tiles(const WsScanParams& P, cudaStream_t s) {   // the tile CDF alone (its offsets: ws_launch_offsets_bounds_mbox)
+    const int64_t cdf_tiles = (P.n + WS_CDF_TILE - 1) / WS_CDF_TILE;
+    int g1 = (int)(cdf_tiles < (int64_t)g_sm_count * WS_CDF_GRID ? cdf_tiles : (int64_t)g_sm_count * WS_CDF_GRID);
+    if (g1 < 1) g1 = 1;
+    ws_cdf_tiles_kernel<<<g1, WS_SCAN_BLOCK, 0, s>>>(P);
+    return cudaGetLastError();
+}
+cudaError_t ws_launch_offsets_bounds_mbox(const WsScanParams& P, const WsMailbox& M, unsigned long long* all_tot, const unsigned long long* xmine,
+                                          int xw, unsigned long long* xall, cudaStream_t s) {
+    const bool exact_fp = P.replay_u != nullptr || P.sorted_u != nullptr;
+    if (exact_fp) ws_offsets_bounds_mbox_kernel<true><<<1, 1024, 0, s>>>(P, M, all_tot, xmine, xw, xall);
+    else ws_offsets_bounds_mbox_kernel<false><<<1, 1024, 0, s>>>(P, M, all_tot, xmine, xw, xall);
     return cudaGetLastError();
 }
 

@@ -296,6 +296,16 @@ struct ws_ctx {
     int64_t* d_xmsg = nullptr;
     size_t xmsg_words = 0;                   // words per rank the buffer was sized for
     int64_t pushed_total = 0;                // particles written directly into peers so far
+    // mailbox exchanges (ws_mailbox.cuh): the small all-to-all messages of a sharded step are stored by the producing
+    // kernel straight into the peers' mailboxes (mapped once, here) instead of travelling as NCCL collectives
+    bool mbox_on = false;                    // every rank mapped every mailbox and the trial exchange went through (env WSB200_MAILBOX=0: off)
+    unsigned long long* d_mbox = nullptr;    // my mailbox: [2 parities][nranks sources][mbox_cap] 8-byte words
+    std::vector<unsigned long long*> mbox_peer;  // rank q's mailbox in this process's address space ([rank] = d_mbox)
+    int32_t mbox_cap = 0;
+    uint32_t mbox_seq = 0;                   // sequence number of the last exchange (the same on every rank)
+    unsigned int* h_mbox_err = nullptr;      // mapped host word: an exchange timed out
+    unsigned int* d_mbox_err = nullptr;      // its device address
+    int64_t mbox_exchanges = 0;
     double phase_ms[8] = {0};                // WSB200_TRACE=1: host wall time per phase of resample_sharded
     int64_t phase_n = 0;
 
@@ -316,6 +326,9 @@ static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out);
 static const int32_t* anc_of_event(const ws_ctx* c, int64_t event);
 static int materialize_tape_planes(ws_ctx* c, int32_t n_extra, const int32_t* col, const int32_t* comp);
 static int resolve_spec(ws_ctx* c);
+static int mbox_setup(ws_ctx* c);
+static WsMailbox mbox_next(ws_ctx* c, int n_exchanges);
+static int mbox_check(ws_ctx* c);
 
 // ------------------------------------------------------------------------------------------
 // error helpers
@@ -622,6 +635,11 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
                 return rc;
             }
         }
+        if (mbox_setup(c) != WS_OK) {
+            int rc = fail(nullptr, WS_ENCCL, "%s", c->err.c_str());
+            ws_destroy(c);
+            return rc;
+        }
     }
     c->logw_uniform = true;
     c->logw_base = 0.0;
@@ -681,6 +699,10 @@ extern "C" int ws_destroy(ws_ctx* c) {
             if (b) cudaIpcCloseMemHandle(b);
     if (c->d_barrier) cudaFree(c->d_barrier);
     if (c->d_xmsg) cudaFree(c->d_xmsg);
+    for (size_t q = 0; q < c->mbox_peer.size(); ++q)
+        if ((int)q != c->rank && c->mbox_peer[q]) cudaIpcCloseMemHandle(c->mbox_peer[q]);
+    if (c->d_mbox) cudaFree(c->d_mbox);
+    if (c->h_mbox_err) cudaFreeHost(c->h_mbox_err);
     if (c->comm) g_nccl.CommDestroy(c->comm);
     cudaFree(c->d_score_ops);
     cudaFree(c->d_seg_ops);
@@ -1420,11 +1442,19 @@ static int ensure_reduced(ws_ctx* c, bool for_resample = false, bool wait = true
         c->partials_valid = true;
     }
     TimedEvent te;
-    timed_begin(c, KC_FINALIZE, te);
     unsigned long long* ties = for_resample ? c->d_counters + 3 : nullptr;   // knife-edge decisions (ws_get_ess_ties)
+    if (c->nranks > 1 && c->mbox_on) {
+        // shard reduction, exchange of the (m, S, Q) triples and their combination in ONE kernel (ws_finalize_mbox_kernel)
+        const WsMailbox M = mbox_next(c, 1);
+        timed_begin(c, KC_FINALIZE, te);
+        CK(c, ws_launch_finalize_mbox(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->d_all_msq, ties, M, c->stream));
+        timed_end(c, te);
+    } else {
+    timed_begin(c, KC_FINALIZE, te);
     CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream, c->nranks > 1 ? nullptr : ties));
     timed_end(c, te);
-    if (c->nranks > 1) {
+    }
+    if (c->nranks > 1 && !c->mbox_on) {
         // every rank reduces its shard; the (m, S, Q) triples are allgathered and combined in rank order
         NCK(c, g_nccl.AllGather(c->d_red, c->d_all_msq, 3, WS_NCCL_FLOAT64, c->comm, c->stream));
         timed_begin(c, KC_FINALIZE, te);
@@ -1435,6 +1465,7 @@ static int ensure_reduced(ws_ctx* c, bool for_resample = false, bool wait = true
     c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut);
     if (!wait) return WS_OK;   // the caller's next wait on the stream delivers *h_red (it then sets red_valid)
     CK(c, cudaStreamSynchronize(c->stream));
+    TRY(mbox_check(c));
     c->red_valid = true;
     return WS_OK;
 }
@@ -1793,6 +1824,118 @@ static int allgather_host_bytes(ws_ctx* c, const void* mine, size_t bytes, std::
     return WS_OK;
 }
 
+// ---- mailboxes (ws_mailbox.cuh) --------------------------------------------------------------------------------
+// the descriptor of the next `n_exchanges` exchanges (one kernel): every rank calls this at the same points
+static WsMailbox mbox_next(ws_ctx* c, int n_exchanges) {
+    WsMailbox M;
+    memset(&M, 0, sizeof(M));
+    for (int q = 0; q < c->nranks; ++q) M.box[q] = c->mbox_peer[(size_t)q];
+    M.rank = c->rank;
+    M.nranks = c->nranks;
+    M.seq = c->mbox_seq + 1u;
+    M.cap = c->mbox_cap;
+    M.err = c->d_mbox_err;
+    M.timeout_ns = 20000000000ull;
+    if (const char* e = getenv("WSB200_MAILBOX_TIMEOUT_MS")) M.timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
+    c->mbox_seq += (uint32_t)n_exchanges;
+    c->mbox_exchanges += n_exchanges;
+    return M;
+}
+// after a host wait on the stream: did an exchange give up?
+static int mbox_check(ws_ctx* c) {
+    if (c->h_mbox_err != nullptr && *reinterpret_cast<volatile unsigned int*>(c->h_mbox_err) != 0u)
+        return fail(c, WS_ENCCL, "mailbox exchange timed out: a rank died or the ranks left lock-step");
+    return WS_OK;
+}
+static void mbox_release(ws_ctx* c) {
+    for (size_t q = 0; q < c->mbox_peer.size(); ++q)
+        if ((int)q != c->rank && c->mbox_peer[q]) cudaIpcCloseMemHandle(c->mbox_peer[q]);
+    c->mbox_peer.clear();
+    if (c->d_mbox) cudaFree(c->d_mbox);
+    c->d_mbox = nullptr;
+    c->mbox_on = false;
+    cudaGetLastError();
+}
+// Allocate this rank's mailbox, map everybody else's (cudaIpc), and prove the path with one barrier exchange.  Any
+// failure on any rank — ranks sharing a process, no IPC / peer access, a trial that times out — is agreed on over
+// NCCL and leaves the whole job on the NCCL collectives (mbox_on = false everywhere).
+static int mbox_setup(ws_ctx* c) {
+    const int R = c->nranks, r = c->rank;
+    if (const char* e = getenv("WSB200_MAILBOX"))
+        if (strcmp(e, "0") == 0) return WS_OK;
+    if (R > WS_MBOX_MAX_RANKS) return WS_OK;
+    CK(c, cudaSetDevice(c->device));
+    struct Msg {
+        int64_t pid, ok;
+        cudaIpcMemHandle_t h;
+    };
+    static_assert(sizeof(Msg) % 8 == 0, "Msg travels as 64-bit words");
+    Msg mine;
+    memset(&mine, 0, sizeof(mine));
+    mine.pid = (int64_t)getpid();
+    c->mbox_cap = 16384;
+    const size_t bytes = sizeof(unsigned long long) * 2 * (size_t)R * (size_t)c->mbox_cap;
+    bool ok = cudaMalloc(&c->d_mbox, bytes) == cudaSuccess && cudaMemset(c->d_mbox, 0, bytes) == cudaSuccess;
+    if (ok && c->h_mbox_err == nullptr) {
+        ok = cudaHostAlloc(&c->h_mbox_err, 64, cudaHostAllocMapped) == cudaSuccess;
+        if (ok) {
+            memset(c->h_mbox_err, 0, 64);
+            ok = cudaHostGetDevicePointer((void**)&c->d_mbox_err, c->h_mbox_err, 0) == cudaSuccess;
+        }
+    }
+    ok = ok && cudaIpcGetMemHandle(&mine.h, c->d_mbox) == cudaSuccess;
+    ok = ok && cudaDeviceSynchronize() == cudaSuccess;   // the mailbox is zero before anybody can learn its handle
+    cudaGetLastError();
+    mine.ok = ok ? 1 : 0;
+    std::vector<char> all;
+    TRY(allgather_host_bytes(c, &mine, sizeof(mine), all));
+    const Msg* msgs = reinterpret_cast<const Msg*>(all.data());
+    bool usable = true;
+    for (int q = 0; q < R; ++q) {
+        if (!msgs[q].ok) usable = false;
+        for (int q2 = q + 1; q2 < R; ++q2)
+            if (msgs[q].pid == msgs[q2].pid) usable = false;   // IPC mappings need separate processes
+    }
+    if (!usable) {
+        mbox_release(c);
+        return WS_OK;
+    }
+    c->mbox_peer.assign((size_t)R, nullptr);
+    c->mbox_peer[(size_t)r] = c->d_mbox;
+    int64_t bad = 0;
+    for (int q = 0; q < R; ++q) {
+        if (q == r) continue;
+        void* base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, msgs[q].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            bad = 1;
+            base = nullptr;
+        }
+        c->mbox_peer[(size_t)q] = (unsigned long long*)base;
+    }
+    std::vector<char> flags;
+    TRY(allgather_host_bytes(c, &bad, sizeof(bad), flags));
+    for (int q = 0; q < R; ++q)
+        if (reinterpret_cast<const int64_t*>(flags.data())[q] != 0) usable = false;
+    if (usable) {
+        // trial: one barrier exchange with a short limit
+        WsMailbox M = mbox_next(c, 1);
+        M.timeout_ns = 10000000000ull;
+        bad = (ws_launch_barrier_mbox(M, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess || *c->h_mbox_err != 0u) ? 1 : 0;
+        cudaGetLastError();
+        TRY(allgather_host_bytes(c, &bad, sizeof(bad), flags));
+        for (int q = 0; q < R; ++q)
+            if (reinterpret_cast<const int64_t*>(flags.data())[q] != 0) usable = false;
+    }
+    if (!usable) {
+        mbox_release(c);
+        if (c->h_mbox_err) *c->h_mbox_err = 0u;
+        return WS_OK;
+    }
+    c->mbox_on = true;
+    return WS_OK;
+}
+
 // (slab index, byte offset) of a device pointer inside this rank's slabs; slab = -1 for nullptr
 static int locate_in_slabs(ws_ctx* c, const void* ptr, int64_t* slab, int64_t* off) {
     *slab = -1;
@@ -1955,6 +2098,18 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     TRY(fill_xmsg(c, planes, xmine));
     CK(c, cudaMemcpyAsync(d_xmine + 1, xmine.data() + 1, sizeof(int64_t) * (xw - 1), cudaMemcpyHostToDevice, c->stream));
     TimedEvent te;
+    const bool mbox = c->mbox_on && 2 * xw <= (size_t)c->mbox_cap;   // (the same on every rank: same planes, same capacity)
+    if (mbox) {
+        // tile CDF, then ONE kernel: group offsets + mass -> masses of all ranks -> my slot bounds -> everybody's message
+        timed_begin(c, KC_SCAN, te);
+        CK(c, ws_launch_cdf_tiles(S, c->stream));
+        S.all_tot = c->d_all_tot;
+        S.rank = r;
+        const WsMailbox M = mbox_next(c, 2);
+        CK(c, ws_launch_offsets_bounds_mbox(S, M, c->d_all_tot, reinterpret_cast<const unsigned long long*>(d_xmine), (int)xw,
+                                            reinterpret_cast<unsigned long long*>(c->d_xmsg), c->stream));
+        timed_end(c, te);
+    } else {
     timed_begin(c, KC_SCAN, te);
     CK(c, ws_launch_cdf(S, c->stream));
     timed_end(c, te);
@@ -1965,9 +2120,11 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     S.rank = r;
     CK(c, ws_launch_bounds(S, c->stream));
     NCK(c, g_nccl.AllGather(d_xmine, c->d_xmsg, xw, WS_NCCL_UINT64, c->comm, c->stream));
+    }
     std::vector<int64_t> xall(xw * (size_t)R);
     CK(c, cudaMemcpyAsync(xall.data(), c->d_xmsg, sizeof(int64_t) * xw * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    TRY(mbox_check(c));
     c->stats.d2h_bytes += (int64_t)(sizeof(int64_t) * xw * (size_t)R);
     if (fired != nullptr) {
         c->red_valid = true;              // *h_red arrived with the same wait
@@ -2134,7 +2291,8 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
         NCK(c, g_nccl.GroupEnd());
     }
     if (push) {
-        NCK(c, g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, WS_NCCL_UINT64, WS_NCCL_SUM, c->comm, c->stream));
+        if (c->mbox_on) CK(c, ws_launch_barrier_mbox(mbox_next(c, 1), c->stream));
+        else NCK(c, g_nccl.AllReduce(c->d_barrier, c->d_barrier, 1, WS_NCCL_UINT64, WS_NCCL_SUM, c->comm, c->stream));
         c->pushed_total += remote_send;
     }
     if (c->phase_n > 6) c->phase_ms[5] += t_now() - t0;  // exchange without the communicator's first-use set-up
@@ -3660,6 +3818,11 @@ extern "C" int ws_next_philox_stream(ws_ctx* c, uint64_t* stream_out, uint64_t* 
     if (!c) return WS_EINVAL;
     if (stream_out) *stream_out = c->next_stream;
     if (seed_out) *seed_out = c->seed;
+    return WS_OK;
+}
+extern "C" int ws_get_mailbox_exchanges(ws_ctx* c, int64_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    *out = c->mbox_on ? c->mbox_exchanges : 0;
     return WS_OK;
 }
 extern "C" int ws_get_pushed(ws_ctx* c, int64_t* out) {
