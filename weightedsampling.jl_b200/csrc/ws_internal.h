@@ -130,6 +130,7 @@ struct WsGatherParams {
 #define WS_COMPOSE_MAX_CHAIN 24
 struct WsComposeParams {
     int64_t n;
+    int64_t n_rows;   // rows >= n_rows end a chain (spare rows of a sharded state); the shard size
     int32_t n_chain;
     int32_t pad;
     const int32_t* chain[WS_COMPOSE_MAX_CHAIN];  // applied in this order: idx = chain[t][idx]
@@ -169,8 +170,17 @@ cudaError_t ws_launch_exp_norm(const double* logw, const WsReduceOut* red, doubl
                                cudaStream_t s);
 cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int grid, cudaStream_t s);
 cudaError_t ws_launch_local_ancestors(int32_t* anc, int64_t n, const int32_t* anc_self, int64_t self_lo, int64_t self_hi,
-                                      int grid, cudaStream_t s);
-cudaError_t ws_launch_patch_ancestors(int32_t* anc, int64_t n, int64_t self_lo, int64_t self_hi, cudaStream_t s);
+                                      int64_t spare_base, int grid, cudaStream_t s);
+cudaError_t ws_launch_patch_ancestors(int32_t* anc, int64_t n, int64_t self_lo, int64_t self_hi, int64_t spare_base, cudaStream_t s);
+// sharded genealogy: offspring pushed to a peer for planes that are `level` events behind (ws_kernels.cu)
+struct WsTracedPlane {
+    const double* src;   // the plane's front buffer (its own, older, particle order)
+    double* dst;         // first row of the piece in the peer's plane
+    int64_t level;       // resampling events the plane is behind
+};
+cudaError_t ws_launch_trace_rows(const int32_t* anc, int64_t m, const int32_t* const* chain, int n_levels, int64_t n_rows, int32_t* rows,
+                                 cudaStream_t s);
+cudaError_t ws_launch_push_traced(const WsTracedPlane* planes, int n_planes, int64_t m, const int32_t* rows, cudaStream_t s);
 cudaError_t ws_launch_gather_rows(const double* src, const int64_t* idx, int64_t n_idx, double* dst, cudaStream_t s);
 cudaError_t ws_launch_compose(const WsComposeParams& P, int32_t* out, const int32_t* start, cudaStream_t s);
 cudaError_t ws_launch_compose_rows(const WsComposeParams& P, int64_t* out, const int64_t* start, cudaStream_t s);

@@ -2664,38 +2664,84 @@ cudaError_t ws_launch_sumsq(const double* w, int64_t n, double* partials, int gr
 // Sharded deferred gather: ancestor of local slot i.  Slots [self_lo, self_hi) are filled by this rank's
 // own offspring (anc_self, slot order); the slots below / above were received from lower / higher ranks
 // and sit, in slot order, in the spare rows n, n+1, ... behind every plane.
+// (`spare_base`: first spare row of this event's received offspring — spare rows are handed out event by event while
+// older planes still read the rows of earlier events, see SpareRing in ws_runtime.cu)
 __global__ void ws_local_ancestors_kernel(int32_t* __restrict__ anc, int64_t n, const int32_t* __restrict__ anc_self,
-                                          int64_t self_lo, int64_t self_hi) {
+                                          int64_t self_lo, int64_t self_hi, int64_t spare_base) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         int32_t a;
-        if (i < self_lo) a = (int32_t)(n + i);
-        else if (i >= self_hi) a = (int32_t)(n + self_lo + (i - self_hi));
+        if (i < self_lo) a = (int32_t)(n + spare_base + i);
+        else if (i >= self_hi) a = (int32_t)(n + spare_base + self_lo + (i - self_hi));
         else a = anc_self[i - self_lo];
         anc[i] = a;
     }
 }
 cudaError_t ws_launch_local_ancestors(int32_t* anc, int64_t n, const int32_t* anc_self, int64_t self_lo, int64_t self_hi,
-                                      int grid, cudaStream_t s) {
-    ws_local_ancestors_kernel<<<grid, 256, 0, s>>>(anc, n, anc_self, self_lo, self_hi);
+                                      int64_t spare_base, int grid, cudaStream_t s) {
+    ws_local_ancestors_kernel<<<grid, 256, 0, s>>>(anc, n, anc_self, self_lo, self_hi, spare_base);
     return cudaGetLastError();
 }
 
 // the same for ancestors that the search already wrote in place: only the received slots are patched
-__global__ void ws_patch_ancestors_kernel(int32_t* __restrict__ anc, int64_t n, int64_t self_lo, int64_t self_hi) {
+__global__ void ws_patch_ancestors_kernel(int32_t* __restrict__ anc, int64_t n, int64_t self_lo, int64_t self_hi, int64_t spare_base) {
     const int64_t n_patch = self_lo + (n - self_hi);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_patch; k += stride) {
-        if (k < self_lo) anc[k] = (int32_t)(n + k);
-        else anc[self_hi + (k - self_lo)] = (int32_t)(n + k);
+        if (k < self_lo) anc[k] = (int32_t)(n + spare_base + k);
+        else anc[self_hi + (k - self_lo)] = (int32_t)(n + spare_base + k);
     }
 }
-cudaError_t ws_launch_patch_ancestors(int32_t* anc, int64_t n, int64_t self_lo, int64_t self_hi, cudaStream_t s) {
+cudaError_t ws_launch_patch_ancestors(int32_t* anc, int64_t n, int64_t self_lo, int64_t self_hi, int64_t spare_base, cudaStream_t s) {
     const int64_t n_patch = self_lo + (n - self_hi);
     if (n_patch <= 0) return cudaSuccess;
     int grid = (int)((n_patch + 255) / 256);
     if (grid > g_sm_count * 8) grid = g_sm_count * 8;
-    ws_patch_ancestors_kernel<<<grid, 256, 0, s>>>(anc, n, self_lo, self_hi);
+    ws_patch_ancestors_kernel<<<grid, 256, 0, s>>>(anc, n, self_lo, self_hi, spare_base);
+    return cudaGetLastError();
+}
+
+// ---- sharded genealogy: migrating offspring of planes that are still in an older particle order -----------------------
+// A plane that is `level` resampling events behind stores the value of current slot a at row chain_{level-1}[ ... chain_0[a]]
+// (chain_t = the ancestors of event E - t, nullptr for a queued step that did not fire; the walk ends at a spare row, see
+// ws_compose_kernel).  For the m offspring a rank produces for another rank, ws_trace_rows_kernel walks the chain ONCE per
+// offspring and keeps the row at every level; ws_push_traced_kernel then writes all planes of all levels into the peer's
+// spare rows in one launch — m chains instead of gathering every stale plane over all n particles before every event.
+__global__ void __launch_bounds__(256) ws_trace_rows_kernel(const int32_t* __restrict__ anc, int64_t m, const int32_t* const* __restrict__ chain,
+                                                            int n_levels, int64_t n_rows, int32_t* __restrict__ rows /* [n_levels + 1][m] */) {
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += stride) {
+        int64_t idx = (int64_t)__ldg(anc + j);
+        rows[j] = (int32_t)idx;
+        for (int t = 0; t < n_levels; ++t) {
+            const int32_t* a = chain[t];
+            if (a != nullptr && idx < n_rows) idx = (int64_t)__ldg(a + idx);
+            rows[(size_t)(t + 1) * (size_t)m + j] = (int32_t)idx;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) ws_push_traced_kernel(const WsTracedPlane* __restrict__ planes, int64_t m, const int32_t* __restrict__ rows) {
+    const WsTracedPlane pl = planes[blockIdx.y];
+    const int32_t* const r = rows + (size_t)pl.level * (size_t)m;
+    const int64_t stride = (int64_t)gridDim.x * 256;
+    for (int64_t j = (int64_t)blockIdx.x * 256 + threadIdx.x; j < m; j += stride) pl.dst[j] = __ldg(pl.src + __ldg(r + j));
+}
+cudaError_t ws_launch_trace_rows(const int32_t* anc, int64_t m, const int32_t* const* chain, int n_levels, int64_t n_rows, int32_t* rows,
+                                 cudaStream_t s) {
+    if (m <= 0) return cudaSuccess;
+    int grid = (int)((m + 255) / 256);
+    if (grid > g_sm_count * 8) grid = g_sm_count * 8;
+    ws_trace_rows_kernel<<<grid, 256, 0, s>>>(anc, m, chain, n_levels, n_rows, rows);
+    return cudaGetLastError();
+}
+cudaError_t ws_launch_push_traced(const WsTracedPlane* planes, int n_planes, int64_t m, const int32_t* rows, cudaStream_t s) {
+    if (m <= 0 || n_planes <= 0) return cudaSuccess;
+    int gx = (int)((m + 255) / 256);
+    if (gx > g_sm_count * 2) gx = g_sm_count * 2;
+    for (int p0 = 0; p0 < n_planes; p0 += 32768) {   // (gridDim.y <= 65535)
+        const int np = n_planes - p0 < 32768 ? n_planes - p0 : 32768;
+        ws_push_traced_kernel<<<dim3((unsigned)gx, (unsigned)np), 256, 0, s>>>(planes + p0, m, rows);
+    }
     return cudaGetLastError();
 }
 
@@ -2725,7 +2771,10 @@ __global__ void __launch_bounds__(256) ws_compose_kernel(const WsComposeParams P
     const int64_t stride = (int64_t)gridDim.x * 256;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < P.n; i += stride) {
         int64_t idx = start != nullptr ? (int64_t)start[i] : i;
-        for (int t = 0; t < P.n_chain; ++t) idx = (int64_t)__ldg(P.chain[t] + idx);
+        // a row >= n_rows is a spare row (sharded states): an offspring received from another rank, whose value the
+        // sender traced through ITS genealogy when it pushed it — the chain ends there
+        for (int t = 0; t < P.n_chain; ++t)
+            if (idx < P.n_rows) idx = (int64_t)__ldg(P.chain[t] + idx);
         out[i] = (I)idx;
     }
 }
