@@ -416,6 +416,10 @@ int ws_get_pushed(ws_ctx* ctx, int64_t* out);
  * storing into the other ranks' mailboxes over NVLink instead of going through an NCCL collective (0: ranks share a
  * process, no peer mappings, or WSB200_MAILBOX=0) */
 int ws_get_mailbox_exchanges(ws_ctx* ctx, int64_t* out);
+/* sharded genealogy: values (offspring x planes) this rank pushed to other ranks for planes that were one or more resampling
+ * events behind, found by tracing the migrating offspring through the retained ancestor vectors (src/stores.jl:105-121
+ * gathers every column at every event instead) */
+int ws_get_traced_pushes(ws_ctx* ctx, int64_t* out);
 /* the Philox stream id the next random statement / resample will use, and the key (tests reproduce draws) */
 int ws_next_philox_stream(ws_ctx* ctx, uint64_t* stream_out, uint64_t* seed_out);
 /* raw cudaStream_t of the context (as void*), so a host can bracket calls with its own events */

@@ -368,4 +368,21 @@ void hh_count_slots_le(const double* cs, int64_t n_c, const double* r, int64_t n
     const double inv_n = 1.0 / (double)n;
     for (int64_t i = 0; i < n_c; ++i) out[i] = ws_count_slots_le(cs[i], n, inv_n, ra);
 }
+// The spare-row ring of the sharded genealogy (csrc/ws_exchange.h): replay a sequence of operations on one ring.
+// ops[k] = (kind, a, b): kind 0 = allocate a rows for event b -> out[k] = start or -1 (a failed allocation changes nothing);
+// kind 1 = release the regions of events <= a -> out[k] = regions left.
+void hh_spare_ring(int64_t cap, const int64_t* ops, int n_ops, int64_t* out) {
+    WsSpareRing ring;
+    for (int k = 0; k < n_ops; ++k) {
+        const int64_t kind = ops[3 * k], a = ops[3 * k + 1], b = ops[3 * k + 2];
+        if (kind == 0) {
+            const int64_t s = ws_spare_ring_peek(ring, cap, a);
+            if (s >= 0) ring.push_back(WsSpareRegion{b, s, a});
+            out[k] = s;
+        } else {
+            ws_spare_ring_release(ring, a);
+            out[k] = (int64_t)ring.size();
+        }
+    }
+}
 }  // extern "C"

@@ -328,3 +328,84 @@ def test_sharded_direct_exchange_equals_single_gpu(lam, push_min, mode):
     else:
         assert pushed == migrated > 1000
         assert (migrated > n // 64) == (mode == "eager")
+
+
+def _worker_history(rank, world, port, n, T, genealogy, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), WSB200_GENEALOGY=genealogy)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import models
+    import wsb200 as ws
+    rng = np.random.default_rng(7)
+    obs = list(np.cumsum(0.3 * rng.standard_normal(T)) + rng.standard_normal(T))
+    st = ws.sharded_state(n, device=rank, seed=31, ess_perc_min=1.0)
+    st.store._call("ws_set_timing", 1)
+    ws.run(ws.model(models.SSM1D)(obs), st)
+    kt = st.kernel_times()
+    g = st.genealogy()
+    traced, mig = ctypes.c_int64(), ctypes.c_int64()
+    st.store._call("ws_get_traced_pushes", ctypes.byref(traced))
+    st.store._call("ws_get_migrated", ctypes.byref(mig))
+    names = st.store.colnames()
+    # history columns read newest first, oldest first and in between
+    order = names[::-1][:5] + names[:5] + names[5:-5]
+    cols = {name: st[name] for name in order}
+    q.put((rank, cols, st.weights, ws.log_evidence(st), g, traced.value, mig.value, kt["gather"]["launches"], st.stats()["resamples_done"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n,T", [(2, 200_003, 40), (2, 60_001, 90), (4, 100_003, 40)])
+def test_sharded_genealogy_keeps_history_columns_in_place(world, n, T):
+    """examples/1D_ssm.jl shape on a sharded state: x{t} is written once and not read again, so it must not be gathered
+    at every later resampling event (src/stores.jl:105-121 does exactly that).  Planes that are behind keep their order
+    over the events of a sharded run too: offspring that change GPU are traced through the retained ancestor vectors
+    by their sender, land in spare rows handed out event by event, and a read composes the vectors as on one GPU.
+    Every column must equal the single-GPU run (itself checked against the oracle's eager resample! in
+    test_gpu_genealogy.py).  The second case has 4 096 spare rows per rank and ~90 events: the rings fill up and the
+    oldest planes are brought up to date to release them."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import models
+    import wsb200 as ws
+    rng = np.random.default_rng(7)
+    obs = list(np.cumsum(0.3 * rng.standard_normal(T)) + rng.standard_normal(T))
+    single = ws.SMCState(n, device=0, seed=31, ess_perc_min=1.0)
+    ws.run(ws.model(models.SSM1D)(obs), single)
+    names = single.store.colnames()
+    ref_cols = {name: single[name] for name in names}
+    res = {}
+    for genealogy in ("1", "0"):
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = 29801 + world + 10 * (genealogy == "0") + (T % 7)
+        procs = [ctx.Process(target=_worker_history, args=(r, world, port, n, T, genealogy, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        out = sorted((q.get(timeout=600) for _ in range(world)), key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=120)
+            assert p.exitcode == 0
+        res[genealogy] = out
+        differing = 0
+        for name in names:
+            got = np.concatenate([o[1][name] for o in out])
+            bad = np.abs(got - ref_cols[name]) > 1e-9 * (1 + np.abs(ref_cols[name]))
+            differing = max(differing, int(bad.sum()))
+        print(f"world={world} n={n} T={T} genealogy={genealogy}: worst column has {differing} of {n} particles differing; "
+              f"vectors kept {[o[4]['vectors'] for o in out]}, traced values {[o[5] for o in out]}, migrated {[o[6] for o in out]}, "
+              f"gather launches {[o[7] for o in out]}")
+        assert differing <= 5
+        np.testing.assert_allclose(np.concatenate([o[2] for o in out]), single.weights, rtol=1e-9, atol=1e-12)
+        for o in out:
+            assert abs(o[3] - ws.log_evidence(single)) <= 1e-10 * abs(ws.log_evidence(single))
+            assert o[8] == single.stats()["resamples_done"]
+    on, off = res["1"], res["0"]
+    assert all(o[5] > 0 for o in on) and all(o[5] == 0 for o in off)          # offspring were traced for planes that were behind
+    assert all(o[4]["vectors"] > 3 for o in on)                                # ... whose ancestor vectors were kept
+    # without the genealogy every stale plane is gathered before every event: O(T^2) plane gathers against O(T)
+    assert sum(o[7] for o in on) * 2 < sum(o[7] for o in off)

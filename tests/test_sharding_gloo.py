@@ -136,3 +136,49 @@ def test_exchange_plan_is_consistent_between_senders_and_receivers(R):
                 assert rows_lazy[0][0] == n_d
                 if fits0:
                     assert rows_lazy[-1][1] <= n_d + max(4096, n_d // 32)         # ... and stay inside the spare rows
+
+
+def test_spare_ring_never_hands_out_a_row_twice():
+    """The spare-row ring of the sharded genealogy (csrc/ws_exchange.h) against a brute-force occupancy map: random
+    allocations (one per resampling event) and releases of the oldest events; a region is contiguous, inside the
+    capacity, disjoint from every live region, and an allocation only fails when the rows behind the newest region
+    and in front of the oldest one are both too short."""
+    import ctypes as C
+    import hostlib
+    L = hostlib.lib()
+    L.hh_spare_ring.argtypes = [C.c_int64, C.c_void_p, C.c_int, C.c_void_p]
+    rng = np.random.default_rng(11)
+    for trial in range(40):
+        cap = int(rng.integers(8, 200))
+        ops, ev, oldest = [], 0, 0
+        for _ in range(120):
+            if rng.random() < 0.7 or oldest > ev:
+                ev += 1
+                ops.append((0, int(rng.integers(0, max(2, cap // 3))), ev))
+            else:
+                oldest = int(rng.integers(oldest, ev + 1))
+                ops.append((1, oldest, 0))
+        a = np.asarray(ops, dtype=np.int64)
+        out = np.zeros(len(ops), dtype=np.int64)
+        L.hh_spare_ring(cap, a.ctypes.data_as(C.c_void_p), len(ops), out.ctypes.data_as(C.c_void_p))
+        live = {}                      # event -> (start, cnt)
+        failed = 0
+        for (kind, x, y), o in zip(ops, out):
+            if kind == 0:
+                if o < 0:
+                    failed += 1
+                    occ = np.zeros(cap, dtype=bool)
+                    for s, c in live.values():
+                        occ[s:s + c] = True
+                    # no contiguous free run of x rows may exist at the two places the ring looks at; in particular
+                    # an empty ring never refuses a request that fits the capacity
+                    assert x > cap or occ.any()
+                    continue
+                assert 0 <= o and o + x <= cap
+                for s, c in live.values():
+                    assert o + x <= s or s + c <= o or x == 0 or c == 0, (trial, o, x, s, c)
+                live[y] = (int(o), x)
+            else:
+                live = {e: v for e, v in live.items() if e > x}
+                assert o == len(live)
+        assert failed < len(ops)

@@ -180,6 +180,7 @@ SIGNATURES = {
     "ws_get_migrated": (C.c_int, [_ctx, _i64p]),
     "ws_get_pushed": (C.c_int, [_ctx, _i64p]),
     "ws_get_mailbox_exchanges": (C.c_int, [_ctx, _i64p]),
+    "ws_get_traced_pushes": (C.c_int, [_ctx, _i64p]),
     "ws_stream": (C.c_int, [_ctx, C.POINTER(C.c_void_p)]),
 }
 

@@ -9,6 +9,7 @@
 #pragma once
 #include <stdint.h>
 #include <algorithm>
+#include <deque>
 #include <vector>
 
 inline int64_t ws_rank_lo(int64_t n_global, int R, int d) { return (n_global * (int64_t)d) / R; }
@@ -78,4 +79,34 @@ inline int64_t ws_push_offset(const int32_t* bnd, int R, int r, int d, int64_t n
     for (int q = 0; q < r; ++q)
         if (q != d) acc += ws_piece(bnd, n_global, R, q, d);
     return (ws_rank_lo(n_global, R, d + 1) - lo_d) + acc;
+}
+
+// ---- spare rows over several resampling events (sharded genealogy) ---------------------------------------------------
+// A plane that is not read does not follow the resampling events: it keeps its own particle order and the
+// offspring it received at event e stay in the spare rows they were pushed to, where the ancestor vector of event e
+// points at them.  Spare rows are therefore handed out event by event, as a ring: the region of event e is released
+// when no plane is older than e any more.  Every rank keeps the rings of ALL ranks (the incoming counts of every rank
+// follow from the all-gathered bounds), so that a sender knows where its piece lands without asking.
+struct WsSpareRegion {
+    int64_t event, start, cnt;
+};
+typedef std::deque<WsSpareRegion> WsSpareRing;
+// first row of a free run of `cnt` spare rows (capacity `cap`), or -1
+inline int64_t ws_spare_ring_peek(const WsSpareRing& ring, int64_t cap, int64_t cnt) {
+    if (cnt > cap) return -1;
+    int64_t tail = -1, head = -1;   // start of the oldest / end of the newest non-empty region
+    for (const auto& g : ring) {
+        if (g.cnt <= 0) continue;
+        if (tail < 0) tail = g.start;
+        head = g.start + g.cnt;
+    }
+    if (tail < 0) return 0;
+    if (head > tail) {              // occupied [tail, head): free behind the head, or in front of the tail
+        if (head + cnt <= cap) return head;
+        return cnt <= tail ? 0 : -1;
+    }
+    return head + cnt <= tail ? head : -1;   // wrapped: free [head, tail)
+}
+inline void ws_spare_ring_release(WsSpareRing& ring, int64_t upto_event) {   // regions of events <= upto_event
+    while (!ring.empty() && ring.front().event <= upto_event) ring.pop_front();
 }

@@ -223,6 +223,15 @@ struct ws_ctx {
     std::vector<int32_t*> anc_pool;   // recycled vectors
     bool genealogy = true;
     size_t genealogy_budget = 0;      // bytes of retained ancestor vectors before old planes are gathered anyway
+    // Sharded genealogy: planes that are not read keep their order over the events of a sharded run too.  The offspring a
+    // plane receives at an event stay in spare rows handed out event by event (ws_exchange.h: WsSpareRing, one ring per
+    // rank, all of them kept on every rank), and what a rank pushes to a peer for a plane that is behind is found by
+    // tracing the migrating offspring — not the whole shard — through the retained ancestor vectors.
+    std::vector<WsSpareRing> spare_rings;  // [rank]
+    bool event_keeps = false;         // the resampling event being prepared keeps stale planes (prepare_resample_event)
+    void* d_gen = nullptr;            // scratch of the traced push: [chain pointers | plane table | rows per level]
+    size_t gen_bytes = 0;
+    int64_t traced_rows = 0;          // offspring pushed for planes that were behind (rows x planes), for the tests
     // planes and ancestor vectors are carved out of slabs: a cudaMalloc per new column costs milliseconds
     // (models that create a column per time step: x{t}), and nothing is ever freed before ws_destroy
     struct Slab {
@@ -610,6 +619,7 @@ extern "C" int ws_create_sharded(ws_ctx** out, int64_t n_global, int rank, int n
             return rc;
         }
         c->peer_slabs.resize((size_t)nranks);
+        c->spare_rings.assign((size_t)nranks, WsSpareRing());
         if (const char* e = getenv("WSB200_EXCHANGE")) c->push_exchange = strcmp(e, "nccl") != 0;
         if (const char* e = getenv("WSB200_PUSH_MIN")) c->push_min = strtoll(e, nullptr, 10);
         if (cudaMalloc(&c->d_barrier, 64) != cudaSuccess || cudaMemset(c->d_barrier, 0, 64) != cudaSuccess) {
@@ -699,6 +709,7 @@ extern "C" int ws_destroy(ws_ctx* c) {
             if (b) cudaIpcCloseMemHandle(b);
     if (c->d_barrier) cudaFree(c->d_barrier);
     if (c->d_xmsg) cudaFree(c->d_xmsg);
+    if (c->d_gen) cudaFree(c->d_gen);
     for (size_t q = 0; q < c->mbox_peer.size(); ++q)
         if ((int)q != c->rank && c->mbox_peer[q]) cudaIpcCloseMemHandle(c->mbox_peer[q]);
     if (c->d_mbox) cudaFree(c->d_mbox);
@@ -1520,7 +1531,9 @@ static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out) {
     while (ep < c->epoch && is_identity(ep + 1)) ++ep;  // leading identity events: the plane is effectively newer
     if (ep >= c->epoch) return WS_OK;
     if (ep == c->epoch - 1) {
-        *out = c->d_anc;
+        // (d_anc itself is the vector of the NEXT event while a resampling step is between its commit and its end)
+        const int32_t* a = anc_of_event(c, c->epoch);
+        *out = a != nullptr ? a : c->d_anc;
         return WS_OK;
     }
     if (c->map_E == c->epoch && c->map_ep == ep) {
@@ -1538,6 +1551,7 @@ static int map_for_epoch(ws_ctx* c, int64_t ep, const int32_t** out) {
         WsComposeParams P;
         memset(&P, 0, sizeof(P));
         P.n = c->n;
+        P.n_rows = c->n;
         while (from > ep && P.n_chain < WS_COMPOSE_MAX_CHAIN) {
             const int32_t* a = anc_of_event(c, from);
             if (a == nullptr) return fail(c, WS_EINVAL, "genealogy: ancestors of event %lld were released", (long long)from);
@@ -1618,15 +1632,21 @@ static int materialize_deep(ws_ctx* c, const std::vector<Plane>& planes) {
     return materialize_planes(c, &deep);
 }
 
-// Called before a resampling event writes a new ancestor vector.  Without genealogy (eager mode, sharded
-// runs) every stale plane is gathered and the single vector is reused.  With it, vectors no plane needs any
-// more are recycled, the retained ones are capped by the byte budget (oldest planes gathered first), and a
-// fresh vector becomes d_anc.
-static int begin_resample_event(ws_ctx* c) {
-    if (!c->genealogy || !c->lazy_gather || c->nranks > 1) {
+// Called before a resampling event writes a new ancestor vector.  Without genealogy (eager mode, sharded runs whose
+// exchange cannot carry stale planes) every stale plane is gathered and the single vector is reused.  With it, vectors
+// no plane needs any more are recycled, the retained ones are capped by the byte budget (oldest planes gathered first),
+// and a fresh vector becomes d_anc.  Two halves: `prepare` does everything that may MOVE planes (a sharded step
+// announces its plane addresses to the other ranks afterwards, and may do this before it knows whether the step fires);
+// `commit` takes the vector.  Every decision in here depends only on what all ranks of a sharded state know alike.
+static bool shard_genealogy_ok(const ws_ctx* c) { return c->push_exchange && c->push_min == 0; }
+static int64_t spare_ring_cap(const ws_ctx* c, int q) {
+    return ws_spare_rows(ws_rank_lo(c->n_global, c->nranks, q + 1) - ws_rank_lo(c->n_global, c->nranks, q));
+}
+static int prepare_resample_event(ws_ctx* c) {
+    c->event_keeps = c->genealogy && c->lazy_gather && (c->nranks == 1 || shard_genealogy_ok(c));
+    if (!c->event_keeps) {
         TRY(materialize_planes(c));
-        c->anc_live.clear();
-        c->anc_live.push_back({c->epoch + 1, c->d_anc});
+        for (auto& rg : c->spare_rings) rg.clear();
         return WS_OK;
     }
     auto min_ep = [&]() {
@@ -1642,18 +1662,46 @@ static int begin_resample_event(ws_ctx* c) {
             c->anc_pool.push_back(c->anc_live.front().ptr);
             c->anc_live.pop_front();
         }
+        for (auto& rg : c->spare_rings) ws_spare_ring_release(rg, m);
     };
-    gc();
-    while (!c->anc_live.empty() && (c->anc_live.size() + 1) * sizeof(int32_t) * (size_t)c->n > c->genealogy_budget) {
-        // over budget: bring the oldest planes up to date, which releases the oldest vectors
+    auto gather_oldest = [&](bool* any) {
         const int64_t m = min_ep();
         std::vector<Plane> oldest;
         for (int32_t ci = 0; ci < (int32_t)c->cols.size(); ++ci)
             for (int32_t k = 0; k < c->cols[ci].width; ++k)
                 if (c->cols[ci].stale[k] && c->cols[ci].ep[k] == m) oldest.push_back(Plane{ci, k});
-        if (oldest.empty()) break;
-        TRY(materialize_planes(c, &oldest));
+        *any = !oldest.empty();
+        if (!*any) return (int)WS_OK;
+        return materialize_planes(c, &oldest);
+    };
+    gc();
+    const size_t n_ref = c->nranks > 1 ? (size_t)(c->n_global / c->nranks + 1) : (size_t)c->n;  // (shards differ by one particle)
+    while (!c->anc_live.empty() && (c->anc_live.size() + 1) * sizeof(int32_t) * n_ref > c->genealogy_budget) {
+        // over budget: bring the oldest planes up to date, which releases the oldest vectors
+        bool any = false;
+        TRY(gather_oldest(&any));
+        if (!any) break;
         gc();
+    }
+    // sharded: keep a quarter of every rank's spare rows free for the offspring of this event (if more arrive the step
+    // brings everything up to date and starts the rings afresh, resample_sharded)
+    for (;;) {
+        bool low = false;
+        for (int q = 0; q < (int)c->spare_rings.size(); ++q)
+            if (ws_spare_ring_peek(c->spare_rings[(size_t)q], spare_ring_cap(c, q), spare_ring_cap(c, q) / 4) < 0) low = true;
+        if (!low) break;
+        bool any = false;
+        TRY(gather_oldest(&any));
+        if (!any) break;
+        gc();
+    }
+    return WS_OK;
+}
+static int commit_resample_event(ws_ctx* c) {
+    if (!c->event_keeps) {
+        c->anc_live.clear();
+        c->anc_live.push_back({c->epoch + 1, c->d_anc});
+        return WS_OK;
     }
     if (c->anc_live.empty() && c->anc_pool.empty() && c->d_anc != nullptr) c->anc_pool.push_back(c->d_anc);  // the vector made by ws_create
     int32_t* fresh = nullptr;
@@ -1661,11 +1709,18 @@ static int begin_resample_event(ws_ctx* c) {
         fresh = c->anc_pool.back();
         c->anc_pool.pop_back();
     } else {
-        TRY(pool_alloc(c, (void**)&fresh, sizeof(int32_t) * (size_t)(c->n + c->spare)));
+        // (sharded: a margin of `spare` entries on both sides, as for the vector made by ws_create_sharded)
+        const int64_t margin = c->nranks > 1 ? c->spare : 0;
+        TRY(pool_alloc(c, (void**)&fresh, sizeof(int32_t) * (size_t)(c->n + c->spare + margin)));
+        fresh += margin;
     }
     c->anc_live.push_back({c->epoch + 1, fresh});
     c->d_anc = fresh;
     return WS_OK;
+}
+static int begin_resample_event(ws_ctx* c) {
+    TRY(prepare_resample_event(c));
+    return commit_resample_event(c);
 }
 
 // after the ancestors of the new event are in d_anc
@@ -2130,8 +2185,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
         c->red_valid = true;              // *h_red arrived with the same wait
         *fired = c->h_red->do_resample ? 1 : 0;
         if (!*fired) return WS_OK;        // (the gated kernels did nothing; every rank reads the same decision)
-        c->anc_live.clear();              // the rest of begin_resample_event for a sharded state
-        c->anc_live.push_back({c->epoch + 1, c->d_anc});
+        TRY(commit_resample_event(c));    // the rest of begin_resample_event
         S.gate = 0;
     }
     std::vector<int32_t> bnd(2 * R);
@@ -2159,6 +2213,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     // d_anc[s - my_lo] — own slots in place, the slots produced for the neighbours into the margins on either side —
     // instead of a staging vector that a second pass copies into place (8 B per particle saved).
     // (ws_exchange.h: every rank derives the whole plan from the all-gathered bounds)
+    auto rank_lo = [&](int d) { return ws_rank_lo(c->n_global, R, d); };
     const WsExchangePlan plan = ws_exchange_plan(bnd.data(), R, r, c->n_global);
     const bool fits_all = plan.fits;
     const int64_t lo_r = (c->n_global * (int64_t)r) / R, hi_r = (c->n_global * (int64_t)(r + 1)) / R;
@@ -2174,13 +2229,57 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     c->phase_ms[2] += t_now() - t0;
     t0 = t_now();
     // ---- exchange plan (slot ranges) ------------------------------------------------------------
-    auto rank_lo = [&](int d) { return ws_rank_lo(c->n_global, R, d); };
     const std::vector<int64_t>&send_off = plan.send_off, &send_cnt = plan.send_cnt, &recv_off = plan.recv_off, &recv_cnt = plan.recv_cnt;
     const int64_t remote_send = plan.remote_send, remote_recv = plan.remote_recv;
     c->migrated_total += remote_recv;
-    // every rank takes the same branch: the spare rows are sized from the shard size and all bounds are known to everybody
-    const bool fits = plan.fits;
+    // Spare rows of this event on every rank (ws_exchange.h: rings kept alike on all ranks), and whether planes that
+    // are behind can follow the exchange through the genealogy.  Every rank takes the same branches: the plan, the
+    // rings and the bookkeeping of the planes are the same everywhere.
+    std::vector<int64_t> incoming((size_t)R, 0), starts((size_t)R, 0);
+    for (int d = 0; d < R; ++d)
+        incoming[(size_t)d] = (rank_lo(d + 1) - rank_lo(d)) - ws_piece(bnd.data(), c->n_global, R, d, d);
+    auto ring_try = [&]() {
+        bool ok = true;
+        for (int q = 0; q < R; ++q) {
+            starts[(size_t)q] = ws_spare_ring_peek(c->spare_rings[(size_t)q], spare_ring_cap(c, q), incoming[(size_t)q]);
+            if (starts[(size_t)q] < 0) {
+                ok = false;
+                starts[(size_t)q] = 0;
+            }
+        }
+        return ok;
+    };
+    bool any_stale = false;
+    for (auto& pl : planes)
+        if (c->cols[pl.col].stale[pl.comp]) any_stale = true;
+    const bool push_wanted = c->push_exchange && plan.total_remote > 0 && plan.total_remote >= c->push_min && !planes.empty();
+    bool ring_ok = ring_try();
+    bool readdress = false;
+    if (any_stale && (!ring_ok || (!push_wanted && plan.total_remote > 0))) {
+        // more offspring than the rings hold, or an exchange that cannot trace stale planes: bring every plane up to
+        // date (the eager and the staged paths below assume that) and start the rings afresh
+        TRY(materialize_planes(c));
+        for (auto& rg : c->spare_rings) rg.clear();
+        ring_ok = ring_try();
+        any_stale = false;
+        readdress = push_wanted;   // front / back buffers were swapped: the peers need the new addresses
+    }
+    if (readdress) {
+        TRY(fill_xmsg(c, planes, xmine));
+        CK(c, cudaMemcpyAsync(d_xmine + 1, xmine.data() + 1, sizeof(int64_t) * (xw - 1), cudaMemcpyHostToDevice, c->stream));
+        NCK(c, g_nccl.AllGather(d_xmine, c->d_xmsg, xw, WS_NCCL_UINT64, c->comm, c->stream));
+        CK(c, cudaMemcpyAsync(xall.data(), c->d_xmsg, sizeof(int64_t) * xw * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    const bool fits = plan.fits && ring_ok;
     const bool lazy = c->lazy_gather && fits;
+    if (lazy) {
+        for (int q = 0; q < R; ++q)
+            c->spare_rings[(size_t)q].push_back(WsSpareRegion{c->epoch + 1, starts[(size_t)q], incoming[(size_t)q]});
+    } else {
+        for (auto& rg : c->spare_rings) rg.clear();   // eager: every plane ends up in the new order, nothing stays in spare rows
+        std::fill(starts.begin(), starts.end(), 0);
+    }
 
     const int BATCH = 8;
     // Direct exchange: the gather kernel that would stage a
@@ -2190,8 +2289,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     // passed the allgather of the bounds, i.e. finished all earlier kernels that touch its planes, and what it
     // runs meanwhile (search, its own gathers) reads front rows [0, n) and writes its OWN slots only.  A
     // stream-ordered all-reduce of one word afterwards is the barrier that tells a rank its incoming rows are complete.
-    const int64_t total_remote = plan.total_remote;
-    bool push = c->push_exchange && total_remote > 0 && total_remote >= c->push_min && !planes.empty();
+    bool push = push_wanted;
     std::vector<std::vector<double*>> peer;
     if (push) {
         bool usable = false;
@@ -2199,6 +2297,10 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
         if (!usable) {
             push = false;
             c->push_exchange = false;  // ranks share a process, or no IPC / peer access: stay on ncclSend / ncclRecv (every rank decides alike)
+            if (any_stale) {           // the staged path reads the planes in the current order
+                TRY(materialize_planes(c));
+                any_stale = false;
+            }
         }
     }
     // the migrating offspring are the produced slots outside my own range: a prefix [0, pre) (to lower
@@ -2218,7 +2320,61 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     // where rank q's offspring land on my side: lazily in the spare rows behind the FRONT planes
     // (lower ranks first), eagerly at their final slots in the BACK planes
     const std::vector<int64_t>& spare_pos = plan.spare_pos;
-    for (size_t p0 = 0; p0 < planes.size(); p0 += BATCH) {
+    if (push && any_stale) {
+        // Planes that are behind (sharded genealogy; lazy by construction): the offspring produced for rank d are traced
+        // through the retained ancestor vectors, once per offspring, and ONE kernel writes every plane — from the row
+        // it has the offspring's value at — into d's spare rows.
+        int64_t n_levels = 0;
+        for (auto& pl : planes)
+            if (c->cols[pl.col].stale[pl.comp]) n_levels = std::max(n_levels, c->epoch - c->cols[pl.col].ep[pl.comp]);
+        std::vector<const int32_t*> chain((size_t)n_levels, nullptr);
+        for (int64_t t = 0; t < n_levels; ++t) {
+            const int64_t ev = c->epoch - t;
+            bool found = false;
+            for (auto& v : c->anc_live)
+                if (v.event == ev) {
+                    found = true;
+                    chain[(size_t)t] = v.identity ? nullptr : v.ptr;
+                }
+            if (!found) return fail(c, WS_EINVAL, "genealogy: ancestors of event %lld were released", (long long)ev);
+        }
+        int64_t m_max = 0;
+        for (int d = 0; d < R; ++d)
+            if (d != r) m_max = std::max(m_max, send_cnt[d]);
+        const size_t chain_b = ((size_t)n_levels * sizeof(void*) + 255) & ~(size_t)255;
+        const size_t table_b = (planes.size() * sizeof(WsTracedPlane) + 255) & ~(size_t)255;
+        const size_t rows_b = (size_t)(n_levels + 1) * (size_t)m_max * sizeof(int32_t);
+        if (chain_b + table_b + rows_b > c->gen_bytes) {
+            CK(c, cudaStreamSynchronize(c->stream));
+            if (c->d_gen) CK(c, cudaFree(c->d_gen));
+            c->d_gen = nullptr;
+            c->gen_bytes = 2 * (chain_b + table_b + rows_b);
+            CK(c, cudaMalloc(&c->d_gen, c->gen_bytes));
+        }
+        const int32_t** d_chain = reinterpret_cast<const int32_t**>(c->d_gen);
+        WsTracedPlane* d_table = reinterpret_cast<WsTracedPlane*>((char*)c->d_gen + chain_b);
+        int32_t* d_rows = reinterpret_cast<int32_t*>((char*)c->d_gen + chain_b + table_b);
+        if (n_levels > 0) CK(c, cudaMemcpyAsync(d_chain, chain.data(), (size_t)n_levels * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+        std::vector<WsTracedPlane> table(planes.size());
+        for (int d = 0; d < R; ++d) {
+            if (d == r || send_cnt[d] <= 0) continue;
+            const int64_t at = ws_push_offset(bnd.data(), R, r, d, c->n_global, true) + starts[(size_t)d];
+            for (size_t p = 0; p < planes.size(); ++p) {
+                const Column& col = c->cols[planes[p].col];
+                table[p].src = col.front[planes[p].comp];
+                table[p].dst = peer[d][p] + at;
+                table[p].level = col.stale[planes[p].comp] ? c->epoch - col.ep[planes[p].comp] : 0;
+            }
+            CK(c, cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(WsTracedPlane), cudaMemcpyHostToDevice, c->stream));
+            timed_begin(c, KC_GATHER, te);
+            CK(c, ws_launch_trace_rows(anc_src + send_off[d], send_cnt[d], d_chain, (int)n_levels, c->n, d_rows, c->stream));
+            CK(c, ws_launch_push_traced(d_table, (int)planes.size(), send_cnt[d], d_rows, c->stream));
+            timed_end(c, te);
+            c->stats.kernel_launches += 2;
+            c->traced_rows += send_cnt[d] * (int64_t)planes.size();
+        }
+    }
+    for (size_t p0 = 0; p0 < planes.size() && !(push && any_stale); p0 += BATCH) {
         const int nb = (int)std::min<size_t>(BATCH, planes.size() - p0);
         if (!lazy && send_cnt[r] > 0) {
             // offspring that stay: gather straight into the back buffers
@@ -2244,7 +2400,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
                 G.n = send_cnt[d];
                 G.ancestors = anc_src + send_off[d];
                 G.n_planes = nb;
-                const int64_t at = ws_push_offset(bnd.data(), R, r, d, c->n_global, lazy);
+                const int64_t at = ws_push_offset(bnd.data(), R, r, d, c->n_global, lazy) + starts[(size_t)d];
                 for (int k = 0; k < nb; ++k) {
                     const Plane pl = planes[p0 + k];
                     G.src[k] = c->cols[pl.col].front[pl.comp];
@@ -2282,7 +2438,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
                 if (send_cnt[d] > 0)
                     NCK(c, g_nccl.Send(c->d_send + (size_t)k * remote_send + stage_pos(d), (size_t)send_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
                 if (recv_cnt[d] > 0) {
-                    double* dst = lazy ? c->cols[pl.col].front[pl.comp] + c->n + spare_pos[d]
+                    double* dst = lazy ? c->cols[pl.col].front[pl.comp] + c->n + starts[(size_t)r] + spare_pos[d]
                                        : c->cols[pl.col].back[pl.comp] + recv_off[d];
                     NCK(c, g_nccl.Recv(dst, (size_t)recv_cnt[d], WS_NCCL_FLOAT64, d, c->comm, c->stream));
                 }
@@ -2306,10 +2462,10 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
         if (inplace) {
             // own slots are already in place: only the slots received from other ranks get their spare-row index
             CK(c, ws_launch_patch_ancestors(c->d_anc, c->n, send_cnt[r] > 0 ? self_lo : c->n, send_cnt[r] > 0 ? self_hi : c->n,
-                                             c->stream));
+                                             starts[(size_t)r], c->stream));
         } else {
             CK(c, ws_launch_local_ancestors(c->d_anc, c->n, anc_src + send_off[r], send_cnt[r] > 0 ? self_lo : c->n,
-                                             send_cnt[r] > 0 ? self_hi : c->n, grid_for(c, c->n, 256, 8), c->stream));
+                                             send_cnt[r] > 0 ? self_hi : c->n, starts[(size_t)r], grid_for(c, c->n, 256, 8), c->stream));
         }
         c->stats.kernel_launches++;
         end_resample_event(c);
@@ -2355,7 +2511,7 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
                 TRY(resample_sharded(c, nullptr, step_stream));
             }
         } else {
-            TRY(materialize_planes(c));   // what begin_resample_event does first on a sharded state (harmless if the step does not fire)
+            TRY(prepare_resample_event(c));   // the half of begin_resample_event that moves planes (harmless if the step does not fire)
             TRY(resample_sharded(c, nullptr, step_stream, &fired));
         }
         const WsReduceOut r = *c->h_red;
@@ -3019,6 +3175,7 @@ extern "C" int ws_col_download_rows(ws_ctx* c, int32_t id, const int64_t* indice
                 WsComposeParams P;
                 memset(&P, 0, sizeof(P));
                 P.n = n_idx;
+                P.n_rows = c->n;
                 while (from > col.ep[k] && P.n_chain < WS_COMPOSE_MAX_CHAIN) {
                     const int32_t* a = anc_of_event(c, from);
                     if (a == nullptr) return fail(c, WS_EINVAL, "genealogy: ancestors of event %lld were released", (long long)from);
@@ -3818,6 +3975,11 @@ extern "C" int ws_next_philox_stream(ws_ctx* c, uint64_t* stream_out, uint64_t* 
     if (!c) return WS_EINVAL;
     if (stream_out) *stream_out = c->next_stream;
     if (seed_out) *seed_out = c->seed;
+    return WS_OK;
+}
+extern "C" int ws_get_traced_pushes(ws_ctx* c, int64_t* out) {
+    if (!c || !out) return WS_EINVAL;
+    *out = c->traced_rows;
     return WS_OK;
 }
 extern "C" int ws_get_mailbox_exchanges(ws_ctx* c, int64_t* out) {
