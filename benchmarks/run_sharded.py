@@ -206,10 +206,45 @@ def c5skew(rank, world, local):
         del st
 
 
+def c2hist(rank, world, local):
+    """examples/2D_ssm.jl VERBATIM (x{t} history kept, 2 (T + 3) planes) as ONE sharded filter: with the sharded genealogy a
+    history column is never gathered again (migrating offspring are traced by their sender); without it every stale plane
+    is gathered before every event, as the reference's resample! does (src/stores.jl:105-121)."""
+    import ctypes as C
+    rng = np.random.default_rng(42)
+    T = 400
+    obs = [rng.standard_normal(2) * 0.5 + np.array([t, 0.0]) for t in range(T)]
+    for n, Tn_off in ((1_000_000, 400), (10_000_000, 100)):
+        for on in (True, False):
+            Tn = T if on else Tn_off   # the eager variant is quadratic in T: shorter run at the large size, per-step figure quoted
+            st = make_state(n, world, local, ess_perc_min=1.0, seed=1)
+            st.set_genealogy(on)
+            root = ws.model(models.SSM2D)(obs[:Tn])
+            st.sync()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            ws.run(root, st)
+            le = ws.log_evidence(st)
+            st.sync()
+            dt = max_over_ranks(time.perf_counter() - t0, world, local)
+            t1 = time.perf_counter()
+            x_mid = st[f"x_{Tn // 2}"]          # a column ~T/2 events behind
+            dt_read = max_over_ranks(time.perf_counter() - t1, world, local)
+            traced, mig = C.c_int64(), C.c_int64()
+            st.store._call("ws_get_traced_pushes", C.byref(traced))
+            st.store._call("ws_get_migrated", C.byref(mig))
+            emit(rank, config=f"C2-history examples/2D_ssm.jl verbatim N={n} T={Tn} over {world} GPU(s), genealogy={'on' if on else 'off'}",
+                 seconds=dt, particle_updates_per_sec=n * Tn / dt, ms_per_step=1e3 * dt / Tn, log_evidence=le, genealogy=st.genealogy(),
+                 read_mid_column_seconds=dt_read, mid_column_mean_rank0=float(x_mid[:, 0].mean()), columns=len(st.store.colnames()),
+                 traced_values_rank0=traced.value, migrated_rank0=mig.value, n_gpus=world)
+            del st
+
+
 if __name__ == "__main__":
     rank, world, local = setup()
     which = [a for a in sys.argv[1:] if not a.startswith("--")] or ["c4", "c5", "c5skew"]
     for w in which:
-        {"c4": c4, "c5": c5, "c5skew": c5skew}[w](rank, world, local)
+        {"c4": c4, "c5": c5, "c5skew": c5skew, "c2hist": c2hist}[w](rank, world, local)
     if world > 1:
         dist.destroy_process_group()
