@@ -368,6 +368,9 @@ def main():
     prof_ms = evp0.elapsed_time(evp1)
     kt = state.kernel_times()
     st._call("ws_set_timing", 0)
+    mbx = C.c_int64()
+    st._call("ws_get_mailbox_exchanges", C.byref(mbx))
+    mailbox_exchanges = int(mbx.value)   # > 0: the small exchanges of the sharded steps went through the mailboxes (0 on one GPU)
 
     # N > 1: one more step, NOT part of the headline, with the weights skewed ACROSS ranks (rank r's log-weights are
     # lowered by skew * r, so the low ranks hold almost all of the mass): most offspring of the following Resample
@@ -483,8 +486,10 @@ def main():
                        "particles_per_gpu": N, "planes": P_PLANES, "resampler": "stratified",
                        "parallelism": "single GPU" if world == 1 else
                        f"{world} ranks: ONE filter of {N * world} particles sharded by slot range; exact global stratified "
-                       "resampling (NCCL allgather of the weight masses; migrating offspring are written straight into the "
-                       "destination rank's planes over NVLink by the gather kernel, ncclSend/Recv as fallback)",
+                       "resampling; the step's small exchanges ((m,S,Q) triples, CDF masses, slot bounds, barrier) are stored by the "
+                       "kernels into peer-mapped mailboxes over NVLink (NCCL collectives as fallback); migrating offspring are written "
+                       "straight into the destination rank's planes over NVLink by the gather kernel (ncclSend/Recv as fallback)",
+                       "mailbox_exchanges": mailbox_exchanges,
                        "migrated_particles_per_step": migrated_per_step,
                        "l2": "working set 10.4 GB per GPU >> 126 MB L2 (no flush needed)",
                        "log_evidence": le, "log_evidence_after_warmup": le0},
