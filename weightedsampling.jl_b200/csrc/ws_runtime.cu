@@ -678,10 +678,10 @@ extern "C" int ws_destroy(ws_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (getenv("WSB200_TRACE") && c->phase_n > 0)
         fprintf(stderr, "[wsb200 rank %d] sharded resample host ms/step: cdf+allgather+sync %.3f | bounds+allgather+sync %.3f | "
-                        "search launch %.3f | exchange %.3f (steady %.3f) | local-anc %.3f  (n=%lld)\n",
+                        "search launch %.3f | exchange %.3f (steady %.3f) | local-anc %.3f | of the first: plane addresses %.3f | prepare %.3f  (n=%lld)\n",
                 c->rank, c->phase_ms[0] / c->phase_n, c->phase_ms[1] / c->phase_n, c->phase_ms[2] / c->phase_n,
                 c->phase_ms[3] / c->phase_n, c->phase_ms[5] / std::max<int64_t>(1, c->phase_n - 6), c->phase_ms[4] / c->phase_n,
-                (long long)c->phase_n);
+                c->phase_ms[6] / c->phase_n, c->phase_ms[7] / c->phase_n, (long long)c->phase_n);
     if (c->d_scratch2) cudaFree(c->d_scratch2);
     for (auto& sl : c->slabs) cudaFree(sl.base);  // planes and ancestor vectors
     cudaFree(c->logw);
@@ -2150,7 +2150,11 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     int64_t* const d_xmine = c->d_xmsg + xw * (size_t)R;
     S.bounds = reinterpret_cast<int32_t*>(d_xmine);   // word 0: (first, end) produced slot, written by ws_bounds_kernel
     std::vector<int64_t> xmine;
-    TRY(fill_xmsg(c, planes, xmine));
+    {
+        const double tf = t_now();
+        TRY(fill_xmsg(c, planes, xmine));
+        c->phase_ms[6] += t_now() - tf;
+    }
     CK(c, cudaMemcpyAsync(d_xmine + 1, xmine.data() + 1, sizeof(int64_t) * (xw - 1), cudaMemcpyHostToDevice, c->stream));
     TimedEvent te;
     const bool mbox = c->mbox_on && 2 * xw <= (size_t)c->mbox_cap;   // (the same on every rank: same planes, same capacity)
@@ -2511,7 +2515,9 @@ extern "C" int ws_resample(ws_ctx* c, ws_resample_info* info) {
                 TRY(resample_sharded(c, nullptr, step_stream));
             }
         } else {
+            const auto tp0 = std::chrono::steady_clock::now();
             TRY(prepare_resample_event(c));   // the half of begin_resample_event that moves planes (harmless if the step does not fire)
+            c->phase_ms[7] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
             TRY(resample_sharded(c, nullptr, step_stream, &fired));
         }
         const WsReduceOut r = *c->h_red;
