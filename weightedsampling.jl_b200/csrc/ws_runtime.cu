@@ -232,6 +232,8 @@ struct ws_ctx {
     void* d_gen = nullptr;            // scratch of the traced push: [chain pointers | plane table | rows per level]
     size_t gen_bytes = 0;
     int64_t traced_rows = 0;          // offspring pushed for planes that were behind (rows x planes), for the tests
+    int64_t trace_forced_planes = 0, trace_full_gathers = 0, trace_ipc_rounds = 0;  // WSB200_TRACE: planes brought up to date to free
+                                      // ancestor vectors / spare rows, events that had to bring everything up to date, IPC mapping rounds
     // planes and ancestor vectors are carved out of slabs: a cudaMalloc per new column costs milliseconds
     // (models that create a column per time step: x{t}), and nothing is ever freed before ws_destroy
     struct Slab {
@@ -677,11 +679,16 @@ extern "C" int ws_destroy(ws_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (getenv("WSB200_TRACE") && c->phase_n > 0)
-        fprintf(stderr, "[wsb200 rank %d] sharded resample host ms/step: cdf+allgather+sync %.3f | bounds+allgather+sync %.3f | "
-                        "search launch %.3f | exchange %.3f (steady %.3f) | local-anc %.3f | of the first: plane addresses %.3f | prepare %.3f  (n=%lld)\n",
+        fprintf(stderr, "[wsb200 rank %d] sharded resample host ms/step: cdf+exchanges+sync %.3f | (of the exchange: peer addresses %.3f) | "
+                        "search launch %.3f | exchange %.3f (steady %.3f) | (of the exchange: traced push %.3f) | of the first: plane addresses %.3f | prepare %.3f  (n=%lld)\n",
                 c->rank, c->phase_ms[0] / c->phase_n, c->phase_ms[1] / c->phase_n, c->phase_ms[2] / c->phase_n,
                 c->phase_ms[3] / c->phase_n, c->phase_ms[5] / std::max<int64_t>(1, c->phase_n - 6), c->phase_ms[4] / c->phase_n,
                 c->phase_ms[6] / c->phase_n, c->phase_ms[7] / c->phase_n, (long long)c->phase_n);
+    if (getenv("WSB200_TRACE") && c->phase_n > 0)
+        fprintf(stderr, "[wsb200 rank %d] genealogy: %lld planes brought up to date to free vectors / spare rows, %lld events gathered everything, "
+                        "%lld IPC mapping rounds, %zu slabs, traced values %lld\n",
+                c->rank, (long long)c->trace_forced_planes, (long long)c->trace_full_gathers, (long long)c->trace_ipc_rounds, c->slabs.size(),
+                (long long)c->traced_rows);
     if (c->d_scratch2) cudaFree(c->d_scratch2);
     for (auto& sl : c->slabs) cudaFree(sl.base);  // planes and ancestor vectors
     cudaFree(c->logw);
@@ -1672,6 +1679,7 @@ static int prepare_resample_event(ws_ctx* c) {
                 if (c->cols[ci].stale[k] && c->cols[ci].ep[k] == m) oldest.push_back(Plane{ci, k});
         *any = !oldest.empty();
         if (!*any) return (int)WS_OK;
+        c->trace_forced_planes += (int64_t)oldest.size();
         return materialize_planes(c, &oldest);
     };
     gc();
@@ -2080,6 +2088,7 @@ static int resolve_peer_planes(ws_ctx* c, const std::vector<int64_t>& all, size_
             }
         }
         rounds++;
+        c->trace_ipc_rounds++;
     }
     if (rounds > 0) {
         // a rank that could not map a peer's memory must not be written to blindly by the others either: everybody
@@ -2263,6 +2272,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
         // more offspring than the rings hold, or an exchange that cannot trace stale planes: bring every plane up to
         // date (the eager and the staged paths below assume that) and start the rings afresh
         TRY(materialize_planes(c));
+        c->trace_full_gathers++;
         for (auto& rg : c->spare_rings) rg.clear();
         ring_ok = ring_try();
         any_stale = false;
@@ -2297,7 +2307,9 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     std::vector<std::vector<double*>> peer;
     if (push) {
         bool usable = false;
+        const double tr0 = t_now();
         TRY(resolve_peer_planes(c, xall, xw, planes.size(), lazy, peer, &usable));
+        c->phase_ms[1] += t_now() - tr0;
         if (!usable) {
             push = false;
             c->push_exchange = false;  // ranks share a process, or no IPC / peer access: stay on ncclSend / ncclRecv (every rank decides alike)
@@ -2324,6 +2336,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
     // where rank q's offspring land on my side: lazily in the spare rows behind the FRONT planes
     // (lower ranks first), eagerly at their final slots in the BACK planes
     const std::vector<int64_t>& spare_pos = plan.spare_pos;
+    const double tt0 = t_now();
     if (push && any_stale) {
         // Planes that are behind (sharded genealogy; lazy by construction): the offspring produced for rank d are traced
         // through the retained ancestor vectors, once per offspring, and ONE kernel writes every plane — from the row
@@ -2377,6 +2390,7 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
             c->stats.kernel_launches += 2;
             c->traced_rows += send_cnt[d] * (int64_t)planes.size();
         }
+        c->phase_ms[4] += t_now() - tt0;
     }
     for (size_t p0 = 0; p0 < planes.size() && !(push && any_stale); p0 += BATCH) {
         const int nb = (int)std::min<size_t>(BATCH, planes.size() - p0);
