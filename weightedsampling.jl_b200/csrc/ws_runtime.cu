@@ -415,8 +415,16 @@ static int pool_alloc(ws_ctx* c, void** out, size_t bytes) {
             return WS_OK;
         }
     }
-    // 32 requests of this size per slab, between 8 MB and 256 MB (never less than the request itself)
-    const size_t slab = std::max(bytes, std::min((size_t)256 << 20, std::max((size_t)8 << 20, 32 * bytes)));
+    // 32 requests of this size per slab, between 8 MB and 256 MB (never less than the request itself).  Sharded states
+    // grow geometrically on top (a new slab is as large as all slabs so far, up to 8 GB): every new slab has to be
+    // mapped into the other ranks (cudaIpcGetMemHandle / cudaIpcOpenMemHandle + two host exchanges, ~3 ms a round,
+    // measured), and a model that creates a column per time step (x{t}) would otherwise pay that every few steps
+    size_t slab = std::max(bytes, std::min((size_t)256 << 20, std::max((size_t)8 << 20, 32 * bytes)));
+    if (c->nranks > 1) {
+        size_t total = 0;
+        for (auto& sl : c->slabs) total += sl.size;
+        slab = std::max(slab, std::min((size_t)8 << 30, total));
+    }
     char* base = nullptr;
     cudaError_t e = cudaMalloc(&base, slab);
     size_t got = slab;
