@@ -9,7 +9,10 @@
 //   ws_search_kernel      per-particle slot counts F(C) on the stratified / systematic grid, offspring
 //                         expansion (ws_expand_heavy_kernel for one-hot weights), ancestors out
 //   ws_gather_kernel      ancestor gather of all planes (resample!)
-//   small helpers         fill, exp_norm write, row gather
+//   sharded states        ws_finalize_mbox_kernel, ws_offsets_bounds_mbox_kernel, ws_barrier_mbox_kernel: the small exchanges
+//                         of a step made by the kernels through peer-mapped mailboxes (ws_mailbox.cuh);
+//                         ws_trace_rows_kernel, ws_push_traced_kernel: migrating offspring of planes that are behind
+//   small helpers         fill, exp_norm write, row gather, ancestor compose
 //
 // None of these is a dense contraction: they are HBM-bound streaming kernels (and FP64-ALU work
 // for exp / log / Philox), so the design rules are coalescing, enough bytes in flight per SM and

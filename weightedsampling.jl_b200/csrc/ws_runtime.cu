@@ -1476,16 +1476,16 @@ static int ensure_reduced(ws_ctx* c, bool for_resample = false, bool wait = true
         CK(c, ws_launch_finalize_mbox(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->d_all_msq, ties, M, c->stream));
         timed_end(c, te);
     } else {
-    timed_begin(c, KC_FINALIZE, te);
-    CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream, c->nranks > 1 ? nullptr : ties));
-    timed_end(c, te);
-    }
-    if (c->nranks > 1 && !c->mbox_on) {
-        // every rank reduces its shard; the (m, S, Q) triples are allgathered and combined in rank order
-        NCK(c, g_nccl.AllGather(c->d_red, c->d_all_msq, 3, WS_NCCL_FLOAT64, c->comm, c->stream));
         timed_begin(c, KC_FINALIZE, te);
-        CK(c, ws_launch_finalize_global(c->d_all_msq, c->nranks, c->n_global, c->ess_perc_min, c->d_red, c->stream, ties));
+        CK(c, ws_launch_finalize(c->d_partials, c->n_partials, c->n_global, c->ess_perc_min, c->d_red, c->stream, c->nranks > 1 ? nullptr : ties));
         timed_end(c, te);
+        if (c->nranks > 1) {
+            // every rank reduces its shard; the (m, S, Q) triples are allgathered and combined in rank order
+            NCK(c, g_nccl.AllGather(c->d_red, c->d_all_msq, 3, WS_NCCL_FLOAT64, c->comm, c->stream));
+            timed_begin(c, KC_FINALIZE, te);
+            CK(c, ws_launch_finalize_global(c->d_all_msq, c->nranks, c->n_global, c->ess_perc_min, c->d_red, c->stream, ties));
+            timed_end(c, te);
+        }
     }
     CK(c, cudaMemcpyAsync(c->h_red, c->d_red, sizeof(WsReduceOut), cudaMemcpyDeviceToHost, c->stream));
     c->stats.d2h_bytes += (int64_t)sizeof(WsReduceOut);
@@ -2186,16 +2186,16 @@ static int resample_sharded(ws_ctx* c, const double* d_ru, uint64_t stream_id, i
                                             reinterpret_cast<unsigned long long*>(c->d_xmsg), c->stream));
         timed_end(c, te);
     } else {
-    timed_begin(c, KC_SCAN, te);
-    CK(c, ws_launch_cdf(S, c->stream));
-    timed_end(c, te);
-    NCK(c, g_nccl.AllGather(c->d_all_tot + R, c->d_all_tot, 1, WS_NCCL_UINT64, c->comm, c->stream));
-    // the CDF offset of this rank (sum of the lower ranks' masses) is formed on the device from the
-    // allgathered masses, so the host does not have to wait for them
-    S.all_tot = c->d_all_tot;
-    S.rank = r;
-    CK(c, ws_launch_bounds(S, c->stream));
-    NCK(c, g_nccl.AllGather(d_xmine, c->d_xmsg, xw, WS_NCCL_UINT64, c->comm, c->stream));
+        timed_begin(c, KC_SCAN, te);
+        CK(c, ws_launch_cdf(S, c->stream));
+        timed_end(c, te);
+        NCK(c, g_nccl.AllGather(c->d_all_tot + R, c->d_all_tot, 1, WS_NCCL_UINT64, c->comm, c->stream));
+        // the CDF offset of this rank (sum of the lower ranks' masses) is formed on the device from the
+        // allgathered masses, so the host does not have to wait for them
+        S.all_tot = c->d_all_tot;
+        S.rank = r;
+        CK(c, ws_launch_bounds(S, c->stream));
+        NCK(c, g_nccl.AllGather(d_xmine, c->d_xmsg, xw, WS_NCCL_UINT64, c->comm, c->stream));
     }
     std::vector<int64_t> xall(xw * (size_t)R);
     CK(c, cudaMemcpyAsync(xall.data(), c->d_xmsg, sizeof(int64_t) * xw * (size_t)R, cudaMemcpyDeviceToHost, c->stream));
