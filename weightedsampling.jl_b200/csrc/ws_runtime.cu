@@ -1906,7 +1906,7 @@ static WsMailbox mbox_next(ws_ctx* c, int n_exchanges) {
     M.seq = c->mbox_seq + 1u;
     M.cap = c->mbox_cap;
     M.err = c->d_mbox_err;
-    M.timeout_ns = 20000000000ull;
+    M.timeout_ns = 60000000000ull;   // (a rank that is merely slow — a long host-side pause between two steps — must not fail the job)
     if (const char* e = getenv("WSB200_MAILBOX_TIMEOUT_MS")) M.timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
     c->mbox_seq += (uint32_t)n_exchanges;
     c->mbox_exchanges += n_exchanges;
