@@ -127,6 +127,22 @@ class Parser:
         params = []
         while not self.accept("op", ")"):
             params.append(self.expect("name")[1])
+            if self.peek() == ("op", ":") and self.t[self.i + 1] == ("op", ":"):
+                # `T::Int`, `data::Vector{Float64}`, `m::Base.Matrix`: a Julia type annotation on a model argument
+                # (test/macro_test.jl:12) restricts dispatch and nothing else — skipped
+                self.next()
+                self.next()
+                self.expect("name")
+                while self.accept("op", "."):
+                    self.expect("name")
+                if self.accept("op", "{"):
+                    nest = 1
+                    while nest > 0:
+                        k, v = self.next()
+                        if k == "eof":
+                            raise ModelSyntaxError("unterminated type parameters in the model signature")
+                        nest += (k, v) == ("op", "{")
+                        nest -= (k, v) == ("op", "}")
             self.accept("op", ",")
         self.depth -= 1
         body = self.parse_block()
