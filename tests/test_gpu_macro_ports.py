@@ -170,3 +170,47 @@ def test_macro_vectorized_ternary_and_short_circuit_or(ws):
     assert abs(st["smoke"].mean() - exact_smoke) < atol
     assert abs(st["lever"].mean() - exact_lever) < atol
     assert abs(st["alarm"].mean() - exact_alarm) < atol
+
+
+# ---- test/move_macro_test.jl ------------------------------------------------------------------------------------------
+LINREG_IF_RESAMPLED = '''
+@model function linear_regression(data)
+    α ~ Normal(0.0, 5.0)
+    β ~ Normal(0.0, 5.0)
+    for (x, y) in data
+        y => Normal(α + β * x, 0.5)
+        if resampled
+            (α, β) << RW(0.1)
+        end
+    end
+end
+'''  # move_macro_test.jl:40-50
+
+LINREG_DIVERSITY = '''
+@model function linear_regression(data)
+    α ~ Normal(0.0, 5.0)
+    β ~ Normal(0.0, 5.0)
+    for (x, y) in data
+        y => Normal(α + β * x, 0.5)
+        (α, β) << RW(0.1; diversity=0.9)
+    end
+end
+'''  # move_macro_test.jl:92-100
+
+
+@pytest.mark.parametrize("src", [LINREG_IF_RESAMPLED, LINREG_DIVERSITY], ids=["if_resampled", "diversity_kwarg"])
+def test_macro_linear_regression_with_mh_moves(ws, src):
+    """move_macro_test.jl:27-66 / 82-116: `<<` end to end — a static-parameter RW move gated by `if resampled`, and the
+    same move self-gated by the macro-level `diversity=` keyword; 10 points, N = 10 000, posterior means within 0.3 of
+    the true (α, β) = (-1, 2).  Run with run (run!), user kernels and proposals handed in by name."""
+    true_a, true_b, noise, n_points = -1.0, 2.0, 0.5, 10
+    rng = np.random.default_rng(42)
+    xs = np.linspace(0.0, 10.0, n_points)
+    ys = true_a + true_b * xs + noise * rng.standard_normal(n_points)
+    data = list(zip(xs.tolist(), ys.tolist()))
+    st = ws.SMCState(10_000, seed=42, device=0)
+    ws.run(ws.model(src)(data, kernels={"Normal": _normal_kernels(ws)["Normal"]}, proposals={"RW": ws.RW}), st)
+    w = ws.exp_norm(st)
+    est_a, est_b = float(np.sum(st["α"] * w)), float(np.sum(st["β"] * w))
+    assert abs(est_a - true_a) < 0.3 and abs(est_b - true_b) < 0.3, (est_a, est_b)
+    assert st.stats()["moves_run"] >= 1
