@@ -385,4 +385,72 @@ void hh_spare_ring(int64_t cap, const int64_t* ops, int n_ops, int64_t* out) {
         }
     }
 }
+// The mailbox protocol of csrc/ws_mailbox.cuh, restated for R host threads over std::atomic words (the device code uses
+// st/ld.relaxed.sys on peer-mapped memory; the layout, the word format and the double-buffering are the same):
+//   box[q] = rank q's mailbox, [2 parities][R sources][cap] words; a message word = (seq << 32) | 32 payload bits;
+//   exchange `seq`: every rank stores its words into every box at [(seq & 1) * R + me], then reads its own box until each
+//   word shows `seq`.
+// Every rank runs K exchanges back to back with random pauses between and inside them (skewed ranks); a rank checks every
+// payload it receives against what the sender must have sent for THAT exchange.  Returns the number of wrong payloads,
+// or -1 if a rank waited longer than `spin_limit` polls (a word was overwritten before it was read: the reader would
+// wait for ever) — both must be 0 / never for the argument "nobody can be two exchanges ahead of anybody" to hold.
+// `buffers` = 2 is the protocol; 1 (no double-buffering) is the negative control the test also runs, with `slow_rank`
+// reading slowly: the others finish the exchange (they only need its message, which it sent first), start the next one
+// and overwrite words it has not read yet.
+}  // extern "C"
+#include <atomic>
+#include <chrono>
+#include <memory>
+#include <thread>
+extern "C" {
+static inline uint32_t hh_mbox_payload(int src, uint32_t seq, int w) { return (uint32_t)(src * 2654435761u) ^ (seq * 40503u) ^ ((uint32_t)w * 97u + 13u); }
+int64_t hh_mailbox_protocol(int R, int K, int n_words, int buffers, uint64_t seed, int64_t spin_limit, int slow_rank) {
+    const int ll = 2 * n_words, cap = ll;
+    std::vector<std::unique_ptr<std::atomic<unsigned long long>[]>> box((size_t)R);
+    for (auto& b : box) {
+        b.reset(new std::atomic<unsigned long long>[(size_t)buffers * R * cap]);
+        for (size_t i = 0; i < (size_t)buffers * R * cap; ++i) b[i].store(0ull, std::memory_order_relaxed);
+    }
+    std::atomic<int64_t> wrong{0};
+    std::atomic<int> dead{0};
+    auto rank_fn = [&](int me) {
+        uint64_t s = seed * 6364136223846793005ull + (uint64_t)me * 1442695040888963407ull + 1ull;
+        auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+        auto pause = [&]() {
+            const int k = (int)(rnd() % 64);
+            if (k < 8) std::this_thread::yield();
+            else if (k == 63) std::this_thread::sleep_for(std::chrono::microseconds(rnd() % 200));
+        };
+        for (uint32_t seq = 1; seq <= (uint32_t)K && dead.load(std::memory_order_relaxed) == 0; ++seq) {
+            pause();
+            const size_t region = (size_t)(seq % (uint32_t)buffers) * (size_t)R;
+            for (int i = 0; i < ll * R; ++i) {
+                const int q = i / ll, w = i - q * ll;
+                box[(size_t)q][(region + (size_t)me) * cap + w].store(((unsigned long long)seq << 32) | hh_mbox_payload(me, seq, w),
+                                                                       std::memory_order_relaxed);
+                if ((i & 7) == 0) pause();
+            }
+            for (int i = 0; i < ll * R; ++i) {
+                const int q = i / ll, w = i - q * ll;
+                const std::atomic<unsigned long long>& cell = box[(size_t)me][(region + (size_t)q) * cap + w];
+                unsigned long long v = cell.load(std::memory_order_relaxed);
+                int64_t spins = 0;
+                while ((uint32_t)(v >> 32) != seq) {
+                    if (++spins > spin_limit || dead.load(std::memory_order_relaxed) != 0) {
+                        dead.store(1, std::memory_order_relaxed);
+                        return;
+                    }
+                    if ((spins & 63) == 0) std::this_thread::yield();
+                    v = cell.load(std::memory_order_relaxed);
+                }
+                if ((uint32_t)v != hh_mbox_payload(q, seq, w)) wrong.fetch_add(1, std::memory_order_relaxed);
+                if (me == slow_rank) std::this_thread::sleep_for(std::chrono::microseconds(20));   // a rank that reads slowly
+            }
+        }
+    };
+    std::vector<std::thread> th;
+    for (int r = 0; r < R; ++r) th.emplace_back(rank_fn, r);
+    for (auto& t : th) t.join();
+    return dead.load() != 0 ? -1 : wrong.load();
+}
 }  // extern "C"

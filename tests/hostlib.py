@@ -18,7 +18,7 @@ def lib():
         deps = [SRC] + [os.path.join(HERE, "..", "weightedsampling.jl_b200", "csrc", f)
                         for f in ("ws_lowering.h", "ws_vm.cuh", "ws_math.cuh", "ws_exchange.h", "ws_vm_sl.cuh")]
         if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
-            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", SO, SRC],
+            subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-o", SO, SRC],
                            check=True)
         L = C.CDLL(SO)
         L.hh_new.restype = C.c_void_p

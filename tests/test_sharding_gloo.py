@@ -182,3 +182,21 @@ def test_spare_ring_never_hands_out_a_row_twice():
                 live = {e: v for e, v in live.items() if e > x}
                 assert o == len(live)
         assert failed < len(ops)
+
+
+def test_mailbox_protocol_double_buffering_holds_under_skew():
+    """The exchange protocol of csrc/ws_mailbox.cuh (sequence-tagged 8-byte words, mailboxes double-buffered on the parity
+    of the sequence number) restated over host threads (tests/host/harness.cpp: hh_mailbox_protocol): R ranks run
+    hundreds of all-to-all exchanges back to back with random pauses, one of them reading slowly — every payload must
+    be the one its sender wrote for THAT exchange and nobody may wait for ever.  Negative control: with one buffer the
+    fast ranks overwrite words the slow reader has not consumed yet, and it waits for a sequence number that is gone."""
+    import ctypes as C
+    import hostlib
+    L = hostlib.lib()
+    L.hh_mailbox_protocol.restype = C.c_int64
+    L.hh_mailbox_protocol.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_int]
+    for R, n_words, slow in ((2, 3, -1), (2, 31, 0), (4, 3, 1), (8, 1, 3), (8, 5, -1)):
+        for seed in (1, 2, 3):
+            assert L.hh_mailbox_protocol(R, 300, n_words, 2, seed, 50_000_000, slow) == 0, (R, n_words, slow, seed)
+    # one buffer: the slow reader is overtaken (detected as a wait beyond the limit, or — never on an atomic word — a torn payload)
+    assert any(L.hh_mailbox_protocol(4, 300, 4, 1, seed, 200_000, 0) != 0 for seed in (1, 2, 3))
