@@ -98,3 +98,48 @@ def test_expression_lowering_rejects_non_device_values():
         ws.core.resolve_kernel("Wishart")
     with pytest.raises(ws.UnsupportedModelError):
         ws.Move(["x"], lambda state, targets: None)
+
+
+def test_model_signature_is_a_julia_signature():
+    """`@model function name(args...; kwargs...)` splices both parameter lists into the generated function verbatim
+    (rewrites.jl:776-806), so type annotations (test/macro_test.jl:12 `T::Int`), optional positional arguments, keyword
+    arguments with defaults (evaluated left to right with the earlier parameters in scope) and required keywords work
+    as in Julia; `kernels` / `proposals` stay the two extra keywords of every model."""
+    src = '''
+    @model function f(data::Vector{Float64}, a=0.5, b::Float64=2a; q=a + b, T::Int)
+        x ~ Normal(0.0, q)
+        for t in 1:T
+            x ~ Normal(a * x, b)
+        end
+    end
+    '''
+    m = ws.model(src)
+    tree = m([1.0], T=2)
+    assert [type(s).__name__ for s in tree.steps] == ["Sample", "Resample", "Loop"]
+    assert len(list(tree.steps[2].collfn(None))) == 2
+    assert len(list(m([1.0], 0.1, 0.2, T=3, q=1.0).steps[2].collfn(None))) == 3
+    with pytest.raises(TypeError):
+        m([1.0])                       # required keyword T
+    with pytest.raises(TypeError):
+        m([1.0], T=1, z=3)             # unknown keyword
+    with pytest.raises(TypeError):
+        m(T=1)                         # required positional argument
+    with pytest.raises(TypeError):
+        m([1.0], 1, 2, 3, T=1)         # too many positional arguments
+
+
+def test_loop_variables_destructure_as_julia_tuples():
+    """`for (i, (x, y)) in enumerate(data)`: the loop variable is the body closure's single destructuring argument
+    (rewrites.jl:652-664), so patterns nest."""
+    src = '''
+    @model function g(data)
+        a ~ Normal(0.0, 1.0)
+        for (i, (x, y)) in enumerate(data)
+            z{i} .= a * x + y
+        end
+    end
+    '''
+    tree = ws.model(src)([(1.0, 2.0), (3.0, 4.0)])
+    loop = tree.steps[2]
+    bodies = [loop.bodyfn(el) for el in loop.collfn(None)]
+    assert [b.steps[0].lhs for b in bodies] == ["z_1", "z_2"]

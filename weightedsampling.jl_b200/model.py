@@ -23,7 +23,9 @@ Supported statements (rewrites.jl:7-36): ``x .= e``, ``x ~ f(a...)``, ``_ ~ f(a.
 ``x << q(a...; diversity=d)``, ``(x, y) << q(...)``, build-time ``=`` / ``+=`` ..., ``for``, ``if`` (no
 else; ``resampled`` allowed), ``Resample()``; dynamic families ``x{e}`` (column ``x_e``), accessors
 ``x[e]`` on vector-valued columns.  A ``Resample()`` is auto-inserted after every ``~`` and ``=>``
-(rewrites.jl:707-711).
+(rewrites.jl:707-711).  The signature is a Julia signature (rewrites.jl:776-806): ``function f(a, b::T=default;
+kw=default, required_kw)`` — annotations are skipped, defaults are build-time expressions evaluated left to right —
+and loop variables destructure as nested tuples (``for (i, (x, y)) in enumerate(data)``, rewrites.jl:652-664).
 """
 from __future__ import annotations
 
@@ -124,9 +126,18 @@ class Parser:
         name = self.expect("name")[1]
         self.expect("op", "(")
         self.depth += 1
-        params = []
+        # `function name(args...; kwargs...)` (rewrites.jl:776-787 splices both lists into the generated function
+        # verbatim): positional and keyword parameters, each with an optional type annotation and default value
+        params, defaults, kwonly = [], {}, set()
+        after_semicolon = False
         while not self.accept("op", ")"):
-            params.append(self.expect("name")[1])
+            if self.accept("op", ";"):
+                after_semicolon = True
+                continue
+            pname = self.expect("name")[1]
+            params.append(pname)
+            if after_semicolon:
+                kwonly.add(pname)
             if self.peek() == ("op", ":") and self.t[self.i + 1] == ("op", ":"):
                 # `T::Int`, `data::Vector{Float64}`, `m::Base.Matrix`: a Julia type annotation on a model argument
                 # (test/macro_test.jl:12) restricts dispatch and nothing else — skipped
@@ -143,7 +154,10 @@ class Parser:
                             raise ModelSyntaxError("unterminated type parameters in the model signature")
                         nest += (k, v) == ("op", "{")
                         nest -= (k, v) == ("op", "}")
+            if self.accept("op", "="):
+                defaults[pname] = self.parse_expr()
             self.accept("op", ",")
+        self.signature = (defaults, kwonly)
         self.depth -= 1
         body = self.parse_block()
         self.expect("name", "end")
@@ -189,11 +203,13 @@ class Parser:
         return ("expr", lhs)
 
     def parse_pattern(self):
+        # `x`, `(x, y)`, `(i, (x, y))`: the loop variable becomes the single destructuring argument of the body
+        # closure (rewrites.jl:652-664), so patterns nest as Julia's do
         if self.accept("op", "("):
             self.depth += 1
             names = []
             while not self.accept("op", ")"):
-                names.append(self.expect("name")[1])
+                names.append(self.parse_pattern())
                 self.accept("op", ",")
             self.depth -= 1
             return names
@@ -497,13 +513,32 @@ def _check_expr(ast, pv, fam, stmt):
                 _check_expr(y, pv, fam, stmt)
 
 
+def _pattern_names(pat):
+    if isinstance(pat, list):
+        return [n for p in pat for n in _pattern_names(p)]
+    return [pat]
+
+
+def _destructure(pat, x, out):
+    """bind the loop element `x` to the (possibly nested) pattern, as Julia's tuple destructuring does"""
+    if isinstance(pat, list):
+        xs = tuple(x)
+        if len(xs) < len(pat):
+            raise ValueError(f"cannot destructure {len(xs)} value(s) into {len(pat)} loop variables")
+        for p, v in zip(pat, xs):
+            _destructure(p, v, out)
+    else:
+        out[pat] = x
+    return out
+
+
 def _static_check(stmts, pv, fam, locals_):
     for s in stmts:
         if s[0] == "for":
             _, pat, it, body = s
             if _contains_particle(it, pv):
                 raise ModelSyntaxError("a `for` collection must not depend on a particle variable")
-            loc = set(locals_) | (set(pat) if isinstance(pat, list) else {pat})
+            loc = set(locals_) | set(_pattern_names(pat))
             _static_check(body, pv, fam, loc)
         elif s[0] == "if":
             _, cond, body = s
@@ -813,10 +848,7 @@ def _build(stmts, env, kernels, proposals):
             coll = ev(it, env)
 
             def bodyfn(x, pat=pat, body=body):
-                if isinstance(pat, list):
-                    vals = dict(zip(pat, x))
-                else:
-                    vals = {pat: x}
+                vals = _destructure(pat, x, {})
                 return core.Sequence(*_build(body, env.child(vals), kernels, proposals))
             steps.append(core.Loop(lambda state, coll=coll: coll, bodyfn))
         elif s[0] == "if":
@@ -897,14 +929,30 @@ def model(src, particle_vars=(), scope=None):
     continuation model applied to an existing SMCState, as benchmarks/ssm/bench_single_update does).
     ``scope`` supplies the names the Julia source takes from its enclosing module: helper functions written
     over particle expressions (``oscillator(t, A, ω, γ, ϕ)``) and user-defined ``WeightedKernel``s."""
-    name, params, body = Parser(tokenize(src)).parse_model()
+    parser = Parser(tokenize(src))
+    name, params, body = parser.parse_model()
+    defaults, kwonly = parser.signature
+    positional = [p for p in params if p not in kwonly]
+    n_required = sum(1 for p in positional if p not in defaults)
     pv, fam = set(particle_vars), set()
     _static_check(body, pv, fam, set(params))
 
-    def build(*args, kernels=None, proposals=None):
-        if len(args) != len(params):
-            raise TypeError(f"{name}() takes {len(params)} positional arguments but {len(args)} were given")
-        env = _Env(dict(zip(params, args)), pv, fam, parent=_Env(dict(scope or {}), pv, fam))
+    def build(*args, kernels=None, proposals=None, **kwargs):
+        if not (n_required <= len(args) <= len(positional)):
+            takes = str(len(positional)) if n_required == len(positional) else f"from {n_required} to {len(positional)}"
+            raise TypeError(f"{name}() takes {takes} positional arguments but {len(args)} were given")
+        unknown = set(kwargs) - kwonly
+        if unknown:
+            raise TypeError(f"{name}() got unexpected keyword argument(s) {sorted(unknown)}")
+        env = _Env(dict(zip(positional, args)), pv, fam, parent=_Env(dict(scope or {}), pv, fam))
+        # defaults are evaluated left to right with the earlier parameters in scope, as Julia does
+        for p in params:
+            if p in kwonly and p in kwargs:
+                env.values[p] = kwargs[p]
+            elif p not in env.values:
+                if p not in defaults:
+                    raise TypeError(f"{name}(): keyword argument `{p}` not assigned")   # Julia: UndefKeywordError
+                env.values[p] = ev(defaults[p], env)
         seq = core.Sequence(*_build(body, env, kernels, proposals))
         seq._has_moves = has_moves  # lets run() skip score-tape recording for move-free models
         return seq
