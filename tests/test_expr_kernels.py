@@ -353,3 +353,113 @@ def test_untraceable_closures_are_rejected_not_run_on_the_host():
         ws.Sample("y", "Wishart", (2.0, 1.0)).apply(hs)      # in the reference's table, outside the device-op set
     with pytest.raises(RuntimeError):
         ws.Observe(ws.col("x") + ws.randn(), "Normal", (0.0, 1.0)).apply(hs)  # variates outside a sampler
+
+
+# ---- Julia Base scalar functions without a micro-op of their own (compositions in expr.py) -----------------------------
+def _julia_round(x):
+    return np.round(x)            # NumPy rounds half to even, as Julia's RoundNearest does
+
+
+_BASE_FUNCTIONS = [
+    # (model expression in x [, y], NumPy restatement of JULIA's function, rtol)
+    ("sign(x)", lambda x, y: np.where(x == 0, x, np.sign(x)), 0.0),          # Julia: sign(-0.0) = -0.0
+    ("ceil(x)", lambda x, y: np.ceil(x), 0.0),
+    ("trunc(x)", lambda x, y: np.trunc(x), 0.0),
+    ("round(x)", lambda x, y: _julia_round(x), 0.0),
+    ("floor(Int, x) + round(Int, x)", lambda x, y: np.floor(x) + _julia_round(x), 0.0),
+    ("clamp(x, -1.5, 2.0)", lambda x, y: np.where(x > 2.0, 2.0, np.where(x < -1.5, -1.5, x)), 0.0),
+    ("isnan(x) ? 1.0 : 0.0", lambda x, y: np.isnan(x).astype(float), 0.0),
+    ("isinf(x) ? 1.0 : 0.0", lambda x, y: np.isinf(x).astype(float), 0.0),
+    ("isfinite(x) ? 1.0 : 0.0", lambda x, y: np.isfinite(x).astype(float), 0.0),
+    ("log2(abs(x))", lambda x, y: np.log2(np.abs(x)), 4e-16),
+    ("log10(abs(x))", lambda x, y: np.log10(np.abs(x)), 4e-16),
+    ("log(3, abs(x))", lambda x, y: np.log(np.abs(x)) / np.log(3.0), 4e-16),
+    ("exp2(x / 8)", lambda x, y: np.exp2(x / 8), 1e-14),
+    ("exp10(x / 8)", lambda x, y: 10.0 ** (x / 8), 1e-14),
+    ("sinh(x / 4)", lambda x, y: np.sinh(x / 4), 1e-14),
+    ("cosh(x / 4)", lambda x, y: np.cosh(x / 4), 1e-14),
+    ("asin(clamp(x / 8, -1, 1))", lambda x, y: np.arcsin(np.clip(x / 8, -1, 1)), 1e-14),
+    ("acos(clamp(x / 8, -1, 1))", lambda x, y: np.arccos(np.clip(x / 8, -1, 1)), 1e-14),
+    ("atan(y, x)", lambda x, y: np.arctan2(y, x), 1e-14),
+    ("hypot(x, y)", lambda x, y: np.hypot(x, y), 1e-15),
+    ("cbrt(x)", lambda x, y: np.cbrt(x), 5e-14),
+    ("inv(x)", lambda x, y: 1.0 / x, 0.0),
+    ("x ÷ 3", lambda x, y: np.trunc(x / 3), 0.0),
+    ("x % 3", lambda x, y: x - 3 * np.trunc(x / 3), 0.0),
+    ("mod(x, 3)", lambda x, y: x - 3 * np.floor(x / 3), 0.0),
+    ("rem(x, y)", lambda x, y: x - y * np.trunc(x / y), 0.0),
+    ("fld(x, 3) + cld(x, 3) + div(x, 3)", lambda x, y: np.floor(x / 3) + np.ceil(x / 3) + np.trunc(x / 3), 0.0),
+    ("max(x, y, 0.5) - min(x, y, -0.5, 0.25)", lambda x, y: np.maximum(np.maximum(x, y), 0.5) - np.minimum(np.minimum(x, y), -0.5), 0.0),
+    ("float(x) + Float64(y) + one(x) + zero(y)", lambda x, y: x + y + 1.0, 0.0),
+    ("√(abs(x)) + √2", lambda x, y: np.sqrt(np.abs(x)) + math.sqrt(2.0), 0.0),
+    ("iszero(x) ? 1.0 : (isone(x) ? 2.0 : 0.0)", lambda x, y: np.where(x == 0, 1.0, np.where(x == 1, 2.0, 0.0)), 0.0),
+]
+
+
+@pytest.mark.parametrize("src,want,rtol", _BASE_FUNCTIONS, ids=[c[0] for c in _BASE_FUNCTIONS])
+def test_julia_base_functions_on_particle_values(src, want, rtol):
+    """`vectorize` broadcasts any Julia function over particle columns (rewrites.jl:150-163); the device-op set is
+    closed, so the common scalar Base functions are compositions of its micro-ops.  Run through the product's lowering
+    and the micro-op interpreter (CPU harness) on ordinary values, ties, signed zeros, infinities and NaN."""
+    rng = np.random.default_rng(7)
+    special = np.array([0.0, -0.0, 0.5, -0.5, 1.5, 2.5, -1.5, -2.5, 3.5, 1.0, -1.0, 2.0, 3.0, -3.0, 1e-300, -1e300, 4503599627370497.0,
+                        np.inf, -np.inf, np.nan])
+    x = np.concatenate([special, 4.0 * rng.standard_normal(400)])
+    y = np.concatenate([special[::-1], 2.0 * rng.standard_normal(400)])
+    hs = HostState(x.size)
+    hs.store.setcol("x", x)
+    hs.store.setcol("y", y)
+    m = ws.model(f"@model function f()\n    r .= {src}\nend", particle_vars=("x", "y"))
+    ws.run(m(), hs) if hasattr(hs, "root") else m().apply(hs)
+    got = hs.store.getcol("r")
+    with np.errstate(all="ignore"):
+        exp = want(x, y)
+    both_nan = np.isnan(got) & np.isnan(exp)
+    if rtol == 0.0:
+        same = (got == exp) | both_nan
+        if src.startswith("max("):
+            same |= np.isnan(x) | np.isnan(y)     # min / max are the device's (fmin / fmax: a NaN operand is ignored; Julia propagates it)
+        if src.startswith(("x % 3", "mod(", "rem(", "x ÷", "fld(")):
+            same |= ~np.isfinite(x) | ~np.isfinite(y) | (np.abs(x) > 1e15)    # inf / inf forms: NaN either way, checked above
+        assert same.all(), (src, x[~same][:5], y[~same][:5], got[~same][:5], exp[~same][:5])
+        if src in ("sign(x)", "ceil(x)", "trunc(x)", "round(x)"):
+            z = (exp == 0) & ~both_nan & ((x != 0) | (src != "round(x)"))     # (round(-0.0) gives +0.0: documented)
+            assert (np.signbit(got[z]) == np.signbit(exp[z])).all(), src   # signed zeros as Julia's
+    else:
+        fin = np.isfinite(exp)
+        edge = np.zeros(x.size, dtype=bool)
+        if src.startswith(("atan(y, x)", "hypot(")):
+            # documented conventions of the short compositions: signed zeros on the axes, both arguments infinite
+            edge = (x == 0) | (y == 0) | (np.isinf(x) & (np.isinf(y) | np.isnan(y))) | (np.isinf(y) & np.isnan(x))
+            if src.startswith("atan"):
+                z = (x == 0) & (y != 0) & ~np.isnan(y)
+                assert np.array_equal(got[z], np.sign(y[z]) * np.pi / 2)
+                assert (got[(x == 0) & (y == 0)] == 0).all()
+        np.testing.assert_allclose(got[fin & ~edge], exp[fin & ~edge], rtol=rtol, atol=1e-300)
+        ok = (got[~fin] == exp[~fin]) | both_nan[~fin] | edge[~fin]
+        assert ok.all(), (src, x[~fin][~ok], y[~fin][~ok], got[~fin][~ok], exp[~fin][~ok])
+
+
+def test_compositions_refuse_fresh_variates_and_local_functions_trace():
+    """A composition mentions its argument more than once; with a fresh variate inside, every mention would be another
+    draw — refused.  Local functions and anonymous functions of a model body are build-time values (rewrites.jl:717-733)
+    and trace into the device expression when called on particle variables; `a[end]`, tuple assignment and Julia's
+    truncated `÷` / `%` on build-time integers."""
+    with pytest.raises(ws.UnsupportedModelError):
+        ws.expr.clamp(ws.randn(), -1.0, 1.0)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(64)
+    hs = HostState(64)
+    hs.store.setcol("x", x)
+    m = ws.model('''
+    @model function f(data)
+        k = 3.0
+        g(u) = k * u + data[end]
+        h = (u, v) -> u * v - data[end - 1]
+        a, b = -7 ÷ 2, -7 % 2
+        (c, d) = (mod(-7, 2), length(data))
+        r .= g(x) + h(x, 2.0) + a + b + c + d
+    end
+    ''', particle_vars=("x",))
+    m([10.0, 20.0, 30.0]).apply(hs)
+    np.testing.assert_allclose(hs.store.getcol("r"), (3.0 * x + 30.0) + (2.0 * x - 20.0) + (-3) + (-1) + 1 + 3, rtol=1e-14)

@@ -206,6 +206,233 @@ maximum = _fn2(L.TOK_MAX, max)
 
 
 # ------------------------------------------------------------------------------------------------
+# Julia Base functions that have no micro-op of their own: compositions of the ones above, written to give Julia's
+# result (signed zeros, NaN propagation, ties) on particle expressions and plain Python arithmetic on build-time numbers.
+# (`vectorize` broadcasts ANY Julia function over particle columns, rewrites.jl:150-163; the device-op set is closed,
+# so the common scalar ones are spelled out here.)
+# ------------------------------------------------------------------------------------------------
+_LN2, _LN10 = math.log(2.0), math.log(10.0)
+
+
+def _is_expr(*xs):
+    return any(isinstance(x, Expr) for x in xs)
+
+
+def _has_draw(e):
+    if isinstance(e, (Rand, RandP)):
+        return True
+    return isinstance(e, Expr) and any(_has_draw(v) for v in vars(e).values() if isinstance(v, (Expr, list, tuple))) or \
+        (isinstance(e, (list, tuple)) and any(_has_draw(v) for v in e))
+
+
+def _reuses_args(fn):
+    """These compositions mention an argument more than once; an expression is a TREE, so a fresh variate inside it
+    (`randn()` in a sampler closure) would be drawn once per mention.  Refuse instead of sampling wrongly."""
+    def f(*a):
+        if any(_has_draw(x) for x in a):
+            raise _unsupported(f"{fn.__name__}() of an expression that contains a fresh variate: assign the draw to a "
+                               "particle variable first (the composition would evaluate it more than once)")
+        return fn(*a)
+    f.__name__ = fn.__name__
+    f.__doc__ = fn.__doc__
+    return f
+
+
+@_reuses_args
+def isnan(x):
+    return ~(x.eq(x)) if isinstance(x, Expr) else math.isnan(x)
+
+
+def isinf(x):
+    return abs(x).eq(math.inf) if isinstance(x, Expr) else math.isinf(x)
+
+
+def isfinite(x):
+    return (abs(x) < math.inf) if isinstance(x, Expr) else math.isfinite(x)
+
+
+@_reuses_args
+def sign(x):
+    if isinstance(x, Expr):
+        return where(x > 0.0, 1.0, where(x < 0.0, -1.0, x))   # sign(±0.0) = ±0.0, sign(NaN) = NaN
+    return math.copysign(1.0, x) if x != 0 and not math.isnan(x) else x
+
+
+def ceil(x):
+    return -floor(-x) if isinstance(x, Expr) else float(math.ceil(x))
+
+
+@_reuses_args
+def trunc(x):
+    if isinstance(x, Expr):
+        return where(x < 0.0, -floor(-x), floor(x))
+    return float(math.trunc(x))
+
+
+@_reuses_args
+def round_even(x):
+    """Julia's `round(x)`: to the nearest integer, ties to even — by the classic (|x| + 2^52) - 2^52, which the
+    round-to-nearest-even addition itself performs exactly for |x| < 2^52 (larger values are integers already).
+    (An expression is a tree, so every reuse of a sub-expression is a copy: the compositions are kept short — a pass
+    holds 96 micro-ops.)"""
+    if isinstance(x, Expr):
+        # (the min is there for the lowering, which folds x + c1 - c2 into x + (c1 - c2): it must not see one linear chain)
+        t = minimum(abs(x) + 4503599627370496.0, math.inf) - 4503599627370496.0
+        # the sign goes back on by a product with ±1 (a negation would be folded into the linear chain and lose -0.0):
+        # round(-0.3) = -0.0 as Julia's (round(-0.0) gives +0.0)
+        return where(abs(x) < 4503599627370496.0, t * where(x < 0.0, -1.0, 1.0), x)
+    return float(round(x))   # Python rounds ties to even, too
+
+
+@_reuses_args
+def clamp(x, lo, hi):
+    if _is_expr(x, lo, hi):
+        x, lo, hi = wrap(x), wrap(lo), wrap(hi)
+        return where(x > hi, hi, where(x < lo, lo, x))   # Base.clamp: ifelse(x > hi, hi, ifelse(x < lo, lo, x))
+    return hi if x > hi else (lo if x < lo else x)
+
+
+def log2(x):
+    return log(x) / _LN2 if isinstance(x, Expr) else math.log2(x)
+
+
+def log10(x):
+    return log(x) / _LN10 if isinstance(x, Expr) else math.log10(x)
+
+
+def logb(*a):
+    """`log(x)` or `log(b, x)`"""
+    if len(a) == 1:
+        return log(a[0])
+    b, x = a
+    return log(x) / log(b)
+
+
+def exp2(x):
+    return exp(x * _LN2) if isinstance(x, Expr) else 2.0 ** x
+
+
+def exp10(x):
+    return exp(x * _LN10) if isinstance(x, Expr) else 10.0 ** x
+
+
+@_reuses_args
+def sinh(x):
+    return (expm1(x) - expm1(-x)) * 0.5 if isinstance(x, Expr) else math.sinh(x)
+
+
+@_reuses_args
+def cosh(x):
+    return (exp(x) + exp(-x)) * 0.5 if isinstance(x, Expr) else math.cosh(x)
+
+
+@_reuses_args
+def asin(x):
+    return atan(x / sqrt((1.0 - x) * (1.0 + x))) if isinstance(x, Expr) else math.asin(x)
+
+
+@_reuses_args
+def acos(x):
+    return 2.0 * atan(sqrt((1.0 - x) / (1.0 + x))) if isinstance(x, Expr) else math.acos(x)
+
+
+@_reuses_args
+def atan2(*a):
+    """`atan(x)` or the two-argument `atan(y, x)`"""
+    if len(a) == 1:
+        return atan(a[0])
+    y, x = a
+    if not _is_expr(y, x):
+        return math.atan2(y, x)
+    # atan(y / x) moved into the right quadrant.  Kept short (see round_even): exactly-zero arguments follow the unsigned
+    # convention (atan(0, 0) = 0, atan(y, ±0.0) = ±π/2 by the sign of y, atan(-0.0, x < 0) = +π) and atan(±Inf, ±Inf) is
+    # NaN, where Julia distinguishes signed zeros and returns ±π/4, ±3π/4.
+    y, x = wrap(y), wrap(x)
+    on_axis = where(y > 0.0, math.pi / 2, where(y < 0.0, -math.pi / 2, y * 0.0))
+    return where(x.eq(0.0), on_axis, atan(y / x) + where(x < 0.0, where(y < 0.0, -math.pi, math.pi), 0.0))
+
+
+@_reuses_args
+def hypot(x, y):
+    """sqrt(x^2 + y^2) without overflow of the squares: m sqrt(1 + (n / m)^2), m = max(|x|, |y|), n = min(|x|, |y|)
+    (hypot(Inf, Inf) and hypot(Inf, NaN) come out NaN; Julia returns Inf)."""
+    if not _is_expr(x, y):
+        return math.hypot(x, y)
+    ax, ay = abs(wrap(x)), abs(wrap(y))
+    m = maximum(ax, ay)
+    return where(m.eq(0.0), 0.0, m * sqrt(1.0 + abs2(minimum(ax, ay) / m)))
+
+
+@_reuses_args
+def cbrt(x):
+    return sign(x) * abs(x) ** (1.0 / 3.0) if isinstance(x, Expr) else math.copysign(abs(x) ** (1.0 / 3.0), x)
+
+
+def inv(x):
+    return 1.0 / x
+
+
+def fld(x, y):
+    return floor(x / y) if _is_expr(x, y) else float(math.floor(x / y))
+
+
+def cld(x, y):
+    return ceil(x / y)
+
+
+def div(x, y):
+    """Julia's `÷` / `div`: the quotient truncated towards zero."""
+    return trunc(x / y) if _is_expr(x, y) else (float(math.trunc(x / y)) if isinstance(x, float) or isinstance(y, float)
+                                                else int(math.trunc(x / y)))
+
+
+@_reuses_args
+def rem(x, y):
+    """Julia's `%` / `rem`: remainder with the sign of the dividend (x - y trunc(x / y); on particle values the
+    quotient is formed in floating point, which is exact while |x / y| < 2^53)."""
+    if _is_expr(x, y):
+        x, y = wrap(x), wrap(y)
+        return x - y * trunc(x / y)
+    return math.fmod(x, y) if isinstance(x, float) or isinstance(y, float) else int(math.fmod(x, y))
+
+
+@_reuses_args
+def mod(x, y):
+    """Julia's `mod`: remainder with the sign of the divisor (x - y floor(x / y))."""
+    if _is_expr(x, y):
+        x, y = wrap(x), wrap(y)
+        return x - y * floor(x / y)
+    return x % y   # Python's % is the floored one
+
+
+def nmin(*a):
+    out = a[0]
+    for b in a[1:]:
+        out = minimum(out, b)
+    return out
+
+
+def nmax(*a):
+    out = a[0]
+    for b in a[1:]:
+        out = maximum(out, b)
+    return out
+
+
+def to_float(x):
+    return x if isinstance(x, Expr) else float(x)
+
+
+def _int_first(fn):
+    """`floor(Int, x)` / `round(Int, x)`: the type argument is dropped — every particle value is a Float64 plane"""
+    def f(*a):
+        if len(a) == 2 and a[0] in (int, float):
+            return fn(a[1])
+        return fn(*a)
+    return f
+
+
+# ------------------------------------------------------------------------------------------------
 # lowering to postfix tokens
 # ------------------------------------------------------------------------------------------------
 class Tokens:

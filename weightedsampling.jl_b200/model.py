@@ -26,6 +26,12 @@ else; ``resampled`` allowed), ``Resample()``; dynamic families ``x{e}`` (column 
 (rewrites.jl:707-711).  The signature is a Julia signature (rewrites.jl:776-806): ``function f(a, b::T=default;
 kw=default, required_kw)`` — annotations are skipped, defaults are build-time expressions evaluated left to right —
 and loop variables destructure as nested tuples (``for (i, (x, y)) in enumerate(data)``, rewrites.jl:652-664).
+Build-time statements (rewrites.jl:717-733) include tuple assignment (``a, b = 1.0, 2.0``), local functions
+(``g(u) = 2u + 1``) and anonymous functions (``h = (u, v) -> u * v``), which trace into the device expression when
+called on particle variables; ``a[end]``, ``√x``, and Julia's truncated ``÷`` / ``%``.  Scalar Base functions without a
+micro-op of their own (``sign clamp ceil trunc round isnan isinf isfinite log2 log10 log(b, x) exp2 exp10 sinh cosh
+asin acos atan(y, x) hypot cbrt inv fld cld div rem mod``, n-ary ``min`` / ``max``, ``floor(Int, x)``) are compositions
+of the micro-ops (``expr.py``; their conventions at signed zeros / infinities are stated there).
 """
 from __future__ import annotations
 
@@ -57,7 +63,7 @@ _TOKEN_RE = re.compile(r"""
   | (?P<nl>\n)
   | (?P<num>(?:\d[\d_]*\.?\d*(?:[eE][+-]?\d+)?|\.\d+(?:[eE][+-]?\d+)?))
   | (?P<name>@?[^\W\d][\w!′]*)
-  | (?P<op>\.\+=|\.-=|\.\*=|\./=|\.=|=>|<<|==|!=|<=|>=|&&|\|\||\+=|-=|\*=|/=|\.\+|\.-|\.\*|\./|\.\^|->|[-+*/^%÷=<>!~:,;()\[\]{}.'?&|])
+  | (?P<op>\.\+=|\.-=|\.\*=|\./=|\.=|=>|<<|==|!=|<=|>=|&&|\|\||\+=|-=|\*=|/=|\.\+|\.-|\.\*|\./|\.\^|->|[-+*/^%÷√=<>!~:,;()\[\]{}.'?&|])
 """, re.X | re.S)
 
 
@@ -87,6 +93,7 @@ class Parser:
         self.t, self.i = toks, 0
         self.depth = 0  # bracket depth: newlines are ignored inside brackets
         self.no_range = 0  # > 0 while parsing the middle operand of a ternary (`:` belongs to the ternary)
+        self.in_index = 0  # > 0 inside `a[...]`: `end` is the last index there, not a block terminator
 
     def peek(self, skip_nl=False):
         j = self.i
@@ -195,10 +202,26 @@ class Parser:
             self.expect("name", "end")
             return ("if", cond, body)
         lhs = self.parse_expr()
+        if self.peek() == ("op", ","):
+            # `a, b = 1.0, 2.0`: a tuple on either side of a plain `=` may be written without parentheses
+            items = [lhs]
+            while self.accept("op", ","):
+                items.append(self.parse_expr())
+            lhs = ("tuple", items)
+            if self.peek() != ("op", "="):
+                raise ModelSyntaxError("unexpected token ','")
         k, v = self.peek()
         if k == "op" and v in _STMT_OPS:
             self.next()
             rhs = self.parse_expr()
+            if v == "=" and self.peek() == ("op", ","):
+                items = [rhs]
+                while self.accept("op", ","):
+                    items.append(self.parse_expr())
+                rhs = ("tuple", items)
+            if v == "=" and lhs[0] == "call" and lhs[1][0] == "name" and not lhs[3] and all(a[0] == "name" for a in lhs[2]):
+                # `g(u, v) = body`: a local function (a build-time `=` like any other, rewrites.jl:717-733)
+                return ("stmt", "=", lhs[1], ("lambda", [a[1] for a in lhs[2]], rhs))
             return ("stmt", v, lhs, rhs)
         return ("expr", lhs)
 
@@ -218,6 +241,13 @@ class Parser:
     # ---- expressions (precedence climbing) ------------------------------------------------------
     def parse_expr(self):
         c = self.parse_or()
+        if self.peek() == ("op", "->"):
+            # `u -> body`, `(u, v) -> body`
+            params = [c] if c[0] == "name" else (c[1] if c[0] == "tuple" else None)
+            if params is None or not all(a[0] == "name" for a in params):
+                raise ModelSyntaxError("the parameters of an anonymous function must be names")
+            self.next()
+            return ("lambda", [a[1] for a in params], self.parse_expr())
         if self.peek() == ("op", "?"):
             # ternary `cond ? a : b` (vectorised to ifelse.(cond, a, b) when cond is per-particle, rewrites.jl:193-199)
             self.next()
@@ -281,6 +311,8 @@ class Parser:
             return self.parse_unary()
         if self.accept("op", "!"):
             return ("un", "!", self.parse_unary())
+        if self.accept("op", "√"):
+            return ("call", ("name", "sqrt"), [self.parse_unary()], {})
         return self.parse_pow()
 
     def parse_pow(self):
@@ -335,7 +367,9 @@ class Parser:
                 a = ("call", a, args, kwargs)
             elif (k, v) == ("op", "["):
                 self.next()
+                self.in_index += 1
                 args, _ = self.parse_args("]")
+                self.in_index -= 1
                 if len(args) != 1:
                     raise ModelSyntaxError("only a single index `x[e]` is supported (rewrites.jl:170-171)")
                 a = ("index", a, args[0])
@@ -369,6 +403,8 @@ class Parser:
                 return ("bin", "*", node, self.parse_atom_paren())
             return node
         if k == "name":
+            if v == "end" and self.in_index > 0:
+                return ("name", "__end__")   # `a[end]`: bound to the length of `a` when the index is evaluated
             return ("name", v)
         if (k, v) == ("op", "("):
             self.i -= 1
@@ -557,14 +593,18 @@ def _static_check(stmts, pv, fam, locals_):
             if op in (".+=", ".-=", ".*=", "./="):
                 raise ModelSyntaxError(f"Dotted compound assignment `{op}` is not supported; write `x .= x {op[1]} ...`")
             if op in ("=", "+=", "-=", "*=", "/="):
-                if lhs[0] != "name":
-                    raise ModelSyntaxError("a plain `=` target must be a local variable name")
-                if lhs[1] in pv or lhs[1] in fam:
-                    raise ModelSyntaxError(f"`{lhs[1]}` is a particle variable; use `.=` instead of `{op}`")
+                targets = [lhs]
+                if lhs[0] == "tuple" and op == "=":
+                    targets = lhs[1]                    # `(a, b) = ...` / `a, b = ...`: build-time destructuring
+                for t in targets:
+                    if t[0] != "name":
+                        raise ModelSyntaxError("a plain `=` target must be a local variable name")
+                    if t[1] in pv or t[1] in fam:
+                        raise ModelSyntaxError(f"`{t[1]}` is a particle variable; use `.=` instead of `{op}`")
                 if _contains_particle(rhs, pv):
                     raise ModelSyntaxError("the right-hand side of a plain `=` runs once at build time and cannot read a "
                                            "particle variable; use `.=` / `~`")
-                locals_ = set(locals_) | {lhs[1]}
+                locals_ = set(locals_) | {t[1] for t in targets}
                 continue
             if op == "<<":
                 targets = lhs[1] if lhs[0] == "tuple" else [lhs]
@@ -673,7 +713,28 @@ _BUILTINS = {
     "minimum": lambda x: float(np.min(x)), "maximum": lambda x: float(np.max(x)), "mean": lambda x: float(np.mean(x)),
     "Diagonal": lambda v: np.diag(np.asarray(v, dtype=float)), "diagm": lambda v: np.diag(np.asarray(v, dtype=float)),
     "eachindex": lambda x: _Range(1, len(x)), "first": lambda x: x[0], "last": lambda x: x[-1],
+    # scalar Base functions without a micro-op of their own: compositions (expr.py), Julia's results on particle values
+    "sign": expr.sign, "clamp": expr.clamp, "ceil": expr._int_first(expr.ceil), "trunc": expr._int_first(expr.trunc),
+    "round": expr._int_first(expr.round_even), "isnan": expr.isnan, "isinf": expr.isinf, "isfinite": expr.isfinite,
+    "log2": expr.log2, "log10": expr.log10, "exp2": expr.exp2, "exp10": expr.exp10, "sinh": expr.sinh, "cosh": expr.cosh,
+    "asin": expr.asin, "acos": expr.acos, "hypot": expr.hypot, "cbrt": expr.cbrt, "inv": expr.inv, "fld": expr.fld,
+    "cld": expr.cld, "div": expr.div, "rem": expr.rem, "mod": expr.mod, "one": lambda x: 1.0, "zero": lambda x: 0.0,
+    "iszero": lambda x: x.eq(0.0) if isinstance(x, Expr) else x == 0, "isone": lambda x: x.eq(1.0) if isinstance(x, Expr) else x == 1,
+    "prod": lambda x: float(np.prod(x)), "abs": lambda x: abs(x), "reverse": lambda x: x[::-1], "range": lambda a, b=None, length=None, step=None, stop=None: _jl_range(a, b, length, step, stop),
 }
+_BUILTINS.update({"floor": expr._int_first(expr.floor), "atan": expr.atan2, "log": expr.logb, "min": expr.nmin, "max": expr.nmax,
+                  "Float64": expr.to_float, "float": expr.to_float})
+
+
+def _jl_range(start, stop=None, length=None, step=None, stop_kw=None):
+    """`range(a, b; length=n)` / `range(a, b; step=s)` / `range(a; stop=b, length=n)` as a list of floats"""
+    if stop is None:
+        stop = stop_kw
+    if length is not None:
+        return [float(v) for v in np.linspace(float(start), float(stop), int(length))]
+    step = 1 if step is None else step
+    n = int(math.floor((stop - start) / step + 1e-12)) + 1
+    return [start + k * step for k in range(max(0, n))]
 
 
 class _Env:
@@ -726,8 +787,8 @@ def _binop(op, a, b):
         return a * b
     if op == "/": return a / b
     if op == "^": return a ** b
-    if op == "%": return a % b
-    if op == "÷": return a // b
+    if op == "%": return expr.rem(a, b)    # Julia: remainder with the sign of the dividend
+    if op == "÷": return expr.div(a, b)    # Julia: quotient truncated towards zero
     if op == "==": return a.eq(b) if isinstance(a, Expr) else (b.eq(a) if isinstance(b, Expr) else a == b)
     if op == "!=": return ~(a.eq(b)) if isinstance(a, Expr) else (~(b.eq(a)) if isinstance(b, Expr) else a != b)
     if op == "<": return a < b
@@ -772,8 +833,25 @@ def ev(ast, env):
     if tag == "curly":
         idx = ev(ast[2], env)
         return Col(dynname(ast[1], idx))
+    if tag == "lambda":
+        params, body, defenv = ast[1], ast[2], env
+
+        def fn(*a):
+            if len(a) != len(params):
+                raise TypeError(f"function takes {len(params)} argument(s) but {len(a)} were given")
+            return ev(body, defenv.child(dict(zip(params, a))))   # (the defining scope stays live, as a Julia closure's does)
+        return fn
     if tag == "index":
-        base, idx = ev(ast[1], env), ev(ast[2], env)
+        base = ev(ast[1], env)
+        ienv = env
+        if "__end__" in _names_in(ast[2])[0]:
+            if isinstance(base, Expr):
+                if not isinstance(base, Vec):
+                    raise _unsupported("`end` in the index of a particle variable (its length is not known when the model is built)")
+                ienv = env.child({"__end__": len(base.items)})
+            else:
+                ienv = env.child({"__end__": len(base)})
+        idx = ev(ast[2], ienv)
         if isinstance(base, Expr):
             return Index(base, int(idx) - 1)  # Julia is 1-based
         if isinstance(idx, _Range):
@@ -873,6 +951,13 @@ def _build(stmts, env, kernels, proposals):
             _, op, lhs, rhs = s
             if op in ("=", "+=", "-=", "*=", "/="):
                 v = ev(rhs, env)
+                if lhs[0] == "tuple":
+                    vals = tuple(v)
+                    if len(vals) < len(lhs[1]):
+                        raise ModelSyntaxError(f"cannot destructure {len(vals)} value(s) into {len(lhs[1])} names")
+                    for t, x in zip(lhs[1], vals):
+                        env.set_local(t[1], x)
+                    continue
                 if op != "=":
                     v = _binop(op[0], env.lookup(lhs[1]), v)
                 env.set_local(lhs[1], v)
