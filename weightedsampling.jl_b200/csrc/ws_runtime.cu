@@ -903,7 +903,6 @@ static int lower_statement(ws_ctx* c, F body) {
             c->cur_n = s_n;
             c->cur_u = s_u;
             c->cur_e = s_e;
-        c->cur_v = s_v;
             c->cur_v = s_v;
             return fail(c, WS_EINVAL, "%s", m.c_str());
         }
