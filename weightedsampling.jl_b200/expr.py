@@ -426,9 +426,11 @@ def to_float(x):
 def _int_first(fn):
     """`floor(Int, x)` / `round(Int, x)`: the type argument is dropped — every particle value is a Float64 plane"""
     def f(*a):
-        if len(a) == 2 and a[0] in (int, float):
+        if len(a) == 2 and isinstance(a[0], type):
             return fn(a[1])
-        return fn(*a)
+        if len(a) != 1:
+            raise _unsupported(f"{fn.__name__}() with {len(a)} arguments (digits / base keywords are outside the device-op set)")
+        return fn(a[0])
     return f
 
 
